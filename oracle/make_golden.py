@@ -1,0 +1,111 @@
+"""Generate tests/golden/*.npz from the REAL reference code (run on CPU under the shims).  TEST INFRASTRUCTURE ONLY.
+
+Run in the dev container (where /root/reference exists):   python -m oracle.make_golden
+The fixtures pin oracle/restate.py and the CUDA path on machines where the reference cannot be imported.
+Weights are not stored: they are regenerated from ``synth.make_state_dict(seed=1234, n_words=300, eos_bias=3.0)`` and
+guarded by the float64 checksums stored in ``weights_checksum``.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from conette_audio_captioning_b200 import synth  # noqa: E402
+from oracle import ref_loader  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+SD_KW = dict(seed=1234, n_words=300, eos_bias=3.0)
+CHECK_KEYS = (
+    "preprocessor.encoder.stages.2.4.pwconv1.weight",
+    "preprocessor.encoder.bn0.running_mean",
+    "model.decoder.layers.3.linear2.weight",
+    "model.decoder.classifier.bias",
+)
+
+
+def checksum(sd) -> np.ndarray:
+    return np.array([float(sd[k].double().sum()) for k in CHECK_KEYS] + [float(sd[k].double().abs().sum()) for k in CHECK_KEYS])
+
+
+def main() -> None:
+    torch.manual_seed(0)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    sd = synth.make_state_dict(**SD_KW)
+    model = ref_loader.build_reference_model(sd, synth.make_corpus(300))
+    beam_mod = ref_loader.ref_module("nn.decoding.beam")
+    os.makedirs(GOLDEN, exist_ok=True)
+
+    # ---- encoder: 2 clips, second one zero-padded (digital silence tail) -------------------------------------
+    n = 24000
+    wav = synth.make_audio(2, n, seed=11)[:, 0].contiguous()
+    wav[1, 15000:] = 0.0
+    x_lens = torch.tensor([[n], [15000]])
+    enc = model.preprocessor.encoder
+    with torch.no_grad():
+        lm = enc.logmel_extractor(enc.spectrogram_extractor(wav))[:, 0]
+        out = enc(wav, x_lens)
+    np.savez_compressed(
+        os.path.join(GOLDEN, "encoder.npz"),
+        wav=wav.numpy(), x_lens=x_lens[:, 0].numpy(), logmel=lm.numpy(),
+        frame_embs=out["frame_embs"].numpy(), frame_embs_lens=out["frame_embs_lens"].numpy(),
+        clip_probs=out["clipwise_output"].numpy(), weights_checksum=checksum(sd),
+    )
+
+    # ---- beam search on given projected frames --------------------------------------------------------------
+    cases = [(1, 3, 20, "content_words"), (2, 0, 20, "content_words"), (3, 3, 20, "content_words"),
+             (3, 3, 20, "none"), (3, 0, 5, "all"), (5, 3, 20, "content_words"), (5, 3, 30, "all")]
+    g = torch.Generator().manual_seed(77)
+    b, tp = 6, 9
+    mem = torch.relu(torch.randn(b, tp, 256, generator=g))
+    lens = torch.randint(1, tp + 1, (b,), generator=g)
+    bos_ids = sd["model.task_id_to_token_id"][torch.randint(0, 7, (b,), generator=g)]
+    mask = torch.arange(tp)[None, :] >= lens[:, None]
+    store = dict(mem=mem.numpy(), lens=lens.numpy(), bos_ids=bos_ids.numpy(),
+                 cases=np.array([f"{k}|{mn}|{mx}|{mode}" for k, mn, mx, mode in cases]), weights_checksum=checksum(sd))
+    dec = model.model.decoder
+    for ci, (k, mn, mx, mode) in enumerate(cases):
+        forbid = synth.make_forbid_rep_mask(synth.make_itos(300), mode)
+        preds, lprobs, mpreds, mlprobs = beam_mod.generate(
+            decoder=dec, pad_id=0, bos_id=bos_ids, eos_id=2, vocab_size=dec.vocab_size,
+            frame_embs=mem.transpose(1, 2).contiguous(), frame_embs_pad_mask=mask, beam_size=k,
+            min_pred_size=mn, max_pred_size=mx, forbid_rep_mask=forbid)
+        store[f"c{ci}_preds"] = preds.numpy()
+        store[f"c{ci}_lprobs"] = lprobs.numpy()
+        store[f"c{ci}_mult_preds"] = mpreds.numpy()
+        store[f"c{ci}_mult_lprobs"] = mlprobs.numpy()
+    # decoder logits for fixed token prefixes (full recompute of the reference decoder)
+    steps = 6
+    toks = torch.randint(4, 300, (b, steps), generator=g)
+    causal = torch.triu(torch.full((steps, steps), float("-inf")), diagonal=1)
+    with torch.no_grad():
+        full = dec(mem.permute(1, 0, 2).contiguous(), mask, toks.T.contiguous(), None, causal)
+    store["tf_tokens"] = toks.numpy()
+    store["tf_logits"] = full.permute(1, 0, 2).contiguous().numpy().astype(np.float32)  # (B, steps, V)
+    np.savez_compressed(os.path.join(GOLDEN, "decode.npz"), **store)
+
+    # ---- end to end through CoNeTTEModel -----------------------------------------------------------------------
+    wav3 = synth.make_audio(3, 32000, seed=5)
+    wav3[2, :, 20000:] = 0.0
+    x_shapes = torch.tensor([[32000], [32000], [20000]])
+    tasks = ["clotho", "audiocaps", "wavcaps_audioset_sl"]
+    with torch.no_grad():
+        out = model(wav3, sr=32000, x_shapes=x_shapes, task=tasks)
+    np.savez_compressed(
+        os.path.join(GOLDEN, "e2e.npz"),
+        wav=wav3.numpy(), x_shapes=x_shapes.numpy(), tasks=np.array(tasks), cands=np.array(out["cands"]),
+        mult_cands=np.array(out["mult_cands"]), preds=out["preds"].numpy(), lprobs=out["lprobs"].numpy(),
+        mult_preds=out["mult_preds"].numpy(), mult_lprobs=out["mult_lprobs"].numpy(),
+        tags_probs=out["tags_probs"].numpy(), weights_checksum=checksum(sd),
+    )
+    for f in sorted(os.listdir(GOLDEN)):
+        print(f, os.path.getsize(os.path.join(GOLDEN, f)))
+
+
+if __name__ == "__main__":
+    main()
