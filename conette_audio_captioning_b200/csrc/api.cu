@@ -1,0 +1,888 @@
+// C-ABI of libconette_b200.so (declared in include/conette_b200.h): handle, weight packing, workspace and the
+// orchestration of the per-stage kernels.  No torch types anywhere; PyTorch only owns the caller's buffers.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/conette_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace cnb {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+static std::atomic<int64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+constexpr int kDims[4] = {96, 192, 384, 768};
+constexpr int kDepths[4] = {3, 3, 9, 3};
+constexpr int kStageW[4] = {56, 28, 14, 7};
+constexpr int kMels = 224, kBins = 513, kNfft = 1024, kHop = 320;
+constexpr int kD = 256, kFF = 2048, kLayers = 6, kTags = 527;
+constexpr int kDefaultChunk = 8;
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+};
+
+// simple bump arena for packed weights (256-byte aligned)
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, used = 0;
+  template <typename T> T* take(size_t n) {
+    used = (used + 255) & ~size_t(255);
+    T* p = reinterpret_cast<T*>(base + used);
+    used += n * sizeof(T);
+    return p;
+  }
+};
+
+struct BlockW {
+  float *dw_w_t, *dw_b, *ln_g, *ln_b, *b1, *b2, *scale, *w1, *w2;
+  __nv_bfloat16 *w1_bf, *w2_bf;
+};
+struct DownW {
+  float *ln_g, *ln_b, *bias, *w;
+  __nv_bfloat16* w_bf;
+};
+struct LayerW {
+  float *sa_in_w, *sa_in_b, *sa_out_w, *sa_out_b, *ca_q_w, *ca_q_b, *ca_out_w, *ca_out_b;
+  float *l1_w, *l1_b, *l2_w, *l2_b, *n1_g, *n1_b, *n2_g, *n2_b, *n3_g, *n3_b;
+};
+
+struct Buffer {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace cnb
+
+using namespace cnb;
+
+struct cnb_handle {
+  cnb_config cfg;
+  std::map<std::string, HostTensor> staged;
+  bool finalized = false;
+  Arena arena;
+  // encoder
+  FrontendParams fe;
+  float *stem_w_t, *stem_b, *stem_ln_g, *stem_ln_b;
+  BlockW blocks[18];
+  DownW down[3];
+  float *head_ln_g, *head_ln_b, *head_w, *head_b;
+  // projection + decoder
+  float *proj_w, *proj_b, *emb, *pe, *ca_kv_w, *ca_kv_b, *cls_w, *cls_b;
+  LayerW layers[6];
+  // workspace (grown on demand)
+  std::map<std::string, Buffer> ws;
+  size_t ws_bytes = 0;
+  int* zero_flag = nullptr;  // device int[4] that stays 0: "done" flag for non-beam callers
+};
+
+namespace cnb {
+
+static int ws_get(cnb_handle* h, const char* name, size_t bytes, void** out) {
+  Buffer& b = h->ws[name];
+  if (b.bytes < bytes) {
+    if (b.ptr) {
+      CNB_CUDA_OK(cudaDeviceSynchronize());
+      CNB_CUDA_OK(cudaFree(b.ptr));
+      h->ws_bytes -= b.bytes;
+      b.ptr = nullptr;
+      b.bytes = 0;
+    }
+    const size_t want = (bytes + 255) & ~size_t(255);
+    CNB_CUDA_OK(cudaMalloc(&b.ptr, want));
+    CNB_CUDA_OK(cudaMemset(b.ptr, 0, want));
+    b.bytes = want;
+    h->ws_bytes += want;
+  }
+  *out = b.ptr;
+  return 0;
+}
+#define WS(h, name, type, count, var)                                                     \
+  type* var = nullptr;                                                                    \
+  do {                                                                                    \
+    void* _p = nullptr;                                                                   \
+    if (int _rc = ws_get(h, name, sizeof(type) * (size_t)(count), &_p)) return _rc;       \
+    var = reinterpret_cast<type*>(_p);                                                    \
+  } while (0)
+
+struct Geometry {
+  int t, h[4], tp;
+};
+static Geometry geometry(int64_t n) {
+  Geometry g;
+  g.t = (int)(n / kHop) + 1;
+  g.h[0] = (g.t + 8 - 4) / 4 + 1;  // Conv2d k=4 s=4 pad=(4,0)  (reference convnext.py:405-408)
+  g.h[1] = g.h[0] / 2;
+  g.h[2] = g.h[1] / 2;
+  g.h[3] = g.h[2] / 2;
+  g.tp = g.h[3];
+  return g;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// weight staging helpers
+// ---------------------------------------------------------------------------------------------------------------------
+static const HostTensor* find(cnb_handle* h, const std::string& name, std::initializer_list<int64_t> shape) {
+  auto it = h->staged.find(name);
+  if (it == h->staged.end()) {
+    set_error("missing weight: " + name);
+    return nullptr;
+  }
+  if (it->second.shape != std::vector<int64_t>(shape)) {
+    std::string s = "[";
+    for (auto d : it->second.shape) s += std::to_string(d) + ",";
+    set_error("unexpected shape for " + name + ": " + s + "]");
+    return nullptr;
+  }
+  return &it->second;
+}
+
+template <typename T> static int upload(T* dst, const std::vector<T>& src) {
+  CNB_CUDA_OK(cudaMemcpy(dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+static int put_f32(cnb_handle* h, const std::vector<float>& v, float** out) {
+  *out = h->arena.take<float>(v.size());
+  return upload(*out, v);
+}
+static int put_bf16(cnb_handle* h, const std::vector<float>& v, __nv_bfloat16** out) {
+  std::vector<__nv_bfloat16> t(v.size());
+  for (size_t i = 0; i < v.size(); ++i) t[i] = __float2bfloat16_rn(v[i]);
+  *out = h->arena.take<__nv_bfloat16>(v.size());
+  CNB_CUDA_OK(cudaMemcpy(*out, t.data(), t.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  return 0;
+}
+#define GET(var, name, ...)                                  \
+  const HostTensor* var = find(h, name, {__VA_ARGS__});      \
+  if (!var) return -4
+#define PUT(dst, vec) \
+  if (int _rc = put_f32(h, vec, &(dst))) return _rc
+#define PUT_BF(dst, vec) \
+  if (int _rc = put_bf16(h, vec, &(dst))) return _rc
+
+static int finalize(cnb_handle* h) {
+  const std::string E = "preprocessor.encoder.", M = "model.", D = "model.decoder.";
+  const int V = h->cfg.vocab_size;
+  CNB_CUDA_OK(cudaSetDevice(h->cfg.device));
+  if (int rc = gemm_tc_init()) return rc;
+
+  size_t total = 0;
+  for (auto& kv : h->staged) total += kv.second.data.size();
+  h->arena.cap = total * 6 + (64u << 20);  // f32 + bf16 copies + slack
+  CNB_CUDA_OK(cudaMalloc(&h->arena.base, h->arena.cap));
+  CNB_CUDA_OK(cudaMemset(h->arena.base, 0, h->arena.cap));
+
+  // ---- front-end: analytic twiddles; the checkpoint's DFT basis must be the Hann-windowed DFT
+  {
+    GET(cr, E + "spectrogram_extractor.stft.conv_real.weight", kBins, 1, kNfft);
+    GET(ci, E + "spectrogram_extractor.stft.conv_imag.weight", kBins, 1, kNfft);
+    double max_err = 0;
+    for (int k : {0, 1, 7, 100, 255, 256, 511, 512})
+      for (int n = 0; n < kNfft; n += 3) {
+        const double w = 0.5 - 0.5 * std::cos(2.0 * M_PI * n / kNfft);
+        const double ang = 2.0 * M_PI * (double)((int64_t)k * n % kNfft) / kNfft;
+        max_err = std::max(max_err, std::fabs(cr->data[(size_t)k * kNfft + n] - w * std::cos(ang)));
+        max_err = std::max(max_err, std::fabs(ci->data[(size_t)k * kNfft + n] + w * std::sin(ang)));
+      }
+    if (max_err > 1e-5) {
+      set_error("spectrogram_extractor.stft.conv_{real,imag}.weight is not the periodic-Hann DFT basis (max err " +
+                std::to_string(max_err) + "); the FFT front-end cannot represent it");
+      return -4;
+    }
+    std::vector<float> tw(2 * kNfft);
+    for (int j = 0; j < kNfft; ++j) {
+      tw[2 * j] = (float)std::cos(2.0 * M_PI * j / kNfft);
+      tw[2 * j + 1] = (float)(-std::sin(2.0 * M_PI * j / kNfft));
+    }
+    float* twd;
+    PUT(twd, tw);
+    h->fe.twiddle = reinterpret_cast<const float2*>(twd);
+    // sparse mel: per filter the contiguous range of non-zero FFT bins (melW is data, never regenerated)
+    GET(mel, E + "logmel_extractor.melW", kBins, kMels);
+    std::vector<int> lo(kMels), cnt(kMels), off(kMels);
+    std::vector<float> wts;
+    for (int m = 0; m < kMels; ++m) {
+      int first = -1, last = -1;
+      for (int k = 0; k < kBins; ++k)
+        if (mel->data[(size_t)k * kMels + m] != 0.f) {
+          if (first < 0) first = k;
+          last = k;
+        }
+      lo[m] = first < 0 ? 0 : first;
+      cnt[m] = first < 0 ? 0 : last - first + 1;
+      off[m] = (int)wts.size();
+      for (int k = 0; k < cnt[m]; ++k) wts.push_back(mel->data[(size_t)(lo[m] + k) * kMels + m]);
+    }
+    if (wts.empty()) wts.push_back(0.f);
+    int *dlo = h->arena.take<int>(kMels), *dcnt = h->arena.take<int>(kMels), *doff = h->arena.take<int>(kMels);
+    if (int rc = upload(dlo, lo)) return rc;
+    if (int rc = upload(dcnt, cnt)) return rc;
+    if (int rc = upload(doff, off)) return rc;
+    float* dw;
+    PUT(dw, wts);
+    h->fe.mel_lo = dlo; h->fe.mel_cnt = dcnt; h->fe.mel_off = doff; h->fe.mel_w = dw;
+    GET(g, E + "bn0.weight", kMels);
+    GET(b, E + "bn0.bias", kMels);
+    GET(mu, E + "bn0.running_mean", kMels);
+    GET(var, E + "bn0.running_var", kMels);
+    std::vector<float> sc(kMels), sh(kMels), ones(kMels, 1.f), zeros(kMels, 0.f);
+    for (int m = 0; m < kMels; ++m) {
+      sc[m] = g->data[m] / std::sqrt(var->data[m] + 1e-5f);
+      sh[m] = b->data[m] - mu->data[m] * sc[m];
+    }
+    float *dsc, *dsh, *dones, *dzeros;
+    PUT(dsc, sc); PUT(dsh, sh); PUT(dones, ones); PUT(dzeros, zeros);
+    h->fe.bn_scale = dsc; h->fe.bn_shift = dsh; h->fe.ones = dones; h->fe.zeros = dzeros;
+  }
+  // ---- stem
+  {
+    GET(w, E + "downsample_layers.0.0.weight", 96, 1, 4, 4);
+    GET(b, E + "downsample_layers.0.0.bias", 96);
+    GET(g, E + "downsample_layers.0.1.weight", 96);
+    GET(be, E + "downsample_layers.0.1.bias", 96);
+    std::vector<float> wt(16 * 96);
+    for (int c = 0; c < 96; ++c)
+      for (int i = 0; i < 16; ++i) wt[i * 96 + c] = w->data[c * 16 + i];
+    PUT(h->stem_w_t, wt); PUT(h->stem_b, b->data); PUT(h->stem_ln_g, g->data); PUT(h->stem_ln_b, be->data);
+  }
+  // ---- downsample layers 1..3: LN(cf) + Conv2d(k=2,s=2); weight reordered to (Cout, kh, kw, Cin)
+  for (int i = 1; i < 4; ++i) {
+    const int cin = kDims[i - 1], cout = kDims[i];
+    const std::string p = E + "downsample_layers." + std::to_string(i) + ".";
+    GET(g, p + "0.weight", cin);
+    GET(be, p + "0.bias", cin);
+    GET(w, p + "1.weight", cout, cin, 2, 2);
+    GET(b, p + "1.bias", cout);
+    std::vector<float> wr((size_t)cout * 4 * cin);
+    for (int o = 0; o < cout; ++o)
+      for (int c = 0; c < cin; ++c)
+        for (int kh = 0; kh < 2; ++kh)
+          for (int kw = 0; kw < 2; ++kw)
+            wr[((size_t)o * 4 + kh * 2 + kw) * cin + c] = w->data[(((size_t)o * cin + c) * 2 + kh) * 2 + kw];
+    DownW& d = h->down[i - 1];
+    PUT(d.ln_g, g->data); PUT(d.ln_b, be->data); PUT(d.bias, b->data); PUT(d.w, wr); PUT_BF(d.w_bf, wr);
+  }
+  // ---- blocks
+  {
+    int bi = 0;
+    for (int s = 0; s < 4; ++s)
+      for (int j = 0; j < kDepths[s]; ++j, ++bi) {
+        const int c = kDims[s];
+        const std::string p = E + "stages." + std::to_string(s) + "." + std::to_string(j) + ".";
+        GET(sc, p + "scale_layer", c);
+        GET(dw, p + "dwconv.weight", c, 1, 7, 7);
+        GET(db, p + "dwconv.bias", c);
+        GET(g, p + "norm.weight", c);
+        GET(be, p + "norm.bias", c);
+        GET(w1, p + "pwconv1.weight", 4 * c, c);
+        GET(b1, p + "pwconv1.bias", 4 * c);
+        GET(w2, p + "pwconv2.weight", c, 4 * c);
+        GET(b2, p + "pwconv2.bias", c);
+        std::vector<float> wt((size_t)49 * c);
+        for (int ch = 0; ch < c; ++ch)
+          for (int t = 0; t < 49; ++t) wt[(size_t)t * c + ch] = dw->data[(size_t)ch * 49 + t];
+        BlockW& b = h->blocks[bi];
+        PUT(b.dw_w_t, wt); PUT(b.dw_b, db->data); PUT(b.ln_g, g->data); PUT(b.ln_b, be->data);
+        PUT(b.b1, b1->data); PUT(b.b2, b2->data); PUT(b.scale, sc->data);
+        PUT(b.w1, w1->data); PUT(b.w2, w2->data); PUT_BF(b.w1_bf, w1->data); PUT_BF(b.w2_bf, w2->data);
+      }
+  }
+  // ---- clip head
+  {
+    GET(g, E + "norm.weight", 768);
+    GET(be, E + "norm.bias", 768);
+    GET(w, E + "head_audioset.weight", kTags, 768);
+    GET(b, E + "head_audioset.bias", kTags);
+    PUT(h->head_ln_g, g->data); PUT(h->head_ln_b, be->data); PUT(h->head_w, w->data); PUT(h->head_b, b->data);
+  }
+  // ---- projection + decoder
+  {
+    GET(pw, M + "projection.2.weight", kD, 768);
+    GET(pb, M + "projection.2.bias", kD);
+    GET(emb, D + "emb_layer.weight", V, kD);
+    GET(cw, D + "classifier.weight", V, kD);
+    GET(cb, D + "classifier.bias", V);
+    PUT(h->proj_w, pw->data); PUT(h->proj_b, pb->data); PUT(h->emb, emb->data); PUT(h->cls_w, cw->data);
+    PUT(h->cls_b, cb->data);
+    auto it = h->staged.find(D + "pos_encoding.pos_embedding");
+    if (it == h->staged.end() || it->second.shape.size() != 3 || it->second.shape[2] != kD) {
+      set_error("missing or malformed weight: " + D + "pos_encoding.pos_embedding");
+      return -4;
+    }
+    PUT(h->pe, it->second.data);
+    std::vector<float> kvw((size_t)kLayers * 2 * kD * kD), kvb((size_t)kLayers * 2 * kD);
+    for (int l = 0; l < kLayers; ++l) {
+      const std::string p = D + "layers." + std::to_string(l) + ".";
+      LayerW& L = h->layers[l];
+      GET(saw, p + "self_attn.in_proj_weight", 3 * kD, kD);
+      GET(sab, p + "self_attn.in_proj_bias", 3 * kD);
+      GET(sow, p + "self_attn.out_proj.weight", kD, kD);
+      GET(sob, p + "self_attn.out_proj.bias", kD);
+      GET(caw, p + "multihead_attn.in_proj_weight", 3 * kD, kD);
+      GET(cab, p + "multihead_attn.in_proj_bias", 3 * kD);
+      GET(cow, p + "multihead_attn.out_proj.weight", kD, kD);
+      GET(cob, p + "multihead_attn.out_proj.bias", kD);
+      GET(l1w, p + "linear1.weight", kFF, kD);
+      GET(l1b, p + "linear1.bias", kFF);
+      GET(l2w, p + "linear2.weight", kD, kFF);
+      GET(l2b, p + "linear2.bias", kD);
+      PUT(L.sa_in_w, saw->data); PUT(L.sa_in_b, sab->data); PUT(L.sa_out_w, sow->data); PUT(L.sa_out_b, sob->data);
+      std::vector<float> qw(caw->data.begin(), caw->data.begin() + (size_t)kD * kD);
+      std::vector<float> qb(cab->data.begin(), cab->data.begin() + kD);
+      PUT(L.ca_q_w, qw); PUT(L.ca_q_b, qb); PUT(L.ca_out_w, cow->data); PUT(L.ca_out_b, cob->data);
+      std::copy(caw->data.begin() + (size_t)kD * kD, caw->data.end(), kvw.begin() + (size_t)l * 2 * kD * kD);
+      std::copy(cab->data.begin() + kD, cab->data.end(), kvb.begin() + (size_t)l * 2 * kD);
+      PUT(L.l1_w, l1w->data); PUT(L.l1_b, l1b->data); PUT(L.l2_w, l2w->data); PUT(L.l2_b, l2b->data);
+      float** gs[3] = {&L.n1_g, &L.n2_g, &L.n3_g};
+      float** bs[3] = {&L.n1_b, &L.n2_b, &L.n3_b};
+      for (int n = 0; n < 3; ++n) {
+        GET(g, p + "norm" + std::to_string(n + 1) + ".weight", kD);
+        GET(b, p + "norm" + std::to_string(n + 1) + ".bias", kD);
+        PUT(*gs[n], g->data); PUT(*bs[n], b->data);
+      }
+    }
+    PUT(h->ca_kv_w, kvw); PUT(h->ca_kv_b, kvb);
+  }
+  CNB_CUDA_OK(cudaMalloc(&h->zero_flag, 4 * sizeof(int)));
+  CNB_CUDA_OK(cudaMemset(h->zero_flag, 0, 4 * sizeof(int)));
+  h->staged.clear();
+  h->finalized = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// encoder orchestration
+// ---------------------------------------------------------------------------------------------------------------------
+struct Tap {
+  int kind = -1, stage = 0, block = 0;
+  float* out = nullptr;
+  int64_t cap = 0;
+  bool hit = false;
+};
+
+static int copy_tap(Tap* tap, const void* src, int64_t elems, bool src_is_bf16, cudaStream_t st);
+
+template <typename ActT>
+static int mlp_gemm(cnb_handle* h, const ActT* a, const float* w32, const __nv_bfloat16* wbf, int m, int n, int k, Epilogue epi,
+                    const EpiParams& ep, void* out, bool out_act, int64_t ldo, cudaStream_t st);
+
+template <>
+int mlp_gemm<float>(cnb_handle* h, const float* a, const float* w32, const __nv_bfloat16*, int m, int n, int k, Epilogue epi,
+                    const EpiParams& ep, void* out, bool, int64_t ldo, cudaStream_t st) {
+  return launch_gemm_f32<float>(a, k, w32, m, n, k, epi, ep, reinterpret_cast<float*>(out), ldo, st);
+}
+template <>
+int mlp_gemm<__nv_bfloat16>(cnb_handle* h, const __nv_bfloat16* a, const float*, const __nv_bfloat16* wbf, int m, int n, int k,
+                            Epilogue epi, const EpiParams& ep, void* out, bool out_act, int64_t ldo, cudaStream_t st) {
+  if (out_act)
+    return launch_gemm_tc<__nv_bfloat16>(a, wbf, m, n, k, epi, ep, reinterpret_cast<__nv_bfloat16*>(out), ldo, st);
+  return launch_gemm_tc<float>(a, wbf, m, n, k, epi, ep, reinterpret_cast<float*>(out), ldo, st);
+}
+
+// encode `nb` clips (nb <= chunk) starting at wav; writes frame_embs (nb, T', 768) and optionally clip probs
+template <typename ActT>
+static int encode_chunk(cnb_handle* h, const float* wav, int nb, int64_t n, float* frame_embs, float* clip_probs, Tap* tap,
+                        cudaStream_t st) {
+  const Geometry g = geometry(n);
+  const int64_t p0 = (int64_t)g.h[0] * kStageW[0];
+  WS(h, "logmel", float, (size_t)nb * g.t * kMels, logmel);
+  WS(h, "xa", float, (size_t)nb * p0 * kDims[0], xa);
+  WS(h, "xb", float, (size_t)nb * p0 * kDims[0] / 2, xb);
+  WS(h, "y", ActT, (size_t)nb * p0 * kDims[0], y);
+  WS(h, "hid", ActT, (size_t)nb * p0 * kDims[0] * 4, hid);
+
+  if (int rc = launch_frontend(wav, nb, n, h->fe, true, logmel, st)) return rc;
+  if (tap && tap->kind == CNB_TAP_LOGMEL_BN) return copy_tap(tap, logmel, (int64_t)nb * g.t * kMels, false, st);
+  if (int rc = launch_stem(logmel, nb, g.t, g.h[0], h->stem_w_t, h->stem_b, h->stem_ln_g, h->stem_ln_b, xa, st)) return rc;
+  if (tap && tap->kind == CNB_TAP_STEM) return copy_tap(tap, xa, (int64_t)nb * p0 * kDims[0], false, st);
+
+  float* x = xa;
+  float* x_other = xb;
+  int bi = 0;
+  for (int s = 0; s < 4; ++s) {
+    const int c = kDims[s], hh = g.h[s], ww = kStageW[s];
+    if (s > 0) {
+      // downsample: LN(channels_first) + 2x2/s2 conv as pack + GEMM (K = 4*Cin)
+      const int cin = kDims[s - 1], hin = g.h[s - 1], win = kStageW[s - 1];
+      const DownW& d = h->down[s - 1];
+      if (int rc = launch_ln_pack2x2<ActT>(x, nb, hin, win, cin, d.ln_g, d.ln_b, y, st)) return rc;
+      const int m = nb * hh * ww;
+      EpiParams ep;
+      ep.bias = d.bias;
+      if (int rc = mlp_gemm<ActT>(h, y, d.w, d.w_bf, m, c, 4 * cin, EPI_BIAS, ep, x_other, false, c, st)) return rc;
+      std::swap(x, x_other);
+      if (tap && tap->kind == CNB_TAP_DOWN && tap->stage == s) return copy_tap(tap, x, (int64_t)m * c, false, st);
+    }
+    const int m = nb * hh * ww;
+    for (int j = 0; j < kDepths[s]; ++j, ++bi) {
+      const BlockW& b = h->blocks[bi];
+      if (int rc = launch_dwconv_ln<ActT>(x, nb, hh, ww, c, b.dw_w_t, b.dw_b, b.ln_g, b.ln_b, y, st)) return rc;
+      if (tap && tap->kind == CNB_TAP_DWLN && tap->stage == s && tap->block == j)
+        return copy_tap(tap, y, (int64_t)m * c, sizeof(ActT) == 2, st);
+      EpiParams e1;
+      e1.bias = b.b1;
+      if (int rc = mlp_gemm<ActT>(h, y, b.w1, b.w1_bf, m, 4 * c, c, EPI_BIAS_GELU, e1, hid, true, 4 * c, st)) return rc;
+      EpiParams e2;
+      e2.bias = b.b2;
+      e2.scale = b.scale;
+      e2.resid = x;
+      if (int rc = mlp_gemm<ActT>(h, hid, b.w2, b.w2_bf, m, c, 4 * c, EPI_SCALE_RESID, e2, x, false, c, st)) return rc;
+      if (tap && tap->kind == CNB_TAP_BLOCK && tap->stage == s && tap->block == j)
+        return copy_tap(tap, x, (int64_t)m * c, false, st);
+    }
+  }
+  if (int rc = launch_freq_mean(x, nb, g.tp, kStageW[3], 768, frame_embs, st)) return rc;
+  if (clip_probs)
+    if (int rc = launch_clip_head(frame_embs, nb, g.tp, h->head_ln_g, h->head_ln_b, h->head_w, h->head_b, kTags, clip_probs,
+                                  st))
+      return rc;
+  return 0;
+}
+
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(in[i]);
+}
+
+static int copy_tap(Tap* tap, const void* src, int64_t elems, bool src_is_bf16, cudaStream_t st) {
+  if (elems > tap->cap) {
+    set_error("encoder tap needs " + std::to_string(elems) + " elements but the output holds " + std::to_string(tap->cap));
+    return -1;
+  }
+  if (src_is_bf16) {
+    bf16_to_f32_kernel<<<(unsigned)ceil_div(elems, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), tap->out,
+                                                                        elems);
+    CNB_LAUNCH_OK();
+  } else {
+    CNB_CUDA_OK(cudaMemcpyAsync(tap->out, src, elems * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  tap->hit = true;
+  return 0;
+}
+
+static int chunk_size(const cnb_handle* h) { return h->cfg.enc_chunk > 0 ? h->cfg.enc_chunk : kDefaultChunk; }
+
+static int encode(cnb_handle* h, const float* wav, int batch, int64_t n, float* frame_embs, float* clip_probs,
+                  cudaStream_t st) {
+  const Geometry g = geometry(n);
+  const int chunk = chunk_size(h);
+  for (int b0 = 0; b0 < batch; b0 += chunk) {
+    const int nb = std::min(chunk, batch - b0);
+    float* fe = frame_embs + (int64_t)b0 * g.tp * 768;
+    float* cp = clip_probs ? clip_probs + (int64_t)b0 * kTags : nullptr;
+    int rc = (h->cfg.precision == CNB_PRECISION_PARITY)
+                 ? encode_chunk<float>(h, wav + (int64_t)b0 * n, nb, n, fe, cp, nullptr, st)
+                 : encode_chunk<__nv_bfloat16>(h, wav + (int64_t)b0 * n, nb, n, fe, cp, nullptr, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// decoder orchestration
+// ---------------------------------------------------------------------------------------------------------------------
+struct DecWs {
+  float *mem, *ckv, *x, *qkv, *attn, *tmp, *ff, *logits, *kc, *vc;
+};
+
+static int dec_prepare(cnb_handle* h, const float* frame_embs, int batch, int tp, int rows, int max_len, DecWs* w,
+                       cudaStream_t st) {
+  const int V = h->cfg.vocab_size;
+  WS(h, "mem", float, (size_t)batch * tp * kD, mem);
+  WS(h, "ckv", float, (size_t)batch * tp * kLayers * 2 * kD, ckv);
+  WS(h, "dx", float, (size_t)rows * kD, x);
+  WS(h, "dqkv", float, (size_t)rows * 3 * kD, qkv);
+  WS(h, "dattn", float, (size_t)rows * kD, attn);
+  WS(h, "dtmp", float, (size_t)rows * kD, tmp);
+  WS(h, "dff", float, (size_t)rows * kFF, ff);
+  WS(h, "dlogits", float, (size_t)rows * V, logits);
+  WS(h, "kc", float, (size_t)kLayers * rows * max_len * kD, kc);
+  WS(h, "vc", float, (size_t)kLayers * rows * max_len * kD, vc);
+  *w = DecWs{mem, ckv, x, qkv, attn, tmp, ff, logits, kc, vc};
+  // projection: Linear(768,256) + ReLU (reference common.py:71-78); cross-attention K|V of all 6 layers in one GEMM
+  EpiParams ep;
+  ep.bias = h->proj_b;
+  if (int rc = launch_gemm_f32<float>(frame_embs, 768, h->proj_w, batch * tp, kD, 768, EPI_BIAS_RELU, ep, mem, kD, st))
+    return rc;
+  EpiParams ek;
+  ek.bias = h->ca_kv_b;
+  return launch_gemm_f32<float>(mem, kD, h->ca_kv_w, batch * tp, kLayers * 2 * kD, kD, EPI_BIAS, ek, ckv, kLayers * 2 * kD, st);
+}
+
+// one decoder step for position `pos`: tokens[r][pos] -> logits (R, V)
+static int dec_step(cnb_handle* h, const DecWs& w, const int* tokens, const int* src_row, const int* lens, int pos,
+                    const DecoderDims& dd, const int* done, cudaStream_t st) {
+  const int R = dd.rows;
+  const int64_t cache_l = (int64_t)R * dd.max_len * kD;
+  const int64_t kv_stride = kLayers * 2 * kD;
+  if (int rc = launch_embed(tokens, pos, h->emb, h->pe, w.x, dd, done, st)) return rc;
+  for (int l = 0; l < kLayers; ++l) {
+    const LayerW& L = h->layers[l];
+    EpiParams e;
+    e.bias = L.sa_in_b;
+    if (int rc = launch_gemm_f32<float>(w.x, kD, L.sa_in_w, R, 3 * kD, kD, EPI_BIAS, e, w.qkv, 3 * kD, st)) return rc;
+    if (int rc = launch_self_attn(w.qkv, w.kc + l * cache_l, w.vc + l * cache_l, src_row, pos, w.attn, dd, done, st)) return rc;
+    e.bias = L.sa_out_b;
+    if (int rc = launch_gemm_f32<float>(w.attn, kD, L.sa_out_w, R, kD, kD, EPI_BIAS, e, w.tmp, kD, st)) return rc;
+    if (int rc = launch_add_ln(w.x, w.tmp, L.n1_g, L.n1_b, R, done, st)) return rc;
+    e.bias = L.ca_q_b;
+    if (int rc = launch_gemm_f32<float>(w.x, kD, L.ca_q_w, R, kD, kD, EPI_BIAS, e, w.tmp, kD, st)) return rc;
+    if (int rc = launch_cross_attn(w.tmp, w.ckv + (int64_t)l * 2 * kD, w.ckv + (int64_t)l * 2 * kD + kD, kv_stride, lens,
+                                   w.attn, dd, done, st))
+      return rc;
+    e.bias = L.ca_out_b;
+    if (int rc = launch_gemm_f32<float>(w.attn, kD, L.ca_out_w, R, kD, kD, EPI_BIAS, e, w.tmp, kD, st)) return rc;
+    if (int rc = launch_add_ln(w.x, w.tmp, L.n2_g, L.n2_b, R, done, st)) return rc;
+    e.bias = L.l1_b;
+    if (int rc = launch_gemm_f32<float>(w.x, kD, L.l1_w, R, kFF, kD, EPI_BIAS_GELU, e, w.ff, kFF, st)) return rc;
+    e.bias = L.l2_b;
+    if (int rc = launch_gemm_f32<float>(w.ff, kFF, L.l2_w, R, kD, kFF, EPI_BIAS, e, w.tmp, kD, st)) return rc;
+    if (int rc = launch_add_ln(w.x, w.tmp, L.n3_g, L.n3_b, R, done, st)) return rc;
+  }
+  EpiParams e;
+  e.bias = h->cls_b;
+  return launch_gemm_f32<float>(w.x, kD, h->cls_w, R, dd.vocab, kD, EPI_BIAS, e, w.logits, dd.vocab, st);
+}
+
+__global__ void gather_mult_kernel(BeamState st, int64_t* __restrict__ mult_preds, float* __restrict__ mult_lp,
+                                   const int* __restrict__ best_len, int* __restrict__ info, int rows, int max_len,
+                                   int batch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows * max_len) mult_preds[i] = st.out_preds[i];
+  if (i < rows) mult_lp[i] = st.out_lp[i];
+  if (i < batch) info[2 + i] = best_len[i];
+  if (i == 0) {
+    info[0] = st.done[1];
+    info[1] = st.done[0];
+  }
+}
+
+__global__ void tokens_i64_to_i32_kernel(const int64_t* __restrict__ in, int* __restrict__ out, int rows, int steps,
+                                         int out_stride) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows * steps) out[(i / steps) * out_stride + (i % steps)] = (int)in[i];
+}
+__global__ void iota_rows_kernel(int* __restrict__ src_row, int rows, int max_len) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows * max_len) src_row[i] = i / max_len;
+}
+__global__ void copy_logits_kernel(const float* __restrict__ logits, float* __restrict__ out, int rows, int vocab, int step,
+                                   int steps) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (int64_t)rows * vocab) {
+    const int r = (int)(i / vocab), v = (int)(i % vocab);
+    out[((int64_t)r * steps + step) * vocab + v] = logits[i];
+  }
+}
+
+static int decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, const int64_t* bos_ids, const uint8_t* forbid,
+                  int batch, int tp, int beam, int min_len, int max_len, int64_t* preds, float* lprobs, int64_t* mult_preds,
+                  float* mult_lprobs, int32_t* info, cudaStream_t st) {
+  const int rows = batch * beam;
+  DecoderDims dd{rows, beam, tp, max_len, h->cfg.vocab_size};
+  DecWs w;
+  if (int rc = dec_prepare(h, frame_embs, batch, tp, rows, max_len, &w, st)) return rc;
+  BeamState bs;
+  WS(h, "tok0", int, (size_t)rows * (max_len + 1), tok0);
+  WS(h, "tok1", int, (size_t)rows * (max_len + 1), tok1);
+  WS(h, "src0", int, (size_t)rows * max_len, src0);
+  WS(h, "src1", int, (size_t)rows * max_len, src1);
+  WS(h, "sum_lp", float, rows, sum_lp);
+  WS(h, "live", uint8_t, rows, live);
+  WS(h, "out_preds", int64_t, (size_t)rows * max_len, out_preds);
+  WS(h, "out_lp", float, rows, out_lp);
+  WS(h, "done", int, 4, done);
+  WS(h, "best_len", int, batch, best_len);
+  bs.tokens[0] = tok0; bs.tokens[1] = tok1; bs.src_row[0] = src0; bs.src_row[1] = src1;
+  bs.sum_lp = sum_lp; bs.live = live; bs.out_preds = out_preds; bs.out_lp = out_lp; bs.done = done;
+  if (int rc = launch_beam_init(bos_ids, bs, dd, st)) return rc;
+  int cur = 0;
+  for (int i = 0; i < max_len; ++i) {
+    if (int rc = dec_step(h, w, bs.tokens[cur], bs.src_row[cur], lens, i, dd, done, st)) return rc;
+    if (int rc = launch_beam_step(w.logits, forbid, bs, i, cur, min_len, dd, st)) return rc;
+    cur ^= 1;
+  }
+  if (int rc = launch_beam_finalize(bs, preds, lprobs, best_len, dd, st)) return rc;
+  gather_mult_kernel<<<(rows * max_len + 255) / 256, 256, 0, st>>>(bs, mult_preds, mult_lprobs, best_len, info, rows, max_len,
+                                                                  batch);
+  CNB_LAUNCH_OK();
+  return 0;
+}
+
+static void frame_lens_host(const int64_t* x_lens, int batch, int64_t n, std::vector<int32_t>* out) {
+  const Geometry g = geometry(n);
+  const int64_t red = n / g.tp;  // reference convnext.py:313
+  out->resize(batch);
+  for (int b = 0; b < batch; ++b) {
+    const int64_t len = x_lens ? x_lens[b] : n;
+    // torch: float32 division then round-half-to-even (convnext.py:315)
+    const float q = (float)len / (float)red;
+    (*out)[b] = (int32_t)std::nearbyintf(q);
+  }
+}
+
+}  // namespace cnb
+
+// =====================================================================================================================
+// extern "C"
+// =====================================================================================================================
+#define CHECK_HANDLE(h)                                       \
+  CNB_REQUIRE((h) != nullptr, "null handle");                 \
+  CNB_CUDA_OK(cudaSetDevice((h)->cfg.device))
+#define CHECK_READY(h) \
+  CHECK_HANDLE(h);     \
+  CNB_REQUIRE((h)->finalized, "weights not finalized (call cnb_finalize_weights)")
+
+extern "C" {
+
+const char* cnb_last_error(void) { return g_error.c_str(); }
+int cnb_abi_version(void) { return CNB_ABI_VERSION; }
+
+int cnb_create(const cnb_config* cfg, cnb_handle** out) {
+  CNB_REQUIRE(cfg != nullptr && out != nullptr, "null argument");
+  CNB_REQUIRE(cfg->abi_version == CNB_ABI_VERSION, "ABI version mismatch");
+  CNB_REQUIRE(cfg->vocab_size > 4, "vocab_size must cover the 4 special tokens");
+  CNB_REQUIRE(cfg->precision == CNB_PRECISION_FAST || cfg->precision == CNB_PRECISION_PARITY, "unknown precision mode");
+  int n_dev = 0;
+  CNB_CUDA_OK(cudaGetDeviceCount(&n_dev));
+  CNB_REQUIRE(cfg->device >= 0 && cfg->device < n_dev, "no such CUDA device");
+  cudaDeviceProp prop;
+  CNB_CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) {
+    set_error(std::string("conette_b200 needs an sm_100-class GPU (B200); found ") + prop.name + " (sm_" +
+              std::to_string(prop.major) + std::to_string(prop.minor) + "); there is no fallback path");
+    return -5;
+  }
+  cnb_handle* h = new cnb_handle();
+  h->cfg = *cfg;
+  *out = h;
+  return 0;
+}
+
+int cnb_destroy(cnb_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  for (auto& kv : h->ws)
+    if (kv.second.ptr) cudaFree(kv.second.ptr);
+  if (h->arena.base) cudaFree(h->arena.base);
+  if (h->zero_flag) cudaFree(h->zero_flag);
+  delete h;
+  return 0;
+}
+
+int cnb_load_weight(cnb_handle* h, const char* name, const void* host_ptr, int32_t dtype, int32_t ndim, const int64_t* shape) {
+  CNB_REQUIRE(h != nullptr && name != nullptr, "null argument");
+  CNB_REQUIRE(!h->finalized, "weights already finalized");
+  if (dtype != CNB_DTYPE_F32) return 0;  // integer / bool tensors are host-side state (task ids, forbid mask, ...)
+  CNB_REQUIRE(host_ptr != nullptr && ndim >= 0 && ndim <= 8, "bad tensor");
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    t.shape.push_back(shape[i]);
+    n *= (size_t)shape[i];
+  }
+  t.data.assign(reinterpret_cast<const float*>(host_ptr), reinterpret_cast<const float*>(host_ptr) + n);
+  h->staged[name] = std::move(t);
+  return 0;
+}
+
+int cnb_finalize_weights(cnb_handle* h) {
+  CNB_REQUIRE(h != nullptr, "null handle");
+  CNB_REQUIRE(!h->finalized, "weights already finalized");
+  return finalize(h);
+}
+
+int cnb_geometry(int64_t n_samples, int32_t* n_stft_frames, int32_t stage_heights[4], int32_t* n_out_frames) {
+  CNB_REQUIRE(n_samples > 0, "n_samples must be positive");
+  const Geometry g = geometry(n_samples);
+  if (n_stft_frames) *n_stft_frames = g.t;
+  if (stage_heights)
+    for (int i = 0; i < 4; ++i) stage_heights[i] = g.h[i];
+  if (n_out_frames) *n_out_frames = g.tp;
+  return 0;
+}
+
+static int check_audio(int32_t batch, int64_t n) {
+  CNB_REQUIRE(batch > 0, "empty batch");
+  CNB_REQUIRE(n > 512, "clips must be longer than the 512-sample reflect padding");
+  CNB_REQUIRE(geometry(n).h[0] >= 8, "padded batch shorter than 7360 samples: the last 2x2 downsample has no input row "
+                                     "(the reference raises RuntimeError here too)");
+  return 0;
+}
+
+int cnb_frontend(cnb_handle* h, const float* wav, int32_t batch, int64_t n, int32_t apply_bn, float* out, void* stream) {
+  CHECK_READY(h);
+  CNB_REQUIRE(wav && out, "null buffer");
+  CNB_REQUIRE(batch > 0 && n > 512, "bad audio shape");
+  return launch_frontend(wav, batch, n, h->fe, apply_bn != 0, out, (cudaStream_t)stream);
+}
+
+int cnb_encoder(cnb_handle* h, const float* wav, int32_t batch, int64_t n, float* frame_embs_out, float* clip_probs_out,
+                void* stream) {
+  CHECK_READY(h);
+  CNB_REQUIRE(wav && frame_embs_out, "null buffer");
+  if (int rc = check_audio(batch, n)) return rc;
+  return encode(h, wav, batch, n, frame_embs_out, clip_probs_out, (cudaStream_t)stream);
+}
+
+int cnb_encoder_tap(cnb_handle* h, const float* wav, int32_t batch, int64_t n, int32_t tap_kind, int32_t stage, int32_t block,
+                    float* out, int64_t cap, void* stream) {
+  CHECK_READY(h);
+  CNB_REQUIRE(wav && out, "null buffer");
+  if (int rc = check_audio(batch, n)) return rc;
+  CNB_REQUIRE(batch <= chunk_size(h), "tap batch must fit one encoder chunk");
+  Tap tap;
+  tap.kind = tap_kind; tap.stage = stage; tap.block = block; tap.out = out; tap.cap = cap;
+  const Geometry g = geometry(n);
+  WS(h, "tap_fe", float, (size_t)batch * g.tp * 768, fe);
+  int rc = (h->cfg.precision == CNB_PRECISION_PARITY)
+               ? encode_chunk<float>(h, wav, batch, n, fe, nullptr, &tap, (cudaStream_t)stream)
+               : encode_chunk<__nv_bfloat16>(h, wav, batch, n, fe, nullptr, &tap, (cudaStream_t)stream);
+  if (rc) return rc;
+  CNB_REQUIRE(tap.hit, "no such tap point");
+  return 0;
+}
+
+static int check_decode(cnb_handle* h, int32_t batch, int32_t tp, int32_t beam, int32_t min_len, int32_t max_len) {
+  CNB_REQUIRE(batch > 0 && tp > 0, "empty batch");
+  CNB_REQUIRE(beam > 0 && beam <= 8, "beam_size must be in [1, 8]");
+  CNB_REQUIRE(min_len >= 0, "min_pred_size must be >= 0");
+  CNB_REQUIRE(max_len > 0 && max_len <= 64, "max_pred_size must be in [1, 64]");
+  return 0;
+}
+
+int cnb_decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, const int64_t* bos_ids, const uint8_t* forbid,
+               int32_t batch, int32_t tp, int32_t beam, int32_t min_len, int32_t max_len, int64_t* preds, float* lprobs,
+               int64_t* mult_preds, float* mult_lprobs, int32_t* info, void* stream) {
+  CHECK_READY(h);
+  CNB_REQUIRE(frame_embs && lens && bos_ids && preds && lprobs && mult_preds && mult_lprobs && info, "null buffer");
+  if (int rc = check_decode(h, batch, tp, beam, min_len, max_len)) return rc;
+  return decode(h, frame_embs, lens, bos_ids, forbid, batch, tp, beam, min_len, max_len, preds, lprobs, mult_preds,
+                mult_lprobs, info, (cudaStream_t)stream);
+}
+
+int cnb_decoder_logits(cnb_handle* h, const float* frame_embs, const int32_t* lens, const int64_t* tokens, int32_t batch,
+                       int32_t tp, int32_t steps, float* logits_out, void* stream) {
+  CHECK_READY(h);
+  CNB_REQUIRE(frame_embs && lens && tokens && logits_out, "null buffer");
+  if (int rc = check_decode(h, batch, tp, 1, 0, steps)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  DecoderDims dd{batch, 1, tp, steps, h->cfg.vocab_size};
+  DecWs w;
+  if (int rc = dec_prepare(h, frame_embs, batch, tp, batch, steps, &w, st)) return rc;
+  WS(h, "tok0", int, (size_t)batch * (steps + 1), tok);
+  WS(h, "src0", int, (size_t)batch * steps, src);
+  tokens_i64_to_i32_kernel<<<(batch * steps + 255) / 256, 256, 0, st>>>(tokens, tok, batch, steps, steps + 1);
+  CNB_LAUNCH_OK();
+  iota_rows_kernel<<<(batch * steps + 255) / 256, 256, 0, st>>>(src, batch, steps);
+  CNB_LAUNCH_OK();
+  for (int i = 0; i < steps; ++i) {
+    if (int rc = dec_step(h, w, tok, src, lens, i, dd, h->zero_flag, st)) return rc;
+    copy_logits_kernel<<<(unsigned)ceil_div((int64_t)batch * dd.vocab, 256), 256, 0, st>>>(w.logits, logits_out, batch,
+                                                                                          dd.vocab, i, steps);
+    CNB_LAUNCH_OK();
+  }
+  return 0;
+}
+
+int cnb_caption(cnb_handle* h, const float* wav, const int64_t* x_lens_host, const int64_t* bos_ids, const uint8_t* forbid,
+                int32_t batch, int64_t n, int32_t beam, int32_t min_len, int32_t max_len, int64_t* preds, float* lprobs,
+                int64_t* mult_preds, float* mult_lprobs, int32_t* info, float* clip_probs, void* stream) {
+  CHECK_READY(h);
+  CNB_REQUIRE(wav && bos_ids && preds && lprobs && mult_preds && mult_lprobs && info, "null buffer");
+  if (int rc = check_audio(batch, n)) return rc;
+  const Geometry g = geometry(n);
+  if (int rc = check_decode(h, batch, g.tp, beam, min_len, max_len)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  WS(h, "frame_embs", float, (size_t)batch * g.tp * 768, fe);
+  WS(h, "lens", int32_t, batch, lens);
+  std::vector<int32_t> lens_h;
+  frame_lens_host(x_lens_host, batch, n, &lens_h);
+  CNB_CUDA_OK(cudaMemcpyAsync(lens, lens_h.data(), batch * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CNB_CUDA_OK(cudaStreamSynchronize(st));  // lens_h is a stack-lifetime pageable buffer
+  if (int rc = encode(h, wav, batch, n, fe, clip_probs, st)) return rc;
+  return decode(h, fe, lens, bos_ids, forbid, batch, g.tp, beam, min_len, max_len, preds, lprobs, mult_preds, mult_lprobs,
+                info, st);
+}
+
+int cnb_caption_host(cnb_handle* h, const float* wav_host, const int64_t* x_lens_host, const int64_t* bos_ids_host,
+                     const uint8_t* forbid_host, int32_t batch, int64_t n, int32_t beam, int32_t min_len, int32_t max_len,
+                     int64_t* preds_host, float* lprobs_host, int64_t* mult_preds_host, float* mult_lprobs_host,
+                     int32_t* info_host, float* clip_probs_host) {
+  CHECK_READY(h);
+  CNB_REQUIRE(wav_host && bos_ids_host && preds_host && lprobs_host && mult_preds_host && mult_lprobs_host && info_host,
+              "null buffer");
+  if (int rc = check_audio(batch, n)) return rc;
+  const int V = h->cfg.vocab_size;
+  const int rows = batch * beam;
+  cudaStream_t st = 0;
+  WS(h, "io_wav", float, (size_t)batch * n, wav);
+  WS(h, "io_bos", int64_t, batch, bos);
+  WS(h, "io_forbid", uint8_t, V, forbid);
+  WS(h, "io_preds", int64_t, (size_t)batch * max_len, preds);
+  WS(h, "io_lprobs", float, batch, lprobs);
+  WS(h, "io_mpreds", int64_t, (size_t)rows * max_len, mpreds);
+  WS(h, "io_mlprobs", float, rows, mlprobs);
+  WS(h, "io_info", int32_t, 2 + batch, info);
+  WS(h, "io_clip", float, (size_t)batch * kTags, clip);
+  CNB_CUDA_OK(cudaMemcpyAsync(wav, wav_host, (size_t)batch * n * sizeof(float), cudaMemcpyHostToDevice, st));
+  CNB_CUDA_OK(cudaMemcpyAsync(bos, bos_ids_host, batch * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  if (forbid_host) CNB_CUDA_OK(cudaMemcpyAsync(forbid, forbid_host, V, cudaMemcpyHostToDevice, st));
+  if (int rc = cnb_caption(h, wav, x_lens_host, bos, forbid_host ? forbid : nullptr, batch, n, beam, min_len, max_len, preds,
+                           lprobs, mpreds, mlprobs, info, clip_probs_host ? clip : nullptr, st))
+    return rc;
+  CNB_CUDA_OK(cudaMemcpyAsync(preds_host, preds, (size_t)batch * max_len * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CNB_CUDA_OK(cudaMemcpyAsync(lprobs_host, lprobs, batch * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CNB_CUDA_OK(cudaMemcpyAsync(mult_preds_host, mpreds, (size_t)rows * max_len * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CNB_CUDA_OK(cudaMemcpyAsync(mult_lprobs_host, mlprobs, rows * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CNB_CUDA_OK(cudaMemcpyAsync(info_host, info, (2 + batch) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (clip_probs_host)
+    CNB_CUDA_OK(cudaMemcpyAsync(clip_probs_host, clip, (size_t)batch * kTags * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CNB_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+
+int cnb_debug_gemm(cnb_handle* h, const float* a, const float* w, const float* bias, const float* scale, const float* resid,
+                   int32_t m, int32_t n, int32_t k, int32_t epi, int32_t use_tc, int32_t out_bf16, float* out, void* stream) {
+  CHECK_READY(h);
+  CNB_REQUIRE(a && w && bias && out, "null buffer");
+  CNB_REQUIRE(epi >= 0 && epi <= 3, "unknown epilogue");
+  cudaStream_t st = (cudaStream_t)stream;
+  EpiParams ep;
+  ep.bias = bias; ep.scale = scale; ep.resid = resid;
+  if (!use_tc) return launch_gemm_f32<float>(a, k, w, m, n, k, (Epilogue)epi, ep, out, n, st);
+  WS(h, "dbg_a", __nv_bfloat16, (size_t)m * k, a_bf);
+  WS(h, "dbg_w", __nv_bfloat16, (size_t)n * k, w_bf);
+  f32_to_bf16_kernel<<<(unsigned)ceil_div((int64_t)m * k, 256), 256, 0, st>>>(a, a_bf, (int64_t)m * k);
+  CNB_LAUNCH_OK();
+  f32_to_bf16_kernel<<<(unsigned)ceil_div((int64_t)n * k, 256), 256, 0, st>>>(w, w_bf, (int64_t)n * k);
+  CNB_LAUNCH_OK();
+  if (!out_bf16) return launch_gemm_tc<float>(a_bf, w_bf, m, n, k, (Epilogue)epi, ep, out, n, st);
+  CNB_REQUIRE(epi != EPI_SCALE_RESID, "the residual epilogue writes fp32");
+  WS(h, "dbg_o", __nv_bfloat16, (size_t)m * n, o_bf);
+  if (int rc = launch_gemm_tc<__nv_bfloat16>(a_bf, w_bf, m, n, k, (Epilogue)epi, ep, o_bf, n, st)) return rc;
+  bf16_to_f32_kernel<<<(unsigned)ceil_div((int64_t)m * n, 256), 256, 0, st>>>(o_bf, out, (int64_t)m * n);
+  CNB_LAUNCH_OK();
+  return 0;
+}
+
+int64_t cnb_launch_count(const cnb_handle*) { return g_launches.load(); }
+int64_t cnb_device_bytes(const cnb_handle* h) { return h ? (int64_t)(h->arena.cap + h->ws_bytes) : 0; }
+
+}  // extern "C"

@@ -1,0 +1,269 @@
+// K-BEAM: one CTA per clip does the whole per-step selection of the reference's batched beam search without any host
+// synchronisation: EOS / no-repeat masking, log-softmax over the vocabulary for every live beam, flat top-k over
+// (live beams x V) by warp-shuffle reductions, history / KV-cache back-pointer update and finish bookkeeping.
+// Reference: nn/decoding/beam.py:113-203 (step loop) and :230-269 (_select_k_next_toks); semantics in SURVEY.md Appendix B.
+// Fixed-slot formulation: physical row = clip * beam + label; labels stick to row positions, finished labels leave the
+// live set, the r-th best candidate goes to the r-th live label (shown equal to the reference's row-compacting code by
+// tests/test_oracle_vs_reference.py on the CPU restatement this kernel mirrors).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace cnb {
+
+constexpr int kBeamThreads = 256;
+constexpr int kMaxBeam = 8;
+constexpr int kPad = 0, kEos = 2;
+
+__global__ void beam_init_kernel(const int64_t* __restrict__ bos_ids, BeamState st, int rows, int beam, int max_len) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r == 0) {
+    st.done[0] = 0;
+    st.done[1] = max_len;
+    st.done[2] = rows;  // live rows remaining
+  }
+  if (r >= rows) return;
+  for (int p = 0; p <= max_len; ++p) {
+    st.tokens[0][(int64_t)r * (max_len + 1) + p] = kPad;
+    st.tokens[1][(int64_t)r * (max_len + 1) + p] = kPad;
+  }
+  st.tokens[0][(int64_t)r * (max_len + 1)] = (int)bos_ids[r / beam];
+  for (int p = 0; p < max_len; ++p) {
+    st.src_row[0][(int64_t)r * max_len + p] = r;
+    st.src_row[1][(int64_t)r * max_len + p] = r;
+    st.out_preds[(int64_t)r * max_len + p] = kPad;
+  }
+  st.sum_lp[r] = 0.f;
+  st.live[r] = 1;
+  st.out_lp[r] = 0.f;
+}
+
+struct Cand {
+  float v;
+  int idx;  // flat index: live_position * V + word
+};
+__device__ __forceinline__ bool better(const Cand& a, const Cand& b) {
+  return a.v > b.v || (a.v == b.v && a.idx < b.idx);
+}
+
+__global__ void __launch_bounds__(kBeamThreads)
+beam_step_kernel(float* __restrict__ logits, const uint8_t* __restrict__ forbid, BeamState st, int step, int cur, int min_len,
+                 int beam, int max_len, int vocab) {
+  if (st.done[0]) return;
+  __shared__ int s_live_label[kMaxBeam];
+  __shared__ int s_nlive;
+  __shared__ float s_prev[kMaxBeam];
+  __shared__ float s_lse_max[kMaxBeam];
+  __shared__ float s_lse_log[kMaxBeam];
+  __shared__ float s_red[kBeamThreads / 32];
+  __shared__ Cand s_cand[kBeamThreads / 32];
+  __shared__ Cand s_win[kMaxBeam];
+  __shared__ int s_winner_tid;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int clip = blockIdx.x;
+  const int row0 = clip * beam;
+  const int tstride = max_len + 1;
+  const int* tok_cur = st.tokens[cur];
+  int* tok_new = st.tokens[cur ^ 1];
+  const int* src_cur = st.src_row[cur];
+  int* src_new = st.src_row[cur ^ 1];
+
+  if (tid == 0) {
+    int n = 0;
+    for (int l = 0; l < beam; ++l)
+      if (st.live[row0 + l]) {
+        s_live_label[n] = l;
+        s_prev[n] = st.sum_lp[row0 + l];
+        ++n;
+      }
+    s_nlive = n;
+  }
+  __syncthreads();
+  const int nlive = s_nlive;
+  if (nlive == 0) return;
+  const int nrows_used = (step == 0) ? 1 : nlive;  // step 0: only the first row (beam.py:243-246)
+  const int k_sel = nlive;                         // number of candidates to select (= beam at step 0)
+
+  // ---- masks: EOS before min_len (beam.py:129-130), no-repeat of forbidden tokens already in the history (:146-156)
+  for (int j = 0; j < nrows_used; ++j) {
+    const int row = row0 + s_live_label[j];
+    float* lg = logits + (int64_t)row * vocab;
+    if (tid == 0 && step < min_len) lg[kEos] = -INFINITY;
+    if (forbid != nullptr && tid <= step) {
+      const int tok = tok_cur[(int64_t)row * tstride + tid];
+      if (forbid[tok]) lg[tok] = -INFINITY;
+    }
+  }
+  __syncthreads();
+
+  // ---- log-softmax statistics per used row
+  for (int j = 0; j < nrows_used; ++j) {
+    const float* lg = logits + (int64_t)(row0 + s_live_label[j]) * vocab;
+    float mx = -INFINITY;
+    for (int v = tid; v < vocab; v += kBeamThreads) mx = fmaxf(mx, lg[v]);
+    mx = warp_max(mx);
+    if (lane == 0) s_red[warp] = mx;
+    __syncthreads();
+    mx = s_red[0];
+#pragma unroll
+    for (int i = 1; i < kBeamThreads / 32; ++i) mx = fmaxf(mx, s_red[i]);
+    __syncthreads();
+    float sm = 0.f;
+    for (int v = tid; v < vocab; v += kBeamThreads) sm += expf(lg[v] - mx);
+    sm = warp_sum(sm);
+    if (lane == 0) s_red[warp] = sm;
+    __syncthreads();
+    if (tid == 0) {
+      float t = 0.f;
+      for (int i = 0; i < kBeamThreads / 32; ++i) t += s_red[i];
+      s_lse_max[j] = mx;
+      s_lse_log[j] = logf(t);
+    }
+    __syncthreads();
+  }
+
+  // ---- thread-local top-k over the flat (row, word) candidates, kept sorted (best first)
+  Cand loc[kMaxBeam];
+#pragma unroll
+  for (int i = 0; i < kMaxBeam; ++i) loc[i] = Cand{-INFINITY, 0x7fffffff};
+  for (int j = 0; j < nrows_used; ++j) {
+    const float* lg = logits + (int64_t)(row0 + s_live_label[j]) * vocab;
+    const float mx = s_lse_max[j], lg_sum = s_lse_log[j];
+    const float prev = (step == 0) ? 0.f : s_prev[j];
+    for (int v = tid; v < vocab; v += kBeamThreads) {
+      Cand c{prev + ((lg[v] - mx) - lg_sum), j * vocab + v};
+      if (step == 0) c.v = (lg[v] - mx) - lg_sum;
+      if (better(c, loc[kMaxBeam - 1])) {
+        loc[kMaxBeam - 1] = c;
+#pragma unroll
+        for (int i = kMaxBeam - 1; i > 0; --i)
+          if (better(loc[i], loc[i - 1])) {
+            const Cand t = loc[i];
+            loc[i] = loc[i - 1];
+            loc[i - 1] = t;
+          }
+      }
+    }
+  }
+  // ---- k_sel rounds of block arg-max over the heads of the thread-local lists
+  for (int r = 0; r < k_sel; ++r) {
+    Cand best = loc[0];
+    int owner = tid;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      Cand other{__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.idx, o)};
+      const int oo = __shfl_xor_sync(0xffffffffu, owner, o);
+      if (better(other, best)) {
+        best = other;
+        owner = oo;
+      }
+    }
+    if (lane == 0) {
+      s_cand[warp] = best;
+      s_red[warp] = __int_as_float(owner);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      Cand b = s_cand[0];
+      int ow = __float_as_int(s_red[0]);
+      for (int i = 1; i < kBeamThreads / 32; ++i)
+        if (better(s_cand[i], b)) {
+          b = s_cand[i];
+          ow = __float_as_int(s_red[i]);
+        }
+      s_win[r] = b;
+      s_winner_tid = ow;
+    }
+    __syncthreads();
+    if (tid == s_winner_tid) {
+#pragma unroll
+      for (int i = 0; i < kMaxBeam - 1; ++i) loc[i] = loc[i + 1];
+      loc[kMaxBeam - 1] = Cand{-INFINITY, 0x7fffffff};
+    }
+    __syncthreads();
+  }
+
+  // ---- bookkeeping: candidate r -> r-th live label (beam.py:165-176), histories via back-pointers
+  for (int item = tid; item < k_sel * (step + 2); item += kBeamThreads) {
+    const int r = item / (step + 2), p = item - r * (step + 2);
+    const int row = row0 + s_live_label[r];
+    const int prev_pos = s_win[r].idx / vocab;
+    const int word = s_win[r].idx - prev_pos * vocab;
+    const int src = row0 + s_live_label[prev_pos];
+    if (p <= step) {
+      tok_new[(int64_t)row * tstride + p] = tok_cur[(int64_t)src * tstride + p];
+      src_new[(int64_t)row * max_len + p] = src_cur[(int64_t)src * max_len + p];
+    } else {
+      tok_new[(int64_t)row * tstride + p] = word;
+      if (p < max_len) src_new[(int64_t)row * max_len + p] = row;
+    }
+  }
+  __syncthreads();
+  if (tid < k_sel) {
+    const int r = tid;
+    const int row = row0 + s_live_label[r];
+    const int prev_pos = s_win[r].idx / vocab;
+    const int word = s_win[r].idx - prev_pos * vocab;
+    st.sum_lp[row] = s_win[r].v;
+    if (word == kEos || step == max_len - 1) {  // beam.py:173-190
+      for (int p = 0; p <= step; ++p)
+        st.out_preds[(int64_t)row * max_len + p] = tok_new[(int64_t)row * tstride + p + 1];
+      st.out_lp[row] = s_win[r].v / (float)(step + 1);
+      st.live[row] = 0;
+      const int left = atomicSub(&st.done[2], 1) - 1;
+      if (left == 0) {  // every slot of every clip is finished (beam.py:192-194)
+        st.done[1] = step + 1;
+        __threadfence();
+        st.done[0] = 1;
+      }
+    }
+  }
+}
+
+// best beam per clip (first arg-max of the average log-prob, beam.py:218-220) + index of its first EOS
+__global__ void beam_finalize_kernel(BeamState st, int64_t* __restrict__ best_preds, float* __restrict__ best_lp,
+                                     int* __restrict__ best_len, int batch, int beam, int max_len) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  int best = 0;
+  float bv = st.out_lp[b * beam];
+  for (int l = 1; l < beam; ++l)
+    if (st.out_lp[b * beam + l] > bv) {
+      bv = st.out_lp[b * beam + l];
+      best = l;
+    }
+  best_lp[b] = bv;
+  int first_eos = max_len;
+  for (int p = 0; p < max_len; ++p) {
+    const int64_t t = st.out_preds[(int64_t)(b * beam + best) * max_len + p];
+    best_preds[(int64_t)b * max_len + p] = t;
+    if (t == kEos && first_eos == max_len) first_eos = p;
+  }
+  best_len[b] = first_eos;
+}
+
+int launch_beam_init(const int64_t* bos_ids, BeamState st, const DecoderDims& dd, cudaStream_t stream) {
+  beam_init_kernel<<<(dd.rows + 127) / 128, 128, 0, stream>>>(bos_ids, st, dd.rows, dd.beam, dd.max_len);
+  CNB_LAUNCH_OK();
+  return 0;
+}
+
+int launch_beam_step(float* logits, const uint8_t* forbid, BeamState st, int step, int cur, int min_len,
+                     const DecoderDims& dd, cudaStream_t stream) {
+  CNB_REQUIRE(dd.beam <= kMaxBeam, "beam_size > 8 is not supported");
+  CNB_REQUIRE(dd.max_len + 1 <= kBeamThreads, "max_pred_size too large");
+  beam_step_kernel<<<dd.rows / dd.beam, kBeamThreads, 0, stream>>>(logits, forbid, st, step, cur, min_len, dd.beam,
+                                                                   dd.max_len, dd.vocab);
+  CNB_LAUNCH_OK();
+  return 0;
+}
+
+int launch_beam_finalize(BeamState st, int64_t* best_preds, float* best_lp, int* best_len, const DecoderDims& dd,
+                         cudaStream_t stream) {
+  const int batch = dd.rows / dd.beam;
+  beam_finalize_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(st, best_preds, best_lp, best_len, batch, dd.beam, dd.max_len);
+  CNB_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace cnb

@@ -1,0 +1,327 @@
+// ConvNeXt-Tiny CUDA-core kernels (everything that is not a GEMM): stem, depthwise 7x7 + LayerNorm, downsample
+// LayerNorm + 2x2 im2col pack, frequency mean and the clip (tag) head.  Activations are NHWC; the residual stream is
+// fp32, GEMM operands are OutT (bf16 in fast mode, f32 in parity mode).
+// Reference: nn/encoders/convnext.py:61-74 (block), :207-217 (stem / downsample), :306-334 (mean + head),
+// nn/modules/norm.py:35-40 (channels_first LayerNorm, biased variance, eps 1e-6).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace cnb {
+
+constexpr float kLnEps = 1e-6f;
+
+// =====================================================================================================================
+// K-STEM: one CTA per output row (b, h): 56 pixels x 96 channels; 8 warps x 7 pixels, lane owns channels l, l+32, l+64
+// =====================================================================================================================
+constexpr int kStemThreads = 256;
+
+__global__ void __launch_bounds__(kStemThreads)
+stem_kernel(const float* __restrict__ lm, int n_frames, int h1, const float* __restrict__ w_t, const float* __restrict__ bias,
+            const float* __restrict__ ln_g, const float* __restrict__ ln_b, float* __restrict__ out) {
+  __shared__ float s_in[4][224];
+  __shared__ float s_w[16][96];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.y, h = blockIdx.x;
+  for (int i = tid; i < 16 * 96; i += kStemThreads) s_w[i / 96][i % 96] = w_t[i];
+  for (int i = tid; i < 4 * 224; i += kStemThreads) {
+    const int r = i / 224, col = i - r * 224;
+    const int t = 4 * h - 4 + r;  // Conv2d padding (4, 0): 4 zero frames before/after in time
+    s_in[r][col] = (t >= 0 && t < n_frames) ? lm[((int64_t)b * n_frames + t) * 224 + col] : 0.f;
+  }
+  __syncthreads();
+  float bia[3], g[3], be[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    bia[j] = bias[lane + 32 * j];
+    g[j] = ln_g[lane + 32 * j];
+    be[j] = ln_b[lane + 32 * j];
+  }
+  for (int p = 0; p < 7; ++p) {
+    const int w = warp * 7 + p;
+    float acc[3] = {bia[0], bia[1], bia[2]};
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float v = s_in[r][4 * w + c];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[j] = fmaf(v, s_w[r * 4 + c][lane + 32 * j], acc[j]);
+      }
+    const float mean = warp_sum(acc[0] + acc[1] + acc[2]) * (1.f / 96.f);
+    const float d0 = acc[0] - mean, d1 = acc[1] - mean, d2 = acc[2] - mean;
+    const float var = warp_sum(d0 * d0 + d1 * d1 + d2 * d2) * (1.f / 96.f);
+    const float rstd = 1.f / sqrtf(var + kLnEps);
+    float* o = out + (((int64_t)b * h1 + h) * 56 + w) * 96;
+    o[lane] = d0 * rstd * g[0] + be[0];
+    o[lane + 32] = d1 * rstd * g[1] + be[1];
+    o[lane + 64] = d2 * rstd * g[2] + be[2];
+  }
+}
+
+int launch_stem(const float* lm, int batch, int n_frames, int h1, const float* w_t, const float* bias, const float* ln_g,
+                const float* ln_b, float* out, cudaStream_t stream) {
+  dim3 grid(h1, batch);
+  stem_kernel<<<grid, kStemThreads, 0, stream>>>(lm, n_frames, h1, w_t, bias, ln_g, ln_b, out);
+  CNB_LAUNCH_OK();
+  return 0;
+}
+
+// =====================================================================================================================
+// K-DWLN: depthwise 7x7 (pad 3) + bias + LayerNorm over C, one CTA per output row (b, h).
+//   thread = (channel pair cp, strip of 7 output pixels); weights for the pair live in registers (49 x float2);
+//   each of the 7 kernel rows streams 13 input float2 through 49 FMAs per channel.
+//   LayerNorm: two-pass (mean, then squared deviations) with warp shuffles + shared-memory atomics per pixel.
+// =====================================================================================================================
+template <int C, int W, typename OutT>
+__global__ void __launch_bounds__(((C / 2 + 31) / 32) * 32 * (W / 7))
+dwconv_ln_kernel(const float* __restrict__ x, int H, const float* __restrict__ w_t, const float* __restrict__ bias,
+                 const float* __restrict__ ln_g, const float* __restrict__ ln_b, OutT* __restrict__ out) {
+  constexpr int CP = C / 2;
+  constexpr int CP_PAD = ((CP + 31) / 32) * 32;
+  constexpr int PW = 7;
+  __shared__ float s_sum[W];
+  __shared__ float s_sq[W];
+
+  const int tid = threadIdx.x;
+  const int strip = tid / CP_PAD;
+  const int cp = tid - strip * CP_PAD;
+  const bool active = cp < CP;
+  const int b = blockIdx.y, h = blockIdx.x;
+  const int w0 = strip * PW;
+  for (int i = tid; i < W; i += blockDim.x) {
+    s_sum[i] = 0.f;
+    s_sq[i] = 0.f;
+  }
+  __syncthreads();
+
+  float2 acc[PW];
+  if (active) {
+    const float2 bi = *reinterpret_cast<const float2*>(bias + 2 * cp);
+#pragma unroll
+    for (int p = 0; p < PW; ++p) acc[p] = bi;
+    const float* xb = x + (int64_t)b * H * W * C + 2 * cp;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      const int r = h + i - 3;
+      if (r < 0 || r >= H) continue;  // zero padding at the padded-batch border
+      float2 wr[7];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) wr[j] = __ldg(reinterpret_cast<const float2*>(w_t + (i * 7 + j) * C + 2 * cp));
+      float2 in[PW + 6];
+#pragma unroll
+      for (int j = 0; j < PW + 6; ++j) {
+        const int col = w0 + j - 3;
+        in[j] = (col >= 0 && col < W) ? __ldg(reinterpret_cast<const float2*>(xb + ((int64_t)r * W + col) * C))
+                                      : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int p = 0; p < PW; ++p)
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+          acc[p].x = fmaf(in[p + j].x, wr[j].x, acc[p].x);
+          acc[p].y = fmaf(in[p + j].y, wr[j].y, acc[p].y);
+        }
+    }
+  } else {
+#pragma unroll
+    for (int p = 0; p < PW; ++p) acc[p] = make_float2(0.f, 0.f);
+  }
+  // pass 1: mean over C for each of the strip's pixels (all lanes of a warp share the strip)
+#pragma unroll
+  for (int p = 0; p < PW; ++p) {
+    const float s = warp_sum(acc[p].x + acc[p].y);
+    if ((tid & 31) == 0) atomicAdd(&s_sum[w0 + p], s);
+  }
+  __syncthreads();
+  float mean[PW];
+#pragma unroll
+  for (int p = 0; p < PW; ++p) {
+    mean[p] = s_sum[w0 + p] * (1.f / C);
+    const float dx = active ? acc[p].x - mean[p] : 0.f, dy = active ? acc[p].y - mean[p] : 0.f;
+    const float s = warp_sum(dx * dx + dy * dy);
+    if ((tid & 31) == 0) atomicAdd(&s_sq[w0 + p], s);
+  }
+  __syncthreads();
+  if (active) {
+    const float2 g = *reinterpret_cast<const float2*>(ln_g + 2 * cp);
+    const float2 be = *reinterpret_cast<const float2*>(ln_b + 2 * cp);
+    OutT* o = out + (((int64_t)b * H + h) * W + w0) * C + 2 * cp;
+#pragma unroll
+    for (int p = 0; p < PW; ++p) {
+      const float rstd = 1.f / sqrtf(s_sq[w0 + p] * (1.f / C) + kLnEps);
+      const float y0 = (acc[p].x - mean[p]) * rstd * g.x + be.x;
+      const float y1 = (acc[p].y - mean[p]) * rstd * g.y + be.y;
+      if constexpr (sizeof(OutT) == 2) {
+        *reinterpret_cast<__nv_bfloat162*>(o + (int64_t)p * C) = __floats2bfloat162_rn(y0, y1);
+      } else {
+        *reinterpret_cast<float2*>(o + (int64_t)p * C) = make_float2(y0, y1);
+      }
+    }
+  }
+}
+
+template <int C, int W, typename OutT>
+static int launch_dwconv_ln_t(const float* x, int batch, int h, const float* w_t, const float* bias, const float* ln_g,
+                              const float* ln_b, OutT* out, cudaStream_t stream) {
+  constexpr int threads = ((C / 2 + 31) / 32) * 32 * (W / 7);
+  dim3 grid(h, batch);
+  dwconv_ln_kernel<C, W, OutT><<<grid, threads, 0, stream>>>(x, h, w_t, bias, ln_g, ln_b, out);
+  CNB_LAUNCH_OK();
+  return 0;
+}
+
+template <typename OutT>
+int launch_dwconv_ln(const float* x, int batch, int h, int w, int c, const float* w_t, const float* bias, const float* ln_g,
+                     const float* ln_b, OutT* out, cudaStream_t stream) {
+  if (c == 96 && w == 56) return launch_dwconv_ln_t<96, 56, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
+  if (c == 192 && w == 28) return launch_dwconv_ln_t<192, 28, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
+  if (c == 384 && w == 14) return launch_dwconv_ln_t<384, 14, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
+  if (c == 768 && w == 7) return launch_dwconv_ln_t<768, 7, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
+  set_error("dwconv_ln: unsupported (C, W) = (" + std::to_string(c) + ", " + std::to_string(w) + ")");
+  return -1;
+}
+template int launch_dwconv_ln<float>(const float*, int, int, int, int, const float*, const float*, const float*,
+                                     const float*, float*, cudaStream_t);
+template int launch_dwconv_ln<__nv_bfloat16>(const float*, int, int, int, int, const float*, const float*, const float*,
+                                             const float*, __nv_bfloat16*, cudaStream_t);
+
+// =====================================================================================================================
+// K-DS (part 1): LayerNorm(channels_first) per pixel + pack 2x2/stride-2 patches as GEMM rows.
+//   out[(b, h', w'), (kh, kw, c)] = LN(x[b, 2h'+kh, 2w'+kw, :])[c]   (odd trailing row/col dropped: floor)
+//   one warp per input pixel.
+// =====================================================================================================================
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+ln_pack2x2_kernel(const float* __restrict__ x, int batch, int H, int W, int C, const float* __restrict__ ln_g,
+                  const float* __restrict__ ln_b, OutT* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int Ho = H / 2, Wo = W / 2;
+  const int64_t n_pix = (int64_t)batch * Ho * 2 * Wo * 2;
+  const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t pix = warp_id; pix < n_pix; pix += n_warps) {
+    // enumerate only the pixels that are used: (b, h < 2*Ho, w < 2*Wo)
+    const int wq = (int)(pix % (2 * Wo));
+    const int hq = (int)((pix / (2 * Wo)) % (2 * Ho));
+    const int b = (int)(pix / ((int64_t)2 * Wo * 2 * Ho));
+    const float* px = x + (((int64_t)b * H + hq) * W + wq) * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += px[c];
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float d = px[c] - mean;
+      q += d * d;
+    }
+    const float rstd = 1.f / sqrtf(warp_sum(q) / C + kLnEps);
+    const int64_t row = ((int64_t)b * Ho + hq / 2) * Wo + wq / 2;
+    OutT* o = out + row * (4 * (int64_t)C) + ((hq & 1) * 2 + (wq & 1)) * C;
+    for (int c = lane; c < C; c += 32) o[c] = from_float<OutT>((px[c] - mean) * rstd * ln_g[c] + ln_b[c]);
+  }
+}
+
+template <typename OutT>
+int launch_ln_pack2x2(const float* x, int batch, int h, int w, int c, const float* ln_g, const float* ln_b, OutT* out,
+                      cudaStream_t stream) {
+  const int64_t n_pix = (int64_t)batch * (h / 2) * 2 * (w / 2) * 2;
+  const int blocks = (int)std::min<int64_t>(ceil_div(n_pix, 8), (int64_t)kNumSMs * 16);
+  ln_pack2x2_kernel<OutT><<<blocks, 256, 0, stream>>>(x, batch, h, w, c, ln_g, ln_b, out);
+  CNB_LAUNCH_OK();
+  return 0;
+}
+template int launch_ln_pack2x2<float>(const float*, int, int, int, int, const float*, const float*, float*, cudaStream_t);
+template int launch_ln_pack2x2<__nv_bfloat16>(const float*, int, int, int, int, const float*, const float*, __nv_bfloat16*,
+                                              cudaStream_t);
+
+// =====================================================================================================================
+// mean over frequency (reference convnext.py:306): (B, T', W, C) -> (B, T', C)
+// =====================================================================================================================
+__global__ void freq_mean_kernel(const float* __restrict__ x, int64_t n_rows, int W, int C, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * C) return;
+  const int64_t row = i / C;
+  const int c = (int)(i - row * C);
+  float s = 0.f;
+  for (int w = 0; w < W; ++w) s += x[(row * W + w) * C + c];
+  out[i] = s / W;
+}
+
+int launch_freq_mean(const float* x, int batch, int tp, int w, int c, float* out, cudaStream_t stream) {
+  const int64_t n = (int64_t)batch * tp * c;
+  freq_mean_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(x, (int64_t)batch * tp, w, c, out);
+  CNB_LAUNCH_OK();
+  return 0;
+}
+
+// =====================================================================================================================
+// clip head (reference convnext.py:324-334): max_t + mean_t -> LayerNorm(768, eps 1e-6) -> Linear(527) -> sigmoid
+//   one CTA (256 threads) per clip; 768 = 3 channels per thread
+// =====================================================================================================================
+__global__ void __launch_bounds__(256)
+clip_head_kernel(const float* __restrict__ fe, int tp, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                 const float* __restrict__ w, const float* __restrict__ bias, int n_cls, float* __restrict__ out) {
+  __shared__ float s_v[768];
+  __shared__ float s_red[8];
+  __shared__ float s_stat[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* f = fe + (int64_t)blockIdx.x * tp * 768;
+  float v[3];
+  float part = 0.f;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int c = tid + 256 * j;
+    float mx = -INFINITY, sm = 0.f;
+    for (int t = 0; t < tp; ++t) {
+      const float a = f[(int64_t)t * 768 + c];
+      mx = fmaxf(mx, a);
+      sm += a;
+    }
+    v[j] = mx + sm / tp;
+    part += v[j];
+  }
+  part = warp_sum(part);
+  if (lane == 0) s_red[warp] = part;
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += s_red[i];
+    s_stat[0] = s / 768.f;
+  }
+  __syncthreads();
+  const float mean = s_stat[0];
+  part = 0.f;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) part += (v[j] - mean) * (v[j] - mean);
+  part = warp_sum(part);
+  __syncthreads();
+  if (lane == 0) s_red[warp] = part;
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += s_red[i];
+    s_stat[1] = 1.f / sqrtf(s / 768.f + kLnEps);
+  }
+  __syncthreads();
+  const float rstd = s_stat[1];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int c = tid + 256 * j;
+    s_v[c] = (v[j] - mean) * rstd * ln_g[c] + ln_b[c];
+  }
+  __syncthreads();
+  for (int n = warp; n < n_cls; n += 8) {
+    float acc = 0.f;
+    for (int c = lane; c < 768; c += 32) acc = fmaf(s_v[c], w[(int64_t)n * 768 + c], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) out[(int64_t)blockIdx.x * n_cls + n] = 1.f / (1.f + expf(-(acc + bias[n])));
+  }
+}
+
+int launch_clip_head(const float* frame_embs, int batch, int tp, const float* ln_g, const float* ln_b, const float* w,
+                     const float* bias, int n_cls, float* out, cudaStream_t stream) {
+  clip_head_kernel<<<batch, 256, 0, stream>>>(frame_embs, tp, ln_g, ln_b, w, bias, n_cls, out);
+  CNB_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace cnb

@@ -1,0 +1,384 @@
+// bf16 tensor-core GEMM for sm_100a: TMA-fed tcgen05.mma with the accumulator in TMEM and fused epilogues.
+//   out[m,n] = epi( sum_k A[m,k] * W[n,k] ),  A (M,K) bf16 and W (N,K) bf16 both K-major, fp32 accumulation.
+// This is the ConvNeXt pointwise-MLP / downsample / projection hot loop (reference convnext.py:66-73, :212-217,
+// pl_modules/common.py:71-78), ~92 % of the encoder FLOPs.
+//
+// Structure (persistent, warp-specialised, one CTA per SM):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of A (128 x 64) and W (BLOCK_N x 64) tiles, 128B swizzle
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16, kind::f16, bf16 in / f32 acc)
+//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias / GELU / layer-scale+residual -> global stores
+// Pipelines: STAGES-deep smem ring (full/empty mbarriers) and a 2-deep TMEM accumulator ring (tmem_full/tmem_empty) so
+// the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace cnb {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 bytes = one swizzle-128B atom row
+constexpr int kUmmaK = 16;
+constexpr int kStages = 4;
+constexpr int kTcThreads = 192;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug becomes a trapped launch (reported through the C ABI) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 22)) {
+      printf("conette_b200: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar,
+             parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(x), "r"(y), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+        "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled shared-memory matrix descriptor (SM100 UMMA): start>>4 | LBO | SBO=1024B | version=1 | SW128
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;             // leading byte offset (unused for swizzled K-major), canonical value 1
+  d |= (uint64_t)(1024 >> 4) << 32;   // stride byte offset: 8 rows x 128 B between core-matrix groups
+  d |= (uint64_t)1 << 46;             // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;             // layout type: SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// epilogue math on 32 consecutive columns of one output row
+// ---------------------------------------------------------------------------------------------------------------------
+template <int EPI, typename OutT>
+__device__ __forceinline__ void epilogue_row32(float* v, int64_t m, int n0, const EpiParams& ep, OutT* out, int64_t ldo) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
+    v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+  }
+  if (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  }
+  if (EPI == EPI_BIAS_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (EPI == EPI_SCALE_RESID) {
+    const float* r = ep.resid + m * ldo + n0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 s = __ldg(reinterpret_cast<const float4*>(ep.scale + n0 + j));
+      const float4 x = *reinterpret_cast<const float4*>(r + j);
+      v[j] = fmaf(s.x, v[j], x.x); v[j + 1] = fmaf(s.y, v[j + 1], x.y);
+      v[j + 2] = fmaf(s.z, v[j + 2], x.z); v[j + 3] = fmaf(s.w, v[j + 3], x.w);
+    }
+  }
+  OutT* o = out + m * ldo + n0;
+  if constexpr (sizeof(OutT) == 2) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+      uint4 u;
+      u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+      u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+      *reinterpret_cast<uint4*>(o + j) = u;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+struct TcSmem {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTotal = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers + tmem ptr*/;
+  static constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
+};
+
+template <int BLOCK_N, int EPI, typename OutT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M, int N, int K,
+               EpiParams ep, OutT* __restrict__ out, int64_t ldo) {
+  using S = TcSmem<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024-byte alignment
+  const uint32_t bars = base + kStages * S::kStageBytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bars + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages + 2 + s); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kStages + 4);
+  uint8_t* smem_aligned = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + kStages * S::kStageBytes +
+                                                                         8 * (2 * kStages + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_n = N / BLOCK_N;
+  const int tiles_m = (M + kBlockM - 1) / kBlockM;
+  const int n_tiles = tiles_m * tiles_n;
+  const int k_blocks = (K + kBlockK - 1) / kBlockK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(S::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int m_blk = t / tiles_n, n_blk = t - m_blk * tiles_n;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1);
+          const uint32_t a_dst = base + s * S::kStageBytes;
+          const uint32_t b_dst = a_dst + S::kABytes;
+          mbar_expect_tx(full_bar(s), S::kStageBytes);
+          tma_load_2d(a_dst, &map_a, kb * kBlockK, m_blk * kBlockM, full_bar(s));
+          tma_load_2d(b_dst, &map_w, kb * kBlockK, n_blk * BLOCK_N, full_bar(s));
+          if (++s == kStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kBlockM, BLOCK_N);
+      int s = 0, as = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        mbar_wait(tempty_bar(as), aph ^ 1);  // epilogue has drained this accumulator stage
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar(s), ph);
+          tcgen05_fence_after();
+          const uint32_t a_addr = base + s * S::kStageBytes;
+          const uint64_t adesc = make_smem_desc(a_addr);
+          const uint64_t bdesc = make_smem_desc(a_addr + S::kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in (addr >> 4) units
+            tcgen05_mma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          tcgen05_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+          if (++s == kStages) { s = 0; ph ^= 1; }
+        }
+        tcgen05_commit(tfull_bar(as));   // accumulator complete -> epilogue
+        as ^= 1;
+        if (as == 0) aph ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) are accessible to this warp
+    int as = 0;
+    uint32_t aph = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int m_blk = t / tiles_n, n_blk = t - m_blk * tiles_n;
+      mbar_wait(tfull_bar(as), aph);
+      tcgen05_fence_after();
+      const int64_t m = (int64_t)m_blk * kBlockM + lane_grp * 32 + lane;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        float v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(as * BLOCK_N + c0);
+        tmem_ld_32x32(taddr, v);
+        if (m < M) epilogue_row32<EPI, OutT>(v, m, n_blk * BLOCK_N + c0, ep, out, ldo);
+      }
+      tcgen05_fence_before();
+      mbar_arrive(tempty_bar(as));
+      as ^= 1;
+      if (as == 0) aph ^= 1;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(S::kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+int gemm_tc_init() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CNB_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point not available in this driver");
+    return -3;
+  }
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return 0;
+}
+
+// 2-D bf16 row-major (rows, cols) tensor, box = (box_rows, 64 cols), 128B swizzle, zero OOB fill
+static int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return -3;
+  }
+  return 0;
+}
+
+template <int BLOCK_N, int EPI, typename OutT>
+static int launch_cfg(const __nv_bfloat16* a, const __nv_bfloat16* w, int m, int n, int k, const EpiParams& ep, OutT* out,
+                      int64_t ldo, cudaStream_t stream) {
+  using S = TcSmem<BLOCK_N>;
+  CUtensorMap map_a, map_w;
+  if (int rc = make_map(&map_a, a, (uint64_t)m, (uint64_t)k, kBlockM)) return rc;
+  if (int rc = make_map(&map_w, w, (uint64_t)n, (uint64_t)k, BLOCK_N)) return rc;
+  auto kern = gemm_tc_kernel<BLOCK_N, EPI, OutT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CNB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    attr_set = true;
+  }
+  const int n_tiles = (int)ceil_div(m, kBlockM) * (n / BLOCK_N);
+  const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+  kern<<<grid, kTcThreads, S::kTotal, stream>>>(map_a, map_w, m, n, k, ep, out, ldo);
+  CNB_LAUNCH_OK();
+  return 0;
+}
+
+template <int EPI, typename OutT>
+static int launch_n(const __nv_bfloat16* a, const __nv_bfloat16* w, int m, int n, int k, const EpiParams& ep, OutT* out,
+                    int64_t ldo, cudaStream_t stream) {
+  if (n % 192 == 0) return launch_cfg<192, EPI, OutT>(a, w, m, n, k, ep, out, ldo, stream);
+  if (n % 128 == 0) return launch_cfg<128, EPI, OutT>(a, w, m, n, k, ep, out, ldo, stream);
+  if (n % 96 == 0) return launch_cfg<96, EPI, OutT>(a, w, m, n, k, ep, out, ldo, stream);
+  set_error("gemm_tc: N=" + std::to_string(n) + " is not a multiple of 96/128/192");
+  return -1;
+}
+
+template <typename OutT>
+int launch_gemm_tc(const __nv_bfloat16* a, const __nv_bfloat16* w, int m, int n, int k, Epilogue epi, const EpiParams& ep,
+                   OutT* out, int64_t ldo, cudaStream_t stream) {
+  CNB_REQUIRE(g_encode != nullptr, "gemm_tc_init() was not called");
+  CNB_REQUIRE(k % 8 == 0, "gemm_tc needs K to be a multiple of 8 (16-byte TMA row stride)");
+  CNB_REQUIRE(ep.bias != nullptr, "gemm_tc epilogues need a bias vector");
+  if (m == 0) return 0;
+  switch (epi) {
+    case EPI_BIAS: return launch_n<EPI_BIAS, OutT>(a, w, m, n, k, ep, out, ldo, stream);
+    case EPI_BIAS_GELU: return launch_n<EPI_BIAS_GELU, OutT>(a, w, m, n, k, ep, out, ldo, stream);
+    case EPI_BIAS_RELU: return launch_n<EPI_BIAS_RELU, OutT>(a, w, m, n, k, ep, out, ldo, stream);
+    case EPI_SCALE_RESID: return launch_n<EPI_SCALE_RESID, OutT>(a, w, m, n, k, ep, out, ldo, stream);
+  }
+  set_error("gemm_tc: unknown epilogue");
+  return -1;
+}
+template int launch_gemm_tc<float>(const __nv_bfloat16*, const __nv_bfloat16*, int, int, int, Epilogue, const EpiParams&,
+                                   float*, int64_t, cudaStream_t);
+template int launch_gemm_tc<__nv_bfloat16>(const __nv_bfloat16*, const __nv_bfloat16*, int, int, int, Epilogue,
+                                           const EpiParams&, __nv_bfloat16*, int64_t, cudaStream_t);
+
+}  // namespace cnb

@@ -1,0 +1,104 @@
+// Internal launcher declarations shared by the translation units of libconette_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace cnb {
+
+// ---- front-end -------------------------------------------------------------------------------------------------
+struct FrontendParams {
+  const float2* twiddle = nullptr;  // (1024) W_1024^j
+  const int* mel_lo = nullptr;      // (224)
+  const int* mel_cnt = nullptr;     // (224)
+  const int* mel_off = nullptr;     // (224)
+  const float* mel_w = nullptr;     // (nnz)
+  const float* bn_scale = nullptr;  // (224)
+  const float* bn_shift = nullptr;  // (224)
+  const float* ones = nullptr;      // (224)
+  const float* zeros = nullptr;     // (224)
+};
+int launch_frontend(const float* wav, int batch, int64_t n_samples, const FrontendParams& p, bool apply_bn, float* out,
+                    cudaStream_t stream);
+
+// ---- stem: Conv2d(1,96,4x4,s4,pad(4,0)) + LayerNorm(channels_first) -> NHWC f32 --------------------------------------
+int launch_stem(const float* logmel_bn, int batch, int n_frames, int h1, const float* w_t /*(16,96)*/, const float* bias,
+                const float* ln_g, const float* ln_b, float* out, cudaStream_t stream);
+
+// ---- depthwise 7x7 + LayerNorm(C) -> (M, C) in OutT ---------------------------------------------------------------------
+template <typename OutT>
+int launch_dwconv_ln(const float* x, int batch, int h, int w, int c, const float* w_t /*(49,C)*/, const float* bias,
+                     const float* ln_g, const float* ln_b, OutT* out, cudaStream_t stream);
+
+// ---- LayerNorm(channels_first) + 2x2/s2 im2col pack: (B,H,W,C) f32 -> (B*(H/2)*(W/2), 4C) in OutT, K order (kh,kw,c) --
+template <typename OutT>
+int launch_ln_pack2x2(const float* x, int batch, int h, int w, int c, const float* ln_g, const float* ln_b, OutT* out,
+                      cudaStream_t stream);
+
+// ---- mean over the 7 frequency columns: (B,T',7,768) f32 -> (B,T',768) f32 ------------------------------------------
+int launch_freq_mean(const float* x, int batch, int tp, int w, int c, float* out, cudaStream_t stream);
+
+// ---- clip head: max_t + mean_t -> LN(768) -> Linear 527 -> sigmoid -------------------------------------------------
+int launch_clip_head(const float* frame_embs, int batch, int tp, const float* ln_g, const float* ln_b, const float* w,
+                     const float* bias, int n_cls, float* out, cudaStream_t stream);
+
+// ---- GEMMs: out[m,n] = epilogue(sum_k A[m,k] * W[n,k]) ---------------------------------------------------------------
+enum Epilogue : int {
+  EPI_BIAS = 0,         // acc + bias[n]
+  EPI_BIAS_GELU = 1,    // gelu_erf(acc + bias[n])
+  EPI_BIAS_RELU = 2,    // relu(acc + bias[n])
+  EPI_SCALE_RESID = 3,  // resid[m,n] + scale[n] * (acc + bias[n])      (layer-scale + residual; in-place allowed)
+};
+struct EpiParams {
+  const float* bias = nullptr;
+  const float* scale = nullptr;
+  const float* resid = nullptr;  // (M, N) f32, row stride = ldo
+};
+// fp32 SIMT GEMM (parity mode + decoder).  A (M,K) f32 row stride lda; W (N,K) f32; out (M,N) OutT row stride ldo.
+template <typename OutT>
+int launch_gemm_f32(const float* a, int64_t lda, const float* w, int m, int n, int k, Epilogue epi, const EpiParams& ep,
+                    OutT* out, int64_t ldo, cudaStream_t stream);
+
+// bf16 tcgen05 GEMM (fast mode).  A (M,K) bf16 contiguous, W (N,K) bf16 contiguous (both K-major, TMA-fed).
+struct TcGemmPlan;  // opaque: TMA descriptors + tile configuration
+template <typename OutT>
+int launch_gemm_tc(const __nv_bfloat16* a, const __nv_bfloat16* w, int m, int n, int k, Epilogue epi, const EpiParams& ep,
+                   OutT* out, int64_t ldo, cudaStream_t stream);
+int gemm_tc_init();  // resolves cuTensorMapEncodeTiled; returns 0 on success
+
+// ---- decoder / beam search ------------------------------------------------------------------------------------------------
+struct DecoderDims {
+  int rows;      // B * beam
+  int beam;
+  int tp;        // encoder frames T'
+  int max_len;   // max_pred_size
+  int vocab;
+};
+struct BeamState {
+  int* tokens[2];      // (R, max_len+1) ping-pong token histories (position 0 = task BOS id)
+  int* src_row[2];     // (R, max_len) ping-pong: physical row whose KV cache holds position p of this row's history
+  float* sum_lp;       // (R)
+  uint8_t* live;       // (R)
+  int64_t* out_preds;  // (R, max_len)
+  float* out_lp;       // (R)
+  int* done;           // [0] all-finished flag, [1] pred_size, [2] live rows remaining
+};
+// every step kernel returns immediately once done[0] is set (device-side early exit, no host sync)
+int launch_embed(const int* tokens, int pos, const float* emb, const float* pe, float* x, const DecoderDims& dd,
+                 const int* done, cudaStream_t stream);
+int launch_self_attn(const float* qkv, float* kcache, float* vcache, const int* src_row, int pos, float* attn,
+                     const DecoderDims& dd, const int* done, cudaStream_t stream);
+int launch_cross_attn(const float* q, const float* ck, const float* cv, int64_t kv_stride, const int* lens, float* attn,
+                      const DecoderDims& dd, const int* done, cudaStream_t stream);
+int launch_add_ln(float* x, const float* delta, const float* g, const float* b, int rows, const int* done,
+                  cudaStream_t stream);
+int launch_beam_init(const int64_t* bos_ids, BeamState st, const DecoderDims& dd, cudaStream_t stream);
+int launch_beam_step(float* logits, const uint8_t* forbid, BeamState st, int step, int cur, int min_len,
+                     const DecoderDims& dd, cudaStream_t stream);
+int launch_beam_finalize(BeamState st, int64_t* best_preds, float* best_lp, int* best_len, const DecoderDims& dd,
+                         cudaStream_t stream);
+
+// global launch counter (reported through cnb_launch_count)
+void count_launch();
+
+}  // namespace cnb

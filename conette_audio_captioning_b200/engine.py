@@ -1,0 +1,218 @@
+"""Thin torch-facing wrapper over the C ABI: one ``Engine`` = one ``cnb_handle`` on one GPU.
+
+PyTorch is used here only for device memory, streams and dtype bookkeeping; all arithmetic happens inside
+libconette_b200.so.  The methods mirror the reference's operator seams:
+
+  ``encoder``        ConvNeXt.forward                 reference nn/encoders/convnext.py:264-336
+  ``decode``         projection + generate()          reference pl_modules/conette.py:452-467, nn/decoding/beam.py:22-227
+  ``decoder_logits`` AACTransformerDecoder.forward    reference nn/decoders/aac_tfmer.py:71-118 (teacher-forced, parity only)
+  ``caption``        CoNeTTEModel.forward minus text  reference huggingface/model.py:185-261
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+N_TAGS = 527
+EOS_ID = 2
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class Engine:
+    def __init__(self, state_dict: Dict[str, Tensor], vocab_size: int, device: int = 0, precision: str = "fast",
+                 enc_chunk: int = 0) -> None:
+        if not torch.cuda.is_available():
+            raise _lib.CnbError("conette_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device)
+        self.vocab_size = int(vocab_size)
+        self.precision = precision
+        cfg = _lib.Config()
+        cfg.abi_version = _lib.ABI_VERSION
+        cfg.device = device
+        cfg.vocab_size = self.vocab_size
+        cfg.precision = {"fast": _lib.PRECISION_FAST, "parity": _lib.PRECISION_PARITY}[precision]
+        cfg.enc_chunk = enc_chunk
+        handle = C.c_void_p()
+        _lib.check(self.lib.cnb_create(C.byref(cfg), C.byref(handle)))
+        self.handle = handle
+        dtype_code = {torch.float32: _lib.DTYPE_F32, torch.int64: _lib.DTYPE_I64, torch.bool: _lib.DTYPE_BOOL,
+                      torch.uint8: _lib.DTYPE_U8}
+        for name, t in state_dict.items():
+            if not isinstance(t, Tensor) or t.dtype not in dtype_code:
+                continue
+            t = t.detach().to("cpu").contiguous()
+            shape = (C.c_int64 * max(t.ndim, 1))(*t.shape)
+            _lib.check(self.lib.cnb_load_weight(self.handle, name.encode(), t.data_ptr(), dtype_code[t.dtype], t.ndim, shape))
+        _lib.check(self.lib.cnb_finalize_weights(self.handle))
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            self.lib.cnb_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- helpers ------------------------------------------------------------------------------------------------------
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _dev(self, t: Tensor, dtype: torch.dtype) -> Tensor:
+        return t.to(device=self.device, dtype=dtype).contiguous()
+
+    def launch_count(self) -> int:
+        return int(self.lib.cnb_launch_count(self.handle))
+
+    def device_bytes(self) -> int:
+        return int(self.lib.cnb_device_bytes(self.handle))
+
+    # ---- stages -------------------------------------------------------------------------------------------------------
+    def frontend(self, wav: Tensor, apply_bn: bool = True) -> Tensor:
+        """(B, N) f32 -> (B, T, 224) log-mel [dB], optionally through bn0."""
+        wav = self._dev(wav, torch.float32)
+        b, n = wav.shape
+        t, _, _ = _lib.geometry(n)
+        out = torch.empty(b, t, 224, device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.cnb_frontend(self.handle, wav.data_ptr(), b, n, int(apply_bn), out.data_ptr(), self._stream()))
+        return out
+
+    def encoder(self, wav: Tensor, with_tags: bool = True) -> Tuple[Tensor, Optional[Tensor]]:
+        """(B, N) f32 -> frame_embs (B, T', 768), clip_probs (B, 527)."""
+        wav = self._dev(wav, torch.float32)
+        b, n = wav.shape
+        _, _, tp = _lib.geometry(n)
+        fe = torch.empty(b, tp, 768, device=self.device, dtype=torch.float32)
+        clip = torch.empty(b, N_TAGS, device=self.device, dtype=torch.float32) if with_tags else None
+        _lib.check(self.lib.cnb_encoder(self.handle, wav.data_ptr(), b, n, fe.data_ptr(), _ptr(clip), self._stream()))
+        return fe, clip
+
+    def encoder_tap(self, wav: Tensor, kind: int, stage: int = 0, block: int = 0) -> Tensor:
+        """Intermediate activation (fp32, NHWC) for stage-isolated parity tests."""
+        wav = self._dev(wav, torch.float32)
+        b, n = wav.shape
+        t, hs, _ = _lib.geometry(n)
+        dims, widths = (96, 192, 384, 768), (56, 28, 14, 7)
+        if kind == _lib.TAP_LOGMEL_BN:
+            shape = (b, t, 224)
+        elif kind == _lib.TAP_STEM:
+            shape = (b, hs[0], 56, 96)
+        else:
+            shape = (b, hs[stage], widths[stage], dims[stage])
+        out = torch.empty(shape, device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.cnb_encoder_tap(self.handle, wav.data_ptr(), b, n, kind, stage, block, out.data_ptr(),
+                                            out.numel(), self._stream()))
+        return out
+
+    def debug_gemm(self, a: Tensor, w: Tensor, bias: Tensor, scale: Optional[Tensor] = None, resid: Optional[Tensor] = None,
+                   epi: int = 0, use_tc: bool = True, out_bf16: bool = False) -> Tensor:
+        """Test hook: out = epi(a @ w.T) through the tcgen05 (bf16) or CUDA-core (fp32) GEMM kernel."""
+        a, w, bias = self._dev(a, torch.float32), self._dev(w, torch.float32), self._dev(bias, torch.float32)
+        scale = None if scale is None else self._dev(scale, torch.float32)
+        resid = None if resid is None else self._dev(resid, torch.float32)
+        m, k = a.shape
+        n = w.shape[0]
+        out = torch.empty(m, n, device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.cnb_debug_gemm(self.handle, a.data_ptr(), w.data_ptr(), bias.data_ptr(), _ptr(scale), _ptr(resid),
+                                           m, n, k, epi, int(use_tc), int(out_bf16), out.data_ptr(), self._stream()))
+        return out
+
+    def _alloc_outputs(self, b: int, beam: int, max_len: int):
+        dev = self.device
+        return (torch.empty(b, max_len, device=dev, dtype=torch.int64), torch.empty(b, device=dev, dtype=torch.float32),
+                torch.empty(b, beam, max_len, device=dev, dtype=torch.int64),
+                torch.empty(b, beam, device=dev, dtype=torch.float32), torch.empty(2 + b, device=dev, dtype=torch.int32))
+
+    @staticmethod
+    def _trim(preds: Tensor, lprobs: Tensor, mult_preds: Tensor, mult_lprobs: Tensor, info: Tensor):
+        """Output trimming of reference beam.py:205-225 (one device->host read of the tiny info vector)."""
+        info_h = info.tolist()
+        pred_size = info_h[0]
+        best_len = max(info_h[2:]) + 1
+        return (preds[:, : min(best_len, pred_size)].contiguous(), lprobs, mult_preds[:, :, :pred_size].contiguous(),
+                mult_lprobs)
+
+    def decode(self, frame_embs: Tensor, lens: Tensor, bos_ids: Tensor, forbid_mask: Optional[Tensor], beam: int = 3,
+               min_len: int = 3, max_len: int = 20):
+        """frame_embs (B, T', 768) -> (preds, lprobs, mult_preds, mult_lprobs) like reference ``generate``."""
+        fe = self._dev(frame_embs, torch.float32)
+        b, tp, _ = fe.shape
+        lens = self._dev(lens, torch.int32)
+        bos = self._dev(bos_ids, torch.int64)
+        forbid = None if forbid_mask is None else self._dev(forbid_mask, torch.uint8)
+        outs = self._alloc_outputs(b, beam, max_len)
+        _lib.check(self.lib.cnb_decode(self.handle, fe.data_ptr(), lens.data_ptr(), bos.data_ptr(), _ptr(forbid), b, tp, beam,
+                                       min_len, max_len, *[o.data_ptr() for o in outs], self._stream()))
+        return self._trim(*outs)
+
+    def decoder_logits(self, frame_embs: Tensor, lens: Tensor, tokens: Tensor) -> Tensor:
+        """Teacher-forced logits (B, steps, V) for given token prefixes (B, steps)."""
+        fe = self._dev(frame_embs, torch.float32)
+        b, tp, _ = fe.shape
+        lens = self._dev(lens, torch.int32)
+        tokens = self._dev(tokens, torch.int64)
+        steps = tokens.shape[1]
+        out = torch.empty(b, steps, self.vocab_size, device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.cnb_decoder_logits(self.handle, fe.data_ptr(), lens.data_ptr(), tokens.data_ptr(), b, tp, steps,
+                                               out.data_ptr(), self._stream()))
+        return out
+
+    def caption(self, wav: Tensor, x_lens: Optional[Tensor], bos_ids: Tensor, forbid_mask: Optional[Tensor], beam: int = 3,
+                min_len: int = 3, max_len: int = 20, with_tags: bool = True, trim: bool = True):
+        """Device-resident path: wav (B, N) on the GPU -> ids; returns (preds, lprobs, mult_preds, mult_lprobs, clip_probs)."""
+        wav = self._dev(wav, torch.float32)
+        b, n = wav.shape
+        bos = self._dev(bos_ids, torch.int64)
+        forbid = None if forbid_mask is None else self._dev(forbid_mask, torch.uint8)
+        xl = None if x_lens is None else x_lens.to("cpu", torch.int64).contiguous()
+        outs = self._alloc_outputs(b, beam, max_len)
+        clip = torch.empty(b, N_TAGS, device=self.device, dtype=torch.float32) if with_tags else None
+        _lib.check(self.lib.cnb_caption(self.handle, wav.data_ptr(), _ptr(xl), bos.data_ptr(), _ptr(forbid), b, n, beam,
+                                        min_len, max_len, *[o.data_ptr() for o in outs], _ptr(clip), self._stream()))
+        if not trim:
+            return (*outs, clip)
+        return (*self._trim(*outs), clip)
+
+    def caption_host(self, wav: Tensor, x_lens: Optional[Tensor], bos_ids: Tensor, forbid_mask: Optional[Tensor],
+                     beam: int = 3, min_len: int = 3, max_len: int = 20, with_tags: bool = True, out: Optional[dict] = None):
+        """End-to-end path with HOST buffers: H2D of the waveforms and D2H of the ids happen inside the C call."""
+        assert wav.device.type == "cpu" and wav.dtype == torch.float32 and wav.is_contiguous()
+        b, n = wav.shape
+        bos = bos_ids.to("cpu", torch.int64).contiguous()
+        forbid = None if forbid_mask is None else forbid_mask.to("cpu", torch.uint8).contiguous()
+        xl = None if x_lens is None else x_lens.to("cpu", torch.int64).contiguous()
+        if out is None:
+            out = self.alloc_host_outputs(b, beam, max_len, with_tags)
+        clip = out.get("clip_probs")
+        _lib.check(self.lib.cnb_caption_host(self.handle, wav.data_ptr(), _ptr(xl), bos.data_ptr(), _ptr(forbid), b, n, beam,
+                                             min_len, max_len, out["preds"].data_ptr(), out["lprobs"].data_ptr(),
+                                             out["mult_preds"].data_ptr(), out["mult_lprobs"].data_ptr(),
+                                             out["info"].data_ptr(), _ptr(clip)))
+        preds, lprobs, mult_preds, mult_lprobs = self._trim(out["preds"], out["lprobs"], out["mult_preds"],
+                                                            out["mult_lprobs"], out["info"])
+        return preds, lprobs, mult_preds, mult_lprobs, clip
+
+    @staticmethod
+    def alloc_host_outputs(b: int, beam: int, max_len: int, with_tags: bool = True) -> dict:
+        pin = dict(pin_memory=True)
+        out = {
+            "preds": torch.empty(b, max_len, dtype=torch.int64, **pin),
+            "lprobs": torch.empty(b, dtype=torch.float32, **pin),
+            "mult_preds": torch.empty(b, beam, max_len, dtype=torch.int64, **pin),
+            "mult_lprobs": torch.empty(b, beam, dtype=torch.float32, **pin),
+            "info": torch.empty(2 + b, dtype=torch.int32, **pin),
+        }
+        if with_tags:
+            out["clip_probs"] = torch.empty(b, N_TAGS, dtype=torch.float32, **pin)
+        return out

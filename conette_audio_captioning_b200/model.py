@@ -1,0 +1,146 @@
+"""``CoNeTTEModel``: drop-in for the reference's public inference API, backed by the sm_100a CUDA library.
+
+Mirrors ``CoNeTTEModel.forward / __call__`` of the reference (huggingface/model.py:185-289): same keyword arguments, same
+task validation and error messages, same output dictionary (``cands, preds, lprobs, mult_cands, mult_preds, mult_lprobs,
+tasks`` and, when preprocessing, ``tags_probs, tags``).  Waveform loading / mono-mix / padding and ids->text stay in
+Python as in the reference; everything between the padded waveform batch and the token ids runs in libconette_b200.so.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Iterable, List, Optional, Sequence, Union
+
+import torch
+from torch import Size, Tensor
+
+from .config import CoNeTTEConfig
+from .engine import Engine
+from .preprocessor import load_resample
+from .synth import make_forbid_rep_mask
+from .tokenizer import IdTokenizer
+
+
+class CoNeTTEModel:
+    def __init__(
+        self,
+        config: Optional[CoNeTTEConfig],
+        state_dict: Dict[str, Tensor],
+        tokenizer: Union[Sequence[str], Any],
+        device: Union[int, str, torch.device] = 0,
+        precision: str = "fast",
+        enc_chunk: int = 0,
+        audioset_idx_to_name: Optional[Dict[int, str]] = None,
+    ) -> None:
+        self.config = config or CoNeTTEConfig()
+        if isinstance(tokenizer, (list, tuple)):
+            tokenizer = IdTokenizer(tokenizer)
+        self.tokenizer = tokenizer  # anything with decode_rec / get_vocab_size / has / token_to_id
+        vocab = tokenizer.get_vocab_size()
+        if state_dict["model.decoder.classifier.weight"].shape[0] != vocab:
+            raise ValueError("vocabulary size does not match decoder.classifier.weight")
+        dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        self.engine = Engine(state_dict, vocab, dev.index or 0, precision, enc_chunk)
+        self.task_id_to_token_id = state_dict["model.task_id_to_token_id"].to("cpu", torch.int64)
+        fm = state_dict.get("model.forbid_rep_mask")
+        self.forbid_rep_mask = None if fm is None else fm.to("cpu", torch.uint8)
+        self._itos = [tokenizer.id_to_token(i) for i in range(vocab)]
+        self.audioset_idx_to_name = audioset_idx_to_name or {i: f"class{i}" for i in range(527)}
+
+    # ---- reference properties (model.py:109-115) -------------------------------------------------------------------
+    @property
+    def default_task(self) -> str:
+        return next(iter(self.config.task_names))
+
+    @property
+    def tasks(self) -> List[str]:
+        return list(self.config.task_names)
+
+    # ---- helpers ---------------------------------------------------------------------------------------------------
+    def _task_token_ids(self, dataset_lst: List[str], source_lst: List[Optional[str]]) -> Tensor:
+        """reference ``batch_to_task_token_ids`` (pl_modules/conette.py:486-525)."""
+        mode = self.config.task_mode
+        if mode == "none":
+            return torch.full((len(dataset_lst),), 1, dtype=torch.int64)
+        names = list(self.config.task_names)
+        if mode == "ds":
+            idx = [names.index(ds) for ds in dataset_lst]
+        else:
+            idx = [names.index(ds if src is None else f"{ds}_{src}".lower()) for ds, src in zip(dataset_lst, source_lst)]
+        return self.task_id_to_token_id[torch.tensor(idx, dtype=torch.int64)]
+
+    def _forbid_mask(self, forbid_rep_mode: Optional[str]) -> Optional[Tensor]:
+        if forbid_rep_mode is None:
+            return self.forbid_rep_mask
+        mask = make_forbid_rep_mask(self._itos, forbid_rep_mode)  # raises ValueError on unknown modes
+        return None if mask is None else mask.to(torch.uint8)
+
+    # ---- forward (reference model.py:185-261) ----------------------------------------------------------------------------
+    def __call__(
+        self,
+        x: Union[Tensor, str, Iterable[str], Iterable[Tensor]],
+        sr: Union[None, int, Iterable[int]] = None,
+        x_shapes: Union[Tensor, None, List[Size]] = None,
+        preprocess: bool = True,
+        threshold: Union[float, Tensor] = 0.3,
+        task: Union[str, List[str], None] = None,
+        beam_size: Optional[int] = None,
+        min_pred_size: Optional[int] = None,
+        max_pred_size: Optional[int] = None,
+        forbid_rep_mode: Optional[str] = None,
+    ) -> Dict[str, Any]:
+        if preprocess:
+            wav, x_lens = load_resample(x, sr, x_shapes)
+            bsize = wav.shape[0]
+        else:
+            assert isinstance(x, Tensor) and isinstance(x_shapes, Tensor)
+            bsize = len(x)
+
+        if task is None:
+            tasks = [self.default_task] * bsize
+        elif isinstance(task, str):
+            tasks = [task] * bsize
+        elif len(task) != bsize:
+            raise ValueError(f"Invalid number of tasks with input. (found {len(task)} tasks but {bsize} elements)")
+        else:
+            tasks = list(task)
+        for t in tasks:
+            if t not in self.config.task_names:
+                raise ValueError(f"Invalid argument tasks={tasks}. (task {t} is not in {self.config.task_names})")
+        dataset_lst, source_lst = [], []
+        for t in tasks:
+            parts = t.split("_")
+            dataset_lst.append(parts[0])
+            source_lst.append("_".join(parts[1:]) if len(parts) >= 2 else None)
+        bos_ids = self._task_token_ids(dataset_lst, source_lst)
+
+        beam = self.config.beam_size if beam_size is None else beam_size
+        min_len = self.config.min_pred_size if min_pred_size is None else min_pred_size
+        max_len = self.config.max_pred_size if max_pred_size is None else max_pred_size
+        assert beam > 0  # reference beam.py:57-58
+        assert min_len >= 0
+        forbid = self._forbid_mask(forbid_rep_mode)
+
+        if preprocess:
+            preds, lprobs, mult_preds, mult_lprobs, clip_probs = self.engine.caption_host(
+                wav, x_lens, bos_ids, forbid, beam, min_len, max_len, with_tags=True)
+        else:
+            lens = x_shapes[:, 1].to(torch.int32)  # FrameIdentEncoder: lens = audio_shape[:, 1] (nn/encoders/ident.py:14-34)
+            preds, lprobs, mult_preds, mult_lprobs = (
+                t.cpu() for t in self.engine.decode(x, lens, bos_ids, forbid, beam, min_len, max_len))
+            clip_probs = None
+
+        outs: Dict[str, Any] = {
+            "cands": self.tokenizer.decode_rec(preds),
+            "preds": preds,
+            "lprobs": lprobs,
+            "mult_cands": self.tokenizer.decode_rec(mult_preds),
+            "mult_preds": mult_preds,
+            "mult_lprobs": mult_lprobs,
+            "tasks": tasks,
+        }
+        if clip_probs is not None:
+            outs["tags_probs"] = clip_probs
+            hot = clip_probs >= threshold  # torchoutil probs_to_names (reference model.py:203-204)
+            outs["tags"] = [[self.audioset_idx_to_name[int(i)] for i in row.nonzero().flatten().tolist()] for row in hot]
+        return outs
+
+    forward = __call__

@@ -1,0 +1,86 @@
+"""Host mirror of the reference ``CoNeTTEPreprocessor._load_resample`` (huggingface/preprocessor.py:82-154).
+
+Same argument forms and error behaviour: str / list[str] paths, Tensor (N,) / (C, N) [ONE clip with C channels] /
+(B, C, N), list[Tensor (C, N_i)]; ``sr`` int / list / None; ``x_shapes`` overrides the inferred lengths and may not be
+combined with resampling.  Output: mono waveforms right-zero-padded to the batch max (B, Nmax) f32 on the HOST in pinned
+memory (the single H2D copy happens inside ``cnb_caption_host``) plus the true lengths (B,) i64.
+
+Resampling (only when sr != 32 kHz; never in the benchmark configs) still calls ``torchaudio.functional.resample`` on the
+host: SURVEY.md 8(f) rank 1 lists the fused GPU polyphase resampler as the next row to build.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence, Tuple, Union
+
+import torch
+from torch import Size, Tensor
+
+TARGET_SR = 32_000
+
+
+def _load(path: str) -> Tuple[Tensor, int]:
+    import torchaudio
+
+    return torchaudio.load(path)  # type: ignore[return-value]
+
+
+def _is_iterable_str(x) -> bool:
+    return isinstance(x, str) or (isinstance(x, Iterable) and not isinstance(x, Tensor) and all(isinstance(xi, str) for xi in x))
+
+
+def load_resample(
+    x: Union[Tensor, str, Iterable[str], Iterable[Tensor]],
+    sr: Union[None, int, Iterable[int]] = None,
+    x_shapes: Union[Tensor, None, Sequence[Size]] = None,
+) -> Tuple[Tensor, Tensor]:
+    if _is_iterable_str(x):
+        if isinstance(x, str):
+            x = [x]
+        loaded = [_load(xi) for xi in x]
+        x = [w for w, _ in loaded]
+        sr = [s for _, s in loaded]
+    else:
+        if isinstance(x, Tensor):
+            if x.ndim == 1:
+                x = x.unsqueeze(0).unsqueeze(1)
+            elif x.ndim == 2:
+                x = x.unsqueeze(0)  # (channels, time) = ONE clip (reference preprocessor.py:99-100)
+            elif x.ndim == 3:
+                pass
+            else:
+                raise ValueError(f"Invalid argument shape x.shape={tuple(x.shape)}.")
+        else:
+            x = list(x)  # type: ignore[arg-type]
+        if isinstance(sr, int):
+            sr = [sr]
+        elif sr is None:
+            sr = [TARGET_SR]
+        else:
+            sr = list(sr)
+
+    if len(sr) == 1 and len(x) != len(sr):
+        sr = list(sr) * len(x)
+    assert len(x) == len(sr) and len(x) > 0
+
+    if any(sri != TARGET_SR for sri in sr):
+        if x_shapes is not None:
+            raise ValueError(f"Invalid argument x_shapes={x_shapes}.")
+        from torchaudio.functional import resample
+
+        if isinstance(x, Tensor) and all(s == sr[0] for s in sr):
+            x = resample(x.float(), sr[0], TARGET_SR)
+        else:
+            x = [resample(xi.float(), sri, TARGET_SR) for xi, sri in zip(x, sr)]
+
+    clips: List[Tensor] = [xi.float().mean(dim=0) for xi in x]  # mono mix (preprocessor.py:143-146)
+    if x_shapes is None:
+        lens = torch.tensor([c.shape[-1] for c in clips], dtype=torch.int64)
+    else:
+        xs = torch.as_tensor(x_shapes)
+        lens = xs.reshape(len(clips), -1)[:, -1].to(torch.int64).cpu()  # last column = time length (convnext.py:312)
+    n_max = max(c.shape[-1] for c in clips)
+    pin = torch.cuda.is_available()
+    out = torch.zeros(len(clips), n_max, dtype=torch.float32, pin_memory=pin)
+    for i, c in enumerate(clips):
+        out[i, : c.shape[-1]] = c  # right zero-pad to the batch max (nn/functional/pad.py:11-17)
+    return out, lens

@@ -1,0 +1,119 @@
+/* conette_b200 -- C ABI of the B200-native CoNeTTE inference hot path.
+ *
+ * The reference (Labbeti/conette-audio-captioning) is pure Python/PyTorch and has no FFI of its own; the operator seams
+ * this library replaces are:
+ *   S1  ConvNeXt.forward(input_, input_shapes) -> {frame_embs, frame_embs_lens, clipwise_output}
+ *         reference src/conette/nn/encoders/convnext.py:264-336           -> cnb_frontend / cnb_encoder
+ *   S2  generate(decoder, pad_id, bos_id, eos_id, vocab_size, frame_embs, frame_embs_pad_mask, beam_size,
+ *                min_pred_size, max_pred_size, forbid_rep_mask) -> 4-tuple
+ *         reference src/conette/nn/decoding/beam.py:22-227                  -> cnb_decode
+ *       (with the projection of pl_modules/conette.py:452-467 + common.py:59-78 folded in front of it)
+ *   S3  AACDecoder.__call__ (decoding/common.py:9-29, nn/decoders/aac_tfmer.py:71-118), replaced wholesale by a
+ *       KV-cached step; exposed only for stage-isolated parity as cnb_decoder_logits (teacher-forced logits).
+ *   S1+S2 behind CoNeTTEModel.forward (huggingface/model.py:185-261)        -> cnb_caption / cnb_caption_host
+ *   state-dict tensors by the reference's names       -> cnb_load_weight
+ *
+ * Conventions: plain C types only; every function returns 0 on success, a negative code on failure and records a
+ * message retrievable with cnb_last_error().  Unless a name ends in _host, pointers are DEVICE pointers owned by the
+ * caller (e.g. torch tensors) and work is enqueued on the given CUDA stream (a cudaStream_t passed as void*, NULL = legacy
+ * default stream) without synchronising.  The library owns only its packed weights and an internal workspace.
+ * There is no CPU fallback: every entry point needs a CUDA device of compute capability 10.x.
+ */
+#ifndef CONETTE_B200_H_
+#define CONETTE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNB_ABI_VERSION 1
+
+typedef struct cnb_handle cnb_handle;
+
+typedef struct cnb_config {
+  int32_t abi_version;   /* must be CNB_ABI_VERSION */
+  int32_t device;        /* CUDA device ordinal */
+  int32_t vocab_size;    /* V: rows of decoder.emb_layer.weight / decoder.classifier.weight */
+  int32_t precision;     /* 0 = fast (bf16 tcgen05 encoder GEMMs, fp32 accumulate, fp32 residual stream)
+                            1 = parity (fp32 CUDA-core GEMMs everywhere); the decoder is fp32 in both modes */
+  int32_t enc_chunk;     /* clips encoded per pass (0 = library default); bounds workspace, keeps tiles in L2 */
+  int32_t reserved[3];
+} cnb_config;
+
+enum { CNB_PRECISION_FAST = 0, CNB_PRECISION_PARITY = 1 };
+enum { CNB_DTYPE_F32 = 0, CNB_DTYPE_I64 = 1, CNB_DTYPE_BOOL = 2, CNB_DTYPE_U8 = 3 };
+/* encoder tap points for stage-isolated parity (cnb_encoder_tap): activation returned as fp32, NHWC */
+enum { CNB_TAP_LOGMEL_BN = 0, CNB_TAP_STEM = 1, CNB_TAP_BLOCK = 2, CNB_TAP_DOWN = 3, CNB_TAP_DWLN = 4 };
+
+const char* cnb_last_error(void);
+int cnb_abi_version(void);
+
+int cnb_create(const cnb_config* cfg, cnb_handle** out);
+int cnb_destroy(cnb_handle* h);
+
+/* Stage one tensor of the reference state dict (HOST pointer, contiguous, row-major). Names are the reference's own
+ * (e.g. "preprocessor.encoder.stages.0.0.pwconv1.weight", "model.decoder.layers.3.linear1.bias"); tensors the CUDA path
+ * does not consume (tokenizer state, task ids, forbid mask, num_batches_tracked) are accepted and ignored. */
+int cnb_load_weight(cnb_handle* h, const char* name, const void* host_ptr, int32_t dtype, int32_t ndim,
+                    const int64_t* shape);
+/* Validate that every required tensor was staged, pack (transpose / bf16 / BN fold / sparse mel) and upload. */
+int cnb_finalize_weights(cnb_handle* h);
+
+/* Output geometry for a padded batch of n_samples: STFT frames T, ConvNeXt stage heights, output frames T'. */
+int cnb_geometry(int64_t n_samples, int32_t* n_stft_frames, int32_t stage_heights[4], int32_t* n_out_frames);
+
+/* S1a front-end: wav (B, N) f32 -> log-mel (B, T, 224) f32, optionally through eval BatchNorm (bn0). */
+int cnb_frontend(cnb_handle* h, const float* wav, int32_t batch, int64_t n_samples, int32_t apply_bn, float* logmel_out,
+                 void* stream);
+/* S1 encoder: wav (B, N) f32 -> frame_embs (B, T', 768) f32 [time-major, i.e. the reference's frame_embs transposed as
+ * preprocessor.py:64 does] and, if clip_probs_out != NULL, AudioSet tag probabilities (B, 527). */
+int cnb_encoder(cnb_handle* h, const float* wav, int32_t batch, int64_t n_samples, float* frame_embs_out,
+                float* clip_probs_out, void* stream);
+/* Debug/parity: run the encoder on (B <= enc_chunk) clips and copy one intermediate activation out (fp32, NHWC). */
+int cnb_encoder_tap(cnb_handle* h, const float* wav, int32_t batch, int64_t n_samples, int32_t tap_kind, int32_t stage,
+                    int32_t block, float* out, int64_t out_capacity_elems, void* stream);
+
+/* S2 projection + beam search: frame_embs (B, T', 768) f32, lens (B) i32 valid frames, bos_ids (B) i64 task BOS token,
+ * forbid_mask (V) u8 or NULL.  Outputs (device): preds (B, max_len) i64 best beam padded with 0; lprobs (B) f32;
+ * mult_preds (B, beam, max_len) i64; mult_lprobs (B, beam) f32; info (2 + B) i32 = {pred_size, reserved,
+ * first-EOS index of the best beam per clip (max_len if none)}.  The caller trims mult_preds to pred_size and preds to
+ * max(first-EOS)+1 exactly as beam.py:205-225 does. */
+int cnb_decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, const int64_t* bos_ids,
+               const uint8_t* forbid_mask, int32_t batch, int32_t n_frames, int32_t beam, int32_t min_len, int32_t max_len,
+               int64_t* preds_out, float* lprobs_out, int64_t* mult_preds_out, float* mult_lprobs_out, int32_t* info_out,
+               void* stream);
+/* S3 (parity only): teacher-forced decoder logits. tokens (B, steps) i64 -> logits (B, steps, V) f32. */
+int cnb_decoder_logits(cnb_handle* h, const float* frame_embs, const int32_t* lens, const int64_t* tokens, int32_t batch,
+                       int32_t n_frames, int32_t steps, float* logits_out, void* stream);
+
+/* S1+S2: waveform -> token ids, all buffers on the device. x_lens_host (B) i64 = true sample counts (HOST; NULL = all
+ * n_samples) from which frame lens = round_half_even(len / (N // T')) are derived (convnext.py:312-315).
+ * frame_embs_out / clip_probs_out may be NULL. */
+int cnb_caption(cnb_handle* h, const float* wav, const int64_t* x_lens_host, const int64_t* bos_ids,
+                const uint8_t* forbid_mask, int32_t batch, int64_t n_samples, int32_t beam, int32_t min_len, int32_t max_len,
+                int64_t* preds_out, float* lprobs_out, int64_t* mult_preds_out, float* mult_lprobs_out, int32_t* info_out,
+                float* clip_probs_out, void* stream);
+/* Same with HOST buffers for everything: host->device copy of the waveforms, compute, device->host copy of the results
+ * and a stream synchronise all happen inside the call (this is the end-to-end entry the Python wrapper uses). */
+int cnb_caption_host(cnb_handle* h, const float* wav_host, const int64_t* x_lens_host, const int64_t* bos_ids_host,
+                     const uint8_t* forbid_mask_host, int32_t batch, int64_t n_samples, int32_t beam, int32_t min_len,
+                     int32_t max_len, int64_t* preds_out_host, float* lprobs_out_host, int64_t* mult_preds_out_host,
+                     float* mult_lprobs_out_host, int32_t* info_out_host, float* clip_probs_out_host);
+
+/* Test hook: one GEMM with a fused epilogue, out (M,N) f32 = epi(A (M,K) f32 x W (N,K) f32 ^T). epi: 0 bias, 1 bias+GELU,
+ * 2 bias+ReLU, 3 resid + scale*(acc+bias).  use_tc=1 runs the bf16 tcgen05 kernel (operands rounded to bf16 first;
+ * out_bf16=1 also rounds the result through the bf16 epilogue), use_tc=0 the fp32 CUDA-core kernel. */
+int cnb_debug_gemm(cnb_handle* h, const float* a, const float* w, const float* bias, const float* scale, const float* resid,
+                   int32_t m, int32_t n, int32_t k, int32_t epi, int32_t use_tc, int32_t out_bf16, float* out, void* stream);
+
+/* Number of kernels launched by this handle since creation (bench.py reports the per-step delta as gpu_launches). */
+int64_t cnb_launch_count(const cnb_handle* h);
+/* Bytes of device memory currently held (weights + workspace). */
+int64_t cnb_device_bytes(const cnb_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONETTE_B200_H_ */

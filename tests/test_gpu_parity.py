@@ -1,0 +1,339 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures.
+
+Tolerances (restated where asserted):
+  log-mel                       <= 1e-2 dB abs where the mel power is well above amin
+  parity mode (fp32 GEMMs)      activations <= 2e-4 rel-L2 per stage, frame_embs <= 5e-4 rel-L2
+  fast mode (bf16 tcgen05)      frame_embs <= 5e-3 rel-L2
+  decoder logits                <= 1e-4 abs (+1e-4 rel) given identical frame_embs
+  token ids                     bit-exact (decoder fed the oracle's frame_embs; end-to-end in parity mode)
+"""
+import numpy as np
+import pytest
+import torch
+
+from conette_audio_captioning_b200 import synth
+
+from golden_util import assert_weights_match, load, t
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def eng_parity(small_sd):
+    from conette_audio_captioning_b200.engine import Engine
+
+    e = Engine(small_sd, vocab_size=small_sd["model.decoder.classifier.weight"].shape[0], precision="parity", enc_chunk=4)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def eng_fast(small_sd):
+    from conette_audio_captioning_b200.engine import Engine
+
+    e = Engine(small_sd, vocab_size=small_sd["model.decoder.classifier.weight"].shape[0], precision="fast", enc_chunk=4)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def oracle_taps(small_sd):
+    """CPU oracle activations for a 2-clip, 1.5 s batch whose second clip has a zero-padded (digital silence) tail."""
+    from oracle import restate
+
+    n = 48000
+    wav = synth.make_audio(2, n, seed=21)[:, 0].contiguous()
+    wav[1, 30000:] = 0.0
+    x_lens = torch.tensor([n, 30000])
+    taps = {}
+    out = restate.encoder(small_sd, wav, x_lens, taps)
+    return wav, x_lens, taps, out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GEMM kernels in isolation
+# ----------------------------------------------------------------------------------------------------------------------
+GEMM_SHAPES = [(300, 384, 96), (128, 96, 384), (1000, 768, 192), (257, 192, 768), (130, 1536, 384), (64, 384, 1536),
+               (77, 3072, 768), (333, 768, 3072), (512, 256, 768), (90, 192, 384)]
+
+
+def _gemm_ref(a, w, bias, scale, resid, epi, bf16_in):
+    if bf16_in:
+        a, w = a.bfloat16().float(), w.bfloat16().float()
+    acc = a.double() @ w.double().T + bias.double()
+    if epi == 1:
+        acc = torch.nn.functional.gelu(acc)
+    elif epi == 2:
+        acc = torch.relu(acc)
+    elif epi == 3:
+        acc = resid.double() + scale.double() * acc
+    return acc.float()
+
+
+@pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
+@pytest.mark.parametrize("epi", [0, 1, 3])
+def test_tcgen05_gemm(eng_fast, m, n, k, epi):
+    g = torch.Generator().manual_seed(m * 7 + n + k + epi)
+    a = torch.randn(m, k, generator=g)
+    w = torch.randn(n, k, generator=g) / k**0.5
+    bias, scale, resid = torch.randn(n, generator=g), torch.rand(n, generator=g), torch.randn(m, n, generator=g)
+    out = eng_fast.debug_gemm(a, w, bias, scale, resid, epi=epi, use_tc=True).cpu()
+    ref = _gemm_ref(a, w, bias, scale, resid, epi, bf16_in=True)
+    torch.testing.assert_close(out, ref, rtol=2e-4, atol=2e-4)  # same bf16 operands, fp32 accumulation
+
+
+@pytest.mark.parametrize("m,n,k", [(300, 384, 96), (257, 192, 768)])
+def test_tcgen05_gemm_bf16_out(eng_fast, m, n, k):
+    g = torch.Generator().manual_seed(5)
+    a, w, bias = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g) / k**0.5, torch.randn(n, generator=g)
+    out = eng_fast.debug_gemm(a, w, bias, epi=1, use_tc=True, out_bf16=True).cpu()
+    ref = _gemm_ref(a, w, bias, None, None, 1, bf16_in=True)
+    torch.testing.assert_close(out, ref.bfloat16().float(), rtol=1e-2, atol=1e-2)
+    assert rel_l2(out, ref) < 4e-3
+
+
+@pytest.mark.parametrize("m,n,k", [(300, 384, 96), (37, 318, 256), (192, 256, 2048), (1000, 192, 768), (5, 768, 256)])
+@pytest.mark.parametrize("epi", [0, 1, 2, 3])
+def test_fp32_gemm(eng_parity, m, n, k, epi):
+    g = torch.Generator().manual_seed(m + n + k + epi)
+    a = torch.randn(m, k, generator=g)
+    w = torch.randn(n, k, generator=g) / k**0.5
+    bias, scale, resid = torch.randn(n, generator=g), torch.rand(n, generator=g), torch.randn(m, n, generator=g)
+    out = eng_parity.debug_gemm(a, w, bias, scale, resid, epi=epi, use_tc=False).cpu()
+    ref = _gemm_ref(a, w, bias, scale, resid, epi, bf16_in=False)
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-4)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# front-end
+# ----------------------------------------------------------------------------------------------------------------------
+def test_frontend_logmel_vs_golden(eng_parity, small_sd):
+    fx = load("encoder.npz")
+    assert_weights_match(small_sd, fx)
+    lm = eng_parity.frontend(t(fx["wav"]), apply_bn=False).cpu()
+    ref = t(fx["logmel"])
+    assert lm.shape == ref.shape
+    loud = ref > -60.0  # mel power >> amin
+    assert float((lm - ref)[loud].abs().max()) < 1e-2  # dB
+    silent = ref == -100.0  # zero-padded tail: clamp(., 1e-10) -> -100 dB
+    assert silent.any()
+    assert float((lm[silent] + 100.0).abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize("kind", ["noise", "tone", "dc", "silence"])
+def test_frontend_signals(eng_parity, small_sd, kind):
+    from oracle import restate
+
+    n = 20000 + 123  # not a multiple of the hop
+    tt = torch.arange(n) / 32000.0
+    wav = {
+        "noise": 0.1 * torch.randn(2, n, generator=torch.Generator().manual_seed(1)),
+        "tone": torch.stack([0.5 * torch.sin(2 * np.pi * 440.0 * tt), 0.3 * torch.sin(2 * np.pi * 7000.0 * tt)]),
+        "dc": torch.full((2, n), 0.25),
+        "silence": torch.zeros(2, n),
+    }[kind]
+    ref = restate.logmel(small_sd, wav)
+    lm = eng_parity.frontend(wav, apply_bn=False).cpu()
+    if kind == "silence":
+        assert float((lm + 100.0).abs().max()) < 1e-3
+        return
+    # compare where the bin carries signal: within 60 dB of the frame maximum (fp32 DFT leakage floor differs below)
+    strong = ref > (ref.amax(dim=-1, keepdim=True) - 60.0)
+    assert float((lm - ref)[strong].abs().max()) < 1e-2
+    bn = eng_parity.frontend(wav, apply_bn=True).cpu()
+    torch.testing.assert_close(bn[strong], restate.bn0(small_sd, ref)[strong], rtol=1e-4, atol=2e-3)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# encoder stages (parity mode = fp32 GEMMs): every tap against the oracle
+# ----------------------------------------------------------------------------------------------------------------------
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def test_encoder_taps_parity(eng_parity, oracle_taps):
+    from conette_audio_captioning_b200 import _lib
+
+    wav, _, taps, _ = oracle_taps
+    got = eng_parity.encoder_tap(wav, _lib.TAP_LOGMEL_BN).cpu()
+    assert rel_l2(got, taps["logmel_bn"]) < 1e-4
+    got = eng_parity.encoder_tap(wav, _lib.TAP_STEM).cpu()
+    assert rel_l2(got, _nhwc(taps["stem"])) < 2e-4
+    depths = (3, 3, 9, 3)
+    for s in range(4):
+        if s > 0:
+            got = eng_parity.encoder_tap(wav, _lib.TAP_DOWN, s).cpu()
+            assert rel_l2(got, _nhwc(taps[f"down.{s}"])) < 2e-4, f"down {s}"
+        for b in range(depths[s]):
+            got = eng_parity.encoder_tap(wav, _lib.TAP_DWLN, s, b).cpu()
+            assert rel_l2(got, taps[f"dwln.{s}.{b}"]) < 2e-4, f"dwln {s}.{b}"
+            got = eng_parity.encoder_tap(wav, _lib.TAP_BLOCK, s, b).cpu()
+            assert rel_l2(got, _nhwc(taps[f"block.{s}.{b}"])) < 2e-4, f"block {s}.{b}"
+
+
+def test_encoder_outputs_parity(eng_parity, oracle_taps):
+    wav, _, _, out = oracle_taps
+    fe, clip = eng_parity.encoder(wav)
+    ref = out["frame_embs"].transpose(1, 2)
+    assert rel_l2(fe, ref) < 5e-4
+    torch.testing.assert_close(clip.cpu(), out["clipwise_output"], rtol=1e-3, atol=1e-4)
+
+
+def test_encoder_outputs_fast(eng_fast, oracle_taps):
+    from conette_audio_captioning_b200 import _lib
+
+    wav, _, taps, out = oracle_taps
+    fe, clip = eng_fast.encoder(wav)
+    err = rel_l2(fe, out["frame_embs"].transpose(1, 2))
+    print(f"fast-mode frame_embs rel-L2 = {err:.2e}")
+    assert err < 5e-3
+    assert float((clip.cpu() - out["clipwise_output"]).abs().max()) < 2e-2
+    got = eng_fast.encoder_tap(wav, _lib.TAP_BLOCK, 0, 0).cpu()
+    assert rel_l2(got, _nhwc(taps["block.0.0"])) < 5e-3
+
+
+def test_encoder_golden(eng_parity, small_sd):
+    fx = load("encoder.npz")
+    fe, clip = eng_parity.encoder(t(fx["wav"]))
+    assert rel_l2(fe, t(fx["frame_embs"]).transpose(1, 2)) < 5e-4
+    torch.testing.assert_close(clip.cpu(), t(fx["clip_probs"]), rtol=1e-3, atol=1e-4)
+
+
+def test_encoder_batch_chunking_is_invisible(eng_parity):
+    """B=6 with enc_chunk=4 (two passes) must equal per-clip results: clips are independent."""
+    wav = synth.make_audio(6, 16000, seed=3)[:, 0].contiguous()
+    fe, _ = eng_parity.encoder(wav)
+    for i in (0, 3, 4, 5):
+        fe1, _ = eng_parity.encoder(wav[i : i + 1])
+        assert torch.equal(fe[i : i + 1], fe1)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# decoder + beam search, fed the golden projected frames
+# ----------------------------------------------------------------------------------------------------------------------
+def test_decoder_logits_vs_oracle(eng_parity, small_sd):
+    from oracle import restate
+
+    g = torch.Generator().manual_seed(0)
+    b, tp, steps = 5, 9, 8
+    fe = torch.randn(b, tp, 768, generator=g)
+    lens = torch.tensor([9, 4, 7, 1, 9])
+    toks = torch.randint(4, 300, (b, steps), generator=g)
+    logits = eng_parity.decoder_logits(fe, lens, toks).cpu()
+    dec = restate.KVDecoder(small_sd, restate.project(small_sd, fe), lens, beam=1, max_len=steps)
+    for i in range(steps):
+        ref = dec.step(toks[:, i], i)
+        torch.testing.assert_close(logits[:, i], ref, rtol=1e-4, atol=1e-4)
+        assert torch.equal(logits[:, i].argmax(-1), ref.argmax(-1))
+
+
+CASES = [(1, 3, 20, "content_words"), (2, 0, 20, "content_words"), (3, 3, 20, "content_words"), (3, 3, 20, "none"),
+         (3, 0, 5, "all"), (5, 3, 20, "content_words"), (5, 3, 30, "all"), (3, 2, 12, "content_words")]
+
+
+@pytest.mark.parametrize("beam,min_len,max_len,mode", CASES)
+@pytest.mark.parametrize("eos_bias", [3.0, -20.0])
+def test_beam_search_vs_oracle(small_sd, beam, min_len, max_len, mode, eos_bias):
+    """ids bit-exact, scores to 1e-4, shapes/trim rules identical; EOS bias 3 => beams finish at different steps
+    (early exit + shrinking live sets), -20 => nothing finishes before the forced stop at max-1."""
+    from conette_audio_captioning_b200.engine import Engine
+    from oracle import restate
+
+    sd = dict(small_sd)
+    bias = small_sd["model.decoder.classifier.bias"].clone()
+    bias[2] += eos_bias - 3.0
+    sd["model.decoder.classifier.bias"] = bias
+    eng = Engine(sd, vocab_size=bias.shape[0], precision="parity")
+    try:
+        g = torch.Generator().manual_seed(100 * beam + max_len)
+        b, tp = 7, 6
+        fe = torch.randn(b, tp, 768, generator=g)
+        lens = torch.randint(1, tp + 1, (b,), generator=g)
+        bos_ids = sd["model.task_id_to_token_id"][torch.randint(0, 7, (b,), generator=g)]
+        forbid = synth.make_forbid_rep_mask(synth.make_itos(300), mode)
+        got = eng.decode(fe, lens, bos_ids, forbid, beam, min_len, max_len)
+        ref = restate.beam_search(sd, restate.project(sd, fe), lens, bos_ids, beam, min_len, max_len, forbid)
+    finally:
+        eng.close()
+    for name, r, m in zip(("preds", "lprobs", "mult_preds", "mult_lprobs"), ref, got):
+        m = m.cpu()
+        assert r.shape == m.shape, name
+        if r.dtype == torch.long:
+            assert torch.equal(r, m), name
+        else:
+            torch.testing.assert_close(m, r, rtol=1e-4, atol=1e-4)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# end to end through the reference-facing API
+# ----------------------------------------------------------------------------------------------------------------------
+def _model(small_sd, precision):
+    from conette_audio_captioning_b200 import CoNeTTEModel
+
+    return CoNeTTEModel(None, small_sd, synth.make_itos(300), precision=precision, enc_chunk=4)
+
+
+def test_e2e_golden_parity_mode(small_sd):
+    fx = load("e2e.npz")
+    assert_weights_match(small_sd, fx)
+    model = _model(small_sd, "parity")
+    out = model(t(fx["wav"]), sr=32000, x_shapes=t(fx["x_shapes"]), task=[str(s) for s in fx["tasks"]])
+    assert np.array_equal(out["preds"].numpy(), fx["preds"])  # ids bit-exact vs the real reference
+    assert np.array_equal(out["mult_preds"].numpy(), fx["mult_preds"])
+    np.testing.assert_allclose(out["lprobs"].numpy(), fx["lprobs"], rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(out["mult_lprobs"].numpy(), fx["mult_lprobs"], rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(out["tags_probs"].numpy(), fx["tags_probs"], rtol=1e-3, atol=1e-4)
+    assert out["cands"] == [str(s) for s in fx["cands"]]
+    assert out["mult_cands"] == [[str(s) for s in row] for row in fx["mult_cands"]]
+    assert out["tasks"] == [str(s) for s in fx["tasks"]]
+    assert set(out) == {"cands", "preds", "lprobs", "mult_cands", "mult_preds", "mult_lprobs", "tasks", "tags_probs", "tags"}
+    model.engine.close()
+
+
+def test_e2e_fast_mode_agreement_is_reported(small_sd):
+    """bf16 encoder: token agreement with the fp32 oracle is REPORTED (near-ties may flip), scores must stay close."""
+    from oracle import restate
+
+    model = _model(small_sd, "fast")
+    wav = synth.make_audio(8, 40000, seed=9)
+    out = model(wav, sr=32000, task="clotho")
+    bos = small_sd["model.task_id_to_token_id"][torch.zeros(8, dtype=torch.long)]
+    ref = restate.caption(small_sd, wav[:, 0], None, bos, 3, 3, 20, small_sd["model.forbid_rep_mask"])
+    same = [bool(torch.equal(a[: len(b)], b) or torch.equal(a, b[: len(a)])) for a, b in
+            zip(out["preds"], ref["preds"])]
+    L = min(out["preds"].shape[1], ref["preds"].shape[1])
+    agree = float((out["preds"][:, :L] == ref["preds"][:, :L]).float().mean())
+    print(f"fast-mode greedy/beam token agreement: {agree:.3f}; identical captions: {sum(same)}/8")
+    assert agree > 0.5
+    assert float((out["lprobs"] - ref["lprobs"]).abs().max()) < 0.1
+    model.engine.close()
+
+
+def test_input_forms_and_errors(small_sd):
+    model = _model(small_sd, "parity")
+    n = 16000
+    mono = synth.make_audio(1, n, seed=2)[0, 0]
+    stereo = torch.stack([mono, 0.5 * mono])
+    o1 = model(mono, sr=32000)  # (N,)
+    o2 = model(stereo, sr=32000)  # (C, N) is ONE clip with C channels
+    o3 = model([stereo, mono[None, : n // 2]], sr=[32000, 32000], task=["clotho", "audiocaps"])  # ragged list
+    assert len(o1["cands"]) == 1 and len(o2["cands"]) == 1 and len(o3["cands"]) == 2
+    assert o3["mult_preds"].shape[:2] == (2, 3)
+    o4 = model(mono, sr=32000, beam_size=1, forbid_rep_mode="none", max_pred_size=7)
+    assert o4["mult_preds"].shape[1] == 1 and o4["preds"].shape[1] <= 7
+    with pytest.raises(ValueError):
+        model(mono, sr=32000, task="not_a_task")
+    with pytest.raises(ValueError):
+        model(torch.zeros(2, 1, n), sr=32000, task=["clotho"])
+    with pytest.raises(ValueError):
+        model(torch.zeros(1, 1, 1, n), sr=32000)
+    with pytest.raises(ValueError):
+        model(mono, sr=32000, forbid_rep_mode="bogus")
+    with pytest.raises(ValueError):
+        model(mono, sr=16000, x_shapes=torch.tensor([[n]]))
+    model.engine.close()
