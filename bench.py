@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""Benchmark of the CoNeTTE inference hot path (BASELINE.json metric: captioned audio-seconds per second).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one pass of the whole path (waveform -> log-mel -> ConvNeXt-Tiny -> projection -> beam-3 decode -> token ids)
+over one batch of synthetic clips.  Workload = BASELINE.json configs[1]: batch 64 x 10 s @ 32 kHz, task=clotho, beam 3,
+min 3 / max 20 tokens, random-init weights of the checkpoint architecture (V = 4018).  With N GPUs every rank processes
+its own 64-clip shard (weak scaling; no data-path collective, one NCCL all_gather of the token ids per step).
+
+Reported on one JSON line (rank 0):
+  value     device-resident throughput: inputs already in HBM, CUDA-event timed, max over ranks
+  e2e       the same through the reference-facing C-ABI call with HOST buffers (H2D of the waveforms + D2H of the ids inside)
+  roofline  dominant kernel class: algorithmic FLOPs or bytes / CUDA-event time, against MEASURED_PEAKS.json
+  kernels   the same for every kernel class (share of the step, achieved, fraction of peak)
+  cpu_baseline  the reference's own CPU code (baseline/_ref, kind "reference") or the oracle port, on a bounded sample
+`--impl reference` times that CPU path alone and prints the same line shape with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "captioned audio-seconds per second (10 s clips, beam 3)"
+UNIT = "audio-s/s"
+SR = 32000
+DIMS, DEPTHS, WIDTHS = (96, 192, 384, 768), (3, 3, 9, 3), (56, 28, 14, 7)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
+    ap.add_argument("--seconds", type=float, default=10.0)
+    ap.add_argument("--beam", type=int, default=3)
+    ap.add_argument("--precision", default="fast", choices=["fast", "parity"])
+    ap.add_argument("--enc-chunk", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=8, help="clips in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback"}
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"configs[1]: batch {args.batch} x {args.seconds:g} s @ 32 kHz synthetic clips per GPU, task=clotho, "
+                    f"beam {args.beam}, min 3 / max 20 tokens, V=4018, random-init weights (seed 1234)",
+        "clips_per_gpu": args.batch, "n_samples": int(args.seconds * SR), "beam": args.beam, "precision": args.precision,
+        "parallelism": f"clip-sharded x{world} (no data-path collective; all_gather of ids)",
+        "l2": "two input batches alternate (2 x 82 MB > 126 MB L2) and ~3 GB of activations stream through L2 per step",
+    }
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# algorithmic work per kernel class for one step (DESIGN.md "Algorithmic work")
+# ---------------------------------------------------------------------------------------------------------------------
+def algorithmic_work(batch: int, n_samples: int, act_bytes: int = 2):
+    t = n_samples // 320 + 1
+    h1 = (t + 4) // 4 + 1
+    hs = [h1, h1 // 2, h1 // 4, h1 // 8]
+    work = {}
+    work["frontend"] = ("hbm", batch * (4 * n_samples + 4 * t * 224))
+    work["stem"] = ("hbm", batch * (4 * t * 224 + 4 * hs[0] * 56 * 96))
+    dw = pw1_f = pw2_f = ds_f = pack_b = 0
+    for s in range(4):
+        m = batch * hs[s] * WIDTHS[s]
+        c = DIMS[s]
+        dw += DEPTHS[s] * m * c * (4 + act_bytes)          # read fp32 residual stream, write GEMM operand
+        pw1_f += DEPTHS[s] * 2 * m * c * 4 * c
+        pw2_f += DEPTHS[s] * 2 * m * 4 * c * c
+        if s > 0:
+            cin = DIMS[s - 1]
+            ds_f += 2 * m * 4 * cin * c
+            pack_b += m * 4 * cin * (4 + act_bytes)
+    work["dwconv_ln"] = ("hbm", dw)
+    work["gemm_pw1_gelu"] = ("tensor", pw1_f)
+    work["gemm_pw2_resid"] = ("tensor", pw2_f)
+    work["ds_gemm"] = ("tensor", ds_f)
+    work["ds_ln_pack"] = ("hbm", pack_b)
+    return work
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks DURING the timed region")
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [l.strip().split(", ") for l in open(self.tmp.name) if l.strip()]
+        os.unlink(self.tmp.name)
+        mine = [r for r in rows if len(r) >= 8 and r[0].strip() == str(self.gpu)]
+        if not mine:
+            return out
+        sm = [float(r[1]) for r in mine]
+        busy = [x for x in sm if x > 0.5 * max(sm)] or sm
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = sorted({n for r in mine for n, v in zip(names, r[4:8]) if v.strip() == "Active"})
+        out.update(sm_mhz=statistics.median(busy), sm_max_mhz=float(mine[0][2]), reasons=reasons, samples=len(mine),
+                   power_w_max=max(float(r[3]) for r in mine))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU baseline: the reference's own code when importable (baseline/_ref or /root/reference), else the oracle port
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference_throughput(n_clips: int, n_samples: int, beam: int, steps: int, warmup: int):
+    import torch
+
+    from conette_audio_captioning_b200 import synth
+    from oracle import ref_loader, restate
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    sd = synth.make_state_dict(seed=1234, n_words=4000)
+    wav = synth.make_audio(n_clips, n_samples, seed=1234)
+    if ref_loader.available():
+        kind = "reference"
+        model = ref_loader.build_reference_model(sd, synth.make_corpus(4000))
+
+        def run():
+            with torch.no_grad():
+                return model(wav, sr=SR, task="clotho", beam_size=beam)
+    else:
+        kind = "port"
+        bos = sd["model.task_id_to_token_id"][torch.zeros(n_clips, dtype=torch.long)]
+
+        def run():
+            with torch.no_grad():
+                return restate.caption(sd, wav[:, 0], None, bos, beam, 3, 20, sd["model.forbid_rep_mask"])
+    for _ in range(warmup):
+        run()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        run()
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    secs = n_clips * n_samples / SR
+    return {
+        "value": secs / best, "unit": UNIT, "cores": cores, "kind": kind,
+        "sample": f"{n_clips} of the workload's clips ({secs:g} audio-s) per call, {warmup} warm-up + best of {steps} calls, "
+                  f"fp32 CPU, torch threads={cores}",
+        "s_per_call": best,
+    }, times
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    n = int(args.seconds * SR)
+    base, times = cpu_reference_throughput(args.cpu_sample, n, args.beam, max(1, args.steps), max(1, min(args.warmup, 2)))
+    ms = 1e3 * statistics.mean(times)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+        "cpu_baseline": base, "gpu_launches": 0,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from conette_audio_captioning_b200 import synth
+    from conette_audio_captioning_b200.engine import Engine
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = int(args.seconds * SR)
+    b = args.batch
+    sd = synth.make_state_dict(seed=1234, n_words=4000)
+    vocab = sd["model.decoder.classifier.weight"].shape[0]
+    eng = Engine(sd, vocab, device=local_rank, precision=args.precision, enc_chunk=args.enc_chunk)
+    forbid = sd["model.forbid_rep_mask"]
+    bos = sd["model.task_id_to_token_id"][torch.zeros(b, dtype=torch.long)]  # task = clotho
+    host_wavs = [synth.make_audio(b, n, seed=1234 + 2 * rank + i)[:, 0].contiguous().pin_memory() for i in range(2)]
+    dev_wavs = [w.to(dev) for w in host_wavs]
+    bos_dev, forbid_dev = bos.to(dev), forbid.to(dev, torch.uint8)
+    host_out = eng.alloc_host_outputs(b, args.beam, 20, with_tags=False)
+    gathered = None
+    if world > 1:
+        gathered = (torch.empty(world * b, 20, device=dev, dtype=torch.int64), torch.empty(world * b, device=dev))
+
+    def step_device(i):
+        outs = eng.caption(dev_wavs[i & 1], None, bos_dev, forbid_dev, args.beam, 3, 20, with_tags=False, trim=False)
+        if world > 1:  # the only collective of the path: gather token ids + scores
+            dist.all_gather_into_tensor(gathered[0], outs[0])
+            dist.all_gather_into_tensor(gathered[1], outs[1])
+        return outs
+
+    def step_host(i):
+        return eng.caption_host(host_wavs[i & 1], None, bos, forbid, args.beam, 3, 20, with_tags=False, out=host_out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local_rank)
+    # ---- device-resident throughput ("value") ------------------------------------------------------------------------
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    sampler.start()
+    launches0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        step_device(i)
+    ev1.record()
+    barrier()
+    launches = eng.launch_count() - launches0
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
+    # ---- end-to-end through the C-ABI host call ("e2e") -----------------------------------------------------------------
+    for i in range(args.warmup):
+        step_host(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        preds, lprobs, mult_preds, mult_lprobs, _ = step_host(i)
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0)) / args.steps
+    clocks = sampler.stop()
+    # ---- per-kernel-class device time (event brackets inside the library) ----------------------------------------------
+    eng.profile_begin()
+    for i in range(args.steps):
+        step_device(i)
+    prof = eng.profile_end()
+    barrier()
+
+    audio_s = b * n / SR * world
+    pk = peaks()
+    work = algorithmic_work(b, n, 2 if args.precision == "fast" else 4)
+    total_ms = sum(ms for ms, _ in prof.values()) or 1.0
+    kernels = {}
+    for name, (ms, cnt) in prof.items():
+        ent = {"ms_per_step": ms / args.steps, "share": ms / total_ms, "brackets_per_step": cnt / args.steps}
+        if name in work and ms > 0:
+            bound, amount = work[name]
+            rate = amount / (ms / args.steps * 1e-3)
+            if bound == "tensor":
+                ent.update(bound="tensor", achieved=rate / 1e12, unit="TFLOP/s", frac=rate / 1e12 / pk["bf16_tflops"])
+            else:
+                ent.update(bound="hbm", achieved=rate / 1e9, unit="GB/s", frac=rate / 1e9 / pk["hbm_gbs"])
+        kernels[name] = ent
+    top = max((k for k in kernels if "bound" in kernels[k]), key=lambda k: kernels[k]["ms_per_step"])
+    kt = kernels[top]
+    roofline = {"kernel": top, "bound": kt["bound"], "achieved": kt["achieved"],
+                "peak": pk["bf16_tflops"] if kt["bound"] == "tensor" else pk["hbm_gbs"], "unit": kt["unit"],
+                "frac": kt["frac"], "traffic": None, "peak_source": pk["source"] + " (sustained)",
+                "share_of_step": kt["share"]}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu, _ = cpu_reference_throughput(args.cpu_sample, n, args.beam, 2, 1)
+        h2d = b * n * 4 + b * 8 + vocab
+        d2h = sum(v.numel() * v.element_size() for v in host_out.values())
+        line = {
+            "metric": METRIC, "value": audio_s / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 tcgen05 GEMMs (f32 accumulate, f32 residual stream); f32 front-end, depthwise conv, decoder",
+            "data": "synthetic", "config": workload_config(args, world),
+            "e2e": {"value": audio_s / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "clocks": clocks,
+            "sample_output": {"preds0": preds[0].tolist(), "lprob0": float(lprobs[0])},
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    from conette_audio_captioning_b200 import build
+
+    if rank == 0:
+        build.build()
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

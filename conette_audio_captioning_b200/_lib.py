@@ -13,6 +13,9 @@ PRECISION_FAST, PRECISION_PARITY = 0, 1
 DTYPE_F32, DTYPE_I64, DTYPE_BOOL, DTYPE_U8 = 0, 1, 2, 3
 TAP_LOGMEL_BN, TAP_STEM, TAP_BLOCK, TAP_DOWN, TAP_DWLN = 0, 1, 2, 3, 4
 
+KERNEL_CLASSES = ("frontend", "stem", "dwconv_ln", "gemm_pw1_gelu", "gemm_pw2_resid", "ds_ln_pack", "ds_gemm", "head",
+                  "proj_crosskv", "dec_gemm", "dec_attn_ln", "dec_classifier", "beam")
+
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libconette_b200.so"
 
 
@@ -50,6 +53,8 @@ SIGNATURES = {
     "cnb_caption": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cnb_caption_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cnb_debug_gemm": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "cnb_profile_begin": (C.c_int, [_vp]),
+    "cnb_profile_end": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(_i64), _i32]),
     "cnb_launch_count": (_i64, [_vp]),
     "cnb_device_bytes": (_i64, [_vp]),
 }

@@ -84,9 +84,36 @@ struct cnb_handle {
   std::map<std::string, Buffer> ws;
   size_t ws_bytes = 0;
   int* zero_flag = nullptr;  // device int[4] that stays 0: "done" flag for non-beam callers
+  // optional per-kernel-class timing (cnb_profile_begin/end): CUDA event pairs around every launch
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_events;  // pool, pairs (start, stop)
+  std::vector<int> prof_class;           // class of pair i
+  size_t prof_used = 0;                  // events used
 };
 
 namespace cnb {
+
+// RAII bracket: records an event pair on `st` around the launches issued while it is alive (only in profile mode)
+struct Prof {
+  cnb_handle* h;
+  cudaStream_t st;
+  bool on;
+  Prof(cnb_handle* h_, int cls, cudaStream_t st_) : h(h_), st(st_), on(h_->prof_on) {
+    if (!on) return;
+    if (h->prof_used + 2 > h->prof_events.size()) {
+      const size_t old = h->prof_events.size();
+      h->prof_events.resize(old + 4096);
+      for (size_t i = old; i < h->prof_events.size(); ++i) cudaEventCreate(&h->prof_events[i]);
+    }
+    h->prof_class.push_back(cls);
+    cudaEventRecord(h->prof_events[h->prof_used], st);
+  }
+  ~Prof() {
+    if (!on) return;
+    cudaEventRecord(h->prof_events[h->prof_used + 1], st);
+    h->prof_used += 2;
+  }
+};
 
 static int ws_get(cnb_handle* h, const char* name, size_t bytes, void** out) {
   Buffer& b = h->ws[name];
@@ -401,9 +428,9 @@ static int encode_chunk(cnb_handle* h, const float* wav, int nb, int64_t n, floa
   WS(h, "y", ActT, (size_t)nb * p0 * kDims[0], y);
   WS(h, "hid", ActT, (size_t)nb * p0 * kDims[0] * 4, hid);
 
-  if (int rc = launch_frontend(wav, nb, n, h->fe, true, logmel, st)) return rc;
+  { Prof _p(h, CNB_K_FRONTEND, st); if (int rc = launch_frontend(wav, nb, n, h->fe, true, logmel, st)) return rc; }
   if (tap && tap->kind == CNB_TAP_LOGMEL_BN) return copy_tap(tap, logmel, (int64_t)nb * g.t * kMels, false, st);
-  if (int rc = launch_stem(logmel, nb, g.t, g.h[0], h->stem_w_t, h->stem_b, h->stem_ln_g, h->stem_ln_b, xa, st)) return rc;
+  { Prof _p(h, CNB_K_STEM, st); if (int rc = launch_stem(logmel, nb, g.t, g.h[0], h->stem_w_t, h->stem_b, h->stem_ln_g, h->stem_ln_b, xa, st)) return rc; }
   if (tap && tap->kind == CNB_TAP_STEM) return copy_tap(tap, xa, (int64_t)nb * p0 * kDims[0], false, st);
 
   float* x = xa;
@@ -415,37 +442,39 @@ static int encode_chunk(cnb_handle* h, const float* wav, int nb, int64_t n, floa
       // downsample: LN(channels_first) + 2x2/s2 conv as pack + GEMM (K = 4*Cin)
       const int cin = kDims[s - 1], hin = g.h[s - 1], win = kStageW[s - 1];
       const DownW& d = h->down[s - 1];
-      if (int rc = launch_ln_pack2x2<ActT>(x, nb, hin, win, cin, d.ln_g, d.ln_b, y, st)) return rc;
+      { Prof _p(h, CNB_K_DS_PACK, st); if (int rc = launch_ln_pack2x2<ActT>(x, nb, hin, win, cin, d.ln_g, d.ln_b, y, st)) return rc; }
       const int m = nb * hh * ww;
       EpiParams ep;
       ep.bias = d.bias;
-      if (int rc = mlp_gemm<ActT>(h, y, d.w, d.w_bf, m, c, 4 * cin, EPI_BIAS, ep, x_other, false, c, st)) return rc;
+      { Prof _p(h, CNB_K_DS_GEMM, st); if (int rc = mlp_gemm<ActT>(h, y, d.w, d.w_bf, m, c, 4 * cin, EPI_BIAS, ep, x_other, false, c, st)) return rc; }
       std::swap(x, x_other);
       if (tap && tap->kind == CNB_TAP_DOWN && tap->stage == s) return copy_tap(tap, x, (int64_t)m * c, false, st);
     }
     const int m = nb * hh * ww;
     for (int j = 0; j < kDepths[s]; ++j, ++bi) {
       const BlockW& b = h->blocks[bi];
-      if (int rc = launch_dwconv_ln<ActT>(x, nb, hh, ww, c, b.dw_w_t, b.dw_b, b.ln_g, b.ln_b, y, st)) return rc;
+      { Prof _p(h, CNB_K_DWLN, st); if (int rc = launch_dwconv_ln<ActT>(x, nb, hh, ww, c, b.dw_w_t, b.dw_b, b.ln_g, b.ln_b, y, st)) return rc; }
       if (tap && tap->kind == CNB_TAP_DWLN && tap->stage == s && tap->block == j)
         return copy_tap(tap, y, (int64_t)m * c, sizeof(ActT) == 2, st);
       EpiParams e1;
       e1.bias = b.b1;
-      if (int rc = mlp_gemm<ActT>(h, y, b.w1, b.w1_bf, m, 4 * c, c, EPI_BIAS_GELU, e1, hid, true, 4 * c, st)) return rc;
+      { Prof _p(h, CNB_K_GEMM_PW1, st); if (int rc = mlp_gemm<ActT>(h, y, b.w1, b.w1_bf, m, 4 * c, c, EPI_BIAS_GELU, e1, hid, true, 4 * c, st)) return rc; }
       EpiParams e2;
       e2.bias = b.b2;
       e2.scale = b.scale;
       e2.resid = x;
-      if (int rc = mlp_gemm<ActT>(h, hid, b.w2, b.w2_bf, m, c, 4 * c, EPI_SCALE_RESID, e2, x, false, c, st)) return rc;
+      { Prof _p(h, CNB_K_GEMM_PW2, st); if (int rc = mlp_gemm<ActT>(h, hid, b.w2, b.w2_bf, m, c, 4 * c, EPI_SCALE_RESID, e2, x, false, c, st)) return rc; }
       if (tap && tap->kind == CNB_TAP_BLOCK && tap->stage == s && tap->block == j)
         return copy_tap(tap, x, (int64_t)m * c, false, st);
     }
   }
-  if (int rc = launch_freq_mean(x, nb, g.tp, kStageW[3], 768, frame_embs, st)) return rc;
-  if (clip_probs)
+  { Prof _p(h, CNB_K_HEAD, st); if (int rc = launch_freq_mean(x, nb, g.tp, kStageW[3], 768, frame_embs, st)) return rc; }
+  if (clip_probs) {
+    Prof _p(h, CNB_K_HEAD, st);
     if (int rc = launch_clip_head(frame_embs, nb, g.tp, h->head_ln_g, h->head_ln_b, h->head_w, h->head_b, kTags, clip_probs,
                                   st))
       return rc;
+  }
   return 0;
 }
 
@@ -512,6 +541,7 @@ static int dec_prepare(cnb_handle* h, const float* frame_embs, int batch, int tp
   // projection: Linear(768,256) + ReLU (reference common.py:71-78); cross-attention K|V of all 6 layers in one GEMM
   EpiParams ep;
   ep.bias = h->proj_b;
+  Prof _p(h, CNB_K_PROJ_KV, st);
   if (int rc = launch_gemm_f32<float>(frame_embs, 768, h->proj_w, batch * tp, kD, 768, EPI_BIAS_RELU, ep, mem, kD, st))
     return rc;
   EpiParams ek;
@@ -525,32 +555,36 @@ static int dec_step(cnb_handle* h, const DecWs& w, const int* tokens, const int*
   const int R = dd.rows;
   const int64_t cache_l = (int64_t)R * dd.max_len * kD;
   const int64_t kv_stride = kLayers * 2 * kD;
-  if (int rc = launch_embed(tokens, pos, h->emb, h->pe, w.x, dd, done, st)) return rc;
+  { Prof _p(h, CNB_K_DEC_ATTN, st); if (int rc = launch_embed(tokens, pos, h->emb, h->pe, w.x, dd, done, st)) return rc; }
   for (int l = 0; l < kLayers; ++l) {
     const LayerW& L = h->layers[l];
     EpiParams e;
     e.bias = L.sa_in_b;
-    if (int rc = launch_gemm_f32<float>(w.x, kD, L.sa_in_w, R, 3 * kD, kD, EPI_BIAS, e, w.qkv, 3 * kD, st)) return rc;
-    if (int rc = launch_self_attn(w.qkv, w.kc + l * cache_l, w.vc + l * cache_l, src_row, pos, w.attn, dd, done, st)) return rc;
+    { Prof _p(h, CNB_K_DEC_GEMM, st);     if (int rc = launch_gemm_f32<float>(w.x, kD, L.sa_in_w, R, 3 * kD, kD, EPI_BIAS, e, w.qkv, 3 * kD, st)) return rc; }
+    { Prof _p(h, CNB_K_DEC_ATTN, st);     if (int rc = launch_self_attn(w.qkv, w.kc + l * cache_l, w.vc + l * cache_l, src_row, pos, w.attn, dd, done, st)) return rc; }
     e.bias = L.sa_out_b;
-    if (int rc = launch_gemm_f32<float>(w.attn, kD, L.sa_out_w, R, kD, kD, EPI_BIAS, e, w.tmp, kD, st)) return rc;
-    if (int rc = launch_add_ln(w.x, w.tmp, L.n1_g, L.n1_b, R, done, st)) return rc;
+    { Prof _p(h, CNB_K_DEC_GEMM, st);     if (int rc = launch_gemm_f32<float>(w.attn, kD, L.sa_out_w, R, kD, kD, EPI_BIAS, e, w.tmp, kD, st)) return rc; }
+    { Prof _p(h, CNB_K_DEC_ATTN, st);     if (int rc = launch_add_ln(w.x, w.tmp, L.n1_g, L.n1_b, R, done, st)) return rc; }
     e.bias = L.ca_q_b;
-    if (int rc = launch_gemm_f32<float>(w.x, kD, L.ca_q_w, R, kD, kD, EPI_BIAS, e, w.tmp, kD, st)) return rc;
-    if (int rc = launch_cross_attn(w.tmp, w.ckv + (int64_t)l * 2 * kD, w.ckv + (int64_t)l * 2 * kD + kD, kv_stride, lens,
-                                   w.attn, dd, done, st))
-      return rc;
+    { Prof _p(h, CNB_K_DEC_GEMM, st);     if (int rc = launch_gemm_f32<float>(w.x, kD, L.ca_q_w, R, kD, kD, EPI_BIAS, e, w.tmp, kD, st)) return rc; }
+    {
+      Prof _p(h, CNB_K_DEC_ATTN, st);
+      if (int rc = launch_cross_attn(w.tmp, w.ckv + (int64_t)l * 2 * kD, w.ckv + (int64_t)l * 2 * kD + kD, kv_stride, lens,
+                                     w.attn, dd, done, st))
+        return rc;
+    }
     e.bias = L.ca_out_b;
-    if (int rc = launch_gemm_f32<float>(w.attn, kD, L.ca_out_w, R, kD, kD, EPI_BIAS, e, w.tmp, kD, st)) return rc;
-    if (int rc = launch_add_ln(w.x, w.tmp, L.n2_g, L.n2_b, R, done, st)) return rc;
+    { Prof _p(h, CNB_K_DEC_GEMM, st);     if (int rc = launch_gemm_f32<float>(w.attn, kD, L.ca_out_w, R, kD, kD, EPI_BIAS, e, w.tmp, kD, st)) return rc; }
+    { Prof _p(h, CNB_K_DEC_ATTN, st);     if (int rc = launch_add_ln(w.x, w.tmp, L.n2_g, L.n2_b, R, done, st)) return rc; }
     e.bias = L.l1_b;
-    if (int rc = launch_gemm_f32<float>(w.x, kD, L.l1_w, R, kFF, kD, EPI_BIAS_GELU, e, w.ff, kFF, st)) return rc;
+    { Prof _p(h, CNB_K_DEC_GEMM, st);     if (int rc = launch_gemm_f32<float>(w.x, kD, L.l1_w, R, kFF, kD, EPI_BIAS_GELU, e, w.ff, kFF, st)) return rc; }
     e.bias = L.l2_b;
-    if (int rc = launch_gemm_f32<float>(w.ff, kFF, L.l2_w, R, kD, kFF, EPI_BIAS, e, w.tmp, kD, st)) return rc;
-    if (int rc = launch_add_ln(w.x, w.tmp, L.n3_g, L.n3_b, R, done, st)) return rc;
+    { Prof _p(h, CNB_K_DEC_GEMM, st);     if (int rc = launch_gemm_f32<float>(w.ff, kFF, L.l2_w, R, kD, kFF, EPI_BIAS, e, w.tmp, kD, st)) return rc; }
+    { Prof _p(h, CNB_K_DEC_ATTN, st);     if (int rc = launch_add_ln(w.x, w.tmp, L.n3_g, L.n3_b, R, done, st)) return rc; }
   }
   EpiParams e;
   e.bias = h->cls_b;
+  Prof _p(h, CNB_K_DEC_CLS, st);
   return launch_gemm_f32<float>(w.x, kD, h->cls_w, R, dd.vocab, kD, EPI_BIAS, e, w.logits, dd.vocab, st);
 }
 
@@ -609,7 +643,7 @@ static int decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, c
   int cur = 0;
   for (int i = 0; i < max_len; ++i) {
     if (int rc = dec_step(h, w, bs.tokens[cur], bs.src_row[cur], lens, i, dd, done, st)) return rc;
-    if (int rc = launch_beam_step(w.logits, forbid, bs, i, cur, min_len, dd, st)) return rc;
+    { Prof _p(h, CNB_K_BEAM, st); if (int rc = launch_beam_step(w.logits, forbid, bs, i, cur, min_len, dd, st)) return rc; }
     cur ^= 1;
   }
   if (int rc = launch_beam_finalize(bs, preds, lprobs, best_len, dd, st)) return rc;
@@ -677,6 +711,7 @@ int cnb_destroy(cnb_handle* h) {
     if (kv.second.ptr) cudaFree(kv.second.ptr);
   if (h->arena.base) cudaFree(h->arena.base);
   if (h->zero_flag) cudaFree(h->zero_flag);
+  for (auto e : h->prof_events) cudaEventDestroy(e);
   delete h;
   return 0;
 }
@@ -879,6 +914,34 @@ int cnb_debug_gemm(cnb_handle* h, const float* a, const float* w, const float* b
   if (int rc = launch_gemm_tc<__nv_bfloat16>(a_bf, w_bf, m, n, k, (Epilogue)epi, ep, o_bf, n, st)) return rc;
   bf16_to_f32_kernel<<<(unsigned)ceil_div((int64_t)m * n, 256), 256, 0, st>>>(o_bf, out, (int64_t)m * n);
   CNB_LAUNCH_OK();
+  return 0;
+}
+
+int cnb_profile_begin(cnb_handle* h) {
+  CHECK_READY(h);
+  h->prof_on = true;
+  h->prof_used = 0;
+  h->prof_class.clear();
+  return 0;
+}
+
+int cnb_profile_end(cnb_handle* h, float* ms_per_class, int64_t* brackets_per_class, int32_t n_classes) {
+  CHECK_READY(h);
+  CNB_REQUIRE(ms_per_class && brackets_per_class && n_classes >= CNB_K_COUNT, "output arrays too small");
+  h->prof_on = false;
+  CNB_CUDA_OK(cudaDeviceSynchronize());
+  for (int i = 0; i < n_classes; ++i) {
+    ms_per_class[i] = 0.f;
+    brackets_per_class[i] = 0;
+  }
+  for (size_t i = 0; i < h->prof_class.size(); ++i) {
+    float ms = 0.f;
+    CNB_CUDA_OK(cudaEventElapsedTime(&ms, h->prof_events[2 * i], h->prof_events[2 * i + 1]));
+    ms_per_class[h->prof_class[i]] += ms;
+    brackets_per_class[h->prof_class[i]] += 1;
+  }
+  h->prof_used = 0;
+  h->prof_class.clear();
   return 0;
 }
 

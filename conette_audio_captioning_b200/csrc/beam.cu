@@ -171,6 +171,7 @@ beam_step_kernel(float* __restrict__ logits, const uint8_t* __restrict__ forbid,
           b = s_cand[i];
           ow = __float_as_int(s_red[i]);
         }
+      if (b.idx == 0x7fffffff) b.idx = 0;  // NaN logits (fully masked clip, len 0): stay memory-safe like a no-op pick
       s_win[r] = b;
       s_winner_tid = ow;
     }

@@ -70,7 +70,7 @@ int launch_stem(const float* lm, int batch, int n_frames, int h1, const float* w
 // K-DWLN: depthwise 7x7 (pad 3) + bias + LayerNorm over C, one CTA per output row (b, h).
 //   thread = (channel pair cp, strip of 7 output pixels); weights for the pair live in registers (49 x float2);
 //   each of the 7 kernel rows streams 13 input float2 through 49 FMAs per channel.
-//   LayerNorm: two-pass (mean, then squared deviations) with warp shuffles + shared-memory atomics per pixel.
+//   LayerNorm: two-pass (mean, then squared deviations): warp shuffles, then per-warp partials summed in fixed order.
 // =====================================================================================================================
 template <int C, int W, typename OutT>
 __global__ void __launch_bounds__(((C / 2 + 31) / 32) * 32 * (W / 7))
@@ -79,20 +79,17 @@ dwconv_ln_kernel(const float* __restrict__ x, int H, const float* __restrict__ w
   constexpr int CP = C / 2;
   constexpr int CP_PAD = ((CP + 31) / 32) * 32;
   constexpr int PW = 7;
-  __shared__ float s_sum[W];
-  __shared__ float s_sq[W];
+  constexpr int NW = CP_PAD / 32;  // warps that share one strip of pixels
+  __shared__ float s_sum[W][NW];   // per-warp partials, summed in a fixed order (deterministic, no atomics)
+  __shared__ float s_sq[W][NW];
 
   const int tid = threadIdx.x;
   const int strip = tid / CP_PAD;
   const int cp = tid - strip * CP_PAD;
+  const int wis = cp >> 5;  // warp index inside the strip
   const bool active = cp < CP;
   const int b = blockIdx.y, h = blockIdx.x;
   const int w0 = strip * PW;
-  for (int i = tid; i < W; i += blockDim.x) {
-    s_sum[i] = 0.f;
-    s_sq[i] = 0.f;
-  }
-  __syncthreads();
 
   float2 acc[PW];
   if (active) {
@@ -130,16 +127,19 @@ dwconv_ln_kernel(const float* __restrict__ x, int H, const float* __restrict__ w
 #pragma unroll
   for (int p = 0; p < PW; ++p) {
     const float s = warp_sum(acc[p].x + acc[p].y);
-    if ((tid & 31) == 0) atomicAdd(&s_sum[w0 + p], s);
+    if ((tid & 31) == 0) s_sum[w0 + p][wis] = s;
   }
   __syncthreads();
   float mean[PW];
 #pragma unroll
   for (int p = 0; p < PW; ++p) {
-    mean[p] = s_sum[w0 + p] * (1.f / C);
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) t += s_sum[w0 + p][i];
+    mean[p] = t * (1.f / C);
     const float dx = active ? acc[p].x - mean[p] : 0.f, dy = active ? acc[p].y - mean[p] : 0.f;
     const float s = warp_sum(dx * dx + dy * dy);
-    if ((tid & 31) == 0) atomicAdd(&s_sq[w0 + p], s);
+    if ((tid & 31) == 0) s_sq[w0 + p][wis] = s;
   }
   __syncthreads();
   if (active) {
@@ -148,7 +148,10 @@ dwconv_ln_kernel(const float* __restrict__ x, int H, const float* __restrict__ w
     OutT* o = out + (((int64_t)b * H + h) * W + w0) * C + 2 * cp;
 #pragma unroll
     for (int p = 0; p < PW; ++p) {
-      const float rstd = 1.f / sqrtf(s_sq[w0 + p] * (1.f / C) + kLnEps);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NW; ++i) q += s_sq[w0 + p][i];
+      const float rstd = 1.f / sqrtf(q * (1.f / C) + kLnEps);
       const float y0 = (acc[p].x - mean[p]) * rstd * g.x + be.x;
       const float y1 = (acc[p].y - mean[p]) * rstd * g.y + be.y;
       if constexpr (sizeof(OutT) == 2) {

@@ -78,6 +78,17 @@ class Engine:
     def device_bytes(self) -> int:
         return int(self.lib.cnb_device_bytes(self.handle))
 
+    def profile_begin(self) -> None:
+        _lib.check(self.lib.cnb_profile_begin(self.handle))
+
+    def profile_end(self) -> Dict[str, Tuple[float, int]]:
+        """{kernel class: (summed device ms, number of event brackets)} since profile_begin."""
+        n = len(_lib.KERNEL_CLASSES)
+        ms = (C.c_float * n)()
+        cnt = (C.c_int64 * n)()
+        _lib.check(self.lib.cnb_profile_end(self.handle, ms, cnt, n))
+        return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(_lib.KERNEL_CLASSES)}
+
     # ---- stages -------------------------------------------------------------------------------------------------------
     def frontend(self, wav: Tensor, apply_bn: bool = True) -> Tensor:
         """(B, N) f32 -> (B, T, 224) log-mel [dB], optionally through bn0."""

@@ -108,6 +108,17 @@ int cnb_caption_host(cnb_handle* h, const float* wav_host, const int64_t* x_lens
 int cnb_debug_gemm(cnb_handle* h, const float* a, const float* w, const float* bias, const float* scale, const float* resid,
                    int32_t m, int32_t n, int32_t k, int32_t epi, int32_t use_tc, int32_t out_bf16, float* out, void* stream);
 
+/* Per-kernel-class device timing: between cnb_profile_begin and cnb_profile_end every launch group issued through this
+ * handle is bracketed by a CUDA event pair on the launching stream; _end synchronises and returns, per class, the summed
+ * event time in ms and the number of brackets. Arrays must hold CNB_K_COUNT entries. */
+enum {
+  CNB_K_FRONTEND = 0, CNB_K_STEM = 1, CNB_K_DWLN = 2, CNB_K_GEMM_PW1 = 3, CNB_K_GEMM_PW2 = 4, CNB_K_DS_PACK = 5,
+  CNB_K_DS_GEMM = 6, CNB_K_HEAD = 7, CNB_K_PROJ_KV = 8, CNB_K_DEC_GEMM = 9, CNB_K_DEC_ATTN = 10, CNB_K_DEC_CLS = 11,
+  CNB_K_BEAM = 12, CNB_K_COUNT = 13
+};
+int cnb_profile_begin(cnb_handle* h);
+int cnb_profile_end(cnb_handle* h, float* ms_per_class, int64_t* brackets_per_class, int32_t n_classes);
+
 /* Number of kernels launched by this handle since creation (bench.py reports the per-step delta as gpu_launches). */
 int64_t cnb_launch_count(const cnb_handle* h);
 /* Bytes of device memory currently held (weights + workspace). */

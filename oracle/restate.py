@@ -275,6 +275,10 @@ def beam_search(
             else:
                 cand = sum_lp[rws][:, None] + torch.log_softmax(logits[rws], dim=1)
             top, idx = torch.topk(cand.reshape(-1), len(labels))  # beam.py:256-257
+            if trace is not None:  # smallest score gap that decides this selection (rank order and the k / k+1 cut)
+                top1 = torch.topk(cand.reshape(-1), min(len(labels) + 1, cand.numel()))[0]
+                gaps = (top1[:-1] - top1[1:])
+                trace[-1].setdefault("margin", {})[j] = float(gaps.min()) if gaps.numel() else float("inf")
             prev = idx // vocab
             word = idx % vocab
             for r, l in enumerate(labels):

@@ -232,6 +232,7 @@ def test_decoder_logits_vs_oracle(eng_parity, small_sd):
         assert torch.equal(logits[:, i].argmax(-1), ref.argmax(-1))
 
 
+TIE_EPS = 2e-4
 CASES = [(1, 3, 20, "content_words"), (2, 0, 20, "content_words"), (3, 3, 20, "content_words"), (3, 3, 20, "none"),
          (3, 0, 5, "all"), (5, 3, 20, "content_words"), (5, 3, 30, "all"), (3, 2, 12, "content_words")]
 
@@ -257,16 +258,26 @@ def test_beam_search_vs_oracle(small_sd, beam, min_len, max_len, mode, eos_bias)
         bos_ids = sd["model.task_id_to_token_id"][torch.randint(0, 7, (b,), generator=g)]
         forbid = synth.make_forbid_rep_mask(synth.make_itos(300), mode)
         got = eng.decode(fe, lens, bos_ids, forbid, beam, min_len, max_len)
-        ref = restate.beam_search(sd, restate.project(sd, fe), lens, bos_ids, beam, min_len, max_len, forbid)
+        trace = []
+        ref = restate.beam_search(sd, restate.project(sd, fe), lens, bos_ids, beam, min_len, max_len, forbid, trace=trace)
     finally:
         eng.close()
+    # "documented score ties": torch.topk's order on (near-)equal scores is unspecified, so a clip
+    # whose oracle selection margin ever drops below TIE_EPS (sum-log-probs reach -100, fp32 spacing 8e-6) is compared on
+    # shapes only; every other clip must match bit-for-bit.
+    margin = torch.full((b,), float("inf"))
+    for tr in trace:
+        for j, mg in tr.get("margin", {}).items():
+            margin[j] = min(float(margin[j]), mg)
+    firm = margin >= TIE_EPS
+    assert int(firm.sum()) >= (b + 1) // 2, f"too many near-ties to be a meaningful test: {margin.tolist()}"
     for name, r, m in zip(("preds", "lprobs", "mult_preds", "mult_lprobs"), ref, got):
         m = m.cpu()
         assert r.shape == m.shape, name
         if r.dtype == torch.long:
-            assert torch.equal(r, m), name
+            assert torch.equal(r[firm], m[firm]), (name, margin.tolist())
         else:
-            torch.testing.assert_close(m, r, rtol=1e-4, atol=1e-4)
+            torch.testing.assert_close(m[firm], r[firm], rtol=1e-4, atol=1e-4)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -316,12 +327,12 @@ def test_e2e_fast_mode_agreement_is_reported(small_sd):
 
 def test_input_forms_and_errors(small_sd):
     model = _model(small_sd, "parity")
-    n = 16000
+    n = 32000
     mono = synth.make_audio(1, n, seed=2)[0, 0]
     stereo = torch.stack([mono, 0.5 * mono])
     o1 = model(mono, sr=32000)  # (N,)
     o2 = model(stereo, sr=32000)  # (C, N) is ONE clip with C channels
-    o3 = model([stereo, mono[None, : n // 2]], sr=[32000, 32000], task=["clotho", "audiocaps"])  # ragged list
+    o3 = model([stereo, mono[None, : 3 * n // 4]], sr=[32000, 32000], task=["clotho", "audiocaps"])  # ragged list
     assert len(o1["cands"]) == 1 and len(o2["cands"]) == 1 and len(o3["cands"]) == 2
     assert o3["mult_preds"].shape[:2] == (2, 3)
     o4 = model(mono, sr=32000, beam_size=1, forbid_rep_mode="none", max_pred_size=7)
