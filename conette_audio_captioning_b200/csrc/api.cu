@@ -61,6 +61,11 @@ struct Buffer {
   void* ptr = nullptr;
   size_t bytes = 0;
 };
+struct DecGraph {
+  std::vector<int64_t> key;
+  cudaGraphExec_t exec;
+  int64_t n_kernels;
+};
 
 }  // namespace cnb
 
@@ -84,6 +89,11 @@ struct cnb_handle {
   std::map<std::string, Buffer> ws;
   size_t ws_bytes = 0;
   int* zero_flag = nullptr;  // device int[4] that stays 0: "done" flag for non-beam callers
+  // CUDA-graph replay of the decode loop
+  bool use_graphs = true;
+  cudaStream_t stream = nullptr;  // library-owned non-blocking stream (graph capture / replay, host-API copies)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  std::vector<DecGraph> dec_graphs;
   // optional per-kernel-class timing (cnb_profile_begin/end): CUDA event pairs around every launch
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_events;  // pool, pairs (start, stop)
@@ -125,9 +135,13 @@ static int ws_get(cnb_handle* h, const char* name, size_t bytes, void** out) {
       b.ptr = nullptr;
       b.bytes = 0;
     }
+    // any (re)allocation invalidates the buffer addresses baked into cached CUDA graphs
+    for (auto& g : h->dec_graphs) cudaGraphExecDestroy(g.exec);
+    h->dec_graphs.clear();
     const size_t want = (bytes + 255) & ~size_t(255);
     CNB_CUDA_OK(cudaMalloc(&b.ptr, want));
     CNB_CUDA_OK(cudaMemset(b.ptr, 0, want));
+    CNB_CUDA_OK(cudaDeviceSynchronize());  // the memset runs on the legacy stream; our streams are non-blocking
     b.bytes = want;
     h->ws_bytes += want;
   }
@@ -521,11 +535,11 @@ static int encode(cnb_handle* h, const float* wav, int batch, int64_t n, float* 
 // decoder orchestration
 // ---------------------------------------------------------------------------------------------------------------------
 struct DecWs {
-  float *mem, *ckv, *x, *qkv, *attn, *tmp, *ff, *logits, *kc, *vc;
+  float *mem, *ckv, *x, *qkv, *attn, *tmp, *ff, *logits, *kc, *vc, *part;
 };
+constexpr int kFf2Splits = 8;  // split-K slices of the 2048-deep FF2 GEMM
 
-static int dec_prepare(cnb_handle* h, const float* frame_embs, int batch, int tp, int rows, int max_len, DecWs* w,
-                       cudaStream_t st) {
+static int dec_prepare(cnb_handle* h, int batch, int tp, int rows, int max_len, DecWs* w) {
   const int V = h->cfg.vocab_size;
   WS(h, "mem", float, (size_t)batch * tp * kD, mem);
   WS(h, "ckv", float, (size_t)batch * tp * kLayers * 2 * kD, ckv);
@@ -537,16 +551,22 @@ static int dec_prepare(cnb_handle* h, const float* frame_embs, int batch, int tp
   WS(h, "dlogits", float, (size_t)rows * V, logits);
   WS(h, "kc", float, (size_t)kLayers * rows * max_len * kD, kc);
   WS(h, "vc", float, (size_t)kLayers * rows * max_len * kD, vc);
-  *w = DecWs{mem, ckv, x, qkv, attn, tmp, ff, logits, kc, vc};
-  // projection: Linear(768,256) + ReLU (reference common.py:71-78); cross-attention K|V of all 6 layers in one GEMM
+  WS(h, "dpart", float, (size_t)kFf2Splits * rows * kD, part);
+  *w = DecWs{mem, ckv, x, qkv, attn, tmp, ff, logits, kc, vc, part};
+  return 0;
+}
+
+// projection: Linear(768,256) + ReLU (reference common.py:71-78); cross-attention K|V of all 6 layers in one GEMM
+static int dec_project(cnb_handle* h, const float* frame_embs, int batch, int tp, const DecWs& w, cudaStream_t st) {
+  Prof _p(h, CNB_K_PROJ_KV, st);
   EpiParams ep;
   ep.bias = h->proj_b;
-  Prof _p(h, CNB_K_PROJ_KV, st);
-  if (int rc = launch_gemm_f32<float>(frame_embs, 768, h->proj_w, batch * tp, kD, 768, EPI_BIAS_RELU, ep, mem, kD, st))
+  if (int rc = launch_gemm_f32<float>(frame_embs, 768, h->proj_w, batch * tp, kD, 768, EPI_BIAS_RELU, ep, w.mem, kD, st))
     return rc;
   EpiParams ek;
   ek.bias = h->ca_kv_b;
-  return launch_gemm_f32<float>(mem, kD, h->ca_kv_w, batch * tp, kLayers * 2 * kD, kD, EPI_BIAS, ek, ckv, kLayers * 2 * kD, st);
+  return launch_gemm_f32<float>(w.mem, kD, h->ca_kv_w, batch * tp, kLayers * 2 * kD, kD, EPI_BIAS, ek, w.ckv,
+                                kLayers * 2 * kD, st);
 }
 
 // one decoder step for position `pos`: tokens[r][pos] -> logits (R, V)
@@ -564,7 +584,7 @@ static int dec_step(cnb_handle* h, const DecWs& w, const int* tokens, const int*
     { Prof _p(h, CNB_K_DEC_ATTN, st);     if (int rc = launch_self_attn(w.qkv, w.kc + l * cache_l, w.vc + l * cache_l, src_row, pos, w.attn, dd, done, st)) return rc; }
     e.bias = L.sa_out_b;
     { Prof _p(h, CNB_K_DEC_GEMM, st);     if (int rc = launch_gemm_f32<float>(w.attn, kD, L.sa_out_w, R, kD, kD, EPI_BIAS, e, w.tmp, kD, st)) return rc; }
-    { Prof _p(h, CNB_K_DEC_ATTN, st);     if (int rc = launch_add_ln(w.x, w.tmp, L.n1_g, L.n1_b, R, done, st)) return rc; }
+    { Prof _p(h, CNB_K_DEC_ATTN, st);     if (int rc = launch_add_ln(w.x, w.tmp, 1, nullptr, L.n1_g, L.n1_b, R, done, st)) return rc; }
     e.bias = L.ca_q_b;
     { Prof _p(h, CNB_K_DEC_GEMM, st);     if (int rc = launch_gemm_f32<float>(w.x, kD, L.ca_q_w, R, kD, kD, EPI_BIAS, e, w.tmp, kD, st)) return rc; }
     {
@@ -575,12 +595,12 @@ static int dec_step(cnb_handle* h, const DecWs& w, const int* tokens, const int*
     }
     e.bias = L.ca_out_b;
     { Prof _p(h, CNB_K_DEC_GEMM, st);     if (int rc = launch_gemm_f32<float>(w.attn, kD, L.ca_out_w, R, kD, kD, EPI_BIAS, e, w.tmp, kD, st)) return rc; }
-    { Prof _p(h, CNB_K_DEC_ATTN, st);     if (int rc = launch_add_ln(w.x, w.tmp, L.n2_g, L.n2_b, R, done, st)) return rc; }
+    { Prof _p(h, CNB_K_DEC_ATTN, st);     if (int rc = launch_add_ln(w.x, w.tmp, 1, nullptr, L.n2_g, L.n2_b, R, done, st)) return rc; }
     e.bias = L.l1_b;
     { Prof _p(h, CNB_K_DEC_GEMM, st);     if (int rc = launch_gemm_f32<float>(w.x, kD, L.l1_w, R, kFF, kD, EPI_BIAS_GELU, e, w.ff, kFF, st)) return rc; }
-    e.bias = L.l2_b;
-    { Prof _p(h, CNB_K_DEC_GEMM, st);     if (int rc = launch_gemm_f32<float>(w.ff, kFF, L.l2_w, R, kD, kFF, EPI_BIAS, e, w.tmp, kD, st)) return rc; }
-    { Prof _p(h, CNB_K_DEC_ATTN, st);     if (int rc = launch_add_ln(w.x, w.tmp, L.n3_g, L.n3_b, R, done, st)) return rc; }
+    e.bias = nullptr;  // FF2 is split-K: bias + residual + LayerNorm happen in the reducing add_ln
+    { Prof _p(h, CNB_K_DEC_GEMM, st); if (int rc = launch_gemm_f32<float>(w.ff, kFF, L.l2_w, R, kD, kFF, EPI_BIAS, e, w.part, kD, st, kFf2Splits)) return rc; }
+    { Prof _p(h, CNB_K_DEC_ATTN, st); if (int rc = launch_add_ln(w.x, w.part, kFf2Splits, L.l2_b, L.n3_g, L.n3_b, R, done, st)) return rc; }
   }
   EpiParams e;
   e.bias = h->cls_b;
@@ -619,13 +639,36 @@ __global__ void copy_logits_kernel(const float* __restrict__ logits, float* __re
   }
 }
 
+// everything of one decode call that runs on the device, in launch order (this is what gets captured into a CUDA graph)
+static int decode_body(cnb_handle* h, const DecWs& w, BeamState bs, const float* frame_embs, const int32_t* lens,
+                       const int64_t* bos_ids, const uint8_t* forbid, int batch, int min_len, const DecoderDims& dd,
+                       int64_t* preds, float* lprobs, int64_t* mult_preds, float* mult_lprobs, int32_t* info, int* best_len,
+                       cudaStream_t st) {
+  if (int rc = dec_project(h, frame_embs, batch, dd.tp, w, st)) return rc;
+  if (int rc = launch_beam_init(bos_ids, bs, dd, st)) return rc;
+  int cur = 0;
+  for (int i = 0; i < dd.max_len; ++i) {
+    if (int rc = dec_step(h, w, bs.tokens[cur], bs.src_row[cur], lens, i, dd, bs.done, st)) return rc;
+    { Prof _p(h, CNB_K_BEAM, st); if (int rc = launch_beam_step(w.logits, forbid, bs, i, cur, min_len, dd, st)) return rc; }
+    cur ^= 1;
+  }
+  if (int rc = launch_beam_finalize(bs, preds, lprobs, best_len, dd, st)) return rc;
+  gather_mult_kernel<<<(dd.rows * dd.max_len + 255) / 256, 256, 0, st>>>(bs, mult_preds, mult_lprobs, best_len, info, dd.rows,
+                                                                        dd.max_len, batch);
+  CNB_LAUNCH_OK();
+  return 0;
+}
+
+// The ~1400 small dependent launches of a 20-step decode are captured once per (shape, buffer) signature into a CUDA
+// graph and replayed on the handle's own stream (stream capture is illegal on the legacy default stream callers often
+// pass); fork/join events order it against the caller's stream.  Profiling mode runs eagerly (event brackets).
 static int decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, const int64_t* bos_ids, const uint8_t* forbid,
                   int batch, int tp, int beam, int min_len, int max_len, int64_t* preds, float* lprobs, int64_t* mult_preds,
                   float* mult_lprobs, int32_t* info, cudaStream_t st) {
   const int rows = batch * beam;
   DecoderDims dd{rows, beam, tp, max_len, h->cfg.vocab_size};
   DecWs w;
-  if (int rc = dec_prepare(h, frame_embs, batch, tp, rows, max_len, &w, st)) return rc;
+  if (int rc = dec_prepare(h, batch, tp, rows, max_len, &w)) return rc;
   BeamState bs;
   WS(h, "tok0", int, (size_t)rows * (max_len + 1), tok0);
   WS(h, "tok1", int, (size_t)rows * (max_len + 1), tok1);
@@ -639,17 +682,47 @@ static int decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, c
   WS(h, "best_len", int, batch, best_len);
   bs.tokens[0] = tok0; bs.tokens[1] = tok1; bs.src_row[0] = src0; bs.src_row[1] = src1;
   bs.sum_lp = sum_lp; bs.live = live; bs.out_preds = out_preds; bs.out_lp = out_lp; bs.done = done;
-  if (int rc = launch_beam_init(bos_ids, bs, dd, st)) return rc;
-  int cur = 0;
-  for (int i = 0; i < max_len; ++i) {
-    if (int rc = dec_step(h, w, bs.tokens[cur], bs.src_row[cur], lens, i, dd, done, st)) return rc;
-    { Prof _p(h, CNB_K_BEAM, st); if (int rc = launch_beam_step(w.logits, forbid, bs, i, cur, min_len, dd, st)) return rc; }
-    cur ^= 1;
+
+  if (h->prof_on || !h->use_graphs)
+    return decode_body(h, w, bs, frame_embs, lens, bos_ids, forbid, batch, min_len, dd, preds, lprobs, mult_preds, mult_lprobs,
+                       info, best_len, st);
+
+  const std::vector<int64_t> key = {batch, tp, beam, min_len, max_len, (int64_t)frame_embs, (int64_t)lens, (int64_t)bos_ids,
+                                    (int64_t)forbid, (int64_t)preds, (int64_t)lprobs, (int64_t)mult_preds,
+                                    (int64_t)mult_lprobs, (int64_t)info, (int64_t)w.logits, (int64_t)w.kc, (int64_t)tok0};
+  DecGraph* dg = nullptr;
+  for (auto& g : h->dec_graphs)
+    if (g.key == key) dg = &g;
+  if (!dg) {
+    const int64_t before = g_launches.load();
+    CNB_CUDA_OK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = decode_body(h, w, bs, frame_embs, lens, bos_ids, forbid, batch, min_len, dd, preds, lprobs, mult_preds,
+                               mult_lprobs, info, best_len, h->stream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+    const int64_t n_kernels = g_launches.load() - before;
+    g_launches.fetch_sub(n_kernels);  // captured, not executed
+    if (rc) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    CNB_CUDA_OK(ce);
+    cudaGraphExec_t exec = nullptr;
+    CNB_CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
+    CNB_CUDA_OK(cudaGraphDestroy(graph));
+    if (h->dec_graphs.size() >= 8) {  // bounded cache: drop the oldest signature
+      cudaGraphExecDestroy(h->dec_graphs.front().exec);
+      h->dec_graphs.erase(h->dec_graphs.begin());
+    }
+    h->dec_graphs.push_back(DecGraph{key, exec, n_kernels});
+    dg = &h->dec_graphs.back();
   }
-  if (int rc = launch_beam_finalize(bs, preds, lprobs, best_len, dd, st)) return rc;
-  gather_mult_kernel<<<(rows * max_len + 255) / 256, 256, 0, st>>>(bs, mult_preds, mult_lprobs, best_len, info, rows, max_len,
-                                                                  batch);
-  CNB_LAUNCH_OK();
+  CNB_CUDA_OK(cudaEventRecord(h->ev_fork, st));
+  CNB_CUDA_OK(cudaStreamWaitEvent(h->stream, h->ev_fork, 0));
+  CNB_CUDA_OK(cudaGraphLaunch(dg->exec, h->stream));
+  g_launches.fetch_add(dg->n_kernels);
+  CNB_CUDA_OK(cudaEventRecord(h->ev_join, h->stream));
+  CNB_CUDA_OK(cudaStreamWaitEvent(st, h->ev_join, 0));
   return 0;
 }
 
@@ -699,6 +772,11 @@ int cnb_create(const cnb_config* cfg, cnb_handle** out) {
   }
   cnb_handle* h = new cnb_handle();
   h->cfg = *cfg;
+  CNB_CUDA_OK(cudaSetDevice(cfg->device));
+  CNB_CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CNB_CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CNB_CUDA_OK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  h->use_graphs = (cfg->reserved[0] & 1) == 0;  // reserved[0] bit 0: disable CUDA graphs (debugging)
   *out = h;
   return 0;
 }
@@ -712,6 +790,10 @@ int cnb_destroy(cnb_handle* h) {
   if (h->arena.base) cudaFree(h->arena.base);
   if (h->zero_flag) cudaFree(h->zero_flag);
   for (auto e : h->prof_events) cudaEventDestroy(e);
+  for (auto& g : h->dec_graphs) cudaGraphExecDestroy(g.exec);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
 }
@@ -815,7 +897,8 @@ int cnb_decoder_logits(cnb_handle* h, const float* frame_embs, const int32_t* le
   cudaStream_t st = (cudaStream_t)stream;
   DecoderDims dd{batch, 1, tp, steps, h->cfg.vocab_size};
   DecWs w;
-  if (int rc = dec_prepare(h, frame_embs, batch, tp, batch, steps, &w, st)) return rc;
+  if (int rc = dec_prepare(h, batch, tp, batch, steps, &w)) return rc;
+  if (int rc = dec_project(h, frame_embs, batch, tp, w, st)) return rc;
   WS(h, "tok0", int, (size_t)batch * (steps + 1), tok);
   WS(h, "src0", int, (size_t)batch * steps, src);
   tokens_i64_to_i32_kernel<<<(batch * steps + 255) / 256, 256, 0, st>>>(tokens, tok, batch, steps, steps + 1);
@@ -861,7 +944,7 @@ int cnb_caption_host(cnb_handle* h, const float* wav_host, const int64_t* x_lens
   if (int rc = check_audio(batch, n)) return rc;
   const int V = h->cfg.vocab_size;
   const int rows = batch * beam;
-  cudaStream_t st = 0;
+  cudaStream_t st = h->stream;
   WS(h, "io_wav", float, (size_t)batch * n, wav);
   WS(h, "io_bos", int64_t, batch, bos);
   WS(h, "io_forbid", uint8_t, V, forbid);

@@ -113,20 +113,24 @@ cross_attn_kernel(const float* __restrict__ q, const float* __restrict__ ck, con
   attn[(int64_t)r * kD + h * kHeadDim + lane] = acc * inv;
 }
 
-// ---- x = LayerNorm(x + delta) (eps 1e-5, biased variance): one warp per row of 256 --------------------------------------
+// ---- x = LayerNorm(x + bias + sum_s delta[s]) (eps 1e-5, biased variance): one warp per row of 256 ---------------------
+// delta holds nsplit slabs of (rows, 256): the raw split-K partial sums of the preceding GEMM, added in a fixed order.
 __global__ void __launch_bounds__(256)
-add_ln_kernel(float* __restrict__ x, const float* __restrict__ delta, const float* __restrict__ g, const float* __restrict__ b,
-              const int* __restrict__ done, int rows) {
+add_ln_kernel(float* __restrict__ x, const float* __restrict__ delta, int nsplit, const float* __restrict__ bias,
+              const float* __restrict__ g, const float* __restrict__ b, const int* __restrict__ done, int rows) {
   if (done && done[0]) return;
   const int lane = threadIdx.x & 31;
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= rows) return;
+  const int64_t slab = (int64_t)rows * kD;
   float v[8];
   float s = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = lane + 32 * j;
-    v[j] = x[(int64_t)r * kD + c] + delta[(int64_t)r * kD + c];
+    float d = bias ? bias[c] : 0.f;
+    for (int sp = 0; sp < nsplit; ++sp) d += delta[sp * slab + (int64_t)r * kD + c];
+    v[j] = x[(int64_t)r * kD + c] + d;
     s += v[j];
   }
   const float mean = warp_sum(s) * (1.f / kD);
@@ -166,9 +170,9 @@ int launch_cross_attn(const float* q, const float* ck, const float* cv, int64_t 
   return 0;
 }
 
-int launch_add_ln(float* x, const float* delta, const float* g, const float* b, int rows, const int* done,
-                  cudaStream_t stream) {
-  add_ln_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, delta, g, b, done, rows);
+int launch_add_ln(float* x, const float* delta, int nsplit, const float* bias, const float* g, const float* b, int rows,
+                  const int* done, cudaStream_t stream) {
+  add_ln_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(x, delta, nsplit, bias, g, b, done, rows);
   CNB_LAUNCH_OK();
   return 0;
 }

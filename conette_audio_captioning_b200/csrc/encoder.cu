@@ -163,6 +163,164 @@ dwconv_ln_kernel(const float* __restrict__ x, int H, const float* __restrict__ w
   }
 }
 
+// =====================================================================================================================
+// K-DWLN v2 (stages 1-3): marching ring buffer.
+//   CTA = (clip, column strip of TW pixels, segment of SEG output rows).  An 8-row ring of (TW+6) x C fp32 input pixels
+//   lives in shared memory; row h+4 is prefetched with 16-byte cp.async (zero-filled outside the image = conv padding)
+//   while row h is computed, so every input row is fetched once per CTA (plus the 6-row halo at segment starts).
+//   thread = (channel pair, 7-pixel strip): its 49 x float2 weights stay in registers for the whole march; each output row
+//   costs 343 packed FFMA2 (fma.rn.f32x2) fed by 91 conflict-free LDS.64.  LayerNorm as in v1 (two-pass, fixed order).
+// =====================================================================================================================
+__device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, bool valid) {
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem);
+  const int bytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem), "r"(bytes) : "memory");
+}
+
+template <int C, int W, int TW, typename OutT>
+__global__ void __launch_bounds__(((C / 2 + 31) / 32) * 32 * (TW / 7), 1)
+dwconv_ln_ring_kernel(const float* __restrict__ x, int H, int seg_rows, const float* __restrict__ w_t,
+                      const float* __restrict__ bias, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                      OutT* __restrict__ out) {
+  constexpr int CP = C / 2;
+  constexpr int CP_PAD = ((CP + 31) / 32) * 32;
+  constexpr int PW = 7;
+  constexpr int NW = CP_PAD / 32;
+  constexpr int NT = CP_PAD * (TW / PW);
+  constexpr int RW = TW + 6;            // ring row width in pixels (3-pixel halo each side)
+  constexpr int ROW_F4 = RW * C / 4;    // float4 per ring row
+  extern __shared__ __align__(16) float s_dyn[];
+  float* ring = s_dyn;                              // [8][RW][C]
+  float* s_sum = s_dyn + 8 * RW * C;                // [TW][NW]
+  float* s_sq = s_sum + TW * NW;                    // [TW][NW]
+
+  const int tid = threadIdx.x;
+  const int strip_t = tid / CP_PAD;
+  const int cp = tid - strip_t * CP_PAD;
+  const int wis = cp >> 5;
+  const bool active = cp < CP;
+  constexpr int STRIPS = W / TW;
+  const int strip_c = blockIdx.x % STRIPS, seg = blockIdx.x / STRIPS;
+  const int b = blockIdx.y;
+  const int w_base = strip_c * TW;      // first output column of this CTA
+  const int h0 = seg * seg_rows;
+  const int h1 = min(H, h0 + seg_rows);
+  if (h0 >= H) return;
+  const float* xb = x + (int64_t)b * H * W * C;
+
+  auto load_row = [&](int r) {          // image row r -> ring slot (r - (h0 - 3)) & 7
+    float* dst = ring + ((r - h0 + 3) & 7) * (RW * C);
+    const bool row_ok = (r >= 0) && (r < H);
+    for (int i = tid; i < ROW_F4; i += NT) {
+      const int px = i / (C / 4), c4 = i - px * (C / 4);
+      const int col = w_base + px - 3;
+      const bool ok = row_ok && col >= 0 && col < W;
+      cp_async16_zfill(dst + px * C + c4 * 4, ok ? xb + ((int64_t)r * W + col) * C + c4 * 4 : xb, ok);
+    }
+  };
+  for (int r = h0 - 3; r <= h0 + 3; ++r) load_row(r);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+
+  float2 wr[49];
+  float2 bi = make_float2(0.f, 0.f), g = bi, be = bi;
+  if (active) {
+#pragma unroll
+    for (int t = 0; t < 49; ++t) wr[t] = __ldg(reinterpret_cast<const float2*>(w_t + t * C + 2 * cp));
+    bi = *reinterpret_cast<const float2*>(bias + 2 * cp);
+    g = *reinterpret_cast<const float2*>(ln_g + 2 * cp);
+    be = *reinterpret_cast<const float2*>(ln_b + 2 * cp);
+  } else {
+#pragma unroll
+    for (int t = 0; t < 49; ++t) wr[t] = make_float2(0.f, 0.f);
+  }
+  const int wl0 = strip_t * PW;         // first output column of this thread inside the CTA strip
+
+  for (int h = h0; h < h1; ++h) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                    // rows h-3..h+3 resident; everybody has left row h-1
+    if (h + 4 <= h1 + 2) load_row(h + 4);  // needed by output rows up to h1-1 (+3); overwrites the slot of row h-4
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    float2 acc[PW];
+#pragma unroll
+    for (int p = 0; p < PW; ++p) acc[p] = bi;
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        const float* row = ring + ((h - h0 + i) & 7) * (RW * C) + wl0 * C + 2 * cp;
+        float2 in[PW + 6];
+#pragma unroll
+        for (int j = 0; j < PW + 6; ++j) in[j] = *reinterpret_cast<const float2*>(row + j * C);
+#pragma unroll
+        for (int p = 0; p < PW; ++p)
+#pragma unroll
+          for (int j = 0; j < 7; ++j) acc[p] = __ffma2_rn(in[p + j], wr[i * 7 + j], acc[p]);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < PW; ++p) {
+      const float s = warp_sum(active ? acc[p].x + acc[p].y : 0.f);
+      if ((tid & 31) == 0) s_sum[(wl0 + p) * NW + wis] = s;
+    }
+    __syncthreads();
+    float mean[PW];
+#pragma unroll
+    for (int p = 0; p < PW; ++p) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < NW; ++i) t += s_sum[(wl0 + p) * NW + i];
+      mean[p] = t * (1.f / C);
+      const float dx = active ? acc[p].x - mean[p] : 0.f, dy = active ? acc[p].y - mean[p] : 0.f;
+      const float s = warp_sum(dx * dx + dy * dy);
+      if ((tid & 31) == 0) s_sq[(wl0 + p) * NW + wis] = s;
+    }
+    __syncthreads();
+    if (active) {
+      OutT* o = out + (((int64_t)b * H + h) * W + w_base + wl0) * C + 2 * cp;
+#pragma unroll
+      for (int p = 0; p < PW; ++p) {
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) q += s_sq[(wl0 + p) * NW + i];
+        const float rstd = 1.f / sqrtf(q * (1.f / C) + kLnEps);
+        const float y0 = (acc[p].x - mean[p]) * rstd * g.x + be.x;
+        const float y1 = (acc[p].y - mean[p]) * rstd * g.y + be.y;
+        if constexpr (sizeof(OutT) == 2) {
+          *reinterpret_cast<__nv_bfloat162*>(o + (int64_t)p * C) = __floats2bfloat162_rn(y0, y1);
+        } else {
+          *reinterpret_cast<float2*>(o + (int64_t)p * C) = make_float2(y0, y1);
+        }
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+template <int C, int W, int TW, typename OutT>
+static int launch_dwconv_ring_t(const float* x, int batch, int h, const float* w_t, const float* bias, const float* ln_g,
+                                const float* ln_b, OutT* out, cudaStream_t stream) {
+  constexpr int threads = ((C / 2 + 31) / 32) * 32 * (TW / 7);
+  constexpr int NW = ((C / 2 + 31) / 32);
+  constexpr size_t smem = (size_t)(8 * (TW + 6) * C + 2 * TW * NW) * sizeof(float);
+  auto kern = dwconv_ln_ring_kernel<C, W, TW, OutT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CNB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  constexpr int strips = W / TW;
+  // one wave of CTAs (1 CTA / SM): segments sized so that strips * batch * n_seg ~ #SMs, but at least 8 rows each
+  int n_seg = kNumSMs / (strips * batch);
+  if (n_seg < 1) n_seg = 1;
+  int seg_rows = (int)ceil_div(h, n_seg);
+  if (seg_rows < 8) seg_rows = 8;
+  n_seg = (int)ceil_div(h, seg_rows);
+  dim3 grid(strips * n_seg, batch);
+  kern<<<grid, threads, smem, stream>>>(x, h, seg_rows, w_t, bias, ln_g, ln_b, out);
+  CNB_LAUNCH_OK();
+  return 0;
+}
+
 template <int C, int W, typename OutT>
 static int launch_dwconv_ln_t(const float* x, int batch, int h, const float* w_t, const float* bias, const float* ln_g,
                               const float* ln_b, OutT* out, cudaStream_t stream) {
@@ -176,9 +334,9 @@ static int launch_dwconv_ln_t(const float* x, int batch, int h, const float* w_t
 template <typename OutT>
 int launch_dwconv_ln(const float* x, int batch, int h, int w, int c, const float* w_t, const float* bias, const float* ln_g,
                      const float* ln_b, OutT* out, cudaStream_t stream) {
-  if (c == 96 && w == 56) return launch_dwconv_ln_t<96, 56, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
-  if (c == 192 && w == 28) return launch_dwconv_ln_t<192, 28, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
-  if (c == 384 && w == 14) return launch_dwconv_ln_t<384, 14, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
+  if (c == 96 && w == 56) return launch_dwconv_ring_t<96, 56, 28, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
+  if (c == 192 && w == 28) return launch_dwconv_ring_t<192, 28, 14, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
+  if (c == 384 && w == 14) return launch_dwconv_ring_t<384, 14, 7, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
   if (c == 768 && w == 7) return launch_dwconv_ln_t<768, 7, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
   set_error("dwconv_ln: unsupported (C, W) = (" + std::to_string(c) + ", " + std::to_string(w) + ")");
   return -1;

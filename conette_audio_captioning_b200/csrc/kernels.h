@@ -55,9 +55,10 @@ struct EpiParams {
   const float* resid = nullptr;  // (M, N) f32, row stride = ldo
 };
 // fp32 SIMT GEMM (parity mode + decoder).  A (M,K) f32 row stride lda; W (N,K) f32; out (M,N) OutT row stride ldo.
+// splits > 1 = split-K: slice z writes raw partial sums to out + z*M*ldo and the epilogue is left to the consumer.
 template <typename OutT>
 int launch_gemm_f32(const float* a, int64_t lda, const float* w, int m, int n, int k, Epilogue epi, const EpiParams& ep,
-                    OutT* out, int64_t ldo, cudaStream_t stream);
+                    OutT* out, int64_t ldo, cudaStream_t stream, int splits = 1);
 
 // bf16 tcgen05 GEMM (fast mode).  A (M,K) bf16 contiguous, W (N,K) bf16 contiguous (both K-major, TMA-fed).
 struct TcGemmPlan;  // opaque: TMA descriptors + tile configuration
@@ -90,8 +91,9 @@ int launch_self_attn(const float* qkv, float* kcache, float* vcache, const int* 
                      const DecoderDims& dd, const int* done, cudaStream_t stream);
 int launch_cross_attn(const float* q, const float* ck, const float* cv, int64_t kv_stride, const int* lens, float* attn,
                       const DecoderDims& dd, const int* done, cudaStream_t stream);
-int launch_add_ln(float* x, const float* delta, const float* g, const float* b, int rows, const int* done,
-                  cudaStream_t stream);
+// x = LayerNorm(x + bias + sum_s delta[s]) (eps 1e-5), in place; delta = nsplit slabs of (rows, 256), bias may be null
+int launch_add_ln(float* x, const float* delta, int nsplit, const float* bias, const float* g, const float* b, int rows,
+                  const int* done, cudaStream_t stream);
 int launch_beam_init(const int64_t* bos_ids, BeamState st, const DecoderDims& dd, cudaStream_t stream);
 int launch_beam_step(float* logits, const uint8_t* forbid, BeamState st, int step, int cur, int min_len,
                      const DecoderDims& dd, cudaStream_t stream);
