@@ -25,7 +25,7 @@ constexpr int kDepths[4] = {3, 3, 9, 3};
 constexpr int kStageW[4] = {56, 28, 14, 7};
 constexpr int kMels = 224, kBins = 513, kNfft = 1024, kHop = 320;
 constexpr int kD = 256, kFF = 2048, kLayers = 6, kTags = 527;
-constexpr int kDefaultChunk = 8;
+constexpr int kDefaultChunk = 64;  // measured on B200: larger encoder passes amortise tails; 64 x 10 s needs ~3.5 GB
 
 struct HostTensor {
   std::vector<float> data;

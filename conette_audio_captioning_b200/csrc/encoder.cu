@@ -164,17 +164,48 @@ dwconv_ln_kernel(const float* __restrict__ x, int H, const float* __restrict__ w
 }
 
 // =====================================================================================================================
-// K-DWLN v2 (stages 1-3): marching ring buffer.
-//   CTA = (clip, column strip of TW pixels, segment of SEG output rows).  An 8-row ring of (TW+6) x C fp32 input pixels
-//   lives in shared memory; row h+4 is prefetched with 16-byte cp.async (zero-filled outside the image = conv padding)
-//   while row h is computed, so every input row is fetched once per CTA (plus the 6-row halo at segment starts).
-//   thread = (channel pair, 7-pixel strip): its 49 x float2 weights stay in registers for the whole march; each output row
-//   costs 343 packed FFMA2 (fma.rn.f32x2) fed by 91 conflict-free LDS.64.  LayerNorm as in v1 (two-pass, fixed order).
+// K-DWLN v2 (stages 1-3): marching ring buffer, two output rows per iteration.
+//   CTA = (clip, column strip of TW pixels, segment of SEG output rows).  A 10-row ring of (TW+6) x C fp32 input pixels
+//   lives in shared memory; rows h+5, h+6 are prefetched with 16-byte cp.async (zero-filled outside the image = conv
+//   padding) while output rows h, h+1 are computed, so every input row is fetched once per CTA (+ the 6-row halo at
+//   segment starts).  thread = (channel pair, 7-pixel strip): its 49 x float2 weights stay in registers for the whole
+//   march; each of the 8 live input rows is read once (13 LDS.64) and feeds both output rows: 686 packed FFMA2
+//   (fma.rn.f32x2) per 104 conflict-free LDS.64.  LayerNorm: one pass (sum, sum of squares) with a 16-value butterfly
+//   that costs 16 shuffles per 16 values, per-warp partials combined in fixed order through shared memory (1 barrier).
 // =====================================================================================================================
 __device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, bool valid) {
   const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem);
   const int bytes = valid ? 16 : 0;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem), "r"(bytes) : "memory");
+}
+
+// Sum 16 per-lane values across the warp with 16 shuffles: afterwards lane l holds the total of value
+// idx(l) = 8*bit4(l) + 4*bit3(l) + 2*bit2(l) + bit1(l)  (lanes l and l^1 hold the same value).
+__device__ __forceinline__ float warp_sum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const bool up = lane & 16;
+    const float keep = up ? v[k + 8] : v[k], send = up ? v[k] : v[k + 8];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool up = lane & 8;
+    const float keep = up ? v[k + 4] : v[k], send = up ? v[k] : v[k + 4];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const bool up = lane & 4;
+    const float keep = up ? v[k + 2] : v[k], send = up ? v[k] : v[k + 2];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const bool up = lane & 2;
+    const float keep = up ? v[1] : v[0], send = up ? v[0] : v[1];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
 template <int C, int W, int TW, typename OutT>
@@ -189,12 +220,12 @@ dwconv_ln_ring_kernel(const float* __restrict__ x, int H, int seg_rows, const fl
   constexpr int NT = CP_PAD * (TW / PW);
   constexpr int RW = TW + 6;            // ring row width in pixels (3-pixel halo each side)
   constexpr int ROW_F4 = RW * C / 4;    // float4 per ring row
+  constexpr int NS = 10;                // ring slots: 8 live rows + 2 in flight
   extern __shared__ __align__(16) float s_dyn[];
-  float* ring = s_dyn;                              // [8][RW][C]
-  float* s_sum = s_dyn + 8 * RW * C;                // [TW][NW]
-  float* s_sq = s_sum + TW * NW;                    // [TW][NW]
+  float* ring = s_dyn;                              // [NS][RW][C] (+ pad so that idle lanes of a padded warp stay in bounds)
+  float* s_part = s_dyn + NS * RW * C + 2 * (CP_PAD - CP);  // [2 rows][2 (sum, sq)][TW][NW]
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int strip_t = tid / CP_PAD;
   const int cp = tid - strip_t * CP_PAD;
   const int wis = cp >> 5;
@@ -208,8 +239,8 @@ dwconv_ln_ring_kernel(const float* __restrict__ x, int H, int seg_rows, const fl
   if (h0 >= H) return;
   const float* xb = x + (int64_t)b * H * W * C;
 
-  auto load_row = [&](int r) {          // image row r -> ring slot (r - (h0 - 3)) & 7
-    float* dst = ring + ((r - h0 + 3) & 7) * (RW * C);
+  auto load_row = [&](int r, int slot) {
+    float* dst = ring + slot * (RW * C);
     const bool row_ok = (r >= 0) && (r < H);
     for (int i = tid; i < ROW_F4; i += NT) {
       const int px = i / (C / 4), c4 = i - px * (C / 4);
@@ -218,8 +249,11 @@ dwconv_ln_ring_kernel(const float* __restrict__ x, int H, int seg_rows, const fl
       cp_async16_zfill(dst + px * C + c4 * 4, ok ? xb + ((int64_t)r * W + col) * C + c4 * 4 : xb, ok);
     }
   };
-  for (int r = h0 - 3; r <= h0 + 3; ++r) load_row(r);
+  for (int i = 0; i < 8; ++i) load_row(h0 - 3 + i, i);
   asm volatile("cp.async.commit_group;" ::: "memory");
+  if (CP_PAD != CP) {  // idle lanes of a padded warp read past their pixel (times zero weights): keep that data finite
+    for (int i = tid; i < 2 * RW * C + 2 * (CP_PAD - CP); i += NT) ring[8 * RW * C + i] = 0.f;  // slots 8, 9 + tail pad
+  }
 
   float2 wr[49];
   float2 bi = make_float2(0.f, 0.f), g = bi, be = bi;
@@ -229,69 +263,95 @@ dwconv_ln_ring_kernel(const float* __restrict__ x, int H, int seg_rows, const fl
     bi = *reinterpret_cast<const float2*>(bias + 2 * cp);
     g = *reinterpret_cast<const float2*>(ln_g + 2 * cp);
     be = *reinterpret_cast<const float2*>(ln_b + 2 * cp);
-  } else {
+  } else {  // idle lanes of a padded warp run the same instruction stream on zero weights (no divergence)
 #pragma unroll
     for (int t = 0; t < 49; ++t) wr[t] = make_float2(0.f, 0.f);
   }
   const int wl0 = strip_t * PW;         // first output column of this thread inside the CTA strip
+  int slot0 = 0;                        // ring slot of input row h-3
 
-  for (int h = h0; h < h1; ++h) {
+  for (int h = h0; h < h1; h += 2) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();                    // rows h-3..h+3 resident; everybody has left row h-1
-    if (h + 4 <= h1 + 2) load_row(h + 4);  // needed by output rows up to h1-1 (+3); overwrites the slot of row h-4
-    asm volatile("cp.async.commit_group;" ::: "memory");
-
-    float2 acc[PW];
+    __syncthreads();                    // rows h-3..h+4 resident; everybody has left rows h-2, h-1
+    {
+      const int s8 = slot0 + 8 >= NS ? slot0 + 8 - NS : slot0 + 8;
+      const int s9 = s8 + 1 >= NS ? s8 + 1 - NS : s8 + 1;
+      if (h + 5 <= h1 + 2) load_row(h + 5, s8);  // overwrites rows h-5 / h-4
+      if (h + 6 <= h1 + 2) load_row(h + 6, s9);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    float2 acc0[PW], acc1[PW];
 #pragma unroll
-    for (int p = 0; p < PW; ++p) acc[p] = bi;
-    if (active) {
+    for (int p = 0; p < PW; ++p) acc0[p] = acc1[p] = bi;
 #pragma unroll
-      for (int i = 0; i < 7; ++i) {
-        const float* row = ring + ((h - h0 + i) & 7) * (RW * C) + wl0 * C + 2 * cp;
-        float2 in[PW + 6];
+    for (int i = 0; i < 8; ++i) {
+      const int sl = slot0 + i >= NS ? slot0 + i - NS : slot0 + i;
+      const float* row = ring + sl * (RW * C) + wl0 * C + 2 * cp;
+      float2 in[PW + 6];
 #pragma unroll
-        for (int j = 0; j < PW + 6; ++j) in[j] = *reinterpret_cast<const float2*>(row + j * C);
+      for (int j = 0; j < PW + 6; ++j) in[j] = *reinterpret_cast<const float2*>(row + j * C);
+      if (i < 7) {
 #pragma unroll
         for (int p = 0; p < PW; ++p)
 #pragma unroll
-          for (int j = 0; j < 7; ++j) acc[p] = __ffma2_rn(in[p + j], wr[i * 7 + j], acc[p]);
+          for (int j = 0; j < 7; ++j) acc0[p] = __ffma2_rn(in[p + j], wr[i * 7 + j], acc0[p]);
+      }
+      if (i > 0) {
+#pragma unroll
+        for (int p = 0; p < PW; ++p)
+#pragma unroll
+          for (int j = 0; j < 7; ++j) acc1[p] = __ffma2_rn(in[p + j], wr[(i - 1) * 7 + j], acc1[p]);
       }
     }
+    // ---- LayerNorm statistics: (sum, sumsq) for 14 pixels
+    float sm[16], sq[16];
 #pragma unroll
     for (int p = 0; p < PW; ++p) {
-      const float s = warp_sum(active ? acc[p].x + acc[p].y : 0.f);
-      if ((tid & 31) == 0) s_sum[(wl0 + p) * NW + wis] = s;
+      sm[p] = acc0[p].x + acc0[p].y;
+      sq[p] = fmaf(acc0[p].x, acc0[p].x, acc0[p].y * acc0[p].y);
+      sm[p + 8] = acc1[p].x + acc1[p].y;
+      sq[p + 8] = fmaf(acc1[p].x, acc1[p].x, acc1[p].y * acc1[p].y);
     }
-    __syncthreads();
-    float mean[PW];
-#pragma unroll
-    for (int p = 0; p < PW; ++p) {
-      float t = 0.f;
-#pragma unroll
-      for (int i = 0; i < NW; ++i) t += s_sum[(wl0 + p) * NW + i];
-      mean[p] = t * (1.f / C);
-      const float dx = active ? acc[p].x - mean[p] : 0.f, dy = active ? acc[p].y - mean[p] : 0.f;
-      const float s = warp_sum(dx * dx + dy * dy);
-      if ((tid & 31) == 0) s_sq[(wl0 + p) * NW + wis] = s;
+    sm[7] = sm[15] = sq[7] = sq[15] = 0.f;
+    const float tsum = warp_sum16(sm, lane);
+    const float tsq = warp_sum16(sq, lane);
+    if ((lane & 1) == 0) {
+      const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+      const int row = idx >> 3, p = idx & 7;
+      if (p < PW) {
+        s_part[((row * 2 + 0) * TW + wl0 + p) * NW + wis] = tsum;
+        s_part[((row * 2 + 1) * TW + wl0 + p) * NW + wis] = tsq;
+      }
     }
     __syncthreads();
     if (active) {
-      OutT* o = out + (((int64_t)b * H + h) * W + w_base + wl0) * C + 2 * cp;
 #pragma unroll
-      for (int p = 0; p < PW; ++p) {
-        float q = 0.f;
+      for (int row = 0; row < 2; ++row) {
+        if (h + row >= h1) break;
+        OutT* o = out + (((int64_t)b * H + h + row) * W + w_base + wl0) * C + 2 * cp;
 #pragma unroll
-        for (int i = 0; i < NW; ++i) q += s_sq[(wl0 + p) * NW + i];
-        const float rstd = 1.f / sqrtf(q * (1.f / C) + kLnEps);
-        const float y0 = (acc[p].x - mean[p]) * rstd * g.x + be.x;
-        const float y1 = (acc[p].y - mean[p]) * rstd * g.y + be.y;
-        if constexpr (sizeof(OutT) == 2) {
-          *reinterpret_cast<__nv_bfloat162*>(o + (int64_t)p * C) = __floats2bfloat162_rn(y0, y1);
-        } else {
-          *reinterpret_cast<float2*>(o + (int64_t)p * C) = make_float2(y0, y1);
+        for (int p = 0; p < PW; ++p) {
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int i = 0; i < NW; ++i) {
+            s1 += s_part[((row * 2 + 0) * TW + wl0 + p) * NW + i];
+            s2 += s_part[((row * 2 + 1) * TW + wl0 + p) * NW + i];
+          }
+          const float mean = s1 * (1.f / C);
+          const float var = fmaxf(s2 * (1.f / C) - mean * mean, 0.f);
+          const float rstd = 1.f / sqrtf(var + kLnEps);
+          const float2 a = row ? acc1[p] : acc0[p];
+          const float y0 = (a.x - mean) * rstd * g.x + be.x;
+          const float y1 = (a.y - mean) * rstd * g.y + be.y;
+          if constexpr (sizeof(OutT) == 2) {
+            *reinterpret_cast<__nv_bfloat162*>(o + (int64_t)p * C) = __floats2bfloat162_rn(y0, y1);
+          } else {
+            *reinterpret_cast<float2*>(o + (int64_t)p * C) = make_float2(y0, y1);
+          }
         }
       }
     }
+    slot0 = slot0 + 2 >= NS ? slot0 + 2 - NS : slot0 + 2;
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
@@ -299,9 +359,10 @@ dwconv_ln_ring_kernel(const float* __restrict__ x, int H, int seg_rows, const fl
 template <int C, int W, int TW, typename OutT>
 static int launch_dwconv_ring_t(const float* x, int batch, int h, const float* w_t, const float* bias, const float* ln_g,
                                 const float* ln_b, OutT* out, cudaStream_t stream) {
-  constexpr int threads = ((C / 2 + 31) / 32) * 32 * (TW / 7);
-  constexpr int NW = ((C / 2 + 31) / 32);
-  constexpr size_t smem = (size_t)(8 * (TW + 6) * C + 2 * TW * NW) * sizeof(float);
+  constexpr int CP_PAD = ((C / 2 + 31) / 32) * 32;
+  constexpr int threads = CP_PAD * (TW / 7);
+  constexpr int NW = CP_PAD / 32;
+  constexpr size_t smem = (size_t)(10 * (TW + 6) * C + 2 * (CP_PAD - C / 2) + 4 * TW * NW) * sizeof(float);
   auto kern = dwconv_ln_ring_kernel<C, W, TW, OutT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -309,10 +370,11 @@ static int launch_dwconv_ring_t(const float* x, int batch, int h, const float* w
     attr_set = true;
   }
   constexpr int strips = W / TW;
-  // one wave of CTAs (1 CTA / SM): segments sized so that strips * batch * n_seg ~ #SMs, but at least 8 rows each
+  // about one wave of CTAs (1 CTA / SM): segments sized so that strips * batch * n_seg ~ #SMs, but at least 8 rows each
   int n_seg = kNumSMs / (strips * batch);
   if (n_seg < 1) n_seg = 1;
   int seg_rows = (int)ceil_div(h, n_seg);
+  seg_rows += seg_rows & 1;  // rows are produced in pairs
   if (seg_rows < 8) seg_rows = 8;
   n_seg = (int)ceil_div(h, seg_rows);
   dim3 grid(strips * n_seg, batch);

@@ -6,7 +6,7 @@
 // Structure (persistent, warp-specialised, one CTA per SM):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of A (128 x 64) and W (BLOCK_N x 64) tiles, 128B swizzle
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16, kind::f16, bf16 in / f32 acc)
-//   warps 2..9  epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias / GELU / layer-scale+residual -> global stores
+//   warps 2..17 epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias / GELU / layer-scale+residual -> global stores
 //               (GELU in this bf16 path = 0.5x(1+tanh(x(a1+a3x^2+a5x^4))), a minimax fit of the erf form, max abs error
 //               2.5e-5 + the 2^-11 relative error of tanh.approx -- both below the bf16 rounding of the stored hidden)
 // Pipelines: STAGES-deep smem ring (full/empty mbarriers) and a 2-deep TMEM accumulator ring (tmem_full/tmem_empty) so
@@ -22,7 +22,9 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 bytes = one swizzle-128B atom row
 constexpr int kUmmaK = 16;
 constexpr int kStages = 4;
-constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter, alternating 32-column chunks
+constexpr int kEpiWarps = 16;                      // four warps per TMEM lane quarter, interleaved 16-column chunks
+constexpr int kEpiChunk = 16;                      // accumulator columns per tcgen05.ld
+constexpr int kMaxN = 3072;                        // bias / layer-scale vectors are staged in shared memory
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -85,16 +87,13 @@ __device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t adesc
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
-        "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
-        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -118,45 +117,50 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
 // ---------------------------------------------------------------------------------------------------------------------
 // epilogue math on 32 consecutive columns of one output row
 // ---------------------------------------------------------------------------------------------------------------------
-// erf-GELU through one MUFU.TANH: coefficients fitted so that max |approx - 0.5x(1+erf(x/sqrt2))| = 2.5e-5 over [-8, 8]
-__device__ __forceinline__ float gelu_tanh_fit(float x) {
-  const float x2 = x * x;
-  const float u = x * fmaf(x2, fmaf(x2, -3.51516789e-04f, 3.70056460e-02f), 7.97507884e-01f);
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
-  const float hx = 0.5f * x;
-  return fmaf(hx, t, hx);
+// erf-GELU through one MUFU.TANH per element: coefficients fitted so that max |approx - 0.5x(1+erf(x/sqrt2))| = 2.5e-5
+// over [-8, 8]; evaluated two elements at a time with the packed fp32 pipe (fma.rn.f32x2 / mul.rn.f32x2).
+__device__ __forceinline__ float2 gelu_tanh_fit2(float2 x) {
+  const float2 x2 = __fmul2_rn(x, x);
+  float2 p = __ffma2_rn(x2, make_float2(-3.51516789e-04f, -3.51516789e-04f), make_float2(3.70056460e-02f, 3.70056460e-02f));
+  p = __ffma2_rn(x2, p, make_float2(7.97507884e-01f, 7.97507884e-01f));
+  const float2 u = __fmul2_rn(x, p);
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(u.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(u.y));
+  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  return __ffma2_rn(hx, t, hx);
 }
 
+// v: kEpiChunk consecutive accumulator columns of output row m; sb / ss: bias / layer-scale for those columns (smem)
 template <int EPI, typename OutT>
-__device__ __forceinline__ void epilogue_row32(float* v, int64_t m, int n0, const EpiParams& ep, OutT* out, int64_t ldo) {
+__device__ __forceinline__ void epilogue_chunk(float* v, int64_t m, int n0, const float* sb, const float* ss,
+                                               const EpiParams& ep, OutT* out, int64_t ldo) {
+  float2* v2 = reinterpret_cast<float2*>(v);
+  const float2* sb2 = reinterpret_cast<const float2*>(sb);
 #pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
-    v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-  }
+  for (int j = 0; j < kEpiChunk / 2; ++j) v2[j] = __fadd2_rn(v2[j], sb2[j]);
   if (EPI == EPI_BIAS_GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_fit(v[j]);
+    for (int j = 0; j < kEpiChunk / 2; ++j) v2[j] = gelu_tanh_fit2(v2[j]);
   }
   if (EPI == EPI_BIAS_RELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    for (int j = 0; j < kEpiChunk; ++j) v[j] = fmaxf(v[j], 0.f);
   }
   if (EPI == EPI_SCALE_RESID) {
     const float* r = ep.resid + m * ldo + n0;
+    const float2* ss2 = reinterpret_cast<const float2*>(ss);
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 s = __ldg(reinterpret_cast<const float4*>(ep.scale + n0 + j));
+    for (int j = 0; j < kEpiChunk; j += 4) {
       const float4 x = *reinterpret_cast<const float4*>(r + j);
-      v[j] = fmaf(s.x, v[j], x.x); v[j + 1] = fmaf(s.y, v[j + 1], x.y);
-      v[j + 2] = fmaf(s.z, v[j + 2], x.z); v[j + 3] = fmaf(s.w, v[j + 3], x.w);
+      v2[j / 2] = __ffma2_rn(ss2[j / 2], v2[j / 2], make_float2(x.x, x.y));
+      v2[j / 2 + 1] = __ffma2_rn(ss2[j / 2 + 1], v2[j / 2 + 1], make_float2(x.z, x.w));
     }
   }
   OutT* o = out + m * ldo + n0;
   if constexpr (sizeof(OutT) == 2) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
+    for (int j = 0; j < kEpiChunk; j += 8) {
       __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
       __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
       uint4 u;
@@ -166,7 +170,7 @@ __device__ __forceinline__ void epilogue_row32(float* v, int64_t m, int n0, cons
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    for (int j = 0; j < kEpiChunk; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
   }
 }
 
@@ -178,7 +182,8 @@ struct TcSmem {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTotal = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers + tmem ptr*/;
+  static constexpr int kVecOff = kStages * kStageBytes + 256;  // bias | scale staging after the barrier block
+  static constexpr int kTotal = kVecOff + 2 * kMaxN * 4 + 1024 /*align*/;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
 };
 
@@ -198,6 +203,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint8_t* smem_aligned = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + kStages * S::kStageBytes +
                                                                          8 * (2 * kStages + 4));
+
+  float* s_bias = reinterpret_cast<float*>(smem_aligned + S::kVecOff);
+  float* s_scale = s_bias + kMaxN;
+  for (int i = threadIdx.x; i < N; i += kTcThreads) {
+    s_bias[i] = ep.bias[i];
+    if (EPI == EPI_SCALE_RESID) s_scale[i] = ep.scale[i];
+  }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = N / BLOCK_N;
@@ -275,9 +287,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue (warps 2..9) =====================
+    // ===================== epilogue (warps 2..17) =====================
     const int lane_grp = warp & 3;            // TMEM lanes [32*lane_grp, +32) are accessible to this warp
-    const int chunk0 = (warp - 2) >> 2;       // the two warps of a lane quarter take alternate 32-column chunks
+    const int sub = (warp - 2) >> 2;          // the four warps of a lane quarter interleave 16-column chunks
     int as = 0;
     uint32_t aph = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -286,11 +298,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tcgen05_fence_after();
       const int64_t m = (int64_t)m_blk * kBlockM + lane_grp * 32 + lane;
 #pragma unroll 1
-      for (int c0 = 32 * chunk0; c0 < BLOCK_N; c0 += 32 * (kEpiWarps / 4)) {
-        float v[32];
+      for (int c0 = kEpiChunk * sub; c0 < BLOCK_N; c0 += kEpiChunk * (kEpiWarps / 4)) {
+        float v[kEpiChunk];
         const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(as * BLOCK_N + c0);
-        tmem_ld_32x32(taddr, v);
-        if (m < M) epilogue_row32<EPI, OutT>(v, m, n_blk * BLOCK_N + c0, ep, out, ldo);
+        tmem_ld_32x16(taddr, v);
+        const int n0 = n_blk * BLOCK_N + c0;
+        if (m < M) epilogue_chunk<EPI, OutT>(v, m, n0, s_bias + n0, s_scale + n0, ep, out, ldo);
       }
       tcgen05_fence_before();
       mbar_arrive(tempty_bar(as));
@@ -380,6 +393,7 @@ int launch_gemm_tc(const __nv_bfloat16* a, const __nv_bfloat16* w, int m, int n,
   CNB_REQUIRE(g_encode != nullptr, "gemm_tc_init() was not called");
   CNB_REQUIRE(k % 8 == 0, "gemm_tc needs K to be a multiple of 8 (16-byte TMA row stride)");
   CNB_REQUIRE(ep.bias != nullptr, "gemm_tc epilogues need a bias vector");
+  CNB_REQUIRE(n <= kMaxN, "gemm_tc stages bias/scale in shared memory: N must be <= 3072");
   if (m == 0) return 0;
   switch (epi) {
     case EPI_BIAS: return launch_n<EPI_BIAS, OutT>(a, w, m, n, k, ep, out, ldo, stream);
