@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--beam", type=int, default=3)
     ap.add_argument("--precision", default="fast", choices=["fast", "parity"])
     ap.add_argument("--enc-chunk", type=int, default=0)
+    ap.add_argument("--decoder", default="graph", choices=["graph", "persistent", "eager"])
     ap.add_argument("--cpu-sample", type=int, default=8, help="clips in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -219,7 +220,7 @@ def run_ours(args, rank, world, local_rank):
     b = args.batch
     sd = synth.make_state_dict(seed=1234, n_words=4000)
     vocab = sd["model.decoder.classifier.weight"].shape[0]
-    eng = Engine(sd, vocab, device=local_rank, precision=args.precision, enc_chunk=args.enc_chunk)
+    eng = Engine(sd, vocab, device=local_rank, precision=args.precision, enc_chunk=args.enc_chunk, decoder=args.decoder)
     forbid = sd["model.forbid_rep_mask"]
     bos = sd["model.task_id_to_token_id"][torch.zeros(b, dtype=torch.long)]  # task = clotho
     host_wavs = [synth.make_audio(b, n, seed=1234 + 2 * rank + i)[:, 0].contiguous().pin_memory() for i in range(2)]

@@ -90,6 +90,7 @@ struct cnb_handle {
   size_t ws_bytes = 0;
   int* zero_flag = nullptr;  // device int[4] that stays 0: "done" flag for non-beam callers
   // CUDA-graph replay of the decode loop
+  bool use_persistent = true;
   bool use_graphs = true;
   cudaStream_t stream = nullptr;  // library-owned non-blocking stream (graph capture / replay, host-API copies)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -580,13 +581,13 @@ static int dec_step(cnb_handle* h, const DecWs& w, const int* tokens, const int*
     const LayerW& L = h->layers[l];
     EpiParams e;
     e.bias = L.sa_in_b;
-    { Prof _p(h, CNB_K_DEC_GEMM, st);     if (int rc = launch_gemm_f32<float>(w.x, kD, L.sa_in_w, R, 3 * kD, kD, EPI_BIAS, e, w.qkv, 3 * kD, st)) return rc; }
+    { Prof _p(h, CNB_K_DEC_GEMM, st);     if (int rc = launch_gemm_f32_panel(w.x, kD, L.sa_in_w, R, 3 * kD, kD, EPI_BIAS, e, w.qkv, 3 * kD, st)) return rc; }
     { Prof _p(h, CNB_K_DEC_ATTN, st);     if (int rc = launch_self_attn(w.qkv, w.kc + l * cache_l, w.vc + l * cache_l, src_row, pos, w.attn, dd, done, st)) return rc; }
     e.bias = L.sa_out_b;
-    { Prof _p(h, CNB_K_DEC_GEMM, st);     if (int rc = launch_gemm_f32<float>(w.attn, kD, L.sa_out_w, R, kD, kD, EPI_BIAS, e, w.tmp, kD, st)) return rc; }
+    { Prof _p(h, CNB_K_DEC_GEMM, st);     if (int rc = launch_gemm_f32_panel(w.attn, kD, L.sa_out_w, R, kD, kD, EPI_BIAS, e, w.tmp, kD, st)) return rc; }
     { Prof _p(h, CNB_K_DEC_ATTN, st);     if (int rc = launch_add_ln(w.x, w.tmp, 1, nullptr, L.n1_g, L.n1_b, R, done, st)) return rc; }
     e.bias = L.ca_q_b;
-    { Prof _p(h, CNB_K_DEC_GEMM, st);     if (int rc = launch_gemm_f32<float>(w.x, kD, L.ca_q_w, R, kD, kD, EPI_BIAS, e, w.tmp, kD, st)) return rc; }
+    { Prof _p(h, CNB_K_DEC_GEMM, st);     if (int rc = launch_gemm_f32_panel(w.x, kD, L.ca_q_w, R, kD, kD, EPI_BIAS, e, w.tmp, kD, st)) return rc; }
     {
       Prof _p(h, CNB_K_DEC_ATTN, st);
       if (int rc = launch_cross_attn(w.tmp, w.ckv + (int64_t)l * 2 * kD, w.ckv + (int64_t)l * 2 * kD + kD, kv_stride, lens,
@@ -594,18 +595,18 @@ static int dec_step(cnb_handle* h, const DecWs& w, const int* tokens, const int*
         return rc;
     }
     e.bias = L.ca_out_b;
-    { Prof _p(h, CNB_K_DEC_GEMM, st);     if (int rc = launch_gemm_f32<float>(w.attn, kD, L.ca_out_w, R, kD, kD, EPI_BIAS, e, w.tmp, kD, st)) return rc; }
+    { Prof _p(h, CNB_K_DEC_GEMM, st);     if (int rc = launch_gemm_f32_panel(w.attn, kD, L.ca_out_w, R, kD, kD, EPI_BIAS, e, w.tmp, kD, st)) return rc; }
     { Prof _p(h, CNB_K_DEC_ATTN, st);     if (int rc = launch_add_ln(w.x, w.tmp, 1, nullptr, L.n2_g, L.n2_b, R, done, st)) return rc; }
     e.bias = L.l1_b;
-    { Prof _p(h, CNB_K_DEC_GEMM, st);     if (int rc = launch_gemm_f32<float>(w.x, kD, L.l1_w, R, kFF, kD, EPI_BIAS_GELU, e, w.ff, kFF, st)) return rc; }
+    { Prof _p(h, CNB_K_DEC_GEMM, st);     if (int rc = launch_gemm_f32_panel(w.x, kD, L.l1_w, R, kFF, kD, EPI_BIAS_GELU, e, w.ff, kFF, st)) return rc; }
     e.bias = nullptr;  // FF2 is split-K: bias + residual + LayerNorm happen in the reducing add_ln
-    { Prof _p(h, CNB_K_DEC_GEMM, st); if (int rc = launch_gemm_f32<float>(w.ff, kFF, L.l2_w, R, kD, kFF, EPI_BIAS, e, w.part, kD, st, kFf2Splits)) return rc; }
+    { Prof _p(h, CNB_K_DEC_GEMM, st); if (int rc = launch_gemm_f32_panel(w.ff, kFF, L.l2_w, R, kD, kFF, EPI_BIAS, e, w.part, kD, st)) return rc; }
     { Prof _p(h, CNB_K_DEC_ATTN, st); if (int rc = launch_add_ln(w.x, w.part, kFf2Splits, L.l2_b, L.n3_g, L.n3_b, R, done, st)) return rc; }
   }
   EpiParams e;
   e.bias = h->cls_b;
   Prof _p(h, CNB_K_DEC_CLS, st);
-  return launch_gemm_f32<float>(w.x, kD, h->cls_w, R, dd.vocab, kD, EPI_BIAS, e, w.logits, dd.vocab, st);
+  return launch_gemm_f32_panel(w.x, kD, h->cls_w, R, dd.vocab, kD, EPI_BIAS, e, w.logits, dd.vocab, st);
 }
 
 __global__ void gather_mult_kernel(BeamState st, int64_t* __restrict__ mult_preds, float* __restrict__ mult_lp,
@@ -683,6 +684,58 @@ static int decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, c
   bs.tokens[0] = tok0; bs.tokens[1] = tok1; bs.src_row[0] = src0; bs.src_row[1] = src1;
   bs.sum_lp = sum_lp; bs.live = live; bs.out_preds = out_preds; bs.out_lp = out_lp; bs.done = done;
 
+  if (!h->prof_on && h->use_persistent) {
+    // one cooperative launch for the whole decode loop (decoder_persistent.cu)
+    WS(h, "dxb", float, (size_t)rows * kD, xb);
+    WS(h, "dbar", unsigned int, 64, bar);
+    if (int rc = dec_project(h, frame_embs, batch, tp, w, st)) return rc;
+    PersistentArgs pa;
+    for (int l = 0; l < kLayers; ++l) {
+      const LayerW& L = h->layers[l];
+      pa.layers[l] = PLayer{L.sa_in_w, L.sa_in_b, L.sa_out_w, L.sa_out_b, L.ca_q_w, L.ca_q_b, L.ca_out_w, L.ca_out_b, L.l1_w,
+                            L.l1_b, L.l2_w, L.l2_b, L.n1_g, L.n1_b, L.n2_g, L.n2_b, L.n3_g, L.n3_b};
+    }
+    pa.emb = h->emb; pa.pe = h->pe; pa.cls_w = h->cls_w; pa.cls_b = h->cls_b;
+    pa.ckv = w.ckv; pa.lens = lens; pa.bos_ids = bos_ids; pa.forbid = forbid;
+    pa.xa = w.x; pa.xb = xb; pa.qkv = w.qkv; pa.attn = w.attn; pa.tmp = w.tmp; pa.ff = w.ff; pa.part = w.part;
+    pa.logits = w.logits; pa.kc = w.kc; pa.vc = w.vc; pa.bs = bs; pa.bar = bar;
+    pa.rows = rows; pa.beam = beam; pa.tp = tp; pa.max_len = max_len; pa.vocab = h->cfg.vocab_size; pa.min_len = min_len;
+    pa.batch = batch;
+    pa.trace = nullptr;
+    const bool trace_on = getenv("CNB_DEC_TRACE") != nullptr;
+    const int n_bar = 1 + max_len * (kLayers * 8 + 2);
+    if (trace_on) {
+      WS(h, "dtrace", unsigned long long, (size_t)3 * n_bar, tr);
+      CNB_CUDA_OK(cudaMemsetAsync(tr, 0, (size_t)3 * n_bar * sizeof(unsigned long long), st));
+      pa.trace = tr;
+    }
+    if (int rc = launch_decoder_persistent(pa, st)) return rc;
+    if (trace_on) {  // debug: per-phase time (work before the barrier, barrier wait) as seen by block 0
+      std::vector<unsigned long long> t((size_t)3 * n_bar);
+      CNB_CUDA_OK(cudaStreamSynchronize(st));
+      CNB_CUDA_OK(cudaMemcpy(t.data(), pa.trace, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      static const char* names[] = {"init", "qkv", "self_attn", "sa_out", "ln1+ca_q", "cross_attn", "ca_out", "ln2+ff1", "ff2",
+                                    "ln3+cls", "beam"};
+      double work[11] = {0}, wait[11] = {0};
+      int cnt[11] = {0};
+      for (int i = 1; i < n_bar; ++i) {
+        if (t[3 * i + 1] == 0) break;
+        const int ph = (int)t[3 * i];
+        work[ph] += (double)(t[3 * i + 1] - t[3 * (i - 1) + 2]);
+        wait[ph] += (double)(t[3 * i + 2] - t[3 * i + 1]);
+        cnt[ph] += 1;
+      }
+      for (int ph = 0; ph < 11; ++ph)
+        if (cnt[ph])
+          fprintf(stderr, "[dec trace] %-11s n=%4d work(block0) %7.2f us  barrier wait %7.2f us\n", names[ph], cnt[ph],
+                  work[ph] / cnt[ph] / 1e3, wait[ph] / cnt[ph] / 1e3);
+    }
+    if (int rc = launch_beam_finalize(bs, preds, lprobs, best_len, dd, st)) return rc;
+    gather_mult_kernel<<<(rows * max_len + 255) / 256, 256, 0, st>>>(bs, mult_preds, mult_lprobs, best_len, info, rows, max_len,
+                                                                    batch);
+    CNB_LAUNCH_OK();
+    return 0;
+  }
   if (h->prof_on || !h->use_graphs)
     return decode_body(h, w, bs, frame_embs, lens, bos_ids, forbid, batch, min_len, dd, preds, lprobs, mult_preds, mult_lprobs,
                        info, best_len, st);
@@ -776,7 +829,8 @@ int cnb_create(const cnb_config* cfg, cnb_handle** out) {
   CNB_CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CNB_CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CNB_CUDA_OK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-  h->use_graphs = (cfg->reserved[0] & 1) == 0;  // reserved[0] bit 0: disable CUDA graphs (debugging)
+  h->use_graphs = (cfg->reserved[0] & 1) == 0;      // reserved[0] bit 0: disable CUDA graphs (debugging)
+  h->use_persistent = (cfg->reserved[0] & 2) == 0;  // reserved[0] bit 1: disable the persistent decoder kernel
   *out = h;
   return 0;
 }

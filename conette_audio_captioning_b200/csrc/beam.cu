@@ -49,15 +49,11 @@ __global__ void __launch_bounds__(kBeamThreads)
 beam_step_kernel(float* __restrict__ logits, const uint8_t* __restrict__ forbid, BeamState st, int step, int cur, int min_len,
                  int beam, int max_len, int vocab) {
   if (st.done[0]) return;
-  __shared__ int s_live_label[kMaxBeam];
-  __shared__ int s_nlive;
-  __shared__ float s_prev[kMaxBeam];
   __shared__ float s_lse_max[kMaxBeam];
   __shared__ float s_lse_log[kMaxBeam];
-  __shared__ float s_red[kBeamThreads / 32];
-  __shared__ Cand s_cand[kBeamThreads / 32];
+  __shared__ Cand s_cand[2][kBeamThreads / 32];
+  __shared__ int s_owner[2][kBeamThreads / 32];
   __shared__ Cand s_win[kMaxBeam];
-  __shared__ int s_winner_tid;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int clip = blockIdx.x;
@@ -68,25 +64,40 @@ beam_step_kernel(float* __restrict__ logits, const uint8_t* __restrict__ forbid,
   const int* src_cur = st.src_row[cur];
   int* src_new = st.src_row[cur ^ 1];
 
-  if (tid == 0) {
-    int n = 0;
-    for (int l = 0; l < beam; ++l)
-      if (st.live[row0 + l]) {
-        s_live_label[n] = l;
-        s_prev[n] = st.sum_lp[row0 + l];
-        ++n;
-      }
-    s_nlive = n;
+  // live labels of this clip in ascending order (every thread derives the same list: no broadcast barrier needed)
+  int live_label[kMaxBeam];
+  float prev_sum[kMaxBeam];
+  int nlive = 0;
+#pragma unroll
+  for (int l = 0; l < kMaxBeam; ++l) {
+    live_label[l] = 0;
+    prev_sum[l] = 0.f;
   }
-  __syncthreads();
-  const int nlive = s_nlive;
+#pragma unroll
+  for (int l = 0; l < kMaxBeam; ++l)
+    if (l < beam && st.live[row0 + l]) {
+#pragma unroll
+      for (int q = 0; q < kMaxBeam; ++q)
+        if (q == nlive) {
+          live_label[q] = l;
+          prev_sum[q] = st.sum_lp[row0 + l];
+        }
+      ++nlive;
+    }
   if (nlive == 0) return;
   const int nrows_used = (step == 0) ? 1 : nlive;  // step 0: only the first row (beam.py:243-246)
   const int k_sel = nlive;                         // number of candidates to select (= beam at step 0)
+  auto label_at = [&](int q) {
+    int r = 0;
+#pragma unroll
+    for (int i = 0; i < kMaxBeam; ++i)
+      if (i == q) r = live_label[i];
+    return r;
+  };
 
   // ---- masks: EOS before min_len (beam.py:129-130), no-repeat of forbidden tokens already in the history (:146-156)
   for (int j = 0; j < nrows_used; ++j) {
-    const int row = row0 + s_live_label[j];
+    const int row = row0 + label_at(j);
     float* lg = logits + (int64_t)row * vocab;
     if (tid == 0 && step < min_len) lg[kEos] = -INFINITY;
     if (forbid != nullptr && tid <= step) {
@@ -96,43 +107,36 @@ beam_step_kernel(float* __restrict__ logits, const uint8_t* __restrict__ forbid,
   }
   __syncthreads();
 
-  // ---- log-softmax statistics per used row
-  for (int j = 0; j < nrows_used; ++j) {
-    const float* lg = logits + (int64_t)(row0 + s_live_label[j]) * vocab;
+  // ---- log-softmax statistics: warp j owns row j (online max / sum-exp, shuffle reductions only)
+  for (int j = warp; j < nrows_used; j += kBeamThreads / 32) {
+    const float* lg = logits + (int64_t)(row0 + label_at(j)) * vocab;
     float mx = -INFINITY;
-    for (int v = tid; v < vocab; v += kBeamThreads) mx = fmaxf(mx, lg[v]);
+    for (int v = lane; v < vocab; v += 32) mx = fmaxf(mx, lg[v]);
     mx = warp_max(mx);
-    if (lane == 0) s_red[warp] = mx;
-    __syncthreads();
-    mx = s_red[0];
-#pragma unroll
-    for (int i = 1; i < kBeamThreads / 32; ++i) mx = fmaxf(mx, s_red[i]);
-    __syncthreads();
     float sm = 0.f;
-    for (int v = tid; v < vocab; v += kBeamThreads) sm += expf(lg[v] - mx);
+    for (int v = lane; v < vocab; v += 32) sm += expf(lg[v] - mx);
     sm = warp_sum(sm);
-    if (lane == 0) s_red[warp] = sm;
-    __syncthreads();
-    if (tid == 0) {
-      float t = 0.f;
-      for (int i = 0; i < kBeamThreads / 32; ++i) t += s_red[i];
+    if (lane == 0) {
       s_lse_max[j] = mx;
-      s_lse_log[j] = logf(t);
+      s_lse_log[j] = logf(sm);
     }
-    __syncthreads();
   }
+  __syncthreads();
 
   // ---- thread-local top-k over the flat (row, word) candidates, kept sorted (best first)
   Cand loc[kMaxBeam];
 #pragma unroll
   for (int i = 0; i < kMaxBeam; ++i) loc[i] = Cand{-INFINITY, 0x7fffffff};
   for (int j = 0; j < nrows_used; ++j) {
-    const float* lg = logits + (int64_t)(row0 + s_live_label[j]) * vocab;
+    const float* lg = logits + (int64_t)(row0 + label_at(j)) * vocab;
     const float mx = s_lse_max[j], lg_sum = s_lse_log[j];
-    const float prev = (step == 0) ? 0.f : s_prev[j];
+    float prev = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxBeam; ++i)
+      if (i == j) prev = prev_sum[i];
     for (int v = tid; v < vocab; v += kBeamThreads) {
-      Cand c{prev + ((lg[v] - mx) - lg_sum), j * vocab + v};
-      if (step == 0) c.v = (lg[v] - mx) - lg_sum;
+      const float lsm = (lg[v] - mx) - lg_sum;
+      const Cand c{step == 0 ? lsm : prev + lsm, j * vocab + v};
       if (better(c, loc[kMaxBeam - 1])) {
         loc[kMaxBeam - 1] = c;
 #pragma unroll
@@ -145,52 +149,50 @@ beam_step_kernel(float* __restrict__ logits, const uint8_t* __restrict__ forbid,
       }
     }
   }
-  // ---- k_sel rounds of block arg-max over the heads of the thread-local lists
+  // ---- k_sel rounds of block arg-max over the heads of the thread-local lists (one barrier per round)
   for (int r = 0; r < k_sel; ++r) {
     Cand best = loc[0];
     int owner = tid;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      Cand other{__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.idx, o)};
+      const Cand other{__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.idx, o)};
       const int oo = __shfl_xor_sync(0xffffffffu, owner, o);
       if (better(other, best)) {
         best = other;
         owner = oo;
       }
     }
+    const int buf = r & 1;
     if (lane == 0) {
-      s_cand[warp] = best;
-      s_red[warp] = __int_as_float(owner);
+      s_cand[buf][warp] = best;
+      s_owner[buf][warp] = owner;
     }
     __syncthreads();
-    if (tid == 0) {
-      Cand b = s_cand[0];
-      int ow = __float_as_int(s_red[0]);
-      for (int i = 1; i < kBeamThreads / 32; ++i)
-        if (better(s_cand[i], b)) {
-          b = s_cand[i];
-          ow = __float_as_int(s_red[i]);
-        }
-      if (b.idx == 0x7fffffff) b.idx = 0;  // NaN logits (fully masked clip, len 0): stay memory-safe like a no-op pick
-      s_win[r] = b;
-      s_winner_tid = ow;
-    }
-    __syncthreads();
-    if (tid == s_winner_tid) {
+    Cand bw = s_cand[buf][0];
+    int ow = s_owner[buf][0];
+#pragma unroll
+    for (int i = 1; i < kBeamThreads / 32; ++i)
+      if (better(s_cand[buf][i], bw)) {
+        bw = s_cand[buf][i];
+        ow = s_owner[buf][i];
+      }
+    if (bw.idx == 0x7fffffff) bw.idx = 0;  // NaN logits (fully masked clip, len 0): stay memory-safe like a no-op pick
+    if (tid == 0) s_win[r] = bw;
+    if (tid == ow) {
 #pragma unroll
       for (int i = 0; i < kMaxBeam - 1; ++i) loc[i] = loc[i + 1];
       loc[kMaxBeam - 1] = Cand{-INFINITY, 0x7fffffff};
     }
-    __syncthreads();
   }
+  __syncthreads();
 
   // ---- bookkeeping: candidate r -> r-th live label (beam.py:165-176), histories via back-pointers
   for (int item = tid; item < k_sel * (step + 2); item += kBeamThreads) {
     const int r = item / (step + 2), p = item - r * (step + 2);
-    const int row = row0 + s_live_label[r];
+    const int row = row0 + label_at(r);
     const int prev_pos = s_win[r].idx / vocab;
     const int word = s_win[r].idx - prev_pos * vocab;
-    const int src = row0 + s_live_label[prev_pos];
+    const int src = row0 + label_at(prev_pos);
     if (p <= step) {
       tok_new[(int64_t)row * tstride + p] = tok_cur[(int64_t)src * tstride + p];
       src_new[(int64_t)row * max_len + p] = src_cur[(int64_t)src * max_len + p];
@@ -202,7 +204,7 @@ beam_step_kernel(float* __restrict__ logits, const uint8_t* __restrict__ forbid,
   __syncthreads();
   if (tid < k_sel) {
     const int r = tid;
-    const int row = row0 + s_live_label[r];
+    const int row = row0 + label_at(r);
     const int prev_pos = s_win[r].idx / vocab;
     const int word = s_win[r].idx - prev_pos * vocab;
     st.sum_lp[row] = s_win[r].v;

@@ -16,7 +16,6 @@ constexpr int kHeads = 8;
 // ---- x[r,:] = emb[token[r,pos],:] * sqrt(256) + PE[pos,:] ---------------------------------------------------------------
 __global__ void embed_kernel(const int* __restrict__ tokens, int tok_stride, int pos, const float* __restrict__ emb,
                              const float* __restrict__ pe, const int* __restrict__ done, float* __restrict__ x, int rows) {
-  if (done[0]) return;
   const int r = blockIdx.x, c = threadIdx.x;
   const int tok = tokens[(int64_t)r * tok_stride + pos];
   x[(int64_t)r * kD + c] = emb[(int64_t)tok * kD + c] * 16.0f + pe[(int64_t)pos * kD + c];
@@ -28,7 +27,6 @@ __global__ void __launch_bounds__(256)
 self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ kcache, float* __restrict__ vcache,
                  const int* __restrict__ src_row, int pos, int max_len, const int* __restrict__ done,
                  float* __restrict__ attn, int rows) {
-  if (done[0]) return;
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (gw >= rows * kHeads) return;
@@ -65,7 +63,6 @@ cross_attn_kernel(const float* __restrict__ q, const float* __restrict__ ck, con
                   const int* __restrict__ lens, int beam, int tp, const int* __restrict__ done, float* __restrict__ attn,
                   int rows) {
   extern __shared__ float s_sc[];  // (8 warps, tp)
-  if (done[0]) return;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (gw >= rows * kHeads) return;
@@ -118,7 +115,6 @@ cross_attn_kernel(const float* __restrict__ q, const float* __restrict__ ck, con
 __global__ void __launch_bounds__(256)
 add_ln_kernel(float* __restrict__ x, const float* __restrict__ delta, int nsplit, const float* __restrict__ bias,
               const float* __restrict__ g, const float* __restrict__ b, const int* __restrict__ done, int rows) {
-  if (done && done[0]) return;
   const int lane = threadIdx.x & 31;
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= rows) return;

@@ -1,0 +1,587 @@
+// K-DEC persistent: the whole beam-search decode (all steps x 6 layers + classifier + beam selection) in ONE cooperative
+// kernel launch, 1 CTA per SM, phases separated by a software grid barrier.
+//
+// Why: a decode step is ~70 tiny, strictly dependent operations on R = clips x beam (~192) rows.  As separate kernels
+// (even replayed from a CUDA graph) each pays ~3 us of launch/drain latency on B200 and the 20-step decode costs ~12 ms;
+// here a phase boundary is one atomic + one L2 poll (~0.5 us) and every operand stays in L2.
+//
+// Phases per layer (B = grid barrier):
+//   QKV GEMM [LayerNorm-on-load of the previous layer's FF2 partial sums]  B  self-attention (KV cache, beam back-pointers)
+//   B  SA-out GEMM  B  LN1-on-load + cross-q GEMM  B  cross-attention  B  CA-out GEMM  B  LN2-on-load + FF1 (GELU)  B
+//   FF2 split-K (8 x 256)  B   ... then LN3-on-load + classifier GEMM  B  beam step (1 CTA per clip) + next embedding  B
+// GEMMs are fp32 CUDA-core (bit-faithful greedy ids): 256-wide K panels staged by cp.async.cg (L2-coherent),
+// interleaved TM x TN micro-tiles.  LayerNorm-on-load: every tile normalises its own rows straight into the shared-memory
+// A panel (x is double-buffered in global so that tiles of the same rows never read what a sibling writes).
+// Reference semantics: nn/decoders/aac_tfmer.py:100-116, nn/decoding/beam.py:113-203 (see decoder.cu / beam.cu).
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace cnb {
+
+constexpr int kPD = 256, kPHeads = 8, kPHeadDim = 32, kPFF = 2048, kPLayers = 6;
+constexpr int kPThreads = 256;
+constexpr int kPanelLds = 256 + 4;
+constexpr int kPMaxBeam = 8;
+constexpr int kPSplits = 8;  // FF2 K-slices
+
+// ---- software grid barrier (monotonic arrival counter; bar[] zeroed by the host before launch) ----------------------
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// trace (debug, optional): block 0 records (phase id, time before the barrier, time after it) for every barrier
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& gen, unsigned long long* trace = nullptr,
+                                             int phase = 0) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (trace && blockIdx.x == 0) {
+      trace[3 * gen] = (unsigned long long)phase;
+      trace[3 * gen + 1] = global_ns();
+    }
+    gen += 1;
+    __threadfence();  // publish this CTA's writes (gpu scope; also invalidates this SM's L1 so later loads see peers' data)
+    const unsigned int arrived = atomicAdd(&bar[0], 1u);
+    if (arrived == gridDim.x * gen - 1u) {
+      atomicExch(&bar[1], gen);
+    } else {
+      unsigned int spins = 0;
+      while (*reinterpret_cast<volatile unsigned int*>(&bar[1]) < gen) {
+        if (++spins > (1u << 26)) {
+          printf("conette_b200: grid barrier timed out (block %d gen %u)\n", blockIdx.x, gen);
+          __trap();
+        }
+      }
+    }
+    __threadfence();
+    if (trace && blockIdx.x == 0) trace[3 * (gen - 1) + 2] = global_ns();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void cp_async16_cg(void* smem, const void* gmem, bool valid) {
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem);
+  const int bytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem), "r"(bytes) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// GEMM tile: out[m0.., n0..] = epi(A[m, k_begin..k_begin+256) . W[n, k_begin..+256))
+//   LN_MODE 0: A rows come from global `a` (row stride lda)
+//   LN_MODE 1: A row = LayerNorm(xin[m] + ln_bias + sum_s delta[s][m]) * g + b   (k_begin must be 0, K = 256);
+//              tiles with n0 == 0 also store the normalised rows to xout
+//   EPI 0: + bias   1: gelu_erf(+ bias)   2: raw store to slab z (split-K partial)
+// ---------------------------------------------------------------------------------------------------------------------
+struct LnArgs {
+  const float* xin;
+  float* xout;
+  const float* delta;
+  int nsplit;
+  const float* ln_bias;
+  const float* g;
+  const float* b;
+};
+
+template <int BM, int BN, int TM, int TN, int LN_MODE, int EPI>
+__device__ __forceinline__ void gemm_tile(float* s_panel, const float* a, int64_t lda, const LnArgs& ln, const float* W, int K,
+                                          int k_begin, const float* bias, float* out, int64_t ldo, int M, int N, int m0,
+                                          int n0) {
+  constexpr int TX = BN / TN, TY = BM / TM;
+  static_assert(TX * TY == kPThreads, "256 threads");
+  float (*As)[kPanelLds] = reinterpret_cast<float (*)[kPanelLds]>(s_panel);
+  float (*Bs)[kPanelLds] = reinterpret_cast<float (*)[kPanelLds]>(s_panel + BM * kPanelLds);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx = tid % TX, ty = tid / TX;
+
+  // W panel (and the A panel when it is plain data): 16-byte cp.async through L2
+  for (int i = tid; i < BN * 64; i += kPThreads) {
+    const int r = i >> 6, kq = (i & 63) * 4;
+    const bool ok = n0 + r < N;
+    cp_async16_cg(&Bs[r][kq], ok ? W + (int64_t)(n0 + r) * K + k_begin + kq : W, ok);
+  }
+  if (LN_MODE == 0) {
+    for (int i = tid; i < BM * 64; i += kPThreads) {
+      const int r = i >> 6, kq = (i & 63) * 4;
+      const bool ok = m0 + r < M;
+      cp_async16_cg(&As[r][kq], ok ? a + (int64_t)(m0 + r) * lda + k_begin + kq : a, ok);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  if (LN_MODE == 1) {
+    // each warp normalises BM/8 rows directly into the A panel
+    for (int r = warp; r < BM; r += kPThreads / 32) {
+      const int m = m0 + r;
+      float v[8];
+      if (m < M) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = lane + 32 * j;
+          float d = ln.ln_bias ? ln.ln_bias[c] : 0.f;
+          for (int sp = 0; sp < ln.nsplit; ++sp) d += __ldcg(&ln.delta[((int64_t)sp * M + m) * kPD + c]);
+          v[j] = __ldcg(&ln.xin[(int64_t)m * kPD + c]) + d;
+          s += v[j];
+        }
+        const float mean = warp_sum(s) * (1.f / kPD);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q += (v[j] - mean) * (v[j] - mean);
+        const float rstd = 1.f / sqrtf(warp_sum(q) * (1.f / kPD) + 1e-5f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = lane + 32 * j;
+          v[j] = (v[j] - mean) * rstd * ln.g[c] + ln.b[c];
+          if (n0 == 0) ln.xout[(int64_t)m * kPD + c] = v[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) As[r][lane + 32 * j] = v[j];
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+  for (int kk = 0; kk < 256; kk += 4) {
+    float4 av[TM], bv[TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i) av[i] = *reinterpret_cast<const float4*>(&As[ty + i * TY][kk]);
+#pragma unroll
+    for (int j = 0; j < TN; ++j) bv[j] = *reinterpret_cast<const float4*>(&Bs[tx + j * TX][kk]);
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        acc[i][j] = fmaf(av[i].x, bv[j].x, acc[i][j]);
+        acc[i][j] = fmaf(av[i].y, bv[j].y, acc[i][j]);
+        acc[i][j] = fmaf(av[i].z, bv[j].z, acc[i][j]);
+        acc[i][j] = fmaf(av[i].w, bv[j].w, acc[i][j]);
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty + i * TY;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tx + j * TX;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (EPI != 2) v += bias[n];
+      if (EPI == 1) v = gelu_erf(v);
+      out[(int64_t)m * ldo + n] = v;
+    }
+  }
+  __syncthreads();  // the panel is reused by the next tile / phase
+}
+
+template <int BM, int BN, int TM, int TN, int LN_MODE, int EPI>
+__device__ __forceinline__ void gemm_phase(float* s_panel, const float* a, int64_t lda, const LnArgs& ln, const float* W, int K,
+                                           const float* bias, float* out, int64_t ldo, int M, int N) {
+  const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+  const int k_slices = (EPI == 2) ? K / 256 : 1;
+  const int n_tiles = tiles_m * tiles_n * k_slices;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int z = t / (tiles_m * tiles_n);
+    const int rem = t - z * tiles_m * tiles_n;
+    const int tm = rem / tiles_n, tn = rem - tm * tiles_n;
+    gemm_tile<BM, BN, TM, TN, LN_MODE, EPI>(s_panel, a, lda, ln, W, K, z * 256, bias, out + (int64_t)z * M * ldo, ldo, M, N,
+                                            tm * BM, tn * BN);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// attention phases (one warp per (row, head)); same arithmetic as decoder.cu
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void self_attn_phase(const float* qkv, float* kcache, float* vcache, const int* src_row, int pos,
+                                                int max_len, float* attn, int rows) {
+  const int lane = threadIdx.x & 31;
+  const int n_tasks = rows * kPHeads;
+  for (int gw = blockIdx.x * (kPThreads / 32) + (threadIdx.x >> 5); gw < n_tasks; gw += gridDim.x * (kPThreads / 32)) {
+    const int r = gw / kPHeads, h = gw - r * kPHeads;
+    const int col = h * kPHeadDim + lane;
+    const float q = __ldcg(&qkv[(int64_t)r * 768 + col]);
+    kcache[((int64_t)r * max_len + pos) * kPD + col] = __ldcg(&qkv[(int64_t)r * 768 + 256 + col]);
+    vcache[((int64_t)r * max_len + pos) * kPD + col] = __ldcg(&qkv[(int64_t)r * 768 + 512 + col]);
+    __syncwarp();
+    const float scale = 0.17677669529663687f;
+    float sc[2] = {-INFINITY, -INFINITY};
+    for (int p = 0; p <= pos; ++p) {
+      const int pr = (p == pos) ? r : src_row[(int64_t)r * max_len + p];
+      const float s = warp_sum(q * __ldcg(&kcache[((int64_t)pr * max_len + p) * kPD + col])) * scale;
+      if ((p & 31) == lane) sc[p >> 5] = s;
+    }
+    const float mx = warp_max(fmaxf(sc[0], sc[1]));
+    const float e0 = (sc[0] == -INFINITY) ? 0.f : expf(sc[0] - mx);
+    const float e1 = (sc[1] == -INFINITY) ? 0.f : expf(sc[1] - mx);
+    const float inv = 1.f / warp_sum(e0 + e1);
+    float acc = 0.f;
+    for (int p = 0; p <= pos; ++p) {
+      const int pr = (p == pos) ? r : src_row[(int64_t)r * max_len + p];
+      const float w = __shfl_sync(0xffffffffu, (p >> 5) ? e1 : e0, p & 31) * inv;
+      acc = fmaf(w, __ldcg(&vcache[((int64_t)pr * max_len + p) * kPD + col]), acc);
+    }
+    attn[(int64_t)r * kPD + col] = acc;
+  }
+}
+
+__device__ __forceinline__ void cross_attn_phase(float* s_scores, const float* q, const float* ck, const float* cv,
+                                                 int64_t kv_stride, const int* lens, int beam, int tp, float* attn, int rows) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* sc = s_scores + wib * tp;
+  const int n_tasks = rows * kPHeads;
+  for (int gw = blockIdx.x * (kPThreads / 32) + wib; gw < n_tasks; gw += gridDim.x * (kPThreads / 32)) {
+    const int r = gw / kPHeads, h = gw - r * kPHeads;
+    const int clip = r / beam;
+    const int len = lens[clip];
+    const float* qh = q + (int64_t)r * kPD + h * kPHeadDim;
+    float qv[kPHeadDim];
+#pragma unroll
+    for (int d = 0; d < kPHeadDim; d += 4) {
+      const float4 t = __ldcg(reinterpret_cast<const float4*>(qh + d));
+      qv[d] = t.x; qv[d + 1] = t.y; qv[d + 2] = t.z; qv[d + 3] = t.w;
+    }
+    const float scale = 0.17677669529663687f;
+    float mx = -INFINITY;
+    for (int t = lane; t < tp; t += 32) {
+      float s = -INFINITY;
+      if (t < len) {
+        const float* kr = ck + ((int64_t)clip * tp + t) * kv_stride + h * kPHeadDim;
+        float a = 0.f;
+#pragma unroll
+        for (int d = 0; d < kPHeadDim; d += 4) {
+          const float4 kk = *reinterpret_cast<const float4*>(kr + d);
+          a = fmaf(qv[d], kk.x, a); a = fmaf(qv[d + 1], kk.y, a); a = fmaf(qv[d + 2], kk.z, a); a = fmaf(qv[d + 3], kk.w, a);
+        }
+        s = a * scale;
+      }
+      sc[t] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int t = lane; t < tp; t += 32) {
+      const float e = (sc[t] == -INFINITY) ? 0.f : expf(sc[t] - mx);
+      sc[t] = e;
+      sum += e;
+    }
+    const float inv = 1.f / warp_sum(sum);
+    __syncwarp();
+    float acc = 0.f;
+    const int tmax = len < tp ? len : tp;
+    for (int t = 0; t < tmax; ++t) acc = fmaf(sc[t], cv[((int64_t)clip * tp + t) * kv_stride + h * kPHeadDim + lane], acc);
+    attn[(int64_t)r * kPD + h * kPHeadDim + lane] = acc * inv;
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// beam step for one clip (same selection logic as beam.cu::beam_step_kernel) + embedding of the next input token
+// ---------------------------------------------------------------------------------------------------------------------
+struct PCand {
+  float v;
+  int idx;
+};
+__device__ __forceinline__ bool pbetter(const PCand& a, const PCand& b) { return a.v > b.v || (a.v == b.v && a.idx < b.idx); }
+
+struct BeamSmem {
+  float lse_max[kPMaxBeam], lse_log[kPMaxBeam];
+  PCand cand[2][kPThreads / 32];
+  int owner[2][kPThreads / 32];
+  PCand win[kPMaxBeam];
+};
+
+__device__ void beam_clip(BeamSmem& sm, float* logits, const uint8_t* forbid, const BeamState& st, int step, int cur, int min_len,
+                          int beam, int max_len, int vocab, int clip, const float* emb, const float* pe, float* x_next) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int row0 = clip * beam;
+  const int tstride = max_len + 1;
+  const int* tok_cur = st.tokens[cur];
+  int* tok_new = st.tokens[cur ^ 1];
+  const int* src_cur = st.src_row[cur];
+  int* src_new = st.src_row[cur ^ 1];
+  int live_label[kPMaxBeam];
+  float prev_sum[kPMaxBeam];
+  int nlive = 0;
+#pragma unroll
+  for (int l = 0; l < kPMaxBeam; ++l) {
+    live_label[l] = 0;
+    prev_sum[l] = 0.f;
+  }
+#pragma unroll
+  for (int l = 0; l < kPMaxBeam; ++l)
+    if (l < beam && st.live[row0 + l]) {
+#pragma unroll
+      for (int q = 0; q < kPMaxBeam; ++q)
+        if (q == nlive) {
+          live_label[q] = l;
+          prev_sum[q] = st.sum_lp[row0 + l];
+        }
+      ++nlive;
+    }
+  auto label_at = [&](int q) {
+    int r = 0;
+#pragma unroll
+    for (int i = 0; i < kPMaxBeam; ++i)
+      if (i == q) r = live_label[i];
+    return r;
+  };
+  __syncthreads();  // all threads have read live / sum_lp before anybody updates them below
+  if (nlive > 0) {
+    const int nrows_used = (step == 0) ? 1 : nlive;
+    const int k_sel = nlive;
+    for (int j = 0; j < nrows_used; ++j) {
+      const int row = row0 + label_at(j);
+      float* lg = logits + (int64_t)row * vocab;
+      if (tid == 0 && step < min_len) lg[2] = -INFINITY;
+      if (forbid != nullptr && tid <= step) {
+        const int tok = tok_cur[(int64_t)row * tstride + tid];
+        if (forbid[tok]) lg[tok] = -INFINITY;
+      }
+    }
+    __syncthreads();
+    for (int j = warp; j < nrows_used; j += kPThreads / 32) {
+      const float* lg = logits + (int64_t)(row0 + label_at(j)) * vocab;
+      float mx = -INFINITY;
+      for (int v = lane; v < vocab; v += 32) mx = fmaxf(mx, lg[v]);
+      mx = warp_max(mx);
+      float s = 0.f;
+      for (int v = lane; v < vocab; v += 32) s += expf(lg[v] - mx);
+      s = warp_sum(s);
+      if (lane == 0) {
+        sm.lse_max[j] = mx;
+        sm.lse_log[j] = logf(s);
+      }
+    }
+    __syncthreads();
+    PCand loc[kPMaxBeam];
+#pragma unroll
+    for (int i = 0; i < kPMaxBeam; ++i) loc[i] = PCand{-INFINITY, 0x7fffffff};
+    for (int j = 0; j < nrows_used; ++j) {
+      const float* lg = logits + (int64_t)(row0 + label_at(j)) * vocab;
+      const float mx = sm.lse_max[j], lg_sum = sm.lse_log[j];
+      float prev = 0.f;
+#pragma unroll
+      for (int i = 0; i < kPMaxBeam; ++i)
+        if (i == j) prev = prev_sum[i];
+      for (int v = tid; v < vocab; v += kPThreads) {
+        const float lsm = (lg[v] - mx) - lg_sum;
+        const PCand c{step == 0 ? lsm : prev + lsm, j * vocab + v};
+        if (pbetter(c, loc[kPMaxBeam - 1])) {
+          loc[kPMaxBeam - 1] = c;
+#pragma unroll
+          for (int i = kPMaxBeam - 1; i > 0; --i)
+            if (pbetter(loc[i], loc[i - 1])) {
+              const PCand t = loc[i];
+              loc[i] = loc[i - 1];
+              loc[i - 1] = t;
+            }
+        }
+      }
+    }
+    for (int r = 0; r < k_sel; ++r) {
+      PCand best = loc[0];
+      int owner = tid;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const PCand other{__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.idx, o)};
+        const int oo = __shfl_xor_sync(0xffffffffu, owner, o);
+        if (pbetter(other, best)) {
+          best = other;
+          owner = oo;
+        }
+      }
+      const int buf = r & 1;
+      if (lane == 0) {
+        sm.cand[buf][warp] = best;
+        sm.owner[buf][warp] = owner;
+      }
+      __syncthreads();
+      PCand bw = sm.cand[buf][0];
+      int ow = sm.owner[buf][0];
+#pragma unroll
+      for (int i = 1; i < kPThreads / 32; ++i)
+        if (pbetter(sm.cand[buf][i], bw)) {
+          bw = sm.cand[buf][i];
+          ow = sm.owner[buf][i];
+        }
+      if (bw.idx == 0x7fffffff) bw.idx = 0;
+      if (tid == 0) sm.win[r] = bw;
+      if (tid == ow) {
+#pragma unroll
+        for (int i = 0; i < kPMaxBeam - 1; ++i) loc[i] = loc[i + 1];
+        loc[kPMaxBeam - 1] = PCand{-INFINITY, 0x7fffffff};
+      }
+    }
+    __syncthreads();
+    for (int item = tid; item < k_sel * (step + 2); item += kPThreads) {
+      const int r = item / (step + 2), p = item - r * (step + 2);
+      const int row = row0 + label_at(r);
+      const int prev_pos = sm.win[r].idx / vocab;
+      const int word = sm.win[r].idx - prev_pos * vocab;
+      const int src = row0 + label_at(prev_pos);
+      if (p <= step) {
+        tok_new[(int64_t)row * tstride + p] = tok_cur[(int64_t)src * tstride + p];
+        src_new[(int64_t)row * max_len + p] = src_cur[(int64_t)src * max_len + p];
+      } else {
+        tok_new[(int64_t)row * tstride + p] = word;
+        if (p < max_len) src_new[(int64_t)row * max_len + p] = row;
+      }
+    }
+    __syncthreads();
+    if (tid < k_sel) {
+      const int r = tid;
+      const int row = row0 + label_at(r);
+      const int prev_pos = sm.win[r].idx / vocab;
+      const int word = sm.win[r].idx - prev_pos * vocab;
+      st.sum_lp[row] = sm.win[r].v;
+      if (word == 2 || step == max_len - 1) {
+        for (int p = 0; p <= step; ++p) st.out_preds[(int64_t)row * max_len + p] = tok_new[(int64_t)row * tstride + p + 1];
+        st.out_lp[row] = sm.win[r].v / (float)(step + 1);
+        st.live[row] = 0;
+        const int left = atomicSub(&st.done[2], 1) - 1;
+        if (left == 0) {
+          st.done[1] = step + 1;
+          __threadfence();
+          st.done[0] = 1;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // embedding of the next input token for every row of the clip (dead rows keep a valid stale token)
+  if (step + 1 < max_len) {
+    for (int i = tid; i < beam * kPD; i += kPThreads) {
+      const int row = row0 + i / kPD, c = i % kPD;
+      const int tok = tok_new[(int64_t)row * tstride + step + 1];
+      x_next[(int64_t)row * kPD + c] = emb[(int64_t)tok * kPD + c] * 16.0f + pe[(int64_t)(step + 1) * kPD + c];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPThreads, 1) decoder_persistent_kernel(const PersistentArgs p) {
+  extern __shared__ __align__(16) float s_dyn[];
+  __shared__ BeamSmem s_beam;
+  unsigned int gen = 0;
+  const int R = p.rows;
+  const int64_t cache_l = (int64_t)R * p.max_len * kPD;
+  const int64_t kv_stride = kPLayers * 2 * kPD;
+  const int tstride = p.max_len + 1;
+  float* x_cur = p.xa;  // residual stream (double-buffered across LayerNorm phases)
+  float* x_alt = p.xb;
+
+  // ---- init (what beam_init_kernel + the first embedding do) ------------------------------------------------------
+  for (int r = blockIdx.x * kPThreads + threadIdx.x; r < R; r += gridDim.x * kPThreads) {
+    for (int q = 0; q <= p.max_len; ++q) {
+      p.bs.tokens[0][(int64_t)r * tstride + q] = 0;
+      p.bs.tokens[1][(int64_t)r * tstride + q] = 0;
+    }
+    p.bs.tokens[0][(int64_t)r * tstride] = (int)p.bos_ids[r / p.beam];
+    for (int q = 0; q < p.max_len; ++q) {
+      p.bs.src_row[0][(int64_t)r * p.max_len + q] = r;
+      p.bs.src_row[1][(int64_t)r * p.max_len + q] = r;
+      p.bs.out_preds[(int64_t)r * p.max_len + q] = 0;
+    }
+    p.bs.sum_lp[r] = 0.f;
+    p.bs.live[r] = 1;
+    p.bs.out_lp[r] = 0.f;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    p.bs.done[0] = 0;
+    p.bs.done[1] = p.max_len;
+    p.bs.done[2] = R;
+  }
+  for (int i = blockIdx.x * kPThreads + threadIdx.x; i < R * kPD; i += gridDim.x * kPThreads) {
+    const int r = i / kPD, c = i - r * kPD;
+    const int tok = (int)p.bos_ids[r / p.beam];
+    x_cur[i] = p.emb[(int64_t)tok * kPD + c] * 16.0f + p.pe[c];
+  }
+  grid_barrier(p.bar, gen, p.trace, 0);
+
+  int cur = 0;
+  for (int step = 0; step < p.max_len; ++step) {
+    const int* src_row = p.bs.src_row[cur];
+    for (int l = 0; l < kPLayers; ++l) {
+      const PLayer& L = p.layers[l];
+      LnArgs ln{};
+      // ---- QKV (layer 0: x is the embedding; later layers: LN3 of the previous layer on load)
+      if (l == 0) {
+        gemm_phase<32, 32, 2, 2, 0, 0>(s_dyn, x_cur, kPD, ln, L.sa_in_w, kPD, L.sa_in_b, p.qkv, 768, R, 768);
+      } else {
+        const PLayer& P = p.layers[l - 1];
+        ln = LnArgs{x_cur, x_alt, p.part, kPSplits, P.l2_b, P.n3_g, P.n3_b};
+        gemm_phase<32, 32, 2, 2, 1, 0>(s_dyn, nullptr, 0, ln, L.sa_in_w, kPD, L.sa_in_b, p.qkv, 768, R, 768);
+        float* t = x_cur; x_cur = x_alt; x_alt = t;
+      }
+      grid_barrier(p.bar, gen, p.trace, 1);
+      self_attn_phase(p.qkv, p.kc + l * cache_l, p.vc + l * cache_l, src_row, step, p.max_len, p.attn, R);
+      grid_barrier(p.bar, gen, p.trace, 2);
+      gemm_phase<32, 32, 2, 2, 0, 0>(s_dyn, p.attn, kPD, ln, L.sa_out_w, kPD, L.sa_out_b, p.tmp, kPD, R, kPD);
+      grid_barrier(p.bar, gen, p.trace, 3);
+      // ---- LN1 on load + cross-attention query projection (q goes to the free qkv buffer, row stride 256)
+      ln = LnArgs{x_cur, x_alt, p.tmp, 1, nullptr, L.n1_g, L.n1_b};
+      gemm_phase<32, 32, 2, 2, 1, 0>(s_dyn, nullptr, 0, ln, L.ca_q_w, kPD, L.ca_q_b, p.qkv, kPD, R, kPD);
+      { float* t = x_cur; x_cur = x_alt; x_alt = t; }
+      grid_barrier(p.bar, gen, p.trace, 4);
+      cross_attn_phase(s_dyn, p.qkv, p.ckv + (int64_t)l * 2 * kPD, p.ckv + (int64_t)l * 2 * kPD + kPD, kv_stride, p.lens, p.beam,
+                       p.tp, p.attn, R);
+      grid_barrier(p.bar, gen, p.trace, 5);
+      gemm_phase<32, 32, 2, 2, 0, 0>(s_dyn, p.attn, kPD, ln, L.ca_out_w, kPD, L.ca_out_b, p.tmp, kPD, R, kPD);
+      grid_barrier(p.bar, gen, p.trace, 6);
+      // ---- LN2 on load + FF1 (GELU)
+      ln = LnArgs{x_cur, x_alt, p.tmp, 1, nullptr, L.n2_g, L.n2_b};
+      gemm_phase<32, 64, 2, 4, 1, 1>(s_dyn, nullptr, 0, ln, L.l1_w, kPD, L.l1_b, p.ff, kPFF, R, kPFF);
+      { float* t = x_cur; x_cur = x_alt; x_alt = t; }
+      grid_barrier(p.bar, gen, p.trace, 7);
+      // ---- FF2: 8 K-slices of raw partial sums (bias + residual + LN3 happen on the next load)
+      gemm_phase<64, 64, 4, 4, 0, 2>(s_dyn, p.ff, kPFF, ln, L.l2_w, kPFF, nullptr, p.part, kPD, R, kPD);
+      grid_barrier(p.bar, gen, p.trace, 8);
+    }
+    {  // ---- LN3 of the last layer on load + classifier
+      const PLayer& P = p.layers[kPLayers - 1];
+      LnArgs ln{x_cur, x_alt, p.part, kPSplits, P.l2_b, P.n3_g, P.n3_b};
+      gemm_phase<64, 64, 4, 4, 1, 0>(s_dyn, nullptr, 0, ln, p.cls_w, kPD, p.cls_b, p.logits, p.vocab, R, p.vocab);
+      grid_barrier(p.bar, gen, p.trace, 9);
+    }
+    // ---- beam step: one CTA per clip; it also writes the next step's embedding into x_cur (free: LN wrote x_alt)
+    for (int clip = blockIdx.x; clip < p.batch; clip += gridDim.x)
+      beam_clip(s_beam, p.logits, p.forbid, p.bs, step, cur, p.min_len, p.beam, p.max_len, p.vocab, clip, p.emb, p.pe, x_cur);
+    cur ^= 1;
+    grid_barrier(p.bar, gen, p.trace, 10);
+    if (*reinterpret_cast<volatile int*>(&p.bs.done[0])) break;  // uniform: read after the barrier by every CTA
+  }
+}
+
+int launch_decoder_persistent(const PersistentArgs& args, cudaStream_t stream) {
+  static int max_blocks_per_sm = -1;
+  const size_t smem = (size_t)(64 + 64) * kPanelLds * sizeof(float);
+  if (max_blocks_per_sm < 0) {
+    CNB_CUDA_OK(cudaFuncSetAttribute(decoder_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CNB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, decoder_persistent_kernel, kPThreads, smem));
+  }
+  CNB_REQUIRE(max_blocks_per_sm >= 1, "persistent decoder kernel does not fit on an SM");
+  CNB_REQUIRE((size_t)8 * args.tp * sizeof(float) <= smem, "too many encoder frames for the cross-attention score buffer");
+  int dev = 0, n_sm = 0;
+  CNB_CUDA_OK(cudaGetDevice(&dev));
+  CNB_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  CNB_CUDA_OK(cudaMemsetAsync(args.bar, 0, 2 * sizeof(unsigned int), stream));
+  void* kargs[] = {const_cast<PersistentArgs*>(&args)};
+  CNB_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(decoder_persistent_kernel), dim3(n_sm), dim3(kPThreads), kargs,
+                                          smem, stream));
+  count_launch();
+  return 0;
+}
+
+}  // namespace cnb

@@ -60,6 +60,11 @@ template <typename OutT>
 int launch_gemm_f32(const float* a, int64_t lda, const float* w, int m, int n, int k, Epilogue epi, const EpiParams& ep,
                     OutT* out, int64_t ldo, cudaStream_t stream, int splits = 1);
 
+// Latency-optimised fp32 GEMM for the decoder (whole 256-wide K panel in shared memory, one L2 round trip).  K > 256 is
+// split into ceil(K/256) slices writing raw partial sums to out + z*M*ldo (epilogue left to the consumer).
+int launch_gemm_f32_panel(const float* a, int64_t lda, const float* w, int m, int n, int k, Epilogue epi, const EpiParams& ep,
+                          float* out, int64_t ldo, cudaStream_t stream);
+
 // bf16 tcgen05 GEMM (fast mode).  A (M,K) bf16 contiguous, W (N,K) bf16 contiguous (both K-major, TMA-fed).
 struct TcGemmPlan;  // opaque: TMA descriptors + tile configuration
 template <typename OutT>
@@ -99,6 +104,26 @@ int launch_beam_step(float* logits, const uint8_t* forbid, BeamState st, int ste
                      const DecoderDims& dd, cudaStream_t stream);
 int launch_beam_finalize(BeamState st, int64_t* best_preds, float* best_lp, int* best_len, const DecoderDims& dd,
                          cudaStream_t stream);
+
+// ---- persistent decoder: the whole decode loop in one cooperative launch (decoder_persistent.cu) ----------------------
+struct PLayer {
+  const float *sa_in_w, *sa_in_b, *sa_out_w, *sa_out_b, *ca_q_w, *ca_q_b, *ca_out_w, *ca_out_b;
+  const float *l1_w, *l1_b, *l2_w, *l2_b, *n1_g, *n1_b, *n2_g, *n2_b, *n3_g, *n3_b;
+};
+struct PersistentArgs {
+  PLayer layers[6];
+  const float *emb, *pe, *cls_w, *cls_b;
+  const float* ckv;          // (B*T', 6*512) cross-attention K|V of all layers
+  const int* lens;
+  const int64_t* bos_ids;
+  const uint8_t* forbid;
+  float *xa, *xb, *qkv, *attn, *tmp, *ff, *part, *logits, *kc, *vc;
+  BeamState bs;
+  unsigned int* bar;         // 2 words, zeroed by the launcher
+  unsigned long long* trace; // optional (debug): 3 words per barrier, written by block 0
+  int rows, beam, tp, max_len, vocab, min_len, batch;
+};
+int launch_decoder_persistent(const PersistentArgs& args, cudaStream_t stream);
 
 // global launch counter (reported through cnb_launch_count)
 void count_launch();

@@ -28,6 +28,7 @@ class CoNeTTEModel:
         device: Union[int, str, torch.device] = 0,
         precision: str = "fast",
         enc_chunk: int = 0,
+        decoder: str = "graph",
         audioset_idx_to_name: Optional[Dict[int, str]] = None,
     ) -> None:
         self.config = config or CoNeTTEConfig()
@@ -38,7 +39,7 @@ class CoNeTTEModel:
         if state_dict["model.decoder.classifier.weight"].shape[0] != vocab:
             raise ValueError("vocabulary size does not match decoder.classifier.weight")
         dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
-        self.engine = Engine(state_dict, vocab, dev.index or 0, precision, enc_chunk)
+        self.engine = Engine(state_dict, vocab, dev.index or 0, precision, enc_chunk, decoder)
         self.task_id_to_token_id = state_dict["model.task_id_to_token_id"].to("cpu", torch.int64)
         fm = state_dict.get("model.forbid_rep_mask")
         self.forbid_rep_mask = None if fm is None else fm.to("cpu", torch.uint8)

@@ -281,6 +281,30 @@ def test_beam_search_vs_oracle(small_sd, beam, min_len, max_len, mode, eos_bias)
             torch.testing.assert_close(m[firm], r[firm], rtol=1e-4, atol=1e-4)
 
 
+def test_decoder_execution_modes_agree_bitwise(small_sd):
+    """persistent cooperative kernel == CUDA-graph replay == eager per-op kernels (same arithmetic, same order)."""
+    from conette_audio_captioning_b200.engine import Engine
+
+    g = torch.Generator().manual_seed(11)
+    b, tp = 37, 31  # 111 rows: exercises ragged 32/64-row tiles
+    fe = torch.randn(b, tp, 768, generator=g)
+    lens = torch.randint(1, tp + 1, (b,), generator=g)
+    bos_ids = small_sd["model.task_id_to_token_id"][torch.randint(0, 7, (b,), generator=g)]
+    forbid = small_sd["model.forbid_rep_mask"]
+    outs = {}
+    for mode in ("persistent", "graph", "eager"):
+        eng = Engine(small_sd, vocab_size=forbid.shape[0], precision="parity", decoder=mode)
+        try:
+            outs[mode] = [o.cpu() for o in eng.decode(fe, lens, bos_ids, forbid, 3, 3, 20)]
+            again = [o.cpu() for o in eng.decode(fe, lens, bos_ids, forbid, 3, 3, 20)]  # second call: graph replay / reuse
+            assert all(torch.equal(a, c) for a, c in zip(outs[mode], again)), mode
+        finally:
+            eng.close()
+    for mode in ("graph", "eager"):
+        for a, c in zip(outs["persistent"], outs[mode]):
+            assert torch.equal(a, c), mode
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # end to end through the reference-facing API
 # ----------------------------------------------------------------------------------------------------------------------
