@@ -91,6 +91,7 @@ struct cnb_handle {
   int* zero_flag = nullptr;  // device int[4] that stays 0: "done" flag for non-beam callers
   // CUDA-graph replay of the decode loop
   bool use_persistent = true;
+  bool use_fused = true;
   bool use_graphs = true;
   cudaStream_t stream = nullptr;  // library-owned non-blocking stream (graph capture / replay, host-API copies)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -660,6 +661,26 @@ static int decode_body(cnb_handle* h, const DecWs& w, BeamState bs, const float*
   return 0;
 }
 
+// "fused" variant: LayerNorm-on-load GEMMs + beam/embedding fusion (50 launches per step instead of 69)
+static int decode_body_fused(cnb_handle* h, const DecWs& w, const PersistentArgs& pa, const float* frame_embs, int batch,
+                             const DecoderDims& dd, int64_t* preds, float* lprobs, int64_t* mult_preds, float* mult_lprobs,
+                             int32_t* info, int* best_len, cudaStream_t st) {
+  if (int rc = dec_project(h, frame_embs, batch, dd.tp, w, st)) return rc;
+  if (int rc = launch_decoder_init(pa, st)) return rc;
+  float* x_cur = pa.xa;
+  float* x_alt = pa.xb;
+  int cur = 0;
+  for (int i = 0; i < dd.max_len; ++i) {
+    if (int rc = launch_decoder_step_fused(pa, i, cur, &x_cur, &x_alt, st)) return rc;
+    cur ^= 1;
+  }
+  if (int rc = launch_beam_finalize(pa.bs, preds, lprobs, best_len, dd, st)) return rc;
+  gather_mult_kernel<<<(dd.rows * dd.max_len + 255) / 256, 256, 0, st>>>(pa.bs, mult_preds, mult_lprobs, best_len, info,
+                                                                        dd.rows, dd.max_len, batch);
+  CNB_LAUNCH_OK();
+  return 0;
+}
+
 // The ~1400 small dependent launches of a 20-step decode are captured once per (shape, buffer) signature into a CUDA
 // graph and replayed on the handle's own stream (stream capture is illegal on the legacy default stream callers often
 // pass); fork/join events order it against the caller's stream.  Profiling mode runs eagerly (event brackets).
@@ -684,24 +705,26 @@ static int decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, c
   bs.tokens[0] = tok0; bs.tokens[1] = tok1; bs.src_row[0] = src0; bs.src_row[1] = src1;
   bs.sum_lp = sum_lp; bs.live = live; bs.out_preds = out_preds; bs.out_lp = out_lp; bs.done = done;
 
+  // argument block shared by the persistent kernel and the fused per-phase launches (decoder_persistent.cu)
+  WS(h, "dxb", float, (size_t)rows * kD, xb);
+  WS(h, "dbar", unsigned int, 64, bar);
+  PersistentArgs pa;
+  for (int l = 0; l < kLayers; ++l) {
+    const LayerW& L = h->layers[l];
+    pa.layers[l] = PLayer{L.sa_in_w, L.sa_in_b, L.sa_out_w, L.sa_out_b, L.ca_q_w, L.ca_q_b, L.ca_out_w, L.ca_out_b, L.l1_w,
+                          L.l1_b, L.l2_w, L.l2_b, L.n1_g, L.n1_b, L.n2_g, L.n2_b, L.n3_g, L.n3_b};
+  }
+  pa.emb = h->emb; pa.pe = h->pe; pa.cls_w = h->cls_w; pa.cls_b = h->cls_b;
+  pa.ckv = w.ckv; pa.lens = lens; pa.bos_ids = bos_ids; pa.forbid = forbid;
+  pa.xa = w.x; pa.xb = xb; pa.qkv = w.qkv; pa.attn = w.attn; pa.tmp = w.tmp; pa.ff = w.ff; pa.part = w.part;
+  pa.logits = w.logits; pa.kc = w.kc; pa.vc = w.vc; pa.bs = bs; pa.bar = bar;
+  pa.rows = rows; pa.beam = beam; pa.tp = tp; pa.max_len = max_len; pa.vocab = h->cfg.vocab_size; pa.min_len = min_len;
+  pa.batch = batch;
+  pa.trace = nullptr;
+
   if (!h->prof_on && h->use_persistent) {
-    // one cooperative launch for the whole decode loop (decoder_persistent.cu)
-    WS(h, "dxb", float, (size_t)rows * kD, xb);
-    WS(h, "dbar", unsigned int, 64, bar);
+    // one cooperative launch for the whole decode loop
     if (int rc = dec_project(h, frame_embs, batch, tp, w, st)) return rc;
-    PersistentArgs pa;
-    for (int l = 0; l < kLayers; ++l) {
-      const LayerW& L = h->layers[l];
-      pa.layers[l] = PLayer{L.sa_in_w, L.sa_in_b, L.sa_out_w, L.sa_out_b, L.ca_q_w, L.ca_q_b, L.ca_out_w, L.ca_out_b, L.l1_w,
-                            L.l1_b, L.l2_w, L.l2_b, L.n1_g, L.n1_b, L.n2_g, L.n2_b, L.n3_g, L.n3_b};
-    }
-    pa.emb = h->emb; pa.pe = h->pe; pa.cls_w = h->cls_w; pa.cls_b = h->cls_b;
-    pa.ckv = w.ckv; pa.lens = lens; pa.bos_ids = bos_ids; pa.forbid = forbid;
-    pa.xa = w.x; pa.xb = xb; pa.qkv = w.qkv; pa.attn = w.attn; pa.tmp = w.tmp; pa.ff = w.ff; pa.part = w.part;
-    pa.logits = w.logits; pa.kc = w.kc; pa.vc = w.vc; pa.bs = bs; pa.bar = bar;
-    pa.rows = rows; pa.beam = beam; pa.tp = tp; pa.max_len = max_len; pa.vocab = h->cfg.vocab_size; pa.min_len = min_len;
-    pa.batch = batch;
-    pa.trace = nullptr;
     const bool trace_on = getenv("CNB_DEC_TRACE") != nullptr;
     const int n_bar = 1 + max_len * (kLayers * 8 + 2);
     if (trace_on) {
@@ -742,15 +765,19 @@ static int decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, c
 
   const std::vector<int64_t> key = {batch, tp, beam, min_len, max_len, (int64_t)frame_embs, (int64_t)lens, (int64_t)bos_ids,
                                     (int64_t)forbid, (int64_t)preds, (int64_t)lprobs, (int64_t)mult_preds,
-                                    (int64_t)mult_lprobs, (int64_t)info, (int64_t)w.logits, (int64_t)w.kc, (int64_t)tok0};
+                                    (int64_t)mult_lprobs, (int64_t)info, (int64_t)w.logits, (int64_t)w.kc, (int64_t)tok0,
+                                    (int64_t)h->use_fused};
   DecGraph* dg = nullptr;
   for (auto& g : h->dec_graphs)
     if (g.key == key) dg = &g;
   if (!dg) {
     const int64_t before = g_launches.load();
     CNB_CUDA_OK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-    const int rc = decode_body(h, w, bs, frame_embs, lens, bos_ids, forbid, batch, min_len, dd, preds, lprobs, mult_preds,
-                               mult_lprobs, info, best_len, h->stream);
+    const int rc = h->use_fused
+                       ? decode_body_fused(h, w, pa, frame_embs, batch, dd, preds, lprobs, mult_preds, mult_lprobs, info,
+                                           best_len, h->stream)
+                       : decode_body(h, w, bs, frame_embs, lens, bos_ids, forbid, batch, min_len, dd, preds, lprobs, mult_preds,
+                                     mult_lprobs, info, best_len, h->stream);
     cudaGraph_t graph = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
     const int64_t n_kernels = g_launches.load() - before;
@@ -831,6 +858,7 @@ int cnb_create(const cnb_config* cfg, cnb_handle** out) {
   CNB_CUDA_OK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   h->use_graphs = (cfg->reserved[0] & 1) == 0;      // reserved[0] bit 0: disable CUDA graphs (debugging)
   h->use_persistent = (cfg->reserved[0] & 2) == 0;  // reserved[0] bit 1: disable the persistent decoder kernel
+  h->use_fused = (cfg->reserved[0] & 4) == 0;       // reserved[0] bit 2: graph mode replays the unfused per-op kernels
   *out = h;
   return 0;
 }

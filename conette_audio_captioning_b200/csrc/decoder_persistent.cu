@@ -15,6 +15,8 @@
 // Reference semantics: nn/decoders/aac_tfmer.py:100-116, nn/decoding/beam.py:113-203 (see decoder.cu / beam.cu).
 #include <cooperative_groups.h>
 
+#include <utility>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -71,7 +73,7 @@ __device__ __forceinline__ void cp_async16_cg(void* smem, const void* gmem, bool
 // ---------------------------------------------------------------------------------------------------------------------
 // GEMM tile: out[m0.., n0..] = epi(A[m, k_begin..k_begin+256) . W[n, k_begin..+256))
 //   LN_MODE 0: A rows come from global `a` (row stride lda)
-//   LN_MODE 1: A row = LayerNorm(xin[m] + ln_bias + sum_s delta[s][m]) * g + b   (k_begin must be 0, K = 256);
+//   LN_MODE n>0: A row = LayerNorm(xin[m] + ln_bias + sum_{s<n} delta[s][m]) * g + b   (k_begin must be 0, K = 256);
 //              tiles with n0 == 0 also store the normalised rows to xout
 //   EPI 0: + bias   1: gelu_erf(+ bias)   2: raw store to slab z (split-K partial)
 // ---------------------------------------------------------------------------------------------------------------------
@@ -110,38 +112,62 @@ __device__ __forceinline__ void gemm_tile(float* s_panel, const float* a, int64_
     }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
-  if (LN_MODE == 1) {
-    // each warp normalises BM/8 rows directly into the A panel
-    for (int r = warp; r < BM; r += kPThreads / 32) {
-      const int m = m0 + r;
-      float v[8];
-      if (m < M) {
-        float s = 0.f;
+  if (LN_MODE != 0) {
+    // LayerNorm-on-load: warp w owns rows w, w+8, ... of the tile.  LN_MODE = number of delta slabs (1 or 8), a compile-time
+    // constant so that every load of every row is issued before the first reduction (one L2 round trip, not one per row).
+    constexpr int RPW = BM / (kPThreads / 32);
+    constexpr int NSPLIT = LN_MODE;
+    float v[RPW][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int c = lane + 32 * j;
-          float d = ln.ln_bias ? ln.ln_bias[c] : 0.f;
-          for (int sp = 0; sp < ln.nsplit; ++sp) d += __ldcg(&ln.delta[((int64_t)sp * M + m) * kPD + c]);
-          v[j] = __ldcg(&ln.xin[(int64_t)m * kPD + c]) + d;
-          s += v[j];
+    for (int rr = 0; rr < RPW; ++rr) {
+      const int m = m0 + warp + rr * (kPThreads / 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = lane + 32 * j;
+        // same association as add_ln_kernel: x + (bias + delta_0 + delta_1 + ...), so the execution modes stay bit-identical
+        float d = ln.ln_bias ? ln.ln_bias[c] : 0.f;
+        float xv = 0.f;
+        if (m < M) {
+          xv = __ldcg(&ln.xin[(int64_t)m * kPD + c]);
+#pragma unroll
+          for (int sp = 0; sp < NSPLIT; ++sp) d += __ldcg(&ln.delta[((int64_t)sp * M + m) * kPD + c]);
         }
-        const float mean = warp_sum(s) * (1.f / kPD);
-        float q = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) q += (v[j] - mean) * (v[j] - mean);
-        const float rstd = 1.f / sqrtf(warp_sum(q) * (1.f / kPD) + 1e-5f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int c = lane + 32 * j;
-          v[j] = (v[j] - mean) * rstd * ln.g[c] + ln.b[c];
-          if (n0 == 0) ln.xout[(int64_t)m * kPD + c] = v[j];
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        v[rr][j] = xv + d;
       }
+    }
+    float gg[8], bb[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) As[r][lane + 32 * j] = v[j];
+    for (int j = 0; j < 8; ++j) {
+      const int c = lane + 32 * j;
+      gg[j] = ln.g[c];
+      bb[j] = ln.b[c];
+    }
+    float mean[RPW], rstd[RPW];
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[rr][j];
+      mean[rr] = warp_sum(s) * (1.f / kPD);
+    }
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q += (v[rr][j] - mean[rr]) * (v[rr][j] - mean[rr]);
+      rstd[rr] = 1.f / sqrtf(warp_sum(q) * (1.f / kPD) + 1e-5f);
+    }
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+      const int r = warp + rr * (kPThreads / 32);
+      const int m = m0 + r;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = lane + 32 * j;
+        const float y = (m < M) ? (v[rr][j] - mean[rr]) * rstd[rr] * gg[j] + bb[j] : 0.f;
+        if (m < M && n0 == 0) ln.xout[(int64_t)m * kPD + c] = y;
+        As[r][c] = y;
+      }
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -522,7 +548,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decoder_persistent_kernel(const 
       } else {
         const PLayer& P = p.layers[l - 1];
         ln = LnArgs{x_cur, x_alt, p.part, kPSplits, P.l2_b, P.n3_g, P.n3_b};
-        gemm_phase<32, 32, 2, 2, 1, 0>(s_dyn, nullptr, 0, ln, L.sa_in_w, kPD, L.sa_in_b, p.qkv, 768, R, 768);
+        gemm_phase<32, 32, 2, 2, kPSplits, 0>(s_dyn, nullptr, 0, ln, L.sa_in_w, kPD, L.sa_in_b, p.qkv, 768, R, 768);
         float* t = x_cur; x_cur = x_alt; x_alt = t;
       }
       grid_barrier(p.bar, gen, p.trace, 1);
@@ -552,7 +578,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decoder_persistent_kernel(const 
     {  // ---- LN3 of the last layer on load + classifier
       const PLayer& P = p.layers[kPLayers - 1];
       LnArgs ln{x_cur, x_alt, p.part, kPSplits, P.l2_b, P.n3_g, P.n3_b};
-      gemm_phase<64, 64, 4, 4, 1, 0>(s_dyn, nullptr, 0, ln, p.cls_w, kPD, p.cls_b, p.logits, p.vocab, R, p.vocab);
+      gemm_phase<64, 64, 4, 4, kPSplits, 0>(s_dyn, nullptr, 0, ln, p.cls_w, kPD, p.cls_b, p.logits, p.vocab, R, p.vocab);
       grid_barrier(p.bar, gen, p.trace, 9);
     }
     // ---- beam step: one CTA per clip; it also writes the next step's embedding into x_cur (free: LN wrote x_alt)
@@ -562,6 +588,143 @@ __global__ void __launch_bounds__(kPThreads, 1) decoder_persistent_kernel(const 
     grid_barrier(p.bar, gen, p.trace, 10);
     if (*reinterpret_cast<volatile int*>(&p.bs.done[0])) break;  // uniform: read after the barrier by every CTA
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The same phases as stand-alone kernels ("fused graph" decoder mode): LayerNorm-on-load GEMMs, attention phases and the
+// beam step (+ next-token embedding) are launched per phase and replayed from a CUDA graph -- 50 launches per step instead
+// of 69 -- with bit-identical arithmetic to the persistent kernel.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int BM, int BN, int TM, int TN, int LN_MODE, int EPI>
+__global__ void __launch_bounds__(kPThreads)
+gemm_phase_kernel(const float* a, int64_t lda, LnArgs ln, const float* W, int K, const float* bias, float* out, int64_t ldo,
+                  int M, int N) {
+  extern __shared__ __align__(16) float s_dyn[];
+  gemm_phase<BM, BN, TM, TN, LN_MODE, EPI>(s_dyn, a, lda, ln, W, K, bias, out, ldo, M, N);
+}
+
+__global__ void __launch_bounds__(kPThreads)
+self_attn_phase_kernel(const float* qkv, float* kcache, float* vcache, const int* src_row, int pos, int max_len, float* attn,
+                       int rows) {
+  self_attn_phase(qkv, kcache, vcache, src_row, pos, max_len, attn, rows);
+}
+
+__global__ void __launch_bounds__(kPThreads)
+cross_attn_phase_kernel(const float* q, const float* ck, const float* cv, int64_t kv_stride, const int* lens, int beam, int tp,
+                        float* attn, int rows) {
+  extern __shared__ __align__(16) float s_dyn[];
+  cross_attn_phase(s_dyn, q, ck, cv, kv_stride, lens, beam, tp, attn, rows);
+}
+
+__global__ void __launch_bounds__(kPThreads)
+beam_embed_kernel(float* logits, const uint8_t* forbid, BeamState st, int step, int cur, int min_len, int beam, int max_len,
+                  int vocab, const float* emb, const float* pe, float* x_next) {
+  __shared__ BeamSmem sm;
+  if (st.done[0]) return;
+  beam_clip(sm, logits, forbid, st, step, cur, min_len, beam, max_len, vocab, blockIdx.x, emb, pe, x_next);
+}
+
+template <int BM, int BN, int TM, int TN, int LN_MODE, int EPI>
+static int launch_phase_cfg(const float* a, int64_t lda, const LnArgs& ln, const float* W, int K, const float* bias, float* out,
+                            int64_t ldo, int M, int N, cudaStream_t stream) {
+  constexpr int smem = (BM + BN) * kPanelLds * (int)sizeof(float);
+  auto kern = gemm_phase_kernel<BM, BN, TM, TN, LN_MODE, EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CNB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int n_tiles = (int)(ceil_div(M, BM) * ceil_div(N, BN)) * (EPI == 2 ? K / 256 : 1);
+  kern<<<n_tiles, kPThreads, smem, stream>>>(a, lda, ln, W, K, bias, out, ldo, M, N);
+  CNB_LAUNCH_OK();
+  return 0;
+}
+
+// one decoder step (position `step`) as 50 phase launches; x_cur / x_alt are swapped in place like in the persistent kernel
+int launch_decoder_step_fused(const PersistentArgs& p, int step, int cur, float** x_cur_io, float** x_alt_io,
+                              cudaStream_t st) {
+  float* x_cur = *x_cur_io;
+  float* x_alt = *x_alt_io;
+  const int R = p.rows;
+  const int64_t cache_l = (int64_t)R * p.max_len * kPD;
+  const int64_t kv_stride = kPLayers * 2 * kPD;
+  const int* src_row = p.bs.src_row[cur];
+  const int attn_blocks = (int)ceil_div((int64_t)R * kPHeads, kPThreads / 32);
+  for (int l = 0; l < kPLayers; ++l) {
+    const PLayer& L = p.layers[l];
+    LnArgs ln{};
+    if (l == 0) {
+      if (int rc = launch_phase_cfg<32, 32, 2, 2, 0, 0>(x_cur, kPD, ln, L.sa_in_w, kPD, L.sa_in_b, p.qkv, 768, R, 768, st)) return rc;
+    } else {
+      const PLayer& P = p.layers[l - 1];
+      ln = LnArgs{x_cur, x_alt, p.part, kPSplits, P.l2_b, P.n3_g, P.n3_b};
+      if (int rc = launch_phase_cfg<32, 32, 2, 2, kPSplits, 0>(nullptr, 0, ln, L.sa_in_w, kPD, L.sa_in_b, p.qkv, 768, R, 768, st)) return rc;
+      std::swap(x_cur, x_alt);
+    }
+    self_attn_phase_kernel<<<attn_blocks, kPThreads, 0, st>>>(p.qkv, p.kc + l * cache_l, p.vc + l * cache_l, src_row, step,
+                                                             p.max_len, p.attn, R);
+    CNB_LAUNCH_OK();
+    if (int rc = launch_phase_cfg<32, 32, 2, 2, 0, 0>(p.attn, kPD, ln, L.sa_out_w, kPD, L.sa_out_b, p.tmp, kPD, R, kPD, st)) return rc;
+    ln = LnArgs{x_cur, x_alt, p.tmp, 1, nullptr, L.n1_g, L.n1_b};
+    if (int rc = launch_phase_cfg<32, 32, 2, 2, 1, 0>(nullptr, 0, ln, L.ca_q_w, kPD, L.ca_q_b, p.qkv, kPD, R, kPD, st)) return rc;
+    std::swap(x_cur, x_alt);
+    cross_attn_phase_kernel<<<attn_blocks, kPThreads, (size_t)8 * p.tp * sizeof(float), st>>>(
+        p.qkv, p.ckv + (int64_t)l * 2 * kPD, p.ckv + (int64_t)l * 2 * kPD + kPD, kv_stride, p.lens, p.beam, p.tp, p.attn, R);
+    CNB_LAUNCH_OK();
+    if (int rc = launch_phase_cfg<32, 32, 2, 2, 0, 0>(p.attn, kPD, ln, L.ca_out_w, kPD, L.ca_out_b, p.tmp, kPD, R, kPD, st)) return rc;
+    ln = LnArgs{x_cur, x_alt, p.tmp, 1, nullptr, L.n2_g, L.n2_b};
+    if (int rc = launch_phase_cfg<32, 64, 2, 4, 1, 1>(nullptr, 0, ln, L.l1_w, kPD, L.l1_b, p.ff, kPFF, R, kPFF, st)) return rc;
+    std::swap(x_cur, x_alt);
+    if (int rc = launch_phase_cfg<64, 64, 4, 4, 0, 2>(p.ff, kPFF, ln, L.l2_w, kPFF, nullptr, p.part, kPD, R, kPD, st)) return rc;
+  }
+  {
+    const PLayer& P = p.layers[kPLayers - 1];
+    LnArgs ln{x_cur, x_alt, p.part, kPSplits, P.l2_b, P.n3_g, P.n3_b};
+    if (int rc = launch_phase_cfg<64, 64, 4, 4, kPSplits, 0>(nullptr, 0, ln, p.cls_w, kPD, p.cls_b, p.logits, p.vocab, R, p.vocab, st))
+      return rc;
+  }
+  beam_embed_kernel<<<p.batch, kPThreads, 0, st>>>(p.logits, p.forbid, p.bs, step, cur, p.min_len, p.beam, p.max_len, p.vocab,
+                                                   p.emb, p.pe, x_cur);
+  CNB_LAUNCH_OK();
+  *x_cur_io = x_cur;
+  *x_alt_io = x_alt;
+  return 0;
+}
+
+// beam-state initialisation + embedding of the task BOS tokens into x (what the persistent kernel does before step 0)
+__global__ void decoder_init_kernel(const PersistentArgs p) {
+  const int R = p.rows, tstride = p.max_len + 1;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < R; r += gridDim.x * blockDim.x) {
+    for (int q = 0; q <= p.max_len; ++q) {
+      p.bs.tokens[0][(int64_t)r * tstride + q] = 0;
+      p.bs.tokens[1][(int64_t)r * tstride + q] = 0;
+    }
+    p.bs.tokens[0][(int64_t)r * tstride] = (int)p.bos_ids[r / p.beam];
+    for (int q = 0; q < p.max_len; ++q) {
+      p.bs.src_row[0][(int64_t)r * p.max_len + q] = r;
+      p.bs.src_row[1][(int64_t)r * p.max_len + q] = r;
+      p.bs.out_preds[(int64_t)r * p.max_len + q] = 0;
+    }
+    p.bs.sum_lp[r] = 0.f;
+    p.bs.live[r] = 1;
+    p.bs.out_lp[r] = 0.f;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    p.bs.done[0] = 0;
+    p.bs.done[1] = p.max_len;
+    p.bs.done[2] = R;
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < R * kPD; i += gridDim.x * blockDim.x) {
+    const int r = i / kPD, c = i - r * kPD;
+    const int tok = (int)p.bos_ids[r / p.beam];
+    p.xa[i] = p.emb[(int64_t)tok * kPD + c] * 16.0f + p.pe[c];
+  }
+}
+
+int launch_decoder_init(const PersistentArgs& p, cudaStream_t st) {
+  decoder_init_kernel<<<(p.rows * kPD + 255) / 256, 256, 0, st>>>(p);
+  CNB_LAUNCH_OK();
+  return 0;
 }
 
 int launch_decoder_persistent(const PersistentArgs& args, cudaStream_t stream) {

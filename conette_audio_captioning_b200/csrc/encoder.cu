@@ -112,12 +112,9 @@ dwconv_ln_kernel(const float* __restrict__ x, int H, const float* __restrict__ w
                                       : make_float2(0.f, 0.f);
       }
 #pragma unroll
-      for (int p = 0; p < PW; ++p)
+      for (int j = 0; j < 7; ++j)
 #pragma unroll
-        for (int j = 0; j < 7; ++j) {
-          acc[p].x = fmaf(in[p + j].x, wr[j].x, acc[p].x);
-          acc[p].y = fmaf(in[p + j].y, wr[j].y, acc[p].y);
-        }
+        for (int p = 0; p < PW; ++p) acc[p] = __ffma2_rn(in[p + j], wr[j], acc[p]);
     }
   } else {
 #pragma unroll
@@ -290,17 +287,14 @@ dwconv_ln_ring_kernel(const float* __restrict__ x, int H, int seg_rows, const fl
       float2 in[PW + 6];
 #pragma unroll
       for (int j = 0; j < PW + 6; ++j) in[j] = *reinterpret_cast<const float2*>(row + j * C);
-      if (i < 7) {
+      // tap-major order: consecutive FFMA2 hit 7 (14) different accumulators, so the issue stream has no dependent chains
 #pragma unroll
-        for (int p = 0; p < PW; ++p)
+      for (int j = 0; j < 7; ++j) {
 #pragma unroll
-          for (int j = 0; j < 7; ++j) acc0[p] = __ffma2_rn(in[p + j], wr[i * 7 + j], acc0[p]);
-      }
-      if (i > 0) {
-#pragma unroll
-        for (int p = 0; p < PW; ++p)
-#pragma unroll
-          for (int j = 0; j < 7; ++j) acc1[p] = __ffma2_rn(in[p + j], wr[(i - 1) * 7 + j], acc1[p]);
+        for (int p = 0; p < PW; ++p) {
+          if (i < 7) acc0[p] = __ffma2_rn(in[p + j], wr[i * 7 + j], acc0[p]);
+          if (i > 0) acc1[p] = __ffma2_rn(in[p + j], wr[(i - 1) * 7 + j], acc1[p]);
+        }
       }
     }
     // ---- LayerNorm statistics: (sum, sumsq) for 14 pixels

@@ -124,6 +124,10 @@ struct PersistentArgs {
   int rows, beam, tp, max_len, vocab, min_len, batch;
 };
 int launch_decoder_persistent(const PersistentArgs& args, cudaStream_t stream);
+// the same phases as separate launches (graph-replayed "fused" mode)
+int launch_decoder_init(const PersistentArgs& args, cudaStream_t stream);
+int launch_decoder_step_fused(const PersistentArgs& args, int step, int cur, float** x_cur_io, float** x_alt_io,
+                              cudaStream_t stream);
 
 // global launch counter (reported through cnb_launch_count)
 void count_launch();

@@ -43,7 +43,7 @@ class Engine:
         cfg.enc_chunk = enc_chunk
         # decoder execution mode: CUDA-graph replay of the per-op kernels (default: fastest so far, 12 ms / 20 steps at
         # R=192), one persistent cooperative kernel with software grid barriers (14 ms), or eager launches
-        cfg.reserved[0] = {"persistent": 0, "graph": 2, "eager": 3}[decoder]
+        cfg.reserved[0] = {"persistent": 0, "graph": 2, "graph_unfused": 6, "eager": 3}[decoder]
         handle = C.c_void_p()
         _lib.check(self.lib.cnb_create(C.byref(cfg), C.byref(handle)))
         self.handle = handle
