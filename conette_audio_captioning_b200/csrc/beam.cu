@@ -51,6 +51,7 @@ beam_step_kernel(float* __restrict__ logits, const uint8_t* __restrict__ forbid,
   if (st.done[0]) return;
   __shared__ float s_lse_max[kMaxBeam];
   __shared__ float s_lse_log[kMaxBeam];
+  __shared__ float s_redw[2][kMaxBeam][kBeamThreads / 32];
   __shared__ Cand s_cand[2][kBeamThreads / 32];
   __shared__ int s_owner[2][kBeamThreads / 32];
   __shared__ Cand s_win[kMaxBeam];
@@ -107,19 +108,43 @@ beam_step_kernel(float* __restrict__ logits, const uint8_t* __restrict__ forbid,
   }
   __syncthreads();
 
-  // ---- log-softmax statistics: warp j owns row j (online max / sum-exp, shuffle reductions only)
-  for (int j = warp; j < nrows_used; j += kBeamThreads / 32) {
+  // ---- log-softmax statistics, all 8 warps per row: unrolled strided loads (8 in flight per thread), two-level reductions
+  for (int j = 0; j < nrows_used; ++j) {
     const float* lg = logits + (int64_t)(row0 + label_at(j)) * vocab;
     float mx = -INFINITY;
-    for (int v = lane; v < vocab; v += 32) mx = fmaxf(mx, lg[v]);
-    mx = warp_max(mx);
-    float sm = 0.f;
-    for (int v = lane; v < vocab; v += 32) sm += expf(lg[v] - mx);
-    sm = warp_sum(sm);
-    if (lane == 0) {
-      s_lse_max[j] = mx;
-      s_lse_log[j] = logf(sm);
+    for (int v0 = tid; v0 < vocab; v0 += 8 * kBeamThreads) {
+      float t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = (v0 + u * kBeamThreads < vocab) ? lg[v0 + u * kBeamThreads] : -INFINITY;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) mx = fmaxf(mx, t[u]);
     }
+    mx = warp_max(mx);
+    if (lane == 0) s_redw[0][j][warp] = mx;
+  }
+  __syncthreads();
+  for (int j = 0; j < nrows_used; ++j) {
+    const float* lg = logits + (int64_t)(row0 + label_at(j)) * vocab;
+    float mx = s_redw[0][j][0];
+#pragma unroll
+    for (int i = 1; i < kBeamThreads / 32; ++i) mx = fmaxf(mx, s_redw[0][j][i]);
+    float sm = 0.f;
+    for (int v0 = tid; v0 < vocab; v0 += 8 * kBeamThreads) {
+      float t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = (v0 + u * kBeamThreads < vocab) ? lg[v0 + u * kBeamThreads] : -INFINITY;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) sm += expf(t[u] - mx);
+    }
+    sm = warp_sum(sm);
+    if (lane == 0) s_redw[1][j][warp] = sm;
+    if (tid == 0) s_lse_max[j] = mx;
+  }
+  __syncthreads();
+  if (tid < nrows_used) {
+    float t = 0.f;
+    for (int i = 0; i < kBeamThreads / 32; ++i) t += s_redw[1][tid][i];  // fixed order
+    s_lse_log[tid] = logf(t);
   }
   __syncthreads();
 

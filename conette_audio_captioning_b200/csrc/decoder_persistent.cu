@@ -323,6 +323,7 @@ __device__ __forceinline__ bool pbetter(const PCand& a, const PCand& b) { return
 
 struct BeamSmem {
   float lse_max[kPMaxBeam], lse_log[kPMaxBeam];
+  float red[2][kPMaxBeam][kPThreads / 32];
   PCand cand[2][kPThreads / 32];
   int owner[2][kPThreads / 32];
   PCand win[kPMaxBeam];
@@ -377,18 +378,43 @@ __device__ void beam_clip(BeamSmem& sm, float* logits, const uint8_t* forbid, co
       }
     }
     __syncthreads();
-    for (int j = warp; j < nrows_used; j += kPThreads / 32) {
+    // log-softmax statistics, all 8 warps per row: unrolled strided loads (8 in flight per thread), two-level reductions
+    for (int j = 0; j < nrows_used; ++j) {
       const float* lg = logits + (int64_t)(row0 + label_at(j)) * vocab;
       float mx = -INFINITY;
-      for (int v = lane; v < vocab; v += 32) mx = fmaxf(mx, lg[v]);
-      mx = warp_max(mx);
-      float s = 0.f;
-      for (int v = lane; v < vocab; v += 32) s += expf(lg[v] - mx);
-      s = warp_sum(s);
-      if (lane == 0) {
-        sm.lse_max[j] = mx;
-        sm.lse_log[j] = logf(s);
+      for (int v0 = tid; v0 < vocab; v0 += 8 * kPThreads) {
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = (v0 + u * kPThreads < vocab) ? lg[v0 + u * kPThreads] : -INFINITY;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) mx = fmaxf(mx, t[u]);
       }
+      mx = warp_max(mx);
+      if (lane == 0) sm.red[0][j][warp] = mx;
+    }
+    __syncthreads();
+    for (int j = 0; j < nrows_used; ++j) {
+      const float* lg = logits + (int64_t)(row0 + label_at(j)) * vocab;
+      float mx = sm.red[0][j][0];
+#pragma unroll
+      for (int i = 1; i < kPThreads / 32; ++i) mx = fmaxf(mx, sm.red[0][j][i]);
+      float s = 0.f;
+      for (int v0 = tid; v0 < vocab; v0 += 8 * kPThreads) {
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = (v0 + u * kPThreads < vocab) ? lg[v0 + u * kPThreads] : -INFINITY;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += expf(t[u] - mx);
+      }
+      s = warp_sum(s);
+      if (lane == 0) sm.red[1][j][warp] = s;
+      if (tid == 0) sm.lse_max[j] = mx;
+    }
+    __syncthreads();
+    if (tid < nrows_used) {
+      float s = 0.f;
+      for (int i = 0; i < kPThreads / 32; ++i) s += sm.red[1][tid][i];  // fixed order
+      sm.lse_log[tid] = logf(s);
     }
     __syncthreads();
     PCand loc[kPMaxBeam];
@@ -568,7 +594,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decoder_persistent_kernel(const 
       grid_barrier(p.bar, gen, p.trace, 6);
       // ---- LN2 on load + FF1 (GELU)
       ln = LnArgs{x_cur, x_alt, p.tmp, 1, nullptr, L.n2_g, L.n2_b};
-      gemm_phase<32, 64, 2, 4, 1, 1>(s_dyn, nullptr, 0, ln, L.l1_w, kPD, L.l1_b, p.ff, kPFF, R, kPFF);
+      gemm_phase<48, 64, 3, 4, 1, 1>(s_dyn, nullptr, 0, ln, L.l1_w, kPD, L.l1_b, p.ff, kPFF, R, kPFF);
       { float* t = x_cur; x_cur = x_alt; x_alt = t; }
       grid_barrier(p.bar, gen, p.trace, 7);
       // ---- FF2: 8 K-slices of raw partial sums (bias + residual + LN3 happen on the next load)
@@ -578,7 +604,7 @@ __global__ void __launch_bounds__(kPThreads, 1) decoder_persistent_kernel(const 
     {  // ---- LN3 of the last layer on load + classifier
       const PLayer& P = p.layers[kPLayers - 1];
       LnArgs ln{x_cur, x_alt, p.part, kPSplits, P.l2_b, P.n3_g, P.n3_b};
-      gemm_phase<64, 64, 4, 4, kPSplits, 0>(s_dyn, nullptr, 0, ln, p.cls_w, kPD, p.cls_b, p.logits, p.vocab, R, p.vocab);
+      gemm_phase<64, 96, 4, 6, kPSplits, 0>(s_dyn, nullptr, 0, ln, p.cls_w, kPD, p.cls_b, p.logits, p.vocab, R, p.vocab);
       grid_barrier(p.bar, gen, p.trace, 9);
     }
     // ---- beam step: one CTA per clip; it also writes the next step's embedding into x_cur (free: LN wrote x_alt)
@@ -673,14 +699,14 @@ int launch_decoder_step_fused(const PersistentArgs& p, int step, int cur, float*
     CNB_LAUNCH_OK();
     if (int rc = launch_phase_cfg<32, 32, 2, 2, 0, 0>(p.attn, kPD, ln, L.ca_out_w, kPD, L.ca_out_b, p.tmp, kPD, R, kPD, st)) return rc;
     ln = LnArgs{x_cur, x_alt, p.tmp, 1, nullptr, L.n2_g, L.n2_b};
-    if (int rc = launch_phase_cfg<32, 64, 2, 4, 1, 1>(nullptr, 0, ln, L.l1_w, kPD, L.l1_b, p.ff, kPFF, R, kPFF, st)) return rc;
+    if (int rc = launch_phase_cfg<48, 64, 3, 4, 1, 1>(nullptr, 0, ln, L.l1_w, kPD, L.l1_b, p.ff, kPFF, R, kPFF, st)) return rc;
     std::swap(x_cur, x_alt);
     if (int rc = launch_phase_cfg<64, 64, 4, 4, 0, 2>(p.ff, kPFF, ln, L.l2_w, kPFF, nullptr, p.part, kPD, R, kPD, st)) return rc;
   }
   {
     const PLayer& P = p.layers[kPLayers - 1];
     LnArgs ln{x_cur, x_alt, p.part, kPSplits, P.l2_b, P.n3_g, P.n3_b};
-    if (int rc = launch_phase_cfg<64, 64, 4, 4, kPSplits, 0>(nullptr, 0, ln, p.cls_w, kPD, p.cls_b, p.logits, p.vocab, R, p.vocab, st))
+    if (int rc = launch_phase_cfg<64, 96, 4, 6, kPSplits, 0>(nullptr, 0, ln, p.cls_w, kPD, p.cls_b, p.logits, p.vocab, R, p.vocab, st))
       return rc;
   }
   beam_embed_kernel<<<p.batch, kPThreads, 0, st>>>(p.logits, p.forbid, p.bs, step, cur, p.min_len, p.beam, p.max_len, p.vocab,
@@ -729,7 +755,7 @@ int launch_decoder_init(const PersistentArgs& p, cudaStream_t st) {
 
 int launch_decoder_persistent(const PersistentArgs& args, cudaStream_t stream) {
   static int max_blocks_per_sm = -1;
-  const size_t smem = (size_t)(64 + 64) * kPanelLds * sizeof(float);
+  const size_t smem = (size_t)(64 + 96) * kPanelLds * sizeof(float);
   if (max_blocks_per_sm < 0) {
     CNB_CUDA_OK(cudaFuncSetAttribute(decoder_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CNB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, decoder_persistent_kernel, kPThreads, smem));
