@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--beam", type=int, default=3)
     ap.add_argument("--precision", default="fast", choices=["fast", "parity"])
     ap.add_argument("--enc-chunk", type=int, default=0)
-    ap.add_argument("--decoder", default="graph", choices=["graph", "graph_unfused", "persistent", "eager"])
+    ap.add_argument("--decoder", default="graph", choices=["graph", "graph_pdl", "graph_unfused", "persistent", "eager"])
     ap.add_argument("--cpu-sample", type=int, default=8, help="clips in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -212,6 +212,8 @@ def run_ours(args, rank, world, local_rank):
     from conette_audio_captioning_b200 import synth
     from conette_audio_captioning_b200.engine import Engine
 
+    if os.environ.get("NCCL_DEBUG", "VERSION") == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout and would precede the JSON line
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:

@@ -859,6 +859,7 @@ int cnb_create(const cnb_config* cfg, cnb_handle** out) {
   h->use_graphs = (cfg->reserved[0] & 1) == 0;      // reserved[0] bit 0: disable CUDA graphs (debugging)
   h->use_persistent = (cfg->reserved[0] & 2) == 0;  // reserved[0] bit 1: disable the persistent decoder kernel
   h->use_fused = (cfg->reserved[0] & 4) == 0;       // reserved[0] bit 2: graph mode replays the unfused per-op kernels
+  decoder_set_pdl((cfg->reserved[0] & 8) == 0);     // reserved[0] bit 3: no programmatic dependent launch
   *out = h;
   return 0;
 }

@@ -87,7 +87,12 @@ struct LnArgs {
   const float* b;
 };
 
-template <int BM, int BN, int TM, int TN, int LN_MODE, int EPI>
+// PDL = launched with programmatic stream serialization: the weight panel (independent of the previous kernel) is requested
+// first, then griddepcontrol.wait orders everything that reads or writes activations after the predecessor's completion.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <int BM, int BN, int TM, int TN, int LN_MODE, int EPI, bool PDL = false>
 __device__ __forceinline__ void gemm_tile(float* s_panel, const float* a, int64_t lda, const LnArgs& ln, const float* W, int K,
                                           int k_begin, const float* bias, float* out, int64_t ldo, int M, int N, int m0,
                                           int n0) {
@@ -104,6 +109,7 @@ __device__ __forceinline__ void gemm_tile(float* s_panel, const float* a, int64_
     const bool ok = n0 + r < N;
     cp_async16_cg(&Bs[r][kq], ok ? W + (int64_t)(n0 + r) * K + k_begin + kq : W, ok);
   }
+  if (PDL) pdl_wait();
   if (LN_MODE == 0) {
     for (int i = tid; i < BM * 64; i += kPThreads) {
       const int r = i >> 6, kq = (i & 63) * 4;
@@ -212,7 +218,7 @@ __device__ __forceinline__ void gemm_tile(float* s_panel, const float* a, int64_
   __syncthreads();  // the panel is reused by the next tile / phase
 }
 
-template <int BM, int BN, int TM, int TN, int LN_MODE, int EPI>
+template <int BM, int BN, int TM, int TN, int LN_MODE, int EPI, bool PDL = false>
 __device__ __forceinline__ void gemm_phase(float* s_panel, const float* a, int64_t lda, const LnArgs& ln, const float* W, int K,
                                            const float* bias, float* out, int64_t ldo, int M, int N) {
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
@@ -222,8 +228,8 @@ __device__ __forceinline__ void gemm_phase(float* s_panel, const float* a, int64
     const int z = t / (tiles_m * tiles_n);
     const int rem = t - z * tiles_m * tiles_n;
     const int tm = rem / tiles_n, tn = rem - tm * tiles_n;
-    gemm_tile<BM, BN, TM, TN, LN_MODE, EPI>(s_panel, a, lda, ln, W, K, z * 256, bias, out + (int64_t)z * M * ldo, ldo, M, N,
-                                            tm * BM, tn * BN);
+    gemm_tile<BM, BN, TM, TN, LN_MODE, EPI, PDL>(s_panel, a, lda, ln, W, K, z * 256, bias, out + (int64_t)z * M * ldo, ldo, M,
+                                                 N, tm * BM, tn * BN);
   }
 }
 
@@ -626,12 +632,15 @@ __global__ void __launch_bounds__(kPThreads)
 gemm_phase_kernel(const float* a, int64_t lda, LnArgs ln, const float* W, int K, const float* bias, float* out, int64_t ldo,
                   int M, int N) {
   extern __shared__ __align__(16) float s_dyn[];
-  gemm_phase<BM, BN, TM, TN, LN_MODE, EPI>(s_dyn, a, lda, ln, W, K, bias, out, ldo, M, N);
+  pdl_launch_dependents();  // the next phase may start its prologue (weight panel loads) while this one drains
+  gemm_phase<BM, BN, TM, TN, LN_MODE, EPI, true>(s_dyn, a, lda, ln, W, K, bias, out, ldo, M, N);
 }
 
 __global__ void __launch_bounds__(kPThreads)
 self_attn_phase_kernel(const float* qkv, float* kcache, float* vcache, const int* src_row, int pos, int max_len, float* attn,
                        int rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   self_attn_phase(qkv, kcache, vcache, src_row, pos, max_len, attn, rows);
 }
 
@@ -639,6 +648,8 @@ __global__ void __launch_bounds__(kPThreads)
 cross_attn_phase_kernel(const float* q, const float* ck, const float* cv, int64_t kv_stride, const int* lens, int beam, int tp,
                         float* attn, int rows) {
   extern __shared__ __align__(16) float s_dyn[];
+  pdl_launch_dependents();
+  pdl_wait();
   cross_attn_phase(s_dyn, q, ck, cv, kv_stride, lens, beam, tp, attn, rows);
 }
 
@@ -646,8 +657,29 @@ __global__ void __launch_bounds__(kPThreads)
 beam_embed_kernel(float* logits, const uint8_t* forbid, BeamState st, int step, int cur, int min_len, int beam, int max_len,
                   int vocab, const float* emb, const float* pe, float* x_next) {
   __shared__ BeamSmem sm;
+  pdl_launch_dependents();
+  pdl_wait();
   if (st.done[0]) return;
   beam_clip(sm, logits, forbid, st, step, cur, min_len, beam, max_len, vocab, blockIdx.x, emb, pe, x_next);
+}
+
+static bool g_use_pdl = true;
+void decoder_set_pdl(bool on) { g_use_pdl = on; }
+
+// launch with the programmatic-stream-serialization attribute (PDL); also valid inside stream capture
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
 template <int BM, int BN, int TM, int TN, int LN_MODE, int EPI>
@@ -661,8 +693,8 @@ static int launch_phase_cfg(const float* a, int64_t lda, const LnArgs& ln, const
     attr_set = true;
   }
   const int n_tiles = (int)(ceil_div(M, BM) * ceil_div(N, BN)) * (EPI == 2 ? K / 256 : 1);
-  kern<<<n_tiles, kPThreads, smem, stream>>>(a, lda, ln, W, K, bias, out, ldo, M, N);
-  CNB_LAUNCH_OK();
+  CNB_CUDA_OK(launch_pdl(kern, dim3(n_tiles), dim3(kPThreads), smem, stream, a, lda, ln, W, K, bias, out, ldo, M, N));
+  count_launch();
   return 0;
 }
 
@@ -687,16 +719,17 @@ int launch_decoder_step_fused(const PersistentArgs& p, int step, int cur, float*
       if (int rc = launch_phase_cfg<32, 32, 2, 2, kPSplits, 0>(nullptr, 0, ln, L.sa_in_w, kPD, L.sa_in_b, p.qkv, 768, R, 768, st)) return rc;
       std::swap(x_cur, x_alt);
     }
-    self_attn_phase_kernel<<<attn_blocks, kPThreads, 0, st>>>(p.qkv, p.kc + l * cache_l, p.vc + l * cache_l, src_row, step,
-                                                             p.max_len, p.attn, R);
-    CNB_LAUNCH_OK();
+    CNB_CUDA_OK(launch_pdl(self_attn_phase_kernel, dim3(attn_blocks), dim3(kPThreads), 0, st, (const float*)p.qkv,
+                           p.kc + l * cache_l, p.vc + l * cache_l, src_row, step, p.max_len, p.attn, R));
+    count_launch();
     if (int rc = launch_phase_cfg<32, 32, 2, 2, 0, 0>(p.attn, kPD, ln, L.sa_out_w, kPD, L.sa_out_b, p.tmp, kPD, R, kPD, st)) return rc;
     ln = LnArgs{x_cur, x_alt, p.tmp, 1, nullptr, L.n1_g, L.n1_b};
     if (int rc = launch_phase_cfg<32, 32, 2, 2, 1, 0>(nullptr, 0, ln, L.ca_q_w, kPD, L.ca_q_b, p.qkv, kPD, R, kPD, st)) return rc;
     std::swap(x_cur, x_alt);
-    cross_attn_phase_kernel<<<attn_blocks, kPThreads, (size_t)8 * p.tp * sizeof(float), st>>>(
-        p.qkv, p.ckv + (int64_t)l * 2 * kPD, p.ckv + (int64_t)l * 2 * kPD + kPD, kv_stride, p.lens, p.beam, p.tp, p.attn, R);
-    CNB_LAUNCH_OK();
+    CNB_CUDA_OK(launch_pdl(cross_attn_phase_kernel, dim3(attn_blocks), dim3(kPThreads), (size_t)8 * p.tp * sizeof(float), st,
+                           (const float*)p.qkv, p.ckv + (int64_t)l * 2 * kPD, p.ckv + (int64_t)l * 2 * kPD + kPD, kv_stride,
+                           p.lens, p.beam, p.tp, p.attn, R));
+    count_launch();
     if (int rc = launch_phase_cfg<32, 32, 2, 2, 0, 0>(p.attn, kPD, ln, L.ca_out_w, kPD, L.ca_out_b, p.tmp, kPD, R, kPD, st)) return rc;
     ln = LnArgs{x_cur, x_alt, p.tmp, 1, nullptr, L.n2_g, L.n2_b};
     if (int rc = launch_phase_cfg<48, 64, 3, 4, 1, 1>(nullptr, 0, ln, L.l1_w, kPD, L.l1_b, p.ff, kPFF, R, kPFF, st)) return rc;
@@ -709,9 +742,9 @@ int launch_decoder_step_fused(const PersistentArgs& p, int step, int cur, float*
     if (int rc = launch_phase_cfg<64, 96, 4, 6, kPSplits, 0>(nullptr, 0, ln, p.cls_w, kPD, p.cls_b, p.logits, p.vocab, R, p.vocab, st))
       return rc;
   }
-  beam_embed_kernel<<<p.batch, kPThreads, 0, st>>>(p.logits, p.forbid, p.bs, step, cur, p.min_len, p.beam, p.max_len, p.vocab,
-                                                   p.emb, p.pe, x_cur);
-  CNB_LAUNCH_OK();
+  CNB_CUDA_OK(launch_pdl(beam_embed_kernel, dim3(p.batch), dim3(kPThreads), 0, st, p.logits, p.forbid, p.bs, step, cur,
+                         p.min_len, p.beam, p.max_len, p.vocab, p.emb, p.pe, x_cur));
+  count_launch();
   *x_cur_io = x_cur;
   *x_alt_io = x_alt;
   return 0;

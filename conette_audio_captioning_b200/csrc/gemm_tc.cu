@@ -96,8 +96,8 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* v) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled shared-memory matrix descriptor (SM100 UMMA): start>>4 | LBO | SBO=1024B | version=1 | SW128
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
@@ -133,8 +133,8 @@ __device__ __forceinline__ float2 gelu_tanh_fit2(float2 x) {
 
 // v: kEpiChunk consecutive accumulator columns of output row m; sb / ss: bias / layer-scale for those columns (smem)
 template <int EPI, typename OutT>
-__device__ __forceinline__ void epilogue_chunk(float* v, int64_t m, int n0, const float* sb, const float* ss,
-                                               const EpiParams& ep, OutT* out, int64_t ldo) {
+__device__ __forceinline__ void epilogue_chunk(float* v, const float4* resid, int64_t m, int n0, const float* sb,
+                                               const float* ss, OutT* out, int64_t ldo) {
   float2* v2 = reinterpret_cast<float2*>(v);
   const float2* sb2 = reinterpret_cast<const float2*>(sb);
 #pragma unroll
@@ -148,11 +148,10 @@ __device__ __forceinline__ void epilogue_chunk(float* v, int64_t m, int n0, cons
     for (int j = 0; j < kEpiChunk; ++j) v[j] = fmaxf(v[j], 0.f);
   }
   if (EPI == EPI_SCALE_RESID) {
-    const float* r = ep.resid + m * ldo + n0;
     const float2* ss2 = reinterpret_cast<const float2*>(ss);
 #pragma unroll
     for (int j = 0; j < kEpiChunk; j += 4) {
-      const float4 x = *reinterpret_cast<const float4*>(r + j);
+      const float4 x = resid[j / 4];
       v2[j / 2] = __ffma2_rn(ss2[j / 2], v2[j / 2], make_float2(x.x, x.y));
       v2[j / 2 + 1] = __ffma2_rn(ss2[j / 2 + 1], v2[j / 2 + 1], make_float2(x.z, x.w));
     }
@@ -297,16 +296,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_wait(tfull_bar(as), aph);
       tcgen05_fence_after();
       const int64_t m = (int64_t)m_blk * kBlockM + lane_grp * 32 + lane;
-#pragma unroll 1
-      for (int c0 = kEpiChunk * sub; c0 < BLOCK_N; c0 += kEpiChunk * (kEpiWarps / 4)) {
-        float v[kEpiChunk];
-        const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(as * BLOCK_N + c0);
-        tmem_ld_32x16(taddr, v);
-        const int n0 = n_blk * BLOCK_N + c0;
-        if (m < M) epilogue_chunk<EPI, OutT>(v, m, n0, s_bias + n0, s_scale + n0, ep, out, ldo);
+      // every TMEM chunk of this warp is requested before the first use (all loads in flight together) and the accumulator
+      // stage is handed back to the MMA warp as soon as the data sits in registers -- the bias/GELU/residual/store work then
+      // overlaps the next tile's MMAs.
+      constexpr int NCH = (BLOCK_N / kEpiChunk + kEpiWarps / 4 - 1) / (kEpiWarps / 4);
+      float v[NCH][kEpiChunk];
+      float4 rs[2][kEpiChunk / 4];  // residual rows (pw2 epilogue): chunk i+1 is fetched while chunk i is finished
+      auto load_resid = [&](int i) {
+        const int c0 = kEpiChunk * (sub + i * (kEpiWarps / 4));
+        if (EPI == EPI_SCALE_RESID && c0 < BLOCK_N && m < M) {
+          const float* r = ep.resid + m * ldo + n_blk * BLOCK_N + c0;
+#pragma unroll
+          for (int j = 0; j < kEpiChunk / 4; ++j) rs[i & 1][j] = *reinterpret_cast<const float4*>(r + 4 * j);
+        }
+      };
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c0 = kEpiChunk * (sub + i * (kEpiWarps / 4));
+        if (c0 < BLOCK_N)
+          tmem_ld_32x16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(as * BLOCK_N + c0), v[i]);
       }
+      load_resid(0);
+      tmem_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(tempty_bar(as));
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c0 = kEpiChunk * (sub + i * (kEpiWarps / 4));
+        const int n0 = n_blk * BLOCK_N + c0;
+        if (i + 1 < NCH) load_resid(i + 1);
+        if (c0 < BLOCK_N && m < M)
+          epilogue_chunk<EPI, OutT>(v[i], rs[i & 1], m, n0, s_bias + n0, s_scale + n0, out, ldo);
+      }
       as ^= 1;
       if (as == 0) aph ^= 1;
     }

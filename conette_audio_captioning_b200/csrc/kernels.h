@@ -125,6 +125,7 @@ struct PersistentArgs {
 };
 int launch_decoder_persistent(const PersistentArgs& args, cudaStream_t stream);
 // the same phases as separate launches (graph-replayed "fused" mode)
+void decoder_set_pdl(bool on);  // programmatic dependent launch between the fused phase kernels (default on)
 int launch_decoder_init(const PersistentArgs& args, cudaStream_t stream);
 int launch_decoder_step_fused(const PersistentArgs& args, int step, int cur, float** x_cur_io, float** x_alt_io,
                               cudaStream_t stream);

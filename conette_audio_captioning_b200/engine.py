@@ -41,9 +41,10 @@ class Engine:
         cfg.vocab_size = self.vocab_size
         cfg.precision = {"fast": _lib.PRECISION_FAST, "parity": _lib.PRECISION_PARITY}[precision]
         cfg.enc_chunk = enc_chunk
-        # decoder execution mode: CUDA-graph replay of the per-op kernels (default: fastest so far, 12 ms / 20 steps at
-        # R=192), one persistent cooperative kernel with software grid barriers (14 ms), or eager launches
-        cfg.reserved[0] = {"persistent": 0, "graph": 2, "graph_unfused": 6, "eager": 3}[decoder]
+        # decoder execution mode (all bit-identical): "graph" = CUDA-graph replay of the fused phase kernels (default, fastest:
+        # ~10 ms / 20 steps at R=192), "graph_pdl" = same with programmatic dependent launch (measured slower), "graph_unfused"
+        # = per-op kernels, "persistent" = one cooperative kernel with software grid barriers, "eager" = plain launches
+        cfg.reserved[0] = {"persistent": 0, "graph": 10, "graph_pdl": 2, "graph_unfused": 14, "eager": 3}[decoder]
         handle = C.c_void_p()
         _lib.check(self.lib.cnb_create(C.byref(cfg), C.byref(handle)))
         self.handle = handle

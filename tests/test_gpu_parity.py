@@ -292,7 +292,7 @@ def test_decoder_execution_modes_agree_bitwise(small_sd):
     bos_ids = small_sd["model.task_id_to_token_id"][torch.randint(0, 7, (b,), generator=g)]
     forbid = small_sd["model.forbid_rep_mask"]
     outs = {}
-    for mode in ("persistent", "graph", "graph_unfused", "eager"):
+    for mode in ("persistent", "graph", "graph_pdl", "graph_unfused", "eager"):
         eng = Engine(small_sd, vocab_size=forbid.shape[0], precision="parity", decoder=mode)
         try:
             outs[mode] = [o.cpu() for o in eng.decode(fe, lens, bos_ids, forbid, 3, 3, 20)]
@@ -300,7 +300,7 @@ def test_decoder_execution_modes_agree_bitwise(small_sd):
             assert all(torch.equal(a, c) for a, c in zip(outs[mode], again)), mode
         finally:
             eng.close()
-    for mode in ("graph", "graph_unfused", "eager"):
+    for mode in ("graph", "graph_pdl", "graph_unfused", "eager"):
         for a, c in zip(outs["persistent"], outs[mode]):
             assert torch.equal(a, c), mode
 
