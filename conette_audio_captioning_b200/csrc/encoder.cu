@@ -3,6 +3,8 @@
 // fp32, GEMM operands are OutT (bf16 in fast mode, f32 in parity mode).
 // Reference: nn/encoders/convnext.py:61-74 (block), :207-217 (stem / downsample), :306-334 (mean + head),
 // nn/modules/norm.py:35-40 (channels_first LayerNorm, biased variance, eps 1e-6).
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -14,53 +16,62 @@ constexpr float kLnEps = 1e-6f;
 // K-STEM: one CTA per output row (b, h): 56 pixels x 96 channels; 8 warps x 7 pixels, lane owns channels l, l+32, l+64
 // =====================================================================================================================
 constexpr int kStemThreads = 256;
+constexpr int kStemRows = 4;  // output rows per CTA (amortises the prologue; weights live in registers)
 
 __global__ void __launch_bounds__(kStemThreads)
 stem_kernel(const float* __restrict__ lm, int n_frames, int h1, const float* __restrict__ w_t, const float* __restrict__ bias,
             const float* __restrict__ ln_g, const float* __restrict__ ln_b, float* __restrict__ out) {
-  __shared__ float s_in[4][224];
-  __shared__ float s_w[16][96];
+  __shared__ __align__(16) float s_in[kStemRows * 4][224];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.y, h = blockIdx.x;
-  for (int i = tid; i < 16 * 96; i += kStemThreads) s_w[i / 96][i % 96] = w_t[i];
-  for (int i = tid; i < 4 * 224; i += kStemThreads) {
+  const int b = blockIdx.y, h0 = blockIdx.x * kStemRows;
+  for (int i = tid; i < kStemRows * 4 * 224; i += kStemThreads) {
     const int r = i / 224, col = i - r * 224;
-    const int t = 4 * h - 4 + r;  // Conv2d padding (4, 0): 4 zero frames before/after in time
+    const int t = 4 * h0 - 4 + r;  // Conv2d padding (4, 0): 4 zero frames before/after in time
     s_in[r][col] = (t >= 0 && t < n_frames) ? lm[((int64_t)b * n_frames + t) * 224 + col] : 0.f;
   }
-  __syncthreads();
-  float bia[3], g[3], be[3];
+  float w[16][3], bia[3], g[3], be[3];
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    bia[j] = bias[lane + 32 * j];
-    g[j] = ln_g[lane + 32 * j];
-    be[j] = ln_b[lane + 32 * j];
+    const int c = lane + 32 * j;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) w[k][j] = w_t[k * 96 + c];
+    bia[j] = bias[c];
+    g[j] = ln_g[c];
+    be[j] = ln_b[c];
   }
-  for (int p = 0; p < 7; ++p) {
-    const int w = warp * 7 + p;
-    float acc[3] = {bia[0], bia[1], bia[2]};
+  __syncthreads();
+  // 8 warps x 7 pixels = one output row of 56 pixels; kStemRows rows per CTA
+  for (int rr = 0; rr < kStemRows; ++rr) {
+    const int h = h0 + rr;
+    if (h >= h1) break;
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int p = 0; p < 7; ++p) {
+      const int wpx = warp * 7 + p;
+      float acc[3] = {bia[0], bia[1], bia[2]};
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float v = s_in[r][4 * w + c];
+      for (int r = 0; r < 4; ++r) {
+        const float4 v = *reinterpret_cast<const float4*>(&s_in[rr * 4 + r][4 * wpx]);
+        const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int j = 0; j < 3; ++j) acc[j] = fmaf(v, s_w[r * 4 + c][lane + 32 * j], acc[j]);
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) acc[j] = fmaf(vv[c], w[r * 4 + c][j], acc[j]);
       }
-    const float mean = warp_sum(acc[0] + acc[1] + acc[2]) * (1.f / 96.f);
-    const float d0 = acc[0] - mean, d1 = acc[1] - mean, d2 = acc[2] - mean;
-    const float var = warp_sum(d0 * d0 + d1 * d1 + d2 * d2) * (1.f / 96.f);
-    const float rstd = 1.f / sqrtf(var + kLnEps);
-    float* o = out + (((int64_t)b * h1 + h) * 56 + w) * 96;
-    o[lane] = d0 * rstd * g[0] + be[0];
-    o[lane + 32] = d1 * rstd * g[1] + be[1];
-    o[lane + 64] = d2 * rstd * g[2] + be[2];
+      const float mean = warp_sum(acc[0] + acc[1] + acc[2]) * (1.f / 96.f);
+      const float d0 = acc[0] - mean, d1 = acc[1] - mean, d2 = acc[2] - mean;
+      const float var = warp_sum(d0 * d0 + d1 * d1 + d2 * d2) * (1.f / 96.f);
+      const float rstd = 1.f / sqrtf(var + kLnEps);
+      float* o = out + (((int64_t)b * h1 + h) * 56 + wpx) * 96;
+      o[lane] = d0 * rstd * g[0] + be[0];
+      o[lane + 32] = d1 * rstd * g[1] + be[1];
+      o[lane + 64] = d2 * rstd * g[2] + be[2];
+    }
   }
 }
 
 int launch_stem(const float* lm, int batch, int n_frames, int h1, const float* w_t, const float* bias, const float* ln_g,
                 const float* ln_b, float* out, cudaStream_t stream) {
-  dim3 grid(h1, batch);
+  dim3 grid((unsigned)ceil_div(h1, kStemRows), batch);
   stem_kernel<<<grid, kStemThreads, 0, stream>>>(lm, n_frames, h1, w_t, bias, ln_g, ln_b, out);
   CNB_LAUNCH_OK();
   return 0;
@@ -407,33 +418,70 @@ template int launch_dwconv_ln<__nv_bfloat16>(const float*, int, int, int, int, c
 //   out[(b, h', w'), (kh, kw, c)] = LN(x[b, 2h'+kh, 2w'+kw, :])[c]   (odd trailing row/col dropped: floor)
 //   one warp per input pixel.
 // =====================================================================================================================
-template <typename OutT>
+template <int C, typename OutT>
 __global__ void __launch_bounds__(256)
-ln_pack2x2_kernel(const float* __restrict__ x, int batch, int H, int W, int C, const float* __restrict__ ln_g,
+ln_pack2x2_kernel(const float* __restrict__ x, int batch, int H, int W, const float* __restrict__ ln_g,
                   const float* __restrict__ ln_b, OutT* __restrict__ out) {
+  // one warp per input pixel; a lane owns float4 groups lane, lane+32, ... of the C channels (kept in registers)
+  constexpr int NV = (C / 4 + 31) / 32;
   const int lane = threadIdx.x & 31;
   const int Ho = H / 2, Wo = W / 2;
   const int64_t n_pix = (int64_t)batch * Ho * 2 * Wo * 2;
   const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float4 g[NV], be[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int q = lane + 32 * i;
+    g[i] = be[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < C / 4) {
+      g[i] = *reinterpret_cast<const float4*>(ln_g + 4 * q);
+      be[i] = *reinterpret_cast<const float4*>(ln_b + 4 * q);
+    }
+  }
   for (int64_t pix = warp_id; pix < n_pix; pix += n_warps) {
-    // enumerate only the pixels that are used: (b, h < 2*Ho, w < 2*Wo)
+    // enumerate only the pixels that are used: (b, h < 2*Ho, w < 2*Wo); odd trailing row / column dropped (floor)
     const int wq = (int)(pix % (2 * Wo));
     const int hq = (int)((pix / (2 * Wo)) % (2 * Ho));
     const int b = (int)(pix / ((int64_t)2 * Wo * 2 * Ho));
     const float* px = x + (((int64_t)b * H + hq) * W + wq) * C;
+    float4 v[NV];
     float s = 0.f;
-    for (int c = lane; c < C; c += 32) s += px[c];
-    const float mean = warp_sum(s) / C;
-    float q = 0.f;
-    for (int c = lane; c < C; c += 32) {
-      const float d = px[c] - mean;
-      q += d * d;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int q = lane + 32 * i;
+      v[i] = (q < C / 4) ? *reinterpret_cast<const float4*>(px + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
-    const float rstd = 1.f / sqrtf(warp_sum(q) / C + kLnEps);
+    const float mean = warp_sum(s) * (1.f / C);
+    float qq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + 32 * i < C / 4) {
+        const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
+        qq += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+      }
+    }
+    const float rstd = 1.f / sqrtf(warp_sum(qq) * (1.f / C) + kLnEps);
     const int64_t row = ((int64_t)b * Ho + hq / 2) * Wo + wq / 2;
     OutT* o = out + row * (4 * (int64_t)C) + ((hq & 1) * 2 + (wq & 1)) * C;
-    for (int c = lane; c < C; c += 32) o[c] = from_float<OutT>((px[c] - mean) * rstd * ln_g[c] + ln_b[c]);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int q = lane + 32 * i;
+      if (q < C / 4) {
+        const float y0 = (v[i].x - mean) * rstd * g[i].x + be[i].x, y1 = (v[i].y - mean) * rstd * g[i].y + be[i].y;
+        const float y2 = (v[i].z - mean) * rstd * g[i].z + be[i].z, y3 = (v[i].w - mean) * rstd * g[i].w + be[i].w;
+        if constexpr (sizeof(OutT) == 2) {
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(y0, y1), p1 = __floats2bfloat162_rn(y2, y3);
+          uint2 u;
+          u.x = *reinterpret_cast<uint32_t*>(&p0);
+          u.y = *reinterpret_cast<uint32_t*>(&p1);
+          *reinterpret_cast<uint2*>(o + 4 * q) = u;
+        } else {
+          *reinterpret_cast<float4*>(o + 4 * q) = make_float4(y0, y1, y2, y3);
+        }
+      }
+    }
   }
 }
 
@@ -442,7 +490,13 @@ int launch_ln_pack2x2(const float* x, int batch, int h, int w, int c, const floa
                       cudaStream_t stream) {
   const int64_t n_pix = (int64_t)batch * (h / 2) * 2 * (w / 2) * 2;
   const int blocks = (int)std::min<int64_t>(ceil_div(n_pix, 8), (int64_t)kNumSMs * 16);
-  ln_pack2x2_kernel<OutT><<<blocks, 256, 0, stream>>>(x, batch, h, w, c, ln_g, ln_b, out);
+  if (c == 96) ln_pack2x2_kernel<96, OutT><<<blocks, 256, 0, stream>>>(x, batch, h, w, ln_g, ln_b, out);
+  else if (c == 192) ln_pack2x2_kernel<192, OutT><<<blocks, 256, 0, stream>>>(x, batch, h, w, ln_g, ln_b, out);
+  else if (c == 384) ln_pack2x2_kernel<384, OutT><<<blocks, 256, 0, stream>>>(x, batch, h, w, ln_g, ln_b, out);
+  else {
+    set_error("ln_pack2x2: unsupported channel count " + std::to_string(c));
+    return -1;
+  }
   CNB_LAUNCH_OK();
   return 0;
 }
