@@ -14,7 +14,10 @@ DTYPE_F32, DTYPE_I64, DTYPE_BOOL, DTYPE_U8 = 0, 1, 2, 3
 TAP_LOGMEL_BN, TAP_STEM, TAP_BLOCK, TAP_DOWN, TAP_DWLN = 0, 1, 2, 3, 4
 
 KERNEL_CLASSES = ("frontend", "stem", "dwconv_ln", "gemm_pw1_gelu", "gemm_pw2_resid", "ds_ln_pack", "ds_gemm", "head",
-                  "proj_crosskv", "dec_gemm", "dec_attn_ln", "dec_classifier", "beam")
+                  "proj_crosskv", "dec_gemm", "dec_attn_ln", "dec_classifier", "beam",
+                  "dwconv_ln.s1", "dwconv_ln.s2", "dwconv_ln.s3", "dwconv_ln.s4",
+                  "gemm_pw1_gelu.s1", "gemm_pw1_gelu.s2", "gemm_pw1_gelu.s3", "gemm_pw1_gelu.s4",
+                  "gemm_pw2_resid.s1", "gemm_pw2_resid.s2", "gemm_pw2_resid.s3", "gemm_pw2_resid.s4")
 
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libconette_b200.so"
 

@@ -469,17 +469,17 @@ static int encode_chunk(cnb_handle* h, const float* wav, int nb, int64_t n, floa
     const int m = nb * hh * ww;
     for (int j = 0; j < kDepths[s]; ++j, ++bi) {
       const BlockW& b = h->blocks[bi];
-      { Prof _p(h, CNB_K_DWLN, st); if (int rc = launch_dwconv_ln<ActT>(x, nb, hh, ww, c, b.dw_w_t, b.dw_b, b.ln_g, b.ln_b, y, st)) return rc; }
+      { Prof _p(h, CNB_K_DWLN_S0 + s, st); if (int rc = launch_dwconv_ln<ActT>(x, nb, hh, ww, c, b.dw_w_t, b.dw_b, b.ln_g, b.ln_b, y, st)) return rc; }
       if (tap && tap->kind == CNB_TAP_DWLN && tap->stage == s && tap->block == j)
         return copy_tap(tap, y, (int64_t)m * c, sizeof(ActT) == 2, st);
       EpiParams e1;
       e1.bias = b.b1;
-      { Prof _p(h, CNB_K_GEMM_PW1, st); if (int rc = mlp_gemm<ActT>(h, y, b.w1, b.w1_bf, m, 4 * c, c, EPI_BIAS_GELU, e1, hid, true, 4 * c, st)) return rc; }
+      { Prof _p(h, CNB_K_GEMM_PW1_S0 + s, st); if (int rc = mlp_gemm<ActT>(h, y, b.w1, b.w1_bf, m, 4 * c, c, EPI_BIAS_GELU, e1, hid, true, 4 * c, st)) return rc; }
       EpiParams e2;
       e2.bias = b.b2;
       e2.scale = b.scale;
       e2.resid = x;
-      { Prof _p(h, CNB_K_GEMM_PW2, st); if (int rc = mlp_gemm<ActT>(h, hid, b.w2, b.w2_bf, m, c, 4 * c, EPI_SCALE_RESID, e2, x, false, c, st)) return rc; }
+      { Prof _p(h, CNB_K_GEMM_PW2_S0 + s, st); if (int rc = mlp_gemm<ActT>(h, hid, b.w2, b.w2_bf, m, c, 4 * c, EPI_SCALE_RESID, e2, x, false, c, st)) return rc; }
       if (tap && tap->kind == CNB_TAP_BLOCK && tap->stage == s && tap->block == j)
         return copy_tap(tap, x, (int64_t)m * c, false, st);
     }

@@ -110,11 +110,14 @@ int cnb_debug_gemm(cnb_handle* h, const float* a, const float* w, const float* b
 
 /* Per-kernel-class device timing: between cnb_profile_begin and cnb_profile_end every launch group issued through this
  * handle is bracketed by a CUDA event pair on the launching stream; _end synchronises and returns, per class, the summed
- * event time in ms and the number of brackets. Arrays must hold CNB_K_COUNT entries. */
+ * event time in ms and the number of brackets. Arrays must hold CNB_K_COUNT entries.  The block kernels are reported
+ * per ConvNeXt stage (CNB_K_*_S0 + stage); the aggregate classes CNB_K_DWLN / GEMM_PW1 / GEMM_PW2 stay zero. */
 enum {
   CNB_K_FRONTEND = 0, CNB_K_STEM = 1, CNB_K_DWLN = 2, CNB_K_GEMM_PW1 = 3, CNB_K_GEMM_PW2 = 4, CNB_K_DS_PACK = 5,
   CNB_K_DS_GEMM = 6, CNB_K_HEAD = 7, CNB_K_PROJ_KV = 8, CNB_K_DEC_GEMM = 9, CNB_K_DEC_ATTN = 10, CNB_K_DEC_CLS = 11,
-  CNB_K_BEAM = 12, CNB_K_COUNT = 13
+  CNB_K_BEAM = 12,
+  /* stage-resolved classes of the three ConvNeXt block kernels: base + stage (0..3) */
+  CNB_K_DWLN_S0 = 13, CNB_K_GEMM_PW1_S0 = 17, CNB_K_GEMM_PW2_S0 = 21, CNB_K_COUNT = 25
 };
 int cnb_profile_begin(cnb_handle* h);
 int cnb_profile_end(cnb_handle* h, float* ms_per_class, int64_t* brackets_per_class, int32_t n_classes);

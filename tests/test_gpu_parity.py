@@ -373,3 +373,48 @@ def test_input_forms_and_errors(small_sd):
     with pytest.raises(ValueError):
         model(mono, sr=16000, x_shapes=torch.tensor([[n]]))
     model.engine.close()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# BASELINE.json full size (configs[1]: 64 x 10 s, beam 3, V = 4018): size-independent properties
+# ----------------------------------------------------------------------------------------------------------------------
+def test_full_size_properties():
+    """At the benchmark size the oracle is too slow to run; check what does not depend on it:
+    determinism (two runs bit-identical), clip independence (a clip's caption does not depend on its batch neighbours or
+    on the encoder chunking), finite scores, output shapes / trimming rule, and that beam 0 of mult_preds is the best beam."""
+    from conette_audio_captioning_b200.engine import Engine
+
+    sd = synth.make_state_dict(seed=1234, n_words=4000)
+    vocab = sd["model.decoder.classifier.weight"].shape[0]
+    eng = Engine(sd, vocab, precision="fast")
+    try:
+        b, n = 64, 320000
+        wav = synth.make_audio(b, n, seed=1234)[:, 0].contiguous().cuda()
+        bos = sd["model.task_id_to_token_id"][torch.zeros(b, dtype=torch.long)]
+        forbid = sd["model.forbid_rep_mask"]
+        out1 = [o.cpu() for o in eng.caption(wav, None, bos, forbid, 3, 3, 20)]
+        out2 = [o.cpu() for o in eng.caption(wav, None, bos, forbid, 3, 3, 20)]
+        for a, c in zip(out1, out2):
+            assert torch.equal(a, c)
+        preds, lprobs, mult_preds, mult_lprobs, clip = out1
+        assert preds.shape[0] == b and mult_preds.shape[:2] == (b, 3) and mult_lprobs.shape == (b, 3) and clip.shape == (b, 527)
+        assert preds.shape[1] <= mult_preds.shape[2] <= 20
+        assert torch.isfinite(lprobs).all() and torch.isfinite(mult_lprobs).all() and (lprobs <= 0).all()
+        best = mult_lprobs.argmax(1)
+        assert torch.equal(lprobs, mult_lprobs[torch.arange(b), best])
+        assert torch.equal(preds, mult_preds[torch.arange(b), best][:, : preds.shape[1]])
+        assert int(preds.max()) < vocab and int(preds.min()) >= 0
+        # clip independence: sub-batches of 1 and 5 clips reproduce the same ids and scores bit-for-bit
+        for lo, hi in ((0, 1), (59, 64)):
+            sub = [o.cpu() for o in eng.caption(wav[lo:hi], None, bos[lo:hi], forbid, 3, 3, 20, trim=False)]
+            L = mult_preds.shape[2]
+            assert torch.equal(sub[2][:, :, :L], mult_preds[lo:hi])
+            assert torch.equal(sub[3], mult_lprobs[lo:hi])
+    finally:
+        eng.close()
+
+
+def test_graft_entry_smoke():
+    import __graft_entry__
+
+    __graft_entry__.smoke()
