@@ -159,18 +159,26 @@ beam_step_kernel(float* __restrict__ logits, const uint8_t* __restrict__ forbid,
 #pragma unroll
     for (int i = 0; i < kMaxBeam; ++i)
       if (i == j) prev = prev_sum[i];
-    for (int v = tid; v < vocab; v += kBeamThreads) {
-      const float lsm = (lg[v] - mx) - lg_sum;
-      const Cand c{step == 0 ? lsm : prev + lsm, j * vocab + v};
-      if (better(c, loc[kMaxBeam - 1])) {
-        loc[kMaxBeam - 1] = c;
+    for (int v0 = tid; v0 < vocab; v0 += 8 * kBeamThreads) {
+      float t[8];
 #pragma unroll
-        for (int i = kMaxBeam - 1; i > 0; --i)
-          if (better(loc[i], loc[i - 1])) {
-            const Cand t = loc[i];
-            loc[i] = loc[i - 1];
-            loc[i - 1] = t;
-          }
+      for (int u = 0; u < 8; ++u) t[u] = (v0 + u * kBeamThreads < vocab) ? lg[v0 + u * kBeamThreads] : -INFINITY;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int v = v0 + u * kBeamThreads;
+        if (v >= vocab) break;
+        const float lsm = (t[u] - mx) - lg_sum;
+        const Cand c{step == 0 ? lsm : prev + lsm, j * vocab + v};
+        if (better(c, loc[kMaxBeam - 1])) {
+          loc[kMaxBeam - 1] = c;
+#pragma unroll
+          for (int i = kMaxBeam - 1; i > 0; --i)
+            if (better(loc[i], loc[i - 1])) {
+              const Cand tt = loc[i];
+              loc[i] = loc[i - 1];
+              loc[i - 1] = tt;
+            }
+        }
       }
     }
   }

@@ -4,6 +4,7 @@
 // Reference: nn/decoders/aac_tfmer.py:100-116 (embedding * sqrt(d) + PE, then torch nn.TransformerDecoder with
 // post-norm layers, eps 1e-5, 8 heads x 32, no final norm); the reference recomputes all i+1 positions and re-projects
 // the memory for every beam at every step -- here K/V are cached.
+#include "attention.cuh"
 #include "common.cuh"
 #include "kernels.h"
 
@@ -21,43 +22,16 @@ __global__ void embed_kernel(const int* __restrict__ tokens, int tok_stride, int
   x[(int64_t)r * kD + c] = emb[(int64_t)tok * kD + c] * 16.0f + pe[(int64_t)pos * kD + c];
 }
 
-// ---- self-attention: one warp per (row, head), lane = head-dim element -----------------------------------------------
-// kcache/vcache: (R, max_len, 256) for this layer; src_row[r][p] = physical row that holds position p of row r's history.
+// ---- self-attention / cross-attention: one warp per (row, head); arithmetic in attention.cuh -----------------------------
 __global__ void __launch_bounds__(256)
-self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ kcache, float* __restrict__ vcache,
-                 const int* __restrict__ src_row, int pos, int max_len, const int* __restrict__ done,
-                 float* __restrict__ attn, int rows) {
+self_attn_kernel(const float* __restrict__ qkv, float* kcache, float* vcache, const int* __restrict__ src_row, int pos,
+                 int max_len, const int* __restrict__ done, float* __restrict__ attn, int rows) {
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (gw >= rows * kHeads) return;
-  const int r = gw / kHeads, h = gw - r * kHeads;
-  const int col = h * kHeadDim + lane;
-  const float q = qkv[(int64_t)r * 768 + col];
-  kcache[((int64_t)r * max_len + pos) * kD + col] = qkv[(int64_t)r * 768 + 256 + col];
-  vcache[((int64_t)r * max_len + pos) * kD + col] = qkv[(int64_t)r * 768 + 512 + col];
-  __syncwarp();
-  const float scale = 0.17677669529663687f;  // 1/sqrt(32)
-  float sc[2] = {-INFINITY, -INFINITY};      // lane holds the scores of positions lane and lane+32
-  for (int p = 0; p <= pos; ++p) {
-    const int pr = (p == pos) ? r : src_row[(int64_t)r * max_len + p];
-    const float s = warp_sum(q * kcache[((int64_t)pr * max_len + p) * kD + col]) * scale;
-    if ((p & 31) == lane) sc[p >> 5] = s;
-  }
-  const float mx = warp_max(fmaxf(sc[0], sc[1]));
-  const float e0 = (sc[0] == -INFINITY) ? 0.f : expf(sc[0] - mx);
-  const float e1 = (sc[1] == -INFINITY) ? 0.f : expf(sc[1] - mx);
-  const float inv = 1.f / warp_sum(e0 + e1);
-  float acc = 0.f;
-  for (int p = 0; p <= pos; ++p) {
-    const int pr = (p == pos) ? r : src_row[(int64_t)r * max_len + p];
-    const float w = __shfl_sync(0xffffffffu, (p >> 5) ? e1 : e0, p & 31) * inv;
-    acc = fmaf(w, vcache[((int64_t)pr * max_len + p) * kD + col], acc);
-  }
-  attn[(int64_t)r * kD + col] = acc;
+  self_attention_task<false>(qkv, kcache, vcache, src_row, pos, max_len, attn, gw / kHeads, gw % kHeads, lane);
 }
 
-// ---- cross-attention: one warp per (row, head); scores staged in shared memory ----------------------------------------
-// ck/cv: rows of the clip's frames with row stride `kv_stride` floats (the 6 layers' K|V are produced by one GEMM).
 __global__ void __launch_bounds__(256)
 cross_attn_kernel(const float* __restrict__ q, const float* __restrict__ ck, const float* __restrict__ cv, int64_t kv_stride,
                   const int* __restrict__ lens, int beam, int tp, const int* __restrict__ done, float* __restrict__ attn,
@@ -66,48 +40,9 @@ cross_attn_kernel(const float* __restrict__ q, const float* __restrict__ ck, con
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (gw >= rows * kHeads) return;
-  const int r = gw / kHeads, h = gw - r * kHeads;
+  const int r = gw / kHeads, h = gw % kHeads;
   const int clip = r / beam;
-  const int len = lens[clip];
-  float* sc = s_sc + wib * tp;
-  const float* qh = q + (int64_t)r * kD + h * kHeadDim;
-  float qv[kHeadDim];
-#pragma unroll
-  for (int d = 0; d < kHeadDim; d += 4) {
-    const float4 t = *reinterpret_cast<const float4*>(qh + d);
-    qv[d] = t.x; qv[d + 1] = t.y; qv[d + 2] = t.z; qv[d + 3] = t.w;
-  }
-  const float scale = 0.17677669529663687f;
-  float mx = -INFINITY;
-  for (int t = lane; t < tp; t += 32) {
-    float s = -INFINITY;
-    if (t < len) {  // key_padding_mask: frames t >= len are masked (reference conette.py:460-462)
-      const float* kr = ck + ((int64_t)clip * tp + t) * kv_stride + h * kHeadDim;
-      float a = 0.f;
-#pragma unroll
-      for (int d = 0; d < kHeadDim; d += 4) {
-        const float4 kk = *reinterpret_cast<const float4*>(kr + d);
-        a = fmaf(qv[d], kk.x, a); a = fmaf(qv[d + 1], kk.y, a); a = fmaf(qv[d + 2], kk.z, a); a = fmaf(qv[d + 3], kk.w, a);
-      }
-      s = a * scale;
-    }
-    sc[t] = s;
-    mx = fmaxf(mx, s);
-  }
-  mx = warp_max(mx);
-  float sum = 0.f;
-  for (int t = lane; t < tp; t += 32) {
-    const float e = (sc[t] == -INFINITY) ? 0.f : expf(sc[t] - mx);
-    sc[t] = e;
-    sum += e;
-  }
-  const float inv = 1.f / warp_sum(sum);
-  __syncwarp();
-  float acc = 0.f;
-  const int tmax = len < tp ? len : tp;
-  for (int t = 0; t < tmax; ++t)
-    acc = fmaf(sc[t], cv[((int64_t)clip * tp + t) * kv_stride + h * kHeadDim + lane], acc);
-  attn[(int64_t)r * kD + h * kHeadDim + lane] = acc * inv;
+  cross_attention_task<false>(s_sc + wib * tp, q, ck, cv, kv_stride, lens[clip], clip, tp, attn, r, h, lane);
 }
 
 // ---- x = LayerNorm(x + bias + sum_s delta[s]) (eps 1e-5, biased variance): one warp per row of 256 ---------------------

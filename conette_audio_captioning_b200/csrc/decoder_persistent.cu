@@ -17,6 +17,7 @@
 
 #include <utility>
 
+#include "attention.cuh"
 #include "common.cuh"
 #include "kernels.h"
 
@@ -240,81 +241,18 @@ __device__ __forceinline__ void self_attn_phase(const float* qkv, float* kcache,
                                                 int max_len, float* attn, int rows) {
   const int lane = threadIdx.x & 31;
   const int n_tasks = rows * kPHeads;
-  for (int gw = blockIdx.x * (kPThreads / 32) + (threadIdx.x >> 5); gw < n_tasks; gw += gridDim.x * (kPThreads / 32)) {
-    const int r = gw / kPHeads, h = gw - r * kPHeads;
-    const int col = h * kPHeadDim + lane;
-    const float q = __ldcg(&qkv[(int64_t)r * 768 + col]);
-    kcache[((int64_t)r * max_len + pos) * kPD + col] = __ldcg(&qkv[(int64_t)r * 768 + 256 + col]);
-    vcache[((int64_t)r * max_len + pos) * kPD + col] = __ldcg(&qkv[(int64_t)r * 768 + 512 + col]);
-    __syncwarp();
-    const float scale = 0.17677669529663687f;
-    float sc[2] = {-INFINITY, -INFINITY};
-    for (int p = 0; p <= pos; ++p) {
-      const int pr = (p == pos) ? r : src_row[(int64_t)r * max_len + p];
-      const float s = warp_sum(q * __ldcg(&kcache[((int64_t)pr * max_len + p) * kPD + col])) * scale;
-      if ((p & 31) == lane) sc[p >> 5] = s;
-    }
-    const float mx = warp_max(fmaxf(sc[0], sc[1]));
-    const float e0 = (sc[0] == -INFINITY) ? 0.f : expf(sc[0] - mx);
-    const float e1 = (sc[1] == -INFINITY) ? 0.f : expf(sc[1] - mx);
-    const float inv = 1.f / warp_sum(e0 + e1);
-    float acc = 0.f;
-    for (int p = 0; p <= pos; ++p) {
-      const int pr = (p == pos) ? r : src_row[(int64_t)r * max_len + p];
-      const float w = __shfl_sync(0xffffffffu, (p >> 5) ? e1 : e0, p & 31) * inv;
-      acc = fmaf(w, __ldcg(&vcache[((int64_t)pr * max_len + p) * kPD + col]), acc);
-    }
-    attn[(int64_t)r * kPD + col] = acc;
-  }
+  for (int gw = blockIdx.x * (kPThreads / 32) + (threadIdx.x >> 5); gw < n_tasks; gw += gridDim.x * (kPThreads / 32))
+    self_attention_task<true>(qkv, kcache, vcache, src_row, pos, max_len, attn, gw / kPHeads, gw % kPHeads, lane);
 }
 
 __device__ __forceinline__ void cross_attn_phase(float* s_scores, const float* q, const float* ck, const float* cv,
                                                  int64_t kv_stride, const int* lens, int beam, int tp, float* attn, int rows) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  float* sc = s_scores + wib * tp;
   const int n_tasks = rows * kPHeads;
   for (int gw = blockIdx.x * (kPThreads / 32) + wib; gw < n_tasks; gw += gridDim.x * (kPThreads / 32)) {
-    const int r = gw / kPHeads, h = gw - r * kPHeads;
+    const int r = gw / kPHeads, h = gw % kPHeads;
     const int clip = r / beam;
-    const int len = lens[clip];
-    const float* qh = q + (int64_t)r * kPD + h * kPHeadDim;
-    float qv[kPHeadDim];
-#pragma unroll
-    for (int d = 0; d < kPHeadDim; d += 4) {
-      const float4 t = __ldcg(reinterpret_cast<const float4*>(qh + d));
-      qv[d] = t.x; qv[d + 1] = t.y; qv[d + 2] = t.z; qv[d + 3] = t.w;
-    }
-    const float scale = 0.17677669529663687f;
-    float mx = -INFINITY;
-    for (int t = lane; t < tp; t += 32) {
-      float s = -INFINITY;
-      if (t < len) {
-        const float* kr = ck + ((int64_t)clip * tp + t) * kv_stride + h * kPHeadDim;
-        float a = 0.f;
-#pragma unroll
-        for (int d = 0; d < kPHeadDim; d += 4) {
-          const float4 kk = *reinterpret_cast<const float4*>(kr + d);
-          a = fmaf(qv[d], kk.x, a); a = fmaf(qv[d + 1], kk.y, a); a = fmaf(qv[d + 2], kk.z, a); a = fmaf(qv[d + 3], kk.w, a);
-        }
-        s = a * scale;
-      }
-      sc[t] = s;
-      mx = fmaxf(mx, s);
-    }
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int t = lane; t < tp; t += 32) {
-      const float e = (sc[t] == -INFINITY) ? 0.f : expf(sc[t] - mx);
-      sc[t] = e;
-      sum += e;
-    }
-    const float inv = 1.f / warp_sum(sum);
-    __syncwarp();
-    float acc = 0.f;
-    const int tmax = len < tp ? len : tp;
-    for (int t = 0; t < tmax; ++t) acc = fmaf(sc[t], cv[((int64_t)clip * tp + t) * kv_stride + h * kPHeadDim + lane], acc);
-    attn[(int64_t)r * kPD + h * kPHeadDim + lane] = acc * inv;
-    __syncwarp();
+    cross_attention_task<true>(s_scores + wib * tp, q, ck, cv, kv_stride, lens[clip], clip, tp, attn, r, h, lane);
   }
 }
 
@@ -433,18 +371,26 @@ __device__ void beam_clip(BeamSmem& sm, float* logits, const uint8_t* forbid, co
 #pragma unroll
       for (int i = 0; i < kPMaxBeam; ++i)
         if (i == j) prev = prev_sum[i];
-      for (int v = tid; v < vocab; v += kPThreads) {
-        const float lsm = (lg[v] - mx) - lg_sum;
-        const PCand c{step == 0 ? lsm : prev + lsm, j * vocab + v};
-        if (pbetter(c, loc[kPMaxBeam - 1])) {
-          loc[kPMaxBeam - 1] = c;
+      for (int v0 = tid; v0 < vocab; v0 += 8 * kPThreads) {
+        float t[8];
 #pragma unroll
-          for (int i = kPMaxBeam - 1; i > 0; --i)
-            if (pbetter(loc[i], loc[i - 1])) {
-              const PCand t = loc[i];
-              loc[i] = loc[i - 1];
-              loc[i - 1] = t;
-            }
+        for (int u = 0; u < 8; ++u) t[u] = (v0 + u * kPThreads < vocab) ? lg[v0 + u * kPThreads] : -INFINITY;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int v = v0 + u * kPThreads;
+          if (v >= vocab) break;
+          const float lsm = (t[u] - mx) - lg_sum;
+          const PCand c{step == 0 ? lsm : prev + lsm, j * vocab + v};
+          if (pbetter(c, loc[kPMaxBeam - 1])) {
+            loc[kPMaxBeam - 1] = c;
+#pragma unroll
+            for (int i = kPMaxBeam - 1; i > 0; --i)
+              if (pbetter(loc[i], loc[i - 1])) {
+                const PCand tt = loc[i];
+                loc[i] = loc[i - 1];
+                loc[i - 1] = tt;
+              }
+          }
         }
       }
     }
