@@ -55,6 +55,7 @@ struct DownW {
 struct LayerW {
   float *sa_in_w, *sa_in_b, *sa_out_w, *sa_out_b, *ca_q_w, *ca_q_b, *ca_out_w, *ca_out_b;
   float *l1_w, *l1_b, *l2_w, *l2_b, *n1_g, *n1_b, *n2_g, *n2_b, *n3_g, *n3_b;
+  float *sa_in_p, *sa_out_p, *ca_q_p, *ca_out_p, *l1_p, *l2_p;  // k4-packed copies (cluster decoder)
 };
 
 struct Buffer {
@@ -83,14 +84,16 @@ struct cnb_handle {
   DownW down[3];
   float *head_ln_g, *head_ln_b, *head_w, *head_b;
   // projection + decoder
-  float *proj_w, *proj_b, *emb, *pe, *ca_kv_w, *ca_kv_b, *cls_w, *cls_b;
+  float *proj_w, *proj_b, *emb, *pe, *ca_kv_w, *ca_kv_b, *cls_w, *cls_b, *cls_p;
+  int cls_vpad = 0;
   LayerW layers[6];
   // workspace (grown on demand)
   std::map<std::string, Buffer> ws;
   size_t ws_bytes = 0;
   int* zero_flag = nullptr;  // device int[4] that stays 0: "done" flag for non-beam callers
   // CUDA-graph replay of the decode loop
-  bool use_persistent = true;
+  bool use_persistent = false;
+  int use_cluster = 1;  // 0 never, 1 when the shape allows it (default), 2 required
   bool use_fused = true;
   bool use_graphs = true;
   cudaStream_t stream = nullptr;  // library-owned non-blocking stream (graph capture / replay, host-API copies)
@@ -213,6 +216,14 @@ static int put_bf16(cnb_handle* h, const std::vector<float>& v, __nv_bfloat16** 
 #define PUT_BF(dst, vec) \
   if (int _rc = put_bf16(h, vec, &(dst))) return _rc
 
+// k4 packing for the cluster decoder: W (n, k) row-major -> Wp[(k/4) * n_pad + col][4] = W[col][4*(k/4) .. +3], zero columns >= n
+static std::vector<float> pack_k4(const std::vector<float>& w, int n, int k, int n_pad) {
+  std::vector<float> out((size_t)(k / 4) * n_pad * 4, 0.f);
+  for (int c = 0; c < n; ++c)
+    for (int kk = 0; kk < k; ++kk) out[((size_t)(kk >> 2) * n_pad + c) * 4 + (kk & 3)] = w[(size_t)c * k + kk];
+  return out;
+}
+
 static int finalize(cnb_handle* h) {
   const std::string E = "preprocessor.encoder.", M = "model.", D = "model.decoder.";
   const int V = h->cfg.vocab_size;
@@ -221,7 +232,7 @@ static int finalize(cnb_handle* h) {
 
   size_t total = 0;
   for (auto& kv : h->staged) total += kv.second.data.size();
-  h->arena.cap = total * 6 + (64u << 20);  // f32 + bf16 copies + slack
+  h->arena.cap = total * 10 + (64u << 20);  // f32 + bf16 + k4-packed decoder copies + slack
   CNB_CUDA_OK(cudaMalloc(&h->arena.base, h->arena.cap));
   CNB_CUDA_OK(cudaMemset(h->arena.base, 0, h->arena.cap));
 
@@ -357,6 +368,8 @@ static int finalize(cnb_handle* h) {
     GET(cb, D + "classifier.bias", V);
     PUT(h->proj_w, pw->data); PUT(h->proj_b, pb->data); PUT(h->emb, emb->data); PUT(h->cls_w, cw->data);
     PUT(h->cls_b, cb->data);
+    h->cls_vpad = 8 * ((((V + 7) / 8) + 3) & ~3);  // 8 slices of a multiple of 4 columns
+    { const std::vector<float> t = pack_k4(cw->data, V, kD, h->cls_vpad); PUT(h->cls_p, t); }
     auto it = h->staged.find(D + "pos_encoding.pos_embedding");
     if (it == h->staged.end() || it->second.shape.size() != 3 || it->second.shape[2] != kD) {
       set_error("missing or malformed weight: " + D + "pos_encoding.pos_embedding");
@@ -386,6 +399,12 @@ static int finalize(cnb_handle* h) {
       std::copy(caw->data.begin() + (size_t)kD * kD, caw->data.end(), kvw.begin() + (size_t)l * 2 * kD * kD);
       std::copy(cab->data.begin() + kD, cab->data.end(), kvb.begin() + (size_t)l * 2 * kD);
       PUT(L.l1_w, l1w->data); PUT(L.l1_b, l1b->data); PUT(L.l2_w, l2w->data); PUT(L.l2_b, l2b->data);
+      { const std::vector<float> t = pack_k4(saw->data, 3 * kD, kD, 3 * kD); PUT(L.sa_in_p, t); }
+      { const std::vector<float> t = pack_k4(sow->data, kD, kD, kD); PUT(L.sa_out_p, t); }
+      { const std::vector<float> t = pack_k4(qw, kD, kD, kD); PUT(L.ca_q_p, t); }
+      { const std::vector<float> t = pack_k4(cow->data, kD, kD, kD); PUT(L.ca_out_p, t); }
+      { const std::vector<float> t = pack_k4(l1w->data, kFF, kD, kFF); PUT(L.l1_p, t); }
+      { const std::vector<float> t = pack_k4(l2w->data, kD, kFF, kD); PUT(L.l2_p, t); }
       float** gs[3] = {&L.n1_g, &L.n2_g, &L.n3_g};
       float** bs[3] = {&L.n1_b, &L.n2_b, &L.n3_b};
       for (int n = 0; n < 3; ++n) {
@@ -712,9 +731,10 @@ static int decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, c
   for (int l = 0; l < kLayers; ++l) {
     const LayerW& L = h->layers[l];
     pa.layers[l] = PLayer{L.sa_in_w, L.sa_in_b, L.sa_out_w, L.sa_out_b, L.ca_q_w, L.ca_q_b, L.ca_out_w, L.ca_out_b, L.l1_w,
-                          L.l1_b, L.l2_w, L.l2_b, L.n1_g, L.n1_b, L.n2_g, L.n2_b, L.n3_g, L.n3_b};
+                          L.l1_b, L.l2_w, L.l2_b, L.n1_g, L.n1_b, L.n2_g, L.n2_b, L.n3_g, L.n3_b,
+                          L.sa_in_p, L.sa_out_p, L.ca_q_p, L.ca_out_p, L.l1_p, L.l2_p};
   }
-  pa.emb = h->emb; pa.pe = h->pe; pa.cls_w = h->cls_w; pa.cls_b = h->cls_b;
+  pa.emb = h->emb; pa.pe = h->pe; pa.cls_w = h->cls_w; pa.cls_b = h->cls_b; pa.cls_p = h->cls_p; pa.vpad = h->cls_vpad;
   pa.ckv = w.ckv; pa.lens = lens; pa.bos_ids = bos_ids; pa.forbid = forbid;
   pa.xa = w.x; pa.xb = xb; pa.qkv = w.qkv; pa.attn = w.attn; pa.tmp = w.tmp; pa.ff = w.ff; pa.part = w.part;
   pa.logits = w.logits; pa.kc = w.kc; pa.vc = w.vc; pa.bs = bs; pa.bar = bar;
@@ -722,6 +742,38 @@ static int decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, c
   pa.batch = batch;
   pa.trace = nullptr;
 
+  if (h->use_cluster == 2 || (h->use_cluster == 1 && decoder_cluster_supported(pa))) {
+    // one cluster of 8 CTAs per group of clips decodes start to finish (decoder_cluster.cu): 2 GEMMs + 1 kernel + 2 gathers
+    if (int rc = dec_project(h, frame_embs, batch, tp, w, st)) return rc;
+    const bool trace_on = getenv("CNB_DEC_TRACE") != nullptr;
+    if (trace_on) {
+      WS(h, "dtrace_cl", unsigned long long, 32, tr);
+      CNB_CUDA_OK(cudaMemsetAsync(tr, 0, 32 * sizeof(unsigned long long), st));
+      pa.trace = tr;
+    }
+    {
+      Prof _p(h, CNB_K_DEC_GEMM, st);
+      if (int rc = launch_decoder_cluster(pa, st)) return rc;
+    }
+    if (trace_on) {  // debug: time between phase marks as seen by thread 0 of the first CTA, summed over steps and layers
+      unsigned long long t[20];
+      CNB_CUDA_OK(cudaStreamSynchronize(st));
+      CNB_CUDA_OK(cudaMemcpy(t, pa.trace, sizeof(t), cudaMemcpyDeviceToHost));
+      static const char* names[] = {"qkv gemm", "self attn", "bcast+sync1", "sa_out gemm", "bcast+sync2", "ln1", "ca_q gemm",
+                                    "cross attn", "bcast+sync3", "ca_out gemm", "bcast+sync4", "ln2+ff1 gemm", "ff2 gemm",
+                                    "scatter+sync5", "reduce+bcast+sync6+ln3", "cls gemm", "beam A", "bcast+sync7", "beam B",
+                                    "-"};
+      double tot = 0;
+      for (int i = 0; i < 19; ++i) tot += (double)t[i];
+      for (int i = 0; i < 19; ++i)
+        fprintf(stderr, "[dec cluster trace] %-24s %9.1f us  (%4.1f %%)\n", names[i], (double)t[i] / 1e3, 100.0 * t[i] / tot);
+    }
+    if (int rc = launch_beam_finalize(bs, preds, lprobs, best_len, dd, st)) return rc;
+    gather_mult_kernel<<<(rows * max_len + 255) / 256, 256, 0, st>>>(bs, mult_preds, mult_lprobs, best_len, info, rows, max_len,
+                                                                    batch);
+    CNB_LAUNCH_OK();
+    return 0;
+  }
   if (!h->prof_on && h->use_persistent) {
     // one cooperative launch for the whole decode loop
     if (int rc = dec_project(h, frame_embs, batch, tp, w, st)) return rc;
@@ -856,10 +908,20 @@ int cnb_create(const cnb_config* cfg, cnb_handle** out) {
   CNB_CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CNB_CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CNB_CUDA_OK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-  h->use_graphs = (cfg->reserved[0] & 1) == 0;      // reserved[0] bit 0: disable CUDA graphs (debugging)
-  h->use_persistent = (cfg->reserved[0] & 2) == 0;  // reserved[0] bit 1: disable the persistent decoder kernel
-  h->use_fused = (cfg->reserved[0] & 4) == 0;       // reserved[0] bit 2: graph mode replays the unfused per-op kernels
-  decoder_set_pdl((cfg->reserved[0] & 8) == 0);     // reserved[0] bit 3: no programmatic dependent launch
+  // reserved[0] = decoder execution mode: 0 default (cluster kernel when the shape allows it, else the fused graph), 1 fused
+  // CUDA graph, 2 fused graph + programmatic dependent launch, 3 unfused graph, 4 eager launches, 5 cooperative persistent
+  // kernel, 6 cluster kernel (error if the shape does not fit)
+  const int dmode = cfg->reserved[0];
+  if (dmode < 0 || dmode > 6) {
+    set_error("cnb_create: reserved[0] (decoder mode) must be 0..6");
+    delete h;
+    return -1;
+  }
+  h->use_cluster = dmode == 0 ? 1 : (dmode == 6 ? 2 : 0);
+  h->use_graphs = dmode != 4;
+  h->use_persistent = dmode == 5;
+  h->use_fused = dmode != 3;
+  decoder_set_pdl(dmode == 2);
   *out = h;
   return 0;
 }

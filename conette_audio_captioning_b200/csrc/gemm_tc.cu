@@ -21,7 +21,6 @@ namespace cnb {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 bytes = one swizzle-128B atom row
 constexpr int kUmmaK = 16;
-constexpr int kStages = 4;
 constexpr int kEpiWarps = 16;                      // four warps per TMEM lane quarter, interleaved 16-column chunks
 constexpr int kEpiChunk = 16;                      // accumulator columns per tcgen05.ld
 constexpr int kMaxN = 3072;                        // bias / layer-scale vectors are staged in shared memory
@@ -115,7 +114,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// epilogue math on 32 consecutive columns of one output row
+// epilogue math on 16 consecutive accumulator columns of one output row
 // ---------------------------------------------------------------------------------------------------------------------
 // erf-GELU through one MUFU.TANH per element: coefficients fitted so that max |approx - 0.5x(1+erf(x/sqrt2))| = 2.5e-5
 // over [-8, 8]; evaluated two elements at a time with the packed fp32 pipe (fma.rn.f32x2 / mul.rn.f32x2).
@@ -131,83 +130,86 @@ __device__ __forceinline__ float2 gelu_tanh_fit2(float2 x) {
   return __ffma2_rn(hx, t, hx);
 }
 
-// v: kEpiChunk consecutive accumulator columns of output row m; sb / ss: bias / layer-scale for those columns (smem)
-template <int EPI, typename OutT>
-__device__ __forceinline__ void epilogue_chunk(float* v, const float4* resid, int64_t m, int n0, const float* sb,
-                                               const float* ss, OutT* out, int64_t ldo) {
-  float2* v2 = reinterpret_cast<float2*>(v);
-  const float2* sb2 = reinterpret_cast<const float2*>(sb);
-#pragma unroll
-  for (int j = 0; j < kEpiChunk / 2; ++j) v2[j] = __fadd2_rn(v2[j], sb2[j]);
-  if (EPI == EPI_BIAS_GELU) {
-#pragma unroll
-    for (int j = 0; j < kEpiChunk / 2; ++j) v2[j] = gelu_tanh_fit2(v2[j]);
-  }
-  if (EPI == EPI_BIAS_RELU) {
-#pragma unroll
-    for (int j = 0; j < kEpiChunk; ++j) v[j] = fmaxf(v[j], 0.f);
-  }
-  if (EPI == EPI_SCALE_RESID) {
-    const float2* ss2 = reinterpret_cast<const float2*>(ss);
-#pragma unroll
-    for (int j = 0; j < kEpiChunk; j += 4) {
-      const float4 x = resid[j / 4];
-      v2[j / 2] = __ffma2_rn(ss2[j / 2], v2[j / 2], make_float2(x.x, x.y));
-      v2[j / 2 + 1] = __ffma2_rn(ss2[j / 2 + 1], v2[j / 2 + 1], make_float2(x.z, x.w));
-    }
-  }
-  OutT* o = out + m * ldo + n0;
-  if constexpr (sizeof(OutT) == 2) {
-#pragma unroll
-    for (int j = 0; j < kEpiChunk; j += 8) {
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-      __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-      uint4 u;
-      u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-      u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
-      *reinterpret_cast<uint4*>(o + j) = u;
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < kEpiChunk; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-  }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(x), "r"(y),
+               "r"(src)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(32 * kEpiWarps) : "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------------------------------
-template <int BLOCK_N>
-struct TcSmem {
+// Output path: the epilogue never touches global memory with per-thread row accesses (one thread = one output row would
+// make every warp-level store hit 32 different cache lines -- measured: the kernel time scaled with the output bytes at
+// ~1.8 TB/s).  Instead 64-column passes are written into 128B-swizzled staging tiles in shared memory and leave through
+// TMA bulk tensor stores; the layer-scale/residual epilogue TMA-loads the fp32 residual tile into the same staging tiles
+// at tile start and updates it in place.
+template <int BLOCK_N, int EPI, typename OutT>
+struct TcCfg {
+  static constexpr bool kResid = (EPI == EPI_SCALE_RESID);
+  static constexpr int kElt = (int)sizeof(OutT);
+  static constexpr int kBoxCols = 128 / kElt;                 // 64 bf16 / 32 fp32 per 128-byte swizzle row
+  static constexpr int kBoxBytes = kBlockM * 128;             // 16 KB
+  static constexpr int kBoxesPerPass = 64 / kBoxCols;         // 1 / 2
+  static constexpr int kPassBytes = kBoxesPerPass * kBoxBytes;
+  static constexpr int kPasses = (BLOCK_N + 63) / 64;
+  static constexpr int kStagingBufs = kResid ? kPasses : 2;   // residual tiles are staged whole, plain outputs ping-pong
+  static constexpr int kVecFloats = kResid ? 2 * 768 : kMaxN; // bias (| scale) staged in smem
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kVecOff = kStages * kStageBytes + 256;  // bias | scale staging after the barrier block
-  static constexpr int kTotal = kVecOff + 2 * kMaxN * 4 + 1024 /*align*/;
+  static constexpr int kFixed = kStagingBufs * kPassBytes + kVecFloats * 4 + 512 /*barriers*/ + 1024 /*align*/;
+  static constexpr int kStagesFit = (232448 - kFixed) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 4 ? 4 : kStagesFit;
+  static_assert(kStages >= 2, "shared memory budget");
+  static constexpr int kStagingOff = kStages * kStageBytes;
+  static constexpr int kBarOff = kStagingOff + kStagingBufs * kPassBytes;
+  static constexpr int kVecOff = kBarOff + 512;
+  static constexpr int kTotal = kVecOff + kVecFloats * 4 + 1024;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
 };
 
 template <int BLOCK_N, int EPI, typename OutT>
 __global__ void __launch_bounds__(kTcThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int M, int N, int K,
-               EpiParams ep, OutT* __restrict__ out, int64_t ldo) {
-  using S = TcSmem<BLOCK_N>;
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+               const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_resid, int M, int N, int K,
+               EpiParams ep) {
+  using C = TcCfg<BLOCK_N, EPI, OutT>;
+  constexpr int kStages = C::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024-byte alignment
-  const uint32_t bars = base + kStages * S::kStageBytes;
+  uint8_t* smem_aligned = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t stg = base + C::kStagingOff;
+  const uint32_t bars = base + C::kBarOff;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * kStages + s); };
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages + 2 + s); };
-  const uint32_t tmem_slot = bars + 8u * (2 * kStages + 4);
-  uint8_t* smem_aligned = smem_raw + (base - smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_aligned + kStages * S::kStageBytes +
-                                                                         8 * (2 * kStages + 4));
+  const uint32_t resid_bar = bars + 8u * (2 * kStages + 4);
+  const uint32_t tmem_slot = bars + 8u * (2 * kStages + 5);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_aligned + C::kBarOff + 8 * (2 * kStages + 5));
 
-  float* s_bias = reinterpret_cast<float*>(smem_aligned + S::kVecOff);
-  float* s_scale = s_bias + kMaxN;
+  float* s_bias = reinterpret_cast<float*>(smem_aligned + C::kVecOff);
+  float* s_scale = s_bias + 768;  // only used by the residual epilogue (N <= 768)
   for (int i = threadIdx.x; i < N; i += kTcThreads) {
     s_bias[i] = ep.bias[i];
-    if (EPI == EPI_SCALE_RESID) s_scale[i] = ep.scale[i];
+    if (C::kResid) s_scale[i] = ep.scale[i];
   }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -225,11 +227,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 32 * kEpiWarps);
     }
+    mbar_init(resid_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(S::kTmemCols)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -247,9 +250,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int m_blk = t / tiles_n, n_blk = t - m_blk * tiles_n;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1);
-          const uint32_t a_dst = base + s * S::kStageBytes;
-          const uint32_t b_dst = a_dst + S::kABytes;
-          mbar_expect_tx(full_bar(s), S::kStageBytes);
+          const uint32_t a_dst = base + s * C::kStageBytes;
+          const uint32_t b_dst = a_dst + C::kABytes;
+          mbar_expect_tx(full_bar(s), C::kStageBytes);
           tma_load_2d(a_dst, &map_a, kb * kBlockK, m_blk * kBlockM, full_bar(s));
           tma_load_2d(b_dst, &map_w, kb * kBlockK, n_blk * BLOCK_N, full_bar(s));
           if (++s == kStages) { s = 0; ph ^= 1; }
@@ -269,9 +272,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(full_bar(s), ph);
           tcgen05_fence_after();
-          const uint32_t a_addr = base + s * S::kStageBytes;
+          const uint32_t a_addr = base + s * C::kStageBytes;
           const uint64_t adesc = make_smem_desc(a_addr);
-          const uint64_t bdesc = make_smem_desc(a_addr + S::kABytes);
+          const uint64_t bdesc = make_smem_desc(a_addr + C::kABytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in (addr >> 4) units
@@ -288,56 +291,128 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else {
     // ===================== epilogue (warps 2..17) =====================
     const int lane_grp = warp & 3;            // TMEM lanes [32*lane_grp, +32) are accessible to this warp
-    const int sub = (warp - 2) >> 2;          // the four warps of a lane quarter interleave 16-column chunks
+    const int sub = (warp - 2) >> 2;          // the four warps of a lane quarter split every 64-column pass 4 x 16
+    const bool leader = (warp == 2 && lane == 0);
+    const int row = lane_grp * 32 + lane;     // row of the tile owned by this thread
     int as = 0;
-    uint32_t aph = 0;
+    uint32_t aph = 0, rph = 0;
+    uint32_t pass_ctr = 0;                    // running pass counter: plain outputs ping-pong the two staging tiles
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int m_blk = t / tiles_n, n_blk = t - m_blk * tiles_n;
+      if (C::kResid && leader) {
+        // previous tile's stores must have finished reading the staging tiles; then fetch this tile's residual rows
+        bulk_wait_read<0>();
+        int n_boxes = 0;
+#pragma unroll
+        for (int i = 0; i < C::kPasses; ++i)
+#pragma unroll
+          for (int bx = 0; bx < C::kBoxesPerPass; ++bx)
+            if (64 * i + bx * C::kBoxCols < BLOCK_N) ++n_boxes;
+        mbar_expect_tx(resid_bar, (uint32_t)n_boxes * C::kBoxBytes);
+#pragma unroll
+        for (int i = 0; i < C::kPasses; ++i)
+#pragma unroll
+          for (int bx = 0; bx < C::kBoxesPerPass; ++bx) {
+            const int c = 64 * i + bx * C::kBoxCols;
+            if (c < BLOCK_N)
+              tma_load_2d(stg + i * C::kPassBytes + bx * C::kBoxBytes, &map_resid, n_blk * BLOCK_N + c, m_blk * kBlockM,
+                          resid_bar);
+          }
+      }
       mbar_wait(tfull_bar(as), aph);
       tcgen05_fence_after();
-      const int64_t m = (int64_t)m_blk * kBlockM + lane_grp * 32 + lane;
-      // every TMEM chunk of this warp is requested before the first use (all loads in flight together) and the accumulator
-      // stage is handed back to the MMA warp as soon as the data sits in registers -- the bias/GELU/residual/store work then
-      // overlaps the next tile's MMAs.
-      constexpr int NCH = (BLOCK_N / kEpiChunk + kEpiWarps / 4 - 1) / (kEpiWarps / 4);
-      float v[NCH][kEpiChunk];
-      float4 rs[2][kEpiChunk / 4];  // residual rows (pw2 epilogue): chunk i+1 is fetched while chunk i is finished
-      auto load_resid = [&](int i) {
-        const int c0 = kEpiChunk * (sub + i * (kEpiWarps / 4));
-        if (EPI == EPI_SCALE_RESID && c0 < BLOCK_N && m < M) {
-          const float* r = ep.resid + m * ldo + n_blk * BLOCK_N + c0;
+      // every TMEM chunk of this warp is requested before the first use and the accumulator stage is handed back to the MMA
+      // warp as soon as the data sits in registers: the epilogue math / staging / stores overlap the next tile's MMAs
+      float v[C::kPasses][kEpiChunk];
 #pragma unroll
-          for (int j = 0; j < kEpiChunk / 4; ++j) rs[i & 1][j] = *reinterpret_cast<const float4*>(r + 4 * j);
-        }
-      };
-#pragma unroll
-      for (int i = 0; i < NCH; ++i) {
-        const int c0 = kEpiChunk * (sub + i * (kEpiWarps / 4));
+      for (int i = 0; i < C::kPasses; ++i) {
+        const int c0 = 64 * i + kEpiChunk * sub;
         if (c0 < BLOCK_N)
           tmem_ld_32x16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(as * BLOCK_N + c0), v[i]);
       }
-      load_resid(0);
       tmem_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(tempty_bar(as));
+      if (C::kResid) {
+        mbar_wait(resid_bar, rph);
+        rph ^= 1;
+      }
 #pragma unroll
-      for (int i = 0; i < NCH; ++i) {
-        const int c0 = kEpiChunk * (sub + i * (kEpiWarps / 4));
-        const int n0 = n_blk * BLOCK_N + c0;
-        if (i + 1 < NCH) load_resid(i + 1);
-        if (c0 < BLOCK_N && m < M)
-          epilogue_chunk<EPI, OutT>(v[i], rs[i & 1], m, n0, s_bias + n0, s_scale + n0, out, ldo);
+      for (int i = 0; i < C::kPasses; ++i) {
+        const int c0 = 64 * i + kEpiChunk * sub;           // first column (inside the tile) of this thread's chunk
+        const uint32_t buf = C::kResid ? (uint32_t)i : (pass_ctr & 1u);
+        const uint32_t tile_smem = stg + buf * C::kPassBytes;
+        if (!C::kResid) {
+          if (leader) bulk_wait_read<1>();                 // the store that last used this staging tile has drained it
+          epi_bar(1);
+        }
+        if (c0 < BLOCK_N) {
+          const int n0 = n_blk * BLOCK_N + c0;
+          float2* v2 = reinterpret_cast<float2*>(v[i]);
+          const float2* sb2 = reinterpret_cast<const float2*>(s_bias + n0);
+#pragma unroll
+          for (int j = 0; j < kEpiChunk / 2; ++j) v2[j] = __fadd2_rn(v2[j], sb2[j]);
+          if (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+            for (int j = 0; j < kEpiChunk / 2; ++j) v2[j] = gelu_tanh_fit2(v2[j]);
+          }
+          if (EPI == EPI_BIAS_RELU) {
+#pragma unroll
+            for (int j = 0; j < kEpiChunk; ++j) v[i][j] = fmaxf(v[i][j], 0.f);
+          }
+          // 16 columns of row `row` inside the pass: byte offset of the first one, then 16-byte chunks XOR (row & 7)
+          const int col_byte = (kEpiChunk * sub) * C::kElt;   // 0, 32, 64, 96 (bf16)  |  0, 64, 128, 192 (fp32)
+          const uint32_t box_base = tile_smem + (uint32_t)(col_byte / 128) * C::kBoxBytes + (uint32_t)row * 128u;
+          const int chunk0 = (col_byte % 128) / 16;
+          if constexpr (C::kElt == 2) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[i][8 * q + 0], v[i][8 * q + 1]);
+              __nv_bfloat162 p1 = __floats2bfloat162_rn(v[i][8 * q + 2], v[i][8 * q + 3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[i][8 * q + 4], v[i][8 * q + 5]);
+              __nv_bfloat162 p3 = __floats2bfloat162_rn(v[i][8 * q + 6], v[i][8 * q + 7]);
+              st_shared_v4(box_base + (uint32_t)(((chunk0 + q) ^ (row & 7)) << 4), *reinterpret_cast<uint32_t*>(&p0),
+                           *reinterpret_cast<uint32_t*>(&p1), *reinterpret_cast<uint32_t*>(&p2),
+                           *reinterpret_cast<uint32_t*>(&p3));
+            }
+          } else {
+            const float2* ss2 = reinterpret_cast<const float2*>(s_scale + n0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t addr = box_base + (uint32_t)(((chunk0 + q) ^ (row & 7)) << 4);
+              if (C::kResid) {
+                const float4 x = ld_shared_v4(addr);
+                v2[2 * q] = __ffma2_rn(ss2[2 * q], v2[2 * q], make_float2(x.x, x.y));
+                v2[2 * q + 1] = __ffma2_rn(ss2[2 * q + 1], v2[2 * q + 1], make_float2(x.z, x.w));
+              }
+              st_shared_v4(addr, __float_as_uint(v[i][4 * q]), __float_as_uint(v[i][4 * q + 1]),
+                           __float_as_uint(v[i][4 * q + 2]), __float_as_uint(v[i][4 * q + 3]));
+            }
+          }
+        }
+        fence_async_smem();   // generic-proxy writes -> visible to the TMA store
+        epi_bar(2);
+        if (leader) {
+#pragma unroll
+          for (int bx = 0; bx < C::kBoxesPerPass; ++bx) {
+            const int c = 64 * i + bx * C::kBoxCols;
+            if (c < BLOCK_N) tma_store_2d(&map_out, tile_smem + bx * C::kBoxBytes, n_blk * BLOCK_N + c, m_blk * kBlockM);
+          }
+          bulk_commit();
+        }
+        ++pass_ctr;
       }
       as ^= 1;
       if (as == 0) aph ^= 1;
     }
+    if (leader) bulk_wait_all();
   }
 
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(S::kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::kTmemCols) : "memory");
   }
 }
 
@@ -362,15 +437,15 @@ int gemm_tc_init() {
   return 0;
 }
 
-// 2-D bf16 row-major (rows, cols) tensor, box = (box_rows, 64 cols), 128B swizzle, zero OOB fill
-static int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// 2-D row-major (rows, cols) tensor of 2- or 4-byte elements, box = (box_rows, 128 bytes of columns), 128B swizzle, zero OOB fill
+static int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, int elt_bytes) {
   const cuuint64_t dims[2] = {cols, rows};
-  const cuuint64_t strides[1] = {cols * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+  const cuuint64_t strides[1] = {cols * (uint64_t)elt_bytes};
+  const cuuint32_t box[2] = {(cuuint32_t)(128 / elt_bytes), box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = g_encode(map, elt_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                        const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
     return -3;
@@ -380,31 +455,35 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t c
 
 template <int BLOCK_N, int EPI, typename OutT>
 static int launch_cfg(const __nv_bfloat16* a, const __nv_bfloat16* w, int m, int n, int k, const EpiParams& ep, OutT* out,
-                      int64_t ldo, cudaStream_t stream) {
-  using S = TcSmem<BLOCK_N>;
-  CUtensorMap map_a, map_w;
-  if (int rc = make_map(&map_a, a, (uint64_t)m, (uint64_t)k, kBlockM)) return rc;
-  if (int rc = make_map(&map_w, w, (uint64_t)n, (uint64_t)k, BLOCK_N)) return rc;
+                      cudaStream_t stream) {
+  using C = TcCfg<BLOCK_N, EPI, OutT>;
+  CUtensorMap map_a, map_w, map_out, map_resid;
+  if (int rc = make_map(&map_a, a, (uint64_t)m, (uint64_t)k, kBlockM, 2)) return rc;
+  if (int rc = make_map(&map_w, w, (uint64_t)n, (uint64_t)k, BLOCK_N, 2)) return rc;
+  if (int rc = make_map(&map_out, out, (uint64_t)m, (uint64_t)n, kBlockM, (int)sizeof(OutT))) return rc;
+  map_resid = map_out;
+  if (C::kResid)
+    if (int rc = make_map(&map_resid, ep.resid, (uint64_t)m, (uint64_t)n, kBlockM, 4)) return rc;
   auto kern = gemm_tc_kernel<BLOCK_N, EPI, OutT>;
   static bool attr_set = false;
   if (!attr_set) {
-    CNB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    CNB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
     attr_set = true;
   }
   const int n_tiles = (int)ceil_div(m, kBlockM) * (n / BLOCK_N);
   const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-  kern<<<grid, kTcThreads, S::kTotal, stream>>>(map_a, map_w, m, n, k, ep, out, ldo);
+  kern<<<grid, kTcThreads, C::kTotal, stream>>>(map_a, map_w, map_out, map_resid, m, n, k, ep);
   CNB_LAUNCH_OK();
   return 0;
 }
 
 template <int EPI, typename OutT>
 static int launch_n(const __nv_bfloat16* a, const __nv_bfloat16* w, int m, int n, int k, const EpiParams& ep, OutT* out,
-                    int64_t ldo, cudaStream_t stream) {
-  if (n % 192 == 0) return launch_cfg<192, EPI, OutT>(a, w, m, n, k, ep, out, ldo, stream);
-  if (n % 128 == 0) return launch_cfg<128, EPI, OutT>(a, w, m, n, k, ep, out, ldo, stream);
-  if (n % 96 == 0) return launch_cfg<96, EPI, OutT>(a, w, m, n, k, ep, out, ldo, stream);
-  set_error("gemm_tc: N=" + std::to_string(n) + " is not a multiple of 96/128/192");
+                    cudaStream_t stream) {
+  if (n % 192 == 0) return launch_cfg<192, EPI, OutT>(a, w, m, n, k, ep, out, stream);
+  if (n % 128 == 0) return launch_cfg<128, EPI, OutT>(a, w, m, n, k, ep, out, stream);
+  if (n == 96) return launch_cfg<96, EPI, OutT>(a, w, m, n, k, ep, out, stream);
+  set_error("gemm_tc: N=" + std::to_string(n) + " is neither 96 nor a multiple of 128/192");
   return -1;
 }
 
@@ -414,15 +493,18 @@ int launch_gemm_tc(const __nv_bfloat16* a, const __nv_bfloat16* w, int m, int n,
   CNB_REQUIRE(g_encode != nullptr, "gemm_tc_init() was not called");
   CNB_REQUIRE(k % 8 == 0, "gemm_tc needs K to be a multiple of 8 (16-byte TMA row stride)");
   CNB_REQUIRE(ep.bias != nullptr, "gemm_tc epilogues need a bias vector");
-  CNB_REQUIRE(n <= kMaxN, "gemm_tc stages bias/scale in shared memory: N must be <= 3072");
+  CNB_REQUIRE(ldo == n, "gemm_tc writes through a TMA tensor map: the output must be contiguous (ldo == N)");
+  CNB_REQUIRE(n <= (epi == EPI_SCALE_RESID ? 768 : kMaxN), "gemm_tc stages bias/scale in shared memory: N too large");
   if (m == 0) return 0;
   switch (epi) {
-    case EPI_BIAS: return launch_n<EPI_BIAS, OutT>(a, w, m, n, k, ep, out, ldo, stream);
-    case EPI_BIAS_GELU: return launch_n<EPI_BIAS_GELU, OutT>(a, w, m, n, k, ep, out, ldo, stream);
-    case EPI_BIAS_RELU: return launch_n<EPI_BIAS_RELU, OutT>(a, w, m, n, k, ep, out, ldo, stream);
-    case EPI_SCALE_RESID: return launch_n<EPI_SCALE_RESID, OutT>(a, w, m, n, k, ep, out, ldo, stream);
+    case EPI_BIAS: return launch_n<EPI_BIAS, OutT>(a, w, m, n, k, ep, out, stream);
+    case EPI_BIAS_GELU: return launch_n<EPI_BIAS_GELU, OutT>(a, w, m, n, k, ep, out, stream);
+    case EPI_BIAS_RELU: return launch_n<EPI_BIAS_RELU, OutT>(a, w, m, n, k, ep, out, stream);
+    case EPI_SCALE_RESID:
+      if constexpr (sizeof(OutT) == 4) return launch_n<EPI_SCALE_RESID, OutT>(a, w, m, n, k, ep, out, stream);
+      break;
   }
-  set_error("gemm_tc: unknown epilogue");
+  set_error("gemm_tc: unsupported epilogue / output type combination");
   return -1;
 }
 template int launch_gemm_tc<float>(const __nv_bfloat16*, const __nv_bfloat16*, int, int, int, Epilogue, const EpiParams&,

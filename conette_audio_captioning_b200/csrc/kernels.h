@@ -109,10 +109,14 @@ int launch_beam_finalize(BeamState st, int64_t* best_preds, float* best_lp, int*
 struct PLayer {
   const float *sa_in_w, *sa_in_b, *sa_out_w, *sa_out_b, *ca_q_w, *ca_q_b, *ca_out_w, *ca_out_b;
   const float *l1_w, *l1_b, *l2_w, *l2_b, *n1_g, *n1_b, *n2_g, *n2_b, *n3_g, *n3_b;
+  // k4-packed copies for the cluster decoder: Wp[(k/4) * N + n][4] = W[n][4*(k/4) .. +3]
+  const float *sa_in_p, *sa_out_p, *ca_q_p, *ca_out_p, *l1_p, *l2_p;
 };
 struct PersistentArgs {
   PLayer layers[6];
   const float *emb, *pe, *cls_w, *cls_b;
+  const float* cls_p;        // k4-packed classifier, vpad columns (zero beyond the vocabulary)
+  int vpad;
   const float* ckv;          // (B*T', 6*512) cross-attention K|V of all layers
   const int* lens;
   const int64_t* bos_ids;
@@ -129,6 +133,10 @@ void decoder_set_pdl(bool on);  // programmatic dependent launch between the fus
 int launch_decoder_init(const PersistentArgs& args, cudaStream_t stream);
 int launch_decoder_step_fused(const PersistentArgs& args, int step, int cur, float** x_cur_io, float** x_alt_io,
                               cudaStream_t stream);
+
+// cluster-resident decode (decoder_cluster.cu): one launch, a cluster of 8 CTAs per group of 12/beam clips
+bool decoder_cluster_supported(const PersistentArgs& args);
+int launch_decoder_cluster(const PersistentArgs& args, cudaStream_t stream);
 
 // global launch counter (reported through cnb_launch_count)
 void count_launch();

@@ -26,9 +26,12 @@ def _ptr(t: Optional[Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+DECODER_MODES = {"auto": 0, "graph": 1, "graph_pdl": 2, "graph_unfused": 3, "eager": 4, "persistent": 5, "cluster": 6}
+
+
 class Engine:
     def __init__(self, state_dict: Dict[str, Tensor], vocab_size: int, device: int = 0, precision: str = "fast",
-                 enc_chunk: int = 0, decoder: str = "graph") -> None:
+                 enc_chunk: int = 0, decoder: str = "auto") -> None:
         if not torch.cuda.is_available():
             raise _lib.CnbError("conette_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -41,10 +44,13 @@ class Engine:
         cfg.vocab_size = self.vocab_size
         cfg.precision = {"fast": _lib.PRECISION_FAST, "parity": _lib.PRECISION_PARITY}[precision]
         cfg.enc_chunk = enc_chunk
-        # decoder execution mode (all bit-identical): "graph" = CUDA-graph replay of the fused phase kernels (default, fastest:
-        # ~10 ms / 20 steps at R=192), "graph_pdl" = same with programmatic dependent launch (measured slower), "graph_unfused"
-        # = per-op kernels, "persistent" = one cooperative kernel with software grid barriers, "eager" = plain launches
-        cfg.reserved[0] = {"persistent": 0, "graph": 10, "graph_pdl": 2, "graph_unfused": 14, "eager": 3}[decoder]
+        # decoder execution mode: "auto" = "cluster" when the shape allows it (beam <= 8, max_len <= 64, vocabulary slice fits in
+        # shared memory), else "graph".  "cluster" = one launch, a cluster of 8 CTAs decodes a group of 12/beam clips start to
+        # finish (DSMEM exchanges + hardware cluster barriers); "graph" = CUDA-graph replay of the fused phase kernels;
+        # "graph_pdl" = same with programmatic dependent launch; "graph_unfused" = per-op kernels; "persistent" = one
+        # cooperative kernel with software grid barriers; "eager" = plain launches.  The five non-cluster modes are
+        # bit-identical; "cluster" differs by fp32 summation order only.
+        cfg.reserved[0] = DECODER_MODES[decoder]
         handle = C.c_void_p()
         _lib.check(self.lib.cnb_create(C.byref(cfg), C.byref(handle)))
         self.handle = handle

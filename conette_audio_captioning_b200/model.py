@@ -28,7 +28,7 @@ class CoNeTTEModel:
         device: Union[int, str, torch.device] = 0,
         precision: str = "fast",
         enc_chunk: int = 0,
-        decoder: str = "graph",
+        decoder: str = "auto",
         audioset_idx_to_name: Optional[Dict[int, str]] = None,
     ) -> None:
         self.config = config or CoNeTTEConfig()

@@ -305,6 +305,41 @@ def test_decoder_execution_modes_agree_bitwise(small_sd):
             assert torch.equal(a, c), mode
 
 
+@pytest.mark.parametrize("b,beam,max_len", [(37, 3, 20), (5, 1, 12), (9, 2, 20), (7, 5, 16), (3, 8, 24), (64, 3, 20), (130, 3, 20)])
+def test_decoder_cluster_mode_matches_graph_mode(small_sd, b, beam, max_len):
+    """One-launch cluster decode (DSMEM + cluster barriers) vs the bit-exact-tested graph mode: same ids / trimming where
+    the winning beam has a firm score margin, scores within fp32 summation-order noise (cluster mode sums in another order)."""
+    from conette_audio_captioning_b200.engine import Engine
+
+    g = torch.Generator().manual_seed(100 + b)
+    tp = 31
+    fe = torch.randn(b, tp, 768, generator=g)
+    lens = torch.randint(1, tp + 1, (b,), generator=g)
+    bos_ids = small_sd["model.task_id_to_token_id"][torch.randint(0, 7, (b,), generator=g)]
+    forbid = small_sd["model.forbid_rep_mask"]
+    outs = {}
+    for mode in ("graph", "cluster"):
+        eng = Engine(small_sd, vocab_size=forbid.shape[0], precision="parity", decoder=mode)
+        try:
+            outs[mode] = [o.cpu() for o in eng.decode(fe, lens, bos_ids, forbid, beam, 3, max_len)]
+            again = [o.cpu() for o in eng.decode(fe, lens, bos_ids, forbid, beam, 3, max_len)]
+            assert all(torch.equal(a, c) for a, c in zip(outs[mode], again)), mode  # deterministic
+        finally:
+            eng.close()
+    gp, gl, gmp, gml = outs["graph"]
+    cp, cl, cmp_, cml = outs["cluster"]
+    assert gp.shape == cp.shape and gmp.shape == cmp_.shape
+    same_clip = (gmp == cmp_).flatten(1).all(1)
+    assert same_clip.float().mean() > 0.9, f"only {int(same_clip.sum())}/{b} clips have identical beams"
+    torch.testing.assert_close(cml[same_clip], gml[same_clip], rtol=2e-4, atol=2e-4)
+    # clips whose beams differ must be explained by a near-tie: their sorted beam scores still agree closely
+    if (~same_clip).any():
+        torch.testing.assert_close(cml[~same_clip].sort(1).values, gml[~same_clip].sort(1).values, rtol=0, atol=5e-3)
+    best_same = (gp == cp).all(1)
+    assert (best_same | ~same_clip).all()
+    torch.testing.assert_close(cl[same_clip], gl[same_clip], rtol=2e-4, atol=2e-4)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # end to end through the reference-facing API
 # ----------------------------------------------------------------------------------------------------------------------
