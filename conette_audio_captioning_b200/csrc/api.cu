@@ -86,6 +86,7 @@ struct cnb_handle {
   // projection + decoder
   float *proj_w, *proj_b, *emb, *pe, *ca_kv_w, *ca_kv_b, *cls_w, *cls_b, *cls_p;
   int cls_vpad = 0;
+  void* dec_tmaps = nullptr;  // 37 TMA descriptors of the decoder weights (cluster decoder)
   LayerW layers[6];
   // workspace (grown on demand)
   std::map<std::string, Buffer> ws;
@@ -414,6 +415,28 @@ static int finalize(cnb_handle* h) {
       }
     }
     PUT(h->ca_kv_w, kvw); PUT(h->ca_kv_b, kvb);
+    // TMA descriptors of the fp32 decoder weights (tf32 tcgen05 GEMMs of the cluster decoder): box = 32 k x {32 | 256} rows
+    {
+      std::vector<uint8_t> maps((size_t)37 * 128);
+      alignas(64) uint8_t tmp[128];
+      auto put_map = [&](int idx, const float* w, int64_t rows, int64_t cols, int box_rows) {
+        if (int rc = tc_make_map(tmp, w, rows, cols, box_rows, 4)) return rc;
+        memcpy(&maps[(size_t)idx * 128], tmp, 128);
+        return 0;
+      };
+      for (int l = 0; l < kLayers; ++l) {
+        const LayerW& L = h->layers[l];
+        if (int rc = put_map(6 * l + 0, L.sa_in_w, 3 * kD, kD, 32)) return rc;
+        if (int rc = put_map(6 * l + 1, L.sa_out_w, kD, kD, 32)) return rc;
+        if (int rc = put_map(6 * l + 2, L.ca_q_w, kD, kD, 32)) return rc;
+        if (int rc = put_map(6 * l + 3, L.ca_out_w, kD, kD, 32)) return rc;
+        if (int rc = put_map(6 * l + 4, L.l1_w, kFF, kD, 256)) return rc;
+        if (int rc = put_map(6 * l + 5, L.l2_w, kD, kFF, 256)) return rc;
+      }
+      if (int rc = put_map(36, h->cls_w, V, kD, 256)) return rc;
+      CNB_CUDA_OK(cudaMalloc(&h->dec_tmaps, maps.size()));
+      CNB_CUDA_OK(cudaMemcpy(h->dec_tmaps, maps.data(), maps.size(), cudaMemcpyHostToDevice));
+    }
   }
   CNB_CUDA_OK(cudaMalloc(&h->zero_flag, 4 * sizeof(int)));
   CNB_CUDA_OK(cudaMemset(h->zero_flag, 0, 4 * sizeof(int)));
@@ -734,7 +757,7 @@ static int decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, c
                           L.l1_b, L.l2_w, L.l2_b, L.n1_g, L.n1_b, L.n2_g, L.n2_b, L.n3_g, L.n3_b,
                           L.sa_in_p, L.sa_out_p, L.ca_q_p, L.ca_out_p, L.l1_p, L.l2_p};
   }
-  pa.emb = h->emb; pa.pe = h->pe; pa.cls_w = h->cls_w; pa.cls_b = h->cls_b; pa.cls_p = h->cls_p; pa.vpad = h->cls_vpad;
+  pa.emb = h->emb; pa.pe = h->pe; pa.cls_w = h->cls_w; pa.cls_b = h->cls_b; pa.cls_p = h->cls_p; pa.vpad = h->cls_vpad; pa.tmaps = h->dec_tmaps;
   pa.ckv = w.ckv; pa.lens = lens; pa.bos_ids = bos_ids; pa.forbid = forbid;
   pa.xa = w.x; pa.xb = xb; pa.qkv = w.qkv; pa.attn = w.attn; pa.tmp = w.tmp; pa.ff = w.ff; pa.part = w.part;
   pa.logits = w.logits; pa.kc = w.kc; pa.vc = w.vc; pa.bs = bs; pa.bar = bar;
@@ -742,7 +765,9 @@ static int decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, c
   pa.batch = batch;
   pa.trace = nullptr;
 
-  if (h->use_cluster == 2 || (h->use_cluster == 1 && decoder_cluster_supported(pa))) {
+  // default: the tf32 tensor-core cluster decoder belongs to precision "fast"; "parity" keeps the fp32 graph decoder
+  if (h->use_cluster == 2 ||
+      (h->use_cluster == 1 && h->cfg.precision == CNB_PRECISION_FAST && decoder_cluster_supported(pa))) {
     // one cluster of 8 CTAs per group of clips decodes start to finish (decoder_cluster.cu): 2 GEMMs + 1 kernel + 2 gathers
     if (int rc = dec_project(h, frame_embs, batch, tp, w, st)) return rc;
     const bool trace_on = getenv("CNB_DEC_TRACE") != nullptr;
@@ -756,7 +781,7 @@ static int decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, c
       if (int rc = launch_decoder_cluster(pa, st)) return rc;
     }
     if (trace_on) {  // debug: time between phase marks as seen by thread 0 of the first CTA, summed over steps and layers
-      unsigned long long t[20];
+      unsigned long long t[24];
       CNB_CUDA_OK(cudaStreamSynchronize(st));
       CNB_CUDA_OK(cudaMemcpy(t, pa.trace, sizeof(t), cudaMemcpyDeviceToHost));
       static const char* names[] = {"qkv gemm", "self attn", "bcast+sync1", "sa_out gemm", "bcast+sync2", "ln1", "ca_q gemm",
@@ -767,6 +792,8 @@ static int decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, c
       for (int i = 0; i < 19; ++i) tot += (double)t[i];
       for (int i = 0; i < 19; ++i)
         fprintf(stderr, "[dec cluster trace] %-24s %9.1f us  (%4.1f %%)\n", names[i], (double)t[i] / 1e3, 100.0 * t[i] / tot);
+      fprintf(stderr, "[dec cluster trace] thread 0 cycles: wait weights %llu, issue MMAs %llu, wait MMAs %llu, wait+epilogue %llu\n",
+              t[20], t[21], t[22], t[23]);
     }
     if (int rc = launch_beam_finalize(bs, preds, lprobs, best_len, dd, st)) return rc;
     gather_mult_kernel<<<(rows * max_len + 255) / 256, 256, 0, st>>>(bs, mult_preds, mult_lprobs, best_len, info, rows, max_len,
@@ -934,6 +961,7 @@ int cnb_destroy(cnb_handle* h) {
     if (kv.second.ptr) cudaFree(kv.second.ptr);
   if (h->arena.base) cudaFree(h->arena.base);
   if (h->zero_flag) cudaFree(h->zero_flag);
+  if (h->dec_tmaps) cudaFree(h->dec_tmaps);
   for (auto e : h->prof_events) cudaEventDestroy(e);
   for (auto& g : h->dec_graphs) cudaGraphExecDestroy(g.exec);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);

@@ -71,6 +71,8 @@ template <typename OutT>
 int launch_gemm_tc(const __nv_bfloat16* a, const __nv_bfloat16* w, int m, int n, int k, Epilogue epi, const EpiParams& ep,
                    OutT* out, int64_t ldo, cudaStream_t stream);
 int gemm_tc_init();  // resolves cuTensorMapEncodeTiled; returns 0 on success
+// 2-D row-major (rows, cols) tensor map into map_out (a 128-byte CUtensorMap): box = (box_rows, 128 bytes), 128B swizzle
+int tc_make_map(void* map_out, const void* ptr, int64_t rows, int64_t cols, int box_rows, int elt_bytes);
 
 // ---- decoder / beam search ------------------------------------------------------------------------------------------------
 struct DecoderDims {
@@ -117,6 +119,7 @@ struct PersistentArgs {
   const float *emb, *pe, *cls_w, *cls_b;
   const float* cls_p;        // k4-packed classifier, vpad columns (zero beyond the vocabulary)
   int vpad;
+  const void* tmaps;         // 37 CUtensorMaps (device): layer l -> [6l + {sa_in, sa_out, ca_q, ca_out, l1, l2}], 36 = classifier
   const float* ckv;          // (B*T', 6*512) cross-attention K|V of all layers
   const int* lens;
   const int64_t* bos_ids;

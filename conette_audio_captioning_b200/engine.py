@@ -165,8 +165,9 @@ class Engine:
                 mult_lprobs)
 
     def decode(self, frame_embs: Tensor, lens: Tensor, bos_ids: Tensor, forbid_mask: Optional[Tensor], beam: int = 3,
-               min_len: int = 3, max_len: int = 20):
-        """frame_embs (B, T', 768) -> (preds, lprobs, mult_preds, mult_lprobs) like reference ``generate``."""
+               min_len: int = 3, max_len: int = 20, trim: bool = True):
+        """frame_embs (B, T', 768) -> (preds, lprobs, mult_preds, mult_lprobs) like reference ``generate``
+        (``trim=False``: the untrimmed (B, max_len) / (B, beam, max_len) buffers + the info vector)."""
         fe = self._dev(frame_embs, torch.float32)
         b, tp, _ = fe.shape
         lens = self._dev(lens, torch.int32)
@@ -175,7 +176,7 @@ class Engine:
         outs = self._alloc_outputs(b, beam, max_len)
         _lib.check(self.lib.cnb_decode(self.handle, fe.data_ptr(), lens.data_ptr(), bos.data_ptr(), _ptr(forbid), b, tp, beam,
                                        min_len, max_len, *[o.data_ptr() for o in outs], self._stream()))
-        return self._trim(*outs)
+        return self._trim(*outs) if trim else tuple(outs)
 
     def decoder_logits(self, frame_embs: Tensor, lens: Tensor, tokens: Tensor) -> Tensor:
         """Teacher-forced logits (B, steps, V) for given token prefixes (B, steps)."""

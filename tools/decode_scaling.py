@@ -30,7 +30,7 @@ def timed(fn, reps=10):
 
 
 eng = Engine(sd, V, precision="fast")
-for b in (8, 16, 32, 64, 128):
+for b in (1, 2, 4, 8, 16, 32, 64, 128):
     fe = torch.randn(b, 31, 768, device="cuda")
     bos = sd["model.task_id_to_token_id"][torch.zeros(b, dtype=torch.long)].cuda()
     lens = torch.full((b,), 31)
