@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB_DIR = PKG / "lib"
 LIB_PATH = LIB_DIR / "libconette_b200.so"
-SOURCES = ("api.cu", "frontend.cu", "encoder.cu", "gemm_simt.cu", "gemm_tc.cu", "decoder.cu", "decoder_persistent.cu", "decoder_cluster.cu", "beam.cu")
+SOURCES = ("api.cu", "frontend.cu", "encoder.cu", "gemm_simt.cu", "gemm_tc.cu", "decoder.cu", "decoder_persistent.cu", "decoder_cluster.cu", "beam.cu", "dwconv_ring.cu")
 NVCC_FLAGS = (
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-shared",
@@ -30,33 +30,49 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found (set $NVCC)")
 
 
-def _fingerprint() -> str:
+def _headers_digest() -> bytes:
     hsh = hashlib.sha256()
-    for f in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) +
-                    [PKG.parent / "include" / "conette_b200.h"]):
+    for f in sorted(list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [PKG.parent / "include" / "conette_b200.h"]):
         hsh.update(f.name.encode())
         hsh.update(f.read_bytes())
     hsh.update(" ".join(NVCC_FLAGS).encode())
-    return hsh.hexdigest()
+    return hsh.digest()
+
+
+def _compile_one(nvcc: str, src: Path, obj: Path, hdr: bytes, force: bool, verbose: bool) -> str:
+    """One translation unit -> one object file; skipped when neither the source nor any header changed."""
+    fp = hashlib.sha256(hdr + src.read_bytes()).hexdigest()
+    stamp = obj.with_suffix(".sha256")
+    if not force and obj.exists() and stamp.exists() and stamp.read_text().strip() == fp:
+        return ""
+    cmd = [nvcc, *[f for f in NVCC_FLAGS if f != "-shared"], "-c", "-o", str(obj), str(src)]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed on {src.name} ({res.returncode}):\n{res.stdout}\n{res.stderr}")
+    stamp.write_text(fp)
+    return res.stderr
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every CUDA source for sm_100a into one shared library; no-op when sources are unchanged."""
+    """Compile every CUDA source for sm_100a (one object per source, in parallel, cached) and link one shared library."""
+    from concurrent.futures import ThreadPoolExecutor
+
     LIB_DIR.mkdir(exist_ok=True)
-    stamp = LIB_DIR / "build.sha256"
-    fp = _fingerprint()
-    if not force and LIB_PATH.exists() and stamp.exists() and stamp.read_text().strip() == fp:
-        return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB_PATH), *[str(CSRC / s) for s in SOURCES]]
+    obj_dir = LIB_DIR / "obj"
+    obj_dir.mkdir(exist_ok=True)
+    nvcc, hdr = _nvcc(), _headers_digest()
+    objs = [obj_dir / (Path(s).stem + ".o") for s in SOURCES]
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        logs = list(ex.map(lambda so: _compile_one(nvcc, CSRC / so[0], so[1], hdr, force, verbose), zip(SOURCES, objs)))
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd), file=sys.stderr)
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError(f"nvcc failed ({res.returncode}):\n{res.stdout}\n{res.stderr}")
-    if verbose:
-        print(res.stderr, file=sys.stderr)
-    stamp.write_text(fp)
+        print("\n".join(l for l in logs if l), file=sys.stderr)
+    newest = max(o.stat().st_mtime for o in objs)
+    if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < newest:
+        res = subprocess.run([nvcc, "-shared", "-o", str(LIB_PATH), *map(str, objs)], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"link failed ({res.returncode}):\n{res.stdout}\n{res.stderr}")
     return LIB_PATH
 
 

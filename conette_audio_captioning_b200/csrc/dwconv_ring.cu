@@ -1,0 +1,300 @@
+// K-DWLN v3: depthwise 7x7 (pad 3) + bias + LayerNorm(C) for ConvNeXt stages 1-2 (reference convnext.py:61-66), sm_100a.
+//
+// The op is bound by the FP32 pipe, not by HBM (49 FMA per 6 algorithmic bytes), so the kernel is organised around keeping
+// every FMA lane of every SM busy with packed fma.rn.f32x2:
+//   * thread = (row group g, 7-pixel strip, channel PAIR): its 49 x float2 weights stay in registers for the whole launch;
+//     per iteration it produces 2 output rows x 7 pixels x 2 channels from 8 input rows x 13 pixels (104 LDS.64, 686 FFMA2);
+//   * CTA = 384 threads = 12 warps (3 per scheduler): 2 row groups x (TW/7 strips) x (C/2 pairs); no padded lanes -- for
+//     C = 96 a strip owns 1.5 warps and the LayerNorm reduction works on half-warps;
+//   * input rows live in a 14-slot shared-memory ring shared by both row groups (10 live rows + 4 in flight), filled by
+//     ONE thread with cp.async.bulk.tensor (4-D NHWC map, box = C x (TW+6) pixels): the conv zero padding -- left/right
+//     halo, rows above/below the clip -- is the TMA out-of-bounds fill, so there is no per-thread address arithmetic;
+//   * work = the flattened (clip, column strip, row quad) space cut into equal contiguous ranges, one per SM (148 CTAs):
+//     an SM crosses a column boundary at most a few times and all SMs finish together;
+//   * LayerNorm: one pass (sum, sum of squares); a 16-value butterfly costs 15-16 shuffles per 16 values; per-(half-)warp
+//     partials are combined in fixed order through shared memory (deterministic); normalisation with packed FFMA2.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_ptx.cuh"
+
+namespace cnb {
+
+namespace {
+
+constexpr float kLnEps = 1e-6f;
+constexpr int kRG = 2;        // row groups per CTA (2 output rows each)
+constexpr int kNS = 14;       // ring slots
+constexpr int kThreads = 384;
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+
+// One butterfly stage: n values survive; lanes with (lane & mask) keep the upper half.
+template <int N>
+__device__ __forceinline__ void bfly_stage(float (&v)[16], int lane, int mask) {
+  const bool up = lane & mask;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const float keep = up ? v[k + N] : v[k], send = up ? v[k] : v[k + N];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+  }
+}
+// 16 values summed over the 16 lanes of a half-warp (15 shuffles): lane l ends with value (l & 15) bit-reversed-free index
+// idx = 8*b3 + 4*b2 + 2*b1 + b0 of its half-warp.
+__device__ __forceinline__ float half_sum16(float (&v)[16], int lane) {
+  bfly_stage<8>(v, lane, 8);
+  bfly_stage<4>(v, lane, 4);
+  bfly_stage<2>(v, lane, 2);
+  bfly_stage<1>(v, lane, 1);
+  return v[0];
+}
+// 16 values summed over the 32 lanes of a warp (16 shuffles): lane l ends with value idx = (l >> 1) & 15 (bit order
+// 8*b4 + 4*b3 + 2*b2 + b1); lanes l and l^1 hold the same total.
+__device__ __forceinline__ float warp_sum16(float (&v)[16], int lane) {
+  bfly_stage<8>(v, lane, 16);
+  bfly_stage<4>(v, lane, 8);
+  bfly_stage<2>(v, lane, 4);
+  bfly_stage<1>(v, lane, 2);
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+template <int C, int W, int TW, typename OutT>
+struct DwCfg {
+  static constexpr int CP = C / 2;
+  static constexpr int NSTRIP = TW / 7;
+  static constexpr int GROUP_T = CP * NSTRIP;           // threads of one row group
+  static constexpr bool HALF = (CP % 32) != 0;          // strips own a non-integral number of warps: reduce per half-warp
+  static constexpr int NPART = HALF ? CP / 16 : CP / 32;  // partial sums per pixel
+  static constexpr int PSTR = NPART <= 4 ? 8 : 16;      // floats per pixel in s_part: [sum x NPART | pad][sq x NPART | pad]
+  static constexpr int RW = TW + 6;
+  static constexpr int ROW_FLOATS = RW * C;
+  static constexpr int ROW_BYTES = ROW_FLOATS * 4;
+  static constexpr int STRIPS = W / TW;
+  static constexpr int PART_FLOATS = kRG * NSTRIP * 16 * PSTR;
+  static constexpr int RING_OFF = 0;
+  static constexpr int PART_OFF = kNS * ROW_BYTES;
+  static constexpr int VEC_OFF = PART_OFF + PART_FLOATS * 4;   // bias | gamma | beta
+  static constexpr int BAR_OFF = VEC_OFF + 3 * C * 4;
+  static constexpr int SMEM = BAR_OFF + 16 + 128;              // + alignment slack
+  static_assert(GROUP_T * kRG == kThreads, "CTA shape");
+  static_assert(CP % 16 == 0 && TW % 7 == 0 && W % TW == 0, "tiling");
+  static_assert(ROW_BYTES % 128 == 0, "TMA destination alignment");
+  static_assert(NPART <= 8, "partials per pixel");
+  static_assert(SMEM <= 232448, "shared memory budget");
+};
+
+template <int C, int W, int TW, typename OutT>
+__global__ void __launch_bounds__(kThreads, 1)
+dwconv_ln_tma_kernel(const __grid_constant__ CUtensorMap map_x, int H, int PQ, int total_units, int quota,
+                     const float* __restrict__ w_t, const float* __restrict__ bias, const float* __restrict__ ln_g,
+                     const float* __restrict__ ln_b, OutT* __restrict__ out) {
+  using Cfg = DwCfg<C, W, TW, OutT>;
+  constexpr int CP = Cfg::CP, PW = 7, NPART = Cfg::NPART, PSTR = Cfg::PSTR, ROW_FLOATS = Cfg::ROW_FLOATS;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base_u32 = (smem_u32(smem_raw) + 127u) & ~127u;
+  uint8_t* sm = smem_raw + (base_u32 - smem_u32(smem_raw));
+  const float* ring = reinterpret_cast<const float*>(sm + Cfg::RING_OFF);
+  float* s_part = reinterpret_cast<float*>(sm + Cfg::PART_OFF);
+  float* s_vec = reinterpret_cast<float*>(sm + Cfg::VEC_OFF);
+  const uint32_t bar0 = base_u32 + Cfg::BAR_OFF;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int g = tid / Cfg::GROUP_T;
+  const int rem = tid - g * Cfg::GROUP_T;
+  const int strip_t = rem / CP;
+  const int cp = rem - strip_t * CP;
+  const int part = Cfg::HALF ? (cp >> 4) : (cp >> 5);
+  const int wl0 = strip_t * PW;
+
+  for (int i = tid; i < C; i += kThreads) {
+    s_vec[i] = bias[i];
+    s_vec[C + i] = ln_g[i];
+    s_vec[2 * C + i] = ln_b[i];
+  }
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async_smem();
+  }
+  float2 wr[49];
+#pragma unroll
+  for (int t = 0; t < 49; ++t) wr[t] = __ldg(reinterpret_cast<const float2*>(w_t + t * C + 2 * cp));
+
+  const int u_begin = blockIdx.x * quota;
+  const int u_end = min(total_units, u_begin + quota);
+  uint32_t q = 0;  // running batch counter: batch q is consumed by the q-th iteration of this CTA (barrier q&1, parity (q>>1)&1)
+
+  for (int u = u_begin; u < u_end;) {
+    const int col = u / PQ, q0 = u - col * PQ;
+    const int nq = min(u_end - u, PQ - q0);
+    const int b = col / Cfg::STRIPS, strip_c = col - b * Cfg::STRIPS;
+    const int w_base = strip_c * TW;
+    const int h0 = 4 * q0;
+    const int h_end = min(H, h0 + 4 * nq);
+    u += nq;
+
+    __syncthreads();  // every thread has left the previous item's ring (and the setup above is visible)
+    if (tid == 0) {
+      const uint32_t bar = bar0 + 8 * (q & 1);
+      mbar_expect_tx(bar, 10 * Cfg::ROW_BYTES);
+#pragma unroll 1
+      for (int v = 0; v < 10; ++v) tma_load_4d(base_u32 + Cfg::RING_OFF + v * Cfg::ROW_BYTES, &map_x, 0, w_base - 3, h0 - 3 + v, b, bar);
+    }
+    int sbase = 0;  // ring slot of input row h - 3 (virtual row 4j)
+#pragma unroll 1
+    for (int j = 0; j < nq; ++j, ++q) {
+      const int h = h0 + 4 * j;
+      __syncthreads();  // iteration j-1 is finished everywhere: its four oldest rows and s_part can be overwritten
+      if (tid == 0 && j + 1 < nq) {
+        const uint32_t bar = bar0 + 8 * ((q + 1) & 1);
+        mbar_expect_tx(bar, 4 * Cfg::ROW_BYTES);
+        int sl = sbase + 10;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (sl >= kNS) sl -= kNS;
+          tma_load_4d(base_u32 + Cfg::RING_OFF + sl * Cfg::ROW_BYTES, &map_x, 0, w_base - 3, h + 7 + t, b, bar);
+          ++sl;
+        }
+      }
+      mbar_wait(bar0 + 8 * (q & 1), (q >> 1) & 1);
+
+      float2 acc0[PW], acc1[PW];
+      {
+        const float2 bi = *reinterpret_cast<const float2*>(s_vec + 2 * cp);
+#pragma unroll
+        for (int p = 0; p < PW; ++p) acc0[p] = acc1[p] = bi;
+      }
+      int sl = sbase + 2 * g;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (sl >= kNS) sl -= kNS;
+        const float* row = ring + sl * ROW_FLOATS + wl0 * C + 2 * cp;
+        ++sl;
+        float2 in[PW + 6];
+#pragma unroll
+        for (int k = 0; k < PW + 6; ++k) in[k] = *reinterpret_cast<const float2*>(row + k * C);
+        // tap-major order: consecutive FFMA2 hit 7 (14) different accumulators, so the issue stream has no dependent chains
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+#pragma unroll
+          for (int p = 0; p < PW; ++p) {
+            if (i < 7) acc0[p] = __ffma2_rn(in[p + k], wr[i * 7 + k], acc0[p]);
+            if (i > 0) acc1[p] = __ffma2_rn(in[p + k], wr[(i - 1) * 7 + k], acc1[p]);
+          }
+        }
+      }
+      // ---- LayerNorm statistics: (sum, sumsq) of 14 pixels, value index = 8 * row + p
+      float smv[16], sqv[16];
+#pragma unroll
+      for (int p = 0; p < PW; ++p) {
+        smv[p] = acc0[p].x + acc0[p].y;
+        sqv[p] = fmaf(acc0[p].x, acc0[p].x, acc0[p].y * acc0[p].y);
+        smv[p + 8] = acc1[p].x + acc1[p].y;
+        sqv[p + 8] = fmaf(acc1[p].x, acc1[p].x, acc1[p].y * acc1[p].y);
+      }
+      smv[7] = smv[15] = sqv[7] = sqv[15] = 0.f;
+      float* my_part = s_part + (g * Cfg::NSTRIP + strip_t) * 16 * PSTR;
+      if (Cfg::HALF) {
+        const float tsum = half_sum16(smv, lane);
+        const float tsq = half_sum16(sqv, lane);
+        const int idx = ((lane >> 3) & 1) * 8 + ((lane >> 2) & 1) * 4 + ((lane >> 1) & 1) * 2 + (lane & 1);
+        my_part[idx * PSTR + part] = tsum;
+        my_part[idx * PSTR + PSTR / 2 + part] = tsq;
+      } else {
+        const float tsum = warp_sum16(smv, lane);
+        const float tsq = warp_sum16(sqv, lane);
+        if ((lane & 1) == 0) {
+          const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+          my_part[idx * PSTR + part] = tsum;
+          my_part[idx * PSTR + PSTR / 2 + part] = tsq;
+        }
+      }
+      __syncthreads();
+      const float2 gm = *reinterpret_cast<const float2*>(s_vec + C + 2 * cp);
+      const float2 be = *reinterpret_cast<const float2*>(s_vec + 2 * C + 2 * cp);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int hr = h + 2 * g + r;
+        if (hr >= h_end) break;
+        OutT* o = out + (((int64_t)b * H + hr) * W + w_base + wl0) * C + 2 * cp;
+#pragma unroll
+        for (int p = 0; p < PW; ++p) {
+          const float* pp = my_part + (r * 8 + p) * PSTR;
+          float s1, s2;
+          if (PSTR == 8) {
+            const float4 a = *reinterpret_cast<const float4*>(pp), c4 = *reinterpret_cast<const float4*>(pp + 4);
+            s1 = NPART == 3 ? (a.x + a.y) + a.z : (a.x + a.y) + (a.z + a.w);
+            s2 = NPART == 3 ? (c4.x + c4.y) + c4.z : (c4.x + c4.y) + (c4.z + c4.w);
+          } else {
+            s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < NPART; ++i) {
+              s1 += pp[i];
+              s2 += pp[8 + i];
+            }
+          }
+          const float mean = s1 * (1.f / C);
+          const float var = fmaxf(fmaf(s2, 1.f / C, -mean * mean), 0.f);
+          const float rstd = rsqrtf(var + kLnEps);
+          const float nmr = -mean * rstd;
+          const float2 a = r ? acc1[p] : acc0[p];
+          const float2 t = __ffma2_rn(a, make_float2(rstd, rstd), make_float2(nmr, nmr));
+          const float2 y = __ffma2_rn(t, gm, be);
+          if constexpr (sizeof(OutT) == 2) {
+            *reinterpret_cast<__nv_bfloat162*>(o + (int64_t)p * C) = __floats2bfloat162_rn(y.x, y.y);
+          } else {
+            *reinterpret_cast<float2*>(o + (int64_t)p * C) = y;
+          }
+        }
+      }
+      sbase += 4;
+      if (sbase >= kNS) sbase -= kNS;
+    }
+  }
+}
+
+template <int C, int W, int TW, typename OutT>
+int launch_t(const float* x, int batch, int h, const float* w_t, const float* bias, const float* ln_g, const float* ln_b,
+             OutT* out, cudaStream_t stream) {
+  using Cfg = DwCfg<C, W, TW, OutT>;
+  static_assert(Cfg::NPART == 3 || Cfg::NPART == 4 || Cfg::PSTR == 16, "partial layout");
+  CUtensorMap map_x;
+  if (int rc = tc_make_map_nhwc_f32(&map_x, x, batch, h, W, C, Cfg::RW)) return rc;
+  auto kern = dwconv_ln_tma_kernel<C, W, TW, OutT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CNB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_set = true;
+  }
+  const int pq = (int)ceil_div(h, 4);
+  const int total = batch * Cfg::STRIPS * pq;
+  int grid = total < kNumSMs ? total : kNumSMs;
+  const int quota = (int)ceil_div(total, grid);
+  grid = (int)ceil_div(total, quota);
+  kern<<<grid, kThreads, Cfg::SMEM, stream>>>(map_x, h, pq, total, quota, w_t, bias, ln_g, ln_b, out);
+  CNB_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace
+
+template <typename OutT>
+int launch_dwconv_ln_tma(const float* x, int batch, int h, int w, int c, const float* w_t, const float* bias,
+                         const float* ln_g, const float* ln_b, OutT* out, cudaStream_t stream) {
+  if (c == 96 && w == 56) return launch_t<96, 56, 28, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
+  if (c == 192 && w == 28) return launch_t<192, 28, 14, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
+  return 1;
+}
+template int launch_dwconv_ln_tma<float>(const float*, int, int, int, int, const float*, const float*, const float*,
+                                         const float*, float*, cudaStream_t);
+template int launch_dwconv_ln_tma<__nv_bfloat16>(const float*, int, int, int, int, const float*, const float*, const float*,
+                                                 const float*, __nv_bfloat16*, cudaStream_t);
+
+}  // namespace cnb

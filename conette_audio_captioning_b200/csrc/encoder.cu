@@ -4,6 +4,7 @@
 // Reference: nn/encoders/convnext.py:61-74 (block), :207-217 (stem / downsample), :306-334 (mean + head),
 // nn/modules/norm.py:35-40 (channels_first LayerNorm, biased variance, eps 1e-6).
 #include <algorithm>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -401,6 +402,11 @@ static int launch_dwconv_ln_t(const float* x, int batch, int h, const float* w_t
 template <typename OutT>
 int launch_dwconv_ln(const float* x, int batch, int h, int w, int c, const float* w_t, const float* bias, const float* ln_g,
                      const float* ln_b, OutT* out, cudaStream_t stream) {
+  static const bool use_tma = getenv("CNB_DWCONV_V2") == nullptr;  // A/B switch: the cp.async ring kernels below
+  if (use_tma) {
+    const int rc = launch_dwconv_ln_tma<OutT>(x, batch, h, w, c, w_t, bias, ln_g, ln_b, out, stream);
+    if (rc <= 0) return rc;  // 1 = no TMA-ring instantiation for this (C, W)
+  }
   if (c == 96 && w == 56) return launch_dwconv_ring_t<96, 56, 28, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
   if (c == 192 && w == 28) return launch_dwconv_ring_t<192, 28, 14, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
   if (c == 384 && w == 14) return launch_dwconv_ring_t<384, 14, 7, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
