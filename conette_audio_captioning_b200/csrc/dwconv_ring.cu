@@ -1,4 +1,4 @@
-// K-DWLN v3: depthwise 7x7 (pad 3) + bias + LayerNorm(C) for ConvNeXt stages 1-2 (reference convnext.py:61-66), sm_100a.
+// K-DWLN v3: depthwise 7x7 (pad 3) + bias + LayerNorm(C) for ConvNeXt stages 1-3 (reference convnext.py:61-66), sm_100a.
 //
 // The op is bound by the FP32 pipe, not by HBM (49 FMA per 6 algorithmic bytes), so the kernel is organised around keeping
 // every FMA lane of every SM busy with packed fma.rn.f32x2:
@@ -11,6 +11,10 @@
 //     halo, rows above/below the clip -- is the TMA out-of-bounds fill, so there is no per-thread address arithmetic;
 //   * work = the flattened (clip, column strip, row quad) space cut into equal contiguous ranges, one per SM (148 CTAs):
 //     an SM crosses a column boundary at most a few times and all SMs finish together;
+//   * C = 384 (stage 3) does not fit a ring of full-channel rows: a 2-CTA cluster splits the channels (192 each, same
+//     smem / thread shape as stage 2) and the CTAs push their LayerNorm partials into each other's shared memory
+//     (st.shared::cluster) with one cluster barrier per iteration; the partial buffers alternate so that a fast peer
+//     can never overwrite sums that are still being read;
 //   * LayerNorm: one pass (sum, sum of squares); a 16-value butterfly costs 15-16 shuffles per 16 values; per-(half-)warp
 //     partials are combined in fixed order through shared memory (deterministic); normalisation with packed FFMA2.
 #include <cuda.h>
@@ -33,6 +37,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
       "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
       : "memory");
+}
+
+__device__ __forceinline__ uint32_t map_peer_smem(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
 }
 
 // One butterfly stage: n values survive; lanes with (lane & mask) keep the upper half.
@@ -64,38 +74,43 @@ __device__ __forceinline__ float warp_sum16(float (&v)[16], int lane) {
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
-template <int C, int W, int TW, typename OutT>
+// C = channels handled by one CTA, CS = channel split (CTAs per cluster; the layer has C * CS channels)
+template <int C, int CS, int W, int TW, typename OutT>
 struct DwCfg {
+  static constexpr int CT = C * CS;
   static constexpr int CP = C / 2;
   static constexpr int NSTRIP = TW / 7;
   static constexpr int GROUP_T = CP * NSTRIP;           // threads of one row group
   static constexpr bool HALF = (CP % 32) != 0;          // strips own a non-integral number of warps: reduce per half-warp
-  static constexpr int NPART = HALF ? CP / 16 : CP / 32;  // partial sums per pixel
-  static constexpr int PSTR = NPART <= 4 ? 8 : 16;      // floats per pixel in s_part: [sum x NPART | pad][sq x NPART | pad]
+  static constexpr int NPART = HALF ? CP / 16 : CP / 32;  // partial sums per pixel produced by one CTA
+  static constexpr int NPT = NPART * CS;                // ... per pixel in total
+  static constexpr int PSTR = NPT <= 4 ? 8 : 16;        // floats per pixel in s_part: [sum x NPT | pad][sq x NPT | pad]
   static constexpr int RW = TW + 6;
   static constexpr int ROW_FLOATS = RW * C;
   static constexpr int ROW_BYTES = ROW_FLOATS * 4;
   static constexpr int STRIPS = W / TW;
   static constexpr int PART_FLOATS = kRG * NSTRIP * 16 * PSTR;
+  static constexpr int PART_BUFS = CS;                  // cluster mode alternates two partial buffers
   static constexpr int RING_OFF = 0;
   static constexpr int PART_OFF = kNS * ROW_BYTES;
-  static constexpr int VEC_OFF = PART_OFF + PART_FLOATS * 4;   // bias | gamma | beta
+  static constexpr int VEC_OFF = PART_OFF + PART_BUFS * PART_FLOATS * 4;   // bias | gamma | beta
   static constexpr int BAR_OFF = VEC_OFF + 3 * C * 4;
   static constexpr int SMEM = BAR_OFF + 16 + 128;              // + alignment slack
+  static_assert(CS == 1 || CS == 2, "channel split");
   static_assert(GROUP_T * kRG == kThreads, "CTA shape");
   static_assert(CP % 16 == 0 && TW % 7 == 0 && W % TW == 0, "tiling");
   static_assert(ROW_BYTES % 128 == 0, "TMA destination alignment");
-  static_assert(NPART <= 8, "partials per pixel");
+  static_assert(NPT <= 8, "partials per pixel");
   static_assert(SMEM <= 232448, "shared memory budget");
 };
 
-template <int C, int W, int TW, typename OutT>
+template <int C, int CS, int W, int TW, typename OutT>
 __global__ void __launch_bounds__(kThreads, 1)
 dwconv_ln_tma_kernel(const __grid_constant__ CUtensorMap map_x, int H, int PQ, int total_units, int quota,
                      const float* __restrict__ w_t, const float* __restrict__ bias, const float* __restrict__ ln_g,
                      const float* __restrict__ ln_b, OutT* __restrict__ out) {
-  using Cfg = DwCfg<C, W, TW, OutT>;
-  constexpr int CP = Cfg::CP, PW = 7, NPART = Cfg::NPART, PSTR = Cfg::PSTR, ROW_FLOATS = Cfg::ROW_FLOATS;
+  using Cfg = DwCfg<C, CS, W, TW, OutT>;
+  constexpr int CP = Cfg::CP, PW = 7, NPT = Cfg::NPT, PSTR = Cfg::PSTR, ROW_FLOATS = Cfg::ROW_FLOATS, CT = Cfg::CT;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base_u32 = (smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* sm = smem_raw + (base_u32 - smem_u32(smem_raw));
@@ -111,11 +126,14 @@ dwconv_ln_tma_kernel(const __grid_constant__ CUtensorMap map_x, int H, int PQ, i
   const int cp = rem - strip_t * CP;
   const int part = Cfg::HALF ? (cp >> 4) : (cp >> 5);
   const int wl0 = strip_t * PW;
+  uint32_t rank = 0;  // which C-channel slice of the layer this CTA owns
+  if (CS > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int c_off = (int)rank * C;
 
   for (int i = tid; i < C; i += kThreads) {
-    s_vec[i] = bias[i];
-    s_vec[C + i] = ln_g[i];
-    s_vec[2 * C + i] = ln_b[i];
+    s_vec[i] = bias[c_off + i];
+    s_vec[C + i] = ln_g[c_off + i];
+    s_vec[2 * C + i] = ln_b[c_off + i];
   }
   if (tid == 0) {
     mbar_init(bar0, 1);
@@ -125,9 +143,13 @@ dwconv_ln_tma_kernel(const __grid_constant__ CUtensorMap map_x, int H, int PQ, i
   }
   float2 wr[49];
 #pragma unroll
-  for (int t = 0; t < 49; ++t) wr[t] = __ldg(reinterpret_cast<const float2*>(w_t + t * C + 2 * cp));
+  for (int t = 0; t < 49; ++t) wr[t] = __ldg(reinterpret_cast<const float2*>(w_t + t * CT + c_off + 2 * cp));
+  if (CS > 1) {  // the peer must be running (its shared memory mapped) before anybody pushes partials into it
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
 
-  const int u_begin = blockIdx.x * quota;
+  const int u_begin = (int)(blockIdx.x / CS) * quota;
   const int u_end = min(total_units, u_begin + quota);
   uint32_t q = 0;  // running batch counter: batch q is consumed by the q-th iteration of this CTA (barrier q&1, parity (q>>1)&1)
 
@@ -145,7 +167,7 @@ dwconv_ln_tma_kernel(const __grid_constant__ CUtensorMap map_x, int H, int PQ, i
       const uint32_t bar = bar0 + 8 * (q & 1);
       mbar_expect_tx(bar, 10 * Cfg::ROW_BYTES);
 #pragma unroll 1
-      for (int v = 0; v < 10; ++v) tma_load_4d(base_u32 + Cfg::RING_OFF + v * Cfg::ROW_BYTES, &map_x, 0, w_base - 3, h0 - 3 + v, b, bar);
+      for (int v = 0; v < 10; ++v) tma_load_4d(base_u32 + Cfg::RING_OFF + v * Cfg::ROW_BYTES, &map_x, c_off, w_base - 3, h0 - 3 + v, b, bar);
     }
     int sbase = 0;  // ring slot of input row h - 3 (virtual row 4j)
 #pragma unroll 1
@@ -159,7 +181,7 @@ dwconv_ln_tma_kernel(const __grid_constant__ CUtensorMap map_x, int H, int PQ, i
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           if (sl >= kNS) sl -= kNS;
-          tma_load_4d(base_u32 + Cfg::RING_OFF + sl * Cfg::ROW_BYTES, &map_x, 0, w_base - 3, h + 7 + t, b, bar);
+          tma_load_4d(base_u32 + Cfg::RING_OFF + sl * Cfg::ROW_BYTES, &map_x, c_off, w_base - 3, h + 7 + t, b, bar);
           ++sl;
         }
       }
@@ -200,57 +222,70 @@ dwconv_ln_tma_kernel(const __grid_constant__ CUtensorMap map_x, int H, int PQ, i
         sqv[p + 8] = fmaf(acc1[p].x, acc1[p].x, acc1[p].y * acc1[p].y);
       }
       smv[7] = smv[15] = sqv[7] = sqv[15] = 0.f;
-      float* my_part = s_part + (g * Cfg::NSTRIP + strip_t) * 16 * PSTR;
-      if (Cfg::HALF) {
-        const float tsum = half_sum16(smv, lane);
-        const float tsq = half_sum16(sqv, lane);
-        const int idx = ((lane >> 3) & 1) * 8 + ((lane >> 2) & 1) * 4 + ((lane >> 1) & 1) * 2 + (lane & 1);
-        my_part[idx * PSTR + part] = tsum;
-        my_part[idx * PSTR + PSTR / 2 + part] = tsq;
-      } else {
-        const float tsum = warp_sum16(smv, lane);
-        const float tsq = warp_sum16(sqv, lane);
-        if ((lane & 1) == 0) {
-          const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-          my_part[idx * PSTR + part] = tsum;
-          my_part[idx * PSTR + PSTR / 2 + part] = tsq;
+      float* my_part = s_part + (CS > 1 ? (q & 1) * Cfg::PART_FLOATS : 0) + (g * Cfg::NSTRIP + strip_t) * 16 * PSTR;
+      {
+        float tsum, tsq;
+        int idx;
+        bool writer = true;
+        if (Cfg::HALF) {
+          tsum = half_sum16(smv, lane);
+          tsq = half_sum16(sqv, lane);
+          idx = lane & 15;
+        } else {
+          tsum = warp_sum16(smv, lane);
+          tsq = warp_sum16(sqv, lane);
+          idx = (lane >> 1) & 15;
+          writer = (lane & 1) == 0;
+        }
+        if (writer) {
+          float* dst = my_part + idx * PSTR + (int)rank * Cfg::NPART + part;
+          dst[0] = tsum;
+          dst[PSTR / 2] = tsq;
+          if (CS > 1) {
+            const uint32_t peer = map_peer_smem(smem_u32(dst), rank ^ 1u);
+            asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(peer), "f"(tsum) : "memory");
+            asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(peer + 4u * (PSTR / 2)), "f"(tsq) : "memory");
+          }
         }
       }
-      __syncthreads();
+      if (CS > 1) {
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+      } else {
+        __syncthreads();
+      }
       const float2 gm = *reinterpret_cast<const float2*>(s_vec + C + 2 * cp);
       const float2 be = *reinterpret_cast<const float2*>(s_vec + 2 * C + 2 * cp);
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int hr = h + 2 * g + r;
         if (hr >= h_end) break;
-        OutT* o = out + (((int64_t)b * H + hr) * W + w_base + wl0) * C + 2 * cp;
+        OutT* o = out + (((int64_t)b * H + hr) * W + w_base + wl0) * CT + c_off + 2 * cp;
 #pragma unroll
         for (int p = 0; p < PW; ++p) {
           const float* pp = my_part + (r * 8 + p) * PSTR;
           float s1, s2;
-          if (PSTR == 8) {
-            const float4 a = *reinterpret_cast<const float4*>(pp), c4 = *reinterpret_cast<const float4*>(pp + 4);
-            s1 = NPART == 3 ? (a.x + a.y) + a.z : (a.x + a.y) + (a.z + a.w);
-            s2 = NPART == 3 ? (c4.x + c4.y) + c4.z : (c4.x + c4.y) + (c4.z + c4.w);
-          } else {
-            s1 = 0.f, s2 = 0.f;
-#pragma unroll
-            for (int i = 0; i < NPART; ++i) {
-              s1 += pp[i];
-              s2 += pp[8 + i];
+          {
+            const float4 a = *reinterpret_cast<const float4*>(pp), c4 = *reinterpret_cast<const float4*>(pp + PSTR / 2);
+            s1 = NPT == 3 ? (a.x + a.y) + a.z : (a.x + a.y) + (a.z + a.w);
+            s2 = NPT == 3 ? (c4.x + c4.y) + c4.z : (c4.x + c4.y) + (c4.z + c4.w);
+            if (NPT > 4) {
+              const float4 a2 = *reinterpret_cast<const float4*>(pp + 4), c2 = *reinterpret_cast<const float4*>(pp + PSTR / 2 + 4);
+              s1 += NPT == 6 ? a2.x + a2.y : (a2.x + a2.y) + (a2.z + a2.w);
+              s2 += NPT == 6 ? c2.x + c2.y : (c2.x + c2.y) + (c2.z + c2.w);
             }
           }
-          const float mean = s1 * (1.f / C);
-          const float var = fmaxf(fmaf(s2, 1.f / C, -mean * mean), 0.f);
+          const float mean = s1 * (1.f / CT);
+          const float var = fmaxf(fmaf(s2, 1.f / CT, -mean * mean), 0.f);
           const float rstd = rsqrtf(var + kLnEps);
           const float nmr = -mean * rstd;
           const float2 a = r ? acc1[p] : acc0[p];
           const float2 t = __ffma2_rn(a, make_float2(rstd, rstd), make_float2(nmr, nmr));
           const float2 y = __ffma2_rn(t, gm, be);
           if constexpr (sizeof(OutT) == 2) {
-            *reinterpret_cast<__nv_bfloat162*>(o + (int64_t)p * C) = __floats2bfloat162_rn(y.x, y.y);
+            *reinterpret_cast<__nv_bfloat162*>(o + (int64_t)p * CT) = __floats2bfloat162_rn(y.x, y.y);
           } else {
-            *reinterpret_cast<float2*>(o + (int64_t)p * C) = y;
+            *reinterpret_cast<float2*>(o + (int64_t)p * CT) = y;
           }
         }
       }
@@ -260,14 +295,14 @@ dwconv_ln_tma_kernel(const __grid_constant__ CUtensorMap map_x, int H, int PQ, i
   }
 }
 
-template <int C, int W, int TW, typename OutT>
+template <int C, int CS, int W, int TW, typename OutT>
 int launch_t(const float* x, int batch, int h, const float* w_t, const float* bias, const float* ln_g, const float* ln_b,
              OutT* out, cudaStream_t stream) {
-  using Cfg = DwCfg<C, W, TW, OutT>;
-  static_assert(Cfg::NPART == 3 || Cfg::NPART == 4 || Cfg::PSTR == 16, "partial layout");
+  using Cfg = DwCfg<C, CS, W, TW, OutT>;
+  static_assert(Cfg::NPT == 3 || Cfg::NPT == 4 || Cfg::NPT == 6 || Cfg::NPT == 8, "partial layout");
   CUtensorMap map_x;
-  if (int rc = tc_make_map_nhwc_f32(&map_x, x, batch, h, W, C, Cfg::RW)) return rc;
-  auto kern = dwconv_ln_tma_kernel<C, W, TW, OutT>;
+  if (int rc = tc_make_map_nhwc_f32(&map_x, x, batch, h, W, Cfg::CT, C, Cfg::RW)) return rc;
+  auto kern = dwconv_ln_tma_kernel<C, CS, W, TW, OutT>;
   static bool attr_set = false;
   if (!attr_set) {
     CNB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
@@ -275,10 +310,23 @@ int launch_t(const float* x, int batch, int h, const float* w_t, const float* bi
   }
   const int pq = (int)ceil_div(h, 4);
   const int total = batch * Cfg::STRIPS * pq;
-  int grid = total < kNumSMs ? total : kNumSMs;
-  const int quota = (int)ceil_div(total, grid);
-  grid = (int)ceil_div(total, quota);
-  kern<<<grid, kThreads, Cfg::SMEM, stream>>>(map_x, h, pq, total, quota, w_t, bias, ln_g, ln_b, out);
+  const int max_groups = kNumSMs / CS;  // one CTA (or CTA pair) per SM (pair)
+  int groups = total < max_groups ? total : max_groups;
+  const int quota = (int)ceil_div(total, groups);
+  groups = (int)ceil_div(total, quota);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(groups * CS));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg::SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CNB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, map_x, h, pq, total, quota, w_t, bias, ln_g, ln_b, out));
   CNB_LAUNCH_OK();
   return 0;
 }
@@ -288,8 +336,9 @@ int launch_t(const float* x, int batch, int h, const float* w_t, const float* bi
 template <typename OutT>
 int launch_dwconv_ln_tma(const float* x, int batch, int h, int w, int c, const float* w_t, const float* bias,
                          const float* ln_g, const float* ln_b, OutT* out, cudaStream_t stream) {
-  if (c == 96 && w == 56) return launch_t<96, 56, 28, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
-  if (c == 192 && w == 28) return launch_t<192, 28, 14, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
+  if (c == 96 && w == 56) return launch_t<96, 1, 56, 28, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
+  if (c == 192 && w == 28) return launch_t<192, 1, 28, 14, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
+  if (c == 384 && w == 14) return launch_t<192, 2, 14, 14, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
   return 1;
 }
 template int launch_dwconv_ln_tma<float>(const float*, int, int, int, int, const float*, const float*, const float*,

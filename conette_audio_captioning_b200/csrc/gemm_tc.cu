@@ -372,14 +372,14 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t c
   return 0;
 }
 
-// 4-D NHWC fp32 activation (C fastest), box = (C, box_w, 1, 1), no swizzle, zero fill outside the image: one TMA op brings
+// 4-D NHWC fp32 activation (C fastest), box = (box_c, box_w, 1, 1), no swizzle, zero fill outside the image: one TMA op brings
 // one haloed row strip of the depthwise-conv ring (dwconv_ring.cu); negative / overshooting coordinates are the padding
-int tc_make_map_nhwc_f32(void* map_out, const float* ptr, int batch, int h, int w, int c, int box_w) {
+int tc_make_map_nhwc_f32(void* map_out, const float* ptr, int batch, int h, int w, int c, int box_c, int box_w) {
   CNB_REQUIRE(g_encode != nullptr, "gemm_tc_init() was not called");
-  CNB_REQUIRE(c <= 256 && box_w <= 256 && c % 4 == 0, "NHWC tensor map: box dimensions out of range");
+  CNB_REQUIRE(box_c <= 256 && box_c <= c && box_w <= 256 && box_c % 4 == 0, "NHWC tensor map: box dimensions out of range");
   const cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
   const cuuint64_t strides[3] = {(cuuint64_t)c * 4, (cuuint64_t)w * c * 4, (cuuint64_t)h * w * c * 4};
-  const cuuint32_t box[4] = {(cuuint32_t)c, (cuuint32_t)box_w, 1, 1};
+  const cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, 1, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = g_encode(reinterpret_cast<CUtensorMap*>(map_out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(ptr),
                         dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,

@@ -74,8 +74,8 @@ int gemm_tc_init();  // resolves cuTensorMapEncodeTiled; returns 0 on success
 // 2-D row-major (rows, cols) tensor map into map_out (a 128-byte CUtensorMap): box = (box_rows, 128 bytes), 128B swizzle
 int tc_make_map(void* map_out, const void* ptr, int64_t rows, int64_t cols, int box_rows, int elt_bytes);
 
-// 4-D NHWC fp32 tensor map, box (C, box_w, 1, 1), no swizzle, zero OOB fill (used by the depthwise-conv ring loader)
-int tc_make_map_nhwc_f32(void* map_out, const float* ptr, int batch, int h, int w, int c, int box_w);
+// 4-D NHWC fp32 tensor map, box (box_c, box_w, 1, 1), no swizzle, zero OOB fill (used by the depthwise-conv ring loader)
+int tc_make_map_nhwc_f32(void* map_out, const float* ptr, int batch, int h, int w, int c, int box_c, int box_w);
 // TMA-ring depthwise 7x7 + LayerNorm (dwconv_ring.cu); returns 1 when (C, W) has no instantiation (caller falls back)
 template <typename OutT>
 int launch_dwconv_ln_tma(const float* x, int batch, int h, int w, int c, const float* w_t, const float* bias,
