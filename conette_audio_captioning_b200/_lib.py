@@ -48,6 +48,7 @@ SIGNATURES = {
     "cnb_load_weight": (C.c_int, [_vp, C.c_char_p, _vp, _i32, _i32, C.POINTER(_i64)]),
     "cnb_finalize_weights": (C.c_int, [_vp]),
     "cnb_geometry": (C.c_int, [_i64, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
+    "cnb_resample": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
     "cnb_frontend": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _vp, _vp]),
     "cnb_encoder": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _vp]),
     "cnb_encoder_tap": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _i32, _vp, _i64, _vp]),

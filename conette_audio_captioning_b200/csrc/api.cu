@@ -25,6 +25,7 @@ constexpr int kDepths[4] = {3, 3, 9, 3};
 constexpr int kStageW[4] = {56, 28, 14, 7};
 constexpr int kMels = 224, kBins = 513, kNfft = 1024, kHop = 320;
 constexpr int kD = 256, kFF = 2048, kLayers = 6, kTags = 527;
+constexpr int kDefaultMlpSlabMB = 0;  // see encode_chunk: MLP row slabs sized to keep the hidden activations in L2
 constexpr int kDefaultChunk = 64;  // measured on B200: larger encoder passes amortise tails; 64 x 10 s needs ~3.5 GB
 
 struct HostTensor {
@@ -100,6 +101,13 @@ struct cnb_handle {
   cudaStream_t stream = nullptr;  // library-owned non-blocking stream (graph capture / replay, host-API copies)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<DecGraph> dec_graphs;
+  // host-buffer path (cnb_caption_host): sliced H2D on a copy stream overlapping the front-end + stem of earlier slices
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_slice[8] = {};
+  cudaEvent_t ev_lens = nullptr;         // the last H2D copy out of pin_lens
+  int32_t* pin_lens = nullptr;           // pinned staging for the per-clip frame counts
+  int pin_lens_cap = 0;
+  bool pre_stem_done = false;            // encode_chunk: the "logmel" / "xa" workspaces already hold this chunk's stem output
   // optional per-kernel-class timing (cnb_profile_begin/end): CUDA event pairs around every launch
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_events;  // pool, pairs (start, stop)
@@ -474,6 +482,15 @@ int mlp_gemm<__nv_bfloat16>(cnb_handle* h, const __nv_bfloat16* a, const float*,
   return launch_gemm_tc<float>(a, wbf, m, n, k, epi, ep, reinterpret_cast<float*>(out), ldo, st);
 }
 
+// bytes of MLP hidden activations per row slab (0 = whole chunk at once); CNB_MLP_SLAB_MB overrides the default
+static int64_t mlp_slab_bytes() {
+  static const int64_t v = [] {
+    const char* e = getenv("CNB_MLP_SLAB_MB");
+    return (int64_t)(e ? atoi(e) : kDefaultMlpSlabMB) << 20;
+  }();
+  return v;
+}
+
 // encode `nb` clips (nb <= chunk) starting at wav; writes frame_embs (nb, T', 768) and optionally clip probs
 template <typename ActT>
 static int encode_chunk(cnb_handle* h, const float* wav, int nb, int64_t n, float* frame_embs, float* clip_probs, Tap* tap,
@@ -486,9 +503,11 @@ static int encode_chunk(cnb_handle* h, const float* wav, int nb, int64_t n, floa
   WS(h, "y", ActT, (size_t)nb * p0 * kDims[0], y);
   WS(h, "hid", ActT, (size_t)nb * p0 * kDims[0] * 4, hid);
 
-  { Prof _p(h, CNB_K_FRONTEND, st); if (int rc = launch_frontend(wav, nb, n, h->fe, true, logmel, st)) return rc; }
-  if (tap && tap->kind == CNB_TAP_LOGMEL_BN) return copy_tap(tap, logmel, (int64_t)nb * g.t * kMels, false, st);
-  { Prof _p(h, CNB_K_STEM, st); if (int rc = launch_stem(logmel, nb, g.t, g.h[0], h->stem_w_t, h->stem_b, h->stem_ln_g, h->stem_ln_b, xa, st)) return rc; }
+  if (!h->pre_stem_done) {
+    { Prof _p(h, CNB_K_FRONTEND, st); if (int rc = launch_frontend(wav, nb, n, h->fe, true, logmel, st)) return rc; }
+    if (tap && tap->kind == CNB_TAP_LOGMEL_BN) return copy_tap(tap, logmel, (int64_t)nb * g.t * kMels, false, st);
+    { Prof _p(h, CNB_K_STEM, st); if (int rc = launch_stem(logmel, nb, g.t, g.h[0], h->stem_w_t, h->stem_b, h->stem_ln_g, h->stem_ln_b, xa, st)) return rc; }
+  }
   if (tap && tap->kind == CNB_TAP_STEM) return copy_tap(tap, xa, (int64_t)nb * p0 * kDims[0], false, st);
 
   float* x = xa;
@@ -514,14 +533,26 @@ static int encode_chunk(cnb_handle* h, const float* wav, int nb, int64_t n, floa
       { Prof _p(h, CNB_K_DWLN_S0 + s, st); if (int rc = launch_dwconv_ln<ActT>(x, nb, hh, ww, c, b.dw_w_t, b.dw_b, b.ln_g, b.ln_b, y, st)) return rc; }
       if (tap && tap->kind == CNB_TAP_DWLN && tap->stage == s && tap->block == j)
         return copy_tap(tap, y, (int64_t)m * c, sizeof(ActT) == 2, st);
-      EpiParams e1;
-      e1.bias = b.b1;
-      { Prof _p(h, CNB_K_GEMM_PW1_S0 + s, st); if (int rc = mlp_gemm<ActT>(h, y, b.w1, b.w1_bf, m, 4 * c, c, EPI_BIAS_GELU, e1, hid, true, 4 * c, st)) return rc; }
-      EpiParams e2;
-      e2.bias = b.b2;
-      e2.scale = b.scale;
-      e2.resid = x;
-      { Prof _p(h, CNB_K_GEMM_PW2_S0 + s, st); if (int rc = mlp_gemm<ActT>(h, hid, b.w2, b.w2_bf, m, c, 4 * c, EPI_SCALE_RESID, e2, x, false, c, st)) return rc; }
+      // The MLP runs in row slabs whose hidden activations (slab x 4C) fit the L2: pw1 writes them, pw2 reads them back and
+      // every slab reuses the SAME hidden buffer, so the dirty lines are overwritten in L2 instead of travelling to HBM and
+      // back (stage 1: 693 MB written + 693 MB read per block otherwise).  Slabs are multiples of the 128-row GEMM tile.
+      int64_t slab = m;
+      if (sizeof(ActT) == 2 && mlp_slab_bytes() > 0) {
+        const int64_t rows_fit = mlp_slab_bytes() / ((int64_t)4 * c * sizeof(ActT));
+        const int64_t n_slab = ceil_div(m, rows_fit > 128 ? rows_fit : 128);
+        slab = ceil_div(ceil_div(m, n_slab), 128) * 128;
+      }
+      for (int64_t m0 = 0; m0 < m; m0 += slab) {
+        const int mm = (int)std::min<int64_t>(slab, m - m0);
+        EpiParams e1;
+        e1.bias = b.b1;
+        { Prof _p(h, CNB_K_GEMM_PW1_S0 + s, st); if (int rc = mlp_gemm<ActT>(h, y + m0 * c, b.w1, b.w1_bf, mm, 4 * c, c, EPI_BIAS_GELU, e1, hid, true, 4 * c, st)) return rc; }
+        EpiParams e2;
+        e2.bias = b.b2;
+        e2.scale = b.scale;
+        e2.resid = x + m0 * c;
+        { Prof _p(h, CNB_K_GEMM_PW2_S0 + s, st); if (int rc = mlp_gemm<ActT>(h, hid, b.w2, b.w2_bf, mm, c, 4 * c, EPI_SCALE_RESID, e2, x + m0 * c, false, c, st)) return rc; }
+      }
       if (tap && tap->kind == CNB_TAP_BLOCK && tap->stage == s && tap->block == j)
         return copy_tap(tap, x, (int64_t)m * c, false, st);
     }
@@ -967,6 +998,11 @@ int cnb_destroy(cnb_handle* h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (auto& e : h->ev_slice)
+    if (e) cudaEventDestroy(e);
+  if (h->pin_lens) cudaFreeHost(h->pin_lens);
+  if (h->ev_lens) cudaEventDestroy(h->ev_lens);
   delete h;
   return 0;
 }
@@ -1009,6 +1045,16 @@ static int check_audio(int32_t batch, int64_t n) {
   CNB_REQUIRE(geometry(n).h[0] >= 8, "padded batch shorter than 7360 samples: the last 2x2 downsample has no input row "
                                      "(the reference raises RuntimeError here too)");
   return 0;
+}
+
+int cnb_resample(cnb_handle* h, const float* wav_in, const int64_t* lens_in, int32_t batch, int64_t n_in, const float* taps,
+                 const int32_t* tap_lo, int32_t orig_freq, int32_t new_freq, int32_t n_taps, int32_t width, float* wav_out,
+                 int64_t n_out, void* stream) {
+  CHECK_READY(h);
+  CNB_REQUIRE(wav_in && taps && tap_lo && wav_out, "null buffer");
+  CNB_REQUIRE(batch > 0 && n_in > 0 && n_out > 0, "bad audio shape");
+  return launch_resample(wav_in, batch, n_in, lens_in, taps, tap_lo, orig_freq, new_freq, n_taps, width, wav_out, n_out,
+                         (cudaStream_t)stream);
 }
 
 int cnb_frontend(cnb_handle* h, const float* wav, int32_t batch, int64_t n, int32_t apply_bn, float* out, void* stream) {
@@ -1098,10 +1144,24 @@ int cnb_caption(cnb_handle* h, const float* wav, const int64_t* x_lens_host, con
   cudaStream_t st = (cudaStream_t)stream;
   WS(h, "frame_embs", float, (size_t)batch * g.tp * 768, fe);
   WS(h, "lens", int32_t, batch, lens);
-  std::vector<int32_t> lens_h;
-  frame_lens_host(x_lens_host, batch, n, &lens_h);
-  CNB_CUDA_OK(cudaMemcpyAsync(lens, lens_h.data(), batch * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  CNB_CUDA_OK(cudaStreamSynchronize(st));  // lens_h is a stack-lifetime pageable buffer
+  // frame counts go through a handle-owned pinned buffer: no host synchronisation between the copy and the launches.  The
+  // buffer is reused by the next call, whose first write happens after this call's work has been enqueued on `st`; calls
+  // that do not end with a synchronisation (device-buffer API) therefore wait for the previous copy first.
+  if (h->pin_lens_cap < batch) {
+    CNB_CUDA_OK(cudaStreamSynchronize(st));
+    if (h->pin_lens) cudaFreeHost(h->pin_lens);
+    CNB_CUDA_OK(cudaMallocHost(&h->pin_lens, sizeof(int32_t) * (size_t)batch));
+    h->pin_lens_cap = batch;
+  }
+  if (!h->ev_lens) CNB_CUDA_OK(cudaEventCreateWithFlags(&h->ev_lens, cudaEventDisableTiming));
+  CNB_CUDA_OK(cudaEventSynchronize(h->ev_lens));  // returns at once when nothing was recorded yet
+  {
+    std::vector<int32_t> lens_h;
+    frame_lens_host(x_lens_host, batch, n, &lens_h);
+    memcpy(h->pin_lens, lens_h.data(), sizeof(int32_t) * (size_t)batch);
+  }
+  CNB_CUDA_OK(cudaMemcpyAsync(lens, h->pin_lens, batch * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CNB_CUDA_OK(cudaEventRecord(h->ev_lens, st));
   if (int rc = encode(h, wav, batch, n, fe, clip_probs, st)) return rc;
   return decode(h, fe, lens, bos_ids, forbid, batch, g.tp, beam, min_len, max_len, preds, lprobs, mult_preds, mult_lprobs,
                 info, st);
@@ -1127,12 +1187,42 @@ int cnb_caption_host(cnb_handle* h, const float* wav_host, const int64_t* x_lens
   WS(h, "io_mlprobs", float, rows, mlprobs);
   WS(h, "io_info", int32_t, 2 + batch, info);
   WS(h, "io_clip", float, (size_t)batch * kTags, clip);
-  CNB_CUDA_OK(cudaMemcpyAsync(wav, wav_host, (size_t)batch * n * sizeof(float), cudaMemcpyHostToDevice, st));
   CNB_CUDA_OK(cudaMemcpyAsync(bos, bos_ids_host, batch * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   if (forbid_host) CNB_CUDA_OK(cudaMemcpyAsync(forbid, forbid_host, V, cudaMemcpyHostToDevice, st));
-  if (int rc = cnb_caption(h, wav, x_lens_host, bos, forbid_host ? forbid : nullptr, batch, n, beam, min_len, max_len, preds,
-                           lprobs, mpreds, mlprobs, info, clip_probs_host ? clip : nullptr, st))
-    return rc;
+  // Waveforms travel in up to 8 slices on a copy stream; the front-end and the stem of slice i run while slice i+1 is still
+  // on the PCIe bus (both are per-clip kernels), so only the copy itself stays exposed.  One encoder chunk only.
+  const int n_slices = (batch <= chunk_size(h) && batch >= 16 && !h->prof_on) ? 8 : 1;
+  if (n_slices > 1) {
+    const Geometry g = geometry(n);
+    if (!h->copy_stream) CNB_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : h->ev_slice)
+      if (!e) CNB_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    WS(h, "logmel", float, (size_t)batch * g.t * kMels, logmel);
+    WS(h, "xa", float, (size_t)batch * g.h[0] * kStageW[0] * kDims[0], xa);
+    // the copy stream must not overwrite io_wav while the previous call's front-end may still read it (stream order on st)
+    CNB_CUDA_OK(cudaEventRecord(h->ev_fork, st));
+    CNB_CUDA_OK(cudaStreamWaitEvent(h->copy_stream, h->ev_fork, 0));
+    const int per = (int)ceil_div(batch, n_slices);
+    for (int i = 0, b0 = 0; b0 < batch; ++i, b0 += per) {
+      const int nb = std::min(per, batch - b0);
+      CNB_CUDA_OK(cudaMemcpyAsync(wav + (int64_t)b0 * n, wav_host + (int64_t)b0 * n, (size_t)nb * n * sizeof(float),
+                                  cudaMemcpyHostToDevice, h->copy_stream));
+      CNB_CUDA_OK(cudaEventRecord(h->ev_slice[i], h->copy_stream));
+      CNB_CUDA_OK(cudaStreamWaitEvent(st, h->ev_slice[i], 0));
+      float* lm = logmel + (int64_t)b0 * g.t * kMels;
+      if (int rc = launch_frontend(wav + (int64_t)b0 * n, nb, n, h->fe, true, lm, st)) return rc;
+      if (int rc = launch_stem(lm, nb, g.t, g.h[0], h->stem_w_t, h->stem_b, h->stem_ln_g, h->stem_ln_b,
+                               xa + (int64_t)b0 * g.h[0] * kStageW[0] * kDims[0], st))
+        return rc;
+    }
+    h->pre_stem_done = true;
+  } else {
+    CNB_CUDA_OK(cudaMemcpyAsync(wav, wav_host, (size_t)batch * n * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  const int rc_cap = cnb_caption(h, wav, x_lens_host, bos, forbid_host ? forbid : nullptr, batch, n, beam, min_len, max_len,
+                                 preds, lprobs, mpreds, mlprobs, info, clip_probs_host ? clip : nullptr, st);
+  h->pre_stem_done = false;
+  if (rc_cap) return rc_cap;
   CNB_CUDA_OK(cudaMemcpyAsync(preds_host, preds, (size_t)batch * max_len * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   CNB_CUDA_OK(cudaMemcpyAsync(lprobs_host, lprobs, batch * sizeof(float), cudaMemcpyDeviceToHost, st));
   CNB_CUDA_OK(cudaMemcpyAsync(mult_preds_host, mpreds, (size_t)rows * max_len * sizeof(int64_t), cudaMemcpyDeviceToHost, st));

@@ -13,6 +13,36 @@ namespace cnb {
 
 constexpr float kLnEps = 1e-6f;
 
+// Sum 16 per-lane values across the warp with 16 shuffles: afterwards lane l holds the total of value
+// idx(l) = 8*bit4(l) + 4*bit3(l) + 2*bit2(l) + bit1(l)  (lanes l and l^1 hold the same value).
+__device__ __forceinline__ float warp_sum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const bool up = lane & 16;
+    const float keep = up ? v[k + 8] : v[k], send = up ? v[k] : v[k + 8];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool up = lane & 8;
+    const float keep = up ? v[k + 4] : v[k], send = up ? v[k] : v[k + 4];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const bool up = lane & 4;
+    const float keep = up ? v[k + 2] : v[k], send = up ? v[k] : v[k + 2];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const bool up = lane & 2;
+    const float keep = up ? v[1] : v[0], send = up ? v[0] : v[1];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+
 // =====================================================================================================================
 // K-STEM: one CTA per output row (b, h): 56 pixels x 96 channels; 8 warps x 7 pixels, lane owns channels l, l+32, l+64
 // =====================================================================================================================
@@ -41,31 +71,48 @@ stem_kernel(const float* __restrict__ lm, int n_frames, int h1, const float* __r
     be[j] = ln_b[c];
   }
   __syncthreads();
-  // 8 warps x 7 pixels = one output row of 56 pixels; kStemRows rows per CTA
+  // 8 warps x 7 pixels = one output row of 56 pixels; kStemRows rows per CTA.  The kernel is issue-bound, not HBM-bound
+  // (~150 instructions per pixel per warp in the first version), so the LayerNorm statistics of a warp's 7 pixels go
+  // through ONE 16-value butterfly (7 sums | 7 sums of squares: 16 shuffles instead of 70) and the normalisation is folded
+  // into one FMA per value.
   for (int rr = 0; rr < kStemRows; ++rr) {
     const int h = h0 + rr;
     if (h >= h1) break;
+    float acc[7][3];
 #pragma unroll
     for (int p = 0; p < 7; ++p) {
-      const int wpx = warp * 7 + p;
-      float acc[3] = {bia[0], bia[1], bia[2]};
+      acc[p][0] = bia[0], acc[p][1] = bia[1], acc[p][2] = bia[2];
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        const float4 v = *reinterpret_cast<const float4*>(&s_in[rr * 4 + r][4 * wpx]);
+        const float4 v = *reinterpret_cast<const float4*>(&s_in[rr * 4 + r][4 * (warp * 7 + p)]);
         const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int j = 0; j < 3; ++j) acc[j] = fmaf(vv[c], w[r * 4 + c][j], acc[j]);
+          for (int j = 0; j < 3; ++j) acc[p][j] = fmaf(vv[c], w[r * 4 + c][j], acc[p][j]);
       }
-      const float mean = warp_sum(acc[0] + acc[1] + acc[2]) * (1.f / 96.f);
-      const float d0 = acc[0] - mean, d1 = acc[1] - mean, d2 = acc[2] - mean;
-      const float var = warp_sum(d0 * d0 + d1 * d1 + d2 * d2) * (1.f / 96.f);
-      const float rstd = 1.f / sqrtf(var + kLnEps);
-      float* o = out + (((int64_t)b * h1 + h) * 56 + wpx) * 96;
-      o[lane] = d0 * rstd * g[0] + be[0];
-      o[lane + 32] = d1 * rstd * g[1] + be[1];
-      o[lane + 64] = d2 * rstd * g[2] + be[2];
+    }
+    float st[16];
+#pragma unroll
+    for (int p = 0; p < 7; ++p) {
+      st[p] = (acc[p][0] + acc[p][1]) + acc[p][2];
+      st[p + 8] = fmaf(acc[p][0], acc[p][0], fmaf(acc[p][1], acc[p][1], acc[p][2] * acc[p][2]));
+    }
+    st[7] = st[15] = 0.f;
+    const float tot = warp_sum16(st, lane);  // lane l holds value (l >> 1) & 15: sums 0..6 | squares 8..14
+    float* o = out + (((int64_t)b * h1 + h) * 56 + warp * 7) * 96;
+#pragma unroll
+    for (int p = 0; p < 7; ++p) {
+      const float s1 = __shfl_sync(0xffffffffu, tot, 2 * p);
+      const float s2 = __shfl_sync(0xffffffffu, tot, 2 * (p + 8));
+      const float mean = s1 * (1.f / 96.f);
+      const float var = fmaxf(fmaf(s2, 1.f / 96.f, -mean * mean), 0.f);
+      const float rstd = rsqrtf(var + kLnEps);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float a = rstd * g[j];
+        o[p * 96 + lane + 32 * j] = fmaf(acc[p][j], a, fmaf(-mean, a, be[j]));
+      }
     }
   }
 }
@@ -186,35 +233,6 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, b
   const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem);
   const int bytes = valid ? 16 : 0;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem), "r"(bytes) : "memory");
-}
-
-// Sum 16 per-lane values across the warp with 16 shuffles: afterwards lane l holds the total of value
-// idx(l) = 8*bit4(l) + 4*bit3(l) + 2*bit2(l) + bit1(l)  (lanes l and l^1 hold the same value).
-__device__ __forceinline__ float warp_sum16(float (&v)[16], int lane) {
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const bool up = lane & 16;
-    const float keep = up ? v[k + 8] : v[k], send = up ? v[k] : v[k + 8];
-    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const bool up = lane & 8;
-    const float keep = up ? v[k + 4] : v[k], send = up ? v[k] : v[k + 4];
-    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const bool up = lane & 4;
-    const float keep = up ? v[k + 2] : v[k], send = up ? v[k] : v[k + 2];
-    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  {
-    const bool up = lane & 2;
-    const float keep = up ? v[1] : v[0], send = up ? v[0] : v[1];
-    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
 template <int C, int W, int TW, typename OutT>
@@ -445,46 +463,80 @@ ln_pack2x2_kernel(const float* __restrict__ x, int batch, int H, int W, const fl
       be[i] = *reinterpret_cast<const float4*>(ln_b + 4 * q);
     }
   }
-  for (int64_t pix = warp_id; pix < n_pix; pix += n_warps) {
-    // enumerate only the pixels that are used: (b, h < 2*Ho, w < 2*Wo); odd trailing row / column dropped (floor)
-    const int wq = (int)(pix % (2 * Wo));
-    const int hq = (int)((pix / (2 * Wo)) % (2 * Ho));
-    const int b = (int)(pix / ((int64_t)2 * Wo * 2 * Ho));
-    const float* px = x + (((int64_t)b * H + hq) * W + wq) * C;
-    float4 v[NV];
-    float s = 0.f;
+  // U pixels per warp iteration: all their loads are issued before the first reduction, so a warp keeps U x C x 4 bytes in
+  // flight (one pixel per warp left the kernel latency-bound at 38 % of the HBM rate)
+  constexpr int U = 4;
+  for (int64_t pix0 = warp_id * U; pix0 < n_pix; pix0 += n_warps * U) {
+    float4 v[U][NV];
+    const float* px[U];
+    OutT* o[U];
+    float s[U];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int q = lane + 32 * i;
-      v[i] = (q < C / 4) ? *reinterpret_cast<const float4*>(px + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    for (int u = 0; u < U; ++u) {
+      // enumerate only the pixels that are used: (b, h < 2*Ho, w < 2*Wo); odd trailing row / column dropped (floor)
+      const int64_t pix = pix0 + u < n_pix ? pix0 + u : n_pix - 1;
+      const int wq = (int)(pix % (2 * Wo));
+      const int hq = (int)((pix / (2 * Wo)) % (2 * Ho));
+      const int b = (int)(pix / ((int64_t)2 * Wo * 2 * Ho));
+      px[u] = x + (((int64_t)b * H + hq) * W + wq) * C;
+      const int64_t row = ((int64_t)b * Ho + hq / 2) * Wo + wq / 2;
+      o[u] = out + row * (4 * (int64_t)C) + ((hq & 1) * 2 + (wq & 1)) * C;
     }
-    const float mean = warp_sum(s) * (1.f / C);
-    float qq = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      if (lane + 32 * i < C / 4) {
-        const float dx = v[i].x - mean, dy = v[i].y - mean, dz = v[i].z - mean, dw = v[i].w - mean;
-        qq += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int q = lane + 32 * i;
+        v[u][i] = (q < C / 4) ? __ldg(reinterpret_cast<const float4*>(px[u] + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    const float rstd = 1.f / sqrtf(warp_sum(qq) * (1.f / C) + kLnEps);
-    const int64_t row = ((int64_t)b * Ho + hq / 2) * Wo + wq / 2;
-    OutT* o = out + row * (4 * (int64_t)C) + ((hq & 1) * 2 + (wq & 1)) * C;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int q = lane + 32 * i;
-      if (q < C / 4) {
-        const float y0 = (v[i].x - mean) * rstd * g[i].x + be[i].x, y1 = (v[i].y - mean) * rstd * g[i].y + be[i].y;
-        const float y2 = (v[i].z - mean) * rstd * g[i].z + be[i].z, y3 = (v[i].w - mean) * rstd * g[i].w + be[i].w;
-        if constexpr (sizeof(OutT) == 2) {
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(y0, y1), p1 = __floats2bfloat162_rn(y2, y3);
-          uint2 u;
-          u.x = *reinterpret_cast<uint32_t*>(&p0);
-          u.y = *reinterpret_cast<uint32_t*>(&p1);
-          *reinterpret_cast<uint2*>(o + 4 * q) = u;
-        } else {
-          *reinterpret_cast<float4*>(o + 4 * q) = make_float4(y0, y1, y2, y3);
+    for (int u = 0; u < U; ++u) {
+      s[u] = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) s[u] += (v[u][i].x + v[u][i].y) + (v[u][i].z + v[u][i].w);
+    }
+#pragma unroll
+    for (int ofs = 16; ofs > 0; ofs >>= 1)
+#pragma unroll
+      for (int u = 0; u < U; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], ofs);
+    float mean[U], qq[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      mean[u] = s[u] * (1.f / C);
+      qq[u] = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (lane + 32 * i < C / 4) {
+          const float dx = v[u][i].x - mean[u], dy = v[u][i].y - mean[u], dz = v[u][i].z - mean[u], dw = v[u][i].w - mean[u];
+          qq[u] += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+        }
+      }
+    }
+#pragma unroll
+    for (int ofs = 16; ofs > 0; ofs >>= 1)
+#pragma unroll
+      for (int u = 0; u < U; ++u) qq[u] += __shfl_xor_sync(0xffffffffu, qq[u], ofs);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (pix0 + u >= n_pix) break;
+      const float rstd = 1.f / sqrtf(qq[u] * (1.f / C) + kLnEps);
+      const float m = mean[u];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int q = lane + 32 * i;
+        if (q < C / 4) {
+          const float y0 = (v[u][i].x - m) * rstd * g[i].x + be[i].x, y1 = (v[u][i].y - m) * rstd * g[i].y + be[i].y;
+          const float y2 = (v[u][i].z - m) * rstd * g[i].z + be[i].z, y3 = (v[u][i].w - m) * rstd * g[i].w + be[i].w;
+          if constexpr (sizeof(OutT) == 2) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(y0, y1), p1 = __floats2bfloat162_rn(y2, y3);
+            uint2 w2;
+            w2.x = *reinterpret_cast<uint32_t*>(&p0);
+            w2.y = *reinterpret_cast<uint32_t*>(&p1);
+            *reinterpret_cast<uint2*>(o[u] + 4 * q) = w2;
+          } else {
+            *reinterpret_cast<float4*>(o[u] + 4 * q) = make_float4(y0, y1, y2, y3);
+          }
         }
       }
     }
@@ -495,7 +547,7 @@ template <typename OutT>
 int launch_ln_pack2x2(const float* x, int batch, int h, int w, int c, const float* ln_g, const float* ln_b, OutT* out,
                       cudaStream_t stream) {
   const int64_t n_pix = (int64_t)batch * (h / 2) * 2 * (w / 2) * 2;
-  const int blocks = (int)std::min<int64_t>(ceil_div(n_pix, 8), (int64_t)kNumSMs * 16);
+  const int blocks = (int)std::min<int64_t>(ceil_div(n_pix, 8 * 4), (int64_t)kNumSMs * 8);
   if (c == 96) ln_pack2x2_kernel<96, OutT><<<blocks, 256, 0, stream>>>(x, batch, h, w, ln_g, ln_b, out);
   else if (c == 192) ln_pack2x2_kernel<192, OutT><<<blocks, 256, 0, stream>>>(x, batch, h, w, ln_g, ln_b, out);
   else if (c == 384) ln_pack2x2_kernel<384, OutT><<<blocks, 256, 0, stream>>>(x, batch, h, w, ln_g, ln_b, out);

@@ -13,6 +13,9 @@
 // the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_ptx.cuh"
@@ -357,7 +360,43 @@ int tc_make_map(void* map_out, const void* ptr, int64_t rows, int64_t cols, int 
   CNB_REQUIRE(g_encode != nullptr, "gemm_tc_init() was not called");
   return make_map(reinterpret_cast<CUtensorMap*>(map_out), ptr, (uint64_t)rows, (uint64_t)cols, (uint32_t)box_rows, elt_bytes);
 }
+// Encoding a tensor map costs a few microseconds of host time; the encoder launches ~100 GEMMs per pass over a handful of
+// (pointer, shape) combinations, so encoded maps are memoised (host launches must stay ahead of ~15 us kernels).
+struct MapKey {
+  const void* ptr;
+  uint64_t rows, cols;
+  uint32_t box_rows;
+  int elt;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && box_rows == o.box_rows && elt == o.elt;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    h = h * 1000003u ^ std::hash<uint64_t>()(k.rows);
+    h = h * 1000003u ^ std::hash<uint64_t>()(k.cols);
+    h = h * 1000003u ^ std::hash<uint64_t>()(((uint64_t)k.box_rows << 8) | (uint64_t)k.elt);
+    return h;
+  }
+};
+static int make_map_uncached(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, int elt_bytes);
 static int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, int elt_bytes) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  const MapKey key{ptr, rows, cols, box_rows, elt_bytes};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *map = it->second;
+    return 0;
+  }
+  if (int rc = make_map_uncached(map, ptr, rows, cols, box_rows, elt_bytes)) return rc;
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, *map);
+  return 0;
+}
+static int make_map_uncached(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, int elt_bytes) {
   const cuuint64_t dims[2] = {cols, rows};
   const cuuint64_t strides[1] = {cols * (uint64_t)elt_bytes};
   const cuuint32_t box[2] = {(cuuint32_t)(128 / elt_bytes), box_rows};

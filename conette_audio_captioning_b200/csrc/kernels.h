@@ -21,6 +21,11 @@ struct FrontendParams {
 int launch_frontend(const float* wav, int batch, int64_t n_samples, const FrontendParams& p, bool apply_bn, float* out,
                     cudaStream_t stream);
 
+// ---- polyphase resampler (input side of the boundary) ----------------------------------------------
+// taps (new, n_taps) compact filter bank, lo (new) first dense column of every phase; lens_in device (B) or null
+int launch_resample(const float* x, int batch, int64_t n_in, const int64_t* lens_in, const float* taps, const int* lo, int orig,
+                    int nw, int n_taps, int width, float* out, int64_t n_out, cudaStream_t stream);
+
 // ---- stem: Conv2d(1,96,4x4,s4,pad(4,0)) + LayerNorm(channels_first) -> NHWC f32 --------------------------------------
 int launch_stem(const float* logmel_bn, int batch, int n_frames, int h1, const float* w_t /*(16,96)*/, const float* bias,
                 const float* ln_g, const float* ln_b, float* out, cudaStream_t stream);

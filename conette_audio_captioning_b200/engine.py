@@ -63,6 +63,7 @@ class Engine:
             shape = (C.c_int64 * max(t.ndim, 1))(*t.shape)
             _lib.check(self.lib.cnb_load_weight(self.handle, name.encode(), t.data_ptr(), dtype_code[t.dtype], t.ndim, shape))
         _lib.check(self.lib.cnb_finalize_weights(self.handle))
+        self._banks: Dict[Tuple[int, int], Tuple[Tensor, Tensor, int]] = {}  # resampler filter banks on the device
 
     def close(self) -> None:
         if getattr(self, "handle", None):
@@ -100,6 +101,32 @@ class Engine:
         return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(_lib.KERNEL_CLASSES)}
 
     # ---- stages -------------------------------------------------------------------------------------------------------
+    def resample(self, wav: Tensor, orig_sr: int, lens: Optional[Tensor] = None, new_sr: int = 32_000,
+                 n_out: Optional[int] = None) -> Tuple[Tensor, Tensor]:
+        """(B, N_in) f32 at ``orig_sr`` -> (B, N_out) f32 at ``new_sr`` on the GPU, plus the resampled lengths (B,) i64 (host).
+
+        Mirrors ``torchaudio.functional.resample`` as the reference calls it (preprocessor.py:139-141); with ``lens`` (true
+        lengths of right-zero-padded clips) every clip equals its own resample followed by right zero-padding."""
+        from . import resample as rs
+
+        wav = self._dev(wav, torch.float32)
+        b, n_in = wav.shape
+        orig, new = rs.reduced_ratio(orig_sr, new_sr)
+        lens_h = torch.full((b,), n_in, dtype=torch.int64) if lens is None else lens.to("cpu", torch.int64)
+        out_lens = torch.tensor([rs.resampled_length(int(n), orig, new) for n in lens_h.tolist()], dtype=torch.int64)
+        if n_out is None:
+            n_out = int(out_lens.max())
+        key = (orig, new)
+        if key not in self._banks:
+            taps, lo, width = rs.filter_bank(orig, new)
+            self._banks[key] = (taps.to(self.device), lo.to(self.device), width)
+        taps, lo, width = self._banks[key]
+        lens_d = None if lens is None else lens_h.to(self.device)
+        out = torch.empty(b, n_out, device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.cnb_resample(self.handle, wav.data_ptr(), _ptr(lens_d), b, n_in, taps.data_ptr(), lo.data_ptr(),
+                                         orig, new, taps.shape[1], width, out.data_ptr(), n_out, self._stream()))
+        return out, out_lens
+
     def frontend(self, wav: Tensor, apply_bn: bool = True) -> Tensor:
         """(B, N) f32 -> (B, T, 224) log-mel [dB], optionally through bn0."""
         wav = self._dev(wav, torch.float32)

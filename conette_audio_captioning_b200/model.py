@@ -89,7 +89,7 @@ class CoNeTTEModel:
         forbid_rep_mode: Optional[str] = None,
     ) -> Dict[str, Any]:
         if preprocess:
-            wav, x_lens = load_resample(x, sr, x_shapes)
+            wav, x_lens = load_resample(x, sr, x_shapes, resampler=self.engine.resample)
             bsize = wav.shape[0]
         else:
             assert isinstance(x, Tensor) and isinstance(x_shapes, Tensor)
@@ -120,9 +120,12 @@ class CoNeTTEModel:
         assert min_len >= 0
         forbid = self._forbid_mask(forbid_rep_mode)
 
-        if preprocess:
+        if preprocess and wav.device.type == "cpu":
             preds, lprobs, mult_preds, mult_lprobs, clip_probs = self.engine.caption_host(
                 wav, x_lens, bos_ids, forbid, beam, min_len, max_len, with_tags=True)
+        elif preprocess:  # resampled on the GPU: the batch is already device-resident
+            preds, lprobs, mult_preds, mult_lprobs, clip_probs = (
+                t.cpu() for t in self.engine.caption(wav, x_lens, bos_ids, forbid, beam, min_len, max_len, with_tags=True))
         else:
             lens = x_shapes[:, 1].to(torch.int32)  # FrameIdentEncoder: lens = audio_shape[:, 1] (nn/encoders/ident.py:14-34)
             preds, lprobs, mult_preds, mult_lprobs = (

@@ -64,6 +64,18 @@ int cnb_finalize_weights(cnb_handle* h);
 /* Output geometry for a padded batch of n_samples: STFT frames T, ConvNeXt stage heights, output frames T'. */
 int cnb_geometry(int64_t n_samples, int32_t* n_stft_frames, int32_t stage_heights[4], int32_t* n_out_frames);
 
+/* S0 input side: polyphase sinc resampler, wav_in (B, n_in) f32 at orig_freq -> wav_out (B, n_out) f32 at
+ * new_freq; replaces torchaudio.functional.resample as called by the reference at
+ * src/conette/huggingface/preprocessor.py:139-141 (sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99).
+ * orig_freq / new_freq are already divided by their gcd.  taps (new_freq, n_taps) f32 = the non-zero support of every phase
+ * of the reference's filter bank, tap_lo (new_freq) i32 = first dense column of that support, width = the bank's
+ * half-width (dense bank = 2 * width + orig_freq columns; tap_lo[p] + n_taps <= that).  lens_in (B) i64 DEVICE true input
+ * lengths or NULL (= n_in): samples at or beyond ceil(new * len / orig) are written as 0, i.e. the result equals
+ * per-clip resampling followed by the reference's right zero-padding (nn/functional/pad.py:11-17). */
+int cnb_resample(cnb_handle* h, const float* wav_in, const int64_t* lens_in, int32_t batch, int64_t n_in, const float* taps,
+                 const int32_t* tap_lo, int32_t orig_freq, int32_t new_freq, int32_t n_taps, int32_t width, float* wav_out,
+                 int64_t n_out, void* stream);
+
 /* S1a front-end: wav (B, N) f32 -> log-mel (B, T, 224) f32, optionally through eval BatchNorm (bn0). */
 int cnb_frontend(cnb_handle* h, const float* wav, int32_t batch, int64_t n_samples, int32_t apply_bn, float* logmel_out,
                  void* stream);

@@ -27,6 +27,41 @@ PAD_ID, BOS_ID, EOS_ID, UNK_ID = 0, 1, 2, 3  # reference tokenization/constants.
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# input side: resample
+# ---------------------------------------------------------------------------------------------------------------------
+def resample(wav: Tensor, orig_sr: int, new_sr: int = 32_000) -> Tensor:
+    """Restatement of ``torchaudio.functional.resample`` (torchaudio==0.13.1 pinned in the reference's requirements.txt:11,
+    NOT under /root/reference; call site huggingface/preprocessor.py:139-141; defaults sinc_interp_hann,
+    lowpass_filter_width=6, rolloff=0.99).  Published algorithm: one windowed-sinc FIR per output phase (``new`` phases after
+    dividing both rates by their gcd), applied as a strided conv1d over the input zero-padded by (width, width + orig), output
+    cut to ceil(new * len / orig).  Pinned against the torchaudio installed in the dev container by
+    tests/test_resample.py (bit-identical filter bank, outputs to fp32 summation order).  wav: (..., N) f32."""
+    g = math.gcd(int(orig_sr), int(new_sr))
+    orig, new = int(orig_sr) // g, int(new_sr) // g
+    if orig == new:
+        return wav
+    lpw, rolloff = 6, 0.99
+    base_freq = min(orig, new) * rolloff
+    width = math.ceil(lpw * orig / base_freq)
+    # functional.resample passes dtype=waveform.dtype, so the whole bank is evaluated in float32
+    idx = torch.arange(-width, width + orig, dtype=torch.float32)[None, None] / orig
+    t = torch.arange(0, -new, -1, dtype=torch.float32)[:, None, None] / new + idx
+    t *= base_freq
+    t = t.clamp_(-lpw, lpw)
+    window = torch.cos(t * math.pi / lpw / 2) ** 2
+    t *= math.pi
+    kernels = torch.where(t == 0, torch.tensor(1.0).to(t), t.sin() / t)
+    kernels *= window * (base_freq / orig)
+    shape = wav.shape
+    x = wav.reshape(-1, shape[-1]).float()
+    n = x.shape[-1]
+    x = F.pad(x, (width, width + orig))
+    y = F.conv1d(x[:, None], kernels, stride=orig).transpose(1, 2).reshape(x.shape[0], -1)
+    y = y[:, : (new * n + orig - 1) // orig]
+    return y.reshape(shape[:-1] + y.shape[-1:])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # geometry
 # ---------------------------------------------------------------------------------------------------------------------
 def n_stft_frames(n_samples: int) -> int:
