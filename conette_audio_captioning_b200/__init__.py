@@ -14,6 +14,10 @@ def __getattr__(name):
         from .model import CoNeTTEModel
 
         return CoNeTTEModel
+    if name in ("conette", "main_predict"):
+        from . import predict
+
+        return getattr(predict, name)
     if name in ("Engine",):
         from .engine import Engine
 

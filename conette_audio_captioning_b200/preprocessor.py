@@ -23,9 +23,9 @@ TARGET_SR = 32_000
 
 
 def _load(path: str) -> Tuple[Tensor, int]:
-    import torchaudio
+    from .audio_io import load_audio
 
-    return torchaudio.load(path)  # type: ignore[return-value]
+    return load_audio(path)
 
 
 def _is_iterable_str(x) -> bool:

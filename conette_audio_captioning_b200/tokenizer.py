@@ -74,8 +74,45 @@ class IdTokenizer:
     def decode_batch(self, sentences: Iterable[Iterable[int]]) -> List[str]:
         return [self._normalize(" ".join(self.itos[int(t)] for t in sent)) for sent in sentences]
 
+    # ---- batched fast path ---------------------------------------------------------------------
+    # With ~12 ms of GPU time per 64-clip batch the regex pipeline above (3.6 ms for 64 + 192 sentences) is a visible part
+    # of a captioning call.  For a sentence whose tokens are all "plain" (lower-case, none of the characters any normaliser
+    # looks at) or one of the four special tokens, the normalisers reduce to "drop the specials, join with one space":
+    # that is done with one vectorised table gather for the whole id tensor.  Any other sentence takes the regex path.
+    def _tables(self):
+        if getattr(self, "_tab", None) is None:
+            import numpy as np
+
+            plain = re.compile(r"^[a-z0-9_]+$")
+            skip = np.array([t in SPECIAL_TOKENS for t in self.itos], dtype=bool)
+            ok = np.array([bool(plain.match(t)) for t in self.itos], dtype=bool) | skip
+            self._tab = (np.array(self.itos, dtype=object), skip, ok)
+        return self._tab
+
+    def decode_tensor(self, ids: torch.Tensor) -> Union[str, list]:
+        """(..., L) integer tensor -> nested lists of sentences, identical to ``decode_rec`` on the same ids."""
+        import numpy as np
+
+        itos_np, skip, ok = self._tables()
+        arr = ids.detach().cpu().numpy()
+        flat = arr.reshape(-1, arr.shape[-1]) if arr.ndim > 1 else arr.reshape(1, -1)
+        toks = itos_np[flat]
+        keep = ~skip[flat]
+        fast = ok[flat].all(axis=1)
+        out: List[str] = []
+        for r in range(flat.shape[0]):
+            if fast[r]:
+                out.append(" ".join(toks[r][keep[r]]))
+            else:
+                out.append(self._normalize(" ".join(toks[r])))
+        res = np.empty(len(out), dtype=object)
+        res[:] = out
+        return res.reshape(arr.shape[:-1]).tolist() if arr.ndim > 1 else out[0]
+
     def decode_rec(self, nested: Union[torch.Tensor, list]) -> Union[str, list]:
         if isinstance(nested, torch.Tensor):
+            if nested.ndim >= 1 and nested.shape[-1] > 0 and not nested.is_floating_point():
+                return self.decode_tensor(nested)
             nested = nested.tolist()
         if len(nested) > 0 and not isinstance(nested[0], (list, tuple)):
             return self.decode_batch([nested])[0]

@@ -104,3 +104,24 @@ def test_forbid_mask_modes():
     assert not m[itos.index("the")] and m[itos.index("w3")] and m[itos.index("<bos_clotho>")]
     with pytest.raises(ValueError):
         synth.make_forbid_rep_mask(itos, "bogus")
+
+
+def test_batched_detokenise_equals_the_regex_pipeline():
+    """the vectorised id -> text path must give exactly what the normaliser chain gives
+    (reference aac_tokenizer.py:197-209, :327-388; normalizers.py:160-188), for plain and for awkward vocabularies."""
+    from conette_audio_captioning_b200 import synth
+    from conette_audio_captioning_b200.tokenizer import IdTokenizer
+
+    g = torch.Generator().manual_seed(0)
+    tok = IdTokenizer(synth.make_itos(500))
+    ids = torch.randint(0, tok.get_vocab_size(), (64, 3, 20), generator=g)
+    ids[:, :, 15:] = 0
+    ids[:, :, 14] = 2
+    assert tok.decode_rec(ids) == tok.decode_rec(ids.tolist())
+    assert tok.decode_rec(ids[:, 0]) == tok.decode_rec(ids[:, 0].tolist())
+    assert tok.decode_rec(ids[3, 1]) == tok.decode_rec(ids[3, 1].tolist())
+    odd = IdTokenizer(["<pad>", "<bos>", "<eos>", "<unk>", "rain", ",", ".", "well-known", "-", "it's", "'", "Dog", "a", "!",
+                       "<bos_clotho>", "x y"])
+    ids = torch.randint(0, odd.get_vocab_size(), (400, 12), generator=g)
+    assert odd.decode_rec(ids) == odd.decode_rec(ids.tolist())
+    assert odd.decode_rec(torch.tensor([[4, 2, 0, 0]])) == ["rain"] and odd.decode_rec(torch.tensor([[0, 0]])) == [""]
