@@ -178,6 +178,31 @@ def test_encoder_taps_parity(eng_parity, oracle_taps):
             assert rel_l2(got, _nhwc(taps[f"block.{s}.{b}"])) < 2e-4, f"block {s}.{b}"
 
 
+@pytest.mark.parametrize("b,n", [(1, 7360), (3, 33000), (5, 100000), (2, 960000)])
+def test_dwconv_ln_shapes(small_sd, b, n):
+    """The TMA-ring depthwise conv + LayerNorm at other geometries than the 1.5 s fixture: the shortest clip the reference
+    accepts (stage heights 6/3/1/0 ... rows below one row quad), heights that are not multiples of 4, more work units than one
+    CTA range, 30 s clips (H = 752/376/188); first and last block of stages 1-3 against the oracle (fp32 mode)."""
+    from conette_audio_captioning_b200 import _lib
+    from conette_audio_captioning_b200.engine import Engine
+    from oracle import restate
+
+    wav = synth.make_audio(b, n, seed=40 + b)[:, 0].contiguous()
+    taps = {}
+    restate.encoder(small_sd, wav, None, taps)
+    eng = Engine(small_sd, vocab_size=small_sd["model.decoder.classifier.weight"].shape[0], precision="parity", enc_chunk=8)
+    try:
+        for s, blk in ((0, 0), (0, 2), (1, 0), (1, 2), (2, 0), (2, 8), (3, 1)):
+            ref = taps[f"dwln.{s}.{blk}"]
+            if ref.numel() == 0:
+                continue
+            got = eng.encoder_tap(wav, _lib.TAP_DWLN, s, blk).cpu()
+            assert got.shape == ref.shape
+            assert rel_l2(got, ref) < 2e-4, f"dwln {s}.{blk} at b={b} n={n}"
+    finally:
+        eng.close()
+
+
 def test_encoder_outputs_parity(eng_parity, oracle_taps):
     wav, _, _, out = oracle_taps
     fe, clip = eng_parity.encoder(wav)
