@@ -104,6 +104,9 @@ struct cnb_handle {
   // host-buffer path (cnb_caption_host): sliced H2D on a copy stream overlapping the front-end + stem of earlier slices
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_slice[8] = {};
+  cudaEvent_t host_done[2] = {};         // cnb_caption_host_begin/end: completion of the batch that used staging slot i
+  bool host_pending[2] = {false, false};
+  int host_next = 0;
   cudaEvent_t ev_lens = nullptr;         // the last H2D copy out of pin_lens
   int32_t* pin_lens = nullptr;           // pinned staging for the per-clip frame counts
   int pin_lens_cap = 0;
@@ -1001,6 +1004,8 @@ int cnb_destroy(cnb_handle* h) {
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (auto& e : h->ev_slice)
     if (e) cudaEventDestroy(e);
+  for (auto& e : h->host_done)
+    if (e) cudaEventDestroy(e);
   if (h->pin_lens) cudaFreeHost(h->pin_lens);
   if (h->ev_lens) cudaEventDestroy(h->ev_lens);
   delete h;
@@ -1167,30 +1172,41 @@ int cnb_caption(cnb_handle* h, const float* wav, const int64_t* x_lens_host, con
                 info, st);
 }
 
-int cnb_caption_host(cnb_handle* h, const float* wav_host, const int64_t* x_lens_host, const int64_t* bos_ids_host,
-                     const uint8_t* forbid_host, int32_t batch, int64_t n, int32_t beam, int32_t min_len, int32_t max_len,
-                     int64_t* preds_host, float* lprobs_host, int64_t* mult_preds_host, float* mult_lprobs_host,
-                     int32_t* info_host, float* clip_probs_host) {
+int cnb_caption_host_begin(cnb_handle* h, const float* wav_host, const int64_t* x_lens_host, const int64_t* bos_ids_host,
+                           const uint8_t* forbid_host, int32_t batch, int64_t n, int32_t beam, int32_t min_len, int32_t max_len,
+                           int64_t* preds_host, float* lprobs_host, int64_t* mult_preds_host, float* mult_lprobs_host,
+                           int32_t* info_host, float* clip_probs_host, int32_t* ticket_out) {
   CHECK_READY(h);
-  CNB_REQUIRE(wav_host && bos_ids_host && preds_host && lprobs_host && mult_preds_host && mult_lprobs_host && info_host,
+  CNB_REQUIRE(wav_host && bos_ids_host && preds_host && lprobs_host && mult_preds_host && mult_lprobs_host && info_host &&
+                  ticket_out,
               "null buffer");
   if (int rc = check_audio(batch, n)) return rc;
   const int V = h->cfg.vocab_size;
   const int rows = batch * beam;
   cudaStream_t st = h->stream;
-  WS(h, "io_wav", float, (size_t)batch * n, wav);
-  WS(h, "io_bos", int64_t, batch, bos);
-  WS(h, "io_forbid", uint8_t, V, forbid);
-  WS(h, "io_preds", int64_t, (size_t)batch * max_len, preds);
-  WS(h, "io_lprobs", float, batch, lprobs);
-  WS(h, "io_mpreds", int64_t, (size_t)rows * max_len, mpreds);
-  WS(h, "io_mlprobs", float, rows, mlprobs);
-  WS(h, "io_info", int32_t, 2 + batch, info);
-  WS(h, "io_clip", float, (size_t)batch * kTags, clip);
+  // two sets of staging buffers: the H2D copy of batch i+1 (copy stream) runs while batch i computes on `st`
+  const int slot = h->host_next;
+  h->host_next ^= 1;
+  if (!h->host_done[slot]) CNB_CUDA_OK(cudaEventCreateWithFlags(&h->host_done[slot], cudaEventDisableTiming));
+  if (h->host_pending[slot]) {  // the caller never collected the batch that used this slot: its buffers are still in use
+    CNB_CUDA_OK(cudaEventSynchronize(h->host_done[slot]));
+    h->host_pending[slot] = false;
+  }
+  const std::string sfx = slot ? ".1" : ".0";
+  WS(h, ("io_wav" + sfx).c_str(), float, (size_t)batch * n, wav);
+  WS(h, ("io_bos" + sfx).c_str(), int64_t, batch, bos);
+  WS(h, ("io_forbid" + sfx).c_str(), uint8_t, V, forbid);
+  WS(h, ("io_preds" + sfx).c_str(), int64_t, (size_t)batch * max_len, preds);
+  WS(h, ("io_lprobs" + sfx).c_str(), float, batch, lprobs);
+  WS(h, ("io_mpreds" + sfx).c_str(), int64_t, (size_t)rows * max_len, mpreds);
+  WS(h, ("io_mlprobs" + sfx).c_str(), float, rows, mlprobs);
+  WS(h, ("io_info" + sfx).c_str(), int32_t, 2 + batch, info);
+  WS(h, ("io_clip" + sfx).c_str(), float, (size_t)batch * kTags, clip);
   CNB_CUDA_OK(cudaMemcpyAsync(bos, bos_ids_host, batch * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   if (forbid_host) CNB_CUDA_OK(cudaMemcpyAsync(forbid, forbid_host, V, cudaMemcpyHostToDevice, st));
   // Waveforms travel in up to 8 slices on a copy stream; the front-end and the stem of slice i run while slice i+1 is still
-  // on the PCIe bus (both are per-clip kernels), so only the copy itself stays exposed.  One encoder chunk only.
+  // on the PCIe bus (both are per-clip kernels).  The copy stream does not wait for `st`: this slot's previous user has
+  // completed (event above), so with two batches in flight the whole copy hides behind the other batch's compute.
   const int n_slices = (batch <= chunk_size(h) && batch >= 16 && !h->prof_on) ? 8 : 1;
   if (n_slices > 1) {
     const Geometry g = geometry(n);
@@ -1199,9 +1215,6 @@ int cnb_caption_host(cnb_handle* h, const float* wav_host, const int64_t* x_lens
       if (!e) CNB_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     WS(h, "logmel", float, (size_t)batch * g.t * kMels, logmel);
     WS(h, "xa", float, (size_t)batch * g.h[0] * kStageW[0] * kDims[0], xa);
-    // the copy stream must not overwrite io_wav while the previous call's front-end may still read it (stream order on st)
-    CNB_CUDA_OK(cudaEventRecord(h->ev_fork, st));
-    CNB_CUDA_OK(cudaStreamWaitEvent(h->copy_stream, h->ev_fork, 0));
     const int per = (int)ceil_div(batch, n_slices);
     for (int i = 0, b0 = 0; b0 < batch; ++i, b0 += per) {
       const int nb = std::min(per, batch - b0);
@@ -1230,8 +1243,31 @@ int cnb_caption_host(cnb_handle* h, const float* wav_host, const int64_t* x_lens
   CNB_CUDA_OK(cudaMemcpyAsync(info_host, info, (2 + batch) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   if (clip_probs_host)
     CNB_CUDA_OK(cudaMemcpyAsync(clip_probs_host, clip, (size_t)batch * kTags * sizeof(float), cudaMemcpyDeviceToHost, st));
-  CNB_CUDA_OK(cudaStreamSynchronize(st));
+  CNB_CUDA_OK(cudaEventRecord(h->host_done[slot], st));
+  h->host_pending[slot] = true;
+  *ticket_out = slot;
   return 0;
+}
+
+int cnb_caption_host_end(cnb_handle* h, int32_t ticket) {
+  CHECK_READY(h);
+  CNB_REQUIRE(ticket == 0 || ticket == 1, "unknown ticket");
+  CNB_REQUIRE(h->host_pending[ticket], "no batch in flight for this ticket");
+  CNB_CUDA_OK(cudaEventSynchronize(h->host_done[ticket]));
+  h->host_pending[ticket] = false;
+  return 0;
+}
+
+int cnb_caption_host(cnb_handle* h, const float* wav_host, const int64_t* x_lens_host, const int64_t* bos_ids_host,
+                     const uint8_t* forbid_host, int32_t batch, int64_t n, int32_t beam, int32_t min_len, int32_t max_len,
+                     int64_t* preds_host, float* lprobs_host, int64_t* mult_preds_host, float* mult_lprobs_host,
+                     int32_t* info_host, float* clip_probs_host) {
+  int32_t ticket = -1;
+  if (int rc = cnb_caption_host_begin(h, wav_host, x_lens_host, bos_ids_host, forbid_host, batch, n, beam, min_len, max_len,
+                                      preds_host, lprobs_host, mult_preds_host, mult_lprobs_host, info_host, clip_probs_host,
+                                      &ticket))
+    return rc;
+  return cnb_caption_host_end(h, ticket);
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {

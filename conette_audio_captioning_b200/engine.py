@@ -252,6 +252,32 @@ class Engine:
                                                             out["mult_lprobs"], out["info"])
         return preds, lprobs, mult_preds, mult_lprobs, clip
 
+    def caption_host_begin(self, wav: Tensor, x_lens: Optional[Tensor], bos_ids: Tensor, forbid_mask: Optional[Tensor],
+                           beam: int = 3, min_len: int = 3, max_len: int = 20, with_tags: bool = True,
+                           out: Optional[dict] = None) -> dict:
+        """Split-phase ``caption_host``: enqueue one batch and return a ticket; up to two batches may be in flight, so the H2D
+        copy of the next batch overlaps this batch's compute.  ``caption_host_end(ticket)`` returns what ``caption_host`` does."""
+        assert wav.device.type == "cpu" and wav.dtype == torch.float32 and wav.is_contiguous()
+        b, n = wav.shape
+        keep = dict(wav=wav, bos=bos_ids.to("cpu", torch.int64).contiguous(),
+                    forbid=None if forbid_mask is None else forbid_mask.to("cpu", torch.uint8).contiguous(),
+                    xl=None if x_lens is None else x_lens.to("cpu", torch.int64).contiguous(),
+                    out=out if out is not None else self.alloc_host_outputs(b, beam, max_len, with_tags))
+        o = keep["out"]
+        ticket = C.c_int32(-1)
+        _lib.check(self.lib.cnb_caption_host_begin(
+            self.handle, wav.data_ptr(), _ptr(keep["xl"]), keep["bos"].data_ptr(), _ptr(keep["forbid"]), b, n, beam, min_len,
+            max_len, o["preds"].data_ptr(), o["lprobs"].data_ptr(), o["mult_preds"].data_ptr(), o["mult_lprobs"].data_ptr(),
+            o["info"].data_ptr(), _ptr(o.get("clip_probs")), C.byref(ticket)))
+        keep["ticket"] = ticket.value  # `keep` holds the host tensors alive until the batch has been collected
+        return keep
+
+    def caption_host_end(self, ticket: dict):
+        _lib.check(self.lib.cnb_caption_host_end(self.handle, ticket["ticket"]))
+        o = ticket["out"]
+        preds, lprobs, mult_preds, mult_lprobs = self._trim(o["preds"], o["lprobs"], o["mult_preds"], o["mult_lprobs"], o["info"])
+        return preds, lprobs, mult_preds, mult_lprobs, o.get("clip_probs")
+
     @staticmethod
     def alloc_host_outputs(b: int, beam: int, max_len: int, with_tags: bool = True) -> dict:
         pin = dict(pin_memory=True)

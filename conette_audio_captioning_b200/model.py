@@ -148,3 +148,52 @@ class CoNeTTEModel:
         return outs
 
     forward = __call__
+
+    # ---- streaming (dataset captioning / serving) --------------------------------------------------------------------------
+    def stream(self, batches: Iterable[Any], sr: Union[None, int, Iterable[int]] = None, task: Union[str, List[str], None] = None,
+               threshold: Union[float, Tensor] = 0.3, **kwargs: Any) -> Iterable[Dict[str, Any]]:
+        """Caption an iterable of batches (each one anything ``__call__`` accepts as ``x``) and yield one output dict per
+        batch, identical to ``self(x, ...)``.  Two batches are in flight: while the GPU works on batch i the host loads /
+        pads batch i+1, its H2D copy runs on the copy stream, and batch i-1 is detokenised -- the call a user makes to caption a
+        dataset (reference predict.py:209 passes the whole file list at once)."""
+        pending = None
+        for x in batches:
+            nxt = self._begin(x, sr, task, **kwargs)
+            if pending is not None:
+                yield self._finish(pending, threshold)
+            pending = nxt
+        if pending is not None:
+            yield self._finish(pending, threshold)
+
+    def _begin(self, x, sr, task, beam_size=None, min_pred_size=None, max_pred_size=None, forbid_rep_mode=None):
+        wav, x_lens = load_resample(x, sr, None, resampler=self.engine.resample)
+        bsize = wav.shape[0]
+        tasks = [self.default_task] * bsize if task is None else ([task] * bsize if isinstance(task, str) else list(task))
+        if len(tasks) != bsize:
+            raise ValueError(f"Invalid number of tasks with input. (found {len(tasks)} tasks but {bsize} elements)")
+        for t in tasks:
+            if t not in self.config.task_names:
+                raise ValueError(f"Invalid argument tasks={tasks}. (task {t} is not in {self.config.task_names})")
+        parts = [t.split("_") for t in tasks]
+        bos_ids = self._task_token_ids([p[0] for p in parts], ["_".join(p[1:]) if len(p) >= 2 else None for p in parts])
+        beam = self.config.beam_size if beam_size is None else beam_size
+        min_len = self.config.min_pred_size if min_pred_size is None else min_pred_size
+        max_len = self.config.max_pred_size if max_pred_size is None else max_pred_size
+        assert beam > 0 and min_len >= 0
+        forbid = self._forbid_mask(forbid_rep_mode)
+        if wav.device.type == "cpu":
+            return ("host", self.engine.caption_host_begin(wav, x_lens, bos_ids, forbid, beam, min_len, max_len, with_tags=True), tasks)
+        return ("dev", self.engine.caption(wav, x_lens, bos_ids, forbid, beam, min_len, max_len, with_tags=True), tasks)
+
+    def _finish(self, pending, threshold) -> Dict[str, Any]:
+        kind, ticket, tasks = pending
+        if kind == "host":
+            preds, lprobs, mult_preds, mult_lprobs, clip_probs = self.engine.caption_host_end(ticket)
+        else:
+            preds, lprobs, mult_preds, mult_lprobs, clip_probs = (t.cpu() for t in ticket)
+        outs: Dict[str, Any] = {"cands": self.tokenizer.decode_rec(preds), "preds": preds, "lprobs": lprobs,
+                                "mult_cands": self.tokenizer.decode_rec(mult_preds), "mult_preds": mult_preds,
+                                "mult_lprobs": mult_lprobs, "tasks": tasks, "tags_probs": clip_probs}
+        hot = clip_probs >= threshold
+        outs["tags"] = [[self.audioset_idx_to_name[int(i)] for i in row.nonzero().flatten().tolist()] for row in hot]
+        return outs

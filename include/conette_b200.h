@@ -113,6 +113,16 @@ int cnb_caption_host(cnb_handle* h, const float* wav_host, const int64_t* x_lens
                      const uint8_t* forbid_mask_host, int32_t batch, int64_t n_samples, int32_t beam, int32_t min_len,
                      int32_t max_len, int64_t* preds_out_host, float* lprobs_out_host, int64_t* mult_preds_out_host,
                      float* mult_lprobs_out_host, int32_t* info_out_host, float* clip_probs_out_host);
+/* Split-phase form of cnb_caption_host for callers that stream batches (dataset captioning as conette-predict does over a
+ * file list, serving): _begin enqueues the H2D copies, the whole path and the D2H copies and returns a ticket, _end blocks
+ * until that batch's outputs are in its host buffers.  Two batches may be in flight, so the H2D copy of batch i+1 overlaps
+ * the compute of batch i; results are identical to cnb_caption_host.  Host buffers must stay valid (pinned, for real
+ * overlap) until _end; calling _begin a third time without _end first waits for the oldest batch. */
+int cnb_caption_host_begin(cnb_handle* h, const float* wav_host, const int64_t* x_lens_host, const int64_t* bos_ids_host,
+                           const uint8_t* forbid_mask_host, int32_t batch, int64_t n_samples, int32_t beam, int32_t min_len,
+                           int32_t max_len, int64_t* preds_host, float* lprobs_host, int64_t* mult_preds_host,
+                           float* mult_lprobs_host, int32_t* info_host, float* clip_probs_host, int32_t* ticket_out);
+int cnb_caption_host_end(cnb_handle* h, int32_t ticket);
 
 /* Test hook: one GEMM with a fused epilogue, out (M,N) f32 = epi(A (M,K) f32 x W (N,K) f32 ^T). epi: 0 bias, 1 bias+GELU,
  * 2 bias+ReLU, 3 resid + scale*(acc+bias).  use_tc=1 runs the bf16 tcgen05 kernel (operands rounded to bf16 first;

@@ -1,0 +1,65 @@
+"""Split-phase host API (cnb_caption_host_begin/_end) and CoNeTTEModel.stream: two batches in flight must give exactly what
+one blocking call per batch gives."""
+import pytest
+import torch
+
+from conette_audio_captioning_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return synth.make_state_dict(seed=1234, n_words=300, eos_bias=3.0)
+
+
+def test_begin_end_equals_blocking_call(sd):
+    from conette_audio_captioning_b200.engine import Engine
+
+    eng = Engine(sd, sd["model.decoder.classifier.weight"].shape[0], precision="fast")
+    try:
+        forbid = sd["model.forbid_rep_mask"]
+        batches = []
+        for i, (b, n) in enumerate([(16, 48000), (20, 64000), (3, 32000), (16, 48000), (17, 40000)]):
+            wav = synth.make_audio(b, n, seed=50 + i)[:, 0].contiguous().pin_memory()
+            lens = torch.randint(n // 2, n + 1, (b,), generator=torch.Generator().manual_seed(i))
+            bos = sd["model.task_id_to_token_id"][torch.randint(0, 7, (b,), generator=torch.Generator().manual_seed(i))]
+            batches.append((wav, lens, bos))
+        want = [eng.caption_host(w, l, bos, forbid, 3, 3, 20) for w, l, bos in batches]
+        got, ticket = [], None
+        for w, l, bos in batches:  # begin(i+1) before end(i)
+            nxt = eng.caption_host_begin(w, l, bos, forbid, 3, 3, 20)
+            if ticket is not None:
+                got.append(eng.caption_host_end(ticket))
+            ticket = nxt
+        got.append(eng.caption_host_end(ticket))
+        for a, c in zip(want, got):
+            for x, y in zip(a, c):
+                assert torch.equal(x, y)
+        with pytest.raises(Exception):
+            eng.caption_host_end(ticket)  # already collected
+        # three begins without an end: the oldest batch is waited for internally, results stay right
+        t = [eng.caption_host_begin(*batches[i][:3], forbid, 3, 3, 20) for i in range(3)]
+        for i in (1, 2):
+            for x, y in zip(want[i], eng.caption_host_end(t[i])):
+                assert torch.equal(x, y)
+    finally:
+        eng.close()
+
+
+def test_model_stream_equals_calls(sd):
+    from conette_audio_captioning_b200 import CoNeTTEModel
+
+    model = CoNeTTEModel(None, sd, synth.make_itos(300), precision="parity")
+    try:
+        xs = [synth.make_audio(b, n, seed=70 + i) for i, (b, n) in enumerate([(2, 32000), (16, 40000), (1, 50000)])]
+        want = [model(x, sr=32000, task="audiocaps") for x in xs]
+        got = list(model.stream(xs, sr=32000, task="audiocaps"))
+        assert len(got) == len(want)
+        for a, c in zip(want, got):
+            assert a["cands"] == c["cands"] and a["mult_cands"] == c["mult_cands"] and a["tasks"] == c["tasks"]
+            assert torch.equal(a["preds"], c["preds"]) and torch.equal(a["mult_preds"], c["mult_preds"])
+            assert torch.equal(a["lprobs"], c["lprobs"]) and torch.equal(a["tags_probs"], c["tags_probs"]) and a["tags"] == c["tags"]
+        assert list(model.stream([])) == []
+    finally:
+        model.engine.close()
