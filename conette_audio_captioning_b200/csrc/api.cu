@@ -104,6 +104,8 @@ struct cnb_handle {
   // host-buffer path (cnb_caption_host): sliced H2D on a copy stream overlapping the front-end + stem of earlier slices
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_slice[8] = {};
+  cudaStream_t dec_stream = nullptr;     // high-priority stream of the decode half when two batches are in flight
+  cudaEvent_t ev_enc[2] = {};            // encoder of the batch in slot i has finished (decode may start)
   cudaEvent_t host_done[2] = {};         // cnb_caption_host_begin/end: completion of the batch that used staging slot i
   bool host_pending[2] = {false, false};
   int host_next = 0;
@@ -1006,6 +1008,9 @@ int cnb_destroy(cnb_handle* h) {
     if (e) cudaEventDestroy(e);
   for (auto& e : h->host_done)
     if (e) cudaEventDestroy(e);
+  for (auto& e : h->ev_enc)
+    if (e) cudaEventDestroy(e);
+  if (h->dec_stream) cudaStreamDestroy(h->dec_stream);
   if (h->pin_lens) cudaFreeHost(h->pin_lens);
   if (h->ev_lens) cudaEventDestroy(h->ev_lens);
   delete h;
@@ -1138,17 +1143,21 @@ int cnb_decoder_logits(cnb_handle* h, const float* frame_embs, const int32_t* le
   return 0;
 }
 
-int cnb_caption(cnb_handle* h, const float* wav, const int64_t* x_lens_host, const int64_t* bos_ids, const uint8_t* forbid,
-                int32_t batch, int64_t n, int32_t beam, int32_t min_len, int32_t max_len, int64_t* preds, float* lprobs,
-                int64_t* mult_preds, float* mult_lprobs, int32_t* info, float* clip_probs, void* stream) {
+// Encoder on `st`, projection + beam search on `st_dec` (the same stream, or the handle's high-priority decode stream when the
+// split-phase host API keeps two batches in flight: then batch i decodes -- a latency-bound kernel that leaves most of every
+// SM idle and 44 SMs untouched -- while batch i+1 is already being encoded).  `slot` selects the frame-embedding buffers,
+// which must outlive the encoder of the following batch in that case.
+static int caption_impl(cnb_handle* h, const float* wav, const int64_t* x_lens_host, const int64_t* bos_ids, const uint8_t* forbid,
+                        int32_t batch, int64_t n, int32_t beam, int32_t min_len, int32_t max_len, int64_t* preds, float* lprobs,
+                        int64_t* mult_preds, float* mult_lprobs, int32_t* info, float* clip_probs, cudaStream_t st,
+                        cudaStream_t st_dec, int slot) {
   CHECK_READY(h);
   CNB_REQUIRE(wav && bos_ids && preds && lprobs && mult_preds && mult_lprobs && info, "null buffer");
   if (int rc = check_audio(batch, n)) return rc;
   const Geometry g = geometry(n);
   if (int rc = check_decode(h, batch, g.tp, beam, min_len, max_len)) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
-  WS(h, "frame_embs", float, (size_t)batch * g.tp * 768, fe);
-  WS(h, "lens", int32_t, batch, lens);
+  WS(h, slot ? "frame_embs.1" : "frame_embs", float, (size_t)batch * g.tp * 768, fe);
+  WS(h, slot ? "lens.1" : "lens", int32_t, batch, lens);
   // frame counts go through a handle-owned pinned buffer: no host synchronisation between the copy and the launches.  The
   // buffer is reused by the next call, whose first write happens after this call's work has been enqueued on `st`; calls
   // that do not end with a synchronisation (device-buffer API) therefore wait for the previous copy first.
@@ -1168,8 +1177,20 @@ int cnb_caption(cnb_handle* h, const float* wav, const int64_t* x_lens_host, con
   CNB_CUDA_OK(cudaMemcpyAsync(lens, h->pin_lens, batch * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   CNB_CUDA_OK(cudaEventRecord(h->ev_lens, st));
   if (int rc = encode(h, wav, batch, n, fe, clip_probs, st)) return rc;
+  if (st_dec != st) {
+    if (!h->ev_enc[slot]) CNB_CUDA_OK(cudaEventCreateWithFlags(&h->ev_enc[slot], cudaEventDisableTiming));
+    CNB_CUDA_OK(cudaEventRecord(h->ev_enc[slot], st));
+    CNB_CUDA_OK(cudaStreamWaitEvent(st_dec, h->ev_enc[slot], 0));
+  }
   return decode(h, fe, lens, bos_ids, forbid, batch, g.tp, beam, min_len, max_len, preds, lprobs, mult_preds, mult_lprobs,
-                info, st);
+                info, st_dec);
+}
+
+int cnb_caption(cnb_handle* h, const float* wav, const int64_t* x_lens_host, const int64_t* bos_ids, const uint8_t* forbid,
+                int32_t batch, int64_t n, int32_t beam, int32_t min_len, int32_t max_len, int64_t* preds, float* lprobs,
+                int64_t* mult_preds, float* mult_lprobs, int32_t* info, float* clip_probs, void* stream) {
+  return caption_impl(h, wav, x_lens_host, bos_ids, forbid, batch, n, beam, min_len, max_len, preds, lprobs, mult_preds,
+                      mult_lprobs, info, clip_probs, (cudaStream_t)stream, (cudaStream_t)stream, 0);
 }
 
 int cnb_caption_host_begin(cnb_handle* h, const float* wav_host, const int64_t* x_lens_host, const int64_t* bos_ids_host,
@@ -1202,12 +1223,21 @@ int cnb_caption_host_begin(cnb_handle* h, const float* wav_host, const int64_t* 
   WS(h, ("io_mlprobs" + sfx).c_str(), float, rows, mlprobs);
   WS(h, ("io_info" + sfx).c_str(), int32_t, 2 + batch, info);
   WS(h, ("io_clip" + sfx).c_str(), float, (size_t)batch * kTags, clip);
-  CNB_CUDA_OK(cudaMemcpyAsync(bos, bos_ids_host, batch * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-  if (forbid_host) CNB_CUDA_OK(cudaMemcpyAsync(forbid, forbid_host, V, cudaMemcpyHostToDevice, st));
+  CNB_CUDA_OK(cudaMemcpyAsync(bos, bos_ids_host, batch * sizeof(int64_t), cudaMemcpyDefault, st));
+  if (forbid_host) CNB_CUDA_OK(cudaMemcpyAsync(forbid, forbid_host, V, cudaMemcpyDefault, st));
+  // `wav_host` may also be DEVICE memory (batches that are already resident, e.g. produced by cnb_resample): it is then used in
+  // place and must stay untouched until _end.
+  bool wav_on_device = false;
+  {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, wav_host) == cudaSuccess) wav_on_device = attr.type == cudaMemoryTypeDevice;
+    else cudaGetLastError();  // plain pageable host memory on old drivers: not an error
+  }
+  if (wav_on_device) wav = const_cast<float*>(wav_host);
   // Waveforms travel in up to 8 slices on a copy stream; the front-end and the stem of slice i run while slice i+1 is still
   // on the PCIe bus (both are per-clip kernels).  The copy stream does not wait for `st`: this slot's previous user has
   // completed (event above), so with two batches in flight the whole copy hides behind the other batch's compute.
-  const int n_slices = (batch <= chunk_size(h) && batch >= 16 && !h->prof_on) ? 8 : 1;
+  const int n_slices = (batch <= chunk_size(h) && batch >= 16 && !h->prof_on && !wav_on_device) ? 8 : 1;
   if (n_slices > 1) {
     const Geometry g = geometry(n);
     if (!h->copy_stream) CNB_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -1229,21 +1259,32 @@ int cnb_caption_host_begin(cnb_handle* h, const float* wav_host, const int64_t* 
         return rc;
     }
     h->pre_stem_done = true;
-  } else {
+  } else if (!wav_on_device) {
     CNB_CUDA_OK(cudaMemcpyAsync(wav, wav_host, (size_t)batch * n * sizeof(float), cudaMemcpyHostToDevice, st));
   }
-  const int rc_cap = cnb_caption(h, wav, x_lens_host, bos, forbid_host ? forbid : nullptr, batch, n, beam, min_len, max_len,
-                                 preds, lprobs, mpreds, mlprobs, info, clip_probs_host ? clip : nullptr, st);
+  // decode on its own high-priority stream (cluster decoder only: the graph decoder replays on h->stream anyway)
+  cudaStream_t sd = st;
+  static const bool overlap_dec = getenv("CNB_NO_DEC_OVERLAP") == nullptr;
+  if (overlap_dec && h->use_cluster != 0 && h->cfg.precision == CNB_PRECISION_FAST && !h->prof_on) {
+    if (!h->dec_stream) {
+      int lo = 0, hi = 0;
+      CNB_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CNB_CUDA_OK(cudaStreamCreateWithPriority(&h->dec_stream, cudaStreamNonBlocking, hi));
+    }
+    sd = h->dec_stream;
+  }
+  const int rc_cap = caption_impl(h, wav, x_lens_host, bos, forbid_host ? forbid : nullptr, batch, n, beam, min_len, max_len,
+                                  preds, lprobs, mpreds, mlprobs, info, clip_probs_host ? clip : nullptr, st, sd, slot);
   h->pre_stem_done = false;
   if (rc_cap) return rc_cap;
-  CNB_CUDA_OK(cudaMemcpyAsync(preds_host, preds, (size_t)batch * max_len * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  CNB_CUDA_OK(cudaMemcpyAsync(lprobs_host, lprobs, batch * sizeof(float), cudaMemcpyDeviceToHost, st));
-  CNB_CUDA_OK(cudaMemcpyAsync(mult_preds_host, mpreds, (size_t)rows * max_len * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-  CNB_CUDA_OK(cudaMemcpyAsync(mult_lprobs_host, mlprobs, rows * sizeof(float), cudaMemcpyDeviceToHost, st));
-  CNB_CUDA_OK(cudaMemcpyAsync(info_host, info, (2 + batch) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CNB_CUDA_OK(cudaMemcpyAsync(preds_host, preds, (size_t)batch * max_len * sizeof(int64_t), cudaMemcpyDeviceToHost, sd));
+  CNB_CUDA_OK(cudaMemcpyAsync(lprobs_host, lprobs, batch * sizeof(float), cudaMemcpyDeviceToHost, sd));
+  CNB_CUDA_OK(cudaMemcpyAsync(mult_preds_host, mpreds, (size_t)rows * max_len * sizeof(int64_t), cudaMemcpyDeviceToHost, sd));
+  CNB_CUDA_OK(cudaMemcpyAsync(mult_lprobs_host, mlprobs, rows * sizeof(float), cudaMemcpyDeviceToHost, sd));
+  CNB_CUDA_OK(cudaMemcpyAsync(info_host, info, (2 + batch) * sizeof(int32_t), cudaMemcpyDeviceToHost, sd));
   if (clip_probs_host)
-    CNB_CUDA_OK(cudaMemcpyAsync(clip_probs_host, clip, (size_t)batch * kTags * sizeof(float), cudaMemcpyDeviceToHost, st));
-  CNB_CUDA_OK(cudaEventRecord(h->host_done[slot], st));
+    CNB_CUDA_OK(cudaMemcpyAsync(clip_probs_host, clip, (size_t)batch * kTags * sizeof(float), cudaMemcpyDeviceToHost, sd));
+  CNB_CUDA_OK(cudaEventRecord(h->host_done[slot], sd));
   h->host_pending[slot] = true;
   *ticket_out = slot;
   return 0;

@@ -256,8 +256,10 @@ class Engine:
                            beam: int = 3, min_len: int = 3, max_len: int = 20, with_tags: bool = True,
                            out: Optional[dict] = None) -> dict:
         """Split-phase ``caption_host``: enqueue one batch and return a ticket; up to two batches may be in flight, so the H2D
-        copy of the next batch overlaps this batch's compute.  ``caption_host_end(ticket)`` returns what ``caption_host`` does."""
-        assert wav.device.type == "cpu" and wav.dtype == torch.float32 and wav.is_contiguous()
+        copy of the next batch overlaps this batch's compute and (fast precision) this batch decodes while the next one is
+        encoded.  ``wav`` may be a host tensor or a device-resident one (used in place).  ``caption_host_end(ticket)`` returns
+        what ``caption_host`` does."""
+        assert wav.dtype == torch.float32 and wav.is_contiguous()  # host (pinned for real overlap) or device-resident
         b, n = wav.shape
         keep = dict(wav=wav, bos=bos_ids.to("cpu", torch.int64).contiguous(),
                     forbid=None if forbid_mask is None else forbid_mask.to("cpu", torch.uint8).contiguous(),

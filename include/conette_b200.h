@@ -116,8 +116,10 @@ int cnb_caption_host(cnb_handle* h, const float* wav_host, const int64_t* x_lens
 /* Split-phase form of cnb_caption_host for callers that stream batches (dataset captioning as conette-predict does over a
  * file list, serving): _begin enqueues the H2D copies, the whole path and the D2H copies and returns a ticket, _end blocks
  * until that batch's outputs are in its host buffers.  Two batches may be in flight, so the H2D copy of batch i+1 overlaps
- * the compute of batch i; results are identical to cnb_caption_host.  Host buffers must stay valid (pinned, for real
- * overlap) until _end; calling _begin a third time without _end first waits for the oldest batch. */
+ * the compute of batch i, and (fast precision) batch i decodes on a high-priority stream while batch i+1 is being encoded;
+ * results are identical to cnb_caption_host.  wav_host may also be DEVICE memory (an already resident batch): it is then used
+ * in place.  Input and output buffers must stay valid and untouched (host ones pinned, for real overlap) until _end; calling
+ * _begin a third time without _end first waits for the oldest batch. */
 int cnb_caption_host_begin(cnb_handle* h, const float* wav_host, const int64_t* x_lens_host, const int64_t* bos_ids_host,
                            const uint8_t* forbid_mask_host, int32_t batch, int64_t n_samples, int32_t beam, int32_t min_len,
                            int32_t max_len, int64_t* preds_host, float* lprobs_host, int64_t* mult_preds_host,

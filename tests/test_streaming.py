@@ -38,6 +38,12 @@ def test_begin_end_equals_blocking_call(sd):
                 assert torch.equal(x, y)
         with pytest.raises(Exception):
             eng.caption_host_end(ticket)  # already collected
+        # device-resident waveforms are used in place by the same entry point
+        t0 = eng.caption_host_begin(batches[0][0].cuda(), batches[0][1], batches[0][2], forbid, 3, 3, 20)
+        t1 = eng.caption_host_begin(batches[1][0].cuda(), batches[1][1], batches[1][2], forbid, 3, 3, 20)
+        for i, tk in ((0, t0), (1, t1)):
+            for x, y in zip(want[i], eng.caption_host_end(tk)):
+                assert torch.equal(x, y)
         # three begins without an end: the oldest batch is waited for internally, results stay right
         t = [eng.caption_host_begin(*batches[i][:3], forbid, 3, 3, 20) for i in range(3)]
         for i in (1, 2):
