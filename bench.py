@@ -10,8 +10,11 @@ min 3 / max 20 tokens, random-init weights of the checkpoint architecture (V = 4
 its own 64-clip shard (weak scaling; no data-path collective, one NCCL all_gather of the token ids per step).
 
 Reported on one JSON line (rank 0):
-  value     device-resident throughput: inputs already in HBM, CUDA-event timed, max over ranks
-  e2e       the same through the reference-facing C-ABI call with HOST buffers (H2D of the waveforms + D2H of the ids inside)
+  value     device-resident throughput: inputs already in HBM, K steps through the streaming API (two batches in flight: batch i
+            decodes on a high-priority stream while batch i+1 is encoded), CUDA-event timed, max over ranks
+  value_sequential  the same K steps as one blocking cnb_caption call after the other (per-kernel times add up to this)
+  e2e       the streaming API with HOST buffers (H2D of every step's waveforms + D2H of its ids inside the timed region)
+  e2e_sync  one blocking cnb_caption_host call per batch
   roofline  dominant kernel class: algorithmic FLOPs or bytes / CUDA-event time, against MEASURED_PEAKS.json
   kernels   the same for every kernel class (share of the step, achieved, fraction of peak)
   cpu_baseline  the reference's own CPU code (baseline/_ref, kind "reference") or the oracle port, on a bounded sample
