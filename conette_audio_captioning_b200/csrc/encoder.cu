@@ -49,7 +49,7 @@ __device__ __forceinline__ float warp_sum16(float (&v)[16], int lane) {
 constexpr int kStemThreads = 256;
 constexpr int kStemRows = 4;  // output rows per CTA (amortises the prologue; weights live in registers)
 
-__global__ void __launch_bounds__(kStemThreads)
+__global__ void __launch_bounds__(kStemThreads, 3)
 stem_kernel(const float* __restrict__ lm, int n_frames, int h1, const float* __restrict__ w_t, const float* __restrict__ bias,
             const float* __restrict__ ln_g, const float* __restrict__ ln_b, float* __restrict__ out) {
   __shared__ __align__(16) float s_in[kStemRows * 4][224];
@@ -440,103 +440,83 @@ template int launch_dwconv_ln<__nv_bfloat16>(const float*, int, int, int, int, c
 // =====================================================================================================================
 // K-DS (part 1): LayerNorm(channels_first) per pixel + pack 2x2/stride-2 patches as GEMM rows.
 //   out[(b, h', w'), (kh, kw, c)] = LN(x[b, 2h'+kh, 2w'+kw, :])[c]   (odd trailing row/col dropped: floor)
-//   one warp per input pixel.
+//   C / 12 lanes per input pixel (8 / 16 / 32), 32 / (C / 12) pixels per warp pass.
 // =====================================================================================================================
 template <int C, typename OutT>
 __global__ void __launch_bounds__(256)
 ln_pack2x2_kernel(const float* __restrict__ x, int batch, int H, int W, const float* __restrict__ ln_g,
                   const float* __restrict__ ln_b, OutT* __restrict__ out) {
-  // one warp per input pixel; a lane owns float4 groups lane, lane+32, ... of the C channels (kept in registers)
-  constexpr int NV = (C / 4 + 31) / 32;
+  // LPP = C / 12 lanes share one input pixel (8 / 16 / 32 for C = 96 / 192 / 384): a lane owns the float4 groups
+  // lip, lip + LPP, lip + 2 LPP of the pixel's channels (coalesced), so a warp normalises 32 / LPP pixels at once and the
+  // two reductions take log2(LPP) shuffles.  The first version (one warp per pixel, 24 of 32 lanes active at C = 96,
+  // 64-bit index divisions) was issue-bound: ncu counted 217 warp instructions per pixel at 25 % of the DRAM rate.
+  constexpr int LPP = C / 12;
+  constexpr int PPW = 32 / LPP;
+  static_assert(C % 12 == 0 && (LPP & (LPP - 1)) == 0 && LPP <= 32, "lanes per pixel");
   const int lane = threadIdx.x & 31;
+  const int lip = lane % LPP, sub = lane / LPP;
   const int Ho = H / 2, Wo = W / 2;
-  const int64_t n_pix = (int64_t)batch * Ho * 2 * Wo * 2;
-  const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  float4 g[NV], be[NV];
+  const uint32_t n_pix = (uint32_t)batch * (uint32_t)(Ho * 2) * (uint32_t)(Wo * 2);
+  const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  float4 g[3], be[3];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int q = lane + 32 * i;
-    g[i] = be[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q < C / 4) {
-      g[i] = *reinterpret_cast<const float4*>(ln_g + 4 * q);
-      be[i] = *reinterpret_cast<const float4*>(ln_b + 4 * q);
-    }
+  for (int i = 0; i < 3; ++i) {
+    g[i] = *reinterpret_cast<const float4*>(ln_g + 4 * (lip + LPP * i));
+    be[i] = *reinterpret_cast<const float4*>(ln_b + 4 * (lip + LPP * i));
   }
-  // U pixels per warp iteration: all their loads are issued before the first reduction, so a warp keeps U x C x 4 bytes in
-  // flight (one pixel per warp left the kernel latency-bound at 38 % of the HBM rate)
-  constexpr int U = 4;
-  for (int64_t pix0 = warp_id * U; pix0 < n_pix; pix0 += n_warps * U) {
-    float4 v[U][NV];
-    const float* px[U];
+  constexpr int U = 2;  // passes in flight per warp (all loads issued before the first reduction)
+  for (uint32_t base = warp_id * (PPW * U); base < n_pix; base += n_warps * (PPW * U)) {
+    float4 v[U][3];
     OutT* o[U];
-    float s[U];
+    bool valid[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       // enumerate only the pixels that are used: (b, h < 2*Ho, w < 2*Wo); odd trailing row / column dropped (floor)
-      const int64_t pix = pix0 + u < n_pix ? pix0 + u : n_pix - 1;
-      const int wq = (int)(pix % (2 * Wo));
-      const int hq = (int)((pix / (2 * Wo)) % (2 * Ho));
-      const int b = (int)(pix / ((int64_t)2 * Wo * 2 * Ho));
-      px[u] = x + (((int64_t)b * H + hq) * W + wq) * C;
-      const int64_t row = ((int64_t)b * Ho + hq / 2) * Wo + wq / 2;
+      uint32_t pix = base + u * PPW + sub;
+      valid[u] = pix < n_pix;
+      if (!valid[u]) pix = n_pix - 1;
+      const uint32_t rowq = pix / (uint32_t)(2 * Wo);
+      const int wq = (int)(pix - rowq * (uint32_t)(2 * Wo));
+      const uint32_t bq = rowq / (uint32_t)(2 * Ho);
+      const int hq = (int)(rowq - bq * (uint32_t)(2 * Ho));
+      const float* px = x + (((int64_t)bq * H + hq) * W + wq) * C;
+      const int64_t row = ((int64_t)bq * Ho + hq / 2) * Wo + wq / 2;
       o[u] = out + row * (4 * (int64_t)C) + ((hq & 1) * 2 + (wq & 1)) * C;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) v[u][i] = __ldg(reinterpret_cast<const float4*>(px + 4 * (lip + LPP * i)));
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+      float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int q = lane + 32 * i;
-        v[u][i] = (q < C / 4) ? __ldg(reinterpret_cast<const float4*>(px[u] + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < 3; ++i) s += (v[u][i].x + v[u][i].y) + (v[u][i].z + v[u][i].w);
+#pragma unroll
+      for (int ofs = LPP / 2; ofs > 0; ofs >>= 1) s += __shfl_xor_sync(0xffffffffu, s, ofs);
+      const float mean = s * (1.f / C);
+      float qq = 0.f;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const float dx = v[u][i].x - mean, dy = v[u][i].y - mean, dz = v[u][i].z - mean, dw = v[u][i].w - mean;
+        qq += (dx * dx + dy * dy) + (dz * dz + dw * dw);
       }
-    }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      s[u] = 0.f;
+      for (int ofs = LPP / 2; ofs > 0; ofs >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, ofs);
+      const float rstd = 1.f / sqrtf(qq * (1.f / C) + kLnEps);
+      if (!valid[u]) continue;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) s[u] += (v[u][i].x + v[u][i].y) + (v[u][i].z + v[u][i].w);
-    }
-#pragma unroll
-    for (int ofs = 16; ofs > 0; ofs >>= 1)
-#pragma unroll
-      for (int u = 0; u < U; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], ofs);
-    float mean[U], qq[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      mean[u] = s[u] * (1.f / C);
-      qq[u] = 0.f;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        if (lane + 32 * i < C / 4) {
-          const float dx = v[u][i].x - mean[u], dy = v[u][i].y - mean[u], dz = v[u][i].z - mean[u], dw = v[u][i].w - mean[u];
-          qq[u] += (dx * dx + dy * dy) + (dz * dz + dw * dw);
-        }
-      }
-    }
-#pragma unroll
-    for (int ofs = 16; ofs > 0; ofs >>= 1)
-#pragma unroll
-      for (int u = 0; u < U; ++u) qq[u] += __shfl_xor_sync(0xffffffffu, qq[u], ofs);
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (pix0 + u >= n_pix) break;
-      const float rstd = 1.f / sqrtf(qq[u] * (1.f / C) + kLnEps);
-      const float m = mean[u];
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int q = lane + 32 * i;
-        if (q < C / 4) {
-          const float y0 = (v[u][i].x - m) * rstd * g[i].x + be[i].x, y1 = (v[u][i].y - m) * rstd * g[i].y + be[i].y;
-          const float y2 = (v[u][i].z - m) * rstd * g[i].z + be[i].z, y3 = (v[u][i].w - m) * rstd * g[i].w + be[i].w;
-          if constexpr (sizeof(OutT) == 2) {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(y0, y1), p1 = __floats2bfloat162_rn(y2, y3);
-            uint2 w2;
-            w2.x = *reinterpret_cast<uint32_t*>(&p0);
-            w2.y = *reinterpret_cast<uint32_t*>(&p1);
-            *reinterpret_cast<uint2*>(o[u] + 4 * q) = w2;
-          } else {
-            *reinterpret_cast<float4*>(o[u] + 4 * q) = make_float4(y0, y1, y2, y3);
-          }
+      for (int i = 0; i < 3; ++i) {
+        const float y0 = (v[u][i].x - mean) * rstd * g[i].x + be[i].x, y1 = (v[u][i].y - mean) * rstd * g[i].y + be[i].y;
+        const float y2 = (v[u][i].z - mean) * rstd * g[i].z + be[i].z, y3 = (v[u][i].w - mean) * rstd * g[i].w + be[i].w;
+        OutT* dst = o[u] + 4 * (lip + LPP * i);
+        if constexpr (sizeof(OutT) == 2) {
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(y0, y1), p1 = __floats2bfloat162_rn(y2, y3);
+          uint2 w2;
+          w2.x = *reinterpret_cast<uint32_t*>(&p0);
+          w2.y = *reinterpret_cast<uint32_t*>(&p1);
+          *reinterpret_cast<uint2*>(dst) = w2;
+        } else {
+          *reinterpret_cast<float4*>(dst) = make_float4(y0, y1, y2, y3);
         }
       }
     }
@@ -547,7 +527,8 @@ template <typename OutT>
 int launch_ln_pack2x2(const float* x, int batch, int h, int w, int c, const float* ln_g, const float* ln_b, OutT* out,
                       cudaStream_t stream) {
   const int64_t n_pix = (int64_t)batch * (h / 2) * 2 * (w / 2) * 2;
-  const int blocks = (int)std::min<int64_t>(ceil_div(n_pix, 8 * 4), (int64_t)kNumSMs * 8);
+  CNB_REQUIRE(n_pix < ((int64_t)1 << 31), "ln_pack2x2: too many pixels for 32-bit indexing (split the batch)");
+  const int blocks = (int)std::min<int64_t>(ceil_div(n_pix, 8 * 2), (int64_t)kNumSMs * 8);
   if (c == 96) ln_pack2x2_kernel<96, OutT><<<blocks, 256, 0, stream>>>(x, batch, h, w, ln_g, ln_b, out);
   else if (c == 192) ln_pack2x2_kernel<192, OutT><<<blocks, 256, 0, stream>>>(x, batch, h, w, ln_g, ln_b, out);
   else if (c == 384) ln_pack2x2_kernel<384, OutT><<<blocks, 256, 0, stream>>>(x, batch, h, w, ln_g, ln_b, out);
