@@ -47,19 +47,38 @@ __device__ __forceinline__ float warp_sum16(float (&v)[16], int lane) {
 // K-STEM: one CTA per output row (b, h): 56 pixels x 96 channels; 8 warps x 7 pixels, lane owns channels l, l+32, l+64
 // =====================================================================================================================
 constexpr int kStemThreads = 256;
-constexpr int kStemRows = 4;  // output rows per CTA (amortises the prologue; weights live in registers)
+constexpr int kStemRows = 4;    // output rows per group (16 input frames x 224 mel bins = 14 KB of shared memory)
+constexpr int kStemMaxGroups = 4;  // groups per CTA (launch parameter, 1..4): the 48 weight registers are loaded once and
+                                   // the next group's frames are fetched with cp.async while the current group is computed
+
+__device__ __forceinline__ void stem_cp_async16(void* smem, const void* gmem, bool valid) {
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem);
+  const int bytes = valid ? 16 : 0;  // zero fill = the conv's zero padding in time
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem), "r"(bytes) : "memory");
+}
 
 __global__ void __launch_bounds__(kStemThreads, 3)
-stem_kernel(const float* __restrict__ lm, int n_frames, int h1, const float* __restrict__ w_t, const float* __restrict__ bias,
-            const float* __restrict__ ln_g, const float* __restrict__ ln_b, float* __restrict__ out) {
-  __shared__ __align__(16) float s_in[kStemRows * 4][224];
+stem_kernel(const float* __restrict__ lm, int n_frames, int h1, int n_groups, const float* __restrict__ w_t,
+            const float* __restrict__ bias, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+            float* __restrict__ out) {
+  __shared__ __align__(16) float s_in[2][kStemRows * 4][224];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.y, h0 = blockIdx.x * kStemRows;
-  for (int i = tid; i < kStemRows * 4 * 224; i += kStemThreads) {
-    const int r = i / 224, col = i - r * 224;
-    const int t = 4 * h0 - 4 + r;  // Conv2d padding (4, 0): 4 zero frames before/after in time
-    s_in[r][col] = (t >= 0 && t < n_frames) ? lm[((int64_t)b * n_frames + t) * 224 + col] : 0.f;
-  }
+  const int b = blockIdx.y;
+  const int hb = blockIdx.x * (kStemRows * n_groups);
+  const float* lmb = lm + (int64_t)b * n_frames * 224;
+  auto fetch = [&](int grp, int buf) {
+    const int h0 = hb + grp * kStemRows;
+    if (h0 < h1) {
+      for (int i = tid; i < kStemRows * 4 * 56; i += kStemThreads) {  // 16 frames x 56 float4
+        const int r = i / 56, c4 = i - r * 56;
+        const int t = 4 * h0 - 4 + r;  // Conv2d padding (4, 0): 4 zero frames before/after in time
+        const bool ok = t >= 0 && t < n_frames;
+        stem_cp_async16(&s_in[buf][r][4 * c4], ok ? lmb + (int64_t)t * 224 + 4 * c4 : lmb, ok);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  fetch(0, 0);
   float w[16][3], bia[3], g[3], be[3];
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
@@ -70,57 +89,70 @@ stem_kernel(const float* __restrict__ lm, int n_frames, int h1, const float* __r
     g[j] = ln_g[c];
     be[j] = ln_b[c];
   }
-  __syncthreads();
-  // 8 warps x 7 pixels = one output row of 56 pixels; kStemRows rows per CTA.  The kernel is issue-bound, not HBM-bound
-  // (~150 instructions per pixel per warp in the first version), so the LayerNorm statistics of a warp's 7 pixels go
-  // through ONE 16-value butterfly (7 sums | 7 sums of squares: 16 shuffles instead of 70) and the normalisation is folded
-  // into one FMA per value.
-  for (int rr = 0; rr < kStemRows; ++rr) {
-    const int h = h0 + rr;
-    if (h >= h1) break;
-    float acc[7][3];
+  // 8 warps x 7 pixels = one output row of 56 pixels.  The kernel is issue / latency bound, not HBM-bound, so the LayerNorm
+  // statistics of a warp's 7 pixels go through ONE 16-value butterfly (7 sums | 7 sums of squares: 16 shuffles instead of
+  // 70) and the normalisation is folded into one FMA per value.
+  for (int grp = 0; grp < n_groups; ++grp) {
+    const int h0 = hb + grp * kStemRows;
+    if (h0 >= h1) break;
+    const int buf = grp & 1;
+    if (grp + 1 < n_groups) fetch(grp + 1, buf ^ 1);  // buffer buf^1 was released by the barrier that ended group grp-1
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    for (int rr = 0; rr < kStemRows; ++rr) {
+      const int h = h0 + rr;
+      if (h >= h1) break;
+      float acc[7][3];
 #pragma unroll
-    for (int p = 0; p < 7; ++p) {
-      acc[p][0] = bia[0], acc[p][1] = bia[1], acc[p][2] = bia[2];
+      for (int p = 0; p < 7; ++p) {
+        acc[p][0] = bia[0], acc[p][1] = bia[1], acc[p][2] = bia[2];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const float4 v = *reinterpret_cast<const float4*>(&s_in[rr * 4 + r][4 * (warp * 7 + p)]);
-        const float vv[4] = {v.x, v.y, v.z, v.w};
+        for (int r = 0; r < 4; ++r) {
+          const float4 v = *reinterpret_cast<const float4*>(&s_in[buf][rr * 4 + r][4 * (warp * 7 + p)]);
+          const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int j = 0; j < 3; ++j) acc[p][j] = fmaf(vv[c], w[r * 4 + c][j], acc[p][j]);
+            for (int j = 0; j < 3; ++j) acc[p][j] = fmaf(vv[c], w[r * 4 + c][j], acc[p][j]);
+        }
+      }
+      float st[16];
+#pragma unroll
+      for (int p = 0; p < 7; ++p) {
+        st[p] = (acc[p][0] + acc[p][1]) + acc[p][2];
+        st[p + 8] = fmaf(acc[p][0], acc[p][0], fmaf(acc[p][1], acc[p][1], acc[p][2] * acc[p][2]));
+      }
+      st[7] = st[15] = 0.f;
+      const float tot = warp_sum16(st, lane);  // lane l holds value (l >> 1) & 15: sums 0..6 | squares 8..14
+      float* o = out + (((int64_t)b * h1 + h) * 56 + warp * 7) * 96;
+#pragma unroll
+      for (int p = 0; p < 7; ++p) {
+        const float s1 = __shfl_sync(0xffffffffu, tot, 2 * p);
+        const float s2 = __shfl_sync(0xffffffffu, tot, 2 * (p + 8));
+        const float mean = s1 * (1.f / 96.f);
+        const float var = fmaxf(fmaf(s2, 1.f / 96.f, -mean * mean), 0.f);
+        const float rstd = rsqrtf(var + kLnEps);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const float a = rstd * g[j];
+          o[p * 96 + lane + 32 * j] = fmaf(acc[p][j], a, fmaf(-mean, a, be[j]));
+        }
       }
     }
-    float st[16];
-#pragma unroll
-    for (int p = 0; p < 7; ++p) {
-      st[p] = (acc[p][0] + acc[p][1]) + acc[p][2];
-      st[p + 8] = fmaf(acc[p][0], acc[p][0], fmaf(acc[p][1], acc[p][1], acc[p][2] * acc[p][2]));
-    }
-    st[7] = st[15] = 0.f;
-    const float tot = warp_sum16(st, lane);  // lane l holds value (l >> 1) & 15: sums 0..6 | squares 8..14
-    float* o = out + (((int64_t)b * h1 + h) * 56 + warp * 7) * 96;
-#pragma unroll
-    for (int p = 0; p < 7; ++p) {
-      const float s1 = __shfl_sync(0xffffffffu, tot, 2 * p);
-      const float s2 = __shfl_sync(0xffffffffu, tot, 2 * (p + 8));
-      const float mean = s1 * (1.f / 96.f);
-      const float var = fmaxf(fmaf(s2, 1.f / 96.f, -mean * mean), 0.f);
-      const float rstd = rsqrtf(var + kLnEps);
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const float a = rstd * g[j];
-        o[p * 96 + lane + 32 * j] = fmaf(acc[p][j], a, fmaf(-mean, a, be[j]));
-      }
-    }
+    __syncthreads();  // everybody has finished reading s_in[buf] before the fetch of group grp+2 overwrites it
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 int launch_stem(const float* lm, int batch, int n_frames, int h1, const float* w_t, const float* bias, const float* ln_g,
                 const float* ln_b, float* out, cudaStream_t stream) {
-  dim3 grid((unsigned)ceil_div(h1, kStemRows), batch);
-  stem_kernel<<<grid, kStemThreads, 0, stream>>>(lm, n_frames, h1, w_t, bias, ln_g, ln_b, out);
+  // enough CTAs for ~6 per SM first, then up to 4 row groups per CTA (small batches / the sliced host path keep 1)
+  const int64_t row_groups = (int64_t)batch * ceil_div(h1, kStemRows);
+  int n_groups = (int)(row_groups / ((int64_t)kNumSMs * 6));
+  n_groups = n_groups < 1 ? 1 : (n_groups > kStemMaxGroups ? kStemMaxGroups : n_groups);
+  dim3 grid((unsigned)ceil_div(h1, kStemRows * n_groups), batch);
+  stem_kernel<<<grid, kStemThreads, 0, stream>>>(lm, n_frames, h1, n_groups, w_t, bias, ln_g, ln_b, out);
   CNB_LAUNCH_OK();
   return 0;
 }
