@@ -547,6 +547,14 @@ static int encode_chunk(cnb_handle* h, const float* wav, int nb, int64_t n, floa
         const int64_t n_slab = ceil_div(m, rows_fit > 128 ? rows_fit : 128);
         slab = ceil_div(ceil_div(m, n_slab), 128) * 128;
       }
+      // stage 1, bf16 operands: one kernel for the whole MLP, the hidden tile never leaves the SM (mlp_fused.cu)
+      static const bool fused_ok = getenv("CNB_NO_MLP_FUSED") == nullptr;
+      if (sizeof(ActT) == 2 && c == 96 && fused_ok) {
+        Prof _p(h, CNB_K_GEMM_PW1_S0 + s, st);
+        if (int rc = launch_mlp_fused_c96(reinterpret_cast<const __nv_bfloat16*>(y), b.w1_bf, b.w2_bf, b.b1, b.b2, b.scale, x, m, st))
+          return rc;
+        slab = m;  // skip the two-GEMM path below
+      } else
       for (int64_t m0 = 0; m0 < m; m0 += slab) {
         const int mm = (int)std::min<int64_t>(slab, m - m0);
         EpiParams e1;

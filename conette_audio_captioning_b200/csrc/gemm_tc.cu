@@ -19,54 +19,16 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_ptx.cuh"
+#include "tc_epi.cuh"
 
 namespace cnb {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 bytes = one swizzle-128B atom row
 constexpr int kUmmaK = 16;
-constexpr int kEpiWarps = 16;                      // four warps per TMEM lane quarter, interleaved 16-column chunks
 constexpr int kEpiChunk = 16;                      // accumulator columns per tcgen05.ld
 constexpr int kMaxN = 3072;                        // bias / layer-scale vectors are staged in shared memory
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
-
-// ---------------------------------------------------------------------------------------------------------------------
-// epilogue math on 16 consecutive accumulator columns of one output row
-// ---------------------------------------------------------------------------------------------------------------------
-// erf-GELU through one MUFU.TANH per element: coefficients fitted so that max |approx - 0.5x(1+erf(x/sqrt2))| = 2.5e-5
-// over [-8, 8]; evaluated two elements at a time with the packed fp32 pipe (fma.rn.f32x2 / mul.rn.f32x2).
-__device__ __forceinline__ float2 gelu_tanh_fit2(float2 x) {
-  const float2 x2 = __fmul2_rn(x, x);
-  float2 p = __ffma2_rn(x2, make_float2(-3.51516789e-04f, -3.51516789e-04f), make_float2(3.70056460e-02f, 3.70056460e-02f));
-  p = __ffma2_rn(x2, p, make_float2(7.97507884e-01f, 7.97507884e-01f));
-  const float2 u = __fmul2_rn(x, p);
-  float2 t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(u.x));
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(u.y));
-  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
-  return __ffma2_rn(hx, t, hx);
-}
-
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int x, int y) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(x), "r"(y),
-               "r"(src)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void bulk_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(32 * kEpiWarps) : "memory"); }
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-  return v;
-}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // kernel
@@ -406,6 +368,25 @@ static int make_map_uncached(CUtensorMap* map, const void* ptr, uint64_t rows, u
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return -3;
+  }
+  return 0;
+}
+
+// 2-D row-major bf16 tensor, box = (box_rows, box_cols) with box_cols * 2 bytes == the swizzle span (64 or 128 bytes)
+int tc_make_map_bf16_box(void* map_out, const void* ptr, int64_t rows, int64_t cols, int box_rows, int box_cols) {
+  CNB_REQUIRE(g_encode != nullptr, "gemm_tc_init() was not called");
+  CNB_REQUIRE(box_cols == 32 || box_cols == 64, "bf16 box must span 64 or 128 bytes");
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(reinterpret_cast<CUtensorMap*>(map_out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (bf16 box) failed with CUresult " + std::to_string((int)r));
     return -3;
   }
   return 0;

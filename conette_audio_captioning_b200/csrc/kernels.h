@@ -75,10 +75,15 @@ struct TcGemmPlan;  // opaque: TMA descriptors + tile configuration
 template <typename OutT>
 int launch_gemm_tc(const __nv_bfloat16* a, const __nv_bfloat16* w, int m, int n, int k, Epilogue epi, const EpiParams& ep,
                    OutT* out, int64_t ldo, cudaStream_t stream);
+// fused pointwise MLP of ConvNeXt stage 1 (mlp_fused.cu): x (M, 96) f32 += scale * (W2 . GELU(W1 . y + b1) + b2), in place
+int launch_mlp_fused_c96(const __nv_bfloat16* y, const __nv_bfloat16* w1, const __nv_bfloat16* w2, const float* b1, const float* b2,
+                         const float* scale, float* x, int m, cudaStream_t stream);
 int gemm_tc_init();  // resolves cuTensorMapEncodeTiled; returns 0 on success
 // 2-D row-major (rows, cols) tensor map into map_out (a 128-byte CUtensorMap): box = (box_rows, 128 bytes), 128B swizzle
 int tc_make_map(void* map_out, const void* ptr, int64_t rows, int64_t cols, int box_rows, int elt_bytes);
 
+// 2-D row-major bf16 tensor map with an explicit box: box_cols 64 -> 128B swizzle, 32 -> 64B swizzle
+int tc_make_map_bf16_box(void* map_out, const void* ptr, int64_t rows, int64_t cols, int box_rows, int box_cols);
 // 4-D NHWC fp32 tensor map, box (box_c, box_w, 1, 1), no swizzle, zero OOB fill (used by the depthwise-conv ring loader)
 int tc_make_map_nhwc_f32(void* map_out, const float* ptr, int batch, int h, int w, int c, int box_c, int box_w);
 // TMA-ring depthwise 7x7 + LayerNorm (dwconv_ring.cu); returns 1 when (C, W) has no instantiation (caller falls back)
