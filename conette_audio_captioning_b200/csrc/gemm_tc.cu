@@ -104,7 +104,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 32 * kEpiWarps);
+      mbar_init(tempty_bar(s), kEpiWarps);   // one arrival per epilogue warp
     }
     mbar_init(resid_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -211,7 +211,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       tmem_ld_wait();
       tcgen05_fence_before();
-      mbar_arrive(tempty_bar(as));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
       if (C::kResid) {
         mbar_wait(resid_bar, rph);
         rph ^= 1;
