@@ -121,48 +121,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====================
+    {
+      const uint32_t sb = __shfl_sync(0xffffffffu, base, 0);
+      const uint32_t ubars = sb + C::kBarOff;
       int s = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int m_blk = t / tiles_n, n_blk = t - m_blk * tiles_n;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(empty_bar(s), ph ^ 1);
-          const uint32_t a_dst = base + s * C::kStageBytes;
-          const uint32_t b_dst = a_dst + C::kABytes;
-          mbar_expect_tx(full_bar(s), C::kStageBytes);
-          tma_load_2d(a_dst, &map_a, kb * kBlockK, m_blk * kBlockM, full_bar(s));
-          tma_load_2d(b_dst, &map_w, kb * kBlockK, n_blk * BLOCK_N, full_bar(s));
+          mbar_wait(ubars + 8u * (kStages + s), ph ^ 1);   // empty
+          if (elect_one()) {
+            const uint32_t a_dst = sb + s * C::kStageBytes;
+            const uint32_t b_dst = a_dst + C::kABytes;
+            const uint32_t full = ubars + 8u * s;
+            mbar_expect_tx(full, C::kStageBytes);
+            tma_load_2d(a_dst, &map_a, kb * kBlockK, m_blk * kBlockM, full);
+            tma_load_2d(b_dst, &map_w, kb * kBlockK, n_blk * BLOCK_N, full);
+          }
+          __syncwarp();
           if (++s == kStages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // the whole warp runs the loop on warp-uniform values, one elected lane issues (see elect_one in tc_ptx.cuh)
+    {
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t sb = __shfl_sync(0xffffffffu, base, 0);
+      const uint32_t ubars = sb + C::kBarOff;
       constexpr uint32_t idesc = make_idesc(kBlockM, BLOCK_N);
       int s = 0, as = 0;
       uint32_t ph = 0, aph = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        mbar_wait(tempty_bar(as), aph ^ 1);  // epilogue has drained this accumulator stage
+        mbar_wait(ubars + 8u * (2 * kStages + 2 + as), aph ^ 1);  // tempty: the epilogue has drained this accumulator stage
         tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BLOCK_N);
+        const uint32_t tmem_d = tb + (uint32_t)(as * BLOCK_N);
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(full_bar(s), ph);
+          mbar_wait(ubars + 8u * s, ph);   // full
           tcgen05_fence_after();
-          const uint32_t a_addr = base + s * C::kStageBytes;
-          const uint64_t adesc = make_smem_desc(a_addr);
-          const uint64_t bdesc = make_smem_desc(a_addr + C::kABytes);
+          if (elect_one()) {
+            const uint32_t a_addr = sb + s * C::kStageBytes;
+            const uint64_t adesc = make_smem_desc(a_addr);
+            const uint64_t bdesc = make_smem_desc(a_addr + C::kABytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in (addr >> 4) units
-            tcgen05_mma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in (addr >> 4) units
+              tcgen05_mma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            }
+            tcgen05_commit(ubars + 8u * (kStages + s));  // empty: frees the smem stage once these MMAs have read it
+            if (kb == k_blocks - 1) tcgen05_commit(ubars + 8u * (2 * kStages + as));   // tfull: accumulator complete -> epilogue
           }
-          tcgen05_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+          __syncwarp();
           if (++s == kStages) { s = 0; ph ^= 1; }
         }
-        tcgen05_commit(tfull_bar(as));   // accumulator complete -> epilogue
         as ^= 1;
         if (as == 0) aph ^= 1;
       }

@@ -76,22 +76,6 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* r)
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int x, int y) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
 }
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "elect.sync _|p, 0xffffffff;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int x, int y) {
-  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(x),
-               "r"(y), "r"(src)
-               : "memory");
-}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D (tmem) (+)= A (tmem: row = lane, two bf16 per 32-bit column, K-major) . B (smem descriptor)^T
 __device__ __forceinline__ void tcgen05_mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
@@ -290,15 +274,16 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_y0, const __grid_consta
             if (j == kNCh - 1) tcgen05_commit(ubars + 24);   // o_full
           }
           __syncwarp();
-          if (has_next && j == kNCh - 1) {
-            // GEMM1 of the next tile overwrites the hidden columns: issued behind the GEMM2s that read them, and only after
-            // the last one so that o_full is not queued behind 1 100 cycles of GEMM1 (the epilogue needs the new hidden tile
-            // only after its output phase)
-            mbar_wait(a_full, (it + 1) & 1);
-            tcgen05_fence_after();
-            mark(1, it, 7);
-            gemm1(0);
-            gemm1(1);
+          if (has_next && (j == 2 || j == kNCh - 1)) {
+            // GEMM1 of the next tile overwrites the hidden columns of three chunks: it is issued behind the GEMM2s that read
+            // them.  The first half goes out in mid-tile (the epilogue starts the next tile's first chunk before this tile's
+            // output phase), the second half after o_full so that o_full is not queued behind it.
+            if (j == 2) {
+              mbar_wait(a_full, (it + 1) & 1);
+              tcgen05_fence_after();
+              mark(1, it, 7);
+            }
+            gemm1(j / 3);
           }
           if (j == kNCh - 1) mark(1, it, 8);
         }
@@ -314,35 +299,40 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_y0, const __grid_consta
     const int row = lane_grp * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
     const bool tr = (warp == 2 || warp == 6) && lane == 0;   // traced threads: half 0 of groups 0 and 1
+    auto do_chunk = [&](int cit, int k) {   // chunk j = 2 k + grp of the tile with iteration index cit
+      const int j = 2 * k + grp;
+      const uint32_t taddr = lane_addr + (uint32_t)(j * kCh + 32 * half);
+      mbar_wait(d1_full(j / 3), cit & 1);   // GEMM1 runs in two 192-column halves
+      if (tr) mark(2 + grp, cit, 2 * k);
+      tcgen05_fence_after();
+      float v[32];
+      tmem_ld_32x16(taddr, v);
+      tmem_ld_32x16(taddr + 16, v + 16);
+      tmem_ld_wait();
+      float2* v2 = reinterpret_cast<float2*>(v);
+      const float2* sb2 = reinterpret_cast<const float2*>(s_b1 + j * kCh + 32 * half);
+      uint32_t h[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float2 g = gelu_tanh_fit2(__fadd2_rn(v2[i], sb2[i]));
+        __nv_bfloat162 p = __floats2bfloat162_rn(g.x, g.y);   // k = 2 i in the low half, 2 i + 1 in the high half
+        h[i] = *reinterpret_cast<uint32_t*>(&p);
+      }
+      tmem_st_32x16(taddr, h);   // over the first 16 of the 32 columns this thread has just read
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(h_full(j));
+      if (tr) mark(2 + grp, cit, 2 * k + 1);
+    };
+    // Software pipeline across the tile boundary: the first chunk of tile i+1 is processed BEFORE the output phase of tile i,
+    // so the wait for the last GEMM2 (o_full: wake-up of the MMA warp, 8 MMAs, completion, ~1 200 cycles) is covered by work.
+    if ((int)blockIdx.x < n_tiles) do_chunk(0, 0);
     int it = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
 #pragma unroll 1
-      for (int k = 0; k < kNCh / 2; ++k) {
-        const int j = 2 * k + grp;
-        const uint32_t taddr = lane_addr + (uint32_t)(j * kCh + 32 * half);
-        mbar_wait(d1_full(j / 3), it & 1);   // GEMM1 runs in two 192-column halves
-        if (tr) mark(2 + grp, it, 2 * k);
-        tcgen05_fence_after();
-        float v[32];
-        tmem_ld_32x16(taddr, v);
-        tmem_ld_32x16(taddr + 16, v + 16);
-        tmem_ld_wait();
-        float2* v2 = reinterpret_cast<float2*>(v);
-        const float2* sb2 = reinterpret_cast<const float2*>(s_b1 + j * kCh + 32 * half);
-        uint32_t h[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float2 g = gelu_tanh_fit2(__fadd2_rn(v2[i], sb2[i]));
-          __nv_bfloat162 p = __floats2bfloat162_rn(g.x, g.y);   // k = 2 i in the low half, 2 i + 1 in the high half
-          h[i] = *reinterpret_cast<uint32_t*>(&p);
-        }
-        tmem_st_32x16(taddr, h);   // over the first 16 of the 32 columns this thread has just read
-        tmem_st_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(h_full(j));
-        if (tr) mark(2 + grp, it, 2 * k + 1);
-      }
+      for (int k = 1; k < kNCh / 2; ++k) do_chunk(it, k);
+      if (t + (int)gridDim.x < n_tiles) do_chunk(it + 1, 0);
       // ---- output: O (128 x 96) + bias2, layer scale, residual ----
       mbar_wait(o_full, it & 1);
       if (tr) mark(2 + grp, it, 6);

@@ -48,6 +48,25 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(x), "r"(y), "r"(bar)
       : "memory");
 }
+// one lane of a converged warp (the single thread that issues tcgen05.mma / commit).  Run the surrounding control flow on the
+// whole warp with warp-uniform values: under `if (lane == 0)` the compiler cannot keep descriptors in uniform registers and
+// wraps every MMA in a vector -> uniform waterfall loop (~90 cycles per instruction).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int x, int y) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(x),
+               "r"(y), "r"(src)
+               : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
