@@ -1348,6 +1348,25 @@ int cnb_debug_gemm(cnb_handle* h, const float* a, const float* w, const float* b
   return 0;
 }
 
+int cnb_debug_mlp_fused(cnb_handle* h, const float* y, const float* w1, const float* b1, const float* w2, const float* b2,
+                        const float* scale, float* x, int32_t m, void* stream) {
+  CHECK_READY(h);
+  CNB_REQUIRE(y && w1 && b1 && w2 && b2 && scale && x, "null buffer");
+  CNB_REQUIRE(m >= 0, "negative row count");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m == 0) return 0;
+  WS(h, "dbg_y", __nv_bfloat16, (size_t)m * 96, y_bf);
+  WS(h, "dbg_w1", __nv_bfloat16, (size_t)384 * 96, w1_bf);
+  WS(h, "dbg_w2", __nv_bfloat16, (size_t)96 * 384, w2_bf);
+  f32_to_bf16_kernel<<<(unsigned)ceil_div((int64_t)m * 96, 256), 256, 0, st>>>(y, y_bf, (int64_t)m * 96);
+  CNB_LAUNCH_OK();
+  f32_to_bf16_kernel<<<(unsigned)ceil_div((int64_t)384 * 96, 256), 256, 0, st>>>(w1, w1_bf, (int64_t)384 * 96);
+  CNB_LAUNCH_OK();
+  f32_to_bf16_kernel<<<(unsigned)ceil_div((int64_t)384 * 96, 256), 256, 0, st>>>(w2, w2_bf, (int64_t)384 * 96);
+  CNB_LAUNCH_OK();
+  return launch_mlp_fused_c96(y_bf, w1_bf, w2_bf, b1, b2, scale, x, m, st);
+}
+
 int cnb_profile_begin(cnb_handle* h) {
   CHECK_READY(h);
   h->prof_on = true;

@@ -132,6 +132,12 @@ int cnb_caption_host_end(cnb_handle* h, int32_t ticket);
 int cnb_debug_gemm(cnb_handle* h, const float* a, const float* w, const float* bias, const float* scale, const float* resid,
                    int32_t m, int32_t n, int32_t k, int32_t epi, int32_t use_tc, int32_t out_bf16, float* out, void* stream);
 
+/* Test hook: the fused pointwise MLP of a ConvNeXt stage-1 block (reference convnext.py:66-73, C = 96):
+ * x (M,96) f32 += scale * (W2 (96,384) . GELU(W1 (384,96) . y (M,96) + b1) + b2), in place, through the kernel the fast
+ * precision mode uses (y, W1, W2 and the hidden activations are rounded to bf16, fp32 accumulation and residual). */
+int cnb_debug_mlp_fused(cnb_handle* h, const float* y, const float* w1, const float* b1, const float* w2, const float* b2,
+                        const float* scale, float* x, int32_t m, void* stream);
+
 /* Per-kernel-class device timing: between cnb_profile_begin and cnb_profile_end every launch group issued through this
  * handle is bracketed by a CUDA event pair on the launching stream; _end synchronises and returns, per class, the summed
  * event time in ms and the number of brackets. Arrays must hold CNB_K_COUNT entries.  The block kernels are reported
