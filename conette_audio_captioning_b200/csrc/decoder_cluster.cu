@@ -332,20 +332,24 @@ __device__ __forceinline__ void tc_gemm(CSmem& S, const PersistentArgs& a, Pipe&
   tcgen05_fence_after();
   const int cpg = 8 / g.ns;  // chunks per tile group
   const int n_tiles = (g.n_chunks / cpg) * g.tpc;
-  if (tid == kProducerTid) {
+  // Producer and MMA issuers run their loops on WHOLE warps with warp-uniform values and one elected lane issuing (elect_one,
+  // tc_ptx.cuh): under a single-thread branch every TMA / MMA operand went through a vector -> uniform register waterfall
+  // loop, ~75-100 cycles per instruction (the decode spent 19 % of its time issuing 24 k MMAs per CTA).
+  if (warp == kCWarps - 1) {
     // producer: this phase's chunks, then run ahead into the next phases' weights as far as the ring allows.  Every wait is
-    // on MMAs that thread 0 issues without depending on this thread beyond the current phase: no deadlock.
+    // on MMAs that the issuers issue without depending on this warp beyond the current phase: no deadlock.
     const uint32_t target = pp.use + (uint32_t)g.n_chunks + (kStages - 1);
     while (pp.load < target) {
       const int s = (int)(pp.load % kStages);
       mbar_wait(smem_addr(&S.empty[s]), ((pp.load / kStages) & 1u) ^ 1u);  // the MMAs that read this stage have completed
-      issue_chunk(S, a, pp.load, rank, v0, chunks_per_step);
+      if (elect_one()) issue_chunk(S, a, pp.load, rank, v0, chunks_per_step);
+      __syncwarp();
       ++pp.load;
     }
-  } else if ((tid & 127) == 0) {
-    const int chain = tid >> 7;
-    // MMA issuers (lane 0 of warps 0, 4, 8, 12; issuer j owns accumulator chain j).  A lone thread issues ~1 instruction per 5 cycles, so the per-MMA instruction count matters more than the
-    // tensor pipe here (a 128 x 16 x 8 MMA keeps the pipe busy for ~24 cycles): descriptors advance by plain adds.
+  } else if ((warp & 3) == 0) {
+    // MMA issuers (warps 0, 4, 8, 12; issuer j owns accumulator chain j): descriptors advance by plain adds.
+    const int chain = __shfl_sync(kFull, warp >> 2, 0);
+    const uint32_t tb = __shfl_sync(kFull, tmem_base, 0);
     const uint64_t bdesc0 = make_smem_desc(smem_addr(xbuf));
     const uint32_t a_step = (uint32_t)g.sub_pitch >> 4;
     for (int i = 0; i < g.n_chunks; ++i) {
@@ -358,17 +362,20 @@ __device__ __forceinline__ void tc_gemm(CSmem& S, const PersistentArgs& a, Pipe&
       const unsigned long long tf1 = clock64();
       if (tr0) S.tr2[0] += tf1 - tf0;
       const int grp = i / cpg, ic = i - grp * cpg;
-      uint64_t adesc = make_smem_desc(smem_addr(&S.ring[s][0]));
-      uint64_t bdesc = bdesc0 + (uint64_t)(ic * g.ns * 128);  // 2048 bytes per k-chunk of the B operand
-      const uint32_t tmem_d = tmem_base + (uint32_t)(grp * g.tpc * kChains * kRm);
-      if (g.tpc == 2) {
-        for (int sub = 0; sub < g.ns; ++sub, adesc += a_step, bdesc += 128) mma_block<2>(tmem_d, adesc, bdesc, (ic | sub) != 0, chain);
-      } else {
-        for (int sub = 0; sub < g.ns; ++sub, adesc += a_step, bdesc += 128) mma_block<1>(tmem_d, adesc, bdesc, (ic | sub) != 0, chain);
+      if (elect_one()) {
+        uint64_t adesc = make_smem_desc(smem_addr(&S.ring[s][0]));
+        uint64_t bdesc = bdesc0 + (uint64_t)(ic * g.ns * 128);  // 2048 bytes per k-chunk of the B operand
+        const uint32_t tmem_d = tb + (uint32_t)(grp * g.tpc * kChains * kRm);
+        if (g.tpc == 2) {
+          for (int sub = 0; sub < g.ns; ++sub, adesc += a_step, bdesc += 128) mma_block<2>(tmem_d, adesc, bdesc, (ic | sub) != 0, chain);
+        } else {
+          for (int sub = 0; sub < g.ns; ++sub, adesc += a_step, bdesc += 128) mma_block<1>(tmem_d, adesc, bdesc, (ic | sub) != 0, chain);
+        }
+        tcgen05_commit(smem_addr(&S.empty[s]));  // frees the stage once these MMAs have read it
+        if (ic == cpg - 1)
+          for (int tt = 0; tt < g.tpc; ++tt) tcgen05_commit(smem_addr(&S.tile_full[grp * g.tpc + tt]));
       }
-      tcgen05_commit(smem_addr(&S.empty[s]));  // frees the stage once these MMAs have read it
-      if (ic == cpg - 1)
-        for (int tt = 0; tt < g.tpc; ++tt) tcgen05_commit(smem_addr(&S.tile_full[grp * g.tpc + tt]));
+      __syncwarp();
       if (tr0) S.tr2[1] += clock64() - tf1;
     }
   }
@@ -909,7 +916,7 @@ decoder_cluster_kernel(const __grid_constant__ PersistentArgs a, int clips_per_g
     steps_max = max(steps_max, steps_done);
   }
   // drain the weight chunks that were requested ahead but never consumed
-  if (tid == kProducerTid)
+  if (warp == kCWarps - 1)
     for (uint32_t u = pp.use; u < pp.load; ++u) mbar_wait(smem_addr(&S.full[u % kStages]), (u / kStages) & 1u);
   if (tr_on)
     for (int i = 0; i < kTrSlots; ++i) a.trace[i] = S.tr_acc[i];
