@@ -47,7 +47,11 @@ struct TcCfg {
   static constexpr int kBoxesPerPass = 64 / kBoxCols;         // 1 / 2
   static constexpr int kPassBytes = kBoxesPerPass * kBoxBytes;
   static constexpr int kPasses = (BLOCK_N + 63) / 64;
-  static constexpr int kStagingBufs = kResid ? kPasses : 2;   // residual tiles are staged whole, plain outputs ping-pong
+  // residual tiles are staged whole; plain bf16 outputs rotate through three 16 KB tiles (one CTA-wide barrier per pass: the
+  // elected lane waits for the store of pass p-1 right after issuing the store of pass p, so whoever has passed the barrier of
+  // pass p+1 knows that the tile of pass p-1 = the tile of pass p+2 is free); plain fp32 outputs (32 KB tiles) ping-pong
+  static constexpr int kStagingBufs = kResid ? kPasses : (kElt == 2 ? 3 : 2);
+  static constexpr bool kOneBar = !kResid && kStagingBufs == 3;
   static constexpr int kVecFloats = kResid ? 2 * 768 : kMaxN; // bias (| scale) staged in smem
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
@@ -184,32 +188,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===================== epilogue (warps 2..17) =====================
     const int lane_grp = warp & 3;            // TMEM lanes [32*lane_grp, +32) are accessible to this warp
     const int sub = (warp - 2) >> 2;          // the four warps of a lane quarter split every 64-column pass 4 x 16
-    const bool leader = (warp == 2 && lane == 0);
+    // TMA stores / residual loads are issued by one elected lane of warp 2, with warp-uniform operands (see elect_one in
+    // tc_ptx.cuh: a plain `lane == 0` branch costs ~90 cycles per TMA instruction, in front of a barrier all 16 warps wait on).
+    // Bulk async-groups belong to the issuing thread: every commit / wait below uses the same elected lane.
+    const bool lead_warp = (warp == 2);
+    const uint32_t ustg = __shfl_sync(0xffffffffu, stg, 0);
+    const uint32_t uresid_bar = __shfl_sync(0xffffffffu, resid_bar, 0);
     const int row = lane_grp * 32 + lane;     // row of the tile owned by this thread
     int as = 0;
     uint32_t aph = 0, rph = 0;
     uint32_t pass_ctr = 0;                    // running pass counter: plain outputs ping-pong the two staging tiles
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int m_blk = t / tiles_n, n_blk = t - m_blk * tiles_n;
-      if (C::kResid && leader) {
-        // previous tile's stores must have finished reading the staging tiles; then fetch this tile's residual rows
-        bulk_wait_read<0>();
-        int n_boxes = 0;
+      if (C::kResid && lead_warp) {
+        if (elect_one()) {
+          // previous tile's stores must have finished reading the staging tiles; then fetch this tile's residual rows
+          bulk_wait_read<0>();
+          int n_boxes = 0;
 #pragma unroll
-        for (int i = 0; i < C::kPasses; ++i)
+          for (int i = 0; i < C::kPasses; ++i)
 #pragma unroll
-          for (int bx = 0; bx < C::kBoxesPerPass; ++bx)
-            if (64 * i + bx * C::kBoxCols < BLOCK_N) ++n_boxes;
-        mbar_expect_tx(resid_bar, (uint32_t)n_boxes * C::kBoxBytes);
+            for (int bx = 0; bx < C::kBoxesPerPass; ++bx)
+              if (64 * i + bx * C::kBoxCols < BLOCK_N) ++n_boxes;
+          mbar_expect_tx(uresid_bar, (uint32_t)n_boxes * C::kBoxBytes);
 #pragma unroll
-        for (int i = 0; i < C::kPasses; ++i)
+          for (int i = 0; i < C::kPasses; ++i)
 #pragma unroll
-          for (int bx = 0; bx < C::kBoxesPerPass; ++bx) {
-            const int c = 64 * i + bx * C::kBoxCols;
-            if (c < BLOCK_N)
-              tma_load_2d(stg + i * C::kPassBytes + bx * C::kBoxBytes, &map_resid, n_blk * BLOCK_N + c, m_blk * kBlockM,
-                          resid_bar);
-          }
+            for (int bx = 0; bx < C::kBoxesPerPass; ++bx) {
+              const int c = 64 * i + bx * C::kBoxCols;
+              if (c < BLOCK_N)
+                tma_load_2d(ustg + i * C::kPassBytes + bx * C::kBoxBytes, &map_resid, n_blk * BLOCK_N + c, m_blk * kBlockM,
+                            uresid_bar);
+            }
+        }
+        __syncwarp();
       }
       mbar_wait(tfull_bar(as), aph);
       tcgen05_fence_after();
@@ -233,10 +245,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
       for (int i = 0; i < C::kPasses; ++i) {
         const int c0 = 64 * i + kEpiChunk * sub;           // first column (inside the tile) of this thread's chunk
-        const uint32_t buf = C::kResid ? (uint32_t)i : (pass_ctr & 1u);
+        const uint32_t buf = C::kResid ? (uint32_t)i : (C::kOneBar ? pass_ctr % 3u : (pass_ctr & 1u));
         const uint32_t tile_smem = stg + buf * C::kPassBytes;
-        if (!C::kResid) {
-          if (leader) bulk_wait_read<1>();                 // the store that last used this staging tile has drained it
+        if (!C::kResid && !C::kOneBar) {
+          if (lead_warp) {
+            if (elect_one()) bulk_wait_read<1>();          // the store that last used this staging tile has drained it
+            __syncwarp();
+          }
           epi_bar(1);
         }
         if (c0 < BLOCK_N) {
@@ -285,20 +300,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         fence_async_smem();   // generic-proxy writes -> visible to the TMA store
         epi_bar(2);
-        if (leader) {
+        if (lead_warp) {
+          if (elect_one()) {
+            const uint32_t utile = ustg + buf * C::kPassBytes;
 #pragma unroll
-          for (int bx = 0; bx < C::kBoxesPerPass; ++bx) {
-            const int c = 64 * i + bx * C::kBoxCols;
-            if (c < BLOCK_N) tma_store_2d(&map_out, tile_smem + bx * C::kBoxBytes, n_blk * BLOCK_N + c, m_blk * kBlockM);
+            for (int bx = 0; bx < C::kBoxesPerPass; ++bx) {
+              const int c = 64 * i + bx * C::kBoxCols;
+              if (c < BLOCK_N) tma_store_2d(&map_out, utile + bx * C::kBoxBytes, n_blk * BLOCK_N + c, m_blk * kBlockM);
+            }
+            bulk_commit();
+            if (C::kOneBar) bulk_wait_read<1>();
           }
-          bulk_commit();
+          __syncwarp();
         }
         ++pass_ctr;
       }
       as ^= 1;
       if (as == 0) aph ^= 1;
     }
-    if (leader) bulk_wait_all();
+    if (lead_warp) {
+      if (elect_one()) bulk_wait_all();
+      __syncwarp();
+    }
   }
 
   tcgen05_fence_before();
