@@ -299,6 +299,49 @@ static int finalize(cnb_handle* h) {
     float* dw;
     PUT(dw, wts);
     h->fe.mel_lo = dlo; h->fe.mel_cnt = dcnt; h->fe.mel_off = doff; h->fe.mel_w = dw;
+    {
+      // Lane-balanced schedule for the warp-per-frame-pair kernel: the filters are dealt to the 32 lanes longest first, each
+      // to the lane with the least work so far; a lane walks its filters as ONE flat list of (weight, bin | end | filter)
+      // entries (bins in ascending order, so the sum order of every filter is unchanged), padded with zero weights to the
+      // longest lane.  Entry i of lane l sits at [i][l].
+      std::vector<int> order(kMels), load(32, 0);
+      for (int m = 0; m < kMels; ++m) order[m] = m;
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cnt[a] > cnt[b]; });
+      std::vector<std::vector<int>> mine(32);
+      for (int m : order) {
+        int best = 0;
+        for (int l = 1; l < 32; ++l)
+          if (load[l] < load[best]) best = l;
+        mine[best].push_back(m);
+        load[best] += std::max(cnt[m], 1);
+      }
+      int len = 0;
+      for (int l = 0; l < 32; ++l) len = std::max(len, load[l]);
+      if (len > kMelSchedMax) {
+        set_error("logmel_extractor.melW: a lane of the balanced mel schedule needs " + std::to_string(len) + " entries (max " +
+                  std::to_string(kMelSchedMax) + ")");
+        return -4;
+      }
+      std::vector<float> sched((size_t)len * 64, 0.f);
+      for (int l = 0; l < 32; ++l) {
+        int i = 0;
+        for (int m : mine[l]) {
+          const int n = std::max(cnt[m], 1);   // an all-zero filter still emits one (zero-weight) entry that ends it
+          for (int k = 0; k < n; ++k, ++i) {
+            const float w = cnt[m] ? wts[(size_t)off[m] + k] : 0.f;
+            const int code = (lo[m] + k) | (k == n - 1 ? 1 << 10 : 0) | (m << 11);
+            float cf;
+            std::memcpy(&cf, &code, 4);
+            sched[((size_t)i * 32 + l) * 2] = w;
+            sched[((size_t)i * 32 + l) * 2 + 1] = cf;
+          }
+        }
+      }
+      float* dsched;
+      PUT(dsched, sched);
+      h->fe.mel_sched = reinterpret_cast<const float2*>(dsched);
+      h->fe.mel_sched_len = len;
+    }
     GET(g, E + "bn0.weight", kMels);
     GET(b, E + "bn0.bias", kMels);
     GET(mu, E + "bn0.running_mean", kMels);

@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "tc_ptx.cuh"
 
 namespace cnb {
 
@@ -190,28 +191,52 @@ __device__ __forceinline__ void fft32_regs(float (&re)[32], float (&im)[32]) {
 __global__ void __launch_bounds__(kFe2Warps * 32, 1)
 frontend_warpfft_kernel(const float* __restrict__ wav, int64_t n_samples, int n_frames, const float2* __restrict__ twiddle,
                         const int* __restrict__ mel_lo, const int* __restrict__ mel_cnt, const int* __restrict__ mel_off,
-                        const float* __restrict__ mel_w, const float* __restrict__ bn_scale,
-                        const float* __restrict__ bn_shift, float* __restrict__ out) {
+                        const float* __restrict__ mel_w, const float2* __restrict__ mel_sched, int sched_len,
+                        const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, float* __restrict__ out) {
   extern __shared__ __align__(16) float s_fe[];
   float* s_wav = s_fe;                       // [kFe2Span]
   float* s_win = s_wav + kFe2Span;           // [1024] periodic Hann
   float2* s_tw = reinterpret_cast<float2*>(s_win + kFftN);  // [32] W_1024^{n2}
-  float* s_scr = reinterpret_cast<float*>(s_tw + 32);       // per-warp scratch
+  float2* s_sched = s_tw + 32;               // [kMelSchedMax][32] lane-balanced mel schedule (weight, bin | end | filter)
+  float* s_scr = reinterpret_cast<float*>(s_sched + kMelSchedMax * 32);  // per-warp scratch
+  __shared__ __align__(8) unsigned long long s_bar;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * kFe2Frames;
   const float* x = wav + (int64_t)b * n_samples;
   const int64_t start = (int64_t)t0 * kHop - kFftN / 2;
-  for (int i = tid; i < kFe2Span; i += kFe2Warps * 32) {
-    int64_t idx = start + i;
-    if (idx < 0) idx = -idx;                                   // reflect without repeating the edge sample
-    if (idx >= n_samples) idx = 2 * (n_samples - 1) - idx;
-    s_wav[i] = (idx >= 0 && idx < n_samples) ? __ldg(x + idx) : 0.f;
+  // Staging.  The span of an interior CTA is contiguous and 16-byte aligned in global memory (hop 320, 32 frames per CTA):
+  // one bulk async copy (plus one for the mel schedule) instead of 43 dependent load/store round trips per thread -- with one
+  // CTA per SM nothing else hides that latency, and the ncu source view had 40 % of the kernel's stall samples here.
+  const bool interior = start >= 0 && start + kFe2Span <= n_samples && (reinterpret_cast<uintptr_t>(x + start) & 15) == 0;
+  const uint32_t bar = smem_u32(&s_bar);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async_smem();
+    const uint32_t sched_bytes = (uint32_t)sched_len * 32u * 8u;
+    mbar_expect_tx(bar, sched_bytes + (interior ? (uint32_t)kFe2Span * 4u : 0u));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(s_sched)),
+                 "l"(mel_sched), "r"(sched_bytes), "r"(bar)
+                 : "memory");
+    if (interior)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(s_wav)),
+                   "l"(x + start), "r"((uint32_t)kFe2Span * 4u), "r"(bar)
+                   : "memory");
+  }
+  if (!interior) {
+    for (int i = tid; i < kFe2Span; i += kFe2Warps * 32) {
+      int64_t idx = start + i;
+      if (idx < 0) idx = -idx;                                   // reflect without repeating the edge sample
+      if (idx >= n_samples) idx = 2 * (n_samples - 1) - idx;
+      s_wav[i] = (idx >= 0 && idx < n_samples) ? __ldg(x + idx) : 0.f;
+    }
   }
   for (int i = tid; i < kFftN; i += kFe2Warps * 32) s_win[i] = 0.5f - 0.5f * twiddle[i].x;
   if (tid < 32) s_tw[tid] = twiddle[tid];
   __syncthreads();
+  mbar_wait(bar, 0);
 
   float* tile_re = s_scr + warp * kFe2WarpScratch;   // [32][33]   (later: spectrum re[1024])
   float* tile_im = tile_re + 32 * 33;                // [32][33]   (later: spectrum im[1024])
@@ -269,20 +294,34 @@ frontend_warpfft_kernel(const float* __restrict__ wav, int64_t n_samples, int n_
       pw[520 + k] = br * br + bi * bi;
     }
     __syncwarp();
-    // sparse mel + dB + BN: lane owns mel bins lane, lane+32, ... for both frames
-    for (int m = lane; m < kMels; m += 32) {
-      const int lo = mel_lo[m], cnt = mel_cnt[m];
-      const float* w = mel_w + mel_off[m];
+    // sparse mel: every lane walks its balanced share of the 884 non-zeros as one flat list (api.cu builds it: the filters
+    // are dealt longest-first to the least loaded lane).  Filter-per-lane rounds made the warp wait for the widest filter
+    // of every round: 95 serial iterations instead of 29.  The sum order inside a filter is unchanged.
+    {
+      float* s_mel = tile_re;   // [2][224]: the spectrum tiles are dead once the power spectra exist
       float a0 = 0.f, a1 = 0.f;
-      for (int i = 0; i < cnt; ++i) {
-        const float wi = w[i];
-        a0 = fmaf(pw[lo + i], wi, a0);
-        a1 = fmaf(pw[520 + lo + i], wi, a1);
+      for (int i = 0; i < sched_len; ++i) {
+        const float2 e = s_sched[i * 32 + lane];
+        const int code = __float_as_int(e.y);
+        const int bin = code & 1023;
+        a0 = fmaf(pw[bin], e.x, a0);
+        a1 = fmaf(pw[520 + bin], e.x, a1);
+        if (code & 1024) {
+          const int m = code >> 11;
+          s_mel[m] = a0;
+          s_mel[kMels + m] = a1;
+          a0 = a1 = 0.f;
+        }
       }
-      const float sc = bn_scale[m], sh = bn_shift[m];
+      __syncwarp();
+      // dB + BN, coalesced
       const int ta = t0 + fa;
-      out[((int64_t)b * n_frames + ta) * kMels + m] = 10.0f * log10f(fmaxf(a0, 1e-10f)) * sc + sh;
-      if (ta + 1 < n_frames) out[((int64_t)b * n_frames + ta + 1) * kMels + m] = 10.0f * log10f(fmaxf(a1, 1e-10f)) * sc + sh;
+      for (int m = lane; m < kMels; m += 32) {
+        const float sc = bn_scale[m], sh = bn_shift[m];
+        out[((int64_t)b * n_frames + ta) * kMels + m] = 10.0f * log10f(fmaxf(s_mel[m], 1e-10f)) * sc + sh;
+        if (ta + 1 < n_frames)
+          out[((int64_t)b * n_frames + ta + 1) * kMels + m] = 10.0f * log10f(fmaxf(s_mel[kMels + m], 1e-10f)) * sc + sh;
+      }
     }
     __syncwarp();
   }
@@ -300,7 +339,7 @@ int launch_frontend(const float* wav, int batch, int64_t n_samples, const Fronte
     CNB_LAUNCH_OK();
     return 0;
   }
-  constexpr size_t smem = (size_t)(kFe2Span + kFftN + 64 + kFe2Warps * kFe2WarpScratch) * sizeof(float);
+  constexpr size_t smem = (size_t)(kFe2Span + kFftN + 64 + kMelSchedMax * 64 + kFe2Warps * kFe2WarpScratch) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     CNB_CUDA_OK(cudaFuncSetAttribute(frontend_warpfft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -308,7 +347,8 @@ int launch_frontend(const float* wav, int batch, int64_t n_samples, const Fronte
   }
   dim3 grid((n_frames + kFe2Frames - 1) / kFe2Frames, batch);
   frontend_warpfft_kernel<<<grid, kFe2Warps * 32, smem, stream>>>(wav, n_samples, n_frames, p.twiddle, p.mel_lo, p.mel_cnt,
-                                                                  p.mel_off, p.mel_w, apply_bn ? p.bn_scale : p.ones,
+                                                                  p.mel_off, p.mel_w, p.mel_sched, p.mel_sched_len,
+                                                                  apply_bn ? p.bn_scale : p.ones,
                                                                   apply_bn ? p.bn_shift : p.zeros, out);
   CNB_LAUNCH_OK();
   return 0;

@@ -7,12 +7,15 @@
 namespace cnb {
 
 // ---- front-end -------------------------------------------------------------------------------------------------
+constexpr int kMelSchedMax = 48;      // entries per lane of the balanced mel schedule (CoNeTTE's bank needs 29)
 struct FrontendParams {
   const float2* twiddle = nullptr;  // (1024) W_1024^j
   const int* mel_lo = nullptr;      // (224)
   const int* mel_cnt = nullptr;     // (224)
   const int* mel_off = nullptr;     // (224)
   const float* mel_w = nullptr;     // (nnz)
+  const float2* mel_sched = nullptr; // (mel_sched_len, 32): lane-balanced schedule of the same non-zeros, see frontend.cu
+  int mel_sched_len = 0;
   const float* bn_scale = nullptr;  // (224)
   const float* bn_shift = nullptr;  // (224)
   const float* ones = nullptr;      // (224)
