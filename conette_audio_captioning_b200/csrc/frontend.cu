@@ -141,11 +141,11 @@ frontend_kernel(const float* __restrict__ wav, int64_t n_samples, int n_frames,
 //   in shared memory; power of the two packed real spectra, sparse mel, dB and BatchNorm follow.  No block barrier after
 //   the initial staging, no bank conflicts in the FFT, ~1100 warp instructions per frame (v1: ~6x more + 9 barriers).
 // =====================================================================================================================
-constexpr int kFe2Warps = 8;
+constexpr int kFe2Warps = 6;                                          // x 2 CTAs per SM = 12 warps, prologues overlap
 constexpr int kFe2PairsPerWarp = 2;
 constexpr int kFe2Frames = kFe2Warps * kFe2PairsPerWarp * 2;           // 32 frames per CTA
 constexpr int kFe2Span = (kFe2Frames - 1) * kHop + kFftN;              // 10 944 samples
-constexpr int kFe2WarpScratch = 32 * 33 * 2 + 2 * 520;                 // transpose / spectrum tile + two power spectra
+constexpr int kFe2WarpScratch = 32 * 33 * 2;                           // transpose / spectrum tiles; power spectra and mel sums reuse them
 
 __device__ __forceinline__ constexpr int bitrev5(int k) {
   return ((k & 1) << 4) | ((k & 2) << 2) | (k & 4) | ((k & 8) >> 2) | ((k & 16) >> 4);
@@ -188,7 +188,7 @@ __device__ __forceinline__ void fft32_regs(float (&re)[32], float (&im)[32]) {
   }
 }
 
-__global__ void __launch_bounds__(kFe2Warps * 32, 1)
+__global__ void __launch_bounds__(kFe2Warps * 32, 2)
 frontend_warpfft_kernel(const float* __restrict__ wav, int64_t n_samples, int n_frames, const float2* __restrict__ twiddle,
                         const int* __restrict__ mel_lo, const int* __restrict__ mel_cnt, const int* __restrict__ mel_off,
                         const float* __restrict__ mel_w, const float2* __restrict__ mel_sched, int sched_len,
@@ -197,8 +197,8 @@ frontend_warpfft_kernel(const float* __restrict__ wav, int64_t n_samples, int n_
   float* s_wav = s_fe;                       // [kFe2Span]
   float* s_win = s_wav + kFe2Span;           // [1024] periodic Hann
   float2* s_tw = reinterpret_cast<float2*>(s_win + kFftN);  // [32] W_1024^{n2}
-  float2* s_sched = s_tw + 32;               // [kMelSchedMax][32] lane-balanced mel schedule (weight, bin | end | filter)
-  float* s_scr = reinterpret_cast<float*>(s_sched + kMelSchedMax * 32);  // per-warp scratch
+  float2* s_sched = s_tw + 32;               // [sched_len][32] lane-balanced mel schedule (weight, bin | end | filter)
+  float* s_scr = reinterpret_cast<float*>(s_sched + sched_len * 32);  // per-warp scratch
   __shared__ __align__(8) unsigned long long s_bar;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -240,7 +240,6 @@ frontend_warpfft_kernel(const float* __restrict__ wav, int64_t n_samples, int n_
 
   float* tile_re = s_scr + warp * kFe2WarpScratch;   // [32][33]   (later: spectrum re[1024])
   float* tile_im = tile_re + 32 * 33;                // [32][33]   (later: spectrum im[1024])
-  float* pw = tile_im + 32 * 33;                     // [2][520]
   const float2 w1 = s_tw[lane];
 
   for (int pp = 0; pp < kFe2PairsPerWarp; ++pp) {
@@ -290,22 +289,24 @@ frontend_warpfft_kernel(const float* __restrict__ wav, int64_t n_samples, int n_
       const float zr = tile_re[k], zi = tile_im[k], nr = tile_re[kn], ni = tile_im[kn];
       const float ar = 0.5f * (zr + nr), ai = 0.5f * (zi - ni);
       const float br = 0.5f * (zi + ni), bi = 0.5f * (zr - nr);
-      pw[k] = ar * ar + ai * ai;
-      pw[520 + k] = br * br + bi * bi;
+      // in place: entry k of the two tiles is read by this iteration only (its partner N-k >= 512 is never written)
+      tile_re[k] = ar * ar + ai * ai;
+      tile_im[k] = br * br + bi * bi;
     }
     __syncwarp();
     // sparse mel: every lane walks its balanced share of the 884 non-zeros as one flat list (api.cu builds it: the filters
     // are dealt longest-first to the least loaded lane).  Filter-per-lane rounds made the warp wait for the widest filter
     // of every round: 95 serial iterations instead of 29.  The sum order inside a filter is unchanged.
     {
-      float* s_mel = tile_re;   // [2][224]: the spectrum tiles are dead once the power spectra exist
+      const float *pwa = tile_re, *pwb = tile_im;   // power spectra of the two frames, bins 0..512
+      float* s_mel = tile_re + 520;   // [2][224] behind the first power spectrum (the upper half of the tile is dead by now)
       float a0 = 0.f, a1 = 0.f;
       for (int i = 0; i < sched_len; ++i) {
         const float2 e = s_sched[i * 32 + lane];
         const int code = __float_as_int(e.y);
         const int bin = code & 1023;
-        a0 = fmaf(pw[bin], e.x, a0);
-        a1 = fmaf(pw[520 + bin], e.x, a1);
+        a0 = fmaf(pwa[bin], e.x, a0);
+        a1 = fmaf(pwb[bin], e.x, a1);
         if (code & 1024) {
           const int m = code >> 11;
           s_mel[m] = a0;
@@ -339,10 +340,11 @@ int launch_frontend(const float* wav, int batch, int64_t n_samples, const Fronte
     CNB_LAUNCH_OK();
     return 0;
   }
-  constexpr size_t smem = (size_t)(kFe2Span + kFftN + 64 + kMelSchedMax * 64 + kFe2Warps * kFe2WarpScratch) * sizeof(float);
+  const size_t smem = (size_t)(kFe2Span + kFftN + 64 + p.mel_sched_len * 64 + kFe2Warps * kFe2WarpScratch) * sizeof(float);
+  constexpr size_t smem_max = (size_t)(kFe2Span + kFftN + 64 + kMelSchedMax * 64 + kFe2Warps * kFe2WarpScratch) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    CNB_CUDA_OK(cudaFuncSetAttribute(frontend_warpfft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CNB_CUDA_OK(cudaFuncSetAttribute(frontend_warpfft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     attr_set = true;
   }
   dim3 grid((n_frames + kFe2Frames - 1) / kFe2Frames, batch);
