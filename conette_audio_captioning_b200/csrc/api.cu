@@ -770,6 +770,47 @@ __global__ void copy_logits_kernel(const float* __restrict__ logits, float* __re
   }
 }
 
+// Teacher-forced scoring (reference pl_modules/conette.py:293-318 + nn/modules/ce_mean.py): log-softmax of one decode
+// position evaluated at the given next token, one CTA per caption row; pad targets (ignore_index = pad_id 0) score 0.
+__global__ void __launch_bounds__(256) score_token_kernel(const float* __restrict__ logits, const int* __restrict__ tokens,
+                                                          float* __restrict__ token_lprobs, int vocab, int pos, int steps) {
+  __shared__ float red_m[8], red_s[8];
+  const int r = blockIdx.x;
+  const float* row = logits + (int64_t)r * vocab;
+  const int tgt = tokens[(int64_t)r * (steps + 1) + pos + 1];
+  float m = -INFINITY, s = 0.f;
+  for (int v = threadIdx.x; v < vocab; v += 256) {
+    const float x = row[v];
+    if (x > m) { s = s * __expf(m - x) + 1.f; m = x; } else { s += __expf(x - m); }
+  }
+  for (int o = 16; o; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    const float mm = fmaxf(m, m2);
+    s = (mm == -INFINITY) ? 0.f : s * __expf(m - mm) + s2 * __expf(m2 - mm);
+    m = mm;
+  }
+  if ((threadIdx.x & 31) == 0) { red_m[threadIdx.x >> 5] = m; red_s[threadIdx.x >> 5] = s; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float mm = red_m[0];
+    for (int w = 1; w < 8; ++w) mm = fmaxf(mm, red_m[w]);
+    float ss = 0.f;
+    for (int w = 0; w < 8; ++w) ss += (red_m[w] == -INFINITY) ? 0.f : red_s[w] * expf(red_m[w] - mm);
+    token_lprobs[(int64_t)r * steps + pos] = (tgt == 0) ? 0.f : row[tgt] - mm - logf(ss);
+  }
+}
+// losses[r] = -mean over non-pad targets of token_lprobs[r, :] (CrossEntropyLossMean(ignore_index=pad, dim=1); count clamped to >= 1)
+__global__ void score_reduce_kernel(const float* __restrict__ token_lprobs, const int* __restrict__ tokens,
+                                    float* __restrict__ losses, int rows, int steps) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float s = 0.f;
+  int n = 0;
+  for (int p = 0; p < steps; ++p)
+    if (tokens[(int64_t)r * (steps + 1) + p + 1] != 0) { s -= token_lprobs[(int64_t)r * steps + p]; ++n; }
+  losses[r] = s / (float)max(n, 1);
+}
+
 // everything of one decode call that runs on the device, in launch order (this is what gets captured into a CUDA graph)
 static int decode_body(cnb_handle* h, const DecWs& w, BeamState bs, const float* frame_embs, const int32_t* lens,
                        const int64_t* bos_ids, const uint8_t* forbid, int batch, int min_len, const DecoderDims& dd,
@@ -1191,6 +1232,36 @@ int cnb_decoder_logits(cnb_handle* h, const float* frame_embs, const int32_t* le
                                                                                           dd.vocab, i, steps);
     CNB_LAUNCH_OK();
   }
+  return 0;
+}
+
+int cnb_score_captions(cnb_handle* h, const float* frame_embs, const int32_t* lens, const int64_t* captions, int32_t batch,
+                       int32_t tp, int32_t n_caps, int32_t cap_len, float* token_lprobs_out, float* losses_out, void* stream) {
+  CHECK_READY(h);
+  CNB_REQUIRE(frame_embs && lens && captions && token_lprobs_out && losses_out, "null buffer");
+  CNB_REQUIRE(n_caps > 0 && n_caps <= 8, "n_caps must be in [1, 8]");
+  CNB_REQUIRE(cap_len >= 2, "captions need at least BOS + one target token");
+  const int steps = cap_len - 1;
+  if (int rc = check_decode(h, batch, tp, n_caps, 0, steps)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rows = batch * n_caps;
+  DecoderDims dd{rows, n_caps, tp, steps, h->cfg.vocab_size};
+  DecWs w;
+  if (int rc = dec_prepare(h, batch, tp, rows, steps, &w)) return rc;
+  if (int rc = dec_project(h, frame_embs, batch, tp, w, st)) return rc;
+  WS(h, "tok0", int, (size_t)rows * cap_len, tok);
+  WS(h, "src0", int, (size_t)rows * steps, src);
+  tokens_i64_to_i32_kernel<<<(rows * cap_len + 255) / 256, 256, 0, st>>>(captions, tok, rows, cap_len, cap_len);
+  CNB_LAUNCH_OK();
+  iota_rows_kernel<<<(rows * steps + 255) / 256, 256, 0, st>>>(src, rows, steps);
+  CNB_LAUNCH_OK();
+  for (int i = 0; i < steps; ++i) {
+    if (int rc = dec_step(h, w, tok, src, lens, i, dd, h->zero_flag, st)) return rc;
+    score_token_kernel<<<rows, 256, 0, st>>>(w.logits, tok, token_lprobs_out, dd.vocab, i, steps);
+    CNB_LAUNCH_OK();
+  }
+  score_reduce_kernel<<<(rows + 127) / 128, 128, 0, st>>>(token_lprobs_out, tok, losses_out, rows, steps);
+  CNB_LAUNCH_OK();
   return 0;
 }
 

@@ -226,6 +226,21 @@ class Engine:
                                                out.data_ptr(), self._stream()))
         return out
 
+    def score_captions(self, frame_embs: Tensor, lens: Tensor, captions: Tensor) -> Tuple[Tensor, Tensor]:
+        """Teacher-forced scoring: captions (B, n_caps, L+1) i64 (position 0 = task BOS id, 0-padded) ->
+        (token_lprobs (B, n_caps, L), losses (B, n_caps)); reference pl_modules/conette.py:293-318, nn/modules/ce_mean.py."""
+        fe = self._dev(frame_embs, torch.float32)
+        b, tp, _ = fe.shape
+        lens = self._dev(lens, torch.int32)
+        caps = self._dev(captions, torch.int64)
+        assert caps.ndim == 3 and caps.shape[0] == b, "captions must be (B, n_caps, cap_len)"
+        n_caps, cap_len = int(caps.shape[1]), int(caps.shape[2])
+        tok_lp = torch.empty(b, n_caps, cap_len - 1, device=self.device, dtype=torch.float32)
+        losses = torch.empty(b, n_caps, device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.cnb_score_captions(self.handle, fe.data_ptr(), lens.data_ptr(), caps.data_ptr(), b, tp, n_caps,
+                                               cap_len, tok_lp.data_ptr(), losses.data_ptr(), self._stream()))
+        return tok_lp, losses
+
     def caption(self, wav: Tensor, x_lens: Optional[Tensor], bos_ids: Tensor, forbid_mask: Optional[Tensor], beam: int = 3,
                 min_len: int = 3, max_len: int = 20, with_tags: bool = True, trim: bool = True):
         """Device-resident path: wav (B, N) on the GPU -> ids; returns (preds, lprobs, mult_preds, mult_lprobs, clip_probs)."""

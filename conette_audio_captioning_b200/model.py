@@ -149,6 +149,57 @@ class CoNeTTEModel:
 
     forward = __call__
 
+    # ---- teacher-forced scoring (evaluation workflows) --------------------------------------------------------------------
+    def score(
+        self,
+        x: Union[Tensor, str, Iterable[str], Iterable[Tensor]],
+        mult_captions: Tensor,
+        sr: Union[None, int, Iterable[int]] = None,
+        x_shapes: Union[Tensor, None, List[Size]] = None,
+        preprocess: bool = True,
+        task: Union[str, List[str], None] = None,
+    ) -> Dict[str, Any]:
+        """Teacher-forced losses of given captions, the loss half of the reference's ``CoNeTTEPLM.test_step`` /
+        ``validation_step`` (pl_modules/conette.py:293-318 and :236-256): ``mult_captions`` (B, n_caps, L+1) i64 token ids
+        (or (B, L+1) for one caption per clip), 0-padded; position 0 is overwritten with the clip's task BOS id exactly like
+        ``replace_first_ids_in_batch`` (conette.py:526-541) on a copy.  Returns ``losses`` (B, n_caps) =
+        CrossEntropyLossMean(ignore_index=pad, dim=1) of logits(caps[:, :-1]) against caps[:, 1:], ``loss`` = their mean,
+        and ``token_lprobs`` (B, n_caps, L)."""
+        caps = torch.as_tensor(mult_captions)
+        if caps.ndim == 2:
+            caps = caps[:, None, :]
+        if caps.ndim != 3 or caps.is_floating_point():
+            raise ValueError(f"Invalid captions shape/dtype {tuple(caps.shape)} {caps.dtype}; expected integer ids (B, n_caps, L+1)")
+        if preprocess:
+            wav, x_lens = load_resample(x, sr, x_shapes, resampler=self.engine.resample)
+            bsize = wav.shape[0]
+        else:
+            assert isinstance(x, Tensor) and isinstance(x_shapes, Tensor)
+            bsize = len(x)
+        if caps.shape[0] != bsize:
+            raise ValueError(f"Invalid number of captions with input. (found {caps.shape[0]} caption sets but {bsize} elements)")
+        tasks = [self.default_task] * bsize if task is None else ([task] * bsize if isinstance(task, str) else list(task))
+        if len(tasks) != bsize:
+            raise ValueError(f"Invalid number of tasks with input. (found {len(tasks)} tasks but {bsize} elements)")
+        for t in tasks:
+            if t not in self.config.task_names:
+                raise ValueError(f"Invalid argument tasks={tasks}. (task {t} is not in {self.config.task_names})")
+        parts = [t.split("_") for t in tasks]
+        bos_ids = self._task_token_ids([p[0] for p in parts], ["_".join(p[1:]) if len(p) >= 2 else None for p in parts])
+        caps = caps.to("cpu", torch.int64).clone()
+        caps[:, :, 0] = bos_ids.to("cpu")[:, None]
+        if preprocess:
+            n = int(wav.shape[1])
+            frame_embs, _ = self.engine.encoder(wav, with_tags=False)
+            red = n // int(frame_embs.shape[1])  # reference convnext.py:312-315: float32 divide, round half to even
+            x_lens = torch.full((bsize,), n, dtype=torch.int64) if x_lens is None else x_lens.to("cpu", torch.int64)
+            lens = x_lens.to(torch.float32).div(red).round().to(torch.int32)
+        else:
+            frame_embs, lens = x, x_shapes[:, 1].to(torch.int32)
+        tok_lp, losses = self.engine.score_captions(frame_embs, lens, caps)
+        losses = losses.cpu()
+        return {"losses": losses, "loss": losses.mean(), "token_lprobs": tok_lp.cpu(), "tasks": tasks}
+
     # ---- streaming (dataset captioning / serving) --------------------------------------------------------------------------
     def stream(self, batches: Iterable[Any], sr: Union[None, int, Iterable[int]] = None, task: Union[str, List[str], None] = None,
                threshold: Union[float, Tensor] = 0.3, **kwargs: Any) -> Iterable[Dict[str, Any]]:

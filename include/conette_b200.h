@@ -99,6 +99,16 @@ int cnb_decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, cons
 /* S3 (parity only): teacher-forced decoder logits. tokens (B, steps) i64 -> logits (B, steps, V) f32. */
 int cnb_decoder_logits(cnb_handle* h, const float* frame_embs, const int32_t* lens, const int64_t* tokens, int32_t batch,
                        int32_t n_frames, int32_t steps, float* logits_out, void* stream);
+/* Teacher-forced scoring of given captions: replaces the loss loop of CoNeTTEPLM.test_step /
+ * validation_step, reference src/conette/pl_modules/conette.py:293-318 (decode_audio(..., "forcing", caps_in=caps[:, :-1]),
+ * nn/decoding/forcing.py:12-76) + CrossEntropyLossMean(ignore_index=pad_id, dim=1) (nn/modules/ce_mean.py:10-40).
+ * captions (B, n_caps, cap_len) i64, position 0 = the clip's task BOS id, right-padded with pad_id 0.  Outputs:
+ * token_lprobs (B, n_caps, cap_len-1) f32 = log-softmax of position p evaluated at token p+1 (0 where that token is pad);
+ * losses (B, n_caps) f32 = -mean of token_lprobs over the non-pad targets.  The (B, cap_len-1, V) logits are never
+ * written to HBM beyond one (B*n_caps, V) step buffer; cross-attention K|V are computed once per clip. */
+int cnb_score_captions(cnb_handle* h, const float* frame_embs, const int32_t* lens, const int64_t* captions, int32_t batch,
+                       int32_t n_frames, int32_t n_caps, int32_t cap_len, float* token_lprobs_out, float* losses_out,
+                       void* stream);
 
 /* S1+S2: waveform -> token ids, all buffers on the device. x_lens_host (B) i64 = true sample counts (HOST; NULL = all
  * n_samples) from which frame lens = round_half_even(len / (N // T')) are derived (convnext.py:312-315).

@@ -33,7 +33,43 @@ def checksum(sd) -> np.ndarray:
     return np.array([float(sd[k].double().sum()) for k in CHECK_KEYS] + [float(sd[k].double().abs().sum()) for k in CHECK_KEYS])
 
 
+def make_score_fixture(sd, model) -> None:
+    """score.npz: teacher-forced losses of the reference's test_step loop (pl_modules/conette.py:307-313) on given frame
+    embeddings, through the REAL ``CoNeTTEPLM.encode_audio`` / ``decode_audio("forcing")`` / ``CrossEntropyLossMean``."""
+    g = torch.Generator().manual_seed(91)
+    b, tp, n_caps, cap_len = 4, 9, 3, 12
+    fe = torch.randn(b, tp, 768, generator=g)
+    lens = torch.tensor([9, 4, 7, 1])
+    bos_ids = sd["model.task_id_to_token_id"][torch.tensor([0, 1, 2, 0])]
+    caps = torch.zeros(b, n_caps, cap_len, dtype=torch.long)
+    for i in range(b):
+        for j in range(n_caps):
+            n_words = cap_len - 2 if (i, j) == (0, 0) else int(torch.randint(1, cap_len - 2, (1,), generator=g))
+            caps[i, j, 0] = bos_ids[i]
+            caps[i, j, 1 : 1 + n_words] = torch.randint(4, 300, (n_words,), generator=g)
+            caps[i, j, 1 + n_words] = 2
+    plm = model.model
+    crit = ref_loader.ref_module("nn.loss.ce_mean").CrossEntropyLossMean(ignore_index=0, dim=1)
+    audio_shape = torch.stack([torch.full((b,), 768), lens], dim=1)
+    losses = torch.empty(b, n_caps)
+    tok_lp = torch.empty(b, n_caps, cap_len - 1)
+    with torch.no_grad():
+        enc_outs = plm.encode_audio(fe, audio_shape)  # FrameIdentEncoder: (B, T', 768), lens = audio_shape[:, 1]
+        for i in range(n_caps):
+            logits = plm.decode_audio(enc_outs, "forcing", caps_in=caps[:, i, :-1])
+            losses[:, i] = crit(logits, caps[:, i, 1:])
+            lp = torch.log_softmax(logits, dim=1).gather(1, caps[:, i, 1:][:, None, :])[:, 0]
+            tok_lp[:, i] = torch.where(caps[:, i, 1:] != 0, lp, torch.zeros(()))
+    np.savez_compressed(os.path.join(GOLDEN, "score.npz"), frame_embs=fe.numpy(), lens=lens.numpy(), captions=caps.numpy(),
+                        losses=losses.numpy(), token_lprobs=tok_lp.numpy(), weights_checksum=checksum(sd))
+
+
 def main() -> None:
+    if "--only-score" in sys.argv:  # added after the other fixtures were committed: leaves them untouched
+        torch.manual_seed(0)
+        sd = synth.make_state_dict(**SD_KW)
+        make_score_fixture(sd, ref_loader.build_reference_model(sd, synth.make_corpus(300)))
+        return
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     sd = synth.make_state_dict(**SD_KW)
@@ -103,6 +139,7 @@ def main() -> None:
         mult_preds=out["mult_preds"].numpy(), mult_lprobs=out["mult_lprobs"].numpy(),
         tags_probs=out["tags_probs"].numpy(), weights_checksum=checksum(sd),
     )
+    make_score_fixture(sd, model)
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 

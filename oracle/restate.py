@@ -342,6 +342,26 @@ def beam_search(
     return best_preds, best_lp, g_preds, g_lp
 
 
+def score_captions(sd: SD, frame_embs_btc: Tensor, lens: Tensor, captions: Tensor) -> Tuple[Tensor, Tensor]:
+    """Teacher-forced scoring (reference pl_modules/conette.py:293-318: ``decode_audio(enc, "forcing", caps_in=caps[:, :-1])``
+    through nn/decoding/forcing.py:12-76, then ``CrossEntropyLossMean(ignore_index=pad_id, dim=1)`` nn/loss/ce_mean.py:10-40
+    against ``caps[:, 1:]``).  captions (B, n_caps, L+1) i64, position 0 = task BOS id, 0-padded.
+    Returns token_lprobs (B, n_caps, L) (0 at pad targets) and losses (B, n_caps).  Trailing pads never influence a non-pad
+    position under the causal mask, so the key-padding mask of forcing.py:49 needs no restatement."""
+    b, n_caps, cap_len = captions.shape
+    steps = cap_len - 1
+    rows = captions.reshape(b * n_caps, cap_len)
+    dec = KVDecoder(sd, project(sd, frame_embs_btc), lens, beam=n_caps, max_len=steps)
+    tok_lp = torch.zeros(b * n_caps, steps)
+    for i in range(steps):
+        lp = torch.log_softmax(dec.step(rows[:, i], i), dim=-1)
+        tgt = rows[:, i + 1]
+        tok_lp[:, i] = torch.where(tgt != 0, lp.gather(1, tgt[:, None])[:, 0], torch.zeros(()))
+    non_pad = rows[:, 1:] != 0
+    losses = -(tok_lp * non_pad).sum(1) / non_pad.sum(1).clamp(min=1)
+    return tok_lp.reshape(b, n_caps, steps), losses.reshape(b, n_caps)
+
+
 def caption(sd: SD, wav: Tensor, x_lens: Optional[Tensor], bos_ids: Tensor, beam: int = 3, min_len: int = 3,
             max_len: int = 20, forbid_mask: Optional[Tensor] = None) -> Dict[str, Tensor]:
     """waveform (B, N) -> dict like reference ``CoNeTTEPLM.forward`` minus the detokenised strings."""

@@ -33,6 +33,14 @@ def test_decoder_logits_golden(small_sd):
         torch.testing.assert_close(logits, t(fx["tf_logits"][:, i]), rtol=1e-4, atol=5e-5)
 
 
+def test_teacher_forced_scoring_golden(small_sd):
+    fx = load("score.npz")
+    assert_weights_match(small_sd, fx)
+    tok_lp, losses = restate.score_captions(small_sd, t(fx["frame_embs"]), t(fx["lens"]), t(fx["captions"]))
+    torch.testing.assert_close(losses, t(fx["losses"]), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(tok_lp, t(fx["token_lprobs"]), rtol=1e-4, atol=1e-4)
+
+
 def test_beam_search_golden(small_sd):
     fx = load("decode.npz")
     mem, lens, bos_ids = t(fx["mem"]), t(fx["lens"]), t(fx["bos_ids"])

@@ -287,6 +287,67 @@ def test_decoder_logits_vs_oracle(eng_parity, small_sd):
         assert torch.equal(logits[:, i].argmax(-1), ref.argmax(-1))
 
 
+@pytest.mark.parametrize("precision", ["parity", "fast"])
+def test_teacher_forced_scoring_golden(small_sd, precision):
+    """cnb_score_captions against the REAL reference's test_step loss loop (tests/golden/score.npz); the scoring path is the
+    fp32 KV-cached step in both precision modes.  Tolerance: losses 1e-4 abs, per-token log-probs 2e-4."""
+    from conette_audio_captioning_b200.engine import Engine
+
+    fx = load("score.npz")
+    assert_weights_match(small_sd, fx)
+    eng = Engine(small_sd, vocab_size=small_sd["model.decoder.classifier.weight"].shape[0], precision=precision)
+    tok_lp, losses = eng.score_captions(t(fx["frame_embs"]), t(fx["lens"]), t(fx["captions"]))
+    torch.testing.assert_close(losses.cpu(), t(fx["losses"]), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(tok_lp.cpu(), t(fx["token_lprobs"]), rtol=2e-4, atol=2e-4)
+    assert (tok_lp.cpu()[t(fx["captions"])[:, :, 1:] == 0] == 0).all()  # pad targets score exactly 0
+    # one caption per clip, every row full length, cap_len = 2 (a single target): edge shapes
+    caps = t(fx["captions"])
+    tl1, l1 = eng.score_captions(t(fx["frame_embs"]), t(fx["lens"]), caps[:, :1, :2])
+    torch.testing.assert_close(tl1.cpu()[:, 0, 0], tok_lp.cpu()[:, 0, 0], rtol=0, atol=1e-6)
+    torch.testing.assert_close(l1.cpu()[:, 0], -tok_lp.cpu()[:, 0, 0], rtol=0, atol=1e-6)
+    with pytest.raises(Exception):
+        eng.score_captions(t(fx["frame_embs"]), t(fx["lens"]), caps[:, :, :1])
+    eng.close()
+
+
+def test_model_score_vs_oracle(small_sd):
+    """CoNeTTEModel.score (waveform -> losses, position 0 replaced by the task BOS id) vs the oracle chain
+    encoder -> projection -> teacher forcing -> CrossEntropyLossMean, parity mode, ragged clips and mixed tasks."""
+    from oracle import restate
+
+    model = _model(small_sd, "parity")
+    wav = synth.make_audio(3, 48000, seed=21)
+    wav[2, :, 30000:] = 0
+    x_shapes = torch.tensor([[48000], [48000], [30000]])
+    tasks = ["clotho", "audiocaps", "wavcaps_audioset_sl"]
+    g = torch.Generator().manual_seed(3)
+    caps = torch.zeros(3, 2, 10, dtype=torch.long)
+    for i in range(3):
+        for j in range(2):
+            n_words = int(torch.randint(1, 8, (1,), generator=g))
+            caps[i, j, 0] = 1  # plain <bos>: the call must replace it
+            caps[i, j, 1 : 1 + n_words] = torch.randint(4, 300, (n_words,), generator=g)
+            caps[i, j, 1 + n_words] = 2
+    out = model.score(wav, caps, sr=32000, x_shapes=x_shapes, task=tasks)
+    assert caps[:, :, 0].eq(1).all()  # the caller's tensor is not mutated
+    bos = small_sd["model.task_id_to_token_id"][torch.tensor([synth.TASK_NAMES.index(k) for k in tasks])]
+    ref_caps = caps.clone()
+    ref_caps[:, :, 0] = bos[:, None]
+    enc = restate.encoder(small_sd, wav[:, 0], x_shapes[:, 0])
+    ref_lp, ref_losses = restate.score_captions(small_sd, enc["frame_embs"].transpose(1, 2), enc["frame_embs_lens"], ref_caps)
+    torch.testing.assert_close(out["losses"], ref_losses, rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(out["token_lprobs"], ref_lp, rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(out["loss"], ref_losses.mean(), rtol=1e-3, atol=1e-3)
+    assert out["tasks"] == tasks and out["losses"].shape == (3, 2)
+    single = model.score(wav, caps[:, 0], sr=32000, x_shapes=x_shapes, task=tasks)  # (B, L+1) form
+    torch.testing.assert_close(single["losses"][:, 0], out["losses"][:, 0], rtol=0, atol=1e-6)
+    with pytest.raises(ValueError):
+        model.score(wav, caps[:2], sr=32000, task=tasks)
+    with pytest.raises(ValueError):
+        model.score(wav, caps.float(), sr=32000, task=tasks)
+    model.engine.close()
+
+
 TIE_EPS = 2e-4
 CASES = [(1, 3, 20, "content_words"), (2, 0, 20, "content_words"), (3, 3, 20, "content_words"), (3, 3, 20, "none"),
          (3, 0, 5, "all"), (5, 3, 20, "content_words"), (5, 3, 30, "all"), (3, 2, 12, "content_words")]

@@ -134,6 +134,43 @@ def test_beam_search_matches_reference_generate(ref_small, small_sd, beam, min_l
         assert (ref[2] == 2).any()
 
 
+def _random_captions(b, n_caps, cap_len, bos_ids, seed):
+    """(B, n_caps, cap_len) ids: task BOS, words, EOS, then pads -- ragged lengths, one caption filling the whole row."""
+    g = torch.Generator().manual_seed(seed)
+    caps = torch.zeros(b, n_caps, cap_len, dtype=torch.long)
+    for i in range(b):
+        for j in range(n_caps):
+            n_words = cap_len - 2 if (i, j) == (0, 0) else int(torch.randint(1, cap_len - 2, (1,), generator=g))
+            caps[i, j, 0] = bos_ids[i]
+            caps[i, j, 1 : 1 + n_words] = torch.randint(4, 300, (n_words,), generator=g)
+            caps[i, j, 1 + n_words] = 2
+    return caps
+
+
+def test_teacher_forced_scoring_matches_reference(ref_small, small_sd):
+    """restate.score_captions == the reference's test_step loss loop (conette.py:307-313) run with the real modules."""
+    g = torch.Generator().manual_seed(1)
+    b, tp, n_caps, cap_len = 4, 9, 3, 12
+    fe = torch.randn(b, tp, 768, generator=g)
+    lens = torch.tensor([9, 4, 7, 1])
+    bos_ids = small_sd["model.task_id_to_token_id"][torch.tensor([0, 1, 2, 0])]
+    caps = _random_captions(b, n_caps, cap_len, bos_ids, seed=2)
+    tok_lp, losses = restate.score_captions(small_sd, fe, lens, caps)
+
+    plm = ref_small.model
+    crit = ref_loader.ref_module("nn.loss.ce_mean").CrossEntropyLossMean(ignore_index=0, dim=1)
+    mem = restate.project(small_sd, fe).transpose(1, 2).contiguous()
+    enc_outs = {"frame_embs": mem, "frame_embs_pad_mask": torch.arange(tp)[None, :] >= lens[:, None]}
+    with torch.no_grad():
+        for i in range(n_caps):
+            logits = plm.decode_audio(enc_outs, "forcing", caps_in=caps[:, i, :-1])  # (B, V, L)
+            ref_loss = crit(logits, caps[:, i, 1:])
+            torch.testing.assert_close(losses[:, i], ref_loss, rtol=1e-5, atol=1e-5)
+            ref_lp = torch.log_softmax(logits, dim=1).gather(1, caps[:, i, 1:][:, None, :])[:, 0]
+            ref_lp = torch.where(caps[:, i, 1:] != 0, ref_lp, torch.zeros(()))
+            torch.testing.assert_close(tok_lp[:, i], ref_lp, rtol=1e-4, atol=1e-4)
+
+
 def test_end_to_end_matches_reference_model(ref_small, small_sd):
     wav = synth.make_audio(3, 64000, seed=3)
     wav[2, :, 40000:] = 0
