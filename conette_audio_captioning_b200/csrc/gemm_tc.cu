@@ -9,9 +9,19 @@
 //   warps 2..17 epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias / GELU / layer-scale+residual -> global stores
 //               (GELU in this bf16 path = 0.5x(1+tanh(x(a1+a3x^2+a5x^4))), a minimax fit of the erf form, max abs error
 //               2.5e-5 + the 2^-11 relative error of tanh.approx -- both below the bf16 rounding of the stored hidden)
+// CTA pairs (PAIR = true, large M): two CTAs of a 2-CTA cluster (one TPC) work on one 256 x BLOCK_N tile with
+// tcgen05.mma.cta_group::2 issued by the even CTA.  Each CTA TMA-loads its own 128 rows of A but only HALF of the W tile
+// (BLOCK_N/2 rows), so the L2 -> shared-memory fill per flop drops by 30 % at BLOCK_N = 192 (the fill rate, not the tensor
+// pipe, bounded the 1-CTA kernel in stages 3-4: profiles/r1_ncu_gemm_tc_stage3.txt) and the smaller stages allow a deeper
+// ring.  Cross-CTA protocol: both producers complete bytes on the LEADER's full barrier; tcgen05.commit multicasts the
+// "stage free" / "accumulator ready" arrivals to both CTAs; the epilogue warps of both CTAs arrive on the leader's
+// "accumulator drained" barrier; cluster barriers bracket barrier init / TMEM allocation and teardown.
 // Pipelines: STAGES-deep smem ring (full/empty mbarriers) and a 2-deep TMEM accumulator ring (tmem_full/tmem_empty) so
 // the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
+
+#include <limits.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <unordered_map>
@@ -38,9 +48,16 @@ constexpr int kTcThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA, war
 // ~1.8 TB/s).  Instead 64-column passes are written into 128B-swizzled staging tiles in shared memory and leave through
 // TMA bulk tensor stores; the layer-scale/residual epilogue TMA-loads the fp32 residual tile into the same staging tiles
 // at tile start and updates it in place.
-template <int BLOCK_N, int EPI, typename OutT>
+template <int BLOCK_N, int EPI, typename OutT, bool PAIR = false>
 struct TcCfg {
-  static constexpr bool kResid = (EPI == EPI_SCALE_RESID);
+  // layer-scale + residual: by default scale * (acc + bias) leaves through a TMA REDUCE-ADD store into x (the add happens
+  // in L2, no residual tile is loaded: 64 KB instead of 96 KB of staging at BLOCK_N = 192, i.e. one more ring stage, and a
+  // third less SM <-> L2 traffic in the epilogue).  -DCNB_PW2_RESID_LOAD=1 restores the load / add / store form.
+#ifndef CNB_PW2_RESID_LOAD
+#define CNB_PW2_RESID_LOAD 0
+#endif
+  static constexpr bool kResid = (EPI == EPI_SCALE_RESID) && CNB_PW2_RESID_LOAD;
+  static constexpr bool kReduce = (EPI == EPI_SCALE_RESID) && !CNB_PW2_RESID_LOAD;
   static constexpr int kElt = (int)sizeof(OutT);
   static constexpr int kBoxCols = 128 / kElt;                 // 64 bf16 / 32 fp32 per 128-byte swizzle row
   static constexpr int kBoxBytes = kBlockM * 128;             // 16 KB
@@ -52,13 +69,17 @@ struct TcCfg {
   // pass p+1 knows that the tile of pass p-1 = the tile of pass p+2 is free); plain fp32 outputs (32 KB tiles) ping-pong
   static constexpr int kStagingBufs = kResid ? kPasses : (kElt == 2 ? 3 : 2);
   static constexpr bool kOneBar = !kResid && kStagingBufs == 3;
-  static constexpr int kVecFloats = kResid ? 2 * 768 : kMaxN; // bias (| scale) staged in smem
+  static constexpr int kVecFloats = (kResid || kReduce) ? 2 * 768 : kMaxN; // bias (| scale) staged in smem
   static constexpr int kABytes = kBlockM * kBlockK * 2;
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kTileM = PAIR ? 2 * kBlockM : kBlockM;     // rows of one MMA tile (both CTAs of a pair)
+  static constexpr int kBRows = PAIR ? BLOCK_N / 2 : BLOCK_N;     // W rows this CTA loads per k-block
+  static constexpr int kBBytes = kBRows * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kFullTx = PAIR ? 2 * kStageBytes : kStageBytes;  // bytes completed on the (leader's) full barrier
+  static constexpr int kMaxStages = PAIR ? 6 : 4;
   static constexpr int kFixed = kStagingBufs * kPassBytes + kVecFloats * 4 + 512 /*barriers*/ + 1024 /*align*/;
   static constexpr int kStagesFit = (232448 - kFixed) / kStageBytes;
-  static constexpr int kStages = kStagesFit > 4 ? 4 : kStagesFit;
+  static constexpr int kStages = kStagesFit > kMaxStages ? kMaxStages : kStagesFit;
   static_assert(kStages >= 2, "shared memory budget");
   static constexpr int kStagingOff = kStages * kStageBytes;
   static constexpr int kBarOff = kStagingOff + kStagingBufs * kPassBytes;
@@ -67,13 +88,16 @@ struct TcCfg {
   static constexpr int kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
 };
 
-template <int BLOCK_N, int EPI, typename OutT>
+template <int BLOCK_N, int EPI, typename OutT, bool PAIR>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_resid, int M, int N, int K,
                EpiParams ep) {
-  using C = TcCfg<BLOCK_N, EPI, OutT>;
+  using C = TcCfg<BLOCK_N, EPI, OutT, PAIR>;
   constexpr int kStages = C::kStages;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;            // 0 = leader (issues the MMAs)
+  const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // persistent worker index (a CTA or a CTA pair)
+  const int n_units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024-byte alignment
   uint8_t* smem_aligned = smem_raw + (base - smem_u32(smem_raw));
@@ -92,12 +116,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   float* s_scale = s_bias + 768;  // only used by the residual epilogue (N <= 768)
   for (int i = threadIdx.x; i < N; i += kTcThreads) {
     s_bias[i] = ep.bias[i];
-    if (C::kResid) s_scale[i] = ep.scale[i];
+    if (C::kResid || C::kReduce) s_scale[i] = ep.scale[i];
   }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = N / BLOCK_N;
-  const int tiles_m = (M + kBlockM - 1) / kBlockM;
+  const int tiles_m = (M + C::kTileM - 1) / C::kTileM;
   const int n_tiles = tiles_m * tiles_n;
   const int k_blocks = (K + kBlockK - 1) / kBlockK;
 
@@ -108,19 +132,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), kEpiWarps);   // one arrival per epilogue warp
+      mbar_init(tempty_bar(s), PAIR ? 2 * kEpiWarps : kEpiWarps);   // one arrival per epilogue warp (of both CTAs)
     }
     mbar_init(resid_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {  // the same warp of both CTAs allocates the same columns in both tensor memories
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(C::kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything is signalled across the pair
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -131,17 +162,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t ubars = sb + C::kBarOff;
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const uint32_t urank = __shfl_sync(0xffffffffu, cta_rank, 0);
+      for (int t = unit; t < n_tiles; t += n_units) {
         const int m_blk = t / tiles_n, n_blk = t - m_blk * tiles_n;
         for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(ubars + 8u * (kStages + s), ph ^ 1);   // empty
+          mbar_wait(ubars + 8u * (kStages + s), ph ^ 1);   // empty (this CTA's own copy)
           if (elect_one()) {
             const uint32_t a_dst = sb + s * C::kStageBytes;
             const uint32_t b_dst = a_dst + C::kABytes;
             const uint32_t full = ubars + 8u * s;
-            mbar_expect_tx(full, C::kStageBytes);
-            tma_load_2d(a_dst, &map_a, kb * kBlockK, m_blk * kBlockM, full);
-            tma_load_2d(b_dst, &map_w, kb * kBlockK, n_blk * BLOCK_N, full);
+            if (PAIR) {
+              const uint32_t lead_full = mapa_cluster(full, 0);
+              if (urank == 0) mbar_expect_tx(full, C::kFullTx);   // the bytes of both CTAs land on the leader's barrier
+              tma_load_2d_pair(a_dst, &map_a, kb * kBlockK, m_blk * C::kTileM + (int)urank * kBlockM, lead_full);
+              tma_load_2d_pair(b_dst, &map_w, kb * kBlockK, n_blk * BLOCK_N + (int)urank * C::kBRows, lead_full);
+            } else {
+              mbar_expect_tx(full, C::kStageBytes);
+              tma_load_2d(a_dst, &map_a, kb * kBlockK, m_blk * kBlockM, full);
+              tma_load_2d(b_dst, &map_w, kb * kBlockK, n_blk * BLOCK_N, full);
+            }
           }
           __syncwarp();
           if (++s == kStages) { s = 0; ph ^= 1; }
@@ -149,16 +188,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer (pairs: the leader CTA only) =====================
     // the whole warp runs the loop on warp-uniform values, one elected lane issues (see elect_one in tc_ptx.cuh)
-    {
+    if (cta_rank == 0) {
       const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t sb = __shfl_sync(0xffffffffu, base, 0);
       const uint32_t ubars = sb + C::kBarOff;
-      constexpr uint32_t idesc = make_idesc(kBlockM, BLOCK_N);
+      constexpr uint32_t idesc = make_idesc(C::kTileM, BLOCK_N);
       int s = 0, as = 0;
       uint32_t ph = 0, aph = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int t = unit; t < n_tiles; t += n_units) {
         mbar_wait(ubars + 8u * (2 * kStages + 2 + as), aph ^ 1);  // tempty: the epilogue has drained this accumulator stage
         tcgen05_fence_after();
         const uint32_t tmem_d = tb + (uint32_t)(as * BLOCK_N);
@@ -172,10 +211,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k) {
               // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in (addr >> 4) units
-              tcgen05_mma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              if (PAIR) tcgen05_mma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              else tcgen05_mma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
             }
-            tcgen05_commit(ubars + 8u * (kStages + s));  // empty: frees the smem stage once these MMAs have read it
-            if (kb == k_blocks - 1) tcgen05_commit(ubars + 8u * (2 * kStages + as));   // tfull: accumulator complete -> epilogue
+            if (PAIR) {  // one arrival on the barrier at this offset in both CTAs
+              tcgen05_commit_pair(ubars + 8u * (kStages + s));
+              if (kb == k_blocks - 1) tcgen05_commit_pair(ubars + 8u * (2 * kStages + as));
+            } else {
+              tcgen05_commit(ubars + 8u * (kStages + s));  // empty: frees the smem stage once these MMAs have read it
+              if (kb == k_blocks - 1) tcgen05_commit(ubars + 8u * (2 * kStages + as));   // tfull: accumulator complete -> epilogue
+            }
           }
           __syncwarp();
           if (++s == kStages) { s = 0; ph ^= 1; }
@@ -198,8 +243,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int as = 0;
     uint32_t aph = 0, rph = 0;
     uint32_t pass_ctr = 0;                    // running pass counter: plain outputs ping-pong the two staging tiles
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const uint32_t lead_tempty0 = PAIR ? mapa_cluster(tempty_bar(0), 0) : tempty_bar(0);
+    for (int t = unit; t < n_tiles; t += n_units) {
       const int m_blk = t / tiles_n, n_blk = t - m_blk * tiles_n;
+      const int m_row0 = m_blk * C::kTileM + (int)cta_rank * kBlockM;   // first output row of this CTA's half of the tile
       if (C::kResid && lead_warp) {
         if (elect_one()) {
           // previous tile's stores must have finished reading the staging tiles; then fetch this tile's residual rows
@@ -217,8 +264,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int bx = 0; bx < C::kBoxesPerPass; ++bx) {
               const int c = 64 * i + bx * C::kBoxCols;
               if (c < BLOCK_N)
-                tma_load_2d(ustg + i * C::kPassBytes + bx * C::kBoxBytes, &map_resid, n_blk * BLOCK_N + c, m_blk * kBlockM,
-                            uresid_bar);
+                tma_load_2d(ustg + i * C::kPassBytes + bx * C::kBoxBytes, &map_resid, n_blk * BLOCK_N + c, m_row0, uresid_bar);
             }
         }
         __syncwarp();
@@ -237,7 +283,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tmem_ld_wait();
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(lead_tempty0 + 8u * as);   // the leader's MMA warp waits for both CTAs' epilogues
+        else mbar_arrive(tempty_bar(as));
+      }
       if (C::kResid) {
         mbar_wait(resid_bar, rph);
         rph ^= 1;
@@ -293,6 +342,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 v2[2 * q] = __ffma2_rn(ss2[2 * q], v2[2 * q], make_float2(x.x, x.y));
                 v2[2 * q + 1] = __ffma2_rn(ss2[2 * q + 1], v2[2 * q + 1], make_float2(x.z, x.w));
               }
+              if (C::kReduce) {
+                v2[2 * q] = __fmul2_rn(ss2[2 * q], v2[2 * q]);
+                v2[2 * q + 1] = __fmul2_rn(ss2[2 * q + 1], v2[2 * q + 1]);
+              }
               st_shared_v4(addr, __float_as_uint(v[i][4 * q]), __float_as_uint(v[i][4 * q + 1]),
                            __float_as_uint(v[i][4 * q + 2]), __float_as_uint(v[i][4 * q + 3]));
             }
@@ -306,7 +359,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int bx = 0; bx < C::kBoxesPerPass; ++bx) {
               const int c = 64 * i + bx * C::kBoxCols;
-              if (c < BLOCK_N) tma_store_2d(&map_out, utile + bx * C::kBoxBytes, n_blk * BLOCK_N + c, m_blk * kBlockM);
+              if (c < BLOCK_N) {
+                if (C::kReduce) tma_reduce_add_2d(&map_out, utile + bx * C::kBoxBytes, n_blk * BLOCK_N + c, m_row0);
+                else tma_store_2d(&map_out, utile + bx * C::kBoxBytes, n_blk * BLOCK_N + c, m_row0);
+              }
             }
             bulk_commit();
             if (C::kOneBar) bulk_wait_read<1>();
@@ -325,10 +381,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // neither CTA leaves (or frees tensor memory) while the other may still signal it
+  else __syncthreads();
   if (warp == 1) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::kTmemCols) : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::kTmemCols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::kTmemCols) : "memory");
   }
 }
 
@@ -448,36 +508,73 @@ int tc_make_map_nhwc_f32(void* map_out, const float* ptr, int batch, int h, int 
   return 0;
 }
 
-template <int BLOCK_N, int EPI, typename OutT>
+template <int BLOCK_N, int EPI, typename OutT, bool PAIR>
 static int launch_cfg(const __nv_bfloat16* a, const __nv_bfloat16* w, int m, int n, int k, const EpiParams& ep, OutT* out,
                       cudaStream_t stream) {
-  using C = TcCfg<BLOCK_N, EPI, OutT>;
+  using C = TcCfg<BLOCK_N, EPI, OutT, PAIR>;
   CUtensorMap map_a, map_w, map_out, map_resid;
   if (int rc = make_map(&map_a, a, (uint64_t)m, (uint64_t)k, kBlockM, 2)) return rc;
-  if (int rc = make_map(&map_w, w, (uint64_t)n, (uint64_t)k, BLOCK_N, 2)) return rc;
+  if (int rc = make_map(&map_w, w, (uint64_t)n, (uint64_t)k, C::kBRows, 2)) return rc;
   if (int rc = make_map(&map_out, out, (uint64_t)m, (uint64_t)n, kBlockM, (int)sizeof(OutT))) return rc;
   map_resid = map_out;
   if (C::kResid)
     if (int rc = make_map(&map_resid, ep.resid, (uint64_t)m, (uint64_t)n, kBlockM, 4)) return rc;
-  auto kern = gemm_tc_kernel<BLOCK_N, EPI, OutT>;
+  auto kern = gemm_tc_kernel<BLOCK_N, EPI, OutT, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
     CNB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
     attr_set = true;
   }
-  const int n_tiles = (int)ceil_div(m, kBlockM) * (n / BLOCK_N);
+  const int n_tiles = (int)ceil_div(m, C::kTileM) * (n / BLOCK_N);
+  if (PAIR) {
+    const int pairs = n_tiles < kNumSMs / 2 ? n_tiles : kNumSMs / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = C::kTotal;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CNB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, map_a, map_w, map_out, map_resid, m, n, k, ep));
+    return 0;
+  }
   const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
   kern<<<grid, kTcThreads, C::kTotal, stream>>>(map_a, map_w, map_out, map_resid, m, n, k, ep);
   CNB_LAUNCH_OK();
   return 0;
 }
 
+// CTA pairs pay off when the tile count fills the 74 pairs several times over; CNB_GEMM_PAIR=0 turns them off, =<rows> sets
+// the minimum M (default 512 so that the ragged-M unit tests exercise the pair protocol too)
+static int pair_min_rows() {
+  static const int v = [] {
+    const char* e = getenv("CNB_GEMM_PAIR");
+    if (!e) return 512;
+    const int x = atoi(e);
+    return x <= 0 ? INT_MAX : x;
+  }();
+  return v;
+}
+
 template <int EPI, typename OutT>
 static int launch_n(const __nv_bfloat16* a, const __nv_bfloat16* w, int m, int n, int k, const EpiParams& ep, OutT* out,
                     cudaStream_t stream) {
-  if (n % 192 == 0) return launch_cfg<192, EPI, OutT>(a, w, m, n, k, ep, out, stream);
-  if (n % 128 == 0) return launch_cfg<128, EPI, OutT>(a, w, m, n, k, ep, out, stream);
-  if (n == 96) return launch_cfg<96, EPI, OutT>(a, w, m, n, k, ep, out, stream);
+  // measured (64 x 10 s clips): pairs win where the K loop is long (pw2 stages 3-4 -18 % / -22 %, pw1 stage 4 -6 %, downsample
+  // -7 %) and lose where a tile has <= 6 k-blocks (pw1 stages 2-3 +39 % / +26 %: the cross-CTA stage hand-back sits inside a
+  // ring that only holds one tile) -> K >= 768 by default
+  static const int pair_min_k = [] { const char* e = getenv("CNB_GEMM_PAIR_MINK"); return e ? atoi(e) : 768; }();
+  if (m >= pair_min_rows() && k >= pair_min_k) {
+    if (n % 192 == 0) return launch_cfg<192, EPI, OutT, true>(a, w, m, n, k, ep, out, stream);
+    if (n % 128 == 0) return launch_cfg<128, EPI, OutT, true>(a, w, m, n, k, ep, out, stream);
+  }
+  if (n % 192 == 0) return launch_cfg<192, EPI, OutT, false>(a, w, m, n, k, ep, out, stream);
+  if (n % 128 == 0) return launch_cfg<128, EPI, OutT, false>(a, w, m, n, k, ep, out, stream);
+  if (n == 96) return launch_cfg<96, EPI, OutT, false>(a, w, m, n, k, ep, out, stream);
   set_error("gemm_tc: N=" + std::to_string(n) + " is neither 96 nor a multiple of 128/192");
   return -1;
 }
@@ -496,7 +593,13 @@ int launch_gemm_tc(const __nv_bfloat16* a, const __nv_bfloat16* w, int m, int n,
     case EPI_BIAS_GELU: return launch_n<EPI_BIAS_GELU, OutT>(a, w, m, n, k, ep, out, stream);
     case EPI_BIAS_RELU: return launch_n<EPI_BIAS_RELU, OutT>(a, w, m, n, k, ep, out, stream);
     case EPI_SCALE_RESID:
-      if constexpr (sizeof(OutT) == 4) return launch_n<EPI_SCALE_RESID, OutT>(a, w, m, n, k, ep, out, stream);
+      if constexpr (sizeof(OutT) == 4) {
+        CNB_REQUIRE(ep.scale != nullptr && ep.resid != nullptr, "gemm_tc: the layer-scale/residual epilogue needs scale and resid");
+        // the reduce-add epilogue accumulates into `out`: the encoder updates x in place (resid == out); otherwise seed it
+        if (!CNB_PW2_RESID_LOAD && (const void*)ep.resid != (const void*)out)
+          CNB_CUDA_OK(cudaMemcpyAsync(out, ep.resid, (size_t)m * n * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+        return launch_n<EPI_SCALE_RESID, OutT>(a, w, m, n, k, ep, out, stream);
+      }
       break;
   }
   set_error("gemm_tc: unsupported epilogue / output type combination");
