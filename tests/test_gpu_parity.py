@@ -59,7 +59,9 @@ def oracle_taps(small_sd):
 # GEMM kernels in isolation
 # ----------------------------------------------------------------------------------------------------------------------
 GEMM_SHAPES = [(300, 384, 96), (128, 96, 384), (1000, 768, 192), (257, 192, 768), (130, 1536, 384), (64, 384, 1536),
-               (77, 3072, 768), (333, 768, 3072), (512, 256, 768), (90, 192, 384)]
+               (77, 3072, 768), (333, 768, 3072), (512, 256, 768), (90, 192, 384),
+               # CTA-pair (cta_group::2) path: M >= 512 and K >= 768; ragged 256-row tiles (peer CTA partly / fully out of range)
+               (700, 384, 1536), (640, 768, 3072), (1300, 3072, 768), (20000, 384, 768)]
 
 
 def _gemm_ref(a, w, bias, scale, resid, epi, bf16_in):
@@ -498,6 +500,45 @@ def test_e2e_fast_mode_agreement_is_reported(small_sd):
     assert agree > 0.5
     assert float((out["lprobs"] - ref["lprobs"]).abs().max()) < 0.1
     model.engine.close()
+
+
+def test_mixed_length_padded_batch_beam5_audiocaps(small_sd):
+    """BASELINE configs[4] at a reduced batch: clips of 1 / 9 / 17 / 30 s zero-padded to 30 s (N = 960 000) with x_shapes,
+    task=audiocaps, beam 5, fp32 parity mode, against the oracle chain on the same padded batch: frame counts follow the
+    padded length (round-half-even of len / (N // T')), frame embeddings <= 5e-4 rel-L2, ids bit-exact on every clip whose
+    oracle selection margin stays above 1e-3 (the encoder's fp32 summation order differs; closer calls are score ties)."""
+    from oracle import restate
+
+    n = 960000
+    secs = [1, 9, 17, 30]
+    wav = synth.make_audio(len(secs), n, seed=31)
+    x_lens = torch.tensor([s * 32000 for s in secs])
+    for i, ln in enumerate(x_lens.tolist()):
+        wav[i, :, ln:] = 0
+    model = _model(small_sd, "parity")
+    out = model(wav, sr=32000, x_shapes=x_lens[:, None], task="audiocaps", beam_size=5)
+    fe, _ = model.engine.encoder(wav[:, 0])
+    model.engine.close()
+    enc = restate.encoder(small_sd, wav[:, 0], x_lens)
+    assert enc["frame_embs_lens"].tolist() == [round(s * 32000 / (n // 94)) for s in secs]  # T' = 94 at 30 s
+    ref_fe = enc["frame_embs"].transpose(1, 2)
+    assert rel_l2(fe.cpu(), ref_fe) < 5e-4
+    bos = small_sd["model.task_id_to_token_id"][torch.full((len(secs),), synth.TASK_NAMES.index("audiocaps"))]
+    trace = []
+    ref = restate.beam_search(small_sd, restate.project(small_sd, ref_fe), enc["frame_embs_lens"], bos, 5, 3, 20,
+                              small_sd["model.forbid_rep_mask"], trace=trace)
+    margin = torch.full((len(secs),), float("inf"))
+    for tr in trace:
+        for j, mg in tr.get("margin", {}).items():
+            margin[j] = min(float(margin[j]), mg)
+    firm = margin >= 1e-3
+    print(f"mixed-length batch: selection margins {margin.tolist()}")
+    assert out["mult_preds"].shape == ref[2].shape and out["mult_lprobs"].shape == (len(secs), 5)
+    assert out["tasks"] == ["audiocaps"] * len(secs)
+    assert int(firm.sum()) >= 3
+    assert torch.equal(out["mult_preds"][firm], ref[2][firm]), margin.tolist()
+    torch.testing.assert_close(out["mult_lprobs"][firm], ref[3][firm], rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(out["lprobs"][firm], ref[1][firm], rtol=2e-3, atol=2e-3)
 
 
 def test_input_forms_and_errors(small_sd):
