@@ -402,6 +402,10 @@ def run_ours(args, rank, world, local_rank):
             "frac": dbytes / (dec_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
             "tensor_tflops": dflops / (dec_ms * 1e-3) / 1e12, "tensor_frac": dflops / (dec_ms * 1e-3) / 1e12 / pk["bf16_tflops"],
             "decode_steps": pred_steps,
+            # what the cluster decoder actually moves from L2 into shared memory: every cluster of floor(16 / beam) clips
+            # streams all decoder weights once per step (weights-as-M formulation)
+            "clusters": -(-b // max(1, 16 // args.beam)),
+            "l2_to_smem_gbs": (-(-b // max(1, 16 // args.beam))) * dbytes / (dec_ms * 1e-3) / 1e9,
             "note": "latency-bound chain of ~50 dependent phases per step on 16-row operands (DESIGN.md section 6): weights are "
                     "re-streamed from L2 every step, so neither roofline is close; reported against the weight-byte stream"}
         work["decoder"] = ("hbm", dbytes)

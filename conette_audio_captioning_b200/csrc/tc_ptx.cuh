@@ -108,7 +108,10 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
 }
 // arrival on an mbarrier of a (possibly remote) CTA of the cluster
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+  // default semantics (.release.cta): ordering against the issuing CTA is all the hand-back needs -- what the arrival
+  // publishes are completed tcgen05.ld reads (tcgen05.wait::ld + fence::before_thread_sync precede it); a .release.cluster
+  // arrival costs a cluster-scope fence per epilogue warp and tile (ncu: membar stalls 7 per issue in the pw1 epilogue)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // completion of all prior cta_group::2 MMAs -> one arrival on the barrier at this offset in BOTH CTAs of the pair
 __device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {
