@@ -564,10 +564,10 @@ static int pair_min_rows() {
 template <int EPI, typename OutT>
 static int launch_n(const __nv_bfloat16* a, const __nv_bfloat16* w, int m, int n, int k, const EpiParams& ep, OutT* out,
                     cudaStream_t stream) {
-  // measured (64 x 10 s clips): pairs win where the K loop is long (pw2 stages 3-4 -18 % / -22 %, pw1 stage 4 -6 %, downsample
-  // -7 %) and lose where a tile has <= 6 k-blocks (pw1 stages 2-3 +39 % / +26 %: the cross-CTA stage hand-back sits inside a
-  // ring that only holds one tile) -> K >= 768 by default
-  static const int pair_min_k = [] { const char* e = getenv("CNB_GEMM_PAIR_MINK"); return e ? atoi(e) : 768; }();
+  // measured (64 x 10 s clips, pair vs 1-CTA): pw2 stages 3-4 -18 % / -22 %, pw1 stage 3 -9 %, stage 4 -12 %, downsample -9 %,
+  // stage 2 equal (HBM-bound).  (With a .release.cluster accumulator hand-back the short-K shapes were 26-39 % SLOWER: the
+  // cluster-scope fence serialised epilogue and MMAs at every tile boundary -- see mbar_arrive_cluster.)
+  static const int pair_min_k = [] { const char* e = getenv("CNB_GEMM_PAIR_MINK"); return e ? atoi(e) : 0; }();
   if (m >= pair_min_rows() && k >= pair_min_k) {
     if (n % 192 == 0) return launch_cfg<192, EPI, OutT, true>(a, w, m, n, k, ep, out, stream);
     if (n % 128 == 0) return launch_cfg<128, EPI, OutT, true>(a, w, m, n, k, ep, out, stream);
