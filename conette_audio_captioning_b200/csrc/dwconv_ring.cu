@@ -13,7 +13,7 @@
 //     an SM crosses a column boundary at most a few times and all SMs finish together;
 //   * C = 384 (stage 3) does not fit a ring of full-channel rows: a 2-CTA cluster splits the channels (192 each, same
 //     smem / thread shape as stage 2) and the CTAs push their LayerNorm partials into each other's shared memory
-//     (st.shared::cluster) with one cluster barrier per iteration; the partial buffers alternate so that a fast peer
+//     (st.async pushes that complete bytes on the receiver's mbarrier); the partial buffers alternate so that a fast peer
 //     can never overwrite sums that are still being read;
 //   * LayerNorm: one pass (sum, sum of squares); a 16-value butterfly costs 15-16 shuffles per 16 values; per-(half-)warp
 //     partials are combined in fixed order through shared memory (deterministic); normalisation with packed FFMA2.
@@ -95,7 +95,9 @@ struct DwCfg {
   static constexpr int PART_OFF = kNS * ROW_BYTES;
   static constexpr int VEC_OFF = PART_OFF + PART_BUFS * PART_FLOATS * 4;   // bias | gamma | beta
   static constexpr int BAR_OFF = VEC_OFF + 3 * C * 4;
-  static constexpr int SMEM = BAR_OFF + 16 + 128;              // + alignment slack
+  static constexpr int SMEM = BAR_OFF + 32 + 128;              // 2 ring barriers + 2 partial-exchange barriers + alignment slack
+  // bytes the peer CTA pushes into this CTA's partial buffer per iteration: every warp has 16 writer lanes x (sum, sumsq)
+  static constexpr int PEER_BYTES = (kThreads / 32) * 16 * 2 * 4;
   static_assert(CS == 1 || CS == 2, "channel split");
   static_assert(GROUP_T * kRG == kThreads, "CTA shape");
   static_assert(CP % 16 == 0 && TW % 7 == 0 && W % TW == 0, "tiling");
@@ -138,6 +140,8 @@ dwconv_ln_tma_kernel(const __grid_constant__ CUtensorMap map_x, int H, int PQ, i
   if (tid == 0) {
     mbar_init(bar0, 1);
     mbar_init(bar0 + 8, 1);
+    mbar_init(bar0 + 16, 1);   // CS > 1: the peer's LayerNorm partials of even / odd iterations have landed
+    mbar_init(bar0 + 24, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async_smem();
   }
@@ -185,6 +189,7 @@ dwconv_ln_tma_kernel(const __grid_constant__ CUtensorMap map_x, int H, int PQ, i
           ++sl;
         }
       }
+      if (CS > 1 && tid == 0) mbar_expect_tx(bar0 + 16 + 8 * (q & 1), Cfg::PEER_BYTES);
       mbar_wait(bar0 + 8 * (q & 1), (q >> 1) & 1);
 
       float2 acc0[PW], acc1[PW];
@@ -242,18 +247,24 @@ dwconv_ln_tma_kernel(const __grid_constant__ CUtensorMap map_x, int H, int PQ, i
           dst[0] = tsum;
           dst[PSTR / 2] = tsq;
           if (CS > 1) {
+            // one-sided push: each store completes its bytes on the RECEIVER's mbarrier -- no cluster barrier and no
+            // cluster-scope fence per iteration (measured against a barrier.cluster release/acquire pair: -2.4 %)
             const uint32_t peer = map_peer_smem(smem_u32(dst), rank ^ 1u);
-            asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(peer), "f"(tsum) : "memory");
-            asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(peer + 4u * (PSTR / 2)), "f"(tsq) : "memory");
+            const uint32_t peer_bar = map_peer_smem(bar0 + 16 + 8 * (q & 1), rank ^ 1u);
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(peer),
+                         "r"(__float_as_uint(tsum)), "r"(peer_bar)
+                         : "memory");
+            asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(
+                             peer + 4u * (PSTR / 2)),
+                         "r"(__float_as_uint(tsq)), "r"(peer_bar)
+                         : "memory");
           }
         }
       }
-      if (CS > 1) {
-        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-      } else {
-        __syncthreads();
-      }
+      __syncthreads();   // this CTA's partials are in place
+      // the peer's partials: buffer q&1 was last read in iteration q-2, which every thread of this CTA finished before any
+      // of them pushed iteration q-1, and the peer cannot push iteration q before it has received all of q-1
+      if (CS > 1) mbar_wait(bar0 + 16 + 8 * (q & 1), (q >> 1) & 1);
       const float2 gm = *reinterpret_cast<const float2*>(s_vec + C + 2 * cp);
       const float2 be = *reinterpret_cast<const float2*>(s_vec + 2 * C + 2 * cp);
 #pragma unroll
@@ -292,6 +303,10 @@ dwconv_ln_tma_kernel(const __grid_constant__ CUtensorMap map_x, int H, int PQ, i
       sbase += 4;
       if (sbase >= kNS) sbase -= kNS;
     }
+  }
+  if (CS > 1) {  // no CTA of the pair leaves while pushes into it could still be in flight
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
 }
 
