@@ -255,6 +255,11 @@ __device__ __forceinline__ void attend(const float* const (&q)[NR], const int (&
   }
 }
 
+// per-thread-0 cycle counters inside the GEMM phases (tr2): compile with -DCNB_DEC_TR2=1 to collect them; off by default
+// because the clock reads and the divergent shared-memory updates sit on the MMA issue path of warp 0
+#ifndef CNB_DEC_TR2
+#define CNB_DEC_TR2 0
+#endif
 #define CL_TR(slot)                                \
   if (tr_on) {                                     \
     const unsigned long long n_ = cl_global_ns();  \
@@ -355,12 +360,16 @@ __device__ __forceinline__ void tc_gemm(CSmem& S, const PersistentArgs& a, Pipe&
     for (int i = 0; i < g.n_chunks; ++i) {
       const uint32_t u = pp.use + (uint32_t)i;
       const int s = (int)(u % kStages);
+#if CNB_DEC_TR2
       const unsigned long long tf0 = clock64();
       const bool tr0 = tid == 0;
+#endif
       mbar_wait(smem_addr(&S.full[s]), (u / kStages) & 1u);
       tcgen05_fence_after();
+#if CNB_DEC_TR2
       const unsigned long long tf1 = clock64();
       if (tr0) S.tr2[0] += tf1 - tf0;
+#endif
       const int grp = i / cpg, ic = i - grp * cpg;
       if (elect_one()) {
         uint64_t adesc = make_smem_desc(smem_addr(&S.ring[s][0]));
@@ -376,7 +385,9 @@ __device__ __forceinline__ void tc_gemm(CSmem& S, const PersistentArgs& a, Pipe&
           for (int tt = 0; tt < g.tpc; ++tt) tcgen05_commit(smem_addr(&S.tile_full[grp * g.tpc + tt]));
       }
       __syncwarp();
+#if CNB_DEC_TR2
       if (tr0) S.tr2[1] += clock64() - tf1;
+#endif
     }
   }
   pp.use += (uint32_t)g.n_chunks;
@@ -385,10 +396,14 @@ __device__ __forceinline__ void tc_gemm(CSmem& S, const PersistentArgs& a, Pipe&
   // warp 15 (the producer) hands tile 3 / quarter 3 to warp 11
   const int quarter = warp & 3;
   for (int t = warp >> 2; t < n_tiles && warp != 15; t += (warp == 11 ? 1 : kMaxClsTiles)) {
+#if CNB_DEC_TR2
     const unsigned long long tw0 = clock64();
+#endif
     mbar_wait(smem_addr(&S.tile_full[t]), (tile_par >> t) & 1u);
     tcgen05_fence_after();
+#if CNB_DEC_TR2
     if (tid == 0) S.tr2[2] += clock64() - tw0;
+#endif
     float v[kRm], w[kRm];
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * kChains * kRm);
     tmem_ld_32x16(taddr, v);
@@ -400,7 +415,9 @@ __device__ __forceinline__ void tc_gemm(CSmem& S, const PersistentArgs& a, Pipe&
       for (int r = 0; r < kRm; ++r) v[r] += w[r];
     }
     epi(t, quarter, lane, v);
+#if CNB_DEC_TR2
     if (tid == 0) S.tr2[3] += clock64() - tw0;
+#endif
   }
   tile_par ^= (1u << n_tiles) - 1u;  // every thread tracks the phase parity of every accumulator tile
   tcgen05_fence_before();

@@ -541,6 +541,38 @@ def test_mixed_length_padded_batch_beam5_audiocaps(small_sd):
     torch.testing.assert_close(out["lprobs"][firm], ref[1][firm], rtol=2e-3, atol=2e-3)
 
 
+def test_precomputed_embeddings_path(small_sd):
+    """``preprocess=False`` (reference huggingface/model.py:205-212): x = frame embeddings (B, T', 768), x_shapes = [[768, len]].
+    Feeding the encoder's own output reproduces the waveform call bit-for-bit (same decoder, same lens), and no tags are
+    returned; against the oracle's beam search on the same embeddings the ids are exact where the margin is firm."""
+    from oracle import restate
+
+    model = _model(small_sd, "parity")
+    wav = synth.make_audio(3, 48000, seed=17)
+    wav[1, :, 25000:] = 0
+    x_lens = torch.tensor([48000, 25000, 48000])
+    tasks = ["clotho", "macs", "audiocaps"]
+    full = model(wav, sr=32000, x_shapes=x_lens[:, None], task=tasks)
+    fe, _ = model.engine.encoder(wav[:, 0])
+    lens = restate.frame_lens(x_lens, 48000)
+    x_shapes = torch.stack([torch.full_like(lens, 768), lens], dim=1)
+    pre = model(fe, x_shapes=x_shapes, preprocess=False, task=tasks)
+    model.engine.close()
+    assert torch.equal(pre["preds"], full["preds"]) and torch.equal(pre["mult_preds"], full["mult_preds"])
+    assert torch.equal(pre["lprobs"], full["lprobs"]) and pre["cands"] == full["cands"]
+    assert "tags" not in pre and "tags_probs" not in pre and pre["tasks"] == tasks
+    bos = small_sd["model.task_id_to_token_id"][torch.tensor([synth.TASK_NAMES.index(k) for k in tasks])]
+    trace = []
+    ref = restate.beam_search(small_sd, restate.project(small_sd, fe.cpu()), lens, bos, 3, 3, 20,
+                              small_sd["model.forbid_rep_mask"], trace=trace)
+    margin = torch.full((3,), float("inf"))
+    for tr in trace:
+        for j, mg in tr.get("margin", {}).items():
+            margin[j] = min(float(margin[j]), mg)
+    firm = margin >= TIE_EPS
+    assert int(firm.sum()) >= 2 and torch.equal(pre["mult_preds"][firm], ref[2][firm])
+
+
 def test_input_forms_and_errors(small_sd):
     model = _model(small_sd, "parity")
     n = 32000

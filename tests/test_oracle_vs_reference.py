@@ -171,6 +171,26 @@ def test_teacher_forced_scoring_matches_reference(ref_small, small_sd):
             torch.testing.assert_close(tok_lp[:, i], ref_lp, rtol=1e-4, atol=1e-4)
 
 
+def test_precomputed_embeddings_path_matches_reference(ref_small, small_sd):
+    """``CoNeTTEModel(x=(B, T', 768), x_shapes=[[768, len]], preprocess=False)`` (reference huggingface/model.py:205-212,
+    FrameIdentEncoder nn/encoders/ident.py:14-34) == projection + fixed-slot beam search of the restatement."""
+    g = torch.Generator().manual_seed(4)
+    b, tp = 4, 11
+    fe = torch.randn(b, tp, 768, generator=g)
+    lens = torch.tensor([11, 3, 8, 1])
+    x_shapes = torch.stack([torch.full((b,), 768), lens], dim=1)
+    tasks = ["clotho", "audiocaps", "macs", "clotho"]
+    with torch.no_grad():
+        ref = ref_small(fe, x_shapes=x_shapes, preprocess=False, task=tasks)
+    bos_ids = small_sd["model.task_id_to_token_id"][torch.tensor([synth.TASK_NAMES.index(t) for t in tasks])]
+    preds, lprobs, mult_preds, mult_lprobs = restate.beam_search(
+        small_sd, restate.project(small_sd, fe), lens, bos_ids, 3, 3, 20, small_sd["model.forbid_rep_mask"])
+    assert torch.equal(ref["preds"], preds) and torch.equal(ref["mult_preds"], mult_preds)
+    torch.testing.assert_close(lprobs, ref["lprobs"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(mult_lprobs, ref["mult_lprobs"], rtol=1e-4, atol=1e-4)
+    assert "tags" not in ref and "tags_probs" not in ref
+
+
 def test_end_to_end_matches_reference_model(ref_small, small_sd):
     wav = synth.make_audio(3, 64000, seed=3)
     wav[2, :, 40000:] = 0
