@@ -569,6 +569,11 @@ static int launch_n(const __nv_bfloat16* a, const __nv_bfloat16* w, int m, int n
   // cluster-scope fence serialised epilogue and MMAs at every tile boundary -- see mbar_arrive_cluster.)
   static const int pair_min_k = [] { const char* e = getenv("CNB_GEMM_PAIR_MINK"); return e ? atoi(e) : 0; }();
   if (m >= pair_min_rows() && k >= pair_min_k) {
+    // pw1 (GELU, bf16 out): 256-column tiles when N allows (768 / 1536 / 3072): the A tile is re-fetched 6x instead of 8x per
+    // 256 rows and the epilogue's per-tile hand-offs amortise over a third more columns (pw1 stages 2-4: -2 % / -3 % / -7 %)
+    static const bool wide = [] { const char* e = getenv("CNB_GEMM_N256"); return !e || atoi(e) != 0; }();
+    if constexpr (EPI == EPI_BIAS_GELU && sizeof(OutT) == 2)
+      if (wide && n % 256 == 0) return launch_cfg<256, EPI, OutT, true>(a, w, m, n, k, ep, out, stream);
     if (n % 192 == 0) return launch_cfg<192, EPI, OutT, true>(a, w, m, n, k, ep, out, stream);
     if (n % 128 == 0) return launch_cfg<128, EPI, OutT, true>(a, w, m, n, k, ep, out, stream);
   }

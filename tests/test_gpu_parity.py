@@ -91,7 +91,8 @@ def test_tcgen05_gemm(eng_fast, m, n, k, epi):
     torch.testing.assert_close(out, ref, rtol=2e-4, atol=2e-4)  # same bf16 operands, fp32 accumulation
 
 
-@pytest.mark.parametrize("m,n,k", [(300, 384, 96), (257, 192, 768)])
+@pytest.mark.parametrize("m,n,k", [(300, 384, 96), (257, 192, 768),
+                                   (1100, 768, 384), (600, 384, 768), (2000, 1536, 192)])  # CTA pairs: 256- / 192-column tiles
 def test_tcgen05_gemm_bf16_out(eng_fast, m, n, k):
     g = torch.Generator().manual_seed(5)
     a, w, bias = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g) / k**0.5, torch.randn(n, generator=g)
