@@ -1395,8 +1395,11 @@ int cnb_caption_host_begin(cnb_handle* h, const float* wav_host, const int64_t* 
     }
     sd = h->dec_stream;
   }
+  // another batch in flight = this batch's encoder will share the GPU with that batch's decoder
+  dwconv_set_overlap_hint(sd != st && h->host_pending[slot ^ 1]);
   const int rc_cap = caption_impl(h, wav, x_lens_host, bos, forbid_host ? forbid : nullptr, batch, n, beam, min_len, max_len,
                                   preds, lprobs, mpreds, mlprobs, info, clip_probs_host ? clip : nullptr, st, sd, slot);
+  dwconv_set_overlap_hint(false);
   h->pre_stem_done = false;
   if (rc_cap) return rc_cap;
   CNB_CUDA_OK(cudaMemcpyAsync(preds_host, preds, (size_t)batch * max_len * sizeof(int64_t), cudaMemcpyDeviceToHost, sd));

@@ -18,6 +18,9 @@
 //   * LayerNorm: one pass (sum, sum of squares); a 16-value butterfly costs 15-16 shuffles per 16 values; per-(half-)warp
 //     partials are combined in fixed order through shared memory (deterministic); normalisation with packed FFMA2.
 #include <cuda.h>
+#include <stdlib.h>
+
+#include <atomic>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -30,7 +33,7 @@ namespace {
 constexpr float kLnEps = 1e-6f;
 constexpr int kRG = 2;        // row groups per CTA (2 output rows each)
 constexpr int kNS = 14;       // ring slots
-constexpr int kThreads = 384;
+constexpr int kThreads = 384;  // CTA size of the one-CTA-per-SM shapes; narrow strips (THREADS = 192) run two CTAs per SM
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
   asm volatile(
@@ -89,6 +92,8 @@ struct DwCfg {
   static constexpr int ROW_FLOATS = RW * C;
   static constexpr int ROW_BYTES = ROW_FLOATS * 4;
   static constexpr int STRIPS = W / TW;
+  static constexpr int THREADS = GROUP_T * kRG;         // 384, or 192 for the 14-pixel strips of stage 1
+  static constexpr int CTAS_PER_SM = kThreads / THREADS;  // 168 registers/thread: 384 threads per SM either way
   static constexpr int PART_FLOATS = kRG * NSTRIP * 16 * PSTR;
   static constexpr int PART_BUFS = CS;                  // cluster mode alternates two partial buffers
   static constexpr int RING_OFF = 0;
@@ -97,9 +102,10 @@ struct DwCfg {
   static constexpr int BAR_OFF = VEC_OFF + 3 * C * 4;
   static constexpr int SMEM = BAR_OFF + 32 + 128;              // 2 ring barriers + 2 partial-exchange barriers + alignment slack
   // bytes the peer CTA pushes into this CTA's partial buffer per iteration: every warp has 16 writer lanes x (sum, sumsq)
-  static constexpr int PEER_BYTES = (kThreads / 32) * 16 * 2 * 4;
+  static constexpr int PEER_BYTES = (THREADS / 32) * 16 * 2 * 4;
   static_assert(CS == 1 || CS == 2, "channel split");
-  static_assert(GROUP_T * kRG == kThreads, "CTA shape");
+  static_assert(THREADS == kThreads || THREADS * 2 == kThreads, "CTA shape");
+  static_assert(SMEM * CTAS_PER_SM <= 232448 - 1024 * CTAS_PER_SM, "shared memory budget per SM");
   static_assert(CP % 16 == 0 && TW % 7 == 0 && W % TW == 0, "tiling");
   static_assert(ROW_BYTES % 128 == 0, "TMA destination alignment");
   static_assert(NPT <= 8, "partials per pixel");
@@ -107,7 +113,7 @@ struct DwCfg {
 };
 
 template <int C, int CS, int W, int TW, typename OutT>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(DwCfg<C, CS, W, TW, OutT>::THREADS, DwCfg<C, CS, W, TW, OutT>::CTAS_PER_SM)
 dwconv_ln_tma_kernel(const __grid_constant__ CUtensorMap map_x, int H, int PQ, int total_units, int quota,
                      const float* __restrict__ w_t, const float* __restrict__ bias, const float* __restrict__ ln_g,
                      const float* __restrict__ ln_b, OutT* __restrict__ out) {
@@ -132,7 +138,7 @@ dwconv_ln_tma_kernel(const __grid_constant__ CUtensorMap map_x, int H, int PQ, i
   if (CS > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   const int c_off = (int)rank * C;
 
-  for (int i = tid; i < C; i += kThreads) {
+  for (int i = tid; i < C; i += Cfg::THREADS) {
     s_vec[i] = bias[c_off + i];
     s_vec[C + i] = ln_g[c_off + i];
     s_vec[2 * C + i] = ln_b[c_off + i];
@@ -325,13 +331,13 @@ int launch_t(const float* x, int batch, int h, const float* w_t, const float* bi
   }
   const int pq = (int)ceil_div(h, 4);
   const int total = batch * Cfg::STRIPS * pq;
-  const int max_groups = kNumSMs / CS;  // one CTA (or CTA pair) per SM (pair)
+  const int max_groups = kNumSMs * Cfg::CTAS_PER_SM / CS;  // one CTA (or CTA pair) per SM (pair); two for the narrow strips
   int groups = total < max_groups ? total : max_groups;
   const int quota = (int)ceil_div(total, groups);
   groups = (int)ceil_div(total, quota);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(groups * CS));
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(Cfg::THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -348,10 +354,23 @@ int launch_t(const float* x, int batch, int h, const float* w_t, const float* bi
 
 }  // namespace
 
+// set by the streaming host API while it enqueues an encoder that will share the GPU with the previous batch's decoder
+static std::atomic<bool> g_overlap_hint{false};
+void dwconv_set_overlap_hint(bool on) { g_overlap_hint.store(on, std::memory_order_relaxed); }
+
 template <typename OutT>
 int launch_dwconv_ln_tma(const float* x, int batch, int h, int w, int c, const float* w_t, const float* bias,
                          const float* ln_g, const float* ln_b, OutT* out, cudaStream_t stream) {
-  if (c == 96 && w == 56) return launch_t<96, 1, 56, 28, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
+  if (c == 96 && w == 56) {
+    // Stage 1 has two shapes.  28-pixel strips, one 384-thread CTA per SM: fastest alone (0.249 ms per launch at 64 clips).
+    // 14-pixel strips, two 192-thread CTAs per SM: 11 % slower alone (wider halo share) but 296 half-size CTAs leave less
+    // wave quantisation when the previous batch's decoder holds 104 of the 148 SMs -- the streaming API sets the hint
+    // (measured: streaming step 9.21 -> 9.17 ms, end to end 66.5 k -> 67.6 k audio-s/s).  CNB_DW_S1_NARROW=0/1 forces one.
+    static const int forced = [] { const char* e = getenv("CNB_DW_S1_NARROW"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
+    const bool narrow = forced >= 0 ? forced == 1 : g_overlap_hint.load(std::memory_order_relaxed);
+    if (narrow) return launch_t<96, 1, 56, 14, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
+    return launch_t<96, 1, 56, 28, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
+  }
   if (c == 192 && w == 28) return launch_t<192, 1, 28, 14, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
   if (c == 384 && w == 14) return launch_t<192, 2, 14, 14, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
   return 1;

@@ -94,6 +94,9 @@ template <typename OutT>
 int launch_dwconv_ln_tma(const float* x, int batch, int h, int w, int c, const float* w_t, const float* bias,
                          const float* ln_g, const float* ln_b, OutT* out, cudaStream_t stream);
 
+// the encoder about to be enqueued overlaps the previous batch's decoder (streaming host API): prefer half-size CTAs
+void dwconv_set_overlap_hint(bool on);
+
 // ---- decoder / beam search ------------------------------------------------------------------------------------------------
 struct DecoderDims {
   int rows;      // B * beam
