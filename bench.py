@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--beam", type=int, default=3)
     ap.add_argument("--precision", default="fast", choices=["fast", "parity"])
     ap.add_argument("--enc-chunk", type=int, default=0)
-    ap.add_argument("--decoder", default="auto", choices=["auto", "cluster", "graph", "graph_pdl", "graph_unfused", "persistent", "eager"])
+    ap.add_argument("--decoder", default="auto", choices=["auto", "cluster", "graph", "eager"])
     ap.add_argument("--cpu-sample", type=int, default=8, help="clips in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()

@@ -53,6 +53,7 @@ SIGNATURES = {
     "cnb_encoder": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _vp]),
     "cnb_encoder_tap": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i32, _i32, _vp, _i64, _vp]),
     "cnb_decode": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cnb_decode_tap": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cnb_decoder_logits": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "cnb_score_captions": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "cnb_caption": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

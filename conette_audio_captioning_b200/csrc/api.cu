@@ -47,16 +47,15 @@ struct Arena {
 
 struct BlockW {
   float *dw_w_t, *dw_b, *ln_g, *ln_b, *b1, *b2, *scale, *w1, *w2;
-  __nv_bfloat16 *w1_bf, *w2_bf;
+  act16 *w1_bf, *w2_bf;
 };
 struct DownW {
   float *ln_g, *ln_b, *bias, *w;
-  __nv_bfloat16* w_bf;
+  act16* w_bf;
 };
 struct LayerW {
   float *sa_in_w, *sa_in_b, *sa_out_w, *sa_out_b, *ca_q_w, *ca_q_b, *ca_out_w, *ca_out_b;
   float *l1_w, *l1_b, *l2_w, *l2_b, *n1_g, *n1_b, *n2_g, *n2_b, *n3_g, *n3_b;
-  float *sa_in_p, *sa_out_p, *ca_q_p, *ca_out_p, *l1_p, *l2_p;  // k4-packed copies (cluster decoder)
 };
 
 struct Buffer {
@@ -85,19 +84,17 @@ struct cnb_handle {
   DownW down[3];
   float *head_ln_g, *head_ln_b, *head_w, *head_b;
   // projection + decoder
-  float *proj_w, *proj_b, *emb, *pe, *ca_kv_w, *ca_kv_b, *cls_w, *cls_b, *cls_p;
-  int cls_vpad = 0;
-  void* dec_tmaps = nullptr;  // 37 TMA descriptors of the decoder weights (cluster decoder)
+  float *proj_w, *proj_b, *emb, *pe, *ca_kv_w, *ca_kv_b, *cls_w, *cls_b;
+  void* dec_tmaps = nullptr;  // kDecMaps TMA descriptors of the fp16-split decoder weights (cluster decoder)
   LayerW layers[6];
   // workspace (grown on demand)
   std::map<std::string, Buffer> ws;
   size_t ws_bytes = 0;
   int* zero_flag = nullptr;  // device int[4] that stays 0: "done" flag for non-beam callers
   // CUDA-graph replay of the decode loop
-  bool use_persistent = false;
   int use_cluster = 1;  // 0 never, 1 when the shape allows it (default), 2 required
-  bool use_fused = true;
   bool use_graphs = true;
+  bool dec_compact = false;  // the decode about to be enqueued shares the GPU with the next batch's encoder (streaming API)
   cudaStream_t stream = nullptr;  // library-owned non-blocking stream (graph capture / replay, host-API copies)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<DecGraph> dec_graphs;
@@ -215,11 +212,11 @@ static int put_f32(cnb_handle* h, const std::vector<float>& v, float** out) {
   *out = h->arena.take<float>(v.size());
   return upload(*out, v);
 }
-static int put_bf16(cnb_handle* h, const std::vector<float>& v, __nv_bfloat16** out) {
-  std::vector<__nv_bfloat16> t(v.size());
-  for (size_t i = 0; i < v.size(); ++i) t[i] = __float2bfloat16_rn(v[i]);
-  *out = h->arena.take<__nv_bfloat16>(v.size());
-  CNB_CUDA_OK(cudaMemcpy(*out, t.data(), t.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+static int put_bf16(cnb_handle* h, const std::vector<float>& v, act16** out) {
+  std::vector<act16> t(v.size());
+  for (size_t i = 0; i < v.size(); ++i) t[i] = float2act(v[i]);
+  *out = h->arena.take<act16>(v.size());
+  CNB_CUDA_OK(cudaMemcpy(*out, t.data(), t.size() * sizeof(act16), cudaMemcpyHostToDevice));
   return 0;
 }
 #define GET(var, name, ...)                                  \
@@ -230,11 +227,21 @@ static int put_bf16(cnb_handle* h, const std::vector<float>& v, __nv_bfloat16** 
 #define PUT_BF(dst, vec) \
   if (int _rc = put_bf16(h, vec, &(dst))) return _rc
 
-// k4 packing for the cluster decoder: W (n, k) row-major -> Wp[(k/4) * n_pad + col][4] = W[col][4*(k/4) .. +3], zero columns >= n
-static std::vector<float> pack_k4(const std::vector<float>& w, int n, int k, int n_pad) {
-  std::vector<float> out((size_t)(k / 4) * n_pad * 4, 0.f);
-  for (int c = 0; c < n; ++c)
-    for (int kk = 0; kk < k; ++kk) out[((size_t)(kk >> 2) * n_pad + c) * 4 + (kk & 3)] = w[(size_t)c * k + kk];
+// fp16 hi/lo split of a decoder weight matrix for the cluster decoder (decoder_cluster.cu): W = W1 + 2^-11 W2 with
+// W1 = fp16(W), W2 = fp16((W - W1) * 2048); `out` = [W1 (n*k) | W2 (n*k)].  `head_pack`: columns regrouped per attention head,
+// out row (h * n + r) = W[r][32 h .. 32 h + 31] (the K-split operand of the attention output projections).
+static std::vector<act16> split_f16(const std::vector<float>& w, int n, int k, bool head_pack) {
+  const size_t sz = (size_t)n * k;
+  std::vector<act16> out(2 * sz);
+  for (int r = 0; r < n; ++r)
+    for (int c = 0; c < k; ++c) {
+      const float v = w[(size_t)r * k + c];
+      const act16 h1 = float2act(v);
+      const act16 h2 = float2act((v - act2float(h1)) * 2048.f);
+      const size_t o = head_pack ? ((size_t)(c / 32) * n + r) * 32 + (c % 32) : (size_t)r * k + c;
+      out[o] = h1;
+      out[sz + o] = h2;
+    }
   return out;
 }
 
@@ -246,7 +253,7 @@ static int finalize(cnb_handle* h) {
 
   size_t total = 0;
   for (auto& kv : h->staged) total += kv.second.data.size();
-  h->arena.cap = total * 10 + (64u << 20);  // f32 + bf16 + k4-packed decoder copies + slack
+  h->arena.cap = total * 10 + (64u << 20);  // f32 + fp16 copies + fp16-split decoder copies + slack
   CNB_CUDA_OK(cudaMalloc(&h->arena.base, h->arena.cap));
   CNB_CUDA_OK(cudaMemset(h->arena.base, 0, h->arena.cap));
 
@@ -425,8 +432,21 @@ static int finalize(cnb_handle* h) {
     GET(cb, D + "classifier.bias", V);
     PUT(h->proj_w, pw->data); PUT(h->proj_b, pb->data); PUT(h->emb, emb->data); PUT(h->cls_w, cw->data);
     PUT(h->cls_b, cb->data);
-    h->cls_vpad = 8 * ((((V + 7) / 8) + 3) & ~3);  // 8 slices of a multiple of 4 columns
-    { const std::vector<float> t = pack_k4(cw->data, V, kD, h->cls_vpad); PUT(h->cls_p, t); }
+    // fp16-split decoder weights + their TMA descriptors (cluster decoder): map index 12 l + 2 j + half, classifier 72 + half
+    std::vector<uint8_t> maps((size_t)kDecMaps * 128);
+    auto put_split = [&](int idx, const std::vector<float>& w, int n, int k, bool head_pack, int box_rows, int box_cols) -> int {
+      const std::vector<act16> sp = split_f16(w, n, k, head_pack);
+      act16* d = h->arena.take<act16>(sp.size());
+      CNB_CUDA_OK(cudaMemcpy(d, sp.data(), sp.size() * sizeof(act16), cudaMemcpyHostToDevice));
+      const int64_t rows = head_pack ? (int64_t)n * (k / 32) : n, cols = head_pack ? 32 : k;
+      for (int half = 0; half < 2; ++half) {
+        alignas(64) uint8_t tmp[128];
+        if (int rc = tc_make_map_bf16_box(tmp, d + (size_t)half * n * k, rows, cols, box_rows, box_cols)) return rc;
+        memcpy(&maps[(size_t)(idx + half) * 128], tmp, 128);
+      }
+      return 0;
+    };
+    if (int rc = put_split(kLayers * kDecMapsPerLayer, cw->data, V, kD, false, 128, 64)) return rc;
     auto it = h->staged.find(D + "pos_encoding.pos_embedding");
     if (it == h->staged.end() || it->second.shape.size() != 3 || it->second.shape[2] != kD) {
       set_error("missing or malformed weight: " + D + "pos_encoding.pos_embedding");
@@ -456,12 +476,13 @@ static int finalize(cnb_handle* h) {
       std::copy(caw->data.begin() + (size_t)kD * kD, caw->data.end(), kvw.begin() + (size_t)l * 2 * kD * kD);
       std::copy(cab->data.begin() + kD, cab->data.end(), kvb.begin() + (size_t)l * 2 * kD);
       PUT(L.l1_w, l1w->data); PUT(L.l1_b, l1b->data); PUT(L.l2_w, l2w->data); PUT(L.l2_b, l2b->data);
-      { const std::vector<float> t = pack_k4(saw->data, 3 * kD, kD, 3 * kD); PUT(L.sa_in_p, t); }
-      { const std::vector<float> t = pack_k4(sow->data, kD, kD, kD); PUT(L.sa_out_p, t); }
-      { const std::vector<float> t = pack_k4(qw, kD, kD, kD); PUT(L.ca_q_p, t); }
-      { const std::vector<float> t = pack_k4(cow->data, kD, kD, kD); PUT(L.ca_out_p, t); }
-      { const std::vector<float> t = pack_k4(l1w->data, kFF, kD, kFF); PUT(L.l1_p, t); }
-      { const std::vector<float> t = pack_k4(l2w->data, kD, kFF, kD); PUT(L.l2_p, t); }
+      const int mb = kDecMapsPerLayer * l;
+      if (int rc = put_split(mb + 0, saw->data, 3 * kD, kD, false, 32, 64)) return rc;
+      if (int rc = put_split(mb + 2, sow->data, kD, kD, true, 128, 32)) return rc;
+      if (int rc = put_split(mb + 4, qw, kD, kD, false, 32, 64)) return rc;
+      if (int rc = put_split(mb + 6, cow->data, kD, kD, true, 128, 32)) return rc;
+      if (int rc = put_split(mb + 8, l1w->data, kFF, kD, false, 128, 64)) return rc;
+      if (int rc = put_split(mb + 10, l2w->data, kD, kFF, false, 128, 64)) return rc;
       float** gs[3] = {&L.n1_g, &L.n2_g, &L.n3_g};
       float** bs[3] = {&L.n1_b, &L.n2_b, &L.n3_b};
       for (int n = 0; n < 3; ++n) {
@@ -471,28 +492,8 @@ static int finalize(cnb_handle* h) {
       }
     }
     PUT(h->ca_kv_w, kvw); PUT(h->ca_kv_b, kvb);
-    // TMA descriptors of the fp32 decoder weights (tf32 tcgen05 GEMMs of the cluster decoder): box = 32 k x {32 | 256} rows
-    {
-      std::vector<uint8_t> maps((size_t)37 * 128);
-      alignas(64) uint8_t tmp[128];
-      auto put_map = [&](int idx, const float* w, int64_t rows, int64_t cols, int box_rows) {
-        if (int rc = tc_make_map(tmp, w, rows, cols, box_rows, 4)) return rc;
-        memcpy(&maps[(size_t)idx * 128], tmp, 128);
-        return 0;
-      };
-      for (int l = 0; l < kLayers; ++l) {
-        const LayerW& L = h->layers[l];
-        if (int rc = put_map(6 * l + 0, L.sa_in_w, 3 * kD, kD, 32)) return rc;
-        if (int rc = put_map(6 * l + 1, L.sa_out_w, kD, kD, 32)) return rc;
-        if (int rc = put_map(6 * l + 2, L.ca_q_w, kD, kD, 32)) return rc;
-        if (int rc = put_map(6 * l + 3, L.ca_out_w, kD, kD, 32)) return rc;
-        if (int rc = put_map(6 * l + 4, L.l1_w, kFF, kD, 256)) return rc;
-        if (int rc = put_map(6 * l + 5, L.l2_w, kD, kFF, 256)) return rc;
-      }
-      if (int rc = put_map(36, h->cls_w, V, kD, 256)) return rc;
-      CNB_CUDA_OK(cudaMalloc(&h->dec_tmaps, maps.size()));
-      CNB_CUDA_OK(cudaMemcpy(h->dec_tmaps, maps.data(), maps.size(), cudaMemcpyHostToDevice));
-    }
+    CNB_CUDA_OK(cudaMalloc(&h->dec_tmaps, maps.size()));
+    CNB_CUDA_OK(cudaMemcpy(h->dec_tmaps, maps.data(), maps.size(), cudaMemcpyHostToDevice));
   }
   CNB_CUDA_OK(cudaMalloc(&h->zero_flag, 4 * sizeof(int)));
   CNB_CUDA_OK(cudaMemset(h->zero_flag, 0, 4 * sizeof(int)));
@@ -514,19 +515,19 @@ struct Tap {
 static int copy_tap(Tap* tap, const void* src, int64_t elems, bool src_is_bf16, cudaStream_t st);
 
 template <typename ActT>
-static int mlp_gemm(cnb_handle* h, const ActT* a, const float* w32, const __nv_bfloat16* wbf, int m, int n, int k, Epilogue epi,
+static int mlp_gemm(cnb_handle* h, const ActT* a, const float* w32, const act16* wbf, int m, int n, int k, Epilogue epi,
                     const EpiParams& ep, void* out, bool out_act, int64_t ldo, cudaStream_t st);
 
 template <>
-int mlp_gemm<float>(cnb_handle* h, const float* a, const float* w32, const __nv_bfloat16*, int m, int n, int k, Epilogue epi,
+int mlp_gemm<float>(cnb_handle* h, const float* a, const float* w32, const act16*, int m, int n, int k, Epilogue epi,
                     const EpiParams& ep, void* out, bool, int64_t ldo, cudaStream_t st) {
   return launch_gemm_f32<float>(a, k, w32, m, n, k, epi, ep, reinterpret_cast<float*>(out), ldo, st);
 }
 template <>
-int mlp_gemm<__nv_bfloat16>(cnb_handle* h, const __nv_bfloat16* a, const float*, const __nv_bfloat16* wbf, int m, int n, int k,
+int mlp_gemm<act16>(cnb_handle* h, const act16* a, const float*, const act16* wbf, int m, int n, int k,
                             Epilogue epi, const EpiParams& ep, void* out, bool out_act, int64_t ldo, cudaStream_t st) {
   if (out_act)
-    return launch_gemm_tc<__nv_bfloat16>(a, wbf, m, n, k, epi, ep, reinterpret_cast<__nv_bfloat16*>(out), ldo, st);
+    return launch_gemm_tc<act16>(a, wbf, m, n, k, epi, ep, reinterpret_cast<act16*>(out), ldo, st);
   return launch_gemm_tc<float>(a, wbf, m, n, k, epi, ep, reinterpret_cast<float*>(out), ldo, st);
 }
 
@@ -594,7 +595,7 @@ static int encode_chunk(cnb_handle* h, const float* wav, int nb, int64_t n, floa
       static const bool fused_ok = getenv("CNB_NO_MLP_FUSED") == nullptr;
       if (sizeof(ActT) == 2 && c == 96 && fused_ok) {
         Prof _p(h, CNB_K_GEMM_PW1_S0 + s, st);
-        if (int rc = launch_mlp_fused_c96(reinterpret_cast<const __nv_bfloat16*>(y), b.w1_bf, b.w2_bf, b.b1, b.b2, b.scale, x, m, st))
+        if (int rc = launch_mlp_fused_c96(reinterpret_cast<const act16*>(y), b.w1_bf, b.w2_bf, b.b1, b.b2, b.scale, x, m, st))
           return rc;
         slab = m;  // skip the two-GEMM path below
       } else
@@ -623,9 +624,9 @@ static int encode_chunk(cnb_handle* h, const float* wav, int nb, int64_t n, floa
   return 0;
 }
 
-__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int64_t n) {
+__global__ void bf16_to_f32_kernel(const act16* __restrict__ in, float* __restrict__ out, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = __bfloat162float(in[i]);
+  if (i < n) out[i] = act2float(in[i]);
 }
 
 static int copy_tap(Tap* tap, const void* src, int64_t elems, bool src_is_bf16, cudaStream_t st) {
@@ -634,7 +635,7 @@ static int copy_tap(Tap* tap, const void* src, int64_t elems, bool src_is_bf16, 
     return -1;
   }
   if (src_is_bf16) {
-    bf16_to_f32_kernel<<<(unsigned)ceil_div(elems, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), tap->out,
+    bf16_to_f32_kernel<<<(unsigned)ceil_div(elems, 256), 256, 0, st>>>(reinterpret_cast<const act16*>(src), tap->out,
                                                                         elems);
     CNB_LAUNCH_OK();
   } else {
@@ -656,7 +657,7 @@ static int encode(cnb_handle* h, const float* wav, int batch, int64_t n, float* 
     float* cp = clip_probs ? clip_probs + (int64_t)b0 * kTags : nullptr;
     int rc = (h->cfg.precision == CNB_PRECISION_PARITY)
                  ? encode_chunk<float>(h, wav + (int64_t)b0 * n, nb, n, fe, cp, nullptr, st)
-                 : encode_chunk<__nv_bfloat16>(h, wav + (int64_t)b0 * n, nb, n, fe, cp, nullptr, st);
+                 : encode_chunk<act16>(h, wav + (int64_t)b0 * n, nb, n, fe, cp, nullptr, st);
     if (rc) return rc;
   }
   return 0;
@@ -831,32 +832,17 @@ static int decode_body(cnb_handle* h, const DecWs& w, BeamState bs, const float*
   return 0;
 }
 
-// "fused" variant: LayerNorm-on-load GEMMs + beam/embedding fusion (50 launches per step instead of 69)
-static int decode_body_fused(cnb_handle* h, const DecWs& w, const PersistentArgs& pa, const float* frame_embs, int batch,
-                             const DecoderDims& dd, int64_t* preds, float* lprobs, int64_t* mult_preds, float* mult_lprobs,
-                             int32_t* info, int* best_len, cudaStream_t st) {
-  if (int rc = dec_project(h, frame_embs, batch, dd.tp, w, st)) return rc;
-  if (int rc = launch_decoder_init(pa, st)) return rc;
-  float* x_cur = pa.xa;
-  float* x_alt = pa.xb;
-  int cur = 0;
-  for (int i = 0; i < dd.max_len; ++i) {
-    if (int rc = launch_decoder_step_fused(pa, i, cur, &x_cur, &x_alt, st)) return rc;
-    cur ^= 1;
-  }
-  if (int rc = launch_beam_finalize(pa.bs, preds, lprobs, best_len, dd, st)) return rc;
-  gather_mult_kernel<<<(dd.rows * dd.max_len + 255) / 256, 256, 0, st>>>(pa.bs, mult_preds, mult_lprobs, best_len, info,
-                                                                        dd.rows, dd.max_len, batch);
-  CNB_LAUNCH_OK();
-  return 0;
-}
-
-// The ~1400 small dependent launches of a 20-step decode are captured once per (shape, buffer) signature into a CUDA
-// graph and replayed on the handle's own stream (stream capture is illegal on the legacy default stream callers often
-// pass); fork/join events order it against the caller's stream.  Profiling mode runs eagerly (event brackets).
+// Two decoder implementations:
+//   * cluster (default of precision "fast"): the whole decode in ONE launch, fp16 hi/lo split tensor-core GEMMs with fp32-level
+//     accuracy (decoder_cluster.cu);
+//   * graph (precision "parity", or decoder="graph"): the fp32 CUDA-core KV-cached step of dec_step, ~1400 small dependent
+//     launches captured once per (shape, buffer) signature into a CUDA graph and replayed on the handle's own stream (stream
+//     capture is illegal on the legacy default stream callers often pass); fork/join events order it against the caller's
+//     stream.  Profiling mode runs the same launches eagerly (event brackets).
+// `tap` (tests only, cluster decoder): raw per-step logits (max_len, rows, V).
 static int decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, const int64_t* bos_ids, const uint8_t* forbid,
                   int batch, int tp, int beam, int min_len, int max_len, int64_t* preds, float* lprobs, int64_t* mult_preds,
-                  float* mult_lprobs, int32_t* info, cudaStream_t st) {
+                  float* mult_lprobs, int32_t* info, cudaStream_t st, float* tap = nullptr) {
   const int rows = batch * beam;
   DecoderDims dd{rows, beam, tp, max_len, h->cfg.vocab_size};
   DecWs w;
@@ -875,53 +861,43 @@ static int decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, c
   bs.tokens[0] = tok0; bs.tokens[1] = tok1; bs.src_row[0] = src0; bs.src_row[1] = src1;
   bs.sum_lp = sum_lp; bs.live = live; bs.out_preds = out_preds; bs.out_lp = out_lp; bs.done = done;
 
-  // argument block shared by the persistent kernel and the fused per-phase launches (decoder_persistent.cu)
-  WS(h, "dxb", float, (size_t)rows * kD, xb);
-  WS(h, "dbar", unsigned int, 64, bar);
-  PersistentArgs pa;
+  ClusterArgs ca;
   for (int l = 0; l < kLayers; ++l) {
     const LayerW& L = h->layers[l];
-    pa.layers[l] = PLayer{L.sa_in_w, L.sa_in_b, L.sa_out_w, L.sa_out_b, L.ca_q_w, L.ca_q_b, L.ca_out_w, L.ca_out_b, L.l1_w,
-                          L.l1_b, L.l2_w, L.l2_b, L.n1_g, L.n1_b, L.n2_g, L.n2_b, L.n3_g, L.n3_b,
-                          L.sa_in_p, L.sa_out_p, L.ca_q_p, L.ca_out_p, L.l1_p, L.l2_p};
+    ca.layers[l] = ClusterLayer{L.sa_in_b, L.sa_out_b, L.ca_q_b, L.ca_out_b, L.l1_b, L.l2_b, L.n1_g, L.n1_b, L.n2_g, L.n2_b,
+                                L.n3_g, L.n3_b};
   }
-  pa.emb = h->emb; pa.pe = h->pe; pa.cls_w = h->cls_w; pa.cls_b = h->cls_b; pa.cls_p = h->cls_p; pa.vpad = h->cls_vpad; pa.tmaps = h->dec_tmaps;
-  pa.ckv = w.ckv; pa.lens = lens; pa.bos_ids = bos_ids; pa.forbid = forbid;
-  pa.xa = w.x; pa.xb = xb; pa.qkv = w.qkv; pa.attn = w.attn; pa.tmp = w.tmp; pa.ff = w.ff; pa.part = w.part;
-  pa.logits = w.logits; pa.kc = w.kc; pa.vc = w.vc; pa.bs = bs; pa.bar = bar;
-  pa.rows = rows; pa.beam = beam; pa.tp = tp; pa.max_len = max_len; pa.vocab = h->cfg.vocab_size; pa.min_len = min_len;
-  pa.batch = batch;
-  pa.trace = nullptr;
+  ca.emb = h->emb; ca.pe = h->pe; ca.cls_b = h->cls_b; ca.tmaps = h->dec_tmaps;
+  ca.ckv = w.ckv; ca.lens = lens; ca.bos_ids = bos_ids; ca.forbid = forbid; ca.kc = w.kc; ca.vc = w.vc; ca.bs = bs;
+  ca.tap = tap; ca.trace = nullptr;
+  ca.rows = rows; ca.beam = beam; ca.tp = tp; ca.max_len = max_len; ca.vocab = h->cfg.vocab_size; ca.min_len = min_len;
+  ca.batch = batch; ca.compact = h->dec_compact ? 1 : 0;
 
-  // default: the tf32 tensor-core cluster decoder belongs to precision "fast"; "parity" keeps the fp32 graph decoder
-  if (h->use_cluster == 2 ||
-      (h->use_cluster == 1 && h->cfg.precision == CNB_PRECISION_FAST && decoder_cluster_supported(pa))) {
-    // one cluster of 8 CTAs per group of clips decodes start to finish (decoder_cluster.cu): 2 GEMMs + 1 kernel + 2 gathers
+  const bool want_cluster = h->use_cluster == 2 || (h->use_cluster == 1 && h->cfg.precision == CNB_PRECISION_FAST);
+  if (want_cluster && (h->use_cluster == 2 || decoder_cluster_supported(ca))) {
+    // one cluster of 8 CTAs per group of clips decodes start to finish: 2 GEMMs + 1 kernel + 2 gathers
     if (int rc = dec_project(h, frame_embs, batch, tp, w, st)) return rc;
     const bool trace_on = getenv("CNB_DEC_TRACE") != nullptr;
     if (trace_on) {
       WS(h, "dtrace_cl", unsigned long long, 32, tr);
       CNB_CUDA_OK(cudaMemsetAsync(tr, 0, 32 * sizeof(unsigned long long), st));
-      pa.trace = tr;
+      ca.trace = tr;
     }
     {
       Prof _p(h, CNB_K_DEC_GEMM, st);
-      if (int rc = launch_decoder_cluster(pa, st)) return rc;
+      if (int rc = launch_decoder_cluster(ca, st)) return rc;
     }
     if (trace_on) {  // debug: time between phase marks as seen by thread 0 of the first CTA, summed over steps and layers
-      unsigned long long t[24];
+      unsigned long long t[20];
       CNB_CUDA_OK(cudaStreamSynchronize(st));
-      CNB_CUDA_OK(cudaMemcpy(t, pa.trace, sizeof(t), cudaMemcpyDeviceToHost));
-      static const char* names[] = {"qkv gemm", "self attn", "bcast+sync1", "sa_out gemm", "bcast+sync2", "ln1", "ca_q gemm",
-                                    "cross attn", "bcast+sync3", "ca_out gemm", "bcast+sync4", "ln2+ff1 gemm", "ff2 gemm",
-                                    "scatter+sync5", "reduce+bcast+sync6+ln3", "cls gemm", "beam A", "bcast+sync7", "beam B",
-                                    "-"};
+      CNB_CUDA_OK(cudaMemcpy(t, ca.trace, sizeof(t), cudaMemcpyDeviceToHost));
+      static const char* names[] = {"qkv gemm", "self attn", "sa_out gemm (K-split)", "reduce+gather+ln1", "ca_q gemm",
+                                    "cross attn", "ca_out gemm (K-split)", "reduce+gather+ln2", "ff1 gemm", "ff2 gemm",
+                                    "reduce+gather+ln3", "cls gemm (rounds)", "cls scan (rounds)", "beam exchange", "beam merge"};
       double tot = 0;
-      for (int i = 0; i < 19; ++i) tot += (double)t[i];
-      for (int i = 0; i < 19; ++i)
+      for (int i = 0; i < 15; ++i) tot += (double)t[i];
+      for (int i = 0; i < 15; ++i)
         fprintf(stderr, "[dec cluster trace] %-24s %9.1f us  (%4.1f %%)\n", names[i], (double)t[i] / 1e3, 100.0 * t[i] / tot);
-      fprintf(stderr, "[dec cluster trace] thread 0 cycles: wait weights %llu, issue MMAs %llu, wait MMAs %llu, wait+epilogue %llu\n",
-              t[20], t[21], t[22], t[23]);
     }
     if (int rc = launch_beam_finalize(bs, preds, lprobs, best_len, dd, st)) return rc;
     gather_mult_kernel<<<(rows * max_len + 255) / 256, 256, 0, st>>>(bs, mult_preds, mult_lprobs, best_len, info, rows, max_len,
@@ -929,62 +905,22 @@ static int decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, c
     CNB_LAUNCH_OK();
     return 0;
   }
-  if (!h->prof_on && h->use_persistent) {
-    // one cooperative launch for the whole decode loop
-    if (int rc = dec_project(h, frame_embs, batch, tp, w, st)) return rc;
-    const bool trace_on = getenv("CNB_DEC_TRACE") != nullptr;
-    const int n_bar = 1 + max_len * (kLayers * 8 + 2);
-    if (trace_on) {
-      WS(h, "dtrace", unsigned long long, (size_t)3 * n_bar, tr);
-      CNB_CUDA_OK(cudaMemsetAsync(tr, 0, (size_t)3 * n_bar * sizeof(unsigned long long), st));
-      pa.trace = tr;
-    }
-    if (int rc = launch_decoder_persistent(pa, st)) return rc;
-    if (trace_on) {  // debug: per-phase time (work before the barrier, barrier wait) as seen by block 0
-      std::vector<unsigned long long> t((size_t)3 * n_bar);
-      CNB_CUDA_OK(cudaStreamSynchronize(st));
-      CNB_CUDA_OK(cudaMemcpy(t.data(), pa.trace, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-      static const char* names[] = {"init", "qkv", "self_attn", "sa_out", "ln1+ca_q", "cross_attn", "ca_out", "ln2+ff1", "ff2",
-                                    "ln3+cls", "beam"};
-      double work[11] = {0}, wait[11] = {0};
-      int cnt[11] = {0};
-      for (int i = 1; i < n_bar; ++i) {
-        if (t[3 * i + 1] == 0) break;
-        const int ph = (int)t[3 * i];
-        work[ph] += (double)(t[3 * i + 1] - t[3 * (i - 1) + 2]);
-        wait[ph] += (double)(t[3 * i + 2] - t[3 * i + 1]);
-        cnt[ph] += 1;
-      }
-      for (int ph = 0; ph < 11; ++ph)
-        if (cnt[ph])
-          fprintf(stderr, "[dec trace] %-11s n=%4d work(block0) %7.2f us  barrier wait %7.2f us\n", names[ph], cnt[ph],
-                  work[ph] / cnt[ph] / 1e3, wait[ph] / cnt[ph] / 1e3);
-    }
-    if (int rc = launch_beam_finalize(bs, preds, lprobs, best_len, dd, st)) return rc;
-    gather_mult_kernel<<<(rows * max_len + 255) / 256, 256, 0, st>>>(bs, mult_preds, mult_lprobs, best_len, info, rows, max_len,
-                                                                    batch);
-    CNB_LAUNCH_OK();
-    return 0;
-  }
+  CNB_REQUIRE(tap == nullptr, "the logits tap belongs to the cluster decoder (cnb_decoder_logits taps the fp32 step)");
   if (h->prof_on || !h->use_graphs)
     return decode_body(h, w, bs, frame_embs, lens, bos_ids, forbid, batch, min_len, dd, preds, lprobs, mult_preds, mult_lprobs,
                        info, best_len, st);
 
   const std::vector<int64_t> key = {batch, tp, beam, min_len, max_len, (int64_t)frame_embs, (int64_t)lens, (int64_t)bos_ids,
                                     (int64_t)forbid, (int64_t)preds, (int64_t)lprobs, (int64_t)mult_preds,
-                                    (int64_t)mult_lprobs, (int64_t)info, (int64_t)w.logits, (int64_t)w.kc, (int64_t)tok0,
-                                    (int64_t)h->use_fused};
+                                    (int64_t)mult_lprobs, (int64_t)info, (int64_t)w.logits, (int64_t)w.kc, (int64_t)tok0};
   DecGraph* dg = nullptr;
   for (auto& g : h->dec_graphs)
     if (g.key == key) dg = &g;
   if (!dg) {
     const int64_t before = g_launches.load();
     CNB_CUDA_OK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-    const int rc = h->use_fused
-                       ? decode_body_fused(h, w, pa, frame_embs, batch, dd, preds, lprobs, mult_preds, mult_lprobs, info,
-                                           best_len, h->stream)
-                       : decode_body(h, w, bs, frame_embs, lens, bos_ids, forbid, batch, min_len, dd, preds, lprobs, mult_preds,
-                                     mult_lprobs, info, best_len, h->stream);
+    const int rc = decode_body(h, w, bs, frame_embs, lens, bos_ids, forbid, batch, min_len, dd, preds, lprobs, mult_preds,
+                               mult_lprobs, info, best_len, h->stream);
     cudaGraph_t graph = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
     const int64_t n_kernels = g_launches.load() - before;
@@ -1063,20 +999,16 @@ int cnb_create(const cnb_config* cfg, cnb_handle** out) {
   CNB_CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CNB_CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CNB_CUDA_OK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-  // reserved[0] = decoder execution mode: 0 default (cluster kernel when the shape allows it, else the fused graph), 1 fused
-  // CUDA graph, 2 fused graph + programmatic dependent launch, 3 unfused graph, 4 eager launches, 5 cooperative persistent
-  // kernel, 6 cluster kernel (error if the shape does not fit)
+  // reserved[0] = decoder implementation: 0 default (cluster kernel in precision "fast" when the shape allows it, else the fp32
+  // graph), 1 fp32 CUDA graph, 2 fp32 eager launches (debugging), 3 cluster kernel (error if the shape does not fit)
   const int dmode = cfg->reserved[0];
-  if (dmode < 0 || dmode > 6) {
-    set_error("cnb_create: reserved[0] (decoder mode) must be 0..6");
+  if (dmode < 0 || dmode > 3) {
+    set_error("cnb_create: reserved[0] (decoder mode) must be 0..3");
     delete h;
     return -1;
   }
-  h->use_cluster = dmode == 0 ? 1 : (dmode == 6 ? 2 : 0);
-  h->use_graphs = dmode != 4;
-  h->use_persistent = dmode == 5;
-  h->use_fused = dmode != 3;
-  decoder_set_pdl(dmode == 2);
+  h->use_cluster = dmode == 0 ? 1 : (dmode == 3 ? 2 : 0);
+  h->use_graphs = dmode != 2;
   *out = h;
   return 0;
 }
@@ -1186,7 +1118,7 @@ int cnb_encoder_tap(cnb_handle* h, const float* wav, int32_t batch, int64_t n, i
   WS(h, "tap_fe", float, (size_t)batch * g.tp * 768, fe);
   int rc = (h->cfg.precision == CNB_PRECISION_PARITY)
                ? encode_chunk<float>(h, wav, batch, n, fe, nullptr, &tap, (cudaStream_t)stream)
-               : encode_chunk<__nv_bfloat16>(h, wav, batch, n, fe, nullptr, &tap, (cudaStream_t)stream);
+               : encode_chunk<act16>(h, wav, batch, n, fe, nullptr, &tap, (cudaStream_t)stream);
   if (rc) return rc;
   CNB_REQUIRE(tap.hit, "no such tap point");
   return 0;
@@ -1208,6 +1140,20 @@ int cnb_decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, cons
   if (int rc = check_decode(h, batch, tp, beam, min_len, max_len)) return rc;
   return decode(h, frame_embs, lens, bos_ids, forbid, batch, tp, beam, min_len, max_len, preds, lprobs, mult_preds,
                 mult_lprobs, info, (cudaStream_t)stream);
+}
+
+int cnb_decode_tap(cnb_handle* h, const float* frame_embs, const int32_t* lens, const int64_t* bos_ids, const uint8_t* forbid,
+                   int32_t batch, int32_t tp, int32_t beam, int32_t min_len, int32_t max_len, int64_t* preds, float* lprobs,
+                   int64_t* mult_preds, float* mult_lprobs, int32_t* info, float* logits_out, void* stream) {
+  CHECK_READY(h);
+  CNB_REQUIRE(frame_embs && lens && bos_ids && preds && lprobs && mult_preds && mult_lprobs && info && logits_out, "null buffer");
+  if (int rc = check_decode(h, batch, tp, beam, min_len, max_len)) return rc;
+  const int keep = h->use_cluster;
+  h->use_cluster = 2;  // the tap lives in the cluster kernel: fail instead of falling back
+  const int rc = decode(h, frame_embs, lens, bos_ids, forbid, batch, tp, beam, min_len, max_len, preds, lprobs, mult_preds,
+                        mult_lprobs, info, (cudaStream_t)stream, logits_out);
+  h->use_cluster = keep;
+  return rc;
 }
 
 int cnb_decoder_logits(cnb_handle* h, const float* frame_embs, const int32_t* lens, const int64_t* tokens, int32_t batch,
@@ -1397,9 +1343,11 @@ int cnb_caption_host_begin(cnb_handle* h, const float* wav_host, const int64_t* 
   }
   // another batch in flight = this batch's encoder will share the GPU with that batch's decoder
   dwconv_set_overlap_hint(sd != st && h->host_pending[slot ^ 1]);
+  h->dec_compact = sd != st && h->host_pending[slot ^ 1];  // steady-state streaming: this decode will overlap the next encoder
   const int rc_cap = caption_impl(h, wav, x_lens_host, bos, forbid_host ? forbid : nullptr, batch, n, beam, min_len, max_len,
                                   preds, lprobs, mpreds, mlprobs, info, clip_probs_host ? clip : nullptr, st, sd, slot);
   dwconv_set_overlap_hint(false);
+  h->dec_compact = false;
   h->pre_stem_done = false;
   if (rc_cap) return rc_cap;
   CNB_CUDA_OK(cudaMemcpyAsync(preds_host, preds, (size_t)batch * max_len * sizeof(int64_t), cudaMemcpyDeviceToHost, sd));
@@ -1436,9 +1384,9 @@ int cnb_caption_host(cnb_handle* h, const float* wav_host, const int64_t* x_lens
   return cnb_caption_host_end(h, ticket);
 }
 
-__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, act16* __restrict__ out, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+  if (i < n) out[i] = float2act(in[i]);
 }
 
 int cnb_debug_gemm(cnb_handle* h, const float* a, const float* w, const float* bias, const float* scale, const float* resid,
@@ -1450,16 +1398,16 @@ int cnb_debug_gemm(cnb_handle* h, const float* a, const float* w, const float* b
   EpiParams ep;
   ep.bias = bias; ep.scale = scale; ep.resid = resid;
   if (!use_tc) return launch_gemm_f32<float>(a, k, w, m, n, k, (Epilogue)epi, ep, out, n, st);
-  WS(h, "dbg_a", __nv_bfloat16, (size_t)m * k, a_bf);
-  WS(h, "dbg_w", __nv_bfloat16, (size_t)n * k, w_bf);
+  WS(h, "dbg_a", act16, (size_t)m * k, a_bf);
+  WS(h, "dbg_w", act16, (size_t)n * k, w_bf);
   f32_to_bf16_kernel<<<(unsigned)ceil_div((int64_t)m * k, 256), 256, 0, st>>>(a, a_bf, (int64_t)m * k);
   CNB_LAUNCH_OK();
   f32_to_bf16_kernel<<<(unsigned)ceil_div((int64_t)n * k, 256), 256, 0, st>>>(w, w_bf, (int64_t)n * k);
   CNB_LAUNCH_OK();
   if (!out_bf16) return launch_gemm_tc<float>(a_bf, w_bf, m, n, k, (Epilogue)epi, ep, out, n, st);
   CNB_REQUIRE(epi != EPI_SCALE_RESID, "the residual epilogue writes fp32");
-  WS(h, "dbg_o", __nv_bfloat16, (size_t)m * n, o_bf);
-  if (int rc = launch_gemm_tc<__nv_bfloat16>(a_bf, w_bf, m, n, k, (Epilogue)epi, ep, o_bf, n, st)) return rc;
+  WS(h, "dbg_o", act16, (size_t)m * n, o_bf);
+  if (int rc = launch_gemm_tc<act16>(a_bf, w_bf, m, n, k, (Epilogue)epi, ep, o_bf, n, st)) return rc;
   bf16_to_f32_kernel<<<(unsigned)ceil_div((int64_t)m * n, 256), 256, 0, st>>>(o_bf, out, (int64_t)m * n);
   CNB_LAUNCH_OK();
   return 0;
@@ -1472,9 +1420,9 @@ int cnb_debug_mlp_fused(cnb_handle* h, const float* y, const float* w1, const fl
   CNB_REQUIRE(m >= 0, "negative row count");
   cudaStream_t st = (cudaStream_t)stream;
   if (m == 0) return 0;
-  WS(h, "dbg_y", __nv_bfloat16, (size_t)m * 96, y_bf);
-  WS(h, "dbg_w1", __nv_bfloat16, (size_t)384 * 96, w1_bf);
-  WS(h, "dbg_w2", __nv_bfloat16, (size_t)96 * 384, w2_bf);
+  WS(h, "dbg_y", act16, (size_t)m * 96, y_bf);
+  WS(h, "dbg_w1", act16, (size_t)384 * 96, w1_bf);
+  WS(h, "dbg_w2", act16, (size_t)96 * 384, w2_bf);
   f32_to_bf16_kernel<<<(unsigned)ceil_div((int64_t)m * 96, 256), 256, 0, st>>>(y, y_bf, (int64_t)m * 96);
   CNB_LAUNCH_OK();
   f32_to_bf16_kernel<<<(unsigned)ceil_div((int64_t)384 * 96, 256), 256, 0, st>>>(w1, w1_bf, (int64_t)384 * 96);

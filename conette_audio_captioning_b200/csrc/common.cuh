@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -51,10 +52,25 @@ __device__ __forceinline__ float warp_max(float v) {
 // exact (erf) GELU, as nn.GELU() / F.gelu default (reference convnext.py:48, get.py:24-28)
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// 16-bit GEMM operand type of precision "fast": IEEE fp16 (11-bit significand = 8x less operand rounding than bf16 at the
+// same tcgen05 kind::f16 rate).  Conversions saturate at +-65504 instead of producing inf: ConvNeXt operands are LayerNorm
+// outputs and GELU hidden units, far inside the range.
+using act16 = __half;
+using act16x2 = __half2;
+__host__ __device__ __forceinline__ float act2float(act16 v) { return __half2float(v); }
+__host__ __device__ __forceinline__ act16 float2act(float v) {
+  return __float2half_rn(v > 65504.f ? 65504.f : (v < -65504.f ? -65504.f : v));
+}
+__device__ __forceinline__ act16x2 floats2act2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return *reinterpret_cast<act16x2*>(&r);
+}
+
 template <typename T> __device__ __forceinline__ T from_float(float v);
 template <> __device__ __forceinline__ float from_float<float>(float v) { return v; }
-template <> __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ act16 from_float<act16>(float v) { return float2act(v); }
 __device__ __forceinline__ float to_float(float v) { return v; }
-__device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_float(act16 v) { return act2float(v); }
 
 }  // namespace cnb

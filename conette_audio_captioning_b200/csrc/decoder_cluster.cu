@@ -1,28 +1,28 @@
 // K-DEC cluster: the whole beam-search decode of a group of clips inside ONE thread-block cluster, one launch per call.
 //
-// Why: a decode step is ~50 strictly dependent tiny operations on R = clips x beam rows.  As separate kernels (CUDA-graph
-// replayed) the 20-step decode is a chain of ~1000 launches at ~9 us each = 9.8 ms for 64 clips -- and 8.3 ms for 8 clips:
-// pure latency.  Beam search never mixes clips, so the batch is cut into groups of G clips (G x beam <= 16 rows) and every
-// group is decoded start to finish by one cluster of 8 CTAs that never talks to the rest of the grid:
-//   * CTA h of the cluster owns attention head h, 1/8 of every projection's output columns, 1/8 of the FF hidden units
-//     and 1/8 of the vocabulary; activations (16 x 256 fp32) are replicated in every CTA's shared memory;
-//   * GEMMs run on the tensor cores with the WEIGHTS as the M operand: D^T (128 weight rows x 16 decoder rows) +=
-//     W_tile (128 x 8, TMA-loaded fp32 straight from the nn.Linear layout, 128B swizzle) x X^T (8 x 16, the activations
-//     kept in shared memory in UMMA K-major layout), tcgen05.mma kind::tf32, fp32 accumulators in TMEM.  One thread feeds a
-//     4-stage TMA ring that runs ahead across phase boundaries (the weight schedule of a step is static) and issues the
-//     MMAs; the epilogue (bias / residual / GELU) reads TMEM with one lane per weight row.  An fp32 CUDA-core version of
-//     these GEMMs was measured first: FFMA2 issues at half rate with three register-pair operands, which left the cluster
-//     decoder no faster than the launch-bound graph (profiles/r1_decoder_cluster_notes.md);
-//   * a phase boundary is a one-sided DSMEM push: every CTA writes its 32-column slice into the 7 peers' buffers with
-//     st.async, each 16-byte store completing bytes on the RECEIVER's mbarrier -- no cluster barrier, no fence, no L1
-//     flush; 7 exchanges per layer-step (6 per layer + 1 for the distributed beam step).  Buffer reuse is safe because
-//     every exchange is all-to-all: a peer can only be one exchange ahead, and consecutive exchanges alternate buffers;
-//   * attention: one warp per row; every K row and every V row is requested before the first use (two L2 round trips);
-//   * the beam step is distributed: every CTA masks + scans its vocabulary slice (per-row max / sum-exp / top-k by
-//     logit), one exchange later every CTA merges the 8 partial results redundantly and deterministically, so the beam
-//     state (token histories, KV back-pointers, scores) is replicated in shared memory and needs no further exchange.
-// Precision: GEMM operands are truncated to tf32 by the tensor core (fp32 accumulate); everything else is fp32.  This
-// mode belongs to precision "fast" (whose encoder GEMMs are bf16); precision "parity" uses the fp32 graph decoder.
+// Why one launch: a decode step is ~50 strictly dependent tiny operations on R = clips x beam rows; as separate kernels the
+// 20-step decode is a chain of ~1400 launches (launch-latency bound, ~10 ms for 64 clips and for 8 clips alike).  Beam search
+// never mixes clips, so the batch is cut into groups of NR / beam clips (NR = 16 or 32 decoder rows) and every group is decoded
+// start to finish by one cluster of 8 CTAs that never talks to the rest of the grid:
+//   * CTA h owns attention head h, 1/8 of every projection, 1/8 of the FF hidden units and 1/8 of the vocabulary;
+//   * GEMMs run on the tensor cores with the WEIGHTS as the M operand and the decoder rows as N, in fp32-ACCURATE arithmetic:
+//     every weight matrix is stored as two fp16 matrices W1 = fp16(W), W2 = fp16((W - W1) * 2048), activations are split the same
+//     way on the fly (x1, x2), and  W.x = W1.x1 + 2^-11 (W1.x2 + W2.x1)  (+ O(2^-22)) is evaluated as TWO tcgen05.mma kind::f16
+//     per k16 step: W1 . [x1 | x2] (N = 2 NR, the hi and lo operand blocks are adjacent in shared memory) into accumulator
+//     columns [hi | lo], then W2 . x1 accumulated onto the lo columns; the epilogue returns hi + 2^-11 lo.  Same weight bytes as
+//     fp32 (4 B / weight), fp32 accumulation in TMEM, logits within ~2e-5 of the fp32 CPU reference -- the earlier tf32 form
+//     truncated operands to 11 bits (biased, 1e-3 on scores) and is gone;
+//   * weights stream L2 -> shared memory through a 3 x 32 KB TMA ring that runs ahead across phase boundaries (the schedule of a
+//     step is static); one warp feeds the ring, one warp issues the MMAs, twelve warps read TMEM for the epilogues;
+//   * the two attention output projections are K-SPLIT: CTA h multiplies its own head's attention output (K = 32, no
+//     all-gather of the heads) with its 32 columns of W_o for ALL 256 outputs (8 MMAs instead of 32 three-quarters-empty ones),
+//     the partial sums are reduce-scattered to the owner of each 32-column slice (the FF2 GEMM works the same way over this CTA's
+//     256 hidden units), the owner adds bias + residual and all-gathers the pre-LayerNorm slice; every CTA normalises all rows
+//     redundantly IN PLACE (fp32 staging -> hi/lo fp16 operand, same bytes).  6 exchanges per layer, all one-sided DSMEM pushes:
+//     st.async completing bytes on the RECEIVER's mbarrier -- no cluster barrier, no fence, no L1 flush;
+//   * the classifier is tiled over the vocabulary (rounds of 256 words per CTA): per round the logits tile is scanned for the
+//     running per-row max / sum-exp / top-`beam` words, so any vocabulary size works; one exchange later every CTA merges the 8
+//     partial results redundantly and deterministically (beam state replicated in shared memory);
 // Reference semantics: nn/decoders/aac_tfmer.py:100-116 (embedding*16 + PE, post-norm nn.TransformerDecoder, eps 1e-5),
 // nn/decoding/beam.py:113-203 and :230-269 (see beam.cu for the fixed-slot formulation this mirrors).
 #include <cooperative_groups.h>
@@ -39,25 +39,25 @@ namespace cnb {
 namespace {
 
 constexpr int kCl = 8;          // CTAs per cluster = attention heads
-constexpr int kRm = 16;         // decoder rows per cluster = N of the MMAs
 constexpr int kCThreads = 512;
 constexpr int kCWarps = kCThreads / 32;
-constexpr int kCD = 256, kCFF = 2048, kCLayers = 6, kCHead = 32;
+constexpr int kCD = 256, kCLayers = 6, kCHead = 32;
 constexpr int kCMaxBeam = 8;
 constexpr int kCMaxLen = 64;
 constexpr int kCMaxTp = 128;    // encoder frames per clip handled by the in-register cross-attention scores
 constexpr int kCPad = 0, kCEos = 2;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr float kCAttScale = 0.17677669529663687f;  // 1/sqrt(32)
-constexpr int kNumEx = 7;       // exchange slots (one mbarrier each)
 constexpr int kTrSlots = 20;
 constexpr int kStages = 3;      // weight ring: 3 x 32 KB
-constexpr int kStageFloats = 8192;
-constexpr int kChunksPerLayer = 4 + 3 + 8 + 8;  // QKV | sa_out, ca_q, ca_out | FF1 | FF2
-constexpr int kMaxClsTiles = 4;
-constexpr int kChains = 4;      // independent TMEM accumulators per tile (k8 step j of every k-chunk goes to chain j)
-constexpr int kTmemCols = kMaxClsTiles * kChains * 16;
-constexpr int kProducerTid = 32 * 15;  // warp 15 feeds the weight ring and has no epilogue duty (warp 11 covers its quarter)
+constexpr int kStageBytes = 32768;
+constexpr int kHalfStage = 16384;                  // W1 tiles in the first half of a stage, W2 tiles in the second
+constexpr int kChunksPerLayer = 4 + 1 + 1 + 1 + 8 + 8;  // QKV | sa_out | ca_q | ca_out | FF1 | FF2
+constexpr int kTileSlots = 4;   // TMEM accumulator tiles (2 per GEMM phase, double-buffered across classifier rounds)
+constexpr int kTmemCols = 256;  // 4 slots x 2 NR columns (NR = 32)
+constexpr int kIssuerWarp = 12, kProducerWarp = 15, kEpiGroups = 3;  // warps 0..11 read TMEM (three groups of four)
+constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
+constexpr int kClsRound = 256;  // words per CTA and classifier round (two 128-word tiles)
 
 __device__ __forceinline__ unsigned long long cl_global_ns() {
   unsigned long long t;
@@ -91,90 +91,97 @@ __device__ __forceinline__ void st_async8(uint32_t peer_addr, uint32_t a, uint32
                "r"(b), "r"(peer_bar)
                : "memory");
 }
-__device__ __forceinline__ void cbar_expect(uint32_t bar, uint32_t bytes) { mbar_expect_tx(bar, bytes); }
-__device__ __forceinline__ void cbar_wait(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
-
-// ---- activation buffers that feed the tensor cores: UMMA K-major, 128B swizzle ---------------------------------------------
-// element (row r, k) of a 16 x 256 operand lives at float index xo(r, k): 8 chunks of 32 k, each 16 rows x 128 bytes, the
-// 16-byte group index XOR-ed with (r & 7).  Chunk h is exactly the 32 columns owned by head / CTA h (2 KB contiguous).
-__device__ __forceinline__ int xo(int r, int k) {
-  return ((k >> 5) << 9) + (r << 5) + (((((k >> 2) & 7) ^ (r & 7)) << 2) | (k & 3));
+__device__ __forceinline__ void st_async4(uint32_t peer_addr, float v, uint32_t peer_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(peer_addr),
+               "r"(__float_as_uint(v)), "r"(peer_bar)
+               : "memory");
 }
 
-struct CSmem {
-  float ring[kStages][kStageFloats];  // weight tiles (A operand), 1024-byte aligned
-  float xs[kRm * kCD];                // layer input / residual stream, operand layout (replicated in every CTA)
-  float ga[kRm * kCD];                // attention outputs of all heads (gathered), operand layout
-  union {                             // never live at the same time (hs: FF1 epilogue -> last FF2 MMA)
-    float hs[kRm * kCD];              // FF1 hidden slice (local), operand layout
-    float gb[kRm][kCD];               // pre-LayerNorm rows (gathered) | FF2 partial sums (local), plain layout
-  };
-  float recv[kCl][kRm][kCHead];       // FF2 partial sums for this CTA's 32 columns, one slab per peer
-  float q[kRm][kCHead];               // q of this CTA's head
-  float kv[kRm][2 * kCHead];          // k | v of the current position, this head
-  float stat[kCl][kRm][2];            // per peer: max / sum-exp of its vocabulary slice
-  CCand cnd[kCl][kRm][kCMaxBeam];     // per peer: its best words per row (by logit)
-  float st_stat[kRm][2];              // local staging of the two above
-  CCand st_cnd[kRm][kCMaxBeam];
+// ---- fp16 hi/lo split --------------------------------------------------------------------------------------------------
+// x = x1 + 2^-11 x2 with x1 = fp16(x), x2 = fp16((x - x1) * 2048): 22 significand bits; |x2| <= |x|, so the lo part cannot
+// overflow where the hi part does not (saturating conversions; decoder activations are LayerNorm outputs, attention averages
+// and GELU hidden units, |x| << 65504).
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const act16x2 p = floats2act2(v[2 * i], v[2 * i + 1]);
+    const float2 f = __half22float2(p);
+    const act16x2 q = floats2act2((v[2 * i] - f.x) * kLoScale, (v[2 * i + 1] - f.y) * kLoScale);
+    h[i] = *reinterpret_cast<const uint32_t*>(&p);
+    l[i] = *reinterpret_cast<const uint32_t*>(&q);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// ---- operand layouts (UMMA K-major) ---------------------------------------------------------------------------------------
+// K = 256 operand of NR rows ("opx" / "oph"): 4 k-chunks of 64, each [hi: NR rows x 128 B | lo: NR rows x 128 B], 128B swizzle
+// (16-byte group index XOR (row & 7)).  hi and lo blocks are adjacent, so one MMA with N = 2 NR reads both.
+template <int NR> __device__ __forceinline__ int op_off(int r, int k) {  // byte offset of the 16-byte group holding hi(r, k..k+7)
+  return (k >> 6) * (2 * NR * 128) + r * 128 + ((((k >> 3) & 7) ^ (r & 7)) << 4);
+}
+// K = 32 operand ("opa", one head): [hi: NR rows x 64 B | lo: NR rows x 64 B], 64B swizzle (group index XOR ((row >> 1) & 3))
+__device__ __forceinline__ int opa_off(int r, int k) { return r * 64 + ((((k >> 3) & 3) ^ ((r >> 1) & 3)) << 4); }
+
+template <int NR> struct CSmem {
+  alignas(1024) uint8_t ring[kStages][kStageBytes];  // weight tiles (A operand)
+  // layer input x as hi/lo operand; between an all-gather and its LayerNorm the same bytes hold the pre-LN rows as fp32 [NR][256]
+  alignas(1024) uint8_t opx[NR * 1024];
+  // FF hidden slice (256 units of this CTA) as hi/lo operand | q [NR][32] + k|v [NR][64] of this head (fp32) during the
+  // attention phases | the fp32 logits tile [NR][256] of a classifier round
+  alignas(1024) uint8_t oph[NR * 1024];
+  alignas(1024) uint8_t opa[NR * 128];               // attention output of this head as hi/lo operand (K = 32)
+  // reduce-scatter landing zone: partial sums for this CTA's 32 columns, one slab per peer.  During the beam exchange the same
+  // bytes hold stat [kCl][NR][2] (max, sum-exp per peer slice) followed by cnd [kCl][NR][kCMaxBeam] (best words per peer slice)
+  float recv[kCl][NR][kCHead];
+  float xr[NR][kCHead];                              // this CTA's 32 columns of the residual stream, exact fp32
+  float st_stat[NR][2];                              // running max / sum-exp of this CTA's vocabulary slice
+  CCand st_cnd[NR][kCMaxBeam];                       // running best words of this CTA's vocabulary slice (by logit)
   CCand win[kCWarps][kCMaxBeam];
-  int tokens[2][kRm][kCMaxLen + 1];
-  int src[2][kRm][kCMaxLen];          // local row holding position p of this row's history (beam back-pointers)
-  float sum_lp[kRm];
-  int live[kRm];
+  uint16_t tokens[2][NR][kCMaxLen + 2];
+  uint8_t src[2][NR][kCMaxLen];                      // local row holding position p of this row's history (beam back-pointers)
+  float sum_lp[NR];
+  int live[NR];
   int any_live;
   uint32_t tmem_slot;
-  unsigned long long bars[kNumEx];    // one mbarrier per exchange slot
-  unsigned long long full[kStages], empty[kStages], tile_full[kMaxClsTiles];
+  unsigned long long bar_rs, bar_ag, bar_beam;       // exchange mbarriers: reduce-scatter, all-gather, beam step
+  unsigned long long full[kStages], empty[kStages], tile_full[kTileSlots];
   unsigned long long tr_acc[kTrSlots];
   unsigned long long tr_last;
-  unsigned long long tr2[4];         // debug (thread 0): cycles waiting for weights / issuing MMAs / waiting for MMAs / epilogue
-};
 
-// state of the weight pipeline, owned by thread 0 of the CTA (plain registers / local memory)
-struct Pipe {
-  uint32_t load = 0;  // chunks requested so far (running over all steps; meaningful in the producer thread)
-  uint32_t use = 0;   // chunks consumed so far (tracked by every thread)
-};
-
-// x = LayerNorm(gb) (eps 1e-5, biased variance), one warp per row; result in operand layout
-__device__ __forceinline__ void ln_rows(const float (*gb)[kCD], float* xs, const float* __restrict__ g,
-                                        const float* __restrict__ b, int warp, int lane) {
-  for (int r = warp; r < kRm; r += kCWarps) {
-    float v[8];
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      v[j] = gb[r][lane + 32 * j];
-      s += v[j];
-    }
-    const float mean = warp_sum(s) * (1.f / kCD);
-    float q = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) q += (v[j] - mean) * (v[j] - mean);
-    const float rstd = 1.f / sqrtf(warp_sum(q) * (1.f / kCD) + 1e-5f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = lane + 32 * j;
-      xs[xo(r, c)] = (v[j] - mean) * rstd * __ldg(g + c) + __ldg(b + c);
-    }
+  __device__ __forceinline__ float (*q())[kCHead] { return reinterpret_cast<float(*)[kCHead]>(oph); }
+  __device__ __forceinline__ float (*kv())[2 * kCHead] { return reinterpret_cast<float(*)[2 * kCHead]>(oph + NR * kCHead * 4); }
+  __device__ __forceinline__ float (*lt())[kClsRound] { return reinterpret_cast<float(*)[kClsRound]>(oph); }
+  __device__ __forceinline__ float (*stage())[kCD] { return reinterpret_cast<float(*)[kCD]>(opx); }
+  __device__ __forceinline__ float (*stat())[NR][2] { return reinterpret_cast<float(*)[NR][2]>(&recv[0][0][0]); }
+  __device__ __forceinline__ CCand (*cnd())[NR][kCMaxBeam] {
+    return reinterpret_cast<CCand(*)[NR][kCMaxBeam]>(reinterpret_cast<uint8_t*>(&recv[0][0][0]) + kCl * NR * 2 * sizeof(float));
   }
-}
+};
 
-// Attention of NR rows at once by one warp over up to NCH*32 cached keys each (+ optionally one extra key/value held in
+// state of the weight pipeline (tracked by every thread; `load` is meaningful in the producer warp)
+struct Pipe {
+  uint32_t load = 0;  // chunks requested so far (running over all steps)
+  uint32_t use = 0;   // chunks consumed so far
+};
+
+// Attention of NRW rows at once by one warp over up to NCH*32 cached keys each (+ optionally one extra key/value held in
 // shared memory: the position being decoded).  kptr(rr, j) / vptr(rr, j) give the 32-float head slice of key / value j of
 // row rr.  Scores: lane = key (8 x LDG.128 each, all rows / chunks requested before the first use).  Values: lane =
 // (key group of 4, 4-dim quad): 16-byte loads, all requested up front, then a 2-step shuffle reduction over the groups.
-template <int NR, int NCH, typename KPtr, typename VPtr>
-__device__ __forceinline__ void attend(const float* const (&q)[NR], const int (&n)[NR], const bool (&valid)[NR], KPtr kptr,
-                                       VPtr vptr, const float* const (&kv_new)[NR], bool has_new, float* const (&out)[NR],
-                                       const int (&out_sw)[NR], int lane) {
-  float sc[NR][NCH];
+// The result (32 floats per row) is written as hi/lo fp16 into the K = 32 operand buffer `opa` (row index out_row[rr]).
+template <int NR, int NRW, int NCH, typename KPtr, typename VPtr>
+__device__ __forceinline__ void attend(const float* const (&q)[NRW], const int (&n)[NRW], const bool (&valid)[NRW], KPtr kptr,
+                                       VPtr vptr, const float* const (&kv_new)[NRW], bool has_new, uint8_t* opa,
+                                       const int (&out_row)[NRW], int lane) {
+  float sc[NRW][NCH];
 #pragma unroll
-  for (int rr = 0; rr < NR; ++rr) {
+  for (int rr = 0; rr < NRW; ++rr) {
     float qv[kCHead];
 #pragma unroll
     for (int d = 0; d < kCHead; d += 4) {
-      const float4 t = *reinterpret_cast<const float4*>(q[rr] + d);
+      const float4 t = valid[rr] ? *reinterpret_cast<const float4*>(q[rr] + d) : make_float4(0.f, 0.f, 0.f, 0.f);
       qv[d] = t.x; qv[d + 1] = t.y; qv[d + 2] = t.z; qv[d + 3] = t.w;
     }
 #pragma unroll
@@ -196,11 +203,11 @@ __device__ __forceinline__ void attend(const float* const (&q)[NR], const int (&
       }
     }
   }
-  float e[NR][NCH], e_new[NR], inv[NR];
+  float e[NRW][NCH], e_new[NRW], inv[NRW];
 #pragma unroll
-  for (int rr = 0; rr < NR; ++rr) {
+  for (int rr = 0; rr < NRW; ++rr) {
     float s_new = -INFINITY;
-    if (has_new) s_new = warp_sum(q[rr][lane] * kv_new[rr][lane]) * kCAttScale;
+    if (has_new) s_new = warp_sum(valid[rr] ? q[rr][lane] * kv_new[rr][lane] : 0.f) * kCAttScale;
     float mx = s_new;
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) mx = fmaxf(mx, sc[rr][ch]);
@@ -218,7 +225,7 @@ __device__ __forceinline__ void attend(const float* const (&q)[NR], const int (&
   // values
   const int dq = lane & 7, pg = lane >> 3;
 #pragma unroll
-  for (int rr = 0; rr < NR; ++rr) {
+  for (int rr = 0; rr < NRW; ++rr) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
@@ -243,23 +250,26 @@ __device__ __forceinline__ void attend(const float* const (&q)[NR], const int (&
       acc.x += __shfl_xor_sync(kFull, acc.x, o); acc.y += __shfl_xor_sync(kFull, acc.y, o);
       acc.z += __shfl_xor_sync(kFull, acc.z, o); acc.w += __shfl_xor_sync(kFull, acc.w, o);
     }
-    if (valid[rr] && lane < 8) {
-      if (has_new) {
-        const float4 vn = *reinterpret_cast<const float4*>(kv_new[rr] + kCHead + 4 * dq);
-        acc.x = fmaf(e_new[rr], vn.x, acc.x); acc.y = fmaf(e_new[rr], vn.y, acc.y);
-        acc.z = fmaf(e_new[rr], vn.z, acc.z); acc.w = fmaf(e_new[rr], vn.w, acc.w);
-      }
-      *reinterpret_cast<float4*>(out[rr] + 4 * (dq ^ out_sw[rr])) =
-          make_float4(acc.x * inv[rr], acc.y * inv[rr], acc.z * inv[rr], acc.w * inv[rr]);
+    if (has_new && valid[rr] && lane < 8) {
+      const float4 vn = *reinterpret_cast<const float4*>(kv_new[rr] + kCHead + 4 * dq);
+      acc.x = fmaf(e_new[rr], vn.x, acc.x); acc.y = fmaf(e_new[rr], vn.y, acc.y);
+      acc.z = fmaf(e_new[rr], vn.z, acc.z); acc.w = fmaf(e_new[rr], vn.w, acc.w);
+    }
+    acc.x *= inv[rr]; acc.y *= inv[rr]; acc.z *= inv[rr]; acc.w *= inv[rr];
+    // lanes 0..7 hold dims [4 dq, +4): even lanes fetch their neighbour's quad and write one 16-byte hi group + one lo group
+    const float nx = __shfl_down_sync(kFull, acc.x, 1), ny = __shfl_down_sync(kFull, acc.y, 1);
+    const float nz = __shfl_down_sync(kFull, acc.z, 1), nw = __shfl_down_sync(kFull, acc.w, 1);
+    if (valid[rr] && lane < 8 && (lane & 1) == 0) {
+      const float v8[8] = {acc.x, acc.y, acc.z, acc.w, nx, ny, nz, nw};
+      uint4 hi, lo;
+      split8(v8, hi, lo);
+      const int off = opa_off(out_row[rr], 4 * dq);
+      *reinterpret_cast<uint4*>(opa + off) = hi;
+      *reinterpret_cast<uint4*>(opa + NR * 64 + off) = lo;
     }
   }
 }
 
-// per-thread-0 cycle counters inside the GEMM phases (tr2): compile with -DCNB_DEC_TR2=1 to collect them; off by default
-// because the clock reads and the divergent shared-memory updates sit on the MMA issue path of warp 0
-#ifndef CNB_DEC_TR2
-#define CNB_DEC_TR2 0
-#endif
 #define CL_TR(slot)                                \
   if (tr_on) {                                     \
     const unsigned long long n_ = cl_global_ns();  \
@@ -268,418 +278,544 @@ __device__ __forceinline__ void attend(const float* const (&q)[NR], const int (&
   }
 
 // ---- weight pipeline --------------------------------------------------------------------------------------------------
-// The chunk stream of one decode step is static (chunk = one 32 KB ring stage):
-//   per layer  QKV      4 chunks: two k-chunks of 32, each 3 boxes [32 rows x 32 k] (q / k / v rows of this head)
-//              sa_out, ca_q, ca_out   1 chunk each: eight boxes [32 rows x 32 k] at a 4 KB pitch (the whole K = 256)
-//              FF1, FF2 8 chunks each: one box [256 rows x 32 k] = both 128-row tiles of one k-chunk
-//   classifier 8 chunks per pair of 128-word tiles
-// Chunk g (running index) lives in ring stage g % kStages.  Producer = thread 32, MMA issuer = thread 0.
-__device__ __forceinline__ void issue_chunk(CSmem& S, const PersistentArgs& a, uint32_t g, int rank, int v0, int chunks_per_step) {
+// The chunk stream of one decode step is static (chunk = one 32 KB ring stage: W1 tiles in the first 16 KB, W2 tiles in the
+// second 16 KB, all fp16, k-chunks of 64 = 128-byte rows):
+//   per layer  QKV      4 chunks: k-chunk c, three boxes [32 rows x 64 k] per half (q / k / v rows of this head: one 96-row tile)
+//              sa_out   1 chunk : head-packed W_o[:, 32 h .. +32]: two boxes [128 rows x 32 k] per half (64-byte rows, 64B swizzle)
+//              ca_q     1 chunk : four boxes [32 rows x 64 k] per half (the whole K = 256 of this head's 32 query rows)
+//              ca_out   1 chunk : like sa_out
+//              FF1      8 chunks: tile t (128 hidden units) x k-chunk c: one box [128 rows x 64 k] per half
+//              FF2      8 chunks: tile t (128 outputs) x k-chunk c of this CTA's K slice [256 rank, +256)
+//   classifier 8 chunks per round of 256 words: tile t x k-chunk c; rows beyond the vocabulary are zero-filled by TMA
+// Chunk g (running index) lives in ring stage g % kStages.
+__device__ __forceinline__ void issue_chunk(uint8_t* ring, unsigned long long* full, const ClusterArgs& a, uint32_t g, int rank,
+                                            int v0, int chunks_per_step) {
   const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(a.tmaps);
   const int s = (int)(g % kStages);
   const int idx = (int)(g % (uint32_t)chunks_per_step);
-  const uint32_t dst = smem_addr(&S.ring[s][0]);
-  const uint32_t bar = smem_addr(&S.full[s]);
+  const uint32_t dst = smem_addr(ring + (size_t)s * kStageBytes);
+  const uint32_t bar = smem_addr(&full[s]);
   if (idx < kCLayers * kChunksPerLayer) {
     const int l = idx / kChunksPerLayer, j = idx - l * kChunksPerLayer;
+    const CUtensorMap* lm = maps + kDecMapsPerLayer * l;
     if (j < 4) {  // QKV
       mbar_expect_tx(bar, 6 * 4096);
 #pragma unroll
-      for (int sub = 0; sub < 2; ++sub)
+      for (int half = 0; half < 2; ++half)
 #pragma unroll
         for (int part = 0; part < 3; ++part)
-          tma_load_2d(dst + sub * 16384 + part * 4096, maps + 6 * l, (2 * j + sub) * 32, part * kCD + rank * kCHead, bar);
-    } else if (j < 7) {  // sa_out / ca_q / ca_out
+          tma_load_2d(dst + half * kHalfStage + part * 4096, lm + 0 + half, j * 64, part * kCD + rank * kCHead, bar);
+    } else if (j == 4 || j == 6) {  // sa_out / ca_out (head-packed, K = 32)
+      mbar_expect_tx(bar, 4 * 8192);
+      const CUtensorMap* m = lm + (j == 4 ? 2 : 6);
+#pragma unroll
+      for (int half = 0; half < 2; ++half)
+#pragma unroll
+        for (int t = 0; t < 2; ++t) tma_load_2d(dst + half * kHalfStage + t * 8192, m + half, 0, rank * kCD + t * 128, bar);
+    } else if (j == 5) {  // ca_q
       mbar_expect_tx(bar, 8 * 4096);
 #pragma unroll
-      for (int sub = 0; sub < 8; ++sub) tma_load_2d(dst + sub * 4096, maps + 6 * l + 1 + (j - 4), sub * 32, rank * kCHead, bar);
-    } else if (j < 15) {  // FF1: hidden units [256 rank, +256)
-      mbar_expect_tx(bar, 32768);
-      tma_load_2d(dst, maps + 6 * l + 4, (j - 7) * 32, rank * kCD, bar);
-    } else {  // FF2: all 256 outputs, this CTA's K slice [256 rank, +256)
-      mbar_expect_tx(bar, 32768);
-      tma_load_2d(dst, maps + 6 * l + 5, rank * kCD + (j - 15) * 32, 0, bar);
+      for (int half = 0; half < 2; ++half)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tma_load_2d(dst + half * kHalfStage + c * 4096, lm + 4 + half, c * 64, rank * kCHead, bar);
+    } else if (j < 15) {  // FF1: hidden units [256 rank + 128 t, +128)
+      const int t = (j - 7) >> 2, c = (j - 7) & 3;
+      mbar_expect_tx(bar, 2 * kHalfStage);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) tma_load_2d(dst + half * kHalfStage, lm + 8 + half, c * 64, rank * kCD + t * 128, bar);
+    } else {  // FF2: outputs [128 t, +128), this CTA's K slice
+      const int t = (j - 15) >> 2, c = (j - 15) & 3;
+      mbar_expect_tx(bar, 2 * kHalfStage);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) tma_load_2d(dst + half * kHalfStage, lm + 10 + half, rank * kCD + c * 64, t * 128, bar);
     }
-  } else {  // classifier: words [v0 + 256 pair, +256); rows beyond the vocabulary are zero-filled by TMA
+  } else {  // classifier
     const int jj = idx - kCLayers * kChunksPerLayer;
-    mbar_expect_tx(bar, 32768);
-    tma_load_2d(dst, maps + 36, (jj & 7) * 32, v0 + (jj >> 3) * 256, bar);
+    const int rd = jj >> 3, t = (jj >> 2) & 1, c = jj & 3;
+    mbar_expect_tx(bar, 2 * kHalfStage);
+#pragma unroll
+    for (int half = 0; half < 2; ++half)
+      tma_load_2d(dst + half * kHalfStage, maps + kCLayers * kDecMapsPerLayer + half, c * 64, v0 + rd * kClsRound + t * 128, bar);
   }
 }
 
-// k8 step j of one k-chunk for TPC tiles (accumulator chain j).  Issuing a tcgen05.mma costs the issuing thread ~100 cycles
-// (measured), far more than the ~24 tensor-pipe cycles of a 128 x 16 x 8 MMA: four threads issue, one per chain.
-template <int TPC>
-__device__ __forceinline__ void mma_block(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, int j) {
-  constexpr uint32_t idesc = make_idesc_tf32(128, kRm);
-#pragma unroll
-  for (int tt = 0; tt < TPC; ++tt)
-    tcgen05_mma_tf32(tmem_d + (uint32_t)((tt * kChains + j) * kRm), adesc + (uint64_t)(2 * j + tt * 1024), bdesc + 2 * j, idesc,
-                     accumulate);
-}
+enum GemmKind : int { G_QKV = 0, G_P32 = 1, G_OUT = 2, G_FF = 3 };
 
-// Geometry of a GEMM phase: n_chunks ring stages; a chunk carries `tpc` tiles (16 KB apart) x `ns` k-chunks of 32 (sub_pitch
-// bytes apart); 8 / ns chunks complete a group of tpc accumulator tiles.
-struct GemmShape {
-  int n_chunks, tpc, ns, sub_pitch;
-};
-
-// One GEMM phase on the tensor cores; xbuf = B operand (16 x 256, operand layout).  epi(tile, quarter, lane, v[16]) is
-// called by the four warps that own the accumulator rows [32 quarter, +32) of that tile: v[r] = sum_k W[row][k] * x[r][k].
+// One GEMM phase on the tensor cores.  `b_addr` = shared-memory address of the B operand (hi/lo activations); accumulator tile t
+// of the phase lives in TMEM slot slot0 + t.  epi(t, quarter, lane, r0, v[16]) is called by the warps that own accumulator rows
+// [32 quarter, +32) of tile t, once per block of 16 decoder rows: v[j] = sum_k W[row][k] * x[r0 + j][k] (hi + 2^-11 lo).
 // Ends with all threads having finished their TMEM reads (callers __syncthreads() before touching what the epilogue wrote).
-template <typename Epi>
-__device__ __forceinline__ void tc_gemm(CSmem& S, const PersistentArgs& a, Pipe& pp, uint32_t tmem_base, uint32_t& tile_par,
-                                        const GemmShape g, const float* xbuf, int rank, int v0, int chunks_per_step, Epi epi) {
+template <int NR, typename Epi>
+__device__ __forceinline__ void tc_gemm(CSmem<NR>& S, const ClusterArgs& a, Pipe& pp, uint32_t tmem_base, uint32_t& tile_par,
+                                        int kind, int n_chunks, uint32_t b_addr, int slot0, int rank, int v0,
+                                        int chunks_per_step, Epi epi) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   fence_proxy_async_smem();  // activations were written through the generic / st.async path: make them visible to the MMA
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const int cpg = 8 / g.ns;  // chunks per tile group
-  const int n_tiles = (g.n_chunks / cpg) * g.tpc;
-  // Producer and MMA issuers run their loops on WHOLE warps with warp-uniform values and one elected lane issuing (elect_one,
-  // tc_ptx.cuh): under a single-thread branch every TMA / MMA operand went through a vector -> uniform register waterfall
-  // loop, ~75-100 cycles per instruction (the decode spent 19 % of its time issuing 24 k MMAs per CTA).
-  if (warp == kCWarps - 1) {
+  const int n_tiles = kind == G_FF ? n_chunks / 4 : (kind == G_OUT ? 2 : 1);
+  if (warp == kProducerWarp) {
     // producer: this phase's chunks, then run ahead into the next phases' weights as far as the ring allows.  Every wait is
-    // on MMAs that the issuers issue without depending on this warp beyond the current phase: no deadlock.
-    const uint32_t target = pp.use + (uint32_t)g.n_chunks + (kStages - 1);
+    // on MMAs that the issuer issues without depending on this warp beyond the current phase: no deadlock.
+    const uint32_t target = pp.use + (uint32_t)n_chunks + (kStages - 1);
     while (pp.load < target) {
       const int s = (int)(pp.load % kStages);
       mbar_wait(smem_addr(&S.empty[s]), ((pp.load / kStages) & 1u) ^ 1u);  // the MMAs that read this stage have completed
-      if (elect_one()) issue_chunk(S, a, pp.load, rank, v0, chunks_per_step);
+      if (elect_one()) issue_chunk(&S.ring[0][0], S.full, a, pp.load, rank, v0, chunks_per_step);
       __syncwarp();
       ++pp.load;
     }
-  } else if ((warp & 3) == 0) {
-    // MMA issuers (warps 0, 4, 8, 12; issuer j owns accumulator chain j): descriptors advance by plain adds.
-    const int chain = __shfl_sync(kFull, warp >> 2, 0);
+  } else if (warp == kIssuerWarp) {
+    // MMA issuer: the whole warp runs the loop with warp-uniform values, one elected lane issues (tc_ptx.cuh elect_one)
+    constexpr uint32_t idesc_hl = make_idesc(128, 2 * NR), idesc_l = make_idesc(128, NR);
     const uint32_t tb = __shfl_sync(kFull, tmem_base, 0);
-    const uint64_t bdesc0 = make_smem_desc(smem_addr(xbuf));
-    const uint32_t a_step = (uint32_t)g.sub_pitch >> 4;
-    for (int i = 0; i < g.n_chunks; ++i) {
+    for (int i = 0; i < n_chunks; ++i) {
       const uint32_t u = pp.use + (uint32_t)i;
       const int s = (int)(u % kStages);
-#if CNB_DEC_TR2
-      const unsigned long long tf0 = clock64();
-      const bool tr0 = tid == 0;
-#endif
       mbar_wait(smem_addr(&S.full[s]), (u / kStages) & 1u);
       tcgen05_fence_after();
-#if CNB_DEC_TR2
-      const unsigned long long tf1 = clock64();
-      if (tr0) S.tr2[0] += tf1 - tf0;
-#endif
-      const int grp = i / cpg, ic = i - grp * cpg;
       if (elect_one()) {
-        uint64_t adesc = make_smem_desc(smem_addr(&S.ring[s][0]));
-        uint64_t bdesc = bdesc0 + (uint64_t)(ic * g.ns * 128);  // 2048 bytes per k-chunk of the B operand
-        const uint32_t tmem_d = tb + (uint32_t)(grp * g.tpc * kChains * kRm);
-        if (g.tpc == 2) {
-          for (int sub = 0; sub < g.ns; ++sub, adesc += a_step, bdesc += 128) mma_block<2>(tmem_d, adesc, bdesc, (ic | sub) != 0, chain);
-        } else {
-          for (int sub = 0; sub < g.ns; ++sub, adesc += a_step, bdesc += 128) mma_block<1>(tmem_d, adesc, bdesc, (ic | sub) != 0, chain);
+        const uint32_t st = smem_addr(&S.ring[s][0]);
+        if (kind == G_OUT) {
+          const uint64_t bdesc = make_smem_desc_sw64(b_addr);
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const uint64_t a1 = make_smem_desc_sw64(st + t * 8192), a2 = make_smem_desc_sw64(st + kHalfStage + t * 8192);
+            const uint32_t d = tb + (uint32_t)((slot0 + t) * 2 * NR);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              tcgen05_mma_bf16(d, a1 + 2 * k, bdesc + 2 * k, idesc_hl, k != 0);
+              tcgen05_mma_bf16(d + NR, a2 + 2 * k, bdesc + 2 * k, idesc_l, 1u);
+            }
+            tcgen05_commit(smem_addr(&S.tile_full[slot0 + t]));
+          }
+        } else if (kind == G_P32) {
+          const uint32_t d = tb + (uint32_t)(slot0 * 2 * NR);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint64_t a1 = make_smem_desc(st + c * 4096), a2 = make_smem_desc(st + kHalfStage + c * 4096);
+            const uint64_t bdesc = make_smem_desc(b_addr + c * (2 * NR * 128));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              tcgen05_mma_bf16(d, a1 + 2 * k, bdesc + 2 * k, idesc_hl, (c | k) != 0);
+              tcgen05_mma_bf16(d + NR, a2 + 2 * k, bdesc + 2 * k, idesc_l, 1u);
+            }
+          }
+          tcgen05_commit(smem_addr(&S.tile_full[slot0]));
+        } else {  // G_QKV: chunk i = k-chunk i of the single tile; G_FF: chunk i = (tile i / 4, k-chunk i % 4)
+          const int t = kind == G_FF ? (i >> 2) : 0, c = kind == G_FF ? (i & 3) : i;
+          const uint32_t d = tb + (uint32_t)((slot0 + t) * 2 * NR);
+          const uint64_t a1 = make_smem_desc(st), a2 = make_smem_desc(st + kHalfStage);
+          const uint64_t bdesc = make_smem_desc(b_addr + c * (2 * NR * 128));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            tcgen05_mma_bf16(d, a1 + 2 * k, bdesc + 2 * k, idesc_hl, (c | k) != 0);
+            tcgen05_mma_bf16(d + NR, a2 + 2 * k, bdesc + 2 * k, idesc_l, 1u);
+          }
+          if (c == 3) tcgen05_commit(smem_addr(&S.tile_full[slot0 + t]));
         }
         tcgen05_commit(smem_addr(&S.empty[s]));  // frees the stage once these MMAs have read it
-        if (ic == cpg - 1)
-          for (int tt = 0; tt < g.tpc; ++tt) tcgen05_commit(smem_addr(&S.tile_full[grp * g.tpc + tt]));
       }
       __syncwarp();
-#if CNB_DEC_TR2
-      if (tr0) S.tr2[1] += clock64() - tf1;
-#endif
     }
   }
-  pp.use += (uint32_t)g.n_chunks;
+  pp.use += (uint32_t)n_chunks;
   __syncwarp();
-  // accumulator rows [32 q, +32) are only reachable from warps with id % 4 == q: warps 4t .. 4t+3 read tile t, except that
-  // warp 15 (the producer) hands tile 3 / quarter 3 to warp 11
-  const int quarter = warp & 3;
-  for (int t = warp >> 2; t < n_tiles && warp != 15; t += (warp == 11 ? 1 : kMaxClsTiles)) {
-#if CNB_DEC_TR2
-    const unsigned long long tw0 = clock64();
-#endif
-    mbar_wait(smem_addr(&S.tile_full[t]), (tile_par >> t) & 1u);
-    tcgen05_fence_after();
-#if CNB_DEC_TR2
-    if (tid == 0) S.tr2[2] += clock64() - tw0;
-#endif
-    float v[kRm], w[kRm];
-    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * kChains * kRm);
-    tmem_ld_32x16(taddr, v);
+  // accumulator rows [32 q, +32) are only reachable from warps with id % 4 == q: warps 4 g .. 4 g + 3 read tiles g, g + 3, ...
+  if (warp < 4 * kEpiGroups) {
+    const int quarter = warp & 3;
+    for (int t = warp >> 2; t < n_tiles; t += kEpiGroups) {
+      const int slot = slot0 + t;
+      mbar_wait(smem_addr(&S.tile_full[slot]), (tile_par >> slot) & 1u);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * 2 * NR);
 #pragma unroll
-    for (int c = 1; c < kChains; ++c) {
-      tmem_ld_32x16(taddr + c * kRm, w);
-      tmem_ld_wait();
+      for (int r0 = 0; r0 < NR; r0 += 16) {
+        float v[16], w[16];
+        tmem_ld_32x16(taddr + r0, v);
+        tmem_ld_32x16(taddr + NR + r0, w);
+        tmem_ld_wait();
 #pragma unroll
-      for (int r = 0; r < kRm; ++r) v[r] += w[r];
+        for (int j = 0; j < 16; ++j) v[j] = fmaf(w[j], kLoInv, v[j]);
+        epi(t, quarter, lane, r0, v);
+      }
     }
-    epi(t, quarter, lane, v);
-#if CNB_DEC_TR2
-    if (tid == 0) S.tr2[3] += clock64() - tw0;
-#endif
   }
-  tile_par ^= (1u << n_tiles) - 1u;  // every thread tracks the phase parity of every accumulator tile
+  tile_par ^= ((1u << n_tiles) - 1u) << slot0;  // every thread tracks the phase parity of every accumulator slot
   tcgen05_fence_before();
 }
 
+// counters of completed exchanges (parity of the mbarrier phases); identical in every thread of every CTA of the cluster
+struct ExCount {
+  uint32_t rs = 0, ag = 0, beam = 0;
+};
+
+// Epilogue of a K-split GEMM (sa_out / ca_out / FF2): partial sum of output column n = 128 t + 32 quarter + lane goes to the CTA
+// that owns the column (n / 32) -- slab `rank` of its reduce-scatter zone.
+template <int NR>
+__device__ __forceinline__ void rs_push(CSmem<NR>& S, int rank, int t, int quarter, int lane, int r0, const float (&v)[16]) {
+  const int owner = 4 * t + quarter;
+  if (owner == rank) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) S.recv[rank][r0 + j][lane] = v[j];
+  } else {
+    const uint32_t dst = map_peer(smem_addr(&S.recv[rank][r0][lane]), owner);
+    const uint32_t bar = map_peer(smem_addr(&S.bar_rs), owner);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) st_async4(dst + j * (kCHead * 4), v[j], bar);
+  }
+}
+
+// After a K-split GEMM: wait for the 7 peers' partial sums, x_pre[r][own 32 columns] = residual + bias + sum of the 8 partials
+// (fixed order), all-gather the pre-LayerNorm slices into every CTA's staging area (= opx), LayerNorm all rows in place:
+// opx becomes the hi/lo operand of the next GEMM, xr the exact fp32 residual slice.
+template <int NR>
+__device__ __forceinline__ void reduce_gather_ln(CSmem<NR>& S, ExCount& ex, int rank, const float* __restrict__ bias,
+                                                 const float* __restrict__ g, const float* __restrict__ b) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr uint32_t kBytes = (kCl - 1) * NR * kCHead * 4;
+  const uint32_t bar_rs = smem_addr(&S.bar_rs), bar_ag = smem_addr(&S.bar_ag);
+  if (tid == 0) {
+    mbar_expect_tx(bar_rs, kBytes);
+    mbar_expect_tx(bar_ag, kBytes);
+  }
+  mbar_wait(bar_rs, ex.rs & 1u);
+  ++ex.rs;
+  __syncthreads();  // this CTA's own slab was written with ordinary stores by the epilogue warps
+  float (*stg)[kCD] = S.stage();
+  for (int idx = tid; idx < NR * 8; idx += kCThreads) {
+    const int r = idx >> 3, q4 = idx & 7;
+    float4 y = __ldg(reinterpret_cast<const float4*>(bias + rank * kCHead) + q4);
+    const float4 x = *reinterpret_cast<const float4*>(&S.xr[r][4 * q4]);
+    y.x += x.x; y.y += x.y; y.z += x.z; y.w += x.w;
+#pragma unroll
+    for (int i = 0; i < kCl; ++i) {  // fixed order
+      const float4 p = *reinterpret_cast<const float4*>(&S.recv[i][r][4 * q4]);
+      y.x += p.x; y.y += p.y; y.z += p.z; y.w += p.w;
+    }
+    float* dst = &stg[r][rank * kCHead + 4 * q4];
+    *reinterpret_cast<float4*>(dst) = y;
+    const uint32_t da = smem_addr(dst);
+#pragma unroll
+    for (int p = 1; p < kCl; ++p) {
+      const int peer = (rank + p) & (kCl - 1);
+      st_async16(map_peer(da, peer), y, map_peer(bar_ag, peer));
+    }
+  }
+  mbar_wait(bar_ag, ex.ag & 1u);
+  ++ex.ag;
+  __syncthreads();  // own slice (ordinary stores) visible to every warp
+  // LayerNorm (eps 1e-5, biased variance): one warp per row, lane holds columns [8 lane, +8)
+  float v[NR / kCWarps][8];
+#pragma unroll
+  for (int rr = 0; rr < NR / kCWarps; ++rr) {
+    const int r = warp + kCWarps * rr;
+    const float4 p0 = *reinterpret_cast<const float4*>(&stg[r][8 * lane]);
+    const float4 p1 = *reinterpret_cast<const float4*>(&stg[r][8 * lane + 4]);
+    const float x[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += x[j];
+    const float mean = warp_sum(s) * (1.f / kCD);
+    float qq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) qq += (x[j] - mean) * (x[j] - mean);
+    const float rstd = 1.f / sqrtf(warp_sum(qq) * (1.f / kCD) + 1e-5f);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(g) + 2 * lane), g1 = __ldg(reinterpret_cast<const float4*>(g) + 2 * lane + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(b) + 2 * lane), b1 = __ldg(reinterpret_cast<const float4*>(b) + 2 * lane + 1);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[rr][j] = (x[j] - mean) * rstd * gg[j] + bb[j];
+  }
+  __syncthreads();  // every row has been read: the staging bytes may now be overwritten by the operand layout
+#pragma unroll
+  for (int rr = 0; rr < NR / kCWarps; ++rr) {
+    const int r = warp + kCWarps * rr;
+    uint4 hi, lo;
+    split8(v[rr], hi, lo);
+    const int off = op_off<NR>(r, 8 * lane);
+    *reinterpret_cast<uint4*>(S.opx + off) = hi;
+    *reinterpret_cast<uint4*>(S.opx + NR * 128 + off) = lo;
+    if ((lane >> 2) == rank) {
+      *reinterpret_cast<float4*>(&S.xr[r][8 * (lane & 3)]) = make_float4(v[rr][0], v[rr][1], v[rr][2], v[rr][3]);
+      *reinterpret_cast<float4*>(&S.xr[r][8 * (lane & 3) + 4]) = make_float4(v[rr][4], v[rr][5], v[rr][6], v[rr][7]);
+    }
+  }
+}
+
+// x[r] = emb[token of row r at `pos`] * 16 + PE[pos] -> opx (hi/lo operand) + xr (own residual slice); rows >= R are zero
+template <int NR>
+__device__ __forceinline__ void embed_rows(CSmem<NR>& S, const ClusterArgs& a, int rank, int R, int cur, int pos) {
+  for (int i = threadIdx.x; i < NR * 32; i += kCThreads) {
+    const int r = i >> 5, ch = i & 31;  // columns [8 ch, +8)
+    float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (r < R) {
+      const int tok = S.tokens[cur][r][pos];
+      const float4* e = reinterpret_cast<const float4*>(a.emb + (int64_t)tok * kCD) + 2 * ch;
+      const float4* p = reinterpret_cast<const float4*>(a.pe + (int64_t)pos * kCD) + 2 * ch;
+      const float4 e0 = __ldg(e), e1 = __ldg(e + 1), p0 = __ldg(p), p1 = __ldg(p + 1);
+      x[0] = fmaf(e0.x, 16.f, p0.x); x[1] = fmaf(e0.y, 16.f, p0.y); x[2] = fmaf(e0.z, 16.f, p0.z); x[3] = fmaf(e0.w, 16.f, p0.w);
+      x[4] = fmaf(e1.x, 16.f, p1.x); x[5] = fmaf(e1.y, 16.f, p1.y); x[6] = fmaf(e1.z, 16.f, p1.z); x[7] = fmaf(e1.w, 16.f, p1.w);
+    }
+    uint4 hi, lo;
+    split8(x, hi, lo);
+    const int off = op_off<NR>(r, 8 * ch);
+    *reinterpret_cast<uint4*>(S.opx + off) = hi;
+    *reinterpret_cast<uint4*>(S.opx + NR * 128 + off) = lo;
+    if ((ch >> 2) == rank) {
+      *reinterpret_cast<float4*>(&S.xr[r][8 * (ch & 3)]) = make_float4(x[0], x[1], x[2], x[3]);
+      *reinterpret_cast<float4*>(&S.xr[r][8 * (ch & 3) + 4]) = make_float4(x[4], x[5], x[6], x[7]);
+    }
+  }
+}
+
 // One decoder layer for the rows of this cluster (all 8 CTAs execute it in lock step through the six exchanges).
-// `par` = parity of this call's exchange mbarrier completions (every slot 0..5 completes exactly once per layer).
-__device__ __noinline__ void decode_layer(CSmem& S, const PersistentArgs& a, Pipe& pp, uint32_t tmem_base, uint32_t& tile_par,
-                                          int l, int rank, int R, int grow0, int clip0, int pos, int cur, uint32_t par,
+template <int NR>
+__device__ __noinline__ void decode_layer(CSmem<NR>& S, const ClusterArgs& a, Pipe& pp, ExCount& ex, uint32_t tmem_base,
+                                          uint32_t& tile_par, int l, int rank, int R, int grow0, int clip0, int pos, int cur,
                                           int v0, int chunks_per_step, bool tr_on) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int beam = a.beam, max_len = a.max_len, tp = a.tp;
   const int64_t cache_l = (int64_t)a.rows * max_len * kCD;
   const int64_t kv_stride = (int64_t)kCLayers * 2 * kCD;
-  const PLayer& L = a.layers[l];
-  // push this CTA's 2 KB chunk `rank` of an operand-layout buffer (same offset in every CTA) to the 7 peers on exchange
-  // slot e, then wait until the 7 peers' chunks have landed here.  Callers __syncthreads() before (the chunk is complete).
-  auto exchange_chunk = [&](float* buf, int e) {
-    const uint32_t bar = smem_addr(&S.bars[e]);
-    if (tid == 0) cbar_expect(bar, (kCl - 1) * kRm * kCHead * 4);
-    for (int idx = tid; idx < (kCl - 1) * kRm * 8; idx += kCThreads) {
-      const int p = idx / (kRm * 8), q = idx - p * (kRm * 8);
-      const int peer = (rank + 1 + p) & (kCl - 1);
-      float* src = buf + rank * (kRm * kCHead) + 4 * q;
-      st_async16(map_peer(smem_addr(src), peer), *reinterpret_cast<const float4*>(src), map_peer(bar, peer));
-    }
-    cbar_wait(bar, par);
-  };
-  // same for columns [32 rank, +32) of the plain-layout gb
-  auto exchange_slice = [&](float* buf, int e) {
-    const uint32_t bar = smem_addr(&S.bars[e]);
-    if (tid == 0) cbar_expect(bar, (kCl - 1) * kRm * kCHead * 4);
-    for (int idx = tid; idx < (kCl - 1) * kRm * 8; idx += kCThreads) {
-      const int p = idx / (kRm * 8), rem = idx - p * (kRm * 8);
-      const int r = rem >> 3, q = rem & 7;
-      const int peer = (rank + 1 + p) & (kCl - 1);
-      float* src = buf + r * kCD + rank * kCHead + 4 * q;
-      st_async16(map_peer(smem_addr(src), peer), *reinterpret_cast<const float4*>(src), map_peer(bar, peer));
-    }
-    cbar_wait(bar, par);
-  };
+  const ClusterLayer& L = a.layers[l];
+  constexpr int NRW = NR / kCWarps;  // rows per warp in the attention phases
+  float (*Q)[kCHead] = S.q();
+  float (*KV)[2 * kCHead] = S.kv();
+  const uint32_t opx = smem_addr(S.opx), oph = smem_addr(S.oph), opa = smem_addr(S.opa);
 
   // ---- P1: q | k | v of head `rank` (96 weight rows), then self-attention for the rows of this head
-  tc_gemm(S, a, pp, tmem_base, tile_par, GemmShape{4, 1, 2, 16384}, S.xs, rank, v0, chunks_per_step,
-          [&](int, int quarter, int d, const float (&v)[kRm]) {
-            if (quarter >= 3) return;
-            const float bias = __ldg(L.sa_in_b + quarter * kCD + rank * kCHead + d);
+  tc_gemm<NR>(S, a, pp, tmem_base, tile_par, G_QKV, 4, opx, 0, rank, v0, chunks_per_step,
+              [&](int, int quarter, int d, int r0, const float (&v)[16]) {
+                if (quarter >= 3) return;
+                const float bias = __ldg(L.sa_in_b + quarter * kCD + rank * kCHead + d);
 #pragma unroll
-            for (int r = 0; r < kRm; ++r) {
-              if (quarter == 0) S.q[r][d] = v[r] + bias;
-              else S.kv[r][(quarter - 1) * kCHead + d] = v[r] + bias;
-            }
-          });
+                for (int j = 0; j < 16; ++j) {
+                  if (quarter == 0) Q[r0 + j][d] = v[j] + bias;
+                  else KV[r0 + j][(quarter - 1) * kCHead + d] = v[j] + bias;
+                }
+              });
   __syncthreads();
   CL_TR(0);
   {
     float* kc = a.kc + l * cache_l;
     float* vc = a.vc + l * cache_l;
-    for (int r = warp; r < R; r += kCWarps) {
-      const float* const qq[1] = {&S.q[r][0]};
-      const float* const kvn[1] = {&S.kv[r][0]};
-      float* const oo[1] = {S.ga + rank * (kRm * kCHead) + r * kCHead};
-      const int osw[1] = {r & 7};
-      const int nn[1] = {pos};
-      const bool valid[1] = {true};
-      const int* s0 = &S.src[cur][r][0];
-      // the new position goes to this head's slice of the global cache (read back in later steps only)
-      const int64_t o = ((int64_t)(grow0 + r) * max_len + pos) * kCD + rank * kCHead + lane;
-      kc[o] = kvn[0][lane];
-      vc[o] = kvn[0][kCHead + lane];
-      auto kp = [&](int, int j) { return kc + ((int64_t)(grow0 + s0[j]) * max_len + j) * kCD + rank * kCHead; };
-      auto vp = [&](int, int j) { return vc + ((int64_t)(grow0 + s0[j]) * max_len + j) * kCD + rank * kCHead; };
-      if (pos <= 32) attend<1, 1>(qq, nn, valid, kp, vp, kvn, true, oo, osw, lane);
-      else attend<1, 2>(qq, nn, valid, kp, vp, kvn, true, oo, osw, lane);
+    const float* qq[NRW];
+    const float* kvn[NRW];
+    int orow[NRW], nn[NRW];
+    bool valid[NRW];
+    const uint8_t* s0[NRW];
+#pragma unroll
+    for (int rr = 0; rr < NRW; ++rr) {
+      const int r = warp + kCWarps * rr;
+      valid[rr] = r < R;
+      qq[rr] = &Q[r][0];
+      kvn[rr] = &KV[r][0];
+      orow[rr] = r;
+      nn[rr] = pos;
+      s0[rr] = &S.src[cur][r][0];
+      if (valid[rr]) {  // the new position goes to this head's slice of the global cache (read back in later steps only)
+        const int64_t o = ((int64_t)(grow0 + r) * max_len + pos) * kCD + rank * kCHead + lane;
+        kc[o] = kvn[rr][lane];
+        vc[o] = kvn[rr][kCHead + lane];
+      }
+    }
+    auto kp = [&](int rr, int j) { return kc + ((int64_t)(grow0 + s0[rr][j]) * max_len + j) * kCD + rank * kCHead; };
+    auto vp = [&](int rr, int j) { return vc + ((int64_t)(grow0 + s0[rr][j]) * max_len + j) * kCD + rank * kCHead; };
+    if (valid[0]) {  // warp-uniform (rows of a warp: r, r + 16)
+      if (pos <= 32) attend<NR, NRW, 1>(qq, nn, valid, kp, vp, kvn, true, S.opa, orow, lane);
+      else attend<NR, NRW, 2>(qq, nn, valid, kp, vp, kvn, true, S.opa, orow, lane);
     }
   }
-  __syncthreads();
   CL_TR(1);
-  exchange_chunk(S.ga, 0);
+  // ---- P2: self-attention output projection, K-split over the heads; reduce-scatter, + bias + residual, all-gather, LayerNorm 1
+  tc_gemm<NR>(S, a, pp, tmem_base, tile_par, G_OUT, 1, opa, 0, rank, v0, chunks_per_step,
+              [&](int t, int quarter, int ln, int r0, const float (&v)[16]) { rs_push<NR>(S, rank, t, quarter, ln, r0, v); });
   CL_TR(2);
-  // ---- P2: self-attention output projection (32 columns) + residual, gather, LayerNorm 1
-  tc_gemm(S, a, pp, tmem_base, tile_par, GemmShape{1, 1, 8, 4096}, S.ga, rank, v0, chunks_per_step,
-          [&](int, int quarter, int j, const float (&v)[kRm]) {
-            if (quarter != 0) return;
-            const int c = rank * kCHead + j;
-            const float bias = __ldg(L.sa_out_b + c);
-#pragma unroll
-            for (int r = 0; r < kRm; ++r) S.gb[r][c] = S.xs[xo(r, c)] + (v[r] + bias);
-          });
-  __syncthreads();
+  reduce_gather_ln<NR>(S, ex, rank, L.sa_out_b, L.n1_g, L.n1_b);
   CL_TR(3);
-  exchange_slice(&S.gb[0][0], 1);
-  CL_TR(4);
-  ln_rows(S.gb, S.xs, L.n1_g, L.n1_b, warp, lane);
-  CL_TR(5);
   // ---- P3: cross-attention query of head `rank`, cross-attention over the clip's encoder frames
-  tc_gemm(S, a, pp, tmem_base, tile_par, GemmShape{1, 1, 8, 4096}, S.xs, rank, v0, chunks_per_step,
-          [&](int, int quarter, int j, const float (&v)[kRm]) {
-            if (quarter != 0) return;
-            const float bias = __ldg(L.ca_q_b + rank * kCHead + j);
+  tc_gemm<NR>(S, a, pp, tmem_base, tile_par, G_P32, 1, opx, 0, rank, v0, chunks_per_step,
+              [&](int, int quarter, int j, int r0, const float (&v)[16]) {
+                if (quarter != 0) return;
+                const float bias = __ldg(L.ca_q_b + rank * kCHead + j);
 #pragma unroll
-            for (int r = 0; r < kRm; ++r) S.q[r][j] = v[r] + bias;
-          });
+                for (int i = 0; i < 16; ++i) Q[r0 + i][j] = v[i] + bias;
+              });
   __syncthreads();
-  CL_TR(6);
+  CL_TR(4);
   {
     const float* ck = a.ckv + (int64_t)l * 2 * kCD + rank * kCHead;  // key-padding mask: frames >= len are skipped
-    for (int r = warp; r < R; r += kCWarps) {
-      const float* const qq[1] = {&S.q[r][0]};
-      const float* const kvn[1] = {nullptr};
-      float* const oo[1] = {S.ga + rank * (kRm * kCHead) + r * kCHead};
-      const int osw[1] = {r & 7};
-      const int c0 = clip0 + r / beam;
-      const int nn[1] = {min(a.lens[c0], tp)};
-      const bool valid[1] = {true};
-      auto kp = [&](int, int j) { return ck + ((int64_t)c0 * tp + j) * kv_stride; };
-      auto vp = [&](int, int j) { return ck + ((int64_t)c0 * tp + j) * kv_stride + kCD; };
-      if (tp <= 32) attend<1, 1>(qq, nn, valid, kp, vp, kvn, false, oo, osw, lane);
-      else if (tp <= 64) attend<1, 2>(qq, nn, valid, kp, vp, kvn, false, oo, osw, lane);
-      else attend<1, 4>(qq, nn, valid, kp, vp, kvn, false, oo, osw, lane);
+    const float* qq[NRW];
+    const float* kvn[NRW];
+    int orow[NRW], nn[NRW], c0[NRW];
+    bool valid[NRW];
+#pragma unroll
+    for (int rr = 0; rr < NRW; ++rr) {
+      const int r = warp + kCWarps * rr;
+      valid[rr] = r < R;
+      qq[rr] = &Q[r][0];
+      kvn[rr] = nullptr;
+      orow[rr] = r;
+      c0[rr] = clip0 + (valid[rr] ? r / beam : 0);
+      nn[rr] = valid[rr] ? min(a.lens[c0[rr]], tp) : 0;
+    }
+    auto kp = [&](int rr, int j) { return ck + ((int64_t)c0[rr] * tp + j) * kv_stride; };
+    auto vp = [&](int rr, int j) { return ck + ((int64_t)c0[rr] * tp + j) * kv_stride + kCD; };
+    if (valid[0]) {
+      if (tp <= 32) attend<NR, NRW, 1>(qq, nn, valid, kp, vp, kvn, false, S.opa, orow, lane);
+      else if (tp <= 64) attend<NR, NRW, 2>(qq, nn, valid, kp, vp, kvn, false, S.opa, orow, lane);
+      else attend<NR, NRW, 4>(qq, nn, valid, kp, vp, kvn, false, S.opa, orow, lane);
     }
   }
-  __syncthreads();
+  CL_TR(5);
+  // ---- P4: cross-attention output projection (K-split), reduce-scatter, all-gather, LayerNorm 2
+  tc_gemm<NR>(S, a, pp, tmem_base, tile_par, G_OUT, 1, opa, 0, rank, v0, chunks_per_step,
+              [&](int t, int quarter, int ln, int r0, const float (&v)[16]) { rs_push<NR>(S, rank, t, quarter, ln, r0, v); });
+  CL_TR(6);
+  reduce_gather_ln<NR>(S, ex, rank, L.ca_out_b, L.n2_g, L.n2_b);
   CL_TR(7);
-  exchange_chunk(S.ga, 2);
+  // ---- P5: FF1 slice (256 hidden units of this CTA) + GELU -> oph (hi/lo operand)
+  tc_gemm<NR>(S, a, pp, tmem_base, tile_par, G_FF, 8, opx, 0, rank, v0, chunks_per_step,
+              [&](int t, int quarter, int d, int r0, const float (&v)[16]) {
+                const int j = t * 128 + quarter * 32 + d;  // hidden unit = k index of the FF2 operand
+                const float bias = __ldg(L.l1_b + rank * kCD + j);
+                uint8_t* base = S.oph + (j >> 6) * (2 * NR * 128) + (j & 7) * 2;
+                const int grp = (j >> 3) & 7;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const int r = r0 + i;
+                  const float h = gelu_erf(v[i] + bias);
+                  const act16 h1 = float2act(h);
+                  const act16 h2 = float2act((h - act2float(h1)) * kLoScale);
+                  uint8_t* p = base + r * 128 + ((grp ^ (r & 7)) << 4);
+                  *reinterpret_cast<act16*>(p) = h1;
+                  *reinterpret_cast<act16*>(p + NR * 128) = h2;
+                }
+              });
   CL_TR(8);
-  // ---- P4: cross-attention output projection + residual, gather, LayerNorm 2
-  tc_gemm(S, a, pp, tmem_base, tile_par, GemmShape{1, 1, 8, 4096}, S.ga, rank, v0, chunks_per_step,
-          [&](int, int quarter, int j, const float (&v)[kRm]) {
-            if (quarter != 0) return;
-            const int c = rank * kCHead + j;
-            const float bias = __ldg(L.ca_out_b + c);
-#pragma unroll
-            for (int r = 0; r < kRm; ++r) S.gb[r][c] = S.xs[xo(r, c)] + (v[r] + bias);
-          });
-  __syncthreads();
+  // ---- P6: FF2 partial sums over this CTA's K slice for all 256 outputs, reduce-scatter, + bias + residual, all-gather, LN 3
+  tc_gemm<NR>(S, a, pp, tmem_base, tile_par, G_FF, 8, oph, 0, rank, v0, chunks_per_step,
+              [&](int t, int quarter, int ln, int r0, const float (&v)[16]) { rs_push<NR>(S, rank, t, quarter, ln, r0, v); });
   CL_TR(9);
-  exchange_slice(&S.gb[0][0], 3);
+  reduce_gather_ln<NR>(S, ex, rank, L.l2_b, L.n3_g, L.n3_b);
   CL_TR(10);
-  ln_rows(S.gb, S.xs, L.n2_g, L.n2_b, warp, lane);
-  // ---- P5: FF1 slice (256 hidden units of this CTA) + GELU -> hs (operand layout)
-  tc_gemm(S, a, pp, tmem_base, tile_par, GemmShape{8, 2, 1, 0}, S.xs, rank, v0, chunks_per_step,
-          [&](int t, int quarter, int d, const float (&v)[kRm]) {
-            const int j = t * 128 + quarter * 32 + d;
-            const float bias = __ldg(L.l1_b + rank * kCD + j);
-#pragma unroll
-            for (int r = 0; r < kRm; ++r) S.hs[xo(r, j)] = gelu_erf(v[r] + bias);
-          });
-  CL_TR(11);
-  // ---- P6: FF2 partial sums over this CTA's K slice for all 256 outputs, reduce-scatter, + bias + residual, gather, LN 3
-  tc_gemm(S, a, pp, tmem_base, tile_par, GemmShape{8, 2, 1, 0}, S.hs, rank, v0, chunks_per_step,
-          [&](int t, int quarter, int d, const float (&v)[kRm]) {
-            const int n = t * 128 + quarter * 32 + d;
-#pragma unroll
-            for (int r = 0; r < kRm; ++r) S.gb[r][n] = v[r];
-          });
-  __syncthreads();
-  CL_TR(12);
-  {
-    const uint32_t bar = smem_addr(&S.bars[4]);
-    if (tid == 0) cbar_expect(bar, (kCl - 1) * kRm * kCHead * 4);
-    for (int idx = tid; idx < kCl * kRm * 8; idx += kCThreads) {
-      const int p = idx / (kRm * 8), rem = idx - p * (kRm * 8);
-      const int r = rem >> 3, q = rem & 7;
-      const int peer = (rank + p) & (kCl - 1);
-      const float4 v = *reinterpret_cast<const float4*>(&S.gb[r][peer * kCHead + 4 * q]);
-      float* dst = &S.recv[rank][r][4 * q];
-      if (peer == rank) *reinterpret_cast<float4*>(dst) = v;
-      else st_async16(map_peer(smem_addr(dst), peer), v, map_peer(bar, peer));
-    }
-    cbar_wait(bar, par);
-    __syncthreads();  // own slab was written with ordinary stores; every thread is done reading the partial sums in gb
-  }
-  CL_TR(13);
-  for (int idx = tid; idx < kRm * kCHead; idx += kCThreads) {
-    const int r = idx >> 5, c = idx & 31;
-    float y = __ldg(L.l2_b + rank * kCHead + c);
-#pragma unroll
-    for (int i = 0; i < kCl; ++i) y += S.recv[i][r][c];  // fixed order
-    S.gb[r][rank * kCHead + c] = S.xs[xo(r, rank * kCHead + c)] + y;
-  }
-  __syncthreads();
-  exchange_slice(&S.gb[0][0], 5);
-  ln_rows(S.gb, S.xs, L.n3_g, L.n3_b, warp, lane);
-  CL_TR(14);
 }
 
-// Classifier slice + distributed beam step (one exchange on slot 6, parity `par`).
-__device__ __noinline__ void decode_select(CSmem& S, const PersistentArgs& a, Pipe& pp, uint32_t tmem_base, uint32_t& tile_par,
-                                           float* s_logits, int rank, int R, int grow0, int nclips, int step, int cur, int vs,
-                                           uint32_t par, int chunks_per_step, bool tr_on) {
+// Classifier slice (rounds of 256 words) + distributed beam step (one exchange).
+template <int NR>
+__device__ __noinline__ void decode_select(CSmem<NR>& S, const ClusterArgs& a, Pipe& pp, ExCount& ex, uint32_t tmem_base,
+                                           uint32_t& tile_par, int rank, int R, int grow0, int nclips, int step, int cur,
+                                           int vs, int chunks_per_step, bool tr_on) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int beam = a.beam, max_len = a.max_len, V = a.vocab;
   const int v0 = rank * vs;
-  const int ncls = min(vs, V - v0) > 0 ? min(vs, V - v0) : 0;
-  // ---- classifier slice: logits[r][c] for words v0 + c (tiles of 128 words)
-  {
-    const int cls_pairs = (vs + 255) / 256;
-    tc_gemm(S, a, pp, tmem_base, tile_par, GemmShape{cls_pairs * 8, 2, 1, 0}, S.xs, rank, v0, chunks_per_step,
-            [&](int t, int quarter, int d, const float (&v)[kRm]) {
-              const int j = t * 128 + quarter * 32 + d;
-              if (j < ncls) {
-                const float bias = __ldg(a.cls_b + v0 + j);
+  const int n_rounds = vs / kClsRound;
+  float (*LT)[kClsRound] = S.lt();
+  // ---- classifier rounds: logits tile -> running per-row max / sum-exp / top-`beam` words of this vocabulary slice
+  for (int rd = 0; rd < n_rounds; ++rd) {
+    const int base = v0 + rd * kClsRound;
+    tc_gemm<NR>(S, a, pp, tmem_base, tile_par, G_FF, 8, smem_addr(S.opx), (rd & 1) * 2, rank, v0, chunks_per_step,
+                [&](int t, int quarter, int d, int r0, const float (&v)[16]) {
+                  const int j = t * 128 + quarter * 32 + d;
+                  const int w = base + j;
+                  const float bias = w < V ? __ldg(a.cls_b + w) : 0.f;
 #pragma unroll
-                for (int r = 0; r < kRm; ++r) s_logits[r * vs + j] = v[r] + bias;
-              }
-            });
+                  for (int i = 0; i < 16; ++i) LT[r0 + i][j] = w < V ? v[i] + bias : -INFINITY;
+                });
+    __syncthreads();
+    CL_TR(11);
+    for (int r = warp; r < R; r += kCWarps) {
+      float x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) x[u] = LT[r][lane + 32 * u];
+      if (a.tap != nullptr) {  // raw logits (before the masks), reference seam AACDecoder.__call__
+        float* tp_ = a.tap + ((int64_t)step * a.rows + grow0 + r) * V;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (base + lane + 32 * u < V) tp_[base + lane + 32 * u] = x[u];
+      }
+      if (step < a.min_len) {  // beam.py:129-130
+        const int e = kCEos - base;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (e == lane + 32 * u) x[u] = -INFINITY;
+      }
+      if (a.forbid != nullptr) {  // beam.py:146-156
+        for (int p = 0; p <= step; ++p) {
+          const int tok = S.tokens[cur][r][p];
+          const int e = tok - base;
+          if (e >= 0 && e < kClsRound && (e & 31) == lane && a.forbid[tok]) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (u == (e >> 5)) x[u] = -INFINITY;
+          }
+        }
+      }
+      float mx = x[0];
+#pragma unroll
+      for (int u = 1; u < 8; ++u) mx = fmaxf(mx, x[u]);
+      mx = warp_max(mx);
+      float sm = 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) sm += (x[u] == -INFINITY) ? 0.f : expf(x[u] - mx);
+      sm = warp_sum(sm);
+      if (mx == -INFINITY) sm = 0.f;
+      // the previous rounds' list joins as one extra candidate per lane (lane k holds entry k)
+      CCand old{-INFINITY, 0x7fffffff};
+      if (rd > 0 && lane < beam) old = S.st_cnd[r][lane];
+      float om = -INFINITY, os = 0.f;
+      if (rd > 0) {
+        om = S.st_stat[r][0];
+        os = S.st_stat[r][1];
+      }
+      __syncwarp();
+      if (lane == 0) {
+        const float m2 = fmaxf(om, mx);
+        float s2 = 0.f;
+        if (m2 != -INFINITY) s2 = (om == -INFINITY ? 0.f : os * expf(om - m2)) + (mx == -INFINITY ? 0.f : sm * expf(mx - m2));
+        S.st_stat[r][0] = m2;
+        S.st_stat[r][1] = s2;
+      }
+      // `beam` rounds of: every lane's best candidate strictly after the previous winner, then a warp arg-max
+      CCand prev{INFINITY, -1};
+      for (int k = 0; k < beam; ++k) {
+        CCand best{-INFINITY, 0x7fffffff};
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const CCand cc{x[u], base + lane + 32 * u};
+          if (cc.idx < V && cbetter(cc, best) && cbetter(prev, cc)) best = cc;
+        }
+        if (old.idx != 0x7fffffff && cbetter(old, best) && cbetter(prev, old)) best = old;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const CCand other{__shfl_xor_sync(kFull, best.v, o), __shfl_xor_sync(kFull, best.idx, o)};
+          if (cbetter(other, best)) best = other;
+        }
+        if (lane == 0) S.st_cnd[r][k] = best;
+        prev = best;
+        if (best.idx == 0x7fffffff) prev = CCand{-INFINITY, 0x7ffffffe};  // exhausted (or NaN logits): keep emitting sentinels
+      }
+      __syncwarp();
+    }
+    CL_TR(12);
   }
   __syncthreads();
-  CL_TR(15);
-  // ---- beam step, part A (local): masks, per-row max / sum-exp / top-`beam` words of this vocabulary slice
-  for (int r = warp; r < R; r += kCWarps) {
-    float* lg = s_logits + r * vs;
-    if (lane == 0 && step < a.min_len && kCEos >= v0 && kCEos < v0 + ncls) lg[kCEos - v0] = -INFINITY;  // beam.py:129-130
-    if (a.forbid != nullptr) {                                                                           // beam.py:146-156
-      for (int p = lane; p <= step; p += 32) {
-        const int tok = S.tokens[cur][r][p];
-        if (a.forbid[tok] && tok >= v0 && tok < v0 + ncls) lg[tok - v0] = -INFINITY;
-      }
-    }
-    __syncwarp();
-    float mx = -INFINITY;
-    for (int c = lane; c < ncls; c += 32) mx = fmaxf(mx, lg[c]);
-    mx = warp_max(mx);
-    float sm = 0.f;
-    for (int c = lane; c < ncls; c += 32) sm += expf(lg[c] - mx);
-    sm = warp_sum(sm);
-    if (lane == 0) {
-      S.st_stat[r][0] = mx;
-      S.st_stat[r][1] = (mx == -INFINITY) ? 0.f : sm;
-    }
-    // `beam` rounds of: every lane's best word strictly after the previous winner, then a warp arg-max
-    CCand prev{INFINITY, -1};
-    for (int k = 0; k < beam; ++k) {
-      CCand best{-INFINITY, 0x7fffffff};
-      for (int c = lane; c < ncls; c += 32) {
-        const CCand cc{lg[c], v0 + c};
-        if (cbetter(cc, best) && cbetter(prev, cc)) best = cc;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const CCand other{__shfl_xor_sync(kFull, best.v, o), __shfl_xor_sync(kFull, best.idx, o)};
-        if (cbetter(other, best)) best = other;
-      }
-      if (lane == 0) S.st_cnd[r][k] = best;
-      prev = best;
-      if (best.idx == 0x7fffffff) prev = CCand{-INFINITY, 0x7ffffffe};  // exhausted (or NaN logits): keep emitting sentinels
-    }
-  }
-  __syncthreads();
-  CL_TR(16);
   {
-    const uint32_t bar = smem_addr(&S.bars[6]);
+    const uint32_t bar = smem_addr(&S.bar_beam);
     constexpr int kUnits = 1 + kCMaxBeam;  // 8-byte units per row: (max, sum-exp) + kCMaxBeam candidates
-    if (tid == 0) cbar_expect(bar, (kCl - 1) * kRm * kUnits * 8);
-    for (int idx = tid; idx < kCl * kRm * kUnits; idx += kCThreads) {
-      const int p = idx / (kRm * kUnits), rem = idx - p * (kRm * kUnits);
+    if (tid == 0) mbar_expect_tx(bar, (kCl - 1) * NR * kUnits * 8);
+    float (*STAT)[NR][2] = S.stat();
+    CCand (*CND)[NR][kCMaxBeam] = S.cnd();
+    for (int idx = tid; idx < kCl * NR * kUnits; idx += kCThreads) {
+      const int p = idx / (NR * kUnits), rem = idx - p * (NR * kUnits);
       const int r = rem / kUnits, u = rem - r * kUnits;
       const int peer = (rank + p) & (kCl - 1);
       const uint32_t* srcw = u == 0 ? reinterpret_cast<const uint32_t*>(&S.st_stat[r][0])
                                     : reinterpret_cast<const uint32_t*>(&S.st_cnd[r][u - 1]);
-      void* dst = u == 0 ? static_cast<void*>(&S.stat[rank][r][0]) : static_cast<void*>(&S.cnd[rank][r][u - 1]);
+      void* dst = u == 0 ? static_cast<void*>(&STAT[rank][r][0]) : static_cast<void*>(&CND[rank][r][u - 1]);
       if (peer == rank) {
         reinterpret_cast<uint32_t*>(dst)[0] = srcw[0];
         reinterpret_cast<uint32_t*>(dst)[1] = srcw[1];
@@ -687,11 +823,14 @@ __device__ __noinline__ void decode_select(CSmem& S, const PersistentArgs& a, Pi
         st_async8(map_peer(smem_addr(dst), peer), srcw[0], srcw[1], map_peer(bar, peer));
       }
     }
-    cbar_wait(bar, par);
+    mbar_wait(bar, ex.beam & 1u);
+    ++ex.beam;
     __syncthreads();
   }
-  CL_TR(17);
+  CL_TR(13);
   // ---- beam step, part B (replicated): merge, flat top-k per clip, history / back-pointer update, finish bookkeeping
+  float (*STAT)[NR][2] = S.stat();
+  CCand (*CND)[NR][kCMaxBeam] = S.cnd();
   const int nxt = cur ^ 1;
   for (int lc = warp; lc < nclips; lc += kCWarps) {
     const int r0 = lc * beam;
@@ -732,12 +871,12 @@ __device__ __noinline__ void decode_select(CSmem& S, const PersistentArgs& a, Pi
       row_lg[j] = 0.f;
       if (j < nrows_used) {
         const int r = r0 + label_at(j);
-        float m = S.stat[0][r][0];
+        float m = STAT[0][r][0];
 #pragma unroll
-        for (int i = 1; i < kCl; ++i) m = fmaxf(m, S.stat[i][r][0]);
+        for (int i = 1; i < kCl; ++i) m = fmaxf(m, STAT[i][r][0]);
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < kCl; ++i) s += S.stat[i][r][1] * expf(S.stat[i][r][0] - m);
+        for (int i = 0; i < kCl; ++i) s += STAT[i][r][1] * expf(STAT[i][r][0] - m);
         row_mx[j] = m;
         row_lg[j] = logf(s);
       }
@@ -751,7 +890,7 @@ __device__ __noinline__ void decode_select(CSmem& S, const PersistentArgs& a, Pi
         const int j = ci / (kCl * beam), rem = ci - j * (kCl * beam);
         const int i = rem / beam, k = rem - i * beam;
         const int r = r0 + label_at(j);
-        const CCand raw = S.cnd[i][r][k];
+        const CCand raw = CND[i][r][k];
         if (raw.idx == 0x7fffffff) continue;
         float mxj = 0.f, lgj = 0.f, pv = 0.f;
 #pragma unroll
@@ -789,8 +928,8 @@ __device__ __noinline__ void decode_select(CSmem& S, const PersistentArgs& a, Pi
         S.tokens[nxt][row][p] = S.tokens[cur][srow][p];
         if (p < max_len) S.src[nxt][row][p] = S.src[cur][srow][p];
       } else {
-        S.tokens[nxt][row][p] = word;
-        if (p < max_len) S.src[nxt][row][p] = row;
+        S.tokens[nxt][row][p] = (uint16_t)word;
+        if (p < max_len) S.src[nxt][row][p] = (uint8_t)row;
       }
     }
     __syncwarp();
@@ -813,16 +952,16 @@ __device__ __noinline__ void decode_select(CSmem& S, const PersistentArgs& a, Pi
     __syncwarp();
   }
   __syncthreads();
-  CL_TR(18);
+  CL_TR(14);
 }
 
+template <int NR>
 __global__ void __launch_bounds__(kCThreads, 1)
-decoder_cluster_kernel(const __grid_constant__ PersistentArgs a, int clips_per_group, int n_groups, int vs /*vocabulary slice*/) {
+decoder_cluster_kernel(const __grid_constant__ ClusterArgs a, int clips_per_group, int n_groups, int vs /*vocabulary slice*/) {
   extern __shared__ uint8_t smem_raw[];
   // operand tiles need 1024-byte alignment (128B swizzle atoms); the offset is the same in every CTA of the launch
   uint8_t* smem_al = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
-  CSmem& S = *reinterpret_cast<CSmem*>(smem_al);
-  float* s_logits = reinterpret_cast<float*>(smem_al + sizeof(CSmem));  // [kRm][vs]
+  CSmem<NR>& S = *reinterpret_cast<CSmem<NR>*>(smem_al);
 
   cg::cluster_group cl = cg::this_cluster();
   const int rank = (int)cl.block_rank();  // = attention head owned by this CTA
@@ -830,21 +969,23 @@ decoder_cluster_kernel(const __grid_constant__ PersistentArgs a, int clips_per_g
   const int tid = threadIdx.x, warp = tid >> 5;
   const int beam = a.beam, max_len = a.max_len;
   const int v0 = rank * vs;
-  const int chunks_per_step = kCLayers * kChunksPerLayer + ((vs + 255) / 256) * 8;
+  const int chunks_per_step = kCLayers * kChunksPerLayer + (vs / kClsRound) * 8;
   int steps_max = 0;
-  for (int i = tid; i < (int)(sizeof(CSmem) / 4); i += kCThreads) reinterpret_cast<uint32_t*>(smem_al)[i] = 0u;
+  for (int i = tid; i < (int)(sizeof(CSmem<NR>) / 4); i += kCThreads) reinterpret_cast<uint32_t*>(smem_al)[i] = 0u;
   __syncthreads();
   if (tid == 0) {
-    for (int e = 0; e < kNumEx; ++e) mbar_init(smem_addr(&S.bars[e]), 1);
+    mbar_init(smem_addr(&S.bar_rs), 1);
+    mbar_init(smem_addr(&S.bar_ag), 1);
+    mbar_init(smem_addr(&S.bar_beam), 1);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(smem_addr(&S.full[s]), 1);
-      mbar_init(smem_addr(&S.empty[s]), kChains);  // one tcgen05.commit per MMA issuer
+      mbar_init(smem_addr(&S.empty[s]), 1);
     }
-    for (int t = 0; t < kMaxClsTiles; ++t) mbar_init(smem_addr(&S.tile_full[t]), kChains);
+    for (int t = 0; t < kTileSlots; ++t) mbar_init(smem_addr(&S.tile_full[t]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async_smem();
   }
-  if (warp == 0) {  // TMEM: 4 tiles x 4 chains x 16 columns
+  if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&S.tmem_slot)), "r"(kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -858,54 +999,42 @@ decoder_cluster_kernel(const __grid_constant__ PersistentArgs a, int clips_per_g
   if (tr_on) S.tr_last = cl_global_ns();
   cl.sync();  // every CTA's mbarriers are initialised before any peer pushes data at them
   Pipe pp;
+  ExCount ex;
   uint32_t tile_par = 0;
-  int n_layers = 0, n_steps = 0;  // completed exchange rounds: parity of the exchange mbarrier phases
 
   for (int g = cluster_id; g < n_groups; g += n_clusters) {
     const int clip0 = g * clips_per_group;
     const int nclips = min(clips_per_group, a.batch - clip0);
-    const int R = nclips * beam;       // live local rows (<= kRm)
+    const int R = nclips * beam;       // live local rows (<= NR)
     const int grow0 = clip0 * beam;    // first global row of the group
 
     // ---- init: beam state (replicated), outputs (rank 0), first embedding
-    for (int i = tid; i < 2 * kRm * (kCMaxLen + 1); i += kCThreads) (&S.tokens[0][0][0])[i] = kCPad;
-    for (int i = tid; i < 2 * kRm * kCMaxLen; i += kCThreads) (&S.src[0][0][0])[i] = (i / kCMaxLen) % kRm;
-    if (tid < kRm) {
+    for (int i = tid; i < 2 * NR * (kCMaxLen + 2); i += kCThreads) (&S.tokens[0][0][0])[i] = kCPad;
+    for (int i = tid; i < 2 * NR * kCMaxLen; i += kCThreads) (&S.src[0][0][0])[i] = (uint8_t)((i / kCMaxLen) % NR);
+    if (tid < NR) {
       S.sum_lp[tid] = 0.f;
       S.live[tid] = tid < R ? 1 : 0;
     }
     __syncthreads();
-    if (tid < R) S.tokens[0][tid][0] = (int)a.bos_ids[clip0 + tid / beam];
+    if (tid < R) S.tokens[0][tid][0] = (uint16_t)a.bos_ids[clip0 + tid / beam];
     if (rank == 0) {
       for (int i = tid; i < R * max_len; i += kCThreads) a.bs.out_preds[(int64_t)grow0 * max_len + i] = kCPad;
       if (tid < R) a.bs.out_lp[grow0 + tid] = 0.f;
     }
     __syncthreads();
-    for (int i = tid; i < kRm * (kCD / 4); i += kCThreads) {
-      const int r = i / (kCD / 4), q = i % (kCD / 4);
-      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r < R) {
-        const int tok = S.tokens[0][r][0];
-        const float4 e = __ldg(reinterpret_cast<const float4*>(a.emb + (int64_t)tok * kCD) + q);
-        const float4 p = __ldg(reinterpret_cast<const float4*>(a.pe) + q);
-        o = make_float4(fmaf(e.x, 16.f, p.x), fmaf(e.y, 16.f, p.y), fmaf(e.z, 16.f, p.z), fmaf(e.w, 16.f, p.w));
-      }
-      *reinterpret_cast<float4*>(&S.xs[xo(r, 4 * q)]) = o;
-    }
+    embed_rows<NR>(S, a, rank, R, 0, 0);
     __syncthreads();
 
     int cur = 0, steps_done = max_len;
     for (int step = 0; step < max_len; ++step) {
-      const int pos = step;
-      for (int l = 0; l < kCLayers; ++l) {
-        decode_layer(S, a, pp, tmem_base, tile_par, l, rank, R, grow0, clip0, pos, cur, (uint32_t)(n_layers & 1), v0,
-                     chunks_per_step, tr_on);
-        ++n_layers;
-      }
-      decode_select(S, a, pp, tmem_base, tile_par, s_logits, rank, R, grow0, nclips, step, cur, vs, (uint32_t)(n_steps & 1),
-                    chunks_per_step, tr_on);
-      ++n_steps;
+      for (int l = 0; l < kCLayers; ++l)
+        decode_layer<NR>(S, a, pp, ex, tmem_base, tile_par, l, rank, R, grow0, clip0, step, cur, v0, chunks_per_step, tr_on);
+      decode_select<NR>(S, a, pp, ex, tmem_base, tile_par, rank, R, grow0, nclips, step, cur, vs, chunks_per_step, tr_on);
       cur ^= 1;
+      // The beam exchange landed in the reduce-scatter zone: no peer may start the next step's first reduce-scatter before
+      // every CTA has finished merging.  Split cluster barrier: arrive here, wait right before the first K-split GEMM could
+      // push (i.e. before the next layer 0) -- the embedding and the early-exit test run in its shadow.
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
       // ---- continue?  (state is replicated, so every CTA of the cluster takes the same branch)
       if (tid == 0) {
         int any = 0;
@@ -913,32 +1042,23 @@ decoder_cluster_kernel(const __grid_constant__ PersistentArgs a, int clips_per_g
         S.any_live = any;
       }
       __syncthreads();
-      if (!S.any_live) {
+      const bool go_on = S.any_live != 0;
+      if (go_on && step + 1 < max_len) embed_rows<NR>(S, a, rank, R, cur, step + 1);
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+      if (!go_on) {
         steps_done = step + 1;
         break;
-      }
-      // ---- next embedding: x[r] = emb[token at position step+1] * 16 + PE[step+1]
-      if (step + 1 < max_len) {
-        for (int i = tid; i < R * (kCD / 4); i += kCThreads) {
-          const int r = i / (kCD / 4), q = i % (kCD / 4);
-          const int tok = S.tokens[cur][r][step + 1];
-          const float4 e = __ldg(reinterpret_cast<const float4*>(a.emb + (int64_t)tok * kCD) + q);
-          const float4 p = __ldg(reinterpret_cast<const float4*>(a.pe + (int64_t)(step + 1) * kCD) + q);
-          *reinterpret_cast<float4*>(&S.xs[xo(r, 4 * q)]) =
-              make_float4(fmaf(e.x, 16.f, p.x), fmaf(e.y, 16.f, p.y), fmaf(e.z, 16.f, p.z), fmaf(e.w, 16.f, p.w));
-        }
       }
       __syncthreads();
     }
     steps_max = max(steps_max, steps_done);
+    __syncthreads();
   }
   // drain the weight chunks that were requested ahead but never consumed
-  if (warp == kCWarps - 1)
+  if (warp == kProducerWarp)
     for (uint32_t u = pp.use; u < pp.load; ++u) mbar_wait(smem_addr(&S.full[u % kStages]), (u / kStages) & 1u);
   if (tr_on)
     for (int i = 0; i < kTrSlots; ++i) a.trace[i] = S.tr_acc[i];
-  if (tr_on)
-    for (int i = 0; i < 4; ++i) a.trace[kTrSlots + i] = S.tr2[i];
   if (rank == 0 && tid == 0 && steps_max > 0) atomicMax(&a.bs.done[1], steps_max);
   tcgen05_fence_before();
   cl.sync();  // no CTA may exit while a peer can still push into its shared memory
@@ -948,18 +1068,18 @@ decoder_cluster_kernel(const __grid_constant__ PersistentArgs a, int clips_per_g
   }
 }
 
-size_t cluster_smem(int vs) { return sizeof(CSmem) + (size_t)kRm * vs * sizeof(float) + 1024; }
+template <int NR> size_t cluster_smem() { return sizeof(CSmem<NR>) + 1024; }
 
 struct ClusterPlan {
-  int clips_per_group = 0, n_groups = 0, vs = 0, n_clusters = 0;
+  int nr = 0, clips_per_group = 0, n_groups = 0, vs = 0, n_clusters = 0;
   size_t smem = 0;
 };
 
-int max_clusters_for(size_t smem, int* out) {
-  static int cached = 0;
-  static size_t cached_smem = 0;
-  if (cached == 0 || cached_smem != smem) {
-    CNB_CUDA_OK(cudaFuncSetAttribute(decoder_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <int NR> int max_clusters_for(int* out) {
+  static int cached = -1;
+  if (cached < 0) {
+    const size_t smem = cluster_smem<NR>();
+    CNB_CUDA_OK(cudaFuncSetAttribute(decoder_cluster_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t lc = {};
     lc.blockDim = dim3(kCThreads);
     lc.gridDim = dim3(kCl * 64);
@@ -972,50 +1092,66 @@ int max_clusters_for(size_t smem, int* out) {
     lc.attrs = la;
     lc.numAttrs = 1;
     int n = 0;
-    CNB_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, decoder_cluster_kernel, &lc));
+    CNB_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, decoder_cluster_kernel<NR>, &lc));
     cached = n;
-    cached_smem = smem;
-    if (getenv("CNB_DEC_TRACE")) fprintf(stderr, "[dec cluster] max active clusters %d, smem %zu B\n", n, smem);
+    if (getenv("CNB_DEC_TRACE")) fprintf(stderr, "[dec cluster] NR %d: max active clusters %d, smem %zu B\n", NR, n, smem);
   }
   *out = cached;
   return 0;
 }
 
-// Group size policy: spread the clips over as many co-resident clusters as the device offers (fewest rows per cluster =
-// least attention / beam work per step), in one wave when 16 rows per cluster allow it.  0 ok, 1 unsupported, < 0 error.
-int cluster_plan(const PersistentArgs& a, ClusterPlan* p) {
-  if (a.beam < 1 || a.beam > kCMaxBeam || a.max_len > kCMaxLen || a.tp > kCMaxTp || a.vpad <= 0 || a.tmaps == nullptr) return 1;
-  p->vs = a.vpad / kCl;
-  if (p->vs > 128 * kMaxClsTiles) return 1;
-  p->smem = cluster_smem(p->vs);
-  if (p->smem > 227 * 1024) return 1;
-  int mc = 0;
-  if (int rc = max_clusters_for(p->smem, &mc)) return rc;
-  if (mc <= 0) return 1;
-  const int gmax = kRm / a.beam;
-  int g = (a.batch + mc - 1) / mc;
-  if (g > gmax) g = gmax;
+// Group size policy.  Fewest rows per cluster = least attention / epilogue work per step, so a call that has the GPU to itself
+// spreads the clips over 16-row clusters (one wave when the device can hold them); 32-row clusters halve the number of SMs and
+// the L2 weight traffic and are chosen when the decode shares the GPU with the next batch's encoder (`compact`) or when 16-row
+// clusters would need more than one wave.  CNB_DEC_NR=16|32 overrides.  0 ok, 1 unsupported, < 0 error.
+int cluster_plan(const ClusterArgs& a, ClusterPlan* p) {
+  if (a.beam < 1 || a.beam > kCMaxBeam || a.max_len > kCMaxLen || a.tp > kCMaxTp || a.vocab <= 4 || a.vocab > 65535 ||
+      a.tmaps == nullptr)
+    return 1;
+  p->vs = (int)ceil_div(ceil_div(a.vocab, kCl), kClsRound) * kClsRound;
+  int mc16 = 0, mc32 = 0;
+  if (int rc = max_clusters_for<16>(&mc16)) return rc;
+  if (int rc = max_clusters_for<32>(&mc32)) return rc;
+  if (mc16 <= 0 && mc32 <= 0) return 1;
+  const char* env_nr = getenv("CNB_DEC_NR");
+  const int forced = env_nr ? atoi(env_nr) : 0;
+  const int need16 = (int)ceil_div(a.batch, 16 / a.beam);
+  int nr = (a.compact || need16 > mc16) ? 32 : 16;
+  if (forced == 16 || forced == 32) nr = forced;
+  if (nr == 32 && (mc32 <= 0 || a.batch * a.beam <= 16)) nr = 16;
+  if (nr == 16 && mc16 <= 0) nr = 32;
+  const int mc = nr == 16 ? mc16 : mc32;
+  const int gmax = nr / a.beam;
+  int g = (int)ceil_div(a.batch, mc);
+  if (g > gmax || a.compact) g = gmax;
+  p->nr = nr;
   p->clips_per_group = g;
-  p->n_groups = (a.batch + g - 1) / g;
+  p->n_groups = (int)ceil_div(a.batch, g);
   p->n_clusters = p->n_groups < mc ? p->n_groups : mc;
+  p->smem = nr == 16 ? cluster_smem<16>() : cluster_smem<32>();
   return 0;
 }
 
 }  // namespace
 
-bool decoder_cluster_supported(const PersistentArgs& a) {
+bool decoder_cluster_supported(const ClusterArgs& a) {
   ClusterPlan p;
   return cluster_plan(a, &p) == 0;
 }
 
-int launch_decoder_cluster(const PersistentArgs& a, cudaStream_t stream) {
+int decoder_cluster_sms(const ClusterArgs& a) {
+  ClusterPlan p;
+  return cluster_plan(a, &p) == 0 ? p.n_clusters * kCl : 0;
+}
+
+int launch_decoder_cluster(const ClusterArgs& a, cudaStream_t stream) {
   ClusterPlan p;
   const int prc = cluster_plan(a, &p);
   if (prc < 0) return prc;
-  CNB_REQUIRE(prc == 0, "decoder cluster mode: unsupported beam / max_len / vocabulary / T'");
+  CNB_REQUIRE(prc == 0, "decoder cluster mode: unsupported beam (<= 8) / max_len (<= 64) / T' (<= 128) / vocabulary (<= 65535)");
   if (getenv("CNB_DEC_TRACE"))
-    fprintf(stderr, "[dec cluster] batch %d beam %d -> %d clips/group, %d groups on %d clusters\n", a.batch, a.beam,
-            p.clips_per_group, p.n_groups, p.n_clusters);
+    fprintf(stderr, "[dec cluster] batch %d beam %d -> NR %d, %d clips/group, %d groups on %d clusters, vocabulary slice %d\n",
+            a.batch, a.beam, p.nr, p.clips_per_group, p.n_groups, p.n_clusters, p.vs);
   cudaLaunchConfig_t lc = {};
   lc.blockDim = dim3(kCThreads);
   lc.gridDim = dim3(p.n_clusters * kCl);
@@ -1029,7 +1165,8 @@ int launch_decoder_cluster(const PersistentArgs& a, cudaStream_t stream) {
   lc.attrs = la;
   lc.numAttrs = 1;
   CNB_CUDA_OK(cudaMemsetAsync(a.bs.done, 0, 4 * sizeof(int), stream));
-  CNB_CUDA_OK(cudaLaunchKernelEx(&lc, decoder_cluster_kernel, a, p.clips_per_group, p.n_groups, p.vs));
+  if (p.nr == 16) CNB_CUDA_OK(cudaLaunchKernelEx(&lc, decoder_cluster_kernel<16>, a, p.clips_per_group, p.n_groups, p.vs));
+  else CNB_CUDA_OK(cudaLaunchKernelEx(&lc, decoder_cluster_kernel<32>, a, p.clips_per_group, p.n_groups, p.vs));
   CNB_LAUNCH_OK();
   return 0;
 }

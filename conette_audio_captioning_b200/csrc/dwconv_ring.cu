@@ -300,7 +300,7 @@ dwconv_ln_tma_kernel(const __grid_constant__ CUtensorMap map_x, int H, int PQ, i
           const float2 t = __ffma2_rn(a, make_float2(rstd, rstd), make_float2(nmr, nmr));
           const float2 y = __ffma2_rn(t, gm, be);
           if constexpr (sizeof(OutT) == 2) {
-            *reinterpret_cast<__nv_bfloat162*>(o + (int64_t)p * CT) = __floats2bfloat162_rn(y.x, y.y);
+            *reinterpret_cast<act16x2*>(o + (int64_t)p * CT) = floats2act2(y.x, y.y);
           } else {
             *reinterpret_cast<float2*>(o + (int64_t)p * CT) = y;
           }
@@ -377,7 +377,7 @@ int launch_dwconv_ln_tma(const float* x, int batch, int h, int w, int c, const f
 }
 template int launch_dwconv_ln_tma<float>(const float*, int, int, int, int, const float*, const float*, const float*,
                                          const float*, float*, cudaStream_t);
-template int launch_dwconv_ln_tma<__nv_bfloat16>(const float*, int, int, int, int, const float*, const float*, const float*,
-                                                 const float*, __nv_bfloat16*, cudaStream_t);
+template int launch_dwconv_ln_tma<act16>(const float*, int, int, int, int, const float*, const float*, const float*,
+                                                 const float*, act16*, cudaStream_t);
 
 }  // namespace cnb

@@ -243,7 +243,7 @@ dwconv_ln_kernel(const float* __restrict__ x, int H, const float* __restrict__ w
       const float y0 = (acc[p].x - mean[p]) * rstd * g.x + be.x;
       const float y1 = (acc[p].y - mean[p]) * rstd * g.y + be.y;
       if constexpr (sizeof(OutT) == 2) {
-        *reinterpret_cast<__nv_bfloat162*>(o + (int64_t)p * C) = __floats2bfloat162_rn(y0, y1);
+        *reinterpret_cast<act16x2*>(o + (int64_t)p * C) = floats2act2(y0, y1);
       } else {
         *reinterpret_cast<float2*>(o + (int64_t)p * C) = make_float2(y0, y1);
       }
@@ -400,7 +400,7 @@ dwconv_ln_ring_kernel(const float* __restrict__ x, int H, int seg_rows, const fl
           const float y0 = (a.x - mean) * rstd * g.x + be.x;
           const float y1 = (a.y - mean) * rstd * g.y + be.y;
           if constexpr (sizeof(OutT) == 2) {
-            *reinterpret_cast<__nv_bfloat162*>(o + (int64_t)p * C) = __floats2bfloat162_rn(y0, y1);
+            *reinterpret_cast<act16x2*>(o + (int64_t)p * C) = floats2act2(y0, y1);
           } else {
             *reinterpret_cast<float2*>(o + (int64_t)p * C) = make_float2(y0, y1);
           }
@@ -466,8 +466,8 @@ int launch_dwconv_ln(const float* x, int batch, int h, int w, int c, const float
 }
 template int launch_dwconv_ln<float>(const float*, int, int, int, int, const float*, const float*, const float*,
                                      const float*, float*, cudaStream_t);
-template int launch_dwconv_ln<__nv_bfloat16>(const float*, int, int, int, int, const float*, const float*, const float*,
-                                             const float*, __nv_bfloat16*, cudaStream_t);
+template int launch_dwconv_ln<act16>(const float*, int, int, int, int, const float*, const float*, const float*,
+                                             const float*, act16*, cudaStream_t);
 
 // =====================================================================================================================
 // K-DS (part 1): LayerNorm(channels_first) per pixel + pack 2x2/stride-2 patches as GEMM rows.
@@ -542,7 +542,7 @@ ln_pack2x2_kernel(const float* __restrict__ x, int batch, int H, int W, const fl
         const float y2 = (v[u][i].z - mean) * rstd * g[i].z + be[i].z, y3 = (v[u][i].w - mean) * rstd * g[i].w + be[i].w;
         OutT* dst = o[u] + 4 * (lip + LPP * i);
         if constexpr (sizeof(OutT) == 2) {
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(y0, y1), p1 = __floats2bfloat162_rn(y2, y3);
+          act16x2 p0 = floats2act2(y0, y1), p1 = floats2act2(y2, y3);
           uint2 w2;
           w2.x = *reinterpret_cast<uint32_t*>(&p0);
           w2.y = *reinterpret_cast<uint32_t*>(&p1);
@@ -572,7 +572,7 @@ int launch_ln_pack2x2(const float* x, int batch, int h, int w, int c, const floa
   return 0;
 }
 template int launch_ln_pack2x2<float>(const float*, int, int, int, int, const float*, const float*, float*, cudaStream_t);
-template int launch_ln_pack2x2<__nv_bfloat16>(const float*, int, int, int, int, const float*, const float*, __nv_bfloat16*,
+template int launch_ln_pack2x2<act16>(const float*, int, int, int, int, const float*, const float*, act16*,
                                               cudaStream_t);
 
 // =====================================================================================================================

@@ -324,10 +324,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if constexpr (C::kElt == 2) {
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[i][8 * q + 0], v[i][8 * q + 1]);
-              __nv_bfloat162 p1 = __floats2bfloat162_rn(v[i][8 * q + 2], v[i][8 * q + 3]);
-              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[i][8 * q + 4], v[i][8 * q + 5]);
-              __nv_bfloat162 p3 = __floats2bfloat162_rn(v[i][8 * q + 6], v[i][8 * q + 7]);
+              act16x2 p0 = floats2act2(v[i][8 * q + 0], v[i][8 * q + 1]);
+              act16x2 p1 = floats2act2(v[i][8 * q + 2], v[i][8 * q + 3]);
+              act16x2 p2 = floats2act2(v[i][8 * q + 4], v[i][8 * q + 5]);
+              act16x2 p3 = floats2act2(v[i][8 * q + 6], v[i][8 * q + 7]);
               st_shared_v4(box_base + (uint32_t)(((chunk0 + q) ^ (row & 7)) << 4), *reinterpret_cast<uint32_t*>(&p0),
                            *reinterpret_cast<uint32_t*>(&p1), *reinterpret_cast<uint32_t*>(&p2),
                            *reinterpret_cast<uint32_t*>(&p3));
@@ -460,7 +460,7 @@ static int make_map_uncached(CUtensorMap* map, const void* ptr, uint64_t rows, u
   const cuuint64_t strides[1] = {cols * (uint64_t)elt_bytes};
   const cuuint32_t box[2] = {(cuuint32_t)(128 / elt_bytes), box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(map, elt_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+  CUresult r = g_encode(map, elt_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                         const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -478,7 +478,7 @@ int tc_make_map_bf16_box(void* map_out, const void* ptr, int64_t rows, int64_t c
   const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
   const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(reinterpret_cast<CUtensorMap*>(map_out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims,
+  CUresult r = g_encode(reinterpret_cast<CUtensorMap*>(map_out), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims,
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -509,7 +509,7 @@ int tc_make_map_nhwc_f32(void* map_out, const float* ptr, int batch, int h, int 
 }
 
 template <int BLOCK_N, int EPI, typename OutT, bool PAIR>
-static int launch_cfg(const __nv_bfloat16* a, const __nv_bfloat16* w, int m, int n, int k, const EpiParams& ep, OutT* out,
+static int launch_cfg(const act16* a, const act16* w, int m, int n, int k, const EpiParams& ep, OutT* out,
                       cudaStream_t stream) {
   using C = TcCfg<BLOCK_N, EPI, OutT, PAIR>;
   CUtensorMap map_a, map_w, map_out, map_resid;
@@ -562,7 +562,7 @@ static int pair_min_rows() {
 }
 
 template <int EPI, typename OutT>
-static int launch_n(const __nv_bfloat16* a, const __nv_bfloat16* w, int m, int n, int k, const EpiParams& ep, OutT* out,
+static int launch_n(const act16* a, const act16* w, int m, int n, int k, const EpiParams& ep, OutT* out,
                     cudaStream_t stream) {
   // measured (64 x 10 s clips, pair vs 1-CTA): pw2 stages 3-4 -18 % / -22 %, pw1 stage 3 -9 %, stage 4 -12 %, downsample -9 %,
   // stage 2 equal (HBM-bound).  (With a .release.cluster accumulator hand-back the short-K shapes were 26-39 % SLOWER: the
@@ -585,7 +585,7 @@ static int launch_n(const __nv_bfloat16* a, const __nv_bfloat16* w, int m, int n
 }
 
 template <typename OutT>
-int launch_gemm_tc(const __nv_bfloat16* a, const __nv_bfloat16* w, int m, int n, int k, Epilogue epi, const EpiParams& ep,
+int launch_gemm_tc(const act16* a, const act16* w, int m, int n, int k, Epilogue epi, const EpiParams& ep,
                    OutT* out, int64_t ldo, cudaStream_t stream) {
   CNB_REQUIRE(g_encode != nullptr, "gemm_tc_init() was not called");
   CNB_REQUIRE(k % 8 == 0, "gemm_tc needs K to be a multiple of 8 (16-byte TMA row stride)");
@@ -610,9 +610,9 @@ int launch_gemm_tc(const __nv_bfloat16* a, const __nv_bfloat16* w, int m, int n,
   set_error("gemm_tc: unsupported epilogue / output type combination");
   return -1;
 }
-template int launch_gemm_tc<float>(const __nv_bfloat16*, const __nv_bfloat16*, int, int, int, Epilogue, const EpiParams&,
+template int launch_gemm_tc<float>(const act16*, const act16*, int, int, int, Epilogue, const EpiParams&,
                                    float*, int64_t, cudaStream_t);
-template int launch_gemm_tc<__nv_bfloat16>(const __nv_bfloat16*, const __nv_bfloat16*, int, int, int, Epilogue,
-                                           const EpiParams&, __nv_bfloat16*, int64_t, cudaStream_t);
+template int launch_gemm_tc<act16>(const act16*, const act16*, int, int, int, Epilogue,
+                                           const EpiParams&, act16*, int64_t, cudaStream_t);
 
 }  // namespace cnb

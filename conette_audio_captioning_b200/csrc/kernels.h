@@ -1,8 +1,9 @@
 // Internal launcher declarations shared by the translation units of libconette_b200.so.
 #pragma once
 #include <cuda_runtime.h>
-#include <cuda_bf16.h>
 #include <stdint.h>
+
+#include "common.cuh"
 
 namespace cnb {
 
@@ -76,10 +77,10 @@ int launch_gemm_f32_panel(const float* a, int64_t lda, const float* w, int m, in
 // bf16 tcgen05 GEMM (fast mode).  A (M,K) bf16 contiguous, W (N,K) bf16 contiguous (both K-major, TMA-fed).
 struct TcGemmPlan;  // opaque: TMA descriptors + tile configuration
 template <typename OutT>
-int launch_gemm_tc(const __nv_bfloat16* a, const __nv_bfloat16* w, int m, int n, int k, Epilogue epi, const EpiParams& ep,
+int launch_gemm_tc(const act16* a, const act16* w, int m, int n, int k, Epilogue epi, const EpiParams& ep,
                    OutT* out, int64_t ldo, cudaStream_t stream);
 // fused pointwise MLP of ConvNeXt stage 1 (mlp_fused.cu): x (M, 96) f32 += scale * (W2 . GELU(W1 . y + b1) + b2), in place
-int launch_mlp_fused_c96(const __nv_bfloat16* y, const __nv_bfloat16* w1, const __nv_bfloat16* w2, const float* b1, const float* b2,
+int launch_mlp_fused_c96(const act16* y, const act16* w1, const act16* w2, const float* b1, const float* b2,
                          const float* scale, float* x, int m, cudaStream_t stream);
 int gemm_tc_init();  // resolves cuTensorMapEncodeTiled; returns 0 on success
 // 2-D row-major (rows, cols) tensor map into map_out (a 128-byte CUtensorMap): box = (box_rows, 128 bytes), 128B swizzle
@@ -130,39 +131,33 @@ int launch_beam_step(float* logits, const uint8_t* forbid, BeamState st, int ste
 int launch_beam_finalize(BeamState st, int64_t* best_preds, float* best_lp, int* best_len, const DecoderDims& dd,
                          cudaStream_t stream);
 
-// ---- persistent decoder: the whole decode loop in one cooperative launch (decoder_persistent.cu) ----------------------
-struct PLayer {
-  const float *sa_in_w, *sa_in_b, *sa_out_w, *sa_out_b, *ca_q_w, *ca_q_b, *ca_out_w, *ca_out_b;
-  const float *l1_w, *l1_b, *l2_w, *l2_b, *n1_g, *n1_b, *n2_g, *n2_b, *n3_g, *n3_b;
-  // k4-packed copies for the cluster decoder: Wp[(k/4) * N + n][4] = W[n][4*(k/4) .. +3]
-  const float *sa_in_p, *sa_out_p, *ca_q_p, *ca_out_p, *l1_p, *l2_p;
+// ---- cluster decoder: the whole beam-search decode in ONE launch (decoder_cluster.cu) -------------------------------------
+// Decoder weights as the tensor cores take them there: every nn.Linear matrix W is split into two fp16 matrices
+// W1 = fp16(W), W2 = fp16((W - W1) * 2048) (22 significand bits together), each behind its own TMA descriptor.
+constexpr int kDecMapsPerLayer = 12;  // {sa_in, sa_out (head-packed), ca_q, ca_out (head-packed), l1, l2} x {W1, W2}
+constexpr int kDecMaps = 6 * kDecMapsPerLayer + 2;  // + classifier {W1, W2}
+struct ClusterLayer {
+  const float *sa_in_b, *sa_out_b, *ca_q_b, *ca_out_b, *l1_b, *l2_b, *n1_g, *n1_b, *n2_g, *n2_b, *n3_g, *n3_b;
 };
-struct PersistentArgs {
-  PLayer layers[6];
-  const float *emb, *pe, *cls_w, *cls_b;
-  const float* cls_p;        // k4-packed classifier, vpad columns (zero beyond the vocabulary)
-  int vpad;
-  const void* tmaps;         // 37 CUtensorMaps (device): layer l -> [6l + {sa_in, sa_out, ca_q, ca_out, l1, l2}], 36 = classifier
+struct ClusterArgs {
+  ClusterLayer layers[6];
+  const float *emb, *pe, *cls_b;
+  const void* tmaps;         // kDecMaps CUtensorMaps (device): layer l -> [12 l + 2 j + half], classifier at 72 + half
   const float* ckv;          // (B*T', 6*512) cross-attention K|V of all layers
   const int* lens;
   const int64_t* bos_ids;
   const uint8_t* forbid;
-  float *xa, *xb, *qkv, *attn, *tmp, *ff, *part, *logits, *kc, *vc;
-  BeamState bs;
-  unsigned int* bar;         // 2 words, zeroed by the launcher
-  unsigned long long* trace; // optional (debug): 3 words per barrier, written by block 0
+  float *kc, *vc;            // self-attention caches (6, rows, max_len, 256)
+  BeamState bs;              // out_preds / out_lp / done are used
+  float* tap;                // optional (tests): raw logits of every step, (max_len, rows, vocab)
+  unsigned long long* trace; // optional (debug): phase times of the first CTA
   int rows, beam, tp, max_len, vocab, min_len, batch;
+  int compact;               // 1 = prefer few, fat clusters (32 rows each): the decode shares the GPU with the next encoder
 };
-int launch_decoder_persistent(const PersistentArgs& args, cudaStream_t stream);
-// the same phases as separate launches (graph-replayed "fused" mode)
-void decoder_set_pdl(bool on);  // programmatic dependent launch between the fused phase kernels (default on)
-int launch_decoder_init(const PersistentArgs& args, cudaStream_t stream);
-int launch_decoder_step_fused(const PersistentArgs& args, int step, int cur, float** x_cur_io, float** x_alt_io,
-                              cudaStream_t stream);
-
-// cluster-resident decode (decoder_cluster.cu): one launch, a cluster of 8 CTAs per group of 12/beam clips
-bool decoder_cluster_supported(const PersistentArgs& args);
-int launch_decoder_cluster(const PersistentArgs& args, cudaStream_t stream);
+bool decoder_cluster_supported(const ClusterArgs& args);
+int launch_decoder_cluster(const ClusterArgs& args, cudaStream_t stream);
+// SMs the launch for `args` will occupy (8 per cluster); 0 when unsupported
+int decoder_cluster_sms(const ClusterArgs& args);
 
 // global launch counter (reported through cnb_launch_count)
 void count_launch();

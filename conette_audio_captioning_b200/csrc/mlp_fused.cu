@@ -315,7 +315,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_y0, const __grid_consta
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float2 g = gelu_tanh_fit2(__fadd2_rn(v2[i], sb2[i]));
-        __nv_bfloat162 p = __floats2bfloat162_rn(g.x, g.y);   // k = 2 i in the low half, 2 i + 1 in the high half
+        act16x2 p = floats2act2(g.x, g.y);   // k = 2 i in the low half, 2 i + 1 in the high half
         h[i] = *reinterpret_cast<uint32_t*>(&p);
       }
       tmem_st_32x16(taddr, h);   // over the first 16 of the 32 columns this thread has just read
@@ -376,7 +376,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_y0, const __grid_consta
 }  // namespace
 
 // y (M, 96) bf16, w1 (384, 96) bf16, w2 (96, 384) bf16, x (M, 96) fp32 updated in place
-int launch_mlp_fused_c96(const __nv_bfloat16* y, const __nv_bfloat16* w1, const __nv_bfloat16* w2, const float* b1, const float* b2,
+int launch_mlp_fused_c96(const act16* y, const act16* w1, const act16* w2, const float* b1, const float* b2,
                          const float* scale, float* x, int m, cudaStream_t stream) {
   if (m == 0) return 0;
   CUtensorMap map_y0, map_y1, map_w1a, map_w1b, map_w2, map_x;

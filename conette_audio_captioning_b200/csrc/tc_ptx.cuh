@@ -162,9 +162,10 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
   d |= (uint64_t)4 << 61;
   return d;
 }
-// instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+// instruction descriptor: D=f32 (bit 4), A=B=fp16 (format 0 at [7,10) and [10,13); bf16 would be 1), both K-major, N>>3 at
+// [17,23), M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // tf32 variant: operands are fp32 words in shared memory, the tensor core uses their top 19 bits (8 k per instruction)

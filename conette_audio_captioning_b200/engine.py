@@ -26,7 +26,7 @@ def _ptr(t: Optional[Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
-DECODER_MODES = {"auto": 0, "graph": 1, "graph_pdl": 2, "graph_unfused": 3, "eager": 4, "persistent": 5, "cluster": 6}
+DECODER_MODES = {"auto": 0, "graph": 1, "eager": 2, "cluster": 3}
 
 
 class Engine:
@@ -44,12 +44,10 @@ class Engine:
         cfg.vocab_size = self.vocab_size
         cfg.precision = {"fast": _lib.PRECISION_FAST, "parity": _lib.PRECISION_PARITY}[precision]
         cfg.enc_chunk = enc_chunk
-        # decoder execution mode: "auto" = "cluster" when the shape allows it (beam <= 8, max_len <= 64, vocabulary slice fits in
-        # shared memory), else "graph".  "cluster" = one launch, a cluster of 8 CTAs decodes a group of 12/beam clips start to
-        # finish (DSMEM exchanges + hardware cluster barriers); "graph" = CUDA-graph replay of the fused phase kernels;
-        # "graph_pdl" = same with programmatic dependent launch; "graph_unfused" = per-op kernels; "persistent" = one
-        # cooperative kernel with software grid barriers; "eager" = plain launches.  The five non-cluster modes are
-        # bit-identical; "cluster" differs by fp32 summation order only.
+        # decoder implementation: "auto" = "cluster" in precision "fast" when the shape allows it (beam <= 8, max_len <= 64,
+        # T' <= 128, V <= 65535), else "graph".  "cluster" = one launch, a cluster of 8 CTAs decodes a group of 16/beam or
+        # 32/beam clips start to finish on the tensor cores (fp16 hi/lo split operands: fp32-level accuracy); "graph" = CUDA-graph
+        # replay of the fp32 CUDA-core step kernels (the decoder of precision "parity"); "eager" = the same launches without a graph.
         cfg.reserved[0] = DECODER_MODES[decoder]
         handle = C.c_void_p()
         _lib.check(self.lib.cnb_create(C.byref(cfg), C.byref(handle)))
@@ -213,6 +211,21 @@ class Engine:
         _lib.check(self.lib.cnb_decode(self.handle, fe.data_ptr(), lens.data_ptr(), bos.data_ptr(), _ptr(forbid), b, tp, beam,
                                        min_len, max_len, *[o.data_ptr() for o in outs], self._stream()))
         return self._trim(*outs) if trim else tuple(outs)
+
+    def decode_tap(self, frame_embs: Tensor, lens: Tensor, bos_ids: Tensor, forbid_mask: Optional[Tensor], beam: int = 3,
+                   min_len: int = 3, max_len: int = 20):
+        """``decode(trim=False)`` through the cluster kernel plus its per-step raw logits (max_len, B*beam, V); steps after the
+        early exit hold NaN.  Test hook for the reference seam ``AACDecoder.__call__`` (nn/decoding/common.py:9-29)."""
+        fe = self._dev(frame_embs, torch.float32)
+        b, tp, _ = fe.shape
+        lens = self._dev(lens, torch.int32)
+        bos = self._dev(bos_ids, torch.int64)
+        forbid = None if forbid_mask is None else self._dev(forbid_mask, torch.uint8)
+        outs = self._alloc_outputs(b, beam, max_len)
+        logits = torch.full((max_len, b * beam, self.vocab_size), float("nan"), device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.cnb_decode_tap(self.handle, fe.data_ptr(), lens.data_ptr(), bos.data_ptr(), _ptr(forbid), b, tp, beam,
+                                           min_len, max_len, *[o.data_ptr() for o in outs], logits.data_ptr(), self._stream()))
+        return (*outs, logits)
 
     def decoder_logits(self, frame_embs: Tensor, lens: Tensor, tokens: Tensor) -> Tensor:
         """Teacher-forced logits (B, steps, V) for given token prefixes (B, steps)."""

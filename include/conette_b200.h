@@ -36,10 +36,14 @@ typedef struct cnb_config {
   int32_t abi_version;   /* must be CNB_ABI_VERSION */
   int32_t device;        /* CUDA device ordinal */
   int32_t vocab_size;    /* V: rows of decoder.emb_layer.weight / decoder.classifier.weight */
-  int32_t precision;     /* 0 = fast (bf16 tcgen05 encoder GEMMs, fp32 accumulate, fp32 residual stream)
-                            1 = parity (fp32 CUDA-core GEMMs everywhere); the decoder is fp32 in both modes */
+  int32_t precision;     /* 0 = fast: fp16-operand tcgen05 encoder GEMMs (fp32 accumulate, fp32 residual stream, tanh-fit GELU)
+                                and the one-launch cluster decoder, whose tensor-core GEMMs run on fp16 hi/lo split
+                                operands (22 significand bits, fp32 accumulate: logits within ~2e-5 of fp32)
+                            1 = parity: fp32 CUDA-core GEMMs everywhere (encoder and the CUDA-graph decoder) */
   int32_t enc_chunk;     /* clips encoded per pass (0 = library default); bounds workspace, keeps tiles in L2 */
-  int32_t reserved[3];
+  int32_t reserved[3];   /* [0] = decoder implementation: 0 default (cluster kernel in precision "fast" when the shape
+                            fits: beam <= 8, max_len <= 64, T' <= 128, V <= 65535; else the fp32 graph), 1 fp32 CUDA graph,
+                            2 fp32 eager launches, 3 cluster kernel or error */
 } cnb_config;
 
 enum { CNB_PRECISION_FAST = 0, CNB_PRECISION_PARITY = 1 };
@@ -58,7 +62,7 @@ int cnb_destroy(cnb_handle* h);
  * does not consume (tokenizer state, task ids, forbid mask, num_batches_tracked) are accepted and ignored. */
 int cnb_load_weight(cnb_handle* h, const char* name, const void* host_ptr, int32_t dtype, int32_t ndim,
                     const int64_t* shape);
-/* Validate that every required tensor was staged, pack (transpose / bf16 / BN fold / sparse mel) and upload. */
+/* Validate that every required tensor was staged, pack (transpose / fp16 copies / fp16 hi-lo split of the decoder / BN fold / sparse mel) and upload. */
 int cnb_finalize_weights(cnb_handle* h);
 
 /* Output geometry for a padded batch of n_samples: STFT frames T, ConvNeXt stage heights, output frames T'. */
@@ -96,7 +100,15 @@ int cnb_decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, cons
                const uint8_t* forbid_mask, int32_t batch, int32_t n_frames, int32_t beam, int32_t min_len, int32_t max_len,
                int64_t* preds_out, float* lprobs_out, int64_t* mult_preds_out, float* mult_lprobs_out, int32_t* info_out,
                void* stream);
-/* S3 (parity only): teacher-forced decoder logits. tokens (B, steps) i64 -> logits (B, steps, V) f32. */
+/* cnb_decode through the cluster kernel (error if the shape does not fit it) with the kernel's per-step logits tapped:
+ * logits_out (max_len, B*beam, V) f32 = what the reference's decoder call returns for the last position at every step
+ * (AACDecoder.__call__, src/conette/nn/decoding/common.py:9-29; beam.py:113-127), before the EOS / no-repeat masks.  Rows are
+ * the fixed beam slots (clip * beam + label); steps after the early exit are left untouched.  Test hook. */
+int cnb_decode_tap(cnb_handle* h, const float* frame_embs, const int32_t* lens, const int64_t* bos_ids,
+                   const uint8_t* forbid_mask, int32_t batch, int32_t n_frames, int32_t beam, int32_t min_len, int32_t max_len,
+                   int64_t* preds_out, float* lprobs_out, int64_t* mult_preds_out, float* mult_lprobs_out, int32_t* info_out,
+                   float* logits_out, void* stream);
+/* S3 (fp32 step kernels): teacher-forced decoder logits. tokens (B, steps) i64 -> logits (B, steps, V) f32. */
 int cnb_decoder_logits(cnb_handle* h, const float* frame_embs, const int32_t* lens, const int64_t* tokens, int32_t batch,
                        int32_t n_frames, int32_t steps, float* logits_out, void* stream);
 /* Teacher-forced scoring of given captions: replaces the loss loop of CoNeTTEPLM.test_step /
@@ -137,14 +149,14 @@ int cnb_caption_host_begin(cnb_handle* h, const float* wav_host, const int64_t* 
 int cnb_caption_host_end(cnb_handle* h, int32_t ticket);
 
 /* Test hook: one GEMM with a fused epilogue, out (M,N) f32 = epi(A (M,K) f32 x W (N,K) f32 ^T). epi: 0 bias, 1 bias+GELU,
- * 2 bias+ReLU, 3 resid + scale*(acc+bias).  use_tc=1 runs the bf16 tcgen05 kernel (operands rounded to bf16 first;
- * out_bf16=1 also rounds the result through the bf16 epilogue), use_tc=0 the fp32 CUDA-core kernel. */
+ * 2 bias+ReLU, 3 resid + scale*(acc+bias).  use_tc=1 runs the fp16-operand tcgen05 kernel (operands rounded to fp16 first;
+ * out_bf16=1 also rounds the result through the 16-bit (fp16) epilogue), use_tc=0 the fp32 CUDA-core kernel. */
 int cnb_debug_gemm(cnb_handle* h, const float* a, const float* w, const float* bias, const float* scale, const float* resid,
                    int32_t m, int32_t n, int32_t k, int32_t epi, int32_t use_tc, int32_t out_bf16, float* out, void* stream);
 
 /* Test hook: the fused pointwise MLP of a ConvNeXt stage-1 block (reference convnext.py:66-73, C = 96):
  * x (M,96) f32 += scale * (W2 (96,384) . GELU(W1 (384,96) . y (M,96) + b1) + b2), in place, through the kernel the fast
- * precision mode uses (y, W1, W2 and the hidden activations are rounded to bf16, fp32 accumulation and residual). */
+ * precision mode uses (y, W1, W2 and the hidden activations are rounded to fp16, fp32 accumulation and residual). */
 int cnb_debug_mlp_fused(cnb_handle* h, const float* y, const float* w1, const float* b1, const float* w2, const float* b2,
                         const float* scale, float* x, int32_t m, void* stream);
 

@@ -3,7 +3,7 @@
 Tolerances (restated where asserted):
   log-mel                       <= 1e-2 dB abs where the mel power is well above amin
   parity mode (fp32 GEMMs)      activations <= 2e-4 rel-L2 per stage, frame_embs <= 5e-4 rel-L2
-  fast mode (bf16 tcgen05)      frame_embs <= 5e-3 rel-L2
+  fast mode (fp16-operand tcgen05, fp32 accumulate)  frame_embs <= 1.5e-3 rel-L2
   decoder logits                <= 1e-4 abs (+1e-4 rel) given identical frame_embs
   token ids                     bit-exact (decoder fed the oracle's frame_embs; end-to-end in parity mode)
 """
@@ -64,9 +64,9 @@ GEMM_SHAPES = [(300, 384, 96), (128, 96, 384), (1000, 768, 192), (257, 192, 768)
                (700, 384, 1536), (640, 768, 3072), (1300, 3072, 768), (20000, 384, 768)]
 
 
-def _gemm_ref(a, w, bias, scale, resid, epi, bf16_in):
-    if bf16_in:
-        a, w = a.bfloat16().float(), w.bfloat16().float()
+def _gemm_ref(a, w, bias, scale, resid, epi, f16_in):
+    if f16_in:  # the fast path rounds both GEMM operands to IEEE fp16 (fp32 accumulation)
+        a, w = a.half().float(), w.half().float()
     acc = a.double() @ w.double().T + bias.double()
     if epi == 1:
         acc = torch.nn.functional.gelu(acc)
@@ -87,19 +87,19 @@ def test_tcgen05_gemm(eng_fast, m, n, k, epi):
     w = torch.randn(n, k, generator=g) / k**0.5
     bias, scale, resid = torch.randn(n, generator=g), torch.rand(n, generator=g), torch.randn(m, n, generator=g)
     out = eng_fast.debug_gemm(a, w, bias, scale, resid, epi=epi, use_tc=True).cpu()
-    ref = _gemm_ref(a, w, bias, scale, resid, epi, bf16_in=True)
-    torch.testing.assert_close(out, ref, rtol=2e-4, atol=2e-4)  # same bf16 operands, fp32 accumulation
+    ref = _gemm_ref(a, w, bias, scale, resid, epi, f16_in=True)
+    torch.testing.assert_close(out, ref, rtol=2e-4, atol=2e-4)  # same fp16 operands, fp32 accumulation
 
 
 @pytest.mark.parametrize("m,n,k", [(300, 384, 96), (257, 192, 768),
                                    (1100, 768, 384), (600, 384, 768), (2000, 1536, 192)])  # CTA pairs: 256- / 192-column tiles
-def test_tcgen05_gemm_bf16_out(eng_fast, m, n, k):
+def test_tcgen05_gemm_f16_out(eng_fast, m, n, k):
     g = torch.Generator().manual_seed(5)
     a, w, bias = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g) / k**0.5, torch.randn(n, generator=g)
     out = eng_fast.debug_gemm(a, w, bias, epi=1, use_tc=True, out_bf16=True).cpu()
-    ref = _gemm_ref(a, w, bias, None, None, 1, bf16_in=True)
-    torch.testing.assert_close(out, ref.bfloat16().float(), rtol=1e-2, atol=1e-2)
-    assert rel_l2(out, ref) < 4e-3
+    ref = _gemm_ref(a, w, bias, None, None, 1, f16_in=True)
+    torch.testing.assert_close(out, ref.half().float(), rtol=2e-3, atol=2e-3)  # tanh-fit GELU (2.5e-5) + fp16 rounding
+    assert rel_l2(out, ref) < 6e-4
 
 
 @pytest.mark.parametrize("m,n,k", [(300, 384, 96), (37, 318, 256), (192, 256, 2048), (1000, 192, 768), (5, 768, 256)])
@@ -110,7 +110,7 @@ def test_fp32_gemm(eng_parity, m, n, k, epi):
     w = torch.randn(n, k, generator=g) / k**0.5
     bias, scale, resid = torch.randn(n, generator=g), torch.rand(n, generator=g), torch.randn(m, n, generator=g)
     out = eng_parity.debug_gemm(a, w, bias, scale, resid, epi=epi, use_tc=False).cpu()
-    ref = _gemm_ref(a, w, bias, scale, resid, epi, bf16_in=False)
+    ref = _gemm_ref(a, w, bias, scale, resid, epi, f16_in=False)
     torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-4)
 
 
@@ -231,8 +231,8 @@ def test_encoder_outputs_fast(eng_fast, oracle_taps):
 @pytest.mark.parametrize("m", [1, 77, 128, 129, 148 * 128, 148 * 128 * 3 + 77])
 def test_fused_mlp_kernel(eng_fast, m):
     """The fused stage-1 MLP kernel (hidden tile in tensor memory) against a plain fp32 torch evaluation of
-    convnext.py:66-73 on the same bf16-rounded operands.  Row counts cover a partial tile, exact tiles, one tile per CTA
-    and the multi-tile pipeline with a ragged tail.  Tolerance: 2e-3 rel-L2 on the update (bf16 hidden + tanh-fit GELU)."""
+    convnext.py:66-73 on the same fp16-rounded operands.  Row counts cover a partial tile, exact tiles, one tile per CTA
+    and the multi-tile pipeline with a ragged tail.  Tolerance: 5e-4 rel-L2 on the update (fp16 hidden + tanh-fit GELU)."""
     g = torch.Generator().manual_seed(m)
     dev = "cuda"
     y = torch.randn(m, 96, generator=g).to(dev)
@@ -243,12 +243,13 @@ def test_fused_mlp_kernel(eng_fast, m):
     b2 = (0.3 * torch.randn(96, generator=g)).to(dev)
     scale = (0.5 + torch.rand(96, generator=g)).to(dev)
     got = eng_fast.debug_mlp_fused(y, w1, b1, w2, b2, scale, x)
-    bf = lambda v: v.to(torch.bfloat16).to(torch.float32)
+    bf = lambda v: v.to(torch.float16).to(torch.float32)
     hid = bf(torch.nn.functional.gelu(bf(y) @ bf(w1).T + b1))
     want = x + scale * (hid @ bf(w2).T + b2)
     upd_err = float(((got - x) - (want - x)).norm() / (want - x).norm())
-    assert upd_err < 2e-3, upd_err
-    assert float((got - want).abs().max()) < 3e-2
+    print(f"fused MLP m={m}: update rel-L2 {upd_err:.2e}")
+    assert upd_err < 1e-3, upd_err
+    assert float((got - want).abs().max()) < 5e-3
     # rows are independent: the last row of a ragged batch equals the same row computed alone
     if m > 1:
         one = eng_fast.debug_mlp_fused(y[-1:], w1, b1, w2, b2, scale, x[-1:])
@@ -400,8 +401,8 @@ def test_beam_search_vs_oracle(small_sd, beam, min_len, max_len, mode, eos_bias)
             torch.testing.assert_close(m[firm], r[firm], rtol=1e-4, atol=1e-4)
 
 
-def test_decoder_execution_modes_agree_bitwise(small_sd):
-    """persistent cooperative kernel == CUDA-graph replay == eager per-op kernels (same arithmetic, same order)."""
+def test_decoder_graph_and_eager_agree_bitwise(small_sd):
+    """fp32 step kernels: CUDA-graph replay == eager launches (same arithmetic, same order), and replays are deterministic."""
     from conette_audio_captioning_b200.engine import Engine
 
     g = torch.Generator().manual_seed(11)
@@ -411,7 +412,7 @@ def test_decoder_execution_modes_agree_bitwise(small_sd):
     bos_ids = small_sd["model.task_id_to_token_id"][torch.randint(0, 7, (b,), generator=g)]
     forbid = small_sd["model.forbid_rep_mask"]
     outs = {}
-    for mode in ("persistent", "graph", "graph_pdl", "graph_unfused", "eager"):
+    for mode in ("graph", "eager"):
         eng = Engine(small_sd, vocab_size=forbid.shape[0], precision="parity", decoder=mode)
         try:
             outs[mode] = [o.cpu() for o in eng.decode(fe, lens, bos_ids, forbid, 3, 3, 20)]
@@ -419,43 +420,56 @@ def test_decoder_execution_modes_agree_bitwise(small_sd):
             assert all(torch.equal(a, c) for a, c in zip(outs[mode], again)), mode
         finally:
             eng.close()
-    for mode in ("graph", "graph_pdl", "graph_unfused", "eager"):
-        for a, c in zip(outs["persistent"], outs[mode]):
-            assert torch.equal(a, c), mode
+    for a, c in zip(outs["graph"], outs["eager"]):
+        assert torch.equal(a, c)
 
 
-@pytest.mark.parametrize("b,beam,max_len", [(37, 3, 20), (5, 1, 12), (9, 2, 20), (7, 5, 16), (3, 8, 24), (64, 3, 20), (130, 3, 20)])
-def test_decoder_cluster_mode_matches_graph_mode(small_sd, b, beam, max_len):
-    """One-launch cluster decode (tf32 tcgen05 GEMMs, DSMEM exchanges) vs the bit-exact-tested fp32 graph mode.  tf32 operand
-    truncation (2^-11 relative) moves scores by ~1e-3, so: most clips keep identical beams, their scores agree to 5e-3, and a
-    clip whose beams differ must be explained by close scores (its best-beam score still agrees to 0.1)."""
+CLUSTER_EPS = 1e-3
+
+
+@pytest.mark.parametrize("b,beam,max_len,tp", [(37, 3, 20, 31), (5, 1, 12, 31), (9, 2, 20, 31), (7, 5, 16, 31), (3, 8, 24, 31),
+                                               (64, 3, 20, 31), (130, 3, 20, 31), (6, 3, 20, 94), (1, 3, 20, 31), (11, 4, 64, 40)])
+@pytest.mark.parametrize("nr", ["16", "32"])
+def test_decoder_cluster_vs_oracle(small_sd, monkeypatch, b, beam, max_len, tp, nr):
+    """One-launch cluster decode (fp16 hi/lo split tcgen05 GEMMs, DSMEM reduce-scatter / all-gather exchanges) against the CPU
+    oracle's beam search, for both cluster widths (16 / 32 rows, CNB_DEC_NR) and ragged group sizes: ids bit-exact on every clip
+    whose oracle selection margin is >= 1e-3, scores within 2e-4 (x length) there, per-step logits <= 1e-4, deterministic."""
     from conette_audio_captioning_b200.engine import Engine
+    from oracle import parity, restate
 
+    monkeypatch.setenv("CNB_DEC_NR", nr)
     g = torch.Generator().manual_seed(100 + b)
-    tp = 31
     fe = torch.randn(b, tp, 768, generator=g)
     lens = torch.randint(1, tp + 1, (b,), generator=g)
     bos_ids = small_sd["model.task_id_to_token_id"][torch.randint(0, 7, (b,), generator=g)]
     forbid = small_sd["model.forbid_rep_mask"]
-    outs = {}
-    for mode in ("graph", "cluster"):
-        eng = Engine(small_sd, vocab_size=forbid.shape[0], precision="parity", decoder=mode)
-        try:
-            outs[mode] = [o.cpu() for o in eng.decode(fe, lens, bos_ids, forbid, beam, 3, max_len, trim=False)]
-            again = [o.cpu() for o in eng.decode(fe, lens, bos_ids, forbid, beam, 3, max_len, trim=False)]
-            assert all(torch.equal(a, c) for a, c in zip(outs[mode], again)), mode  # deterministic
-        finally:
-            eng.close()
-    gp, gl, gmp, gml = outs["graph"][:4]
-    cp, cl, cmp_, cml = outs["cluster"][:4]
-    assert gp.shape == cp.shape and gmp.shape == cmp_.shape
-    same_clip = (gmp == cmp_).flatten(1).all(1)
-    print(f"cluster vs graph: identical beams for {int(same_clip.sum())}/{b} clips")
-    assert same_clip.float().mean() >= 0.7, f"only {int(same_clip.sum())}/{b} clips have identical beams"
-    torch.testing.assert_close(cml[same_clip], gml[same_clip], rtol=0, atol=5e-3)
-    torch.testing.assert_close(cl[same_clip], gl[same_clip], rtol=0, atol=5e-3)
-    assert torch.equal(gp[same_clip], cp[same_clip])
-    torch.testing.assert_close(cl, gl, rtol=0, atol=0.1)  # best-beam score of every clip, flipped near-ties included
+    trace = []
+    ref = restate.beam_search(small_sd, restate.project(small_sd, fe), lens, bos_ids, beam, 3, max_len, forbid, trace=trace)
+    margin = torch.full((b,), float("inf"))
+    for tr in trace:
+        for j, mg in tr.get("margin", {}).items():
+            margin[j] = min(float(margin[j]), mg)
+    eng = Engine(small_sd, vocab_size=forbid.shape[0], precision="fast", decoder="cluster")
+    try:
+        out = [o.cpu() for o in eng.decode_tap(fe, lens, bos_ids, forbid, beam, 3, max_len)]
+        again = [o.cpu() for o in eng.decode(fe, lens, bos_ids, forbid, beam, 3, max_len, trim=False)]
+        trimmed = [o.cpu() for o in eng.decode(fe, lens, bos_ids, forbid, beam, 3, max_len)]
+    finally:
+        eng.close()
+    assert all(torch.equal(a, c) for a, c in zip(out[:4], again[:4]))  # deterministic, tap or no tap
+    rec = parity.compare(out[2], out[3], {"mult_preds": ref[2], "mult_lprobs": ref[3], "margin": margin}, CLUSTER_EPS)
+    lg0 = out[5][0][::beam]
+    rec["max_logit_err_step0"] = float((lg0 - trace[0]["logits"][::beam]).abs().max())
+    print(f"[parity] cluster NR={nr} b={b} beam={beam}: {rec}")
+    assert rec["max_logit_err_step0"] < 1e-4, rec
+    assert rec["mismatched_firm_clips"] == [], rec
+    assert rec["max_score_err"] is None or 2 * rec["max_score_err"] <= CLUSTER_EPS, rec
+    assert rec["identical"] >= (2 * b) // 3, rec
+    # output shapes / trim rules of beam.py:205-225 on the firm clips
+    firm = margin >= CLUSTER_EPS
+    assert trimmed[2].shape == ref[2].shape and trimmed[0].shape[0] == b
+    if bool(firm.all()):
+        assert trimmed[0].shape == ref[0].shape and torch.equal(trimmed[0], ref[0])
 
 
 # ----------------------------------------------------------------------------------------------------------------------
