@@ -740,6 +740,19 @@ static int dec_step(cnb_handle* h, const DecWs& w, const int* tokens, const int*
   return launch_gemm_f32_panel(w.x, kD, h->cls_w, R, dd.vocab, kD, EPI_BIAS, e, w.logits, dd.vocab, st);
 }
 
+// cross-attention keys of every clip regrouped for the cluster decoder: ckt[clip][layer][head][dim][tpad] = ckv[clip, t][layer, 0:256]
+// (frames contiguous per (head, dim): lane = frame reads coalesced words), zero beyond T'
+__global__ void cross_k_transpose_kernel(const float* __restrict__ ckv, float* __restrict__ ckt, int batch, int tp, int tpad) {
+  const int64_t total = (int64_t)batch * kLayers * kD * tpad;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(i % tpad);
+    const int64_t r = i / tpad;          // (clip * 6 + layer) * 256 + head * 32 + dim
+    const int c = (int)(r % kD), l = (int)((r / kD) % kLayers);
+    const int64_t clip = r / (kD * kLayers);
+    ckt[i] = t < tp ? ckv[(clip * tp + t) * (kLayers * 2 * kD) + l * 2 * kD + c] : 0.f;
+  }
+}
+
 __global__ void gather_mult_kernel(BeamState st, int64_t* __restrict__ mult_preds, float* __restrict__ mult_lp,
                                    const int* __restrict__ best_len, int* __restrict__ info, int rows, int max_len,
                                    int batch) {
@@ -869,14 +882,24 @@ static int decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, c
   }
   ca.emb = h->emb; ca.pe = h->pe; ca.cls_b = h->cls_b; ca.tmaps = h->dec_tmaps;
   ca.ckv = w.ckv; ca.lens = lens; ca.bos_ids = bos_ids; ca.forbid = forbid; ca.kc = w.kc; ca.vc = w.vc; ca.bs = bs;
-  ca.tap = tap; ca.trace = nullptr;
+  ca.tap = tap; ca.trace = nullptr; ca.ckt = nullptr; ca.tpad = 0;
   ca.rows = rows; ca.beam = beam; ca.tp = tp; ca.max_len = max_len; ca.vocab = h->cfg.vocab_size; ca.min_len = min_len;
   ca.batch = batch; ca.compact = h->dec_compact ? 1 : 0;
 
   const bool want_cluster = h->use_cluster == 2 || (h->use_cluster == 1 && h->cfg.precision == CNB_PRECISION_FAST);
   if (want_cluster && (h->use_cluster == 2 || decoder_cluster_supported(ca))) {
-    // one cluster of 8 CTAs per group of clips decodes start to finish: 2 GEMMs + 1 kernel + 2 gathers
+    // one cluster of 8 CTAs per group of clips decodes start to finish: 2 GEMMs + key regrouping + 1 kernel + 2 gathers
     if (int rc = dec_project(h, frame_embs, batch, tp, w, st)) return rc;
+    const int tpad = (tp + 31) / 32 * 32;
+    WS(h, "ckt", float, (size_t)batch * kLayers * kD * tpad, ckt);
+    {
+      Prof _p(h, CNB_K_PROJ_KV, st);
+      const int64_t total = (int64_t)batch * kLayers * kD * tpad;
+      cross_k_transpose_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total, 256), 148 * 8), 256, 0, st>>>(w.ckv, ckt, batch, tp, tpad);
+      CNB_LAUNCH_OK();
+    }
+    ca.ckt = ckt;
+    ca.tpad = tpad;
     const bool trace_on = getenv("CNB_DEC_TRACE") != nullptr;
     if (trace_on) {
       WS(h, "dtrace_cl", unsigned long long, 32, tr);
@@ -891,12 +914,13 @@ static int decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, c
       unsigned long long t[20];
       CNB_CUDA_OK(cudaStreamSynchronize(st));
       CNB_CUDA_OK(cudaMemcpy(t, ca.trace, sizeof(t), cudaMemcpyDeviceToHost));
-      static const char* names[] = {"qkv gemm", "self attn", "sa_out gemm (K-split)", "reduce+gather+ln1", "ca_q gemm",
-                                    "cross attn", "ca_out gemm (K-split)", "reduce+gather+ln2", "ff1 gemm", "ff2 gemm",
-                                    "reduce+gather+ln3", "cls gemm (rounds)", "cls scan (rounds)", "beam exchange", "beam merge"};
+      static const char* names[] = {"qkv gemm", "self attn", "sa_out gemm (K-split)", "ln1", "ca_q gemm",
+                                    "cross attn", "ca_out gemm (K-split)", "ln2", "ff1 gemm", "ff2 gemm",
+                                    "ln3", "cls gemm (rounds)", "cls scan (rounds)", "beam exchange", "beam merge",
+                                    "3x wait reduce-scatter", "3x sum + all-gather push", "3x wait all-gather"};
       double tot = 0;
-      for (int i = 0; i < 15; ++i) tot += (double)t[i];
-      for (int i = 0; i < 15; ++i)
+      for (int i = 0; i < 18; ++i) tot += (double)t[i];
+      for (int i = 0; i < 18; ++i)
         fprintf(stderr, "[dec cluster trace] %-24s %9.1f us  (%4.1f %%)\n", names[i], (double)t[i] / 1e3, 100.0 * t[i] / tot);
     }
     if (int rc = launch_beam_finalize(bs, preds, lprobs, best_len, dd, st)) return rc;

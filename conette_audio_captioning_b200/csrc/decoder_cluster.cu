@@ -49,8 +49,10 @@ constexpr int kCPad = 0, kCEos = 2;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr float kCAttScale = 0.17677669529663687f;  // 1/sqrt(32)
 constexpr int kTrSlots = 20;
-constexpr int kStages = 3;      // weight ring: 3 x 32 KB
 constexpr int kStageBytes = 32768;
+// weight ring depth: bytes in flight bound the L2 -> shared-memory stream (~32 KB per microsecond and stage); 16-row clusters
+// have room for five stages, 32-row clusters for three
+template <int NR> struct RingDepth { static constexpr int value = NR <= 16 ? 5 : 3; };
 constexpr int kHalfStage = 16384;                  // W1 tiles in the first half of a stage, W2 tiles in the second
 constexpr int kChunksPerLayer = 4 + 1 + 1 + 1 + 8 + 8;  // QKV | sa_out | ca_q | ca_out | FF1 | FF2
 constexpr int kTileSlots = 4;   // TMEM accumulator tiles (2 per GEMM phase, double-buffered across classifier rounds)
@@ -125,6 +127,7 @@ template <int NR> __device__ __forceinline__ int op_off(int r, int k) {  // byte
 __device__ __forceinline__ int opa_off(int r, int k) { return r * 64 + ((((k >> 3) & 3) ^ ((r >> 1) & 3)) << 4); }
 
 template <int NR> struct CSmem {
+  static constexpr int kStages = RingDepth<NR>::value;
   alignas(1024) uint8_t ring[kStages][kStageBytes];  // weight tiles (A operand)
   // layer input x as hi/lo operand; between an all-gather and its LayerNorm the same bytes hold the pre-LN rows as fp32 [NR][256]
   alignas(1024) uint8_t opx[NR * 1024];
@@ -171,10 +174,13 @@ struct Pipe {
 // row rr.  Scores: lane = key (8 x LDG.128 each, all rows / chunks requested before the first use).  Values: lane =
 // (key group of 4, 4-dim quad): 16-byte loads, all requested up front, then a 2-step shuffle reduction over the groups.
 // The result (32 floats per row) is written as hi/lo fp16 into the K = 32 operand buffer `opa` (row index out_row[rr]).
-template <int NR, int NRW, int NCH, typename KPtr, typename VPtr>
+// KT = true (cross-attention): kptr(rr, 0) is the base of the clip's TRANSPOSED key slab [32 dims][tpad frames] (written once per
+// call by cross_k_transpose_kernel), so lane = frame reads 32 coalesced words (one L1 wavefront each) instead of eight 16-byte
+// pieces of its own 128-byte row (32 wavefronts per instruction: the L1 request queue was the bottleneck of the phase).
+template <int NR, int NRW, int NCH, bool KT, typename KPtr, typename VPtr>
 __device__ __forceinline__ void attend(const float* const (&q)[NRW], const int (&n)[NRW], const bool (&valid)[NRW], KPtr kptr,
                                        VPtr vptr, const float* const (&kv_new)[NRW], bool has_new, uint8_t* opa,
-                                       const int (&out_row)[NRW], int lane) {
+                                       const int (&out_row)[NRW], int lane, int tpad = 0) {
   float sc[NRW][NCH];
 #pragma unroll
   for (int rr = 0; rr < NRW; ++rr) {
@@ -188,7 +194,18 @@ __device__ __forceinline__ void attend(const float* const (&q)[NRW], const int (
     for (int ch = 0; ch < NCH; ++ch) {
       const int j = lane + 32 * ch;
       sc[rr][ch] = -INFINITY;
-      if (valid[rr] && j < n[rr]) {
+      if (KT) {
+        if (valid[rr] && j < n[rr]) {
+          const float* kb = kptr(rr, 0) + j;
+          float kk[kCHead];
+#pragma unroll
+          for (int d = 0; d < kCHead; ++d) kk[d] = kb[d * tpad];
+          float a = 0.f;
+#pragma unroll
+          for (int d = 0; d < kCHead; ++d) a = fmaf(qv[d], kk[d], a);
+          sc[rr][ch] = a * kCAttScale;
+        }
+      } else if (valid[rr] && j < n[rr]) {
         const float4* kr = reinterpret_cast<const float4*>(kptr(rr, j));
         float4 kk[8];
 #pragma unroll
@@ -288,6 +305,7 @@ __device__ __forceinline__ void attend(const float* const (&q)[NRW], const int (
 //              FF2      8 chunks: tile t (128 outputs) x k-chunk c of this CTA's K slice [256 rank, +256)
 //   classifier 8 chunks per round of 256 words: tile t x k-chunk c; rows beyond the vocabulary are zero-filled by TMA
 // Chunk g (running index) lives in ring stage g % kStages.
+template <int kStages>
 __device__ __forceinline__ void issue_chunk(uint8_t* ring, unsigned long long* full, const ClusterArgs& a, uint32_t g, int rank,
                                             int v0, int chunks_per_step) {
   const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(a.tmaps);
@@ -349,6 +367,7 @@ template <int NR, typename Epi>
 __device__ __forceinline__ void tc_gemm(CSmem<NR>& S, const ClusterArgs& a, Pipe& pp, uint32_t tmem_base, uint32_t& tile_par,
                                         int kind, int n_chunks, uint32_t b_addr, int slot0, int rank, int v0,
                                         int chunks_per_step, Epi epi) {
+  constexpr int kStages = CSmem<NR>::kStages;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   fence_proxy_async_smem();  // activations were written through the generic / st.async path: make them visible to the MMA
   tcgen05_fence_before();
@@ -362,7 +381,7 @@ __device__ __forceinline__ void tc_gemm(CSmem<NR>& S, const ClusterArgs& a, Pipe
     while (pp.load < target) {
       const int s = (int)(pp.load % kStages);
       mbar_wait(smem_addr(&S.empty[s]), ((pp.load / kStages) & 1u) ^ 1u);  // the MMAs that read this stage have completed
-      if (elect_one()) issue_chunk(&S.ring[0][0], S.full, a, pp.load, rank, v0, chunks_per_step);
+      if (elect_one()) issue_chunk<kStages>(&S.ring[0][0], S.full, a, pp.load, rank, v0, chunks_per_step);
       __syncwarp();
       ++pp.load;
     }
@@ -472,7 +491,7 @@ __device__ __forceinline__ void rs_push(CSmem<NR>& S, int rank, int t, int quart
 // opx becomes the hi/lo operand of the next GEMM, xr the exact fp32 residual slice.
 template <int NR>
 __device__ __forceinline__ void reduce_gather_ln(CSmem<NR>& S, ExCount& ex, int rank, const float* __restrict__ bias,
-                                                 const float* __restrict__ g, const float* __restrict__ b) {
+                                                 const float* __restrict__ g, const float* __restrict__ b, bool tr_on) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr uint32_t kBytes = (kCl - 1) * NR * kCHead * 4;
   const uint32_t bar_rs = smem_addr(&S.bar_rs), bar_ag = smem_addr(&S.bar_ag);
@@ -483,6 +502,7 @@ __device__ __forceinline__ void reduce_gather_ln(CSmem<NR>& S, ExCount& ex, int 
   mbar_wait(bar_rs, ex.rs & 1u);
   ++ex.rs;
   __syncthreads();  // this CTA's own slab was written with ordinary stores by the epilogue warps
+  CL_TR(15);
   float (*stg)[kCD] = S.stage();
   for (int idx = tid; idx < NR * 8; idx += kCThreads) {
     const int r = idx >> 3, q4 = idx & 7;
@@ -503,9 +523,11 @@ __device__ __forceinline__ void reduce_gather_ln(CSmem<NR>& S, ExCount& ex, int 
       st_async16(map_peer(da, peer), y, map_peer(bar_ag, peer));
     }
   }
+  CL_TR(16);
   mbar_wait(bar_ag, ex.ag & 1u);
   ++ex.ag;
   __syncthreads();  // own slice (ordinary stores) visible to every warp
+  CL_TR(17);
   // LayerNorm (eps 1e-5, biased variance): one warp per row, lane holds columns [8 lane, +8)
   float v[NR / kCWarps][8];
 #pragma unroll
@@ -625,8 +647,8 @@ __device__ __noinline__ void decode_layer(CSmem<NR>& S, const ClusterArgs& a, Pi
     auto kp = [&](int rr, int j) { return kc + ((int64_t)(grow0 + s0[rr][j]) * max_len + j) * kCD + rank * kCHead; };
     auto vp = [&](int rr, int j) { return vc + ((int64_t)(grow0 + s0[rr][j]) * max_len + j) * kCD + rank * kCHead; };
     if (valid[0]) {  // warp-uniform (rows of a warp: r, r + 16)
-      if (pos <= 32) attend<NR, NRW, 1>(qq, nn, valid, kp, vp, kvn, true, S.opa, orow, lane);
-      else attend<NR, NRW, 2>(qq, nn, valid, kp, vp, kvn, true, S.opa, orow, lane);
+      if (pos <= 32) attend<NR, NRW, 1, false>(qq, nn, valid, kp, vp, kvn, true, S.opa, orow, lane);
+      else attend<NR, NRW, 2, false>(qq, nn, valid, kp, vp, kvn, true, S.opa, orow, lane);
     }
   }
   CL_TR(1);
@@ -634,7 +656,7 @@ __device__ __noinline__ void decode_layer(CSmem<NR>& S, const ClusterArgs& a, Pi
   tc_gemm<NR>(S, a, pp, tmem_base, tile_par, G_OUT, 1, opa, 0, rank, v0, chunks_per_step,
               [&](int t, int quarter, int ln, int r0, const float (&v)[16]) { rs_push<NR>(S, rank, t, quarter, ln, r0, v); });
   CL_TR(2);
-  reduce_gather_ln<NR>(S, ex, rank, L.sa_out_b, L.n1_g, L.n1_b);
+  reduce_gather_ln<NR>(S, ex, rank, L.sa_out_b, L.n1_g, L.n1_b, tr_on);
   CL_TR(3);
   // ---- P3: cross-attention query of head `rank`, cross-attention over the clip's encoder frames
   tc_gemm<NR>(S, a, pp, tmem_base, tile_par, G_P32, 1, opx, 0, rank, v0, chunks_per_step,
@@ -662,12 +684,14 @@ __device__ __noinline__ void decode_layer(CSmem<NR>& S, const ClusterArgs& a, Pi
       c0[rr] = clip0 + (valid[rr] ? r / beam : 0);
       nn[rr] = valid[rr] ? min(a.lens[c0[rr]], tp) : 0;
     }
-    auto kp = [&](int rr, int j) { return ck + ((int64_t)c0[rr] * tp + j) * kv_stride; };
+    const int tpad = a.tpad;
+    const float* kt = a.ckt + ((int64_t)l * kCl + rank) * kCHead * tpad;  // [clip][layer][head][32][tpad]
+    auto kp = [&](int rr, int) { return kt + (int64_t)c0[rr] * kCLayers * kCD * tpad; };
     auto vp = [&](int rr, int j) { return ck + ((int64_t)c0[rr] * tp + j) * kv_stride + kCD; };
     if (valid[0]) {
-      if (tp <= 32) attend<NR, NRW, 1>(qq, nn, valid, kp, vp, kvn, false, S.opa, orow, lane);
-      else if (tp <= 64) attend<NR, NRW, 2>(qq, nn, valid, kp, vp, kvn, false, S.opa, orow, lane);
-      else attend<NR, NRW, 4>(qq, nn, valid, kp, vp, kvn, false, S.opa, orow, lane);
+      if (tp <= 32) attend<NR, NRW, 1, true>(qq, nn, valid, kp, vp, kvn, false, S.opa, orow, lane, tpad);
+      else if (tp <= 64) attend<NR, NRW, 2, true>(qq, nn, valid, kp, vp, kvn, false, S.opa, orow, lane, tpad);
+      else attend<NR, NRW, 4, true>(qq, nn, valid, kp, vp, kvn, false, S.opa, orow, lane, tpad);
     }
   }
   CL_TR(5);
@@ -675,7 +699,7 @@ __device__ __noinline__ void decode_layer(CSmem<NR>& S, const ClusterArgs& a, Pi
   tc_gemm<NR>(S, a, pp, tmem_base, tile_par, G_OUT, 1, opa, 0, rank, v0, chunks_per_step,
               [&](int t, int quarter, int ln, int r0, const float (&v)[16]) { rs_push<NR>(S, rank, t, quarter, ln, r0, v); });
   CL_TR(6);
-  reduce_gather_ln<NR>(S, ex, rank, L.ca_out_b, L.n2_g, L.n2_b);
+  reduce_gather_ln<NR>(S, ex, rank, L.ca_out_b, L.n2_g, L.n2_b, tr_on);
   CL_TR(7);
   // ---- P5: FF1 slice (256 hidden units of this CTA) + GELU -> oph (hi/lo operand)
   tc_gemm<NR>(S, a, pp, tmem_base, tile_par, G_FF, 8, opx, 0, rank, v0, chunks_per_step,
@@ -700,7 +724,7 @@ __device__ __noinline__ void decode_layer(CSmem<NR>& S, const ClusterArgs& a, Pi
   tc_gemm<NR>(S, a, pp, tmem_base, tile_par, G_FF, 8, oph, 0, rank, v0, chunks_per_step,
               [&](int t, int quarter, int ln, int r0, const float (&v)[16]) { rs_push<NR>(S, rank, t, quarter, ln, r0, v); });
   CL_TR(9);
-  reduce_gather_ln<NR>(S, ex, rank, L.l2_b, L.n3_g, L.n3_b);
+  reduce_gather_ln<NR>(S, ex, rank, L.l2_b, L.n3_g, L.n3_b, tr_on);
   CL_TR(10);
 }
 
@@ -743,14 +767,24 @@ __device__ __noinline__ void decode_select(CSmem<NR>& S, const ClusterArgs& a, P
         for (int u = 0; u < 8; ++u)
           if (e == lane + 32 * u) x[u] = -INFINITY;
       }
-      if (a.forbid != nullptr) {  // beam.py:146-156
-        for (int p = 0; p <= step; ++p) {
-          const int tok = S.tokens[cur][r][p];
-          const int e = tok - base;
-          if (e >= 0 && e < kClsRound && (e & 31) == lane && a.forbid[tok]) {
+      if (a.forbid != nullptr) {  // beam.py:146-156: lane p fetches history token p and its flag, then all lanes walk the list
+        for (int p0 = 0; p0 <= step; p0 += 32) {
+          int my_e = -1;
+          if (p0 + lane <= step) {
+            const int tok = S.tokens[cur][r][p0 + lane];
+            const int e = tok - base;
+            if (e >= 0 && e < kClsRound && a.forbid[tok]) my_e = e;
+          }
+          unsigned hit = __ballot_sync(kFull, my_e >= 0);
+          while (hit) {
+            const int src = __ffs(hit) - 1;
+            hit &= hit - 1;
+            const int e = __shfl_sync(kFull, my_e, src);
+            if ((e & 31) == lane) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-              if (u == (e >> 5)) x[u] = -INFINITY;
+              for (int u = 0; u < 8; ++u)
+                if (u == (e >> 5)) x[u] = -INFINITY;
+            }
           }
         }
       }
@@ -958,6 +992,7 @@ __device__ __noinline__ void decode_select(CSmem<NR>& S, const ClusterArgs& a, P
 template <int NR>
 __global__ void __launch_bounds__(kCThreads, 1)
 decoder_cluster_kernel(const __grid_constant__ ClusterArgs a, int clips_per_group, int n_groups, int vs /*vocabulary slice*/) {
+  constexpr int kStages = CSmem<NR>::kStages;
   extern __shared__ uint8_t smem_raw[];
   // operand tiles need 1024-byte alignment (128B swizzle atoms); the offset is the same in every CTA of the launch
   uint8_t* smem_al = smem_raw + ((1024u - (smem_addr(smem_raw) & 1023u)) & 1023u);
@@ -1100,10 +1135,10 @@ template <int NR> int max_clusters_for(int* out) {
   return 0;
 }
 
-// Group size policy.  Fewest rows per cluster = least attention / epilogue work per step, so a call that has the GPU to itself
-// spreads the clips over 16-row clusters (one wave when the device can hold them); 32-row clusters halve the number of SMs and
-// the L2 weight traffic and are chosen when the decode shares the GPU with the next batch's encoder (`compact`) or when 16-row
-// clusters would need more than one wave.  CNB_DEC_NR=16|32 overrides.  0 ok, 1 unsupported, < 0 error.
+// Group size policy.  Fewest rows per cluster = least attention / epilogue / LayerNorm work per step (those phases scale with
+// the rows; measured: 15 rows take 4.0 ms in a 16-row cluster and 5.3 ms in a 32-row one), so the clips are spread over 16-row
+// clusters as long as one wave of them fits the device; beyond that 32-row clusters (half as many groups, deeper per step) beat
+// a second wave.  CNB_DEC_NR=16|32 overrides.  0 ok, 1 unsupported, < 0 error.
 int cluster_plan(const ClusterArgs& a, ClusterPlan* p) {
   if (a.beam < 1 || a.beam > kCMaxBeam || a.max_len > kCMaxLen || a.tp > kCMaxTp || a.vocab <= 4 || a.vocab > 65535 ||
       a.tmaps == nullptr)
@@ -1116,14 +1151,14 @@ int cluster_plan(const ClusterArgs& a, ClusterPlan* p) {
   const char* env_nr = getenv("CNB_DEC_NR");
   const int forced = env_nr ? atoi(env_nr) : 0;
   const int need16 = (int)ceil_div(a.batch, 16 / a.beam);
-  int nr = (a.compact || need16 > mc16) ? 32 : 16;
+  int nr = need16 > mc16 ? 32 : 16;
   if (forced == 16 || forced == 32) nr = forced;
   if (nr == 32 && (mc32 <= 0 || a.batch * a.beam <= 16)) nr = 16;
   if (nr == 16 && mc16 <= 0) nr = 32;
   const int mc = nr == 16 ? mc16 : mc32;
   const int gmax = nr / a.beam;
   int g = (int)ceil_div(a.batch, mc);
-  if (g > gmax || a.compact) g = gmax;
+  if (g > gmax) g = gmax;
   p->nr = nr;
   p->clips_per_group = g;
   p->n_groups = (int)ceil_div(a.batch, g);

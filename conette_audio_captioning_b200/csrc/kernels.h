@@ -144,6 +144,8 @@ struct ClusterArgs {
   const float *emb, *pe, *cls_b;
   const void* tmaps;         // kDecMaps CUtensorMaps (device): layer l -> [12 l + 2 j + half], classifier at 72 + half
   const float* ckv;          // (B*T', 6*512) cross-attention K|V of all layers
+  const float* ckt;          // cross-attention keys transposed per clip: [B][6 layers][8 heads][32 dims][tpad]
+  int tpad;                  // T' rounded up to a multiple of 32 (128-byte rows)
   const int* lens;
   const int64_t* bos_ids;
   const uint8_t* forbid;

@@ -6,8 +6,10 @@ margin (oracle/parity.py): a clip whose smallest oracle selection gap is >= eps 
 derived from the measured score error of the path (a selection can only flip when the gap is below twice the error of a
 cumulative score) and both halves are asserted: `2 * max_score_err <= eps` and `all firm clips identical`.
 
-  decoder alone (fed the oracle's frame embeddings)    EPS_DEC = 1e-3   measured cumulative-score error <= 2e-4
-  end to end (fp16-operand encoder in front)           EPS_E2E = 4e-2   measured cumulative-score error <= 2e-2
+  decoder alone (fed the oracle's frame embeddings)    EPS_DEC = 2e-4   measured: logits <= 1.4e-5, cumulative scores <= 4e-5
+  end to end (fp16-operand encoder in front)           EPS_E2E = 5e-3   measured: frame_embs 5.8e-4 rel-L2, scores <= 2e-3
+(B200, round 2: 16/16 clips bit-identical to the oracle at beam 3 in both settings; greedy 16/16 decoder-only and 15/16 end to
+end -- the odd one is an exact fp32 tie in the oracle, margin 0.0)
 
 The oracle (oracle/restate.py, pinned to the reference by tests/test_oracle_vs_reference.py) needs ~0.4 s per 10 s clip on the
 GPU box's host cores, so 16 of the 64 clips of the benchmark batch are checked; the CUDA path runs the whole 64-clip batch.
@@ -19,8 +21,8 @@ from conette_audio_captioning_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
-EPS_DEC = 1e-3
-EPS_E2E = 4e-2
+EPS_DEC = 2e-4
+EPS_E2E = 5e-3
 N_SAMPLES = 320000
 N_CHECK = 16
 
@@ -66,7 +68,7 @@ def test_fast_path_vs_oracle_at_bench_config(bench_eng, bench_batch, beam):
     fe, _ = bench_eng.encoder(wav[:N_CHECK].cuda(), with_tags=False)
     rec["frame_embs_rel_l2"] = float((fe.cpu() - ref[beam]["frame_embs"]).norm() / ref[beam]["frame_embs"].norm())
     _report(f"end-to-end beam {beam}", rec)
-    assert rec["frame_embs_rel_l2"] < 1.5e-3
+    assert rec["frame_embs_rel_l2"] < 1e-3
     assert rec["mismatched_firm_clips"] == [], rec
     assert rec["max_score_err"] is not None and 2 * rec["max_score_err"] <= EPS_E2E, rec
     assert rec["identical"] >= N_CHECK // 2, rec  # the claim must not be vacuous
@@ -136,3 +138,4 @@ def test_cluster_decoder_large_vocabulary(n_words, beam):
     assert rec["max_logit_err_step0"] < 2e-4, rec
     assert rec["mismatched_firm_clips"] == [], rec
     assert rec["identical"] >= (3 * b) // 4, rec
+    assert rec["max_score_err"] is not None and 2 * rec["max_score_err"] <= EPS_DEC, rec

@@ -221,10 +221,10 @@ def test_encoder_outputs_fast(eng_fast, oracle_taps):
     fe, clip = eng_fast.encoder(wav)
     err = rel_l2(fe, out["frame_embs"].transpose(1, 2))
     print(f"fast-mode frame_embs rel-L2 = {err:.2e}")
-    assert err < 5e-3
-    assert float((clip.cpu() - out["clipwise_output"]).abs().max()) < 2e-2
+    assert err < 1e-3  # fp16 operands + tanh-fit GELU: measured 5.8e-4 (bf16 operands gave 4.5e-3)
+    assert float((clip.cpu() - out["clipwise_output"]).abs().max()) < 5e-3
     got = eng_fast.encoder_tap(wav, _lib.TAP_BLOCK, 0, 0).cpu()
-    assert rel_l2(got, _nhwc(taps["block.0.0"])) < 5e-3
+    assert rel_l2(got, _nhwc(taps["block.0.0"])) < 1e-3
 
 
 @pytest.mark.gpu
@@ -248,7 +248,7 @@ def test_fused_mlp_kernel(eng_fast, m):
     want = x + scale * (hid @ bf(w2).T + b2)
     upd_err = float(((got - x) - (want - x)).norm() / (want - x).norm())
     print(f"fused MLP m={m}: update rel-L2 {upd_err:.2e}")
-    assert upd_err < 1e-3, upd_err
+    assert upd_err < 3e-4, upd_err  # measured 9e-5 .. 1.2e-4
     assert float((got - want).abs().max()) < 5e-3
     # rows are independent: the last row of a ragged batch equals the same row computed alone
     if m > 1:
@@ -424,7 +424,7 @@ def test_decoder_graph_and_eager_agree_bitwise(small_sd):
         assert torch.equal(a, c)
 
 
-CLUSTER_EPS = 1e-3
+CLUSTER_EPS = 2e-4
 
 
 @pytest.mark.parametrize("b,beam,max_len,tp", [(37, 3, 20, 31), (5, 1, 12, 31), (9, 2, 20, 31), (7, 5, 16, 31), (3, 8, 24, 31),
@@ -433,7 +433,8 @@ CLUSTER_EPS = 1e-3
 def test_decoder_cluster_vs_oracle(small_sd, monkeypatch, b, beam, max_len, tp, nr):
     """One-launch cluster decode (fp16 hi/lo split tcgen05 GEMMs, DSMEM reduce-scatter / all-gather exchanges) against the CPU
     oracle's beam search, for both cluster widths (16 / 32 rows, CNB_DEC_NR) and ragged group sizes: ids bit-exact on every clip
-    whose oracle selection margin is >= 1e-3, scores within 2e-4 (x length) there, per-step logits <= 1e-4, deterministic."""
+    whose oracle selection margin is >= 2e-4 (measured cumulative-score error <= 1.2e-5), step-0 logits <= 1e-4 (measured 3e-6),
+    deterministic."""
     from conette_audio_captioning_b200.engine import Engine
     from oracle import parity, restate
 

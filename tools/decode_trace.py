@@ -4,7 +4,7 @@ import argparse
 import os
 import sys
 
-os.environ["CNB_DEC_TRACE"] = "1"
+os.environ.setdefault("CNB_DEC_TRACE", "1")
 import torch  # noqa: E402
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
