@@ -106,6 +106,8 @@ struct cnb_handle {
   cudaEvent_t host_done[2] = {};         // cnb_caption_host_begin/end: completion of the batch that used staging slot i
   bool host_pending[2] = {false, false};
   int host_next = 0;
+  cudaEvent_t ev_dev_last = nullptr;     // end of the last device-buffer entry point (cnb_caption / encoder / decode ...)
+  bool dev_last_valid = false;
   cudaEvent_t ev_lens = nullptr;         // the last H2D copy out of pin_lens
   int32_t* pin_lens = nullptr;           // pinned staging for the per-clip frame counts
   int pin_lens_cap = 0;
@@ -212,7 +214,7 @@ static int put_f32(cnb_handle* h, const std::vector<float>& v, float** out) {
   *out = h->arena.take<float>(v.size());
   return upload(*out, v);
 }
-static int put_bf16(cnb_handle* h, const std::vector<float>& v, act16** out) {
+static int put_f16(cnb_handle* h, const std::vector<float>& v, act16** out) {
   std::vector<act16> t(v.size());
   for (size_t i = 0; i < v.size(); ++i) t[i] = float2act(v[i]);
   *out = h->arena.take<act16>(v.size());
@@ -225,7 +227,7 @@ static int put_bf16(cnb_handle* h, const std::vector<float>& v, act16** out) {
 #define PUT(dst, vec) \
   if (int _rc = put_f32(h, vec, &(dst))) return _rc
 #define PUT_BF(dst, vec) \
-  if (int _rc = put_bf16(h, vec, &(dst))) return _rc
+  if (int _rc = put_f16(h, vec, &(dst))) return _rc
 
 // fp16 hi/lo split of a decoder weight matrix for the cluster decoder (decoder_cluster.cu): W = W1 + 2^-11 W2 with
 // W1 = fp16(W), W2 = fp16((W - W1) * 2048); `out` = [W1 (n*k) | W2 (n*k)].  `head_pack`: columns regrouped per attention head,
@@ -441,7 +443,7 @@ static int finalize(cnb_handle* h) {
       const int64_t rows = head_pack ? (int64_t)n * (k / 32) : n, cols = head_pack ? 32 : k;
       for (int half = 0; half < 2; ++half) {
         alignas(64) uint8_t tmp[128];
-        if (int rc = tc_make_map_bf16_box(tmp, d + (size_t)half * n * k, rows, cols, box_rows, box_cols)) return rc;
+        if (int rc = tc_make_map_f16_box(tmp, d + (size_t)half * n * k, rows, cols, box_rows, box_cols)) return rc;
         memcpy(&maps[(size_t)(idx + half) * 128], tmp, 128);
       }
       return 0;
@@ -512,7 +514,7 @@ struct Tap {
   bool hit = false;
 };
 
-static int copy_tap(Tap* tap, const void* src, int64_t elems, bool src_is_bf16, cudaStream_t st);
+static int copy_tap(Tap* tap, const void* src, int64_t elems, bool src_is_f16, cudaStream_t st);
 
 template <typename ActT>
 static int mlp_gemm(cnb_handle* h, const ActT* a, const float* w32, const act16* wbf, int m, int n, int k, Epilogue epi,
@@ -624,18 +626,18 @@ static int encode_chunk(cnb_handle* h, const float* wav, int nb, int64_t n, floa
   return 0;
 }
 
-__global__ void bf16_to_f32_kernel(const act16* __restrict__ in, float* __restrict__ out, int64_t n) {
+__global__ void act16_to_f32_kernel(const act16* __restrict__ in, float* __restrict__ out, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = act2float(in[i]);
 }
 
-static int copy_tap(Tap* tap, const void* src, int64_t elems, bool src_is_bf16, cudaStream_t st) {
+static int copy_tap(Tap* tap, const void* src, int64_t elems, bool src_is_f16, cudaStream_t st) {
   if (elems > tap->cap) {
     set_error("encoder tap needs " + std::to_string(elems) + " elements but the output holds " + std::to_string(tap->cap));
     return -1;
   }
-  if (src_is_bf16) {
-    bf16_to_f32_kernel<<<(unsigned)ceil_div(elems, 256), 256, 0, st>>>(reinterpret_cast<const act16*>(src), tap->out,
+  if (src_is_f16) {
+    act16_to_f32_kernel<<<(unsigned)ceil_div(elems, 256), 256, 0, st>>>(reinterpret_cast<const act16*>(src), tap->out,
                                                                         elems);
     CNB_LAUNCH_OK();
   } else {
@@ -985,6 +987,28 @@ static void frame_lens_host(const int64_t* x_lens, int batch, int64_t n, std::ve
   }
 }
 
+// The device-buffer entry points (caller's stream) and the split-phase host API (the handle's own streams) share the
+// un-suffixed workspaces (log-mel, activations, decoder buffers ...).  Ordering between the two families:
+//   dev_enter: the caller's stream waits for every host batch still in flight;
+//   dev_leave: records the end of the device-path work, which the next cnb_caption_host_begin makes its streams wait for.
+static int dev_enter(cnb_handle* h, cudaStream_t st) {
+  for (int slot = 0; slot < 2; ++slot)
+    if (h->host_pending[slot]) CNB_CUDA_OK(cudaStreamWaitEvent(st, h->host_done[slot], 0));
+  return 0;
+}
+static int dev_leave(cnb_handle* h, cudaStream_t st) {
+  if (!h->ev_dev_last) CNB_CUDA_OK(cudaEventCreateWithFlags(&h->ev_dev_last, cudaEventDisableTiming));
+  CNB_CUDA_OK(cudaEventRecord(h->ev_dev_last, st));
+  h->dev_last_valid = true;
+  return 0;
+}
+#define DEV_SCOPE(h, st, call)                      \
+  do {                                              \
+    if (int _rc = dev_enter(h, st)) return _rc;     \
+    if (int _rc = (call)) return _rc;               \
+    return dev_leave(h, st);                        \
+  } while (0)
+
 }  // namespace cnb
 
 // =====================================================================================================================
@@ -1061,6 +1085,7 @@ int cnb_destroy(cnb_handle* h) {
   if (h->dec_stream) cudaStreamDestroy(h->dec_stream);
   if (h->pin_lens) cudaFreeHost(h->pin_lens);
   if (h->ev_lens) cudaEventDestroy(h->ev_lens);
+  if (h->ev_dev_last) cudaEventDestroy(h->ev_dev_last);
   delete h;
   return 0;
 }
@@ -1127,7 +1152,7 @@ int cnb_encoder(cnb_handle* h, const float* wav, int32_t batch, int64_t n, float
   CHECK_READY(h);
   CNB_REQUIRE(wav && frame_embs_out, "null buffer");
   if (int rc = check_audio(batch, n)) return rc;
-  return encode(h, wav, batch, n, frame_embs_out, clip_probs_out, (cudaStream_t)stream);
+  DEV_SCOPE(h, (cudaStream_t)stream, encode(h, wav, batch, n, frame_embs_out, clip_probs_out, (cudaStream_t)stream));
 }
 
 int cnb_encoder_tap(cnb_handle* h, const float* wav, int32_t batch, int64_t n, int32_t tap_kind, int32_t stage, int32_t block,
@@ -1140,19 +1165,20 @@ int cnb_encoder_tap(cnb_handle* h, const float* wav, int32_t batch, int64_t n, i
   tap.kind = tap_kind; tap.stage = stage; tap.block = block; tap.out = out; tap.cap = cap;
   const Geometry g = geometry(n);
   WS(h, "tap_fe", float, (size_t)batch * g.tp * 768, fe);
+  if (int rc = dev_enter(h, (cudaStream_t)stream)) return rc;
   int rc = (h->cfg.precision == CNB_PRECISION_PARITY)
                ? encode_chunk<float>(h, wav, batch, n, fe, nullptr, &tap, (cudaStream_t)stream)
                : encode_chunk<act16>(h, wav, batch, n, fe, nullptr, &tap, (cudaStream_t)stream);
   if (rc) return rc;
   CNB_REQUIRE(tap.hit, "no such tap point");
-  return 0;
+  return dev_leave(h, (cudaStream_t)stream);
 }
 
 static int check_decode(cnb_handle* h, int32_t batch, int32_t tp, int32_t beam, int32_t min_len, int32_t max_len) {
   CNB_REQUIRE(batch > 0 && tp > 0, "empty batch");
-  CNB_REQUIRE(beam > 0 && beam <= 8, "beam_size must be in [1, 8]");
+  CNB_REQUIRE(beam > 0 && beam <= CNB_MAX_BEAM, "beam_size must be in [1, 8] (CNB_MAX_BEAM)");
   CNB_REQUIRE(min_len >= 0, "min_pred_size must be >= 0");
-  CNB_REQUIRE(max_len > 0 && max_len <= 64, "max_pred_size must be in [1, 64]");
+  CNB_REQUIRE(max_len > 0 && max_len <= CNB_MAX_PRED_SIZE, "max_pred_size must be in [1, 64] (CNB_MAX_PRED_SIZE)");
   return 0;
 }
 
@@ -1162,8 +1188,8 @@ int cnb_decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, cons
   CHECK_READY(h);
   CNB_REQUIRE(frame_embs && lens && bos_ids && preds && lprobs && mult_preds && mult_lprobs && info, "null buffer");
   if (int rc = check_decode(h, batch, tp, beam, min_len, max_len)) return rc;
-  return decode(h, frame_embs, lens, bos_ids, forbid, batch, tp, beam, min_len, max_len, preds, lprobs, mult_preds,
-                mult_lprobs, info, (cudaStream_t)stream);
+  DEV_SCOPE(h, (cudaStream_t)stream, decode(h, frame_embs, lens, bos_ids, forbid, batch, tp, beam, min_len, max_len, preds, lprobs,
+                                            mult_preds, mult_lprobs, info, (cudaStream_t)stream));
 }
 
 int cnb_decode_tap(cnb_handle* h, const float* frame_embs, const int32_t* lens, const int64_t* bos_ids, const uint8_t* forbid,
@@ -1174,10 +1200,11 @@ int cnb_decode_tap(cnb_handle* h, const float* frame_embs, const int32_t* lens, 
   if (int rc = check_decode(h, batch, tp, beam, min_len, max_len)) return rc;
   const int keep = h->use_cluster;
   h->use_cluster = 2;  // the tap lives in the cluster kernel: fail instead of falling back
+  if (int rc = dev_enter(h, (cudaStream_t)stream)) return rc;
   const int rc = decode(h, frame_embs, lens, bos_ids, forbid, batch, tp, beam, min_len, max_len, preds, lprobs, mult_preds,
                         mult_lprobs, info, (cudaStream_t)stream, logits_out);
   h->use_cluster = keep;
-  return rc;
+  return rc ? rc : dev_leave(h, (cudaStream_t)stream);
 }
 
 int cnb_decoder_logits(cnb_handle* h, const float* frame_embs, const int32_t* lens, const int64_t* tokens, int32_t batch,
@@ -1186,6 +1213,7 @@ int cnb_decoder_logits(cnb_handle* h, const float* frame_embs, const int32_t* le
   CNB_REQUIRE(frame_embs && lens && tokens && logits_out, "null buffer");
   if (int rc = check_decode(h, batch, tp, 1, 0, steps)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = dev_enter(h, st)) return rc;
   DecoderDims dd{batch, 1, tp, steps, h->cfg.vocab_size};
   DecWs w;
   if (int rc = dec_prepare(h, batch, tp, batch, steps, &w)) return rc;
@@ -1202,18 +1230,19 @@ int cnb_decoder_logits(cnb_handle* h, const float* frame_embs, const int32_t* le
                                                                                           dd.vocab, i, steps);
     CNB_LAUNCH_OK();
   }
-  return 0;
+  return dev_leave(h, st);
 }
 
 int cnb_score_captions(cnb_handle* h, const float* frame_embs, const int32_t* lens, const int64_t* captions, int32_t batch,
                        int32_t tp, int32_t n_caps, int32_t cap_len, float* token_lprobs_out, float* losses_out, void* stream) {
   CHECK_READY(h);
   CNB_REQUIRE(frame_embs && lens && captions && token_lprobs_out && losses_out, "null buffer");
-  CNB_REQUIRE(n_caps > 0 && n_caps <= 8, "n_caps must be in [1, 8]");
+  CNB_REQUIRE(n_caps > 0 && n_caps <= CNB_MAX_BEAM, "n_caps must be in [1, 8] (CNB_MAX_BEAM)");
   CNB_REQUIRE(cap_len >= 2, "captions need at least BOS + one target token");
   const int steps = cap_len - 1;
   if (int rc = check_decode(h, batch, tp, n_caps, 0, steps)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = dev_enter(h, st)) return rc;
   const int rows = batch * n_caps;
   DecoderDims dd{rows, n_caps, tp, steps, h->cfg.vocab_size};
   DecWs w;
@@ -1232,7 +1261,7 @@ int cnb_score_captions(cnb_handle* h, const float* frame_embs, const int32_t* le
   }
   score_reduce_kernel<<<(rows + 127) / 128, 128, 0, st>>>(token_lprobs_out, tok, losses_out, rows, steps);
   CNB_LAUNCH_OK();
-  return 0;
+  return dev_leave(h, st);
 }
 
 // Encoder on `st`, projection + beam search on `st_dec` (the same stream, or the handle's high-priority decode stream when the
@@ -1281,8 +1310,10 @@ static int caption_impl(cnb_handle* h, const float* wav, const int64_t* x_lens_h
 int cnb_caption(cnb_handle* h, const float* wav, const int64_t* x_lens_host, const int64_t* bos_ids, const uint8_t* forbid,
                 int32_t batch, int64_t n, int32_t beam, int32_t min_len, int32_t max_len, int64_t* preds, float* lprobs,
                 int64_t* mult_preds, float* mult_lprobs, int32_t* info, float* clip_probs, void* stream) {
-  return caption_impl(h, wav, x_lens_host, bos_ids, forbid, batch, n, beam, min_len, max_len, preds, lprobs, mult_preds,
-                      mult_lprobs, info, clip_probs, (cudaStream_t)stream, (cudaStream_t)stream, 0);
+  CHECK_READY(h);
+  DEV_SCOPE(h, (cudaStream_t)stream, caption_impl(h, wav, x_lens_host, bos_ids, forbid, batch, n, beam, min_len, max_len, preds,
+                                                  lprobs, mult_preds, mult_lprobs, info, clip_probs, (cudaStream_t)stream,
+                                                  (cudaStream_t)stream, 0));
 }
 
 int cnb_caption_host_begin(cnb_handle* h, const float* wav_host, const int64_t* x_lens_host, const int64_t* bos_ids_host,
@@ -1304,6 +1335,10 @@ int cnb_caption_host_begin(cnb_handle* h, const float* wav_host, const int64_t* 
   if (h->host_pending[slot]) {  // the caller never collected the batch that used this slot: its buffers are still in use
     CNB_CUDA_OK(cudaEventSynchronize(h->host_done[slot]));
     h->host_pending[slot] = false;
+  }
+  if (h->dev_last_valid) {  // a device-buffer call may still be using the shared workspaces on the caller's stream
+    CNB_CUDA_OK(cudaStreamWaitEvent(st, h->ev_dev_last, 0));
+    h->dev_last_valid = false;
   }
   const std::string sfx = slot ? ".1" : ".0";
   WS(h, ("io_wav" + sfx).c_str(), float, (size_t)batch * n, wav);
@@ -1408,7 +1443,7 @@ int cnb_caption_host(cnb_handle* h, const float* wav_host, const int64_t* x_lens
   return cnb_caption_host_end(h, ticket);
 }
 
-__global__ void f32_to_bf16_kernel(const float* __restrict__ in, act16* __restrict__ out, int64_t n) {
+__global__ void f32_to_act16_kernel(const float* __restrict__ in, act16* __restrict__ out, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = float2act(in[i]);
 }
@@ -1424,15 +1459,15 @@ int cnb_debug_gemm(cnb_handle* h, const float* a, const float* w, const float* b
   if (!use_tc) return launch_gemm_f32<float>(a, k, w, m, n, k, (Epilogue)epi, ep, out, n, st);
   WS(h, "dbg_a", act16, (size_t)m * k, a_bf);
   WS(h, "dbg_w", act16, (size_t)n * k, w_bf);
-  f32_to_bf16_kernel<<<(unsigned)ceil_div((int64_t)m * k, 256), 256, 0, st>>>(a, a_bf, (int64_t)m * k);
+  f32_to_act16_kernel<<<(unsigned)ceil_div((int64_t)m * k, 256), 256, 0, st>>>(a, a_bf, (int64_t)m * k);
   CNB_LAUNCH_OK();
-  f32_to_bf16_kernel<<<(unsigned)ceil_div((int64_t)n * k, 256), 256, 0, st>>>(w, w_bf, (int64_t)n * k);
+  f32_to_act16_kernel<<<(unsigned)ceil_div((int64_t)n * k, 256), 256, 0, st>>>(w, w_bf, (int64_t)n * k);
   CNB_LAUNCH_OK();
   if (!out_bf16) return launch_gemm_tc<float>(a_bf, w_bf, m, n, k, (Epilogue)epi, ep, out, n, st);
   CNB_REQUIRE(epi != EPI_SCALE_RESID, "the residual epilogue writes fp32");
   WS(h, "dbg_o", act16, (size_t)m * n, o_bf);
   if (int rc = launch_gemm_tc<act16>(a_bf, w_bf, m, n, k, (Epilogue)epi, ep, o_bf, n, st)) return rc;
-  bf16_to_f32_kernel<<<(unsigned)ceil_div((int64_t)m * n, 256), 256, 0, st>>>(o_bf, out, (int64_t)m * n);
+  act16_to_f32_kernel<<<(unsigned)ceil_div((int64_t)m * n, 256), 256, 0, st>>>(o_bf, out, (int64_t)m * n);
   CNB_LAUNCH_OK();
   return 0;
 }
@@ -1447,11 +1482,11 @@ int cnb_debug_mlp_fused(cnb_handle* h, const float* y, const float* w1, const fl
   WS(h, "dbg_y", act16, (size_t)m * 96, y_bf);
   WS(h, "dbg_w1", act16, (size_t)384 * 96, w1_bf);
   WS(h, "dbg_w2", act16, (size_t)96 * 384, w2_bf);
-  f32_to_bf16_kernel<<<(unsigned)ceil_div((int64_t)m * 96, 256), 256, 0, st>>>(y, y_bf, (int64_t)m * 96);
+  f32_to_act16_kernel<<<(unsigned)ceil_div((int64_t)m * 96, 256), 256, 0, st>>>(y, y_bf, (int64_t)m * 96);
   CNB_LAUNCH_OK();
-  f32_to_bf16_kernel<<<(unsigned)ceil_div((int64_t)384 * 96, 256), 256, 0, st>>>(w1, w1_bf, (int64_t)384 * 96);
+  f32_to_act16_kernel<<<(unsigned)ceil_div((int64_t)384 * 96, 256), 256, 0, st>>>(w1, w1_bf, (int64_t)384 * 96);
   CNB_LAUNCH_OK();
-  f32_to_bf16_kernel<<<(unsigned)ceil_div((int64_t)384 * 96, 256), 256, 0, st>>>(w2, w2_bf, (int64_t)384 * 96);
+  f32_to_act16_kernel<<<(unsigned)ceil_div((int64_t)384 * 96, 256), 256, 0, st>>>(w2, w2_bf, (int64_t)384 * 96);
   CNB_LAUNCH_OK();
   return launch_mlp_fused_c96(y_bf, w1_bf, w2_bf, b1, b2, scale, x, m, st);
 }

@@ -404,8 +404,8 @@ __device__ __forceinline__ void tc_gemm(CSmem<NR>& S, const ClusterArgs& a, Pipe
             const uint32_t d = tb + (uint32_t)((slot0 + t) * 2 * NR);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-              tcgen05_mma_bf16(d, a1 + 2 * k, bdesc + 2 * k, idesc_hl, k != 0);
-              tcgen05_mma_bf16(d + NR, a2 + 2 * k, bdesc + 2 * k, idesc_l, 1u);
+              tcgen05_mma_f16(d, a1 + 2 * k, bdesc + 2 * k, idesc_hl, k != 0);
+              tcgen05_mma_f16(d + NR, a2 + 2 * k, bdesc + 2 * k, idesc_l, 1u);
             }
             tcgen05_commit(smem_addr(&S.tile_full[slot0 + t]));
           }
@@ -417,8 +417,8 @@ __device__ __forceinline__ void tc_gemm(CSmem<NR>& S, const ClusterArgs& a, Pipe
             const uint64_t bdesc = make_smem_desc(b_addr + c * (2 * NR * 128));
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              tcgen05_mma_bf16(d, a1 + 2 * k, bdesc + 2 * k, idesc_hl, (c | k) != 0);
-              tcgen05_mma_bf16(d + NR, a2 + 2 * k, bdesc + 2 * k, idesc_l, 1u);
+              tcgen05_mma_f16(d, a1 + 2 * k, bdesc + 2 * k, idesc_hl, (c | k) != 0);
+              tcgen05_mma_f16(d + NR, a2 + 2 * k, bdesc + 2 * k, idesc_l, 1u);
             }
           }
           tcgen05_commit(smem_addr(&S.tile_full[slot0]));
@@ -429,8 +429,8 @@ __device__ __forceinline__ void tc_gemm(CSmem<NR>& S, const ClusterArgs& a, Pipe
           const uint64_t bdesc = make_smem_desc(b_addr + c * (2 * NR * 128));
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            tcgen05_mma_bf16(d, a1 + 2 * k, bdesc + 2 * k, idesc_hl, (c | k) != 0);
-            tcgen05_mma_bf16(d + NR, a2 + 2 * k, bdesc + 2 * k, idesc_l, 1u);
+            tcgen05_mma_f16(d, a1 + 2 * k, bdesc + 2 * k, idesc_hl, (c | k) != 0);
+            tcgen05_mma_f16(d + NR, a2 + 2 * k, bdesc + 2 * k, idesc_l, 1u);
           }
           if (c == 3) tcgen05_commit(smem_addr(&S.tile_full[slot0 + t]));
         }

@@ -211,8 +211,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k) {
               // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in (addr >> 4) units
-              if (PAIR) tcgen05_mma_bf16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-              else tcgen05_mma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              if (PAIR) tcgen05_mma_f16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              else tcgen05_mma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
             }
             if (PAIR) {  // one arrival on the barrier at this offset in both CTAs
               tcgen05_commit_pair(ubars + 8u * (kStages + s));
@@ -471,7 +471,7 @@ static int make_map_uncached(CUtensorMap* map, const void* ptr, uint64_t rows, u
 }
 
 // 2-D row-major bf16 tensor, box = (box_rows, box_cols) with box_cols * 2 bytes == the swizzle span (64 or 128 bytes)
-int tc_make_map_bf16_box(void* map_out, const void* ptr, int64_t rows, int64_t cols, int box_rows, int box_cols) {
+int tc_make_map_f16_box(void* map_out, const void* ptr, int64_t rows, int64_t cols, int box_rows, int box_cols) {
   CNB_REQUIRE(g_encode != nullptr, "gemm_tc_init() was not called");
   CNB_REQUIRE(box_cols == 32 || box_cols == 64, "bf16 box must span 64 or 128 bytes");
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -541,6 +541,7 @@ static int launch_cfg(const act16* a, const act16* w, int m, int n, int k, const
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     CNB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, map_a, map_w, map_out, map_resid, m, n, k, ep));
+    CNB_LAUNCH_OK();
     return 0;
   }
   const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;

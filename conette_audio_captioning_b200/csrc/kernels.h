@@ -87,7 +87,7 @@ int gemm_tc_init();  // resolves cuTensorMapEncodeTiled; returns 0 on success
 int tc_make_map(void* map_out, const void* ptr, int64_t rows, int64_t cols, int box_rows, int elt_bytes);
 
 // 2-D row-major bf16 tensor map with an explicit box: box_cols 64 -> 128B swizzle, 32 -> 64B swizzle
-int tc_make_map_bf16_box(void* map_out, const void* ptr, int64_t rows, int64_t cols, int box_rows, int box_cols);
+int tc_make_map_f16_box(void* map_out, const void* ptr, int64_t rows, int64_t cols, int box_rows, int box_cols);
 // 4-D NHWC fp32 tensor map, box (box_c, box_w, 1, 1), no swizzle, zero OOB fill (used by the depthwise-conv ring loader)
 int tc_make_map_nhwc_f32(void* map_out, const float* ptr, int batch, int h, int w, int c, int box_c, int box_w);
 // TMA-ring depthwise 7x7 + LayerNorm (dwconv_ring.cu); returns 1 when (C, W) has no instantiation (caller falls back)

@@ -78,7 +78,7 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int x, i
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D (tmem) (+)= A (tmem: row = lane, two bf16 per 32-bit column, K-major) . B (smem descriptor)^T
-__device__ __forceinline__ void tcgen05_mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void tcgen05_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
                                                     uint32_t accumulate) {
   asm volatile(
       "{\n"
@@ -236,13 +236,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_y0, const __grid_consta
             const uint64_t adesc = make_smem_desc(sb + kOffA0);
             const uint64_t bdesc = make_smem_desc(sb + kOffW1a + hf * (kN1 * 128));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tcgen05_mma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc1, k != 0);
+            for (int k = 0; k < 4; ++k) tcgen05_mma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc1, k != 0);
           }
           {
             const uint64_t adesc = make_smem_desc_sw64(sb + kOffA1);
             const uint64_t bdesc = make_smem_desc_sw64(sb + kOffW1b + hf * (kN1 * 64));
 #pragma unroll
-            for (int k = 0; k < 2; ++k) tcgen05_mma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc1, 1u);
+            for (int k = 0; k < 2; ++k) tcgen05_mma_f16(d, adesc + 2 * k, bdesc + 2 * k, idesc1, 1u);
           }
           tcgen05_commit(ubars + 64 + 8u * hf);   // d1_full(hf)
           if (hf == 1) tcgen05_commit(ubars + 16);  // a_empty: the last GEMM1 of the tile has been issued
@@ -269,7 +269,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_y0, const __grid_consta
             const uint64_t bdesc = make_smem_desc(sb + kOffW2 + j * (kC * 128));
 #pragma unroll
             for (int k = 0; k < 4; ++k)   // k-steps 0,1 come from the columns written by the half-0 warps, 2,3 from half 1
-              tcgen05_mma_bf16_ts(tb + kTmemO, tb + (uint32_t)(j * kCh + (k >> 1) * 32 + (k & 1) * 8), bdesc + 2 * k, idesc2,
+              tcgen05_mma_f16_ts(tb + kTmemO, tb + (uint32_t)(j * kCh + (k >> 1) * 32 + (k & 1) * 8), bdesc + 2 * k, idesc2,
                                   (j | k) != 0);
             if (j == kNCh - 1) tcgen05_commit(ubars + 24);   // o_full
           }
@@ -380,10 +380,10 @@ int launch_mlp_fused_c96(const act16* y, const act16* w1, const act16* w2, const
                          const float* scale, float* x, int m, cudaStream_t stream) {
   if (m == 0) return 0;
   CUtensorMap map_y0, map_y1, map_w1a, map_w1b, map_w2, map_x;
-  if (int rc = tc_make_map_bf16_box(&map_y0, y, m, kC, kBM, 64)) return rc;
-  if (int rc = tc_make_map_bf16_box(&map_y1, y, m, kC, kBM, 32)) return rc;
-  if (int rc = tc_make_map_bf16_box(&map_w1a, w1, kHid, kC, 192, 64)) return rc;
-  if (int rc = tc_make_map_bf16_box(&map_w1b, w1, kHid, kC, 192, 32)) return rc;
+  if (int rc = tc_make_map_f16_box(&map_y0, y, m, kC, kBM, 64)) return rc;
+  if (int rc = tc_make_map_f16_box(&map_y1, y, m, kC, kBM, 32)) return rc;
+  if (int rc = tc_make_map_f16_box(&map_w1a, w1, kHid, kC, 192, 64)) return rc;
+  if (int rc = tc_make_map_f16_box(&map_w1b, w1, kHid, kC, 192, 32)) return rc;
   if (int rc = tc_make_map(&map_w2, w2, kC, kHid, kC, 2)) return rc;
   if (int rc = tc_make_map(&map_x, x, m, kC, kBM, 4)) return rc;
   static bool attr_set = false;

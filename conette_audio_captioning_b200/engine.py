@@ -55,7 +55,11 @@ class Engine:
         dtype_code = {torch.float32: _lib.DTYPE_F32, torch.int64: _lib.DTYPE_I64, torch.bool: _lib.DTYPE_BOOL,
                       torch.uint8: _lib.DTYPE_U8}
         for name, t in state_dict.items():
-            if not isinstance(t, Tensor) or t.dtype not in dtype_code:
+            if not isinstance(t, Tensor):
+                continue
+            if t.dtype in (torch.float16, torch.bfloat16, torch.float64):  # checkpoints stored in another float type
+                t = t.to(torch.float32)
+            if t.dtype not in dtype_code:
                 continue
             t = t.detach().to("cpu").contiguous()
             shape = (C.c_int64 * max(t.ndim, 1))(*t.shape)

@@ -15,8 +15,7 @@ from torch import Size, Tensor
 from .config import CoNeTTEConfig
 from .engine import Engine
 from .preprocessor import load_resample
-from .synth import make_forbid_rep_mask
-from .tokenizer import IdTokenizer
+from .tokenizer import IdTokenizer, make_forbid_rep_mask
 
 
 class CoNeTTEModel:
@@ -38,7 +37,12 @@ class CoNeTTEModel:
         vocab = tokenizer.get_vocab_size()
         if state_dict["model.decoder.classifier.weight"].shape[0] != vocab:
             raise ValueError("vocabulary size does not match decoder.classifier.weight")
+        if isinstance(device, str) and device in ("cuda_if_available", "auto"):  # torchoutil get_device (reference model.py:60)
+            device = "cuda"
         dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        if dev.type != "cuda":
+            raise ValueError(f"Invalid argument device={device!r}. (conette_b200 runs on a CUDA device of compute capability 10.x "
+                             "only; there is no CPU path)")
         self.engine = Engine(state_dict, vocab, dev.index or 0, precision, enc_chunk, decoder)
         self.task_id_to_token_id = state_dict["model.task_id_to_token_id"].to("cpu", torch.int64)
         fm = state_dict.get("model.forbid_rep_mask")
@@ -73,6 +77,17 @@ class CoNeTTEModel:
             return self.forbid_rep_mask
         mask = make_forbid_rep_mask(self._itos, forbid_rep_mode)  # raises ValueError on unknown modes
         return None if mask is None else mask.to(torch.uint8)
+
+    @staticmethod
+    def _check_limits(beam: int, max_len: int, n_caps: int = 1) -> None:
+        """The CUDA library's hard limits (include/conette_b200.h CNB_MAX_BEAM / CNB_MAX_PRED_SIZE); the reference accepts any
+        value, so exceeding them is reported as a ValueError that names the supported range."""
+        if beam > 8:
+            raise ValueError(f"Invalid argument beam_size={beam}. (conette_b200 supports beam_size in [1, 8])")
+        if not 1 <= max_len <= 64:
+            raise ValueError(f"Invalid argument max_pred_size={max_len}. (conette_b200 supports max_pred_size in [1, 64])")
+        if not 1 <= n_caps <= 8:
+            raise ValueError(f"Invalid number of captions per clip {n_caps}. (conette_b200 scores 1 to 8 captions per clip)")
 
     # ---- forward (reference model.py:185-261) ----------------------------------------------------------------------------
     def __call__(
@@ -118,6 +133,7 @@ class CoNeTTEModel:
         max_len = self.config.max_pred_size if max_pred_size is None else max_pred_size
         assert beam > 0  # reference beam.py:57-58
         assert min_len >= 0
+        self._check_limits(beam, max_len)
         forbid = self._forbid_mask(forbid_rep_mode)
 
         if preprocess and wav.device.type == "cpu":
@@ -186,6 +202,7 @@ class CoNeTTEModel:
                 raise ValueError(f"Invalid argument tasks={tasks}. (task {t} is not in {self.config.task_names})")
         parts = [t.split("_") for t in tasks]
         bos_ids = self._task_token_ids([p[0] for p in parts], ["_".join(p[1:]) if len(p) >= 2 else None for p in parts])
+        self._check_limits(1, max(int(caps.shape[2]) - 1, 1), int(caps.shape[1]))
         caps = caps.to("cpu", torch.int64).clone()
         caps[:, :, 0] = bos_ids.to("cpu")[:, None]
         if preprocess:
@@ -231,6 +248,7 @@ class CoNeTTEModel:
         min_len = self.config.min_pred_size if min_pred_size is None else min_pred_size
         max_len = self.config.max_pred_size if max_pred_size is None else max_pred_size
         assert beam > 0 and min_len >= 0
+        self._check_limits(beam, max_len)
         forbid = self._forbid_mask(forbid_rep_mode)
         if wav.device.type == "cpu":
             return ("host", self.engine.caption_host_begin(wav, x_lens, bos_ids, forbid, beam, min_len, max_len, with_tags=True), tasks)

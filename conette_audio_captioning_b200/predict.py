@@ -69,7 +69,7 @@ def main_predict(argv: Optional[Sequence[str]] = None) -> List[Dict[str, str]]:
     path = args.model_path if args.model_path is not None else args.model_name
     if path is None:
         raise ValueError(f"Invalid arguments {args.model_name=} and {args.model_path=}. (expected at one str value)")
-    device = 0 if args.device in ("cuda_if_available", "cuda", "auto") else args.device
+    device = args.device  # "cuda_if_available" (the reference default) resolves to cuda:0; anything but CUDA raises ValueError
     model = conette(path, model_kwds=dict(device=device, precision=args.precision))
     tasks = args.task
     if tasks is not None and len(tasks) == 1:

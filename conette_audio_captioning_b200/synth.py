@@ -57,20 +57,7 @@ def make_itos(n_words: int = 4000, task_names: Sequence[str] = TASK_NAMES) -> Li
     return list(SPECIAL_TOKENS) + words + [f"<bos_{t}>" for t in task_names]
 
 
-def make_forbid_rep_mask(itos: Sequence[str], mode: str = "content_words", stopwords: Sequence[str] | None = None) -> Tensor | None:
-    """Host mirror of reference ``get_forbid_rep_mask`` (pl_modules/common.py:222-299)."""
-    if mode == "none":
-        return None
-    if mode == "all":
-        return torch.ones(len(itos), dtype=torch.bool)
-    if mode == "content_words":
-        if stopwords is None:
-            from .tokenizer import ENGLISH_STOPWORDS as stopwords  # noqa: N811
-        sw = set(stopwords)
-        return torch.tensor([tok not in sw for tok in itos], dtype=torch.bool)
-    raise ValueError(
-        f"Invalid argument forbid_rep_mode={mode!r}. (expected one of ('none', 'all', 'content_words'))"
-    )
+from .tokenizer import make_forbid_rep_mask  # noqa: E402,F401  (product code lives in tokenizer.py; kept here for the tests)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

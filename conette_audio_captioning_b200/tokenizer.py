@@ -119,3 +119,19 @@ class IdTokenizer:
         if all(len(s) == 0 or not isinstance(s[0], (list, tuple)) for s in nested):
             return self.decode_batch(nested)
         return [self.decode_rec(s) for s in nested]
+
+
+def make_forbid_rep_mask(itos: Sequence[str], mode: str = "content_words", stopwords: "Sequence[str] | None" = None) -> "Tensor | None":
+    """Host mirror of reference ``get_forbid_rep_mask`` (pl_modules/common.py:222-299)."""
+    if mode == "none":
+        return None
+    if mode == "all":
+        return torch.ones(len(itos), dtype=torch.bool)
+    if mode == "content_words":
+        if stopwords is None:
+            stopwords = ENGLISH_STOPWORDS
+        sw = set(stopwords)
+        return torch.tensor([tok not in sw for tok in itos], dtype=torch.bool)
+    raise ValueError(
+        f"Invalid argument forbid_rep_mode={mode!r}. (expected one of ('none', 'all', 'content_words'))"
+    )

@@ -47,6 +47,10 @@ typedef struct cnb_config {
 } cnb_config;
 
 enum { CNB_PRECISION_FAST = 0, CNB_PRECISION_PARITY = 1 };
+/* Hard limits of the decode entry points (the reference accepts any value; these cover its configurations: beam 2/3/5,
+ * max_pred_size 20/30).  Violations return -1 with a message naming the limit. */
+#define CNB_MAX_BEAM 8        /* beam_size, and captions per clip of cnb_score_captions */
+#define CNB_MAX_PRED_SIZE 64  /* max_pred_size */
 enum { CNB_DTYPE_F32 = 0, CNB_DTYPE_I64 = 1, CNB_DTYPE_BOOL = 2, CNB_DTYPE_U8 = 3 };
 /* encoder tap points for stage-isolated parity (cnb_encoder_tap): activation returned as fp32, NHWC */
 enum { CNB_TAP_LOGMEL_BN = 0, CNB_TAP_STEM = 1, CNB_TAP_BLOCK = 2, CNB_TAP_DOWN = 3, CNB_TAP_DWLN = 4 };

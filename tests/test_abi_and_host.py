@@ -125,3 +125,19 @@ def test_batched_detokenise_equals_the_regex_pipeline():
     ids = torch.randint(0, odd.get_vocab_size(), (400, 12), generator=g)
     assert odd.decode_rec(ids) == odd.decode_rec(ids.tolist())
     assert odd.decode_rec(torch.tensor([[4, 2, 0, 0]])) == ["rain"] and odd.decode_rec(torch.tensor([[0, 0]])) == [""]
+
+
+def test_wrapper_rejects_unsupported_arguments_before_touching_the_gpu():
+    """a CPU device must not silently become cuda:0, and values beyond the CUDA library's limits (beam <= 8,
+    max_pred_size <= 64, <= 8 captions per clip) must surface as a ValueError naming the range, not as a generic C-ABI error."""
+    import pytest
+
+    from conette_audio_captioning_b200 import CoNeTTEModel, synth
+
+    sd = {"model.decoder.classifier.weight": __import__("torch").zeros(318, 256)}
+    with pytest.raises(ValueError, match="CUDA device"):
+        CoNeTTEModel(None, sd, synth.make_itos(300), device="cpu")
+    CoNeTTEModel._check_limits(8, 64, 8)
+    for bad in ((9, 20, 1), (3, 65, 1), (3, 0, 1), (3, 20, 9)):
+        with pytest.raises(ValueError, match="supports|scores"):
+            CoNeTTEModel._check_limits(*bad)

@@ -66,12 +66,17 @@ def _worker(rank, world, port, ret):
         wav = torch.zeros(b, 8)  # placeholder: the fake runner works from `mem`
         lo_hi = shard_bounds(b, rank, world)
         out = caption_sharded(_oracle_shard_runner(sd, mem, lens, beam, max_len, lo_hi), wav, lens, bos, beam, max_len)
+        # fewer clips than ranks: rank 1's slice is empty, it must still join the (single) collective
+        one = caption_sharded(_oracle_shard_runner(sd, mem[:1], lens[:1], beam, max_len, shard_bounds(1, rank, world)), wav[:1],
+                              lens[:1], bos[:1], beam, max_len)
         if rank == 0:
             from oracle import restate
 
             ref = restate.beam_search(sd, mem, lens, bos, beam, 3, max_len, sd["model.forbid_rep_mask"])
             ok = all(torch.equal(a, r) if a.dtype == torch.long else torch.allclose(a, r, atol=1e-6) for a, r in zip(out, ref))
-            ret.put(bool(ok) and all(a.shape == r.shape for a, r in zip(out, ref)))
+            ref1 = restate.beam_search(sd, mem[:1], lens[:1], bos[:1], beam, 3, max_len, sd["model.forbid_rep_mask"])
+            ok1 = all(torch.equal(a, r) if a.dtype == torch.long else torch.allclose(a, r, atol=1e-6) for a, r in zip(one, ref1))
+            ret.put(bool(ok) and bool(ok1) and all(a.shape == r.shape for a, r in zip(out, ref)))
     finally:
         dist.destroy_process_group()
 

@@ -69,3 +69,34 @@ def test_model_stream_equals_calls(sd):
         assert list(model.stream([])) == []
     finally:
         model.engine.close()
+
+
+def test_stream_with_mixed_sample_rates(sd):
+    """A 32 kHz batch goes through the split-phase host path (the handle's own streams), a 44.1 kHz batch is resampled on the
+    GPU and goes through the device-buffer path (torch's stream); both use the same workspaces, so the library orders them
+    (dev_enter / dev_leave in csrc/api.cu).  Alternating the two -- and interleaving unrelated engine calls between a yield and
+    the next collect -- must give exactly what one call per batch gives."""
+    from conette_audio_captioning_b200 import CoNeTTEModel
+
+    model = CoNeTTEModel(None, sd, synth.make_itos(300), precision="fast")
+    try:
+        specs = [(16, 48000, 32000), (16, 66150, 44100), (16, 48000, 32000), (3, 44100, 44100), (17, 40000, 32000),
+                 (16, 48000, 32000), (2, 70000, 44100)]
+        xs = [synth.make_audio(b, n, seed=90 + i) for i, (b, n, _) in enumerate(specs)]
+        srs = [s for _, _, s in specs]
+        want = [model(x, sr=s, task="clotho") for x, s in zip(xs, srs)]
+        for rep in range(3):  # the race, when present, is timing dependent
+            got, pending = [], None
+            for i, (x, s) in enumerate(zip(xs, srs)):
+                nxt = model._begin(x, s, "clotho")
+                if i % 2 == 0:  # unrelated device-path work while a host batch may be in flight
+                    model.engine.encoder(xs[0][:2, 0].cuda(), with_tags=False)
+                if pending is not None:
+                    got.append(model._finish(pending, 0.3))
+                pending = nxt
+            got.append(model._finish(pending, 0.3))
+            for a, c in zip(want, got):
+                assert torch.equal(a["preds"], c["preds"]) and torch.equal(a["mult_preds"], c["mult_preds"]), rep
+                assert torch.equal(a["lprobs"], c["lprobs"]) and torch.equal(a["tags_probs"], c["tags_probs"]), rep
+    finally:
+        model.engine.close()
