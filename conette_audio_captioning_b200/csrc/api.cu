@@ -76,6 +76,7 @@ struct cnb_handle {
   cnb_config cfg;
   std::map<std::string, HostTensor> staged;
   bool finalized = false;
+  bool has_encoder = true;  // false: only the projection + decoder were loaded (BaselinePLM, precomputed embeddings)
   Arena arena;
   // encoder
   FrontendParams fe;
@@ -259,8 +260,11 @@ static int finalize(cnb_handle* h) {
   CNB_CUDA_OK(cudaMalloc(&h->arena.base, h->arena.cap));
   CNB_CUDA_OK(cudaMemset(h->arena.base, 0, h->arena.cap));
 
+  // A state dict without the audio encoder (reference BaselinePLM, pl_modules/baseline.py:35: FrameIdentEncoder + projection +
+  // decoder on precomputed frame embeddings) loads the decoder half only; the waveform entry points then refuse to run.
+  h->has_encoder = h->staged.count(E + "bn0.weight") != 0;
   // ---- front-end: analytic twiddles; the checkpoint's DFT basis must be the Hann-windowed DFT
-  {
+  if (h->has_encoder) {
     GET(cr, E + "spectrogram_extractor.stft.conv_real.weight", kBins, 1, kNfft);
     GET(ci, E + "spectrogram_extractor.stft.conv_imag.weight", kBins, 1, kNfft);
     double max_err = 0;
@@ -365,7 +369,7 @@ static int finalize(cnb_handle* h) {
     h->fe.bn_scale = dsc; h->fe.bn_shift = dsh; h->fe.ones = dones; h->fe.zeros = dzeros;
   }
   // ---- stem
-  {
+  if (h->has_encoder) {
     GET(w, E + "downsample_layers.0.0.weight", 96, 1, 4, 4);
     GET(b, E + "downsample_layers.0.0.bias", 96);
     GET(g, E + "downsample_layers.0.1.weight", 96);
@@ -376,7 +380,7 @@ static int finalize(cnb_handle* h) {
     PUT(h->stem_w_t, wt); PUT(h->stem_b, b->data); PUT(h->stem_ln_g, g->data); PUT(h->stem_ln_b, be->data);
   }
   // ---- downsample layers 1..3: LN(cf) + Conv2d(k=2,s=2); weight reordered to (Cout, kh, kw, Cin)
-  for (int i = 1; i < 4; ++i) {
+  for (int i = 1; i < 4 && h->has_encoder; ++i) {
     const int cin = kDims[i - 1], cout = kDims[i];
     const std::string p = E + "downsample_layers." + std::to_string(i) + ".";
     GET(g, p + "0.weight", cin);
@@ -393,7 +397,7 @@ static int finalize(cnb_handle* h) {
     PUT(d.ln_g, g->data); PUT(d.ln_b, be->data); PUT(d.bias, b->data); PUT(d.w, wr); PUT_BF(d.w_bf, wr);
   }
   // ---- blocks
-  {
+  if (h->has_encoder) {
     int bi = 0;
     for (int s = 0; s < 4; ++s)
       for (int j = 0; j < kDepths[s]; ++j, ++bi) {
@@ -418,7 +422,7 @@ static int finalize(cnb_handle* h) {
       }
   }
   // ---- clip head
-  {
+  if (h->has_encoder) {
     GET(g, E + "norm.weight", 768);
     GET(be, E + "norm.bias", 768);
     GET(w, E + "head_audioset.weight", kTags, 768);
@@ -1122,6 +1126,9 @@ int cnb_geometry(int64_t n_samples, int32_t* n_stft_frames, int32_t stage_height
   return 0;
 }
 
+#define CHECK_ENCODER(h) \
+  CNB_REQUIRE((h)->has_encoder, "this handle holds no audio encoder weights (decoder-only state dict): use cnb_decode / cnb_score_captions")
+
 static int check_audio(int32_t batch, int64_t n) {
   CNB_REQUIRE(batch > 0, "empty batch");
   CNB_REQUIRE(n > 512, "clips must be longer than the 512-sample reflect padding");
@@ -1142,6 +1149,7 @@ int cnb_resample(cnb_handle* h, const float* wav_in, const int64_t* lens_in, int
 
 int cnb_frontend(cnb_handle* h, const float* wav, int32_t batch, int64_t n, int32_t apply_bn, float* out, void* stream) {
   CHECK_READY(h);
+  CHECK_ENCODER(h);
   CNB_REQUIRE(wav && out, "null buffer");
   CNB_REQUIRE(batch > 0 && n > 512, "bad audio shape");
   return launch_frontend(wav, batch, n, h->fe, apply_bn != 0, out, (cudaStream_t)stream);
@@ -1150,6 +1158,7 @@ int cnb_frontend(cnb_handle* h, const float* wav, int32_t batch, int64_t n, int3
 int cnb_encoder(cnb_handle* h, const float* wav, int32_t batch, int64_t n, float* frame_embs_out, float* clip_probs_out,
                 void* stream) {
   CHECK_READY(h);
+  CHECK_ENCODER(h);
   CNB_REQUIRE(wav && frame_embs_out, "null buffer");
   if (int rc = check_audio(batch, n)) return rc;
   DEV_SCOPE(h, (cudaStream_t)stream, encode(h, wav, batch, n, frame_embs_out, clip_probs_out, (cudaStream_t)stream));
@@ -1158,6 +1167,7 @@ int cnb_encoder(cnb_handle* h, const float* wav, int32_t batch, int64_t n, float
 int cnb_encoder_tap(cnb_handle* h, const float* wav, int32_t batch, int64_t n, int32_t tap_kind, int32_t stage, int32_t block,
                     float* out, int64_t cap, void* stream) {
   CHECK_READY(h);
+  CHECK_ENCODER(h);
   CNB_REQUIRE(wav && out, "null buffer");
   if (int rc = check_audio(batch, n)) return rc;
   CNB_REQUIRE(batch <= chunk_size(h), "tap batch must fit one encoder chunk");
@@ -1273,6 +1283,7 @@ static int caption_impl(cnb_handle* h, const float* wav, const int64_t* x_lens_h
                         int64_t* mult_preds, float* mult_lprobs, int32_t* info, float* clip_probs, cudaStream_t st,
                         cudaStream_t st_dec, int slot) {
   CHECK_READY(h);
+  CHECK_ENCODER(h);
   CNB_REQUIRE(wav && bos_ids && preds && lprobs && mult_preds && mult_lprobs && info, "null buffer");
   if (int rc = check_audio(batch, n)) return rc;
   const Geometry g = geometry(n);
@@ -1321,6 +1332,7 @@ int cnb_caption_host_begin(cnb_handle* h, const float* wav_host, const int64_t* 
                            int64_t* preds_host, float* lprobs_host, int64_t* mult_preds_host, float* mult_lprobs_host,
                            int32_t* info_host, float* clip_probs_host, int32_t* ticket_out) {
   CHECK_READY(h);
+  CHECK_ENCODER(h);
   CNB_REQUIRE(wav_host && bos_ids_host && preds_host && lprobs_host && mult_preds_host && mult_lprobs_host && info_host &&
                   ticket_out,
               "null buffer");

@@ -64,7 +64,56 @@ def make_score_fixture(sd, model) -> None:
                         losses=losses.numpy(), token_lprobs=tok_lp.numpy(), weights_checksum=checksum(sd))
 
 
+def make_baseline_fixture(sd) -> None:
+    """baseline.npz: the REAL ``BaselinePLM`` (pl_modules/baseline.py:35; beam 3, min 3, max 12) loaded with the projection +
+    decoder of the synthetic state dict, on given frame embeddings: ``forward(batch, "generate")``, ``"greedy"`` and
+    ``"forcing"`` outputs.  Note BaselinePLM's vocabulary has no task tokens: V = 311 = rows 0..310 of the CoNeTTE tensors."""
+    tok_mod = ref_loader.ref_module("tokenization.aac_tokenizer")
+    base_mod = ref_loader.ref_module("pl_modules.baseline")
+    tokenizer = tok_mod.AACTokenizer()
+    tokenizer.fit(list(synth.make_corpus(300)))
+    plm = base_mod.BaselinePLM(train_tokenizer=tokenizer, beam_size=3, min_pred_size=3, max_pred_size=12)
+    v = tokenizer.get_vocab_size()
+    own = plm.state_dict()
+    with torch.no_grad():
+        for k, dst in list(plm.named_parameters()) + list(plm.named_buffers()):
+            if k == "forbid_rep_mask":
+                continue
+            src = sd["model." + k]
+            if src.shape != dst.shape:  # vocabulary-sized tensors: BaselinePLM has no <bos_task> rows
+                src = src[:v]
+            dst.copy_(src)
+    plm.eval()
+    assert set(own) >= {"decoder.classifier.weight", "projection.2.weight"}
+    g = torch.Generator().manual_seed(123)
+    b, tp, cap_len = 5, 9, 10
+    fe = torch.randn(b, tp, 768, generator=g)
+    lens = torch.tensor([9, 4, 7, 1, 9])
+    audio_shape = torch.stack([torch.full((b,), 768), lens], dim=1)
+    caps = torch.zeros(b, cap_len, dtype=torch.long)
+    for i in range(b):
+        n_words = cap_len - 2 if i == 0 else int(torch.randint(1, cap_len - 2, (1,), generator=g))
+        caps[i, 0] = 1
+        caps[i, 1 : 1 + n_words] = torch.randint(4, 300, (n_words,), generator=g)
+        caps[i, 1 + n_words] = 2
+    batch = {"audio": fe, "audio_shape": audio_shape, "captions": caps}
+    with torch.no_grad():
+        gen = plm(batch, "generate")
+        greedy = plm(batch, "greedy")
+        forcing = plm(batch, "forcing")
+    np.savez_compressed(
+        os.path.join(GOLDEN, "baseline.npz"), frame_embs=fe.numpy(), lens=lens.numpy(), captions=caps.numpy(), vocab=np.array(v),
+        forbid_rep_mask=plm.forbid_rep_mask.numpy(), cands=np.array(gen["cands"]), preds=gen["preds"].numpy(),
+        lprobs=gen["lprobs"].numpy(), mult_preds=gen["mult_preds"].numpy(), mult_lprobs=gen["mult_lprobs"].numpy(),
+        greedy_logits=greedy.numpy().astype(np.float32), forcing_logits=forcing.numpy().astype(np.float32),
+        weights_checksum=checksum(sd))
+
+
 def main() -> None:
+    if "--only-baseline" in sys.argv:  # added in round 2: leaves the other fixtures untouched
+        torch.manual_seed(0)
+        make_baseline_fixture(synth.make_state_dict(**SD_KW))
+        return
     if "--only-score" in sys.argv:  # added after the other fixtures were committed: leaves them untouched
         torch.manual_seed(0)
         sd = synth.make_state_dict(**SD_KW)
@@ -140,6 +189,7 @@ def main() -> None:
         tags_probs=out["tags_probs"].numpy(), weights_checksum=checksum(sd),
     )
     make_score_fixture(sd, model)
+    make_baseline_fixture(sd)
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 
