@@ -71,8 +71,30 @@ struct CCand {
   float v;
   int idx;
 };
-__device__ __forceinline__ bool cbetter(const CCand& a, const CCand& b) {
-  return a.v > b.v || (a.v == b.v && a.idx < b.idx);
+// order of candidates: higher value first, ties -> lower index (torch.topk is unspecified on ties; the oracle's margins cover it)
+
+// The same order as one unsigned 64-bit comparison (no branches): key(a) > key(b) <=> cbetter(a, b).  High word = the float mapped
+// monotonically onto unsigned integers, low word = 0x7fffffff - idx (ties -> lower index).  NaN scores and the "nothing" sentinel
+// (idx = 0x7fffffff) map to key 0, below every real candidate (-inf maps to 0x007fffff in the high word).
+__device__ __forceinline__ unsigned long long ckey(float v, int idx) {
+  uint32_t u = __float_as_uint(v);
+  u ^= (u >> 31) ? 0xffffffffu : 0x80000000u;
+  const bool none = (v != v) || idx == 0x7fffffff;
+  return none ? 0ull : ((unsigned long long)u << 32) | (uint32_t)(0x7fffffff - idx);
+}
+__device__ __forceinline__ CCand ckey_decode(unsigned long long k) {
+  if (k == 0ull) return CCand{-INFINITY, 0x7fffffff};
+  uint32_t u = (uint32_t)(k >> 32);
+  u ^= (u >> 31) ? 0x80000000u : 0xffffffffu;
+  return CCand{__uint_as_float(u), 0x7fffffff - (int)(uint32_t)k};
+}
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long k) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, k, o);
+    k = other > k ? other : k;
+  }
+  return k;
 }
 
 // ---- DSMEM push with receiver-side completion ------------------------------------------------------------------------
@@ -142,6 +164,7 @@ template <int NR> struct CSmem {
   float st_stat[NR][2];                              // running max / sum-exp of this CTA's vocabulary slice
   CCand st_cnd[NR][kCMaxBeam];                       // running best words of this CTA's vocabulary slice (by logit)
   CCand win[kCWarps][kCMaxBeam];
+  int2 winj[kCWarps][kCMaxBeam];                     // (previous beam position, word) of every winner
   uint16_t tokens[2][NR][kCMaxLen + 2];
   uint8_t src[2][NR][kCMaxLen];                      // local row holding position p of this row's history (beam back-pointers)
   float sum_lp[NR];
@@ -182,6 +205,18 @@ __device__ __forceinline__ void attend(const float* const (&q)[NRW], const int (
                                        VPtr vptr, const float* const (&kv_new)[NRW], bool has_new, uint8_t* opa,
                                        const int (&out_row)[NRW], int lane, int tpad = 0) {
   float sc[NRW][NCH];
+  // one row x one chunk per warp (10 s clips in 16-row clusters): the value rows are requested together with the keys, so the
+  // phase costs one L2 round trip instead of two (the addresses do not depend on the scores)
+  constexpr bool kHoist = NRW * NCH == 1;
+  float4 vh[kHoist ? 8 : 1];
+  if (kHoist) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = (lane >> 3) + 4 * u;
+      vh[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid[0] && j < n[0]) vh[u] = *reinterpret_cast<const float4*>(vptr(0, j) + 4 * (lane & 7));
+    }
+  }
 #pragma unroll
   for (int rr = 0; rr < NRW; ++rr) {
     float qv[kCHead];
@@ -253,8 +288,12 @@ __device__ __forceinline__ void attend(const float* const (&q)[NRW], const int (
         const int jl = pg + 4 * u;  // key index inside the chunk
         const int j = jl + 32 * ch;
         ww[u] = __shfl_sync(kFull, e[rr][ch], jl);
-        vv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid[rr] && j < n[rr]) vv[u] = *reinterpret_cast<const float4*>(vptr(rr, j) + 4 * dq);
+        if (kHoist) {
+          vv[u] = vh[u];
+        } else {
+          vv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid[rr] && j < n[rr]) vv[u] = *reinterpret_cast<const float4*>(vptr(rr, j) + 4 * dq);
+        }
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
@@ -798,8 +837,11 @@ __device__ __noinline__ void decode_select(CSmem<NR>& S, const ClusterArgs& a, P
       sm = warp_sum(sm);
       if (mx == -INFINITY) sm = 0.f;
       // the previous rounds' list joins as one extra candidate per lane (lane k holds entry k)
-      CCand old{-INFINITY, 0x7fffffff};
-      if (rd > 0 && lane < beam) old = S.st_cnd[r][lane];
+      unsigned long long old_key = 0ull;
+      if (rd > 0 && lane < beam) {
+        const CCand oc = S.st_cnd[r][lane];
+        old_key = ckey(oc.v, oc.idx);
+      }
       float om = -INFINITY, os = 0.f;
       if (rd > 0) {
         om = S.st_stat[r][0];
@@ -813,24 +855,21 @@ __device__ __noinline__ void decode_select(CSmem<NR>& S, const ClusterArgs& a, P
         S.st_stat[r][0] = m2;
         S.st_stat[r][1] = s2;
       }
-      // `beam` rounds of: every lane's best candidate strictly after the previous winner, then a warp arg-max
-      CCand prev{INFINITY, -1};
+      // `beam` rounds of: every lane's best candidate strictly after the previous winner, then a warp arg-max (64-bit keys)
+      unsigned long long keys[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) keys[u] = (base + lane + 32 * u < V) ? ckey(x[u], base + lane + 32 * u) : 0ull;
+      unsigned long long prev = ~0ull;
       for (int k = 0; k < beam; ++k) {
-        CCand best{-INFINITY, 0x7fffffff};
+        unsigned long long best = old_key < prev ? old_key : 0ull;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const CCand cc{x[u], base + lane + 32 * u};
-          if (cc.idx < V && cbetter(cc, best) && cbetter(prev, cc)) best = cc;
+          const unsigned long long c = keys[u] < prev ? keys[u] : 0ull;
+          best = c > best ? c : best;
         }
-        if (old.idx != 0x7fffffff && cbetter(old, best) && cbetter(prev, old)) best = old;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const CCand other{__shfl_xor_sync(kFull, best.v, o), __shfl_xor_sync(kFull, best.idx, o)};
-          if (cbetter(other, best)) best = other;
-        }
-        if (lane == 0) S.st_cnd[r][k] = best;
-        prev = best;
-        if (best.idx == 0x7fffffff) prev = CCand{-INFINITY, 0x7ffffffe};  // exhausted (or NaN logits): keep emitting sentinels
+        best = warp_max_u64(best);
+        if (lane == 0) S.st_cnd[r][k] = ckey_decode(best);
+        prev = best;  // 0 = exhausted (or NaN logits): every later round emits the sentinel too
       }
       __syncwarp();
     }
@@ -915,55 +954,53 @@ __device__ __noinline__ void decode_select(CSmem<NR>& S, const ClusterArgs& a, P
         row_lg[j] = logf(s);
       }
     }
-    // candidates: (used row j, peer i, k) -> value; k_sel rounds of "best candidate strictly after the previous winner"
-    const int n_c = nrows_used * kCl * beam;
-    CCand prev_win{INFINITY, -1};
+    // candidates: lane = (peer i = lane & 7, k in {lane >> 3, (lane >> 3) + 4}) for every used row j; value = cumulative score,
+    // index = j * V + word (beam.py:256-263).  k_sel rounds of "best candidate strictly after the previous winner".
+    const int pi = lane & 7, kg = lane >> 3;
+    unsigned long long prev_key = ~0ull;
     for (int rsel = 0; rsel < k_sel; ++rsel) {
-      CCand best{-INFINITY, 0x7fffffff};
-      for (int ci = lane; ci < n_c; ci += 32) {
-        const int j = ci / (kCl * beam), rem = ci - j * (kCl * beam);
-        const int i = rem / beam, k = rem - i * beam;
-        const int r = r0 + label_at(j);
-        const CCand raw = CND[i][r][k];
-        if (raw.idx == 0x7fffffff) continue;
-        float mxj = 0.f, lgj = 0.f, pv = 0.f;
+      unsigned long long best = 0ull;
 #pragma unroll
-        for (int q = 0; q < kCMaxBeam; ++q)
-          if (q == j) {
-            mxj = row_mx[q];
-            lgj = row_lg[q];
-            pv = prev_sum[q];
+      for (int j = 0; j < kCMaxBeam; ++j) {
+        if (j < nrows_used) {
+          const int r = r0 + label_at(j);
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const int k = kg + 4 * kk;
+            if (k < beam) {
+              const CCand raw = CND[pi][r][k];
+              const float lsm = (raw.v - row_mx[j]) - row_lg[j];
+              unsigned long long c = raw.idx == 0x7fffffff ? 0ull : ckey(step == 0 ? lsm : prev_sum[j] + lsm, j * V + raw.idx);
+              c = c < prev_key ? c : 0ull;
+              best = c > best ? c : best;
+            }
           }
-        const float lsm = (raw.v - mxj) - lgj;
-        const CCand c{step == 0 ? lsm : pv + lsm, j * V + raw.idx};
-        if (cbetter(c, best) && cbetter(prev_win, c)) best = c;
+        }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const CCand other{__shfl_xor_sync(kFull, best.v, o), __shfl_xor_sync(kFull, best.idx, o)};
-        if (cbetter(other, best)) best = other;
+      best = warp_max_u64(best);
+      prev_key = best;
+      CCand w = ckey_decode(best);
+      if (w.idx == 0x7fffffff) w.idx = 0;  // NaN logits (fully masked clip, len 0): stay memory-safe like a no-op pick
+      if (lane == 0) {
+        const int pj = w.idx / V;  // row of the previous beam, word
+        S.win[warp][rsel] = w;
+        S.winj[warp][rsel] = make_int2(pj, w.idx - pj * V);
       }
-      prev_win = best;
-      if (best.idx == 0x7fffffff) {  // NaN logits (fully masked clip, len 0): stay memory-safe like a no-op pick
-        best.idx = 0;
-        prev_win = CCand{-INFINITY, 0x7ffffffe};
-      }
-      if (lane == 0) S.win[warp][rsel] = best;
     }
     __syncwarp();
-    // candidate r -> r-th live label (beam.py:165-176); histories via back-pointers
-    for (int item = lane; item < k_sel * (step + 2); item += 32) {
-      const int r = item / (step + 2), p = item - r * (step + 2);
+    // candidate r -> r-th live label (beam.py:165-176); histories via back-pointers: lane = position
+    for (int r = 0; r < k_sel; ++r) {
       const int row = r0 + label_at(r);
-      const int prev_pos = S.win[warp][r].idx / V;
-      const int word = S.win[warp][r].idx - prev_pos * V;
-      const int srow = r0 + label_at(prev_pos);
-      if (p <= step) {
-        S.tokens[nxt][row][p] = S.tokens[cur][srow][p];
-        if (p < max_len) S.src[nxt][row][p] = S.src[cur][srow][p];
-      } else {
-        S.tokens[nxt][row][p] = (uint16_t)word;
-        if (p < max_len) S.src[nxt][row][p] = (uint8_t)row;
+      const int2 pw = S.winj[warp][r];
+      const int srow = r0 + label_at(pw.x);
+      for (int p = lane; p <= step + 1; p += 32) {
+        if (p <= step) {
+          S.tokens[nxt][row][p] = S.tokens[cur][srow][p];
+          if (p < max_len) S.src[nxt][row][p] = S.src[cur][srow][p];
+        } else {
+          S.tokens[nxt][row][p] = (uint16_t)pw.y;
+          if (p < max_len) S.src[nxt][row][p] = (uint8_t)row;
+        }
       }
     }
     __syncwarp();
@@ -971,8 +1008,7 @@ __device__ __noinline__ void decode_select(CSmem<NR>& S, const ClusterArgs& a, P
       const int r = lane;
       const int row = r0 + label_at(r);
       const CCand w = S.win[warp][r];
-      const int prev_pos = w.idx / V;
-      const int word = w.idx - prev_pos * V;
+      const int word = S.winj[warp][r].y;
       S.sum_lp[row] = w.v;
       if (word == kCEos || step == max_len - 1) {  // beam.py:173-190
         if (rank == 0) {
@@ -1158,7 +1194,7 @@ int cluster_plan(const ClusterArgs& a, ClusterPlan* p) {
   const int mc = nr == 16 ? mc16 : mc32;
   const int gmax = nr / a.beam;
   int g = (int)ceil_div(a.batch, mc);
-  if (g > gmax) g = gmax;
+  if (g > gmax || getenv("CNB_DEC_FILL")) g = gmax;  // CNB_DEC_FILL: experiments with full clusters
   p->nr = nr;
   p->clips_per_group = g;
   p->n_groups = (int)ceil_div(a.batch, g);
