@@ -597,7 +597,7 @@ static int encode_chunk(cnb_handle* h, const float* wav, int nb, int64_t n, floa
         const int64_t n_slab = ceil_div(m, rows_fit > 128 ? rows_fit : 128);
         slab = ceil_div(ceil_div(m, n_slab), 128) * 128;
       }
-      // stage 1, bf16 operands: one kernel for the whole MLP, the hidden tile never leaves the SM (mlp_fused.cu)
+      // stage 1, fp16 operands: one kernel for the whole MLP, the hidden tile never leaves the SM (mlp_fused.cu)
       static const bool fused_ok = getenv("CNB_NO_MLP_FUSED") == nullptr;
       if (sizeof(ActT) == 2 && c == 96 && fused_ok) {
         Prof _p(h, CNB_K_GEMM_PW1_S0 + s, st);

@@ -1,6 +1,6 @@
 // ConvNeXt-Tiny CUDA-core kernels (everything that is not a GEMM): stem, depthwise 7x7 + LayerNorm, downsample
 // LayerNorm + 2x2 im2col pack, frequency mean and the clip (tag) head.  Activations are NHWC; the residual stream is
-// fp32, GEMM operands are OutT (bf16 in fast mode, f32 in parity mode).
+// fp32, GEMM operands are OutT (fp16 in fast mode, f32 in parity mode).
 // Reference: nn/encoders/convnext.py:61-74 (block), :207-217 (stem / downsample), :306-334 (mean + head),
 // nn/modules/norm.py:35-40 (channels_first LayerNorm, biased variance, eps 1e-6).
 #include <algorithm>

@@ -1,14 +1,14 @@
-// bf16 tensor-core GEMM for sm_100a: TMA-fed tcgen05.mma with the accumulator in TMEM and fused epilogues.
-//   out[m,n] = epi( sum_k A[m,k] * W[n,k] ),  A (M,K) bf16 and W (N,K) bf16 both K-major, fp32 accumulation.
+// fp16-operand tensor-core GEMM for sm_100a: TMA-fed tcgen05.mma with the accumulator in TMEM and fused epilogues.
+//   out[m,n] = epi( sum_k A[m,k] * W[n,k] ),  A (M,K) fp16 and W (N,K) fp16 both K-major, fp32 accumulation.
 // This is the ConvNeXt pointwise-MLP / downsample / projection hot loop (reference convnext.py:66-73, :212-217,
 // pl_modules/common.py:71-78), ~92 % of the encoder FLOPs.
 //
 // Structure (persistent, warp-specialised, one CTA per SM):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of A (128 x 64) and W (BLOCK_N x 64) tiles, 128B swizzle
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16, kind::f16, bf16 in / f32 acc)
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16, kind::f16, fp16 in / f32 acc)
 //   warps 2..17 epilogue: tcgen05.ld (32 lanes x 32 columns) -> bias / GELU / layer-scale+residual -> global stores
-//               (GELU in this bf16 path = 0.5x(1+tanh(x(a1+a3x^2+a5x^4))), a minimax fit of the erf form, max abs error
-//               2.5e-5 + the 2^-11 relative error of tanh.approx -- both below the bf16 rounding of the stored hidden)
+//               (GELU in this 16-bit path = 0.5x(1+tanh(x(a1+a3x^2+a5x^4))), a minimax fit of the erf form, max abs error
+//               2.5e-5 + the 2^-11 relative error of tanh.approx -- of the order of the fp16 rounding of the stored hidden)
 // CTA pairs (PAIR = true, large M): two CTAs of a 2-CTA cluster (one TPC) work on one 256 x BLOCK_N tile with
 // tcgen05.mma.cta_group::2 issued by the even CTA.  Each CTA TMA-loads its own 128 rows of A but only HALF of the W tile
 // (BLOCK_N/2 rows), so the L2 -> shared-memory fill per flop drops by 30 % at BLOCK_N = 192 (the fill rate, not the tensor
@@ -34,7 +34,7 @@
 namespace cnb {
 
 constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;  // 64 bf16 = 128 bytes = one swizzle-128B atom row
+constexpr int kBlockK = 64;  // 64 fp16 = 128 bytes = one swizzle-128B atom row
 constexpr int kUmmaK = 16;
 constexpr int kEpiChunk = 16;                      // accumulator columns per tcgen05.ld
 constexpr int kMaxN = 3072;                        // bias / layer-scale vectors are staged in shared memory
@@ -59,12 +59,12 @@ struct TcCfg {
   static constexpr bool kResid = (EPI == EPI_SCALE_RESID) && CNB_PW2_RESID_LOAD;
   static constexpr bool kReduce = (EPI == EPI_SCALE_RESID) && !CNB_PW2_RESID_LOAD;
   static constexpr int kElt = (int)sizeof(OutT);
-  static constexpr int kBoxCols = 128 / kElt;                 // 64 bf16 / 32 fp32 per 128-byte swizzle row
+  static constexpr int kBoxCols = 128 / kElt;                 // 64 fp16 / 32 fp32 per 128-byte swizzle row
   static constexpr int kBoxBytes = kBlockM * 128;             // 16 KB
   static constexpr int kBoxesPerPass = 64 / kBoxCols;         // 1 / 2
   static constexpr int kPassBytes = kBoxesPerPass * kBoxBytes;
   static constexpr int kPasses = (BLOCK_N + 63) / 64;
-  // residual tiles are staged whole; plain bf16 outputs rotate through three 16 KB tiles (one CTA-wide barrier per pass: the
+  // residual tiles are staged whole; plain fp16 outputs rotate through three 16 KB tiles (one CTA-wide barrier per pass: the
   // elected lane waits for the store of pass p-1 right after issuing the store of pass p, so whoever has passed the barrier of
   // pass p+1 knows that the tile of pass p-1 = the tile of pass p+2 is free); plain fp32 outputs (32 KB tiles) ping-pong
   static constexpr int kStagingBufs = kResid ? kPasses : (kElt == 2 ? 3 : 2);
@@ -210,7 +210,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint64_t bdesc = make_smem_desc(a_addr + C::kABytes);
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in (addr >> 4) units
+              // advance 16 fp16 = 32 bytes inside the 128-byte swizzle atom: +2 in (addr >> 4) units
               if (PAIR) tcgen05_mma_f16_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
               else tcgen05_mma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
             }
@@ -318,7 +318,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int j = 0; j < kEpiChunk; ++j) v[i][j] = fmaxf(v[i][j], 0.f);
           }
           // 16 columns of row `row` inside the pass: byte offset of the first one, then 16-byte chunks XOR (row & 7)
-          const int col_byte = (kEpiChunk * sub) * C::kElt;   // 0, 32, 64, 96 (bf16)  |  0, 64, 128, 192 (fp32)
+          const int col_byte = (kEpiChunk * sub) * C::kElt;   // 0, 32, 64, 96 (fp16)  |  0, 64, 128, 192 (fp32)
           const uint32_t box_base = tile_smem + (uint32_t)(col_byte / 128) * C::kBoxBytes + (uint32_t)row * 128u;
           const int chunk0 = (col_byte % 128) / 16;
           if constexpr (C::kElt == 2) {
@@ -470,10 +470,10 @@ static int make_map_uncached(CUtensorMap* map, const void* ptr, uint64_t rows, u
   return 0;
 }
 
-// 2-D row-major bf16 tensor, box = (box_rows, box_cols) with box_cols * 2 bytes == the swizzle span (64 or 128 bytes)
+// 2-D row-major fp16 tensor, box = (box_rows, box_cols) with box_cols * 2 bytes == the swizzle span (64 or 128 bytes)
 int tc_make_map_f16_box(void* map_out, const void* ptr, int64_t rows, int64_t cols, int box_rows, int box_cols) {
   CNB_REQUIRE(g_encode != nullptr, "gemm_tc_init() was not called");
-  CNB_REQUIRE(box_cols == 32 || box_cols == 64, "bf16 box must span 64 or 128 bytes");
+  CNB_REQUIRE(box_cols == 32 || box_cols == 64, "fp16 box must span 64 or 128 bytes");
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
   const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
@@ -483,7 +483,7 @@ int tc_make_map_f16_box(void* map_out, const void* ptr, int64_t rows, int64_t co
                         box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled (bf16 box) failed with CUresult " + std::to_string((int)r));
+    set_error("cuTensorMapEncodeTiled (fp16 box) failed with CUresult " + std::to_string((int)r));
     return -3;
   }
   return 0;
@@ -570,7 +570,7 @@ static int launch_n(const act16* a, const act16* w, int m, int n, int k, const E
   // cluster-scope fence serialised epilogue and MMAs at every tile boundary -- see mbar_arrive_cluster.)
   static const int pair_min_k = [] { const char* e = getenv("CNB_GEMM_PAIR_MINK"); return e ? atoi(e) : 0; }();
   if (m >= pair_min_rows() && k >= pair_min_k) {
-    // pw1 (GELU, bf16 out): 256-column tiles when N allows (768 / 1536 / 3072): the A tile is re-fetched 6x instead of 8x per
+    // pw1 (GELU, fp16 out): 256-column tiles when N allows (768 / 1536 / 3072): the A tile is re-fetched 6x instead of 8x per
     // 256 rows and the epilogue's per-tile hand-offs amortise over a third more columns (pw1 stages 2-4: -2 % / -3 % / -7 %)
     static const bool wide = [] { const char* e = getenv("CNB_GEMM_N256"); return !e || atoi(e) != 0; }();
     if constexpr (EPI == EPI_BIAS_GELU && sizeof(OutT) == 2)

@@ -74,7 +74,7 @@ int launch_gemm_f32(const float* a, int64_t lda, const float* w, int m, int n, i
 int launch_gemm_f32_panel(const float* a, int64_t lda, const float* w, int m, int n, int k, Epilogue epi, const EpiParams& ep,
                           float* out, int64_t ldo, cudaStream_t stream);
 
-// bf16 tcgen05 GEMM (fast mode).  A (M,K) bf16 contiguous, W (N,K) bf16 contiguous (both K-major, TMA-fed).
+// fp16-operand tcgen05 GEMM (fast mode).  A (M,K) fp16 contiguous, W (N,K) fp16 contiguous (both K-major, TMA-fed).
 struct TcGemmPlan;  // opaque: TMA descriptors + tile configuration
 template <typename OutT>
 int launch_gemm_tc(const act16* a, const act16* w, int m, int n, int k, Epilogue epi, const EpiParams& ep,
@@ -86,7 +86,7 @@ int gemm_tc_init();  // resolves cuTensorMapEncodeTiled; returns 0 on success
 // 2-D row-major (rows, cols) tensor map into map_out (a 128-byte CUtensorMap): box = (box_rows, 128 bytes), 128B swizzle
 int tc_make_map(void* map_out, const void* ptr, int64_t rows, int64_t cols, int box_rows, int elt_bytes);
 
-// 2-D row-major bf16 tensor map with an explicit box: box_cols 64 -> 128B swizzle, 32 -> 64B swizzle
+// 2-D row-major fp16 tensor map with an explicit box: box_cols 64 -> 128B swizzle, 32 -> 64B swizzle
 int tc_make_map_f16_box(void* map_out, const void* ptr, int64_t rows, int64_t cols, int box_rows, int box_cols);
 // 4-D NHWC fp32 tensor map, box (box_c, box_w, 1, 1), no swizzle, zero OOB fill (used by the depthwise-conv ring loader)
 int tc_make_map_nhwc_f32(void* map_out, const float* ptr, int batch, int h, int w, int c, int box_c, int box_w);

@@ -1,7 +1,7 @@
 // Fused ConvNeXt pointwise MLP for stage 1 (C = 96): x += scale * (W2 . GELU(W1 . y + b1) + b2) in ONE kernel
 // (reference convnext.py:66-73: pwconv1 -> GELU -> pwconv2 -> layer scale -> residual).
 //
-// Why: as two GEMM launches the stage-1 MLP is HBM-bound on the hidden activations -- pw1 writes (M, 384) bf16 = 693 MB per
+// Why: as two GEMM launches the stage-1 MLP is HBM-bound on the hidden activations -- pw1 writes (M, 384) fp16 = 693 MB per
 // block at 64 clips, pw2 reads it back (ncu: pw2 at 81 % of the DRAM peak).  Here the hidden tile never leaves the SM and
 // never even reaches shared memory:
 //   * both weight matrices live in shared memory for the whole launch (72 KB each), loaded once per CTA; K = 96 is held as
@@ -9,8 +9,8 @@
 //   * tensor memory holds the whole 128 x 384 fp32 hidden tile (six 64-column chunks, columns 0..383) plus the 128 x 96 output
 //     accumulator (columns 384..479).  GEMM1 of tile i+1 is issued chunk by chunk right behind GEMM2 of tile i, so the
 //     epilogue never waits for a GEMM1;
-//   * per chunk the epilogue warps load the fp32 accumulator, add the bias, apply GELU and write the bf16 result back over
-//     the first half of the columns they have just read (tcgen05.st, two bf16 per 32-bit column).  GEMM2 takes that as its A
+//   * per chunk the epilogue warps load the fp32 accumulator, add the bias, apply GELU and write the fp16 result back over
+//     the first half of the columns they have just read (tcgen05.st, two fp16 per 32-bit column).  GEMM2 takes that as its A
 //     operand straight from tensor memory (tcgen05.mma with a TMEM A operand, the layout of CUTLASS' SM100_MMA_F16BF16_TS),
 //     so there is no hidden tile in shared memory, no proxy fence and no buffer hand-back: tcgen05.mma instructions of one
 //     thread execute in issue order, which is all the protection the in-place reuse needs;
@@ -37,8 +37,8 @@ namespace {
 
 constexpr int kC = 96, kHid = 384, kBM = 128, kCh = 64, kNCh = kHid / kCh;  // 6 hidden chunks of 64
 constexpr int kThreadsF = 64 + 32 * kEpiWarps + 32;   // producer, MMA issuer, 16 epilogue warps, residual/output warp
-constexpr int kW1aBytes = kHid * 128;           // W1 k-block 0: [384 rows x 64 bf16], 128B swizzle
-constexpr int kW1bBytes = kHid * 64;            // W1 k-block 1: [384 rows x 32 bf16], 64B swizzle
+constexpr int kW1aBytes = kHid * 128;           // W1 k-block 0: [384 rows x 64 fp16], 128B swizzle
+constexpr int kW1bBytes = kHid * 64;            // W1 k-block 1: [384 rows x 32 fp16], 64B swizzle
 constexpr int kW2Bytes = kNCh * kC * 128;       // six k-blocks of [96 rows x 128 B]
 constexpr int kA0Bytes = kBM * 128, kA1Bytes = kBM * 64;
 constexpr int kStgBytes = kBM * kC * 4;         // fp32 residual / output tile: 3 boxes of [128 rows x 32 columns], 128B swizzle
@@ -77,7 +77,7 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int x, i
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// D (tmem) (+)= A (tmem: row = lane, two bf16 per 32-bit column, K-major) . B (smem descriptor)^T
+// D (tmem) (+)= A (tmem: row = lane, two fp16 per 32-bit column, K-major) . B (smem descriptor)^T
 __device__ __forceinline__ void tcgen05_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
                                                     uint32_t accumulate) {
   asm volatile(
@@ -108,7 +108,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_y0, const __grid_consta
   const uint32_t w_full = bars, a_full = bars + 8, a_empty = bars + 16, o_full = bars + 24, o_empty = bars + 32;
   const uint32_t resid_full = bars + 40, stg_ready = bars + 48;
   auto d1_full = [&](int hf) { return bars + 64 + 8u * hf; }; // GEMM1 of chunks 3 hf .. 3 hf + 2 has completed (once per tile)
-  auto h_full = [&](int j) { return bars + 112 + 8u * j; };   // the bf16 hidden chunk j is in tensor memory (once per tile)
+  auto h_full = [&](int j) { return bars + 112 + 8u * j; };   // the fp16 hidden chunk j is in tensor memory (once per tile)
   const uint32_t tmem_slot = bars + 160;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + kOffBar + 160);
 
@@ -260,7 +260,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_y0, const __grid_consta
         const bool has_next = t + (int)gridDim.x < n_tiles;
 #pragma unroll 1
         for (int j = 0; j < kNCh; ++j) {
-          mbar_wait(ubars + 112 + 8u * j, it & 1);  // h_full(j): the epilogue has written hidden chunk j (bf16) into tensor memory
+          mbar_wait(ubars + 112 + 8u * j, it & 1);  // h_full(j): the epilogue has written hidden chunk j (fp16) into tensor memory
           mark(1, it, j);
           if (j == 0) mbar_wait(o_empty, (it & 1) ^ 1);  // the previous tile's output accumulator has been read
           if (j == 0) mark(1, it, 6);
@@ -375,7 +375,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_y0, const __grid_consta
 
 }  // namespace
 
-// y (M, 96) bf16, w1 (384, 96) bf16, w2 (96, 384) bf16, x (M, 96) fp32 updated in place
+// y (M, 96) fp16, w1 (384, 96) fp16, w2 (96, 384) fp16, x (M, 96) fp32 updated in place
 int launch_mlp_fused_c96(const act16* y, const act16* w1, const act16* w2, const float* b1, const float* b2,
                          const float* scale, float* x, int m, cudaStream_t stream) {
   if (m == 0) return 0;

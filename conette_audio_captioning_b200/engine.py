@@ -167,7 +167,7 @@ class Engine:
 
     def debug_gemm(self, a: Tensor, w: Tensor, bias: Tensor, scale: Optional[Tensor] = None, resid: Optional[Tensor] = None,
                    epi: int = 0, use_tc: bool = True, out_bf16: bool = False) -> Tensor:
-        """Test hook: out = epi(a @ w.T) through the tcgen05 (bf16) or CUDA-core (fp32) GEMM kernel."""
+        """Test hook: out = epi(a @ w.T) through the tcgen05 (fp16 operands) or CUDA-core (fp32) GEMM kernel."""
         a, w, bias = self._dev(a, torch.float32), self._dev(w, torch.float32), self._dev(bias, torch.float32)
         scale = None if scale is None else self._dev(scale, torch.float32)
         resid = None if resid is None else self._dev(resid, torch.float32)

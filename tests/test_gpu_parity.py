@@ -500,7 +500,7 @@ def test_e2e_golden_parity_mode(small_sd):
 
 
 def test_e2e_fast_mode_agreement_is_reported(small_sd):
-    """bf16 encoder: token agreement with the fp32 oracle is REPORTED (near-ties may flip), scores must stay close."""
+    """fp16-operand encoder: token agreement with the fp32 oracle is REPORTED (near-ties may flip), scores must stay close."""
     from oracle import restate
 
     model = _model(small_sd, "fast")

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Cluster (tf32 tensor-core) decoder vs fp32 graph decoder on the same inputs: agreement + timing."""
+"""Cluster (fp16 hi/lo split tensor-core) decoder vs fp32 graph decoder on the same inputs: agreement + timing."""
 import os
 import sys
 

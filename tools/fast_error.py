@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Relative L2 error of the fast (bf16 GEMM) and parity (fp32) encoders against the fp32 CPU oracle."""
+"""Relative L2 error of the fast (fp16-operand GEMM) and parity (fp32) encoders against the fp32 CPU oracle."""
 import os
 import sys
 
