@@ -175,14 +175,16 @@ def decoder_work(batch: int, beam: int, steps: int, vocab: int, tp: int):
     return byts, flops
 
 
-def ncu_traffic(kernel_class: str, batch: int, n_samples: int):
+def ncu_traffic(kernel_class: str, batch: int, n_samples: int, vocab: int = 4018):
     """DRAM bytes per launch of a kernel class from the committed ncu capture summary (profiles/ncu_traffic.json), when one
     exists for exactly this shape; None otherwise (never a guess)."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if not os.path.exists(path):
         return None
     rec = json.load(open(path)).get(f"{batch}x{n_samples}", {}).get(kernel_class)
-    return None if rec is None else rec["dram_bytes_per_launch"]
+    if rec is None or rec.get("vocab", vocab) != vocab:
+        return None
+    return rec["dram_bytes_per_launch"]
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -363,7 +365,7 @@ def kernel_table(prof, steps, work, second, pk, clocks):
     return kernels, total_ms / steps
 
 
-def roofline_of(kernels, work, pk, b, n):
+def roofline_of(kernels, work, pk, b, n, vocab):
     dec_parts = ("dec_gemm", "dec_attn_ln", "dec_classifier", "beam")
     classified = [k for k in kernels if "bound" in kernels[k] and k not in dec_parts]
     top = max(classified, key=lambda k: kernels[k]["ms_per_step"])
@@ -371,7 +373,7 @@ def roofline_of(kernels, work, pk, b, n):
     launches_per_step = kt["brackets_per_step"]
     roofline = {"kernel": top, "bound": kt["bound"], "achieved": kt["achieved"],
                 "peak": pk["bf16_tflops"] if kt["bound"] == "tensor" else pk["hbm_gbs"], "unit": kt["unit"],
-                "frac": kt["frac"], "traffic": ncu_traffic(top, b, n),
+                "frac": kt["frac"], "traffic": ncu_traffic(top, b, n, vocab),
                 "algorithmic_per_launch": work[top][1] / launches_per_step, "launches_per_step": launches_per_step,
                 "avg_launch_ms": kt["ms_per_step"] / launches_per_step, "peak_source": pk["source"] + " (sustained)",
                 "share_of_step": kt["share"]}
@@ -382,7 +384,7 @@ def roofline_of(kernels, work, pk, b, n):
         enc_top = max(enc, key=lambda k: kernels[k]["ms_per_step"])
         roofline["next"] = {"kernel": enc_top, **{k: v for k, v in kernels[enc_top].items() if k != "brackets_per_step"},
                             "avg_launch_ms": kernels[enc_top]["ms_per_step"] / kernels[enc_top]["brackets_per_step"],
-                            "traffic": ncu_traffic(enc_top, b, n)}
+                            "traffic": ncu_traffic(enc_top, b, n, vocab)}
     return roofline
 
 
@@ -610,7 +612,7 @@ def run_ours(args, rank, world, local_rank):
                     "phases, 3 reduce-scatter + all-gather + LayerNorm exchanges} + classifier rounds + beam merge) on 16-row operands, "
                     "fp16 hi/lo split MMAs (fp32-level accuracy); reported against the weight bytes one step has to stream"}
         work["decoder"] = ("hbm", dbytes)
-    roofline = roofline_of(kernels, work, pk, b, n)
+    roofline = roofline_of(kernels, work, pk, b, n, vocab)
 
     if rank == 0:
         cpu = parity_rec = None

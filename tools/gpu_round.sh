@@ -18,3 +18,5 @@ python bench.py --config 4 --steps 2 --warmup 3 --cpu-sample 2 > gpurun_out/benc
 python bench.py --config 3 --steps 2 --warmup 3 --cpu-sample 2 > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err
 python bench.py --vocab-words 8174 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c1_v8192.json 2> gpurun_out/bench_c1_v8192.err
 tail -c 300 gpurun_out/bench_c3.err
+CNB_PARITY_CLIPS=64 python -m pytest tests/test_bench_parity.py -m gpu -q --timeout 900 -s -k "bench_config" > gpurun_out/t_parity64.log 2>&1
+grep "parity\]" gpurun_out/t_parity64.log | cut -c1-400
