@@ -118,7 +118,7 @@ def workload_config(args, world, vocab):
 # ---------------------------------------------------------------------------------------------------------------------
 # algorithmic work per kernel class for one step (DESIGN.md "Algorithmic work")
 # ---------------------------------------------------------------------------------------------------------------------
-def algorithmic_work(batch: int, n_samples: int, act_bytes: int = 2, fused_s1: bool = True):
+def algorithmic_work(batch: int, n_samples: int, act_bytes: int = 2, fused=(0, 1)):
     t = n_samples // 320 + 1
     h1 = (t + 4) // 4 + 1
     hs = [h1, h1 // 2, h1 // 4, h1 // 8]
@@ -132,8 +132,8 @@ def algorithmic_work(batch: int, n_samples: int, act_bytes: int = 2, fused_s1: b
         # dw+LN reads the fp32 residual stream and writes the GEMM operand; flops 98 per element (informational)
         work[f"dwconv_ln.s{s + 1}"] = ("hbm", DEPTHS[s] * m * c * (4 + act_bytes))
         pw = DEPTHS[s] * 2 * m * c * 4 * c
-        # stage 1, fast precision: ONE fused kernel does pw1 + GELU + pw2 and is bracketed under the pw1 class
-        work[f"gemm_pw1_gelu.s{s + 1}"] = ("tensor", 2 * pw if (s == 0 and fused_s1) else pw)
+        # stages 1-2, fast precision: ONE fused kernel does pw1 + GELU + pw2 and is bracketed under the pw1 class
+        work[f"gemm_pw1_gelu.s{s + 1}"] = ("tensor", 2 * pw if s in fused else pw)
         work[f"gemm_pw2_resid.s{s + 1}"] = ("tensor", pw)
         if s > 0:
             cin = DIMS[s - 1]
@@ -144,7 +144,7 @@ def algorithmic_work(batch: int, n_samples: int, act_bytes: int = 2, fused_s1: b
     return work
 
 
-def secondary_bounds(batch: int, n_samples: int, act_bytes: int = 2, fused_s1: bool = True):
+def secondary_bounds(batch: int, n_samples: int, act_bytes: int = 2, fused=(0, 1)):
     """The other roofline of the classes whose nominal bound (north_star) is not the physical one:
     pointwise GEMMs -> minimum HBM bytes (operand in, result out, fp32 residual in+out, weights once);
     depthwise conv + LN -> FP32 FMAs (49 per output element) against the CUDA-core peak."""
@@ -155,8 +155,8 @@ def secondary_bounds(batch: int, n_samples: int, act_bytes: int = 2, fused_s1: b
     for s in range(4):
         m = batch * hs[s] * WIDTHS[s]
         c = DIMS[s]
-        if s == 0 and fused_s1:  # fused MLP: operand in, fp32 residual in + out, weights once
-            out["gemm_pw1_gelu.s1"] = ("hbm", DEPTHS[s] * (m * c * act_bytes + 2 * m * c * 4 + 8 * c * c * 2))
+        if s in fused:  # fused MLP: operand in, fp32 residual in + out, weights once
+            out[f"gemm_pw1_gelu.s{s + 1}"] = ("hbm", DEPTHS[s] * (m * c * act_bytes + 2 * m * c * 4 + 8 * c * c * 2))
         else:
             out[f"gemm_pw1_gelu.s{s + 1}"] = ("hbm", DEPTHS[s] * (m * c * act_bytes + m * 4 * c * act_bytes + 4 * c * c * 2))
         out[f"gemm_pw2_resid.s{s + 1}"] = ("hbm", DEPTHS[s] * (m * 4 * c * act_bytes + 2 * m * c * 4 + 4 * c * c * 2))
@@ -448,7 +448,9 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     pk = peaks()
     act_bytes = 2 if args.precision == "fast" else 4
-    fused = args.precision == "fast" and os.environ.get("CNB_NO_MLP_FUSED") is None
+    fused = ()
+    if args.precision == "fast" and os.environ.get("CNB_NO_MLP_FUSED") is None:
+        fused = (0,) if os.environ.get("CNB_NO_MLP_FUSED192") is not None else (0, 1)
     work = algorithmic_work(b, n, act_bytes, fused)
     second = secondary_bounds(b, n, act_bytes, fused)
     line_extra = {}

@@ -256,6 +256,34 @@ def test_fused_mlp_kernel(eng_fast, m):
         assert torch.equal(one, got[-1:])
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("m", [1, 129, 256, 257, 74 * 256, 74 * 256 * 3 + 77])
+def test_fused_mlp192_kernel(eng_fast, m):
+    """The fused stage-2 MLP kernel (CTA pairs, streamed weight ring, hidden chunks in tensor memory) against a plain fp32 torch
+    evaluation of convnext.py:66-73 on the same fp16-rounded operands: partial pairs (the odd CTA entirely out of range), exact
+    tiles, one tile per pair and the multi-tile pipeline with a ragged tail.  Tolerance: 3e-4 rel-L2 on the update."""
+    g = torch.Generator().manual_seed(m + 7)
+    dev = "cuda"
+    y = torch.randn(m, 192, generator=g).to(dev)
+    x = torch.randn(m, 192, generator=g).to(dev)
+    w1 = (torch.randn(768, 192, generator=g) / 192 ** 0.5).to(dev)
+    w2 = (torch.randn(192, 768, generator=g) / 768 ** 0.5).to(dev)
+    b1 = (0.3 * torch.randn(768, generator=g)).to(dev)
+    b2 = (0.3 * torch.randn(192, generator=g)).to(dev)
+    scale = (0.5 + torch.rand(192, generator=g)).to(dev)
+    got = eng_fast.debug_mlp_fused192(y, w1, b1, w2, b2, scale, x)
+    hf = lambda v: v.to(torch.float16).to(torch.float32)
+    hid = hf(torch.nn.functional.gelu(hf(y) @ hf(w1).T + b1))
+    want = x + scale * (hid @ hf(w2).T + b2)
+    upd_err = float(((got - x) - (want - x)).norm() / (want - x).norm())
+    print(f"fused MLP-192 m={m}: update rel-L2 {upd_err:.2e}")
+    assert upd_err < 3e-4, upd_err
+    assert float((got - want).abs().max()) < 5e-3
+    if m > 1:
+        one = eng_fast.debug_mlp_fused192(y[-1:], w1, b1, w2, b2, scale, x[-1:])
+        assert torch.equal(one, got[-1:])
+
+
 def test_encoder_golden(eng_parity, small_sd):
     fx = load("encoder.npz")
     fe, clip = eng_parity.encoder(t(fx["wav"]))
