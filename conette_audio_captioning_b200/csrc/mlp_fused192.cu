@@ -6,12 +6,12 @@
 // nor the hidden tile (768 fp32 columns) fit on an SM, so:
 //   * a CTA PAIR (one TPC) owns a 256-row tile, 128 rows per CTA, and runs every MMA as tcgen05.mma cta_group::2 (issued by the
 //     even CTA): each CTA loads only HALF of every weight chunk, which halves the L2 -> shared-memory weight stream per row;
-//   * the hidden dimension is walked in 12 chunks of 64 units.  Chunk j: GEMM1 D1[j & 1] (128 x 64 fp32 in tensor memory, double
-//     buffered) = y . W1[j]^T; the 16 epilogue warps add the bias, apply GELU and write the fp16 result back over the columns
+//   * the hidden dimension is walked in 12 chunks of 64 units.  Chunk j: GEMM1 D1[j % 3] (128 x 64 fp32 in tensor memory, three
+//     buffers) = y . W1[j]^T; the 16 epilogue warps add the bias, apply GELU and write the fp16 result back over the columns
 //     they have just read (tcgen05.st); GEMM2 takes that as its A operand straight from tensor memory and accumulates
-//     O (128 x 192 fp32, tensor memory) += H_j . W2[:, j]^T.  GEMM1 of chunk j + 1 is issued before GEMM2 of chunk j, so the tensor
-//     pipe works while the epilogue runs; tcgen05.mma instructions execute in issue order, which protects the in-place reuse;
-//   * weights stream through a 3-stage ring of 24 KB (W1 half chunk 32 x 192 + W2 half chunk 96 x 64), y tiles are double
+//     O (128 x 192 fp32, tensor memory) += H_j . W2[:, j]^T.  GEMM2 trails GEMM1 by two chunks, so the tensor pipe always has
+//     work while the epilogue runs; tcgen05.mma instructions execute in issue order, which protects the in-place reuse;
+//   * weights stream through a 4-stage ring of 24 KB (W1 half chunk 32 x 192 + W2 half chunk 96 x 64), y tiles are double
 //     buffered (the next tile is in flight a whole tile ahead), the output leaves through TMA reduce-add stores into the fp32
 //     residual stream (no residual load), 64 columns per pass through a 32 KB staging buffer.
 // HBM traffic per block: y 87 MB + x 173 MB read-modify-write in L2 = 434 MB instead of 1 128 MB.
@@ -30,25 +30,36 @@ namespace cnb {
 
 namespace {
 
-constexpr int kC2 = 192, kHid2 = 768, kBM2 = 128, kCh2 = 64, kNCh2 = kHid2 / kCh2;  // 12 hidden chunks of 64
-constexpr int kKB2 = kC2 / 64;                          // 3 k-blocks of 64 in GEMM1
+constexpr int kBM2 = 128, kCh2 = 64;                   // rows per CTA, hidden units per chunk
 constexpr int kThreads2 = 64 + 32 * kEpiWarps + 32;     // producer, MMA issuer, 16 epilogue warps, store warp
-constexpr int kYBytes = kKB2 * kBM2 * 128;              // 48 KB: three [128 rows x 64 fp16] boxes
-constexpr int kW1Half = kKB2 * 32 * 128;                // 12 KB: three [32 rows x 64 fp16] boxes (this CTA's half of the chunk)
-constexpr int kW2Half = 96 * 128;                       // 12 KB: [96 output rows x 64 fp16]
-constexpr int kStage2 = kW1Half + kW2Half;              // 24 KB
-constexpr int kRing2 = 3;
 constexpr int kStgBox = kBM2 * 128;                     // [128 rows x 32 fp32]
-constexpr int kOffY = 0;
-constexpr int kOffRing = kOffY + 2 * kYBytes;
-constexpr int kOffStg2 = kOffRing + kRing2 * kStage2;
-constexpr int kOffVec2 = kOffStg2 + 2 * kStgBox;        // b1 (768) | b2 (192) | scale (192)
-constexpr int kOffBar2 = kOffVec2 + (kHid2 + 2 * kC2) * 4;
-constexpr int kSmem2 = kOffBar2 + 256 + 1024;
-static_assert(kOffRing % 1024 == 0 && kOffStg2 % 1024 == 0 && kStage2 % 1024 == 0 && kW1Half % 1024 == 0, "align");
-static_assert(kSmem2 <= 232448, "shared memory budget");
-constexpr int kTmemCols2 = 512;                         // O 0..191 | D1[0] 192..255 | D1[1] 256..319
-constexpr int kTmemD1 = kC2;
+
+// C = 192 (stage 2): y double buffered, 4 weight stages, 3 hidden-chunk buffers in tensor memory, 64 output columns per store pass.
+// (C = 384, stage 3, was budgeted and dropped: O would fill 384 of the 512 tensor-memory columns and shared memory would only
+// leave one 96 KB y buffer and two 48 KB weight stages -- too shallow a ring to keep the tensor pipe fed, for a block that already
+// runs at 65-77 % of the tensor rate as two GEMMs.)
+template <int C> struct F2Cfg {
+  static constexpr int kHid = 4 * C, kNCh = kHid / kCh2, kKB = C / 64, kNSplit = C / 192;
+  static constexpr int kYBufs = 2, kRing = 4, kStgBoxes = 2, kD1Bufs = 3;
+  static constexpr int kYBytes = kKB * kBM2 * 128;           // kKB boxes of [128 rows x 64 fp16]
+  static constexpr int kW1Half = kKB * 32 * 128;             // kKB boxes of [32 rows x 64 fp16] (this CTA's half of the chunk)
+  static constexpr int kW2Half = kNSplit * 96 * 128;         // kNSplit boxes of [96 output rows x 64 fp16]
+  static constexpr int kStage = kW1Half + kW2Half;
+  static constexpr int kPassCols = 32 * kStgBoxes, kPasses = C / kPassCols, kColsPerThread = kPassCols / 4;
+  static constexpr int kOffY = 0;
+  static constexpr int kOffRing = kOffY + kYBufs * kYBytes;
+  static constexpr int kOffStg = kOffRing + kRing * kStage;
+  static constexpr int kOffVec = kOffStg + kStgBoxes * kStgBox;   // b2 (C) | scale (C); b1 is read through the L1 (no room)
+  static constexpr int kOffBar = kOffVec + 2 * C * 4;
+  static constexpr int kSmem = kOffBar + 256 + 1024;
+  static constexpr int kTmemD1 = C;                          // O 0..C-1 | D1[b] at C + 64 b
+  static_assert(C == 192, "stage 2");
+  static_assert(kNCh % kD1Bufs == 0, "hidden chunks per buffer");
+  static_assert(kOffRing % 1024 == 0 && kOffStg % 1024 == 0 && kStage % 1024 == 0 && kW1Half % 1024 == 0, "align");
+  static_assert(kSmem <= 232448, "shared memory budget");
+  static_assert(C + kD1Bufs * kCh2 <= 512, "tensor memory columns");
+};
+constexpr int kTmemCols2 = 512;
 
 __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
@@ -69,30 +80,32 @@ __device__ __forceinline__ void tcgen05_mma_f16_ts_pair(uint32_t tmem_d, uint32_
       : "memory");
 }
 
+template <int C>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
-mlp_fused192_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_w1,
-                    const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_x, int M,
-                    const float* __restrict__ b1, const float* __restrict__ b2, const float* __restrict__ scale) {
+mlp_fused_pair_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_w1,
+                      const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_x, int M,
+                      const float* __restrict__ b1, const float* __restrict__ b2, const float* __restrict__ scale) {
+  using F = F2Cfg<C>;
+  constexpr int kNCh = F::kNCh, kKB = F::kKB, kRing = F::kRing, kYBufs = F::kYBufs;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-  float* s_b1 = reinterpret_cast<float*>(sm + kOffVec2);
-  float* s_b2 = s_b1 + kHid2;
-  float* s_sc = s_b2 + kC2;
-  const uint32_t bars = base + kOffBar2;
+  float* s_b2 = reinterpret_cast<float*>(sm + F::kOffVec);
+  float* s_sc = s_b2 + C;
+  const uint32_t bars = base + F::kOffBar;
   auto a_full = [&](int b) { return bars + 8u * b; };            // even CTA: y tile b of both CTAs has landed
   auto a_empty = [&](int b) { return bars + 16 + 8u * b; };      // both: the last GEMM1 reading y tile b has completed
   auto w_full = [&](int s) { return bars + 32 + 8u * s; };       // even CTA: weight stage s of both CTAs has landed
-  auto w_empty = [&](int s) { return bars + 56 + 8u * s; };      // both: the MMAs reading weight stage s have completed
-  auto d1_full = [&](int b) { return bars + 80 + 8u * b; };      // both: GEMM1 into D1[b] has completed
-  auto h_full = [&](int b) { return bars + 96 + 8u * b; };       // even CTA: both CTAs' epilogues have written hidden chunk b
-  const uint32_t o_full = bars + 112, o_empty = bars + 120;      // both | even CTA
-  const uint32_t stg_ready = bars + 128, stg_free = bars + 136;  // local
-  const uint32_t tmem_slot = bars + 144;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + kOffBar2 + 144);
+  auto w_empty = [&](int s) { return bars + 64 + 8u * s; };      // both: the MMAs reading weight stage s have completed
+  auto d1_full = [&](int b) { return bars + 96 + 8u * b; };      // both: GEMM1 into D1[b] has completed
+  auto h_full = [&](int b) { return bars + 120 + 8u * b; };      // even CTA: both CTAs' epilogues have written hidden chunk b
+  const uint32_t o_full = bars + 144, o_empty = bars + 152;      // both | even CTA
+  const uint32_t stg_ready = bars + 160, stg_free = bars + 168;  // local
+  const uint32_t tmem_slot = bars + 176;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + F::kOffBar + 176);
+  constexpr int kD1 = F::kD1Bufs;
 
-  for (int i = threadIdx.x; i < kHid2; i += kThreads2) s_b1[i] = b1[i];
-  for (int i = threadIdx.x; i < kC2; i += kThreads2) {
+  for (int i = threadIdx.x; i < C; i += kThreads2) {
     s_b2[i] = b2[i];
     s_sc[i] = scale[i];
   }
@@ -105,10 +118,12 @@ mlp_fused192_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_cons
     for (int b = 0; b < 2; ++b) {
       mbar_init(a_full(b), 1);
       mbar_init(a_empty(b), 1);
+    }
+    for (int b = 0; b < kD1; ++b) {
       mbar_init(d1_full(b), 1);
       mbar_init(h_full(b), 2 * kEpiWarps);   // one arrival per epilogue warp of both CTAs
     }
-    for (int s = 0; s < kRing2; ++s) {
+    for (int s = 0; s < kRing; ++s) {
       mbar_init(w_full(s), 1);
       mbar_init(w_empty(s), 1);
     }
@@ -131,34 +146,37 @@ mlp_fused192_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_cons
   if (warp == 0) {
     // ===================== TMA producer (both CTAs: own 128 rows of y, own half of every weight chunk) =====================
     const uint32_t sb = __shfl_sync(0xffffffffu, base, 0);
-    const uint32_t ubars = sb + kOffBar2;
+    const uint32_t ubars = sb + F::kOffBar;
     const uint32_t urank = __shfl_sync(0xffffffffu, rank, 0);
-    uint32_t g = 0;   // running weight-chunk counter: chunk g lives in ring stage g % 3
+    uint32_t g = 0;   // running weight-chunk counter: chunk g lives in ring stage g % kRing
     int it = 0;
     for (int t = pair; t < n_tiles; t += n_pairs, ++it) {
-      const int b = it & 1;
-      mbar_wait(ubars + 16 + 8u * b, ((uint32_t)(it >> 1) & 1u) ^ 1u);   // a_empty(b), this CTA's copy
+      const int b = it % kYBufs;
+      const uint32_t use = (uint32_t)(it / kYBufs);   // how often buffer b has been filled before
+      mbar_wait(ubars + 16 + 8u * b, (use & 1u) ^ 1u);   // a_empty(b), this CTA's copy
       if (elect_one()) {
         const uint32_t full = ubars + 8u * b;
         const uint32_t lead = mapa_cluster(full, 0);
-        if (urank == 0) mbar_expect_tx(full, 2 * kYBytes);
+        if (urank == 0) mbar_expect_tx(full, 2 * F::kYBytes);
 #pragma unroll
-        for (int kb = 0; kb < kKB2; ++kb)
-          tma_load_2d_pair(sb + kOffY + b * kYBytes + kb * (kBM2 * 128), &map_y, kb * 64, t * (2 * kBM2) + (int)urank * kBM2, lead);
+        for (int kb = 0; kb < kKB; ++kb)
+          tma_load_2d_pair(sb + F::kOffY + b * F::kYBytes + kb * (kBM2 * 128), &map_y, kb * 64, t * (2 * kBM2) + (int)urank * kBM2, lead);
       }
       __syncwarp();
-      for (int j = 0; j < kNCh2; ++j, ++g) {
-        const uint32_t s = g % kRing2;
-        mbar_wait(ubars + 56 + 8u * s, ((g / kRing2) & 1u) ^ 1u);   // w_empty(s)
+      for (int j = 0; j < kNCh; ++j, ++g) {
+        const uint32_t s = g % kRing;
+        mbar_wait(ubars + 64 + 8u * s, ((g / kRing) & 1u) ^ 1u);   // w_empty(s)
         if (elect_one()) {
           const uint32_t full = ubars + 32 + 8u * s;
           const uint32_t lead = mapa_cluster(full, 0);
-          const uint32_t dst = sb + kOffRing + s * kStage2;
-          if (urank == 0) mbar_expect_tx(full, 2 * kStage2);
+          const uint32_t dst = sb + F::kOffRing + s * F::kStage;
+          if (urank == 0) mbar_expect_tx(full, 2 * F::kStage);
 #pragma unroll
-          for (int kb = 0; kb < kKB2; ++kb)
+          for (int kb = 0; kb < kKB; ++kb)
             tma_load_2d_pair(dst + kb * (32 * 128), &map_w1, kb * 64, j * kCh2 + (int)urank * 32, lead);
-          tma_load_2d_pair(dst + kW1Half, &map_w2, j * kCh2, (int)urank * 96, lead);
+#pragma unroll
+          for (int ns = 0; ns < F::kNSplit; ++ns)   // output columns [192 ns + 96 rank, +96) of W2's k-columns [64 j, +64)
+            tma_load_2d_pair(dst + F::kW1Half + ns * (96 * 128), &map_w2, j * kCh2, ns * 192 + (int)urank * 96, lead);
         }
         __syncwarp();
       }
@@ -168,69 +186,75 @@ mlp_fused192_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_cons
     if (rank == 0) {
       const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t sb = __shfl_sync(0xffffffffu, base, 0);
-      const uint32_t ubars = sb + kOffBar2;
-      constexpr uint32_t idesc1 = make_idesc(2 * kBM2, kCh2), idesc2 = make_idesc(2 * kBM2, kC2);
+      const uint32_t ubars = sb + F::kOffBar;
+      constexpr uint32_t idesc1 = make_idesc(2 * kBM2, kCh2), idesc2 = make_idesc(2 * kBM2, 192);
       uint32_t g = 0;
       int it = 0;
-      // GEMM2 of chunk jj (running index gj) of tile `it`: O (+)= H_jj . W2[:, jj]^T
+      // GEMM2 of chunk jj (running index gj) of tile `cit`: O (+)= H_jj . W2[:, jj]^T
       auto gemm2 = [&](int jj, uint32_t gj, int cit) {
-        const int hb = jj & 1;
-        mbar_wait(ubars + 96 + 8u * hb, (uint32_t)(cit * (kNCh2 / 2) + (jj >> 1)) & 1u);   // h_full(hb)
-        if (jj == 0) mbar_wait(ubars + 120, ((uint32_t)cit & 1u) ^ 1u);                    // o_empty: previous tile's output read
+        const int hb = jj % kD1;
+        mbar_wait(ubars + 120 + 8u * hb, (uint32_t)(cit * (kNCh / kD1) + jj / kD1) & 1u);   // h_full(hb)
+        if (jj == 0) mbar_wait(ubars + 152, ((uint32_t)cit & 1u) ^ 1u);                     // o_empty: previous tile's output read
         tcgen05_fence_after();
         if (elect_one()) {
-          const uint32_t s = gj % kRing2;
-          const uint64_t bdesc = make_smem_desc(sb + kOffRing + s * kStage2 + kW1Half);
-          const uint32_t a_col = tb + (uint32_t)(kTmemD1 + hb * kCh2);
+          const uint32_t s = gj % kRing;
+          const uint32_t a_col = tb + (uint32_t)(F::kTmemD1 + hb * kCh2);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)   // k16 step k: packed fp16 at columns [16 k, 16 k + 8) of the chunk (written by sub-warp k)
-            tcgen05_mma_f16_ts_pair(tb, a_col + 16u * k, bdesc + 2 * k, idesc2, (jj | k) != 0);
-          tcgen05_commit_pair(ubars + 56 + 8u * s);                 // w_empty(s): both halves of the stage have been read
-          if (jj == kNCh2 - 1) tcgen05_commit_pair(ubars + 112);    // o_full
+          for (int ns = 0; ns < F::kNSplit; ++ns) {
+            const uint64_t bdesc = make_smem_desc(sb + F::kOffRing + s * F::kStage + F::kW1Half + ns * (96 * 128));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)   // k16 step k: packed fp16 at columns [16 k, 16 k + 8) of the chunk (written by sub-warp k)
+              tcgen05_mma_f16_ts_pair(tb + (uint32_t)(ns * 192), a_col + 16u * k, bdesc + 2 * k, idesc2, (jj | k) != 0);
+          }
+          tcgen05_commit_pair(ubars + 64 + 8u * s);               // w_empty(s): both halves of the stage have been read
+          if (jj == kNCh - 1) tcgen05_commit_pair(ubars + 144);   // o_full
         }
         __syncwarp();
       };
       for (int t = pair; t < n_tiles; t += n_pairs, ++it) {
-        const int b = it & 1;
-        mbar_wait(ubars + 8u * b, (uint32_t)(it >> 1) & 1u);   // a_full(b)
-        for (int j = 0; j < kNCh2; ++j, ++g) {
-          const uint32_t s = g % kRing2;
-          mbar_wait(ubars + 32 + 8u * s, (g / kRing2) & 1u);   // w_full(s)
+        const int b = it % kYBufs;
+        mbar_wait(ubars + 8u * b, (uint32_t)(it / kYBufs) & 1u);   // a_full(b)
+        for (int j = 0; j < kNCh; ++j, ++g) {
+          const uint32_t s = g % kRing;
+          mbar_wait(ubars + 32 + 8u * s, (g / kRing) & 1u);   // w_full(s)
           tcgen05_fence_after();
           if (elect_one()) {
-            const uint32_t d1 = tb + (uint32_t)(kTmemD1 + (j & 1) * kCh2);
+            const uint32_t d1 = tb + (uint32_t)(F::kTmemD1 + (j % kD1) * kCh2);
 #pragma unroll
-            for (int kb = 0; kb < kKB2; ++kb) {
-              const uint64_t adesc = make_smem_desc(sb + kOffY + b * kYBytes + kb * (kBM2 * 128));
-              const uint64_t bdesc = make_smem_desc(sb + kOffRing + s * kStage2 + kb * (32 * 128));
+            for (int kb = 0; kb < kKB; ++kb) {
+              const uint64_t adesc = make_smem_desc(sb + F::kOffY + b * F::kYBytes + kb * (kBM2 * 128));
+              const uint64_t bdesc = make_smem_desc(sb + F::kOffRing + s * F::kStage + kb * (32 * 128));
 #pragma unroll
               for (int k = 0; k < 4; ++k) tcgen05_mma_f16_pair(d1, adesc + 2 * k, bdesc + 2 * k, idesc1, (kb | k) != 0);
             }
-            tcgen05_commit_pair(ubars + 80 + 8u * (j & 1));                  // d1_full(j & 1)
-            if (j == kNCh2 - 1) tcgen05_commit_pair(ubars + 16 + 8u * b);    // a_empty(b): y tile b is free
+            tcgen05_commit_pair(ubars + 96 + 8u * (j % kD1));              // d1_full(j % 3)
+            if (j == kNCh - 1) tcgen05_commit_pair(ubars + 16 + 8u * b);   // a_empty(b): y tile b is free
           }
           __syncwarp();
-          if (j >= 1) gemm2(j - 1, g - 1, it);
+          // GEMM2 trails GEMM1 by TWO chunks: while the epilogue turns chunk j - 1 into fp16 (tensor-memory load, GELU at the
+          // MUFU rate, store, an arrival that crosses the pair: ~1 100 cycles) the tensor pipe has GEMM1(j) and GEMM2(j - 2)
+          if (j >= 2) gemm2(j - 2, g - 2, it);
         }
-        gemm2(kNCh2 - 1, g - 1, it);
+        gemm2(kNCh - 2, g - 2, it);
+        gemm2(kNCh - 1, g - 1, it);
       }
     }
   } else if (warp == kEpiWarps + 2) {
-    // ===================== output stores: 64 columns per pass, TMA reduce-add into the residual stream =====================
+    // ===================== output stores: one pass of kPassCols columns at a time, TMA reduce-add into the residual stream ====
     const uint32_t sb = __shfl_sync(0xffffffffu, base, 0);
-    const uint32_t ubars = sb + kOffBar2;
+    const uint32_t ubars = sb + F::kOffBar;
     const uint32_t urank = __shfl_sync(0xffffffffu, rank, 0);
     uint32_t pc = 0;
     for (int t = pair; t < n_tiles; t += n_pairs) {
-      for (int p = 0; p < 3; ++p, ++pc) {
-        mbar_wait(ubars + 128, pc & 1u);   // stg_ready: the 16 epilogue warps have written this pass
+      for (int p = 0; p < F::kPasses; ++p, ++pc) {
+        mbar_wait(ubars + 160, pc & 1u);   // stg_ready: the 16 epilogue warps have written this pass
         if (elect_one()) {
 #pragma unroll
-          for (int bx = 0; bx < 2; ++bx)
-            tma_reduce_add_2d(&map_x, sb + kOffStg2 + bx * kStgBox, 64 * p + 32 * bx, t * (2 * kBM2) + (int)urank * kBM2);
+          for (int bx = 0; bx < F::kStgBoxes; ++bx)
+            tma_reduce_add_2d(&map_x, sb + F::kOffStg + bx * kStgBox, F::kPassCols * p + 32 * bx, t * (2 * kBM2) + (int)urank * kBM2);
           bulk_commit();
           bulk_wait_read<0>();             // the stores have read the staging buffer
-          mbar_arrive(ubars + 136);        // stg_free
+          mbar_arrive(ubars + 168);        // stg_free
         }
         __syncwarp();
       }
@@ -240,29 +264,33 @@ mlp_fused192_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_cons
   } else {
     // ===================== epilogue (warps 2..17) =====================
     const int lane_grp = warp & 3;            // TMEM lanes [32 lane_grp, +32)
-    const int sub = (warp - 2) >> 2;          // 16-column slice of a hidden chunk / of an output pass
+    const int sub = (warp - 2) >> 2;          // 16-column slice of a hidden chunk / quarter of an output pass
     const int row = lane_grp * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
-    const uint32_t lead_h0 = mapa_cluster(h_full(0), 0), lead_h1 = mapa_cluster(h_full(1), 0);
+    const uint32_t lead_h0 = mapa_cluster(h_full(0), 0);
     const uint32_t lead_oe = mapa_cluster(o_empty, 0);
+    constexpr int CPT = F::kColsPerThread;    // output columns per thread and pass (16 or 8)
     uint32_t pc = 0;
     int it = 0;
     for (int t = pair; t < n_tiles; t += n_pairs, ++it) {
 #pragma unroll 1
-      for (int j = 0; j < kNCh2; ++j) {
-        const int hb = j & 1;
-        mbar_wait(d1_full(hb), (uint32_t)(it * (kNCh2 / 2) + (j >> 1)) & 1u);
+      for (int j = 0; j < kNCh; ++j) {
+        const int hb = j % kD1;
+        mbar_wait(d1_full(hb), (uint32_t)(it * (kNCh / kD1) + j / kD1) & 1u);
         tcgen05_fence_after();
-        const uint32_t taddr = lane_addr + (uint32_t)(kTmemD1 + hb * kCh2 + 16 * sub);
+        const uint32_t taddr = lane_addr + (uint32_t)(F::kTmemD1 + hb * kCh2 + 16 * sub);
         float v[16];
         tmem_ld_32x16(taddr, v);
         tmem_ld_wait();
         float2* v2 = reinterpret_cast<float2*>(v);
-        const float2* sb2 = reinterpret_cast<const float2*>(s_b1 + j * kCh2 + 16 * sub);
+        const float4* gb = reinterpret_cast<const float4*>(b1 + j * kCh2 + 16 * sub);   // 64 bytes, L1-resident after the first tile
+        const float4 q0 = __ldg(gb), q1 = __ldg(gb + 1), q2 = __ldg(gb + 2), q3 = __ldg(gb + 3);
+        const float2 bia[8] = {make_float2(q0.x, q0.y), make_float2(q0.z, q0.w), make_float2(q1.x, q1.y), make_float2(q1.z, q1.w),
+                               make_float2(q2.x, q2.y), make_float2(q2.z, q2.w), make_float2(q3.x, q3.y), make_float2(q3.z, q3.w)};
         uint32_t h[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float2 gl = gelu_tanh_fit2(__fadd2_rn(v2[i], sb2[i]));
+          const float2 gl = gelu_tanh_fit2(__fadd2_rn(v2[i], bia[i]));
           act16x2 pk = floats2act2(gl.x, gl.y);   // k = 2 i in the low half, 2 i + 1 in the high half
           h[i] = *reinterpret_cast<uint32_t*>(&pk);
         }
@@ -270,32 +298,35 @@ mlp_fused192_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_cons
         tmem_st_wait2();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(hb ? lead_h1 : lead_h0);
+        if (lane == 0) mbar_arrive_cluster(lead_h0 + 8u * hb);
       }
-      // ---- output: O (128 x 192) + bias2, layer scale; the residual add happens in the TMA reduce store ----
+      // ---- output: O (128 x C) + bias2, layer scale; the residual add happens in the TMA reduce store ----
       mbar_wait(o_full, (uint32_t)it & 1u);
       tcgen05_fence_after();
-      float o[3][16];
+      // few enough columns to hold in registers: the accumulator is handed back before the stores start
+      float o[F::kPasses][CPT];
 #pragma unroll
-      for (int p = 0; p < 3; ++p) tmem_ld_32x16(lane_addr + (uint32_t)(64 * p + 16 * sub), o[p]);
+      for (int p = 0; p < F::kPasses; ++p) tmem_ld_32x16(lane_addr + (uint32_t)(F::kPassCols * p + CPT * sub), o[p]);
       tmem_ld_wait();
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(lead_oe);   // the accumulator may be overwritten by the next tile's GEMM2
 #pragma unroll
-      for (int p = 0; p < 3; ++p, ++pc) {
+      for (int p = 0; p < F::kPasses; ++p, ++pc) {
+        const float (&ov)[CPT] = o[p];
         mbar_wait(stg_free, (pc & 1u) ^ 1u);   // the previous pass has left the staging buffer
-        const int c0 = 64 * p + 16 * sub;      // first of this thread's 16 output columns
-        const uint32_t box = base + kOffStg2 + (uint32_t)(sub >> 1) * kStgBox + (uint32_t)row * 128u;
+        const int c0 = F::kPassCols * p + CPT * sub;   // first of this thread's output columns
+        const int in_pass = CPT * sub;                 // column offset inside the pass
+        const uint32_t box = base + F::kOffStg + (uint32_t)(in_pass >> 5) * kStgBox + (uint32_t)row * 128u;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < CPT / 4; ++q) {
           const int c = c0 + 4 * q;
           const float4 bb = *reinterpret_cast<const float4*>(s_b2 + c);
           const float4 ss = *reinterpret_cast<const float4*>(s_sc + c);
-          const int grp16 = (sub & 1) * 4 + q;   // 16-byte group inside the 128-byte box row
-          st_shared_v4(box + (uint32_t)((grp16 ^ (row & 7)) << 4), __float_as_uint(ss.x * (o[p][4 * q + 0] + bb.x)),
-                       __float_as_uint(ss.y * (o[p][4 * q + 1] + bb.y)), __float_as_uint(ss.z * (o[p][4 * q + 2] + bb.z)),
-                       __float_as_uint(ss.w * (o[p][4 * q + 3] + bb.w)));
+          const int grp16 = ((in_pass & 31) >> 2) + q;   // 16-byte group inside the 128-byte box row
+          st_shared_v4(box + (uint32_t)((grp16 ^ (row & 7)) << 4), __float_as_uint(ss.x * (ov[4 * q + 0] + bb.x)),
+                       __float_as_uint(ss.y * (ov[4 * q + 1] + bb.y)), __float_as_uint(ss.z * (ov[4 * q + 2] + bb.z)),
+                       __float_as_uint(ss.w * (ov[4 * q + 3] + bb.w)));
         }
         fence_async_smem();   // generic-proxy writes -> visible to the TMA store issued by the store warp
         __syncwarp();
@@ -312,27 +343,39 @@ mlp_fused192_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_cons
   }
 }
 
-}  // namespace
-
-// y (M, 192) fp16, w1 (768, 192) fp16, w2 (192, 768) fp16, x (M, 192) fp32 updated in place
-int launch_mlp_fused_c192(const act16* y, const act16* w1, const act16* w2, const float* b1, const float* b2,
-                          const float* scale, float* x, int m, cudaStream_t stream) {
+template <int C>
+int launch_pair(const act16* y, const act16* w1, const act16* w2, const float* b1, const float* b2, const float* scale, float* x,
+                int m, cudaStream_t stream) {
+  using F = F2Cfg<C>;
   if (m == 0) return 0;
   CUtensorMap map_y, map_w1, map_w2, map_x;
-  if (int rc = tc_make_map_f16_box(&map_y, y, m, kC2, kBM2, 64)) return rc;
-  if (int rc = tc_make_map_f16_box(&map_w1, w1, kHid2, kC2, 32, 64)) return rc;
-  if (int rc = tc_make_map_f16_box(&map_w2, w2, kC2, kHid2, 96, 64)) return rc;
-  if (int rc = tc_make_map(&map_x, x, m, kC2, kBM2, 4)) return rc;
+  if (int rc = tc_make_map_f16_box(&map_y, y, m, C, kBM2, 64)) return rc;
+  if (int rc = tc_make_map_f16_box(&map_w1, w1, F::kHid, C, 32, 64)) return rc;
+  if (int rc = tc_make_map_f16_box(&map_w2, w2, C, F::kHid, 96, 64)) return rc;
+  if (int rc = tc_make_map(&map_x, x, m, C, kBM2, 4)) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    CNB_CUDA_OK(cudaFuncSetAttribute(mlp_fused192_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2));
+    CNB_CUDA_OK(cudaFuncSetAttribute(mlp_fused_pair_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, F::kSmem));
     attr_set = true;
   }
   const int n_tiles = (int)ceil_div(m, 2 * kBM2);
   const int pairs = n_tiles < kNumSMs / 2 ? n_tiles : kNumSMs / 2;
-  mlp_fused192_kernel<<<2 * pairs, kThreads2, kSmem2, stream>>>(map_y, map_w1, map_w2, map_x, m, b1, b2, scale);
+  mlp_fused_pair_kernel<C><<<2 * pairs, kThreads2, F::kSmem, stream>>>(map_y, map_w1, map_w2, map_x, m, b1, b2, scale);
   CNB_LAUNCH_OK();
   return 0;
+}
+
+}  // namespace
+
+// y (M, C) fp16, w1 (4C, C) fp16, w2 (C, 4C) fp16, x (M, C) fp32 updated in place; C = 192 (stage 2) or 384 (stage 3)
+int launch_mlp_fused_pair(int c, const act16* y, const act16* w1, const act16* w2, const float* b1, const float* b2,
+                          const float* scale, float* x, int m, cudaStream_t stream) {
+  CNB_REQUIRE(c == 192, "fused pair MLP: C must be 192");
+  return launch_pair<192>(y, w1, w2, b1, b2, scale, x, m, stream);
+}
+int launch_mlp_fused_c192(const act16* y, const act16* w1, const act16* w2, const float* b1, const float* b2,
+                          const float* scale, float* x, int m, cudaStream_t stream) {
+  return launch_pair<192>(y, w1, w2, b1, b2, scale, x, m, stream);
 }
 
 }  // namespace cnb
