@@ -118,7 +118,7 @@ def workload_config(args, world, vocab):
 # ---------------------------------------------------------------------------------------------------------------------
 # algorithmic work per kernel class for one step (DESIGN.md "Algorithmic work")
 # ---------------------------------------------------------------------------------------------------------------------
-def algorithmic_work(batch: int, n_samples: int, act_bytes: int = 2, fused=(0, 1)):
+def algorithmic_work(batch: int, n_samples: int, act_bytes: int = 2, fused=(0, 1, 2)):
     t = n_samples // 320 + 1
     h1 = (t + 4) // 4 + 1
     hs = [h1, h1 // 2, h1 // 4, h1 // 8]
@@ -132,7 +132,7 @@ def algorithmic_work(batch: int, n_samples: int, act_bytes: int = 2, fused=(0, 1
         # dw+LN reads the fp32 residual stream and writes the GEMM operand; flops 98 per element (informational)
         work[f"dwconv_ln.s{s + 1}"] = ("hbm", DEPTHS[s] * m * c * (4 + act_bytes))
         pw = DEPTHS[s] * 2 * m * c * 4 * c
-        # stages 1-2, fast precision: ONE fused kernel does pw1 + GELU + pw2 and is bracketed under the pw1 class
+        # stages 1-3, fast precision: ONE fused kernel does pw1 + GELU + pw2 and is bracketed under the pw1 class
         work[f"gemm_pw1_gelu.s{s + 1}"] = ("tensor", 2 * pw if s in fused else pw)
         work[f"gemm_pw2_resid.s{s + 1}"] = ("tensor", pw)
         if s > 0:
@@ -144,7 +144,7 @@ def algorithmic_work(batch: int, n_samples: int, act_bytes: int = 2, fused=(0, 1
     return work
 
 
-def secondary_bounds(batch: int, n_samples: int, act_bytes: int = 2, fused=(0, 1)):
+def secondary_bounds(batch: int, n_samples: int, act_bytes: int = 2, fused=(0, 1, 2)):
     """The other roofline of the classes whose nominal bound (north_star) is not the physical one:
     pointwise GEMMs -> minimum HBM bytes (operand in, result out, fp32 residual in+out, weights once);
     depthwise conv + LN -> FP32 FMAs (49 per output element) against the CUDA-core peak."""
@@ -450,7 +450,8 @@ def run_ours(args, rank, world, local_rank):
     act_bytes = 2 if args.precision == "fast" else 4
     fused = ()
     if args.precision == "fast" and os.environ.get("CNB_NO_MLP_FUSED") is None:
-        fused = (0,) if os.environ.get("CNB_NO_MLP_FUSED192") is not None else (0, 1)
+        fused = (0,) + ((1,) if os.environ.get("CNB_NO_MLP_FUSED192") is None else ()) + (
+            (2,) if os.environ.get("CNB_NO_MLP_FUSED384") is None else ())
     work = algorithmic_work(b, n, act_bytes, fused)
     second = secondary_bounds(b, n, act_bytes, fused)
     line_extra = {}

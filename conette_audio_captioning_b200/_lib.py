@@ -63,7 +63,7 @@ SIGNATURES = {
     "cnb_caption_host_end": (C.c_int, [_vp, _i32]),
     "cnb_debug_gemm": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "cnb_debug_mlp_fused": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
-    "cnb_debug_mlp_fused192": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "cnb_debug_mlp_fused_pair": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "cnb_profile_begin": (C.c_int, [_vp]),
     "cnb_profile_end": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(_i64), _i32]),
     "cnb_launch_count": (_i64, [_vp]),

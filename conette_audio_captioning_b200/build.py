@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB_DIR = PKG / "lib"
 LIB_PATH = LIB_DIR / "libconette_b200.so"
-SOURCES = ("api.cu", "frontend.cu", "encoder.cu", "gemm_simt.cu", "gemm_tc.cu", "decoder.cu", "decoder_cluster.cu", "beam.cu", "dwconv_ring.cu", "resample.cu", "mlp_fused.cu", "mlp_fused192.cu")
+SOURCES = ("api.cu", "frontend.cu", "encoder.cu", "gemm_simt.cu", "gemm_tc.cu", "decoder.cu", "decoder_cluster.cu", "beam.cu", "dwconv_ring.cu", "resample.cu", "mlp_fused.cu", "mlp_fused_pair.cu")
 NVCC_FLAGS = (
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-shared",

@@ -600,15 +600,16 @@ static int encode_chunk(cnb_handle* h, const float* wav, int nb, int64_t n, floa
       // stage 1, fp16 operands: one kernel for the whole MLP, the hidden tile never leaves the SM (mlp_fused.cu)
       static const bool fused_ok = getenv("CNB_NO_MLP_FUSED") == nullptr;
       static const bool fused192_ok = fused_ok && getenv("CNB_NO_MLP_FUSED192") == nullptr;
+      static const bool fused384_ok = fused_ok && getenv("CNB_NO_MLP_FUSED384") == nullptr;
       if (sizeof(ActT) == 2 && c == 96 && fused_ok) {
         Prof _p(h, CNB_K_GEMM_PW1_S0 + s, st);
         if (int rc = launch_mlp_fused_c96(reinterpret_cast<const act16*>(y), b.w1_bf, b.w2_bf, b.b1, b.b2, b.scale, x, m, st))
           return rc;
         slab = m;  // skip the two-GEMM path below
-      } else if (sizeof(ActT) == 2 && c == 192 && fused192_ok) {
-        // stage 2: the same fusion over CTA pairs with the weights streamed and the hidden tile walked in chunks (mlp_fused192.cu)
+      } else if (sizeof(ActT) == 2 && ((c == 192 && fused192_ok) || (c == 384 && fused384_ok))) {
+        // stages 2-3: the same fusion over CTA pairs with the weights streamed and the hidden tile walked in chunks (mlp_fused_pair.cu)
         Prof _p(h, CNB_K_GEMM_PW1_S0 + s, st);
-        if (int rc = launch_mlp_fused_c192(reinterpret_cast<const act16*>(y), b.w1_bf, b.w2_bf, b.b1, b.b2, b.scale, x, m, st))
+        if (int rc = launch_mlp_fused_pair(c, reinterpret_cast<const act16*>(y), b.w1_bf, b.w2_bf, b.b1, b.b2, b.scale, x, m, st))
           return rc;
         slab = m;
       } else
@@ -1510,23 +1511,25 @@ int cnb_debug_mlp_fused(cnb_handle* h, const float* y, const float* w1, const fl
   return launch_mlp_fused_c96(y_bf, w1_bf, w2_bf, b1, b2, scale, x, m, st);
 }
 
-int cnb_debug_mlp_fused192(cnb_handle* h, const float* y, const float* w1, const float* b1, const float* w2, const float* b2,
-                           const float* scale, float* x, int32_t m, void* stream) {
+int cnb_debug_mlp_fused_pair(cnb_handle* h, int32_t c, const float* y, const float* w1, const float* b1, const float* w2,
+                             const float* b2, const float* scale, float* x, int32_t m, void* stream) {
   CHECK_READY(h);
   CNB_REQUIRE(y && w1 && b1 && w2 && b2 && scale && x, "null buffer");
+  CNB_REQUIRE(c == 192 || c == 384, "C must be 192 or 384");
   CNB_REQUIRE(m >= 0, "negative row count");
   cudaStream_t st = (cudaStream_t)stream;
   if (m == 0) return 0;
-  WS(h, "dbg_y", act16, (size_t)m * 192, y_bf);
-  WS(h, "dbg_w1", act16, (size_t)768 * 192, w1_bf);
-  WS(h, "dbg_w2", act16, (size_t)192 * 768, w2_bf);
-  f32_to_act16_kernel<<<(unsigned)ceil_div((int64_t)m * 192, 256), 256, 0, st>>>(y, y_bf, (int64_t)m * 192);
+  const int64_t nw = (int64_t)4 * c * c;
+  WS(h, "dbg_y", act16, (size_t)m * c, y_bf);
+  WS(h, "dbg_w1", act16, (size_t)nw, w1_bf);
+  WS(h, "dbg_w2", act16, (size_t)nw, w2_bf);
+  f32_to_act16_kernel<<<(unsigned)ceil_div((int64_t)m * c, 256), 256, 0, st>>>(y, y_bf, (int64_t)m * c);
   CNB_LAUNCH_OK();
-  f32_to_act16_kernel<<<(unsigned)ceil_div((int64_t)768 * 192, 256), 256, 0, st>>>(w1, w1_bf, (int64_t)768 * 192);
+  f32_to_act16_kernel<<<(unsigned)ceil_div(nw, 256), 256, 0, st>>>(w1, w1_bf, nw);
   CNB_LAUNCH_OK();
-  f32_to_act16_kernel<<<(unsigned)ceil_div((int64_t)768 * 192, 256), 256, 0, st>>>(w2, w2_bf, (int64_t)768 * 192);
+  f32_to_act16_kernel<<<(unsigned)ceil_div(nw, 256), 256, 0, st>>>(w2, w2_bf, nw);
   CNB_LAUNCH_OK();
-  return launch_mlp_fused_c192(y_bf, w1_bf, w2_bf, b1, b2, scale, x, m, st);
+  return launch_mlp_fused_pair(c, y_bf, w1_bf, w2_bf, b1, b2, scale, x, m, st);
 }
 
 int cnb_profile_begin(cnb_handle* h) {

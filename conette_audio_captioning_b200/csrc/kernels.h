@@ -82,9 +82,9 @@ int launch_gemm_tc(const act16* a, const act16* w, int m, int n, int k, Epilogue
 // fused pointwise MLP of ConvNeXt stage 1 (mlp_fused.cu): x (M, 96) f32 += scale * (W2 . GELU(W1 . y + b1) + b2), in place
 int launch_mlp_fused_c96(const act16* y, const act16* w1, const act16* w2, const float* b1, const float* b2,
                          const float* scale, float* x, int m, cudaStream_t stream);
-// fused pointwise MLP of ConvNeXt stage 2 (mlp_fused192.cu): x (M, 192) f32 += scale * (W2 . GELU(W1 . y + b1) + b2), CTA pairs
-int launch_mlp_fused_c192(const act16* y, const act16* w1, const act16* w2, const float* b1, const float* b2, const float* scale,
-                          float* x, int m, cudaStream_t stream);
+// fused pointwise MLP of ConvNeXt stages 2 / 3 (mlp_fused_pair.cu, C = 192 / 384): x (M, C) f32 += scale * (W2 . GELU(W1 . y + b1) + b2)
+int launch_mlp_fused_pair(int c, const act16* y, const act16* w1, const act16* w2, const float* b1, const float* b2,
+                          const float* scale, float* x, int m, cudaStream_t stream);
 int gemm_tc_init();  // resolves cuTensorMapEncodeTiled; returns 0 on success
 // 2-D row-major (rows, cols) tensor map into map_out (a 128-byte CUtensorMap): box = (box_rows, 128 bytes), 128B swizzle
 int tc_make_map(void* map_out, const void* ptr, int64_t rows, int64_t cols, int box_rows, int elt_bytes);

@@ -1,20 +1,24 @@
-// Fused ConvNeXt pointwise MLP for stage 2 (C = 192, hidden 768): x += scale * (W2 . GELU(W1 . y + b1) + b2) in ONE kernel
+// Fused ConvNeXt pointwise MLP for stages 2 and 3 (C = 192 / 384): x += scale * (W2 . GELU(W1 . y + b1) + b2) in ONE kernel
 // (reference convnext.py:66-73: pwconv1 -> GELU -> pwconv2 -> layer scale -> residual).
 //
-// Why: as two GEMM launches the stage-2 MLP writes the (M, 768) fp16 hidden tensor (347 MB per block at 64 clips) and reads it
-// back: pw2 sat at 92 % of the HBM rate and 43 % of the tensor rate.  Unlike stage 1 (mlp_fused.cu) neither the weights (590 KB)
-// nor the hidden tile (768 fp32 columns) fit on an SM, so:
+// Why: as two GEMM launches the MLP writes the (M, 4C) fp16 hidden tensor and reads it back (stage 2: 347 MB per block at 64
+// clips; pw2 sat at 92 % of the HBM rate and 43 % of the tensor rate).  Unlike stage 1 (mlp_fused.cu) neither the weights (590 KB /
+// 2.4 MB) nor the hidden tile (768 / 1536 fp32 columns) fit on an SM, so:
 //   * a CTA PAIR (one TPC) owns a 256-row tile, 128 rows per CTA, and runs every MMA as tcgen05.mma cta_group::2 (issued by the
 //     even CTA): each CTA loads only HALF of every weight chunk, which halves the L2 -> shared-memory weight stream per row;
-//   * the hidden dimension is walked in 12 chunks of 64 units.  Chunk j: GEMM1 D1[j % 3] (128 x 64 fp32 in tensor memory, three
-//     buffers) = y . W1[j]^T; the 16 epilogue warps add the bias, apply GELU and write the fp16 result back over the columns
-//     they have just read (tcgen05.st); GEMM2 takes that as its A operand straight from tensor memory and accumulates
-//     O (128 x 192 fp32, tensor memory) += H_j . W2[:, j]^T.  GEMM2 trails GEMM1 by two chunks, so the tensor pipe always has
-//     work while the epilogue runs; tcgen05.mma instructions execute in issue order, which protects the in-place reuse;
-//   * weights stream through a 4-stage ring of 24 KB (W1 half chunk 32 x 192 + W2 half chunk 96 x 64), y tiles are double
-//     buffered (the next tile is in flight a whole tile ahead), the output leaves through TMA reduce-add stores into the fp32
-//     residual stream (no residual load), 64 columns per pass through a 32 KB staging buffer.
-// HBM traffic per block: y 87 MB + x 173 MB read-modify-write in L2 = 434 MB instead of 1 128 MB.
+//   * the hidden dimension is walked in chunks of 64 units.  Chunk j: GEMM1 D1[j % kD1] (128 x 64 fp32 in tensor memory) =
+//     y . W1[j]^T; the 16 epilogue warps add the bias, apply GELU and write the fp16 result back over the columns they have just
+//     read (tcgen05.st); GEMM2 takes that as its A operand straight from tensor memory and accumulates O (128 x C fp32, tensor
+//     memory) += H_j . W2[:, j]^T (C = 384: two N = 192 instructions per k16 step).  GEMM2 trails GEMM1 by kD1 - 1 chunks, so the
+//     tensor pipe has work while the epilogue (tensor-memory load, GELU at the MUFU rate, store, an arrival that crosses the
+//     pair: ~1 100 cycles) runs; tcgen05.mma instructions execute in issue order, which protects the in-place reuse;
+//   * W1 half-chunks and W2 half-chunks stream through two separate TMA rings (a W1 slot is free as soon as its GEMM1 has
+//     completed, a W2 slot only after the trailing GEMM2), the output leaves through TMA reduce-add stores into the fp32 residual
+//     stream (no residual load) through a small staging buffer.
+//   C = 192: y double buffered, 4 + 4 ring slots of 12 KB, three D1 buffers, O preloaded into registers, 64 columns per store pass.
+//   C = 384: O fills 384 of the 512 tensor-memory columns (two D1 buffers), ONE 96 KB y buffer (the next tile is requested when
+//            the last GEMM1 has read it, behind the last two GEMM2s and the output phase), 2 + 2 ring slots of 24 KB, 32 columns
+//            per store pass read from tensor memory pass by pass.
 // Warp roles (both CTAs): warp 0 TMA producer, warp 1 TMEM allocator (+ MMA issuer in the even CTA), warps 2..17 epilogue,
 // warp 18 output stores.  Barriers that both CTAs feed (operand bytes, "hidden chunk written", "output read") live in the even CTA.
 #include <cuda.h>
@@ -33,34 +37,42 @@ namespace {
 constexpr int kBM2 = 128, kCh2 = 64;                   // rows per CTA, hidden units per chunk
 constexpr int kThreads2 = 64 + 32 * kEpiWarps + 32;     // producer, MMA issuer, 16 epilogue warps, store warp
 constexpr int kStgBox = kBM2 * 128;                     // [128 rows x 32 fp32]
+constexpr int kTmemCols2 = 512;
 
-// C = 192 (stage 2): y double buffered, 4 weight stages, 3 hidden-chunk buffers in tensor memory, 64 output columns per store pass.
-// (C = 384, stage 3, was budgeted and dropped: O would fill 384 of the 512 tensor-memory columns and shared memory would only
-// leave one 96 KB y buffer and two 48 KB weight stages -- too shallow a ring to keep the tensor pipe fed, for a block that already
-// runs at 65-77 % of the tensor rate as two GEMMs.)
 template <int C> struct F2Cfg {
   static constexpr int kHid = 4 * C, kNCh = kHid / kCh2, kKB = C / 64, kNSplit = C / 192;
-  static constexpr int kYBufs = 2, kRing = 4, kStgBoxes = 2, kD1Bufs = 3;
+  static constexpr int kYBufs = C == 192 ? 2 : 1, kR1 = C == 192 ? 4 : 2, kR2 = C == 192 ? 4 : 2;
+  static constexpr int kStgBoxes = C == 192 ? 2 : 1, kD1 = C == 192 ? 3 : 2, kLag = kD1 - 1;
+  static constexpr bool kPreloadO = C == 192;
   static constexpr int kYBytes = kKB * kBM2 * 128;           // kKB boxes of [128 rows x 64 fp16]
   static constexpr int kW1Half = kKB * 32 * 128;             // kKB boxes of [32 rows x 64 fp16] (this CTA's half of the chunk)
   static constexpr int kW2Half = kNSplit * 96 * 128;         // kNSplit boxes of [96 output rows x 64 fp16]
-  static constexpr int kStage = kW1Half + kW2Half;
   static constexpr int kPassCols = 32 * kStgBoxes, kPasses = C / kPassCols, kColsPerThread = kPassCols / 4;
   static constexpr int kOffY = 0;
-  static constexpr int kOffRing = kOffY + kYBufs * kYBytes;
-  static constexpr int kOffStg = kOffRing + kRing * kStage;
+  static constexpr int kOffW1 = kOffY + kYBufs * kYBytes;
+  static constexpr int kOffW2 = kOffW1 + kR1 * kW1Half;
+  static constexpr int kOffStg = kOffW2 + kR2 * kW2Half;
   static constexpr int kOffVec = kOffStg + kStgBoxes * kStgBox;   // b2 (C) | scale (C); b1 is read through the L1 (no room)
   static constexpr int kOffBar = kOffVec + 2 * C * 4;
   static constexpr int kSmem = kOffBar + 256 + 1024;
   static constexpr int kTmemD1 = C;                          // O 0..C-1 | D1[b] at C + 64 b
-  static_assert(C == 192, "stage 2");
-  static_assert(kNCh % kD1Bufs == 0, "hidden chunks per buffer");
-  static_assert(kOffRing % 1024 == 0 && kOffStg % 1024 == 0 && kStage % 1024 == 0 && kW1Half % 1024 == 0, "align");
+  static_assert(C == 192 || C == 384, "stage 2 / stage 3");
+  static_assert(kNCh % kD1 == 0, "hidden chunks per buffer");
+  static_assert(kOffW1 % 1024 == 0 && kOffW2 % 1024 == 0 && kOffStg % 1024 == 0 && kW1Half % 1024 == 0 && kW2Half % 1024 == 0, "align");
   static_assert(kSmem <= 232448, "shared memory budget");
-  static_assert(C + kD1Bufs * kCh2 <= 512, "tensor memory columns");
+  static_assert(C + kD1 * kCh2 <= 512, "tensor memory columns");
 };
-constexpr int kTmemCols2 = 512;
+// barrier table (byte offsets from kOffBar; every CTA has its own copy, "lead" = the even CTA's copy is the one that counts)
+constexpr uint32_t kBAFull = 0, kBAEmpty = 16, kBW1Full = 32, kBW1Empty = 64, kBW2Full = 96, kBW2Empty = 128, kBD1Full = 160,
+                   kBHFull = 184, kBOFull = 208, kBOEmpty = 216, kBStgReady = 224, kBStgFree = 232, kBTmemSlot = 240;
 
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t* r) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
                "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
@@ -86,24 +98,14 @@ mlp_fused_pair_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_co
                       const __grid_constant__ CUtensorMap map_w2, const __grid_constant__ CUtensorMap map_x, int M,
                       const float* __restrict__ b1, const float* __restrict__ b2, const float* __restrict__ scale) {
   using F = F2Cfg<C>;
-  constexpr int kNCh = F::kNCh, kKB = F::kKB, kRing = F::kRing, kYBufs = F::kYBufs;
+  constexpr int kNCh = F::kNCh, kKB = F::kKB, kR1 = F::kR1, kR2 = F::kR2, kYBufs = F::kYBufs, kD1 = F::kD1, kLag = F::kLag;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
   float* s_b2 = reinterpret_cast<float*>(sm + F::kOffVec);
   float* s_sc = s_b2 + C;
   const uint32_t bars = base + F::kOffBar;
-  auto a_full = [&](int b) { return bars + 8u * b; };            // even CTA: y tile b of both CTAs has landed
-  auto a_empty = [&](int b) { return bars + 16 + 8u * b; };      // both: the last GEMM1 reading y tile b has completed
-  auto w_full = [&](int s) { return bars + 32 + 8u * s; };       // even CTA: weight stage s of both CTAs has landed
-  auto w_empty = [&](int s) { return bars + 64 + 8u * s; };      // both: the MMAs reading weight stage s have completed
-  auto d1_full = [&](int b) { return bars + 96 + 8u * b; };      // both: GEMM1 into D1[b] has completed
-  auto h_full = [&](int b) { return bars + 120 + 8u * b; };      // even CTA: both CTAs' epilogues have written hidden chunk b
-  const uint32_t o_full = bars + 144, o_empty = bars + 152;      // both | even CTA
-  const uint32_t stg_ready = bars + 160, stg_free = bars + 168;  // local
-  const uint32_t tmem_slot = bars + 176;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + F::kOffBar + 176);
-  constexpr int kD1 = F::kD1Bufs;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + F::kOffBar + kBTmemSlot);
 
   for (int i = threadIdx.x; i < C; i += kThreads2) {
     s_b2[i] = b2[i];
@@ -116,26 +118,29 @@ mlp_fused_pair_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_co
 
   if (threadIdx.x == 0) {
     for (int b = 0; b < 2; ++b) {
-      mbar_init(a_full(b), 1);
-      mbar_init(a_empty(b), 1);
+      mbar_init(bars + kBAFull + 8u * b, 1);     // even CTA: y tile b of both CTAs has landed
+      mbar_init(bars + kBAEmpty + 8u * b, 1);    // both: the last GEMM1 reading y tile b has completed
     }
-    for (int b = 0; b < kD1; ++b) {
-      mbar_init(d1_full(b), 1);
-      mbar_init(h_full(b), 2 * kEpiWarps);   // one arrival per epilogue warp of both CTAs
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(bars + kBW1Full + 8u * s, 1);    // even CTA: W1 slot s of both CTAs has landed
+      mbar_init(bars + kBW1Empty + 8u * s, 1);   // both: the GEMM1 reading W1 slot s has completed
+      mbar_init(bars + kBW2Full + 8u * s, 1);
+      mbar_init(bars + kBW2Empty + 8u * s, 1);   // both: the GEMM2 reading W2 slot s has completed
     }
-    for (int s = 0; s < kRing; ++s) {
-      mbar_init(w_full(s), 1);
-      mbar_init(w_empty(s), 1);
+    for (int b = 0; b < 3; ++b) {
+      mbar_init(bars + kBD1Full + 8u * b, 1);               // both: GEMM1 into D1[b] has completed
+      mbar_init(bars + kBHFull + 8u * b, 2 * kEpiWarps);    // even CTA: one arrival per epilogue warp of both CTAs
     }
-    mbar_init(o_full, 1);
-    mbar_init(o_empty, 2 * kEpiWarps);
-    mbar_init(stg_ready, kEpiWarps);
-    mbar_init(stg_free, 1);
+    mbar_init(bars + kBOFull, 1);
+    mbar_init(bars + kBOEmpty, 2 * kEpiWarps);
+    mbar_init(bars + kBStgReady, kEpiWarps);
+    mbar_init(bars + kBStgFree, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {  // the same warp of both CTAs allocates the same columns in both tensor memories
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols2) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars + kBTmemSlot), "r"(kTmemCols2)
+                 : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
@@ -148,14 +153,13 @@ mlp_fused_pair_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_co
     const uint32_t sb = __shfl_sync(0xffffffffu, base, 0);
     const uint32_t ubars = sb + F::kOffBar;
     const uint32_t urank = __shfl_sync(0xffffffffu, rank, 0);
-    uint32_t g = 0;   // running weight-chunk counter: chunk g lives in ring stage g % kRing
+    uint32_t g = 0;   // running weight-chunk counter: chunk g lives in W1 slot g % kR1 and W2 slot g % kR2
     int it = 0;
     for (int t = pair; t < n_tiles; t += n_pairs, ++it) {
       const int b = it % kYBufs;
-      const uint32_t use = (uint32_t)(it / kYBufs);   // how often buffer b has been filled before
-      mbar_wait(ubars + 16 + 8u * b, (use & 1u) ^ 1u);   // a_empty(b), this CTA's copy
+      mbar_wait(ubars + kBAEmpty + 8u * b, ((uint32_t)(it / kYBufs) & 1u) ^ 1u);   // this CTA's copy
       if (elect_one()) {
-        const uint32_t full = ubars + 8u * b;
+        const uint32_t full = ubars + kBAFull + 8u * b;
         const uint32_t lead = mapa_cluster(full, 0);
         if (urank == 0) mbar_expect_tx(full, 2 * F::kYBytes);
 #pragma unroll
@@ -164,19 +168,25 @@ mlp_fused_pair_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_co
       }
       __syncwarp();
       for (int j = 0; j < kNCh; ++j, ++g) {
-        const uint32_t s = g % kRing;
-        mbar_wait(ubars + 64 + 8u * s, ((g / kRing) & 1u) ^ 1u);   // w_empty(s)
+        const uint32_t s1 = g % kR1, s2 = g % kR2;
+        mbar_wait(ubars + kBW1Empty + 8u * s1, ((g / kR1) & 1u) ^ 1u);
         if (elect_one()) {
-          const uint32_t full = ubars + 32 + 8u * s;
+          const uint32_t full = ubars + kBW1Full + 8u * s1;
           const uint32_t lead = mapa_cluster(full, 0);
-          const uint32_t dst = sb + F::kOffRing + s * F::kStage;
-          if (urank == 0) mbar_expect_tx(full, 2 * F::kStage);
+          if (urank == 0) mbar_expect_tx(full, 2 * F::kW1Half);
 #pragma unroll
           for (int kb = 0; kb < kKB; ++kb)
-            tma_load_2d_pair(dst + kb * (32 * 128), &map_w1, kb * 64, j * kCh2 + (int)urank * 32, lead);
+            tma_load_2d_pair(sb + F::kOffW1 + s1 * F::kW1Half + kb * (32 * 128), &map_w1, kb * 64, j * kCh2 + (int)urank * 32, lead);
+        }
+        __syncwarp();
+        mbar_wait(ubars + kBW2Empty + 8u * s2, ((g / kR2) & 1u) ^ 1u);
+        if (elect_one()) {
+          const uint32_t full = ubars + kBW2Full + 8u * s2;
+          const uint32_t lead = mapa_cluster(full, 0);
+          if (urank == 0) mbar_expect_tx(full, 2 * F::kW2Half);
 #pragma unroll
           for (int ns = 0; ns < F::kNSplit; ++ns)   // output columns [192 ns + 96 rank, +96) of W2's k-columns [64 j, +64)
-            tma_load_2d_pair(dst + F::kW1Half + ns * (96 * 128), &map_w2, j * kCh2, ns * 192 + (int)urank * 96, lead);
+            tma_load_2d_pair(sb + F::kOffW2 + s2 * F::kW2Half + ns * (96 * 128), &map_w2, j * kCh2, ns * 192 + (int)urank * 96, lead);
         }
         __syncwarp();
       }
@@ -193,50 +203,50 @@ mlp_fused_pair_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_co
       // GEMM2 of chunk jj (running index gj) of tile `cit`: O (+)= H_jj . W2[:, jj]^T
       auto gemm2 = [&](int jj, uint32_t gj, int cit) {
         const int hb = jj % kD1;
-        mbar_wait(ubars + 120 + 8u * hb, (uint32_t)(cit * (kNCh / kD1) + jj / kD1) & 1u);   // h_full(hb)
-        if (jj == 0) mbar_wait(ubars + 152, ((uint32_t)cit & 1u) ^ 1u);                     // o_empty: previous tile's output read
+        const uint32_t s2 = gj % kR2;
+        mbar_wait(ubars + kBHFull + 8u * hb, (uint32_t)(cit * (kNCh / kD1) + jj / kD1) & 1u);   // both epilogues wrote H_jj
+        mbar_wait(ubars + kBW2Full + 8u * s2, (gj / kR2) & 1u);
+        if (jj == 0) mbar_wait(ubars + kBOEmpty, ((uint32_t)cit & 1u) ^ 1u);                    // previous tile's output read
         tcgen05_fence_after();
         if (elect_one()) {
-          const uint32_t s = gj % kRing;
           const uint32_t a_col = tb + (uint32_t)(F::kTmemD1 + hb * kCh2);
 #pragma unroll
           for (int ns = 0; ns < F::kNSplit; ++ns) {
-            const uint64_t bdesc = make_smem_desc(sb + F::kOffRing + s * F::kStage + F::kW1Half + ns * (96 * 128));
+            const uint64_t bdesc = make_smem_desc(sb + F::kOffW2 + s2 * F::kW2Half + ns * (96 * 128));
 #pragma unroll
             for (int k = 0; k < 4; ++k)   // k16 step k: packed fp16 at columns [16 k, 16 k + 8) of the chunk (written by sub-warp k)
               tcgen05_mma_f16_ts_pair(tb + (uint32_t)(ns * 192), a_col + 16u * k, bdesc + 2 * k, idesc2, (jj | k) != 0);
           }
-          tcgen05_commit_pair(ubars + 64 + 8u * s);               // w_empty(s): both halves of the stage have been read
-          if (jj == kNCh - 1) tcgen05_commit_pair(ubars + 144);   // o_full
+          tcgen05_commit_pair(ubars + kBW2Empty + 8u * s2);
+          if (jj == kNCh - 1) tcgen05_commit_pair(ubars + kBOFull);
         }
         __syncwarp();
       };
       for (int t = pair; t < n_tiles; t += n_pairs, ++it) {
         const int b = it % kYBufs;
-        mbar_wait(ubars + 8u * b, (uint32_t)(it / kYBufs) & 1u);   // a_full(b)
+        mbar_wait(ubars + kBAFull + 8u * b, (uint32_t)(it / kYBufs) & 1u);
         for (int j = 0; j < kNCh; ++j, ++g) {
-          const uint32_t s = g % kRing;
-          mbar_wait(ubars + 32 + 8u * s, (g / kRing) & 1u);   // w_full(s)
+          const uint32_t s1 = g % kR1;
+          mbar_wait(ubars + kBW1Full + 8u * s1, (g / kR1) & 1u);
           tcgen05_fence_after();
           if (elect_one()) {
             const uint32_t d1 = tb + (uint32_t)(F::kTmemD1 + (j % kD1) * kCh2);
 #pragma unroll
             for (int kb = 0; kb < kKB; ++kb) {
               const uint64_t adesc = make_smem_desc(sb + F::kOffY + b * F::kYBytes + kb * (kBM2 * 128));
-              const uint64_t bdesc = make_smem_desc(sb + F::kOffRing + s * F::kStage + kb * (32 * 128));
+              const uint64_t bdesc = make_smem_desc(sb + F::kOffW1 + s1 * F::kW1Half + kb * (32 * 128));
 #pragma unroll
               for (int k = 0; k < 4; ++k) tcgen05_mma_f16_pair(d1, adesc + 2 * k, bdesc + 2 * k, idesc1, (kb | k) != 0);
             }
-            tcgen05_commit_pair(ubars + 96 + 8u * (j % kD1));              // d1_full(j % 3)
-            if (j == kNCh - 1) tcgen05_commit_pair(ubars + 16 + 8u * b);   // a_empty(b): y tile b is free
+            tcgen05_commit_pair(ubars + kBD1Full + 8u * (j % kD1));
+            tcgen05_commit_pair(ubars + kBW1Empty + 8u * s1);
+            if (j == kNCh - 1) tcgen05_commit_pair(ubars + kBAEmpty + 8u * b);   // y tile b is free
           }
           __syncwarp();
-          // GEMM2 trails GEMM1 by TWO chunks: while the epilogue turns chunk j - 1 into fp16 (tensor-memory load, GELU at the
-          // MUFU rate, store, an arrival that crosses the pair: ~1 100 cycles) the tensor pipe has GEMM1(j) and GEMM2(j - 2)
-          if (j >= 2) gemm2(j - 2, g - 2, it);
+          if (j >= kLag) gemm2(j - kLag, g - kLag, it);   // GEMM2 trails GEMM1 by kLag chunks
         }
-        gemm2(kNCh - 2, g - 2, it);
-        gemm2(kNCh - 1, g - 1, it);
+#pragma unroll
+        for (int r = kLag; r >= 1; --r) gemm2(kNCh - r, g - r, it);
       }
     }
   } else if (warp == kEpiWarps + 2) {
@@ -247,14 +257,14 @@ mlp_fused_pair_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_co
     uint32_t pc = 0;
     for (int t = pair; t < n_tiles; t += n_pairs) {
       for (int p = 0; p < F::kPasses; ++p, ++pc) {
-        mbar_wait(ubars + 160, pc & 1u);   // stg_ready: the 16 epilogue warps have written this pass
+        mbar_wait(ubars + kBStgReady, pc & 1u);   // the 16 epilogue warps have written this pass
         if (elect_one()) {
 #pragma unroll
           for (int bx = 0; bx < F::kStgBoxes; ++bx)
             tma_reduce_add_2d(&map_x, sb + F::kOffStg + bx * kStgBox, F::kPassCols * p + 32 * bx, t * (2 * kBM2) + (int)urank * kBM2);
           bulk_commit();
           bulk_wait_read<0>();             // the stores have read the staging buffer
-          mbar_arrive(ubars + 168);        // stg_free
+          mbar_arrive(ubars + kBStgFree);
         }
         __syncwarp();
       }
@@ -267,8 +277,8 @@ mlp_fused_pair_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_co
     const int sub = (warp - 2) >> 2;          // 16-column slice of a hidden chunk / quarter of an output pass
     const int row = lane_grp * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
-    const uint32_t lead_h0 = mapa_cluster(h_full(0), 0);
-    const uint32_t lead_oe = mapa_cluster(o_empty, 0);
+    const uint32_t lead_h0 = mapa_cluster(bars + kBHFull, 0);
+    const uint32_t lead_oe = mapa_cluster(bars + kBOEmpty, 0);
     constexpr int CPT = F::kColsPerThread;    // output columns per thread and pass (16 or 8)
     uint32_t pc = 0;
     int it = 0;
@@ -276,7 +286,7 @@ mlp_fused_pair_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_co
 #pragma unroll 1
       for (int j = 0; j < kNCh; ++j) {
         const int hb = j % kD1;
-        mbar_wait(d1_full(hb), (uint32_t)(it * (kNCh / kD1) + j / kD1) & 1u);
+        mbar_wait(bars + kBD1Full + 8u * hb, (uint32_t)(it * (kNCh / kD1) + j / kD1) & 1u);
         tcgen05_fence_after();
         const uint32_t taddr = lane_addr + (uint32_t)(F::kTmemD1 + hb * kCh2 + 16 * sub);
         float v[16];
@@ -301,20 +311,33 @@ mlp_fused_pair_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_co
         if (lane == 0) mbar_arrive_cluster(lead_h0 + 8u * hb);
       }
       // ---- output: O (128 x C) + bias2, layer scale; the residual add happens in the TMA reduce store ----
-      mbar_wait(o_full, (uint32_t)it & 1u);
+      mbar_wait(bars + kBOFull, (uint32_t)it & 1u);
       tcgen05_fence_after();
-      // few enough columns to hold in registers: the accumulator is handed back before the stores start
-      float o[F::kPasses][CPT];
+      float o[F::kPreloadO ? F::kPasses : 1][16];
+      if constexpr (F::kPreloadO) {   // few enough columns to hold: the accumulator is handed back before the stores start
 #pragma unroll
-      for (int p = 0; p < F::kPasses; ++p) tmem_ld_32x16(lane_addr + (uint32_t)(F::kPassCols * p + CPT * sub), o[p]);
-      tmem_ld_wait();
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(lead_oe);   // the accumulator may be overwritten by the next tile's GEMM2
+        for (int p = 0; p < F::kPasses; ++p) tmem_ld_32x16(lane_addr + (uint32_t)(F::kPassCols * p + CPT * sub), o[p]);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(lead_oe);   // the accumulator may be overwritten by the next tile's GEMM2
+      }
 #pragma unroll
       for (int p = 0; p < F::kPasses; ++p, ++pc) {
-        const float (&ov)[CPT] = o[p];
-        mbar_wait(stg_free, (pc & 1u) ^ 1u);   // the previous pass has left the staging buffer
+        float ov[CPT];
+        if constexpr (F::kPreloadO) {
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) ov[i] = o[p][i];
+        } else {
+          tmem_ld_32x8(lane_addr + (uint32_t)(F::kPassCols * p + CPT * sub), ov);
+          tmem_ld_wait();
+          if (p == F::kPasses - 1) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(lead_oe);
+          }
+        }
+        mbar_wait(bars + kBStgFree, (pc & 1u) ^ 1u);   // the previous pass has left the staging buffer
         const int c0 = F::kPassCols * p + CPT * sub;   // first of this thread's output columns
         const int in_pass = CPT * sub;                 // column offset inside the pass
         const uint32_t box = base + F::kOffStg + (uint32_t)(in_pass >> 5) * kStgBox + (uint32_t)row * 128u;
@@ -330,7 +353,7 @@ mlp_fused_pair_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_co
         }
         fence_async_smem();   // generic-proxy writes -> visible to the TMA store issued by the store warp
         __syncwarp();
-        if (lane == 0) mbar_arrive(stg_ready);
+        if (lane == 0) mbar_arrive(bars + kBStgReady);
       }
     }
   }
@@ -370,12 +393,10 @@ int launch_pair(const act16* y, const act16* w1, const act16* w2, const float* b
 // y (M, C) fp16, w1 (4C, C) fp16, w2 (C, 4C) fp16, x (M, C) fp32 updated in place; C = 192 (stage 2) or 384 (stage 3)
 int launch_mlp_fused_pair(int c, const act16* y, const act16* w1, const act16* w2, const float* b1, const float* b2,
                           const float* scale, float* x, int m, cudaStream_t stream) {
-  CNB_REQUIRE(c == 192, "fused pair MLP: C must be 192");
-  return launch_pair<192>(y, w1, w2, b1, b2, scale, x, m, stream);
-}
-int launch_mlp_fused_c192(const act16* y, const act16* w1, const act16* w2, const float* b1, const float* b2,
-                          const float* scale, float* x, int m, cudaStream_t stream) {
-  return launch_pair<192>(y, w1, w2, b1, b2, scale, x, m, stream);
+  if (c == 192) return launch_pair<192>(y, w1, w2, b1, b2, scale, x, m, stream);
+  if (c == 384) return launch_pair<384>(y, w1, w2, b1, b2, scale, x, m, stream);
+  CNB_REQUIRE(false, "fused pair MLP: C must be 192 or 384");
+  return -1;
 }
 
 }  // namespace cnb

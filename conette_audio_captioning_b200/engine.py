@@ -187,13 +187,14 @@ class Engine:
                                                 b2.data_ptr(), scale.data_ptr(), out.data_ptr(), y.shape[0], self._stream()))
         return out
 
-    def debug_mlp_fused192(self, y: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, scale: Tensor, x: Tensor) -> Tensor:
-        """Test hook: the same through the fused stage-2 MLP kernel (C = 192, hidden 768); returns the new x."""
+    def debug_mlp_fused_pair(self, y: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, scale: Tensor, x: Tensor) -> Tensor:
+        """Test hook: the same through the fused stage-2 / stage-3 MLP kernel (C = 192 / 384, hidden 4C); returns the new x."""
         y, w1, b1, w2, b2, scale = (self._dev(v, torch.float32) for v in (y, w1, b1, w2, b2, scale))
         out = self._dev(x, torch.float32).clone()
-        assert y.shape[1] == 192 and w1.shape == (768, 192) and w2.shape == (192, 768) and out.shape == y.shape
-        _lib.check(self.lib.cnb_debug_mlp_fused192(self.handle, y.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
-                                                   b2.data_ptr(), scale.data_ptr(), out.data_ptr(), y.shape[0], self._stream()))
+        c = y.shape[1]
+        assert c in (192, 384) and w1.shape == (4 * c, c) and w2.shape == (c, 4 * c) and out.shape == y.shape
+        _lib.check(self.lib.cnb_debug_mlp_fused_pair(self.handle, c, y.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                                                     b2.data_ptr(), scale.data_ptr(), out.data_ptr(), y.shape[0], self._stream()))
         return out
 
     def _alloc_outputs(self, b: int, beam: int, max_len: int):

@@ -163,10 +163,10 @@ int cnb_debug_gemm(cnb_handle* h, const float* a, const float* w, const float* b
  * precision mode uses (y, W1, W2 and the hidden activations are rounded to fp16, fp32 accumulation and residual). */
 int cnb_debug_mlp_fused(cnb_handle* h, const float* y, const float* w1, const float* b1, const float* w2, const float* b2,
                         const float* scale, float* x, int32_t m, void* stream);
-/* Test hook: the same for the fused stage-2 MLP kernel (C = 192, hidden 768; CTA pairs, streamed weights): y (M, 192),
- * w1 (768, 192), w2 (192, 768), x (M, 192) updated in place. */
-int cnb_debug_mlp_fused192(cnb_handle* h, const float* y, const float* w1, const float* b1, const float* w2, const float* b2,
-                           const float* scale, float* x, int32_t m, void* stream);
+/* Test hook: the same for the fused stage-2 / stage-3 MLP kernel (C = 192 / 384, hidden 4C; CTA pairs, streamed weights):
+ * y (M, C), w1 (4C, C), w2 (C, 4C), x (M, C) updated in place. */
+int cnb_debug_mlp_fused_pair(cnb_handle* h, int32_t c, const float* y, const float* w1, const float* b1, const float* w2,
+                             const float* b2, const float* scale, float* x, int32_t m, void* stream);
 
 /* Per-kernel-class device timing: between cnb_profile_begin and cnb_profile_end every launch group issued through this
  * handle is bracketed by a CUDA event pair on the launching stream; _end synchronises and returns, per class, the summed

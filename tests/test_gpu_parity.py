@@ -257,30 +257,31 @@ def test_fused_mlp_kernel(eng_fast, m):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("c", [192, 384])
 @pytest.mark.parametrize("m", [1, 129, 256, 257, 74 * 256, 74 * 256 * 3 + 77])
-def test_fused_mlp192_kernel(eng_fast, m):
-    """The fused stage-2 MLP kernel (CTA pairs, streamed weight ring, hidden chunks in tensor memory) against a plain fp32 torch
-    evaluation of convnext.py:66-73 on the same fp16-rounded operands: partial pairs (the odd CTA entirely out of range), exact
-    tiles, one tile per pair and the multi-tile pipeline with a ragged tail.  Tolerance: 3e-4 rel-L2 on the update."""
-    g = torch.Generator().manual_seed(m + 7)
+def test_fused_mlp_pair_kernel(eng_fast, c, m):
+    """The fused stage-2 / stage-3 MLP kernel (CTA pairs, streamed weight rings, hidden chunks in tensor memory) against a plain fp32
+    torch evaluation of convnext.py:66-73 on the same fp16-rounded operands: partial pairs (the odd CTA entirely out of range),
+    exact tiles, one tile per pair and the multi-tile pipeline with a ragged tail.  Tolerance: 3e-4 rel-L2 on the update."""
+    g = torch.Generator().manual_seed(m + c)
     dev = "cuda"
-    y = torch.randn(m, 192, generator=g).to(dev)
-    x = torch.randn(m, 192, generator=g).to(dev)
-    w1 = (torch.randn(768, 192, generator=g) / 192 ** 0.5).to(dev)
-    w2 = (torch.randn(192, 768, generator=g) / 768 ** 0.5).to(dev)
-    b1 = (0.3 * torch.randn(768, generator=g)).to(dev)
-    b2 = (0.3 * torch.randn(192, generator=g)).to(dev)
-    scale = (0.5 + torch.rand(192, generator=g)).to(dev)
-    got = eng_fast.debug_mlp_fused192(y, w1, b1, w2, b2, scale, x)
+    y = torch.randn(m, c, generator=g).to(dev)
+    x = torch.randn(m, c, generator=g).to(dev)
+    w1 = (torch.randn(4 * c, c, generator=g) / c ** 0.5).to(dev)
+    w2 = (torch.randn(c, 4 * c, generator=g) / (4 * c) ** 0.5).to(dev)
+    b1 = (0.3 * torch.randn(4 * c, generator=g)).to(dev)
+    b2 = (0.3 * torch.randn(c, generator=g)).to(dev)
+    scale = (0.5 + torch.rand(c, generator=g)).to(dev)
+    got = eng_fast.debug_mlp_fused_pair(y, w1, b1, w2, b2, scale, x)
     hf = lambda v: v.to(torch.float16).to(torch.float32)
     hid = hf(torch.nn.functional.gelu(hf(y) @ hf(w1).T + b1))
     want = x + scale * (hid @ hf(w2).T + b2)
     upd_err = float(((got - x) - (want - x)).norm() / (want - x).norm())
-    print(f"fused MLP-192 m={m}: update rel-L2 {upd_err:.2e}")
+    print(f"fused pair MLP C={c} m={m}: update rel-L2 {upd_err:.2e}")
     assert upd_err < 3e-4, upd_err
     assert float((got - want).abs().max()) < 5e-3
     if m > 1:
-        one = eng_fast.debug_mlp_fused192(y[-1:], w1, b1, w2, b2, scale, x[-1:])
+        one = eng_fast.debug_mlp_fused_pair(y[-1:], w1, b1, w2, b2, scale, x[-1:])
         assert torch.equal(one, got[-1:])
 
 
