@@ -66,6 +66,8 @@ SIGNATURES = {
     "cnb_debug_mlp_fused_pair": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "cnb_profile_begin": (C.c_int, [_vp]),
     "cnb_profile_end": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(_i64), _i32]),
+    "cnb_profile_timeline_begin": (C.c_int, [_vp]),
+    "cnb_profile_timeline_end": (C.c_int, [_vp, C.POINTER(_i32), C.POINTER(C.c_float), C.POINTER(C.c_float), _i32, C.POINTER(_i32)]),
     "cnb_launch_count": (_i64, [_vp]),
     "cnb_device_bytes": (_i64, [_vp]),
 }

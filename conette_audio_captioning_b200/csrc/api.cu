@@ -112,9 +112,12 @@ struct cnb_handle {
   cudaEvent_t ev_lens = nullptr;         // the last H2D copy out of pin_lens
   int32_t* pin_lens = nullptr;           // pinned staging for the per-clip frame counts
   int pin_lens_cap = 0;
+  int enc_narrow_blocks = 0;             // streaming: the first ConvNeXt blocks of this encode share the GPU with a decoder ...
+  int enc_narrow_sms = 148;              // ... that leaves this many SMs (set_sm_budget)
   bool pre_stem_done = false;            // encode_chunk: the "logmel" / "xa" workspaces already hold this chunk's stem output
   // optional per-kernel-class timing (cnb_profile_begin/end): CUDA event pairs around every launch
   bool prof_on = false;
+  bool prof_timeline = false;            // cnb_profile_timeline_begin: keep the streaming overlap while bracketing (see _end)
   std::vector<cudaEvent_t> prof_events;  // pool, pairs (start, stop)
   std::vector<int> prof_class;           // class of pair i
   size_t prof_used = 0;                  // events used
@@ -574,6 +577,7 @@ static int encode_chunk(cnb_handle* h, const float* wav, int nb, int64_t n, floa
       // downsample: LN(channels_first) + 2x2/s2 conv as pack + GEMM (K = 4*Cin)
       const int cin = kDims[s - 1], hin = g.h[s - 1], win = kStageW[s - 1];
       const DownW& d = h->down[s - 1];
+      set_sm_budget(bi < h->enc_narrow_blocks ? h->enc_narrow_sms : kNumSMs);
       { Prof _p(h, CNB_K_DS_PACK, st); if (int rc = launch_ln_pack2x2<ActT>(x, nb, hin, win, cin, d.ln_g, d.ln_b, y, st)) return rc; }
       const int m = nb * hh * ww;
       EpiParams ep;
@@ -585,6 +589,7 @@ static int encode_chunk(cnb_handle* h, const float* wav, int nb, int64_t n, floa
     const int m = nb * hh * ww;
     for (int j = 0; j < kDepths[s]; ++j, ++bi) {
       const BlockW& b = h->blocks[bi];
+      set_sm_budget(bi < h->enc_narrow_blocks ? h->enc_narrow_sms : kNumSMs);
       { Prof _p(h, CNB_K_DWLN_S0 + s, st); if (int rc = launch_dwconv_ln<ActT>(x, nb, hh, ww, c, b.dw_w_t, b.dw_b, b.ln_g, b.ln_b, y, st)) return rc; }
       if (tap && tap->kind == CNB_TAP_DWLN && tap->stage == s && tap->block == j)
         return copy_tap(tap, y, (int64_t)m * c, sizeof(ActT) == 2, st);
@@ -628,6 +633,7 @@ static int encode_chunk(cnb_handle* h, const float* wav, int nb, int64_t n, floa
         return copy_tap(tap, x, (int64_t)m * c, false, st);
     }
   }
+  set_sm_budget(kNumSMs);
   { Prof _p(h, CNB_K_HEAD, st); if (int rc = launch_freq_mean(x, nb, g.tp, kStageW[3], 768, frame_embs, st)) return rc; }
   if (clip_probs) {
     Prof _p(h, CNB_K_HEAD, st);
@@ -899,6 +905,14 @@ static int decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, c
   ca.tap = tap; ca.trace = nullptr; ca.ckt = nullptr; ca.tpad = 0;
   ca.rows = rows; ca.beam = beam; ca.tp = tp; ca.max_len = max_len; ca.vocab = h->cfg.vocab_size; ca.min_len = min_len;
   ca.batch = batch; ca.compact = h->dec_compact ? 1 : 0;
+  {
+    // L2 eviction priority of the weight-ring loads.  Every cluster re-reads the weights from L2 every step while the next
+    // batch's encoder streams activations through the same L2; CNB_DEC_L2=last keeps them at the lowest eviction priority.
+    // Measured on the streaming step (tools/stream_timeline.py): decoder 4.33 ms either way -- the weights stay resident
+    // anyway -- so the default is the plain policy.
+    const char* e = getenv("CNB_DEC_L2");
+    ca.w_policy = e && !strcmp(e, "last") ? kL2EvictLast : e && !strcmp(e, "first") ? kL2EvictFirst : kL2EvictNormal;
+  }
 
   const bool want_cluster = h->use_cluster == 2 || (h->use_cluster == 1 && h->cfg.precision == CNB_PRECISION_FAST);
   if (want_cluster && (h->use_cluster == 2 || decoder_cluster_supported(ca))) {
@@ -914,9 +928,33 @@ static int decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, c
     }
     ca.ckt = ckt;
     ca.tpad = tpad;
-    const bool trace_on = getenv("CNB_DEC_TRACE") != nullptr;
-    if (trace_on) {
+    // debug: time between phase marks as seen by thread 0 of the first CTA, summed over steps and layers.  CNB_DEC_TRACE=1
+    // reads it back right after the launch (serialises the host); =2 prints the PREVIOUS launch's marks before the next one,
+    // so the traced decode still overlapped whatever was enqueued after it (the streaming API's next encoder).
+    const char* trace_env = getenv("CNB_DEC_TRACE");
+    const int trace_mode = trace_env ? (trace_env[0] == '2' ? 2 : 1) : 0;
+    auto print_trace = [&](unsigned long long* dev) -> int {
+      unsigned long long t[20];
+      CNB_CUDA_OK(cudaStreamSynchronize(st));
+      CNB_CUDA_OK(cudaMemcpy(t, dev, sizeof(t), cudaMemcpyDeviceToHost));
+      static const char* names[] = {"qkv gemm", "self attn", "sa_out gemm (K-split)", "ln1", "ca_q gemm",
+                                    "cross attn", "ca_out gemm (K-split)", "ln2", "ff1 gemm", "ff2 gemm",
+                                    "ln3", "cls gemm (rounds)", "cls scan (rounds)", "beam exchange", "beam merge",
+                                    "3x wait reduce-scatter", "3x sum + all-gather push", "3x wait all-gather"};
+      double tot = 0;
+      for (int i = 0; i < 18; ++i) tot += (double)t[i];
+      if (tot == 0) return 0;
+      for (int i = 0; i < 18; ++i)
+        fprintf(stderr, "[dec cluster trace] %-24s %9.1f us  (%4.1f %%)\n", names[i], (double)t[i] / 1e3, 100.0 * t[i] / tot);
+      fprintf(stderr, "[dec cluster trace] total %.1f us\n", tot / 1e3);
+      return 0;
+    };
+    if (trace_mode) {
       WS(h, "dtrace_cl", unsigned long long, 32, tr);
+      static bool primed = false;  // the first launch has no predecessor (and the fresh buffer is not zeroed)
+      if (trace_mode == 2 && primed)
+        if (int rc = print_trace(tr)) return rc;
+      primed = true;
       CNB_CUDA_OK(cudaMemsetAsync(tr, 0, 32 * sizeof(unsigned long long), st));
       ca.trace = tr;
     }
@@ -924,19 +962,8 @@ static int decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, c
       Prof _p(h, CNB_K_DEC_GEMM, st);
       if (int rc = launch_decoder_cluster(ca, st)) return rc;
     }
-    if (trace_on) {  // debug: time between phase marks as seen by thread 0 of the first CTA, summed over steps and layers
-      unsigned long long t[20];
-      CNB_CUDA_OK(cudaStreamSynchronize(st));
-      CNB_CUDA_OK(cudaMemcpy(t, ca.trace, sizeof(t), cudaMemcpyDeviceToHost));
-      static const char* names[] = {"qkv gemm", "self attn", "sa_out gemm (K-split)", "ln1", "ca_q gemm",
-                                    "cross attn", "ca_out gemm (K-split)", "ln2", "ff1 gemm", "ff2 gemm",
-                                    "ln3", "cls gemm (rounds)", "cls scan (rounds)", "beam exchange", "beam merge",
-                                    "3x wait reduce-scatter", "3x sum + all-gather push", "3x wait all-gather"};
-      double tot = 0;
-      for (int i = 0; i < 18; ++i) tot += (double)t[i];
-      for (int i = 0; i < 18; ++i)
-        fprintf(stderr, "[dec cluster trace] %-24s %9.1f us  (%4.1f %%)\n", names[i], (double)t[i] / 1e3, 100.0 * t[i] / tot);
-    }
+    if (trace_mode == 1)
+      if (int rc = print_trace(ca.trace)) return rc;
     if (int rc = launch_beam_finalize(bs, preds, lprobs, best_len, dd, st)) return rc;
     gather_mult_kernel<<<(rows * max_len + 255) / 256, 256, 0, st>>>(bs, mult_preds, mult_lprobs, best_len, info, rows, max_len,
                                                                     batch);
@@ -1384,7 +1411,7 @@ int cnb_caption_host_begin(cnb_handle* h, const float* wav_host, const int64_t* 
   // Waveforms travel in up to 8 slices on a copy stream; the front-end and the stem of slice i run while slice i+1 is still
   // on the PCIe bus (both are per-clip kernels).  The copy stream does not wait for `st`: this slot's previous user has
   // completed (event above), so with two batches in flight the whole copy hides behind the other batch's compute.
-  const int n_slices = (batch <= chunk_size(h) && batch >= 16 && !h->prof_on && !wav_on_device) ? 8 : 1;
+  const int n_slices = (batch <= chunk_size(h) && batch >= 16 && (!h->prof_on || h->prof_timeline) && !wav_on_device) ? 8 : 1;
   if (n_slices > 1) {
     const Geometry g = geometry(n);
     if (!h->copy_stream) CNB_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -1400,7 +1427,8 @@ int cnb_caption_host_begin(cnb_handle* h, const float* wav_host, const int64_t* 
       CNB_CUDA_OK(cudaEventRecord(h->ev_slice[i], h->copy_stream));
       CNB_CUDA_OK(cudaStreamWaitEvent(st, h->ev_slice[i], 0));
       float* lm = logmel + (int64_t)b0 * g.t * kMels;
-      if (int rc = launch_frontend(wav + (int64_t)b0 * n, nb, n, h->fe, true, lm, st)) return rc;
+      { Prof _p(h, CNB_K_FRONTEND, st); if (int rc = launch_frontend(wav + (int64_t)b0 * n, nb, n, h->fe, true, lm, st)) return rc; }
+      Prof _p(h, CNB_K_STEM, st);
       if (int rc = launch_stem(lm, nb, g.t, g.h[0], h->stem_w_t, h->stem_b, h->stem_ln_g, h->stem_ln_b,
                                xa + (int64_t)b0 * g.h[0] * kStageW[0] * kDims[0], st))
         return rc;
@@ -1412,7 +1440,7 @@ int cnb_caption_host_begin(cnb_handle* h, const float* wav_host, const int64_t* 
   // decode on its own high-priority stream (cluster decoder only: the graph decoder replays on h->stream anyway)
   cudaStream_t sd = st;
   static const bool overlap_dec = getenv("CNB_NO_DEC_OVERLAP") == nullptr;
-  if (overlap_dec && h->use_cluster != 0 && h->cfg.precision == CNB_PRECISION_FAST && !h->prof_on) {
+  if (overlap_dec && h->use_cluster != 0 && h->cfg.precision == CNB_PRECISION_FAST && (!h->prof_on || h->prof_timeline)) {
     if (!h->dec_stream) {
       int lo = 0, hi = 0;
       CNB_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -1422,10 +1450,18 @@ int cnb_caption_host_begin(cnb_handle* h, const float* wav_host, const int64_t* 
   }
   // another batch in flight = this batch's encoder will share the GPU with that batch's decoder
   dwconv_set_overlap_hint(sd != st && h->host_pending[slot ^ 1]);
+  {
+    static const int nb_env = [] { const char* e = getenv("CNB_ENC_NARROW_BLOCKS"); return e ? atoi(e) : 0; }();
+    static const int ns_env = [] { const char* e = getenv("CNB_ENC_NARROW_SMS"); return e ? atoi(e) : 92; }();
+    h->enc_narrow_blocks = sd != st && h->host_pending[slot ^ 1] ? nb_env : 0;
+    h->enc_narrow_sms = ns_env;
+  }
   h->dec_compact = sd != st && h->host_pending[slot ^ 1];  // steady-state streaming: this decode will overlap the next encoder
   const int rc_cap = caption_impl(h, wav, x_lens_host, bos, forbid_host ? forbid : nullptr, batch, n, beam, min_len, max_len,
                                   preds, lprobs, mpreds, mlprobs, info, clip_probs_host ? clip : nullptr, st, sd, slot);
   dwconv_set_overlap_hint(false);
+  set_sm_budget(kNumSMs);
+  h->enc_narrow_blocks = 0;
   h->dec_compact = false;
   h->pre_stem_done = false;
   if (rc_cap) return rc_cap;
@@ -1555,6 +1591,31 @@ int cnb_profile_end(cnb_handle* h, float* ms_per_class, int64_t* brackets_per_cl
     ms_per_class[h->prof_class[i]] += ms;
     brackets_per_class[h->prof_class[i]] += 1;
   }
+  h->prof_used = 0;
+  h->prof_class.clear();
+  return 0;
+}
+
+int cnb_profile_timeline_begin(cnb_handle* h) {
+  CHECK_READY(h);
+  h->prof_on = h->prof_timeline = true;
+  h->prof_used = 0;
+  h->prof_class.clear();
+  return 0;
+}
+
+int cnb_profile_timeline_end(cnb_handle* h, int32_t* cls, float* t_begin_ms, float* t_end_ms, int32_t cap, int32_t* n_out) {
+  CHECK_READY(h);
+  CNB_REQUIRE(cls && t_begin_ms && t_end_ms && n_out && cap >= 0, "null buffer");
+  h->prof_on = h->prof_timeline = false;
+  CNB_CUDA_OK(cudaDeviceSynchronize());
+  const int n = (int)std::min<size_t>(h->prof_class.size(), (size_t)cap);
+  for (int i = 0; i < n; ++i) {
+    cls[i] = h->prof_class[i];
+    CNB_CUDA_OK(cudaEventElapsedTime(&t_begin_ms[i], h->prof_events[0], h->prof_events[2 * i]));
+    CNB_CUDA_OK(cudaEventElapsedTime(&t_end_ms[i], h->prof_events[0], h->prof_events[2 * i + 1]));
+  }
+  *n_out = (int32_t)h->prof_class.size();
   h->prof_used = 0;
   h->prof_class.clear();
   return 0;

@@ -361,30 +361,30 @@ __device__ __forceinline__ void issue_chunk(uint8_t* ring, unsigned long long* f
       for (int half = 0; half < 2; ++half)
 #pragma unroll
         for (int part = 0; part < 3; ++part)
-          tma_load_2d(dst + half * kHalfStage + part * 4096, lm + 0 + half, j * 64, part * kCD + rank * kCHead, bar);
+          tma_load_2d_hint(dst + half * kHalfStage + part * 4096, lm + 0 + half, j * 64, part * kCD + rank * kCHead, bar, a.w_policy);
     } else if (j == 4 || j == 6) {  // sa_out / ca_out (head-packed, K = 32)
       mbar_expect_tx(bar, 4 * 8192);
       const CUtensorMap* m = lm + (j == 4 ? 2 : 6);
 #pragma unroll
       for (int half = 0; half < 2; ++half)
 #pragma unroll
-        for (int t = 0; t < 2; ++t) tma_load_2d(dst + half * kHalfStage + t * 8192, m + half, 0, rank * kCD + t * 128, bar);
+        for (int t = 0; t < 2; ++t) tma_load_2d_hint(dst + half * kHalfStage + t * 8192, m + half, 0, rank * kCD + t * 128, bar, a.w_policy);
     } else if (j == 5) {  // ca_q
       mbar_expect_tx(bar, 8 * 4096);
 #pragma unroll
       for (int half = 0; half < 2; ++half)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tma_load_2d(dst + half * kHalfStage + c * 4096, lm + 4 + half, c * 64, rank * kCHead, bar);
+        for (int c = 0; c < 4; ++c) tma_load_2d_hint(dst + half * kHalfStage + c * 4096, lm + 4 + half, c * 64, rank * kCHead, bar, a.w_policy);
     } else if (j < 15) {  // FF1: hidden units [256 rank + 128 t, +128)
       const int t = (j - 7) >> 2, c = (j - 7) & 3;
       mbar_expect_tx(bar, 2 * kHalfStage);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) tma_load_2d(dst + half * kHalfStage, lm + 8 + half, c * 64, rank * kCD + t * 128, bar);
+      for (int half = 0; half < 2; ++half) tma_load_2d_hint(dst + half * kHalfStage, lm + 8 + half, c * 64, rank * kCD + t * 128, bar, a.w_policy);
     } else {  // FF2: outputs [128 t, +128), this CTA's K slice
       const int t = (j - 15) >> 2, c = (j - 15) & 3;
       mbar_expect_tx(bar, 2 * kHalfStage);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) tma_load_2d(dst + half * kHalfStage, lm + 10 + half, rank * kCD + c * 64, t * 128, bar);
+      for (int half = 0; half < 2; ++half) tma_load_2d_hint(dst + half * kHalfStage, lm + 10 + half, rank * kCD + c * 64, t * 128, bar, a.w_policy);
     }
   } else {  // classifier
     const int jj = idx - kCLayers * kChunksPerLayer;
@@ -392,7 +392,7 @@ __device__ __forceinline__ void issue_chunk(uint8_t* ring, unsigned long long* f
     mbar_expect_tx(bar, 2 * kHalfStage);
 #pragma unroll
     for (int half = 0; half < 2; ++half)
-      tma_load_2d(dst + half * kHalfStage, maps + kCLayers * kDecMapsPerLayer + half, c * 64, v0 + rd * kClsRound + t * 128, bar);
+      tma_load_2d_hint(dst + half * kHalfStage, maps + kCLayers * kDecMapsPerLayer + half, c * 64, v0 + rd * kClsRound + t * 128, bar, a.w_policy);
   }
 }
 
@@ -1195,6 +1195,7 @@ int cluster_plan(const ClusterArgs& a, ClusterPlan* p) {
   const int gmax = nr / a.beam;
   int g = (int)ceil_div(a.batch, mc);
   if (g > gmax || getenv("CNB_DEC_FILL")) g = gmax;  // CNB_DEC_FILL: experiments with full clusters
+  if (const char* eg = getenv("CNB_DEC_GROUP")) g = std::max(g, std::min(atoi(eg), gmax));  // ... or a given clips per cluster
   p->nr = nr;
   p->clips_per_group = g;
   p->n_groups = (int)ceil_div(a.batch, g);

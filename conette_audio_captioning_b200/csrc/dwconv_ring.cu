@@ -331,7 +331,7 @@ int launch_t(const float* x, int batch, int h, const float* w_t, const float* bi
   }
   const int pq = (int)ceil_div(h, 4);
   const int total = batch * Cfg::STRIPS * pq;
-  const int max_groups = kNumSMs * Cfg::CTAS_PER_SM / CS;  // one CTA (or CTA pair) per SM (pair); two for the narrow strips
+  const int max_groups = sm_budget() * Cfg::CTAS_PER_SM / CS;  // one CTA (or CTA pair) per SM (pair); two for the narrow strips
   int groups = total < max_groups ? total : max_groups;
   const int quota = (int)ceil_div(total, groups);
   groups = (int)ceil_div(total, quota);
@@ -355,6 +355,9 @@ int launch_t(const float* x, int batch, int h, const float* w_t, const float* bi
 }  // namespace
 
 // set by the streaming host API while it enqueues an encoder that will share the GPU with the previous batch's decoder
+static std::atomic<int> g_sm_budget{kNumSMs};
+void set_sm_budget(int sms) { g_sm_budget.store(sms < 8 ? 8 : sms > kNumSMs ? kNumSMs : sms, std::memory_order_relaxed); }
+int sm_budget() { return g_sm_budget.load(std::memory_order_relaxed); }
 static std::atomic<bool> g_overlap_hint{false};
 void dwconv_set_overlap_hint(bool on) { g_overlap_hint.store(on, std::memory_order_relaxed); }
 

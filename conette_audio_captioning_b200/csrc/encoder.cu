@@ -597,12 +597,12 @@ int launch_freq_mean(const float* x, int batch, int tp, int w, int c, float* out
 
 // =====================================================================================================================
 // clip head (reference convnext.py:324-334): max_t + mean_t -> LayerNorm(768, eps 1e-6) -> Linear(527) -> sigmoid
-//   one CTA (256 threads) per clip; 768 = 3 channels per thread
+//   grid (clip, class slice), 256 threads; 768 = 3 channels per thread
 // =====================================================================================================================
 __global__ void __launch_bounds__(256)
 clip_head_kernel(const float* __restrict__ fe, int tp, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
                  const float* __restrict__ w, const float* __restrict__ bias, int n_cls, float* __restrict__ out) {
-  __shared__ float s_v[768];
+  __shared__ __align__(16) float s_v[768];
   __shared__ float s_red[8];
   __shared__ float s_stat[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -651,9 +651,25 @@ clip_head_kernel(const float* __restrict__ fe, int tp, const float* __restrict__
     s_v[c] = (v[j] - mean) * rstd * ln_g[c] + ln_b[c];
   }
   __syncthreads();
-  for (int n = warp; n < n_cls; n += 8) {
+  // classes [blockIdx.y * per, +per) of this clip: one warp per class, 6 x LDG.128 per lane, all in flight before the first use
+  const int per = (n_cls + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int n_end = min(n_cls, ((int)blockIdx.y + 1) * per);
+  float4 xv[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) xv[j] = *reinterpret_cast<const float4*>(&s_v[4 * (lane + 32 * j)]);
+  for (int n = (int)blockIdx.y * per + warp; n < n_end; n += 8) {
+    const float4* wr = reinterpret_cast<const float4*>(w + (int64_t)n * 768);
+    float4 wv[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) wv[j] = __ldg(wr + lane + 32 * j);
     float acc = 0.f;
-    for (int c = lane; c < 768; c += 32) acc = fmaf(s_v[c], w[(int64_t)n * 768 + c], acc);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      acc = fmaf(xv[j].x, wv[j].x, acc);
+      acc = fmaf(xv[j].y, wv[j].y, acc);
+      acc = fmaf(xv[j].z, wv[j].z, acc);
+      acc = fmaf(xv[j].w, wv[j].w, acc);
+    }
     acc = warp_sum(acc);
     if (lane == 0) out[(int64_t)blockIdx.x * n_cls + n] = 1.f / (1.f + expf(-(acc + bias[n])));
   }
@@ -661,7 +677,9 @@ clip_head_kernel(const float* __restrict__ fe, int tp, const float* __restrict__
 
 int launch_clip_head(const float* frame_embs, int batch, int tp, const float* ln_g, const float* ln_b, const float* w,
                      const float* bias, int n_cls, float* out, cudaStream_t stream) {
-  clip_head_kernel<<<batch, 256, 0, stream>>>(frame_embs, tp, ln_g, ln_b, w, bias, n_cls, out);
+  // the pooling + LayerNorm prologue (95 KB of L2 reads per clip) is repeated by every class slice: cheaper than a second launch
+  const int slices = batch >= 148 ? 4 : 8;
+  clip_head_kernel<<<dim3(batch, slices), 256, 0, stream>>>(frame_embs, tp, ln_g, ln_b, w, bias, n_cls, out);
   CNB_LAUNCH_OK();
   return 0;
 }

@@ -527,7 +527,7 @@ static int launch_cfg(const act16* a, const act16* w, int m, int n, int k, const
   }
   const int n_tiles = (int)ceil_div(m, C::kTileM) * (n / BLOCK_N);
   if (PAIR) {
-    const int pairs = n_tiles < kNumSMs / 2 ? n_tiles : kNumSMs / 2;
+    const int pairs = n_tiles < sm_budget() / 2 ? n_tiles : sm_budget() / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs);
     cfg.blockDim = dim3(kTcThreads);
@@ -544,7 +544,7 @@ static int launch_cfg(const act16* a, const act16* w, int m, int n, int k, const
     CNB_LAUNCH_OK();
     return 0;
   }
-  const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+  const int grid = n_tiles < sm_budget() ? n_tiles : sm_budget();
   kern<<<grid, kTcThreads, C::kTotal, stream>>>(map_a, map_w, map_out, map_resid, m, n, k, ep);
   CNB_LAUNCH_OK();
   return 0;

@@ -100,6 +100,10 @@ int launch_dwconv_ln_tma(const float* x, int batch, int h, int w, int c, const f
 
 // the encoder about to be enqueued overlaps the previous batch's decoder (streaming host API): prefer half-size CTAs
 void dwconv_set_overlap_hint(bool on);
+// SMs the persistent encoder kernels (gemm_tc, mlp_fused, mlp_fused_pair, dwconv_ring) size their grids for: 148 unless the
+// streaming host API knows that a decoder holds some of them (a 148-CTA persistent grid on fewer free SMs runs as two waves)
+void set_sm_budget(int sms);
+int sm_budget();
 
 // ---- decoder / beam search ------------------------------------------------------------------------------------------------
 struct DecoderDims {
@@ -139,6 +143,11 @@ int launch_beam_finalize(BeamState st, int64_t* best_preds, float* best_lp, int*
 // W1 = fp16(W), W2 = fp16((W - W1) * 2048) (22 significand bits together), each behind its own TMA descriptor.
 constexpr int kDecMapsPerLayer = 12;  // {sa_in, sa_out (head-packed), ca_q, ca_out (head-packed), l1, l2} x {W1, W2}
 constexpr int kDecMaps = 6 * kDecMapsPerLayer + 2;  // + classifier {W1, W2}
+// L2 eviction-priority policies for the .L2::cache_hint forms of the TMA loads (the encodings createpolicy.fractional.L2::evict_*
+// produces at fraction 1.0)
+constexpr unsigned long long kL2EvictNormal = 0x1000000000000000ull, kL2EvictFirst = 0x12F0000000000000ull,
+                             kL2EvictLast = 0x14F0000000000000ull;
+
 struct ClusterLayer {
   const float *sa_in_b, *sa_out_b, *ca_q_b, *ca_out_b, *l1_b, *l2_b, *n1_g, *n1_b, *n2_g, *n2_b, *n3_g, *n3_b;
 };
@@ -156,6 +165,7 @@ struct ClusterArgs {
   BeamState bs;              // out_preds / out_lp / done are used
   float* tap;                // optional (tests): raw logits of every step, (max_len, rows, vocab)
   unsigned long long* trace; // optional (debug): phase times of the first CTA
+  unsigned long long w_policy; // L2 eviction policy of the weight-ring loads (kL2Evict*)
   int rows, beam, tp, max_len, vocab, min_len, batch;
   int compact;               // 1 = prefer few, fat clusters (32 rows each): the decode shares the GPU with the next encoder
 };

@@ -393,7 +393,7 @@ int launch_mlp_fused_c96(const act16* y, const act16* w1, const act16* w2, const
     attr_set = true;
   }
   const int n_tiles = (int)ceil_div(m, kBM);
-  const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+  const int grid = n_tiles < sm_budget() ? n_tiles : sm_budget();
   static const bool use_reduce = getenv("CNB_MLP_NO_REDUCE") == nullptr;   // default: residual add by the TMA store (6 % faster)
   static const bool want_trace = getenv("CNB_MLP_TRACE") != nullptr;
   static int traced = 0;

@@ -382,7 +382,7 @@ int launch_pair(const act16* y, const act16* w1, const act16* w2, const float* b
     attr_set = true;
   }
   const int n_tiles = (int)ceil_div(m, 2 * kBM2);
-  const int pairs = n_tiles < kNumSMs / 2 ? n_tiles : kNumSMs / 2;
+  const int pairs = n_tiles < sm_budget() / 2 ? n_tiles : sm_budget() / 2;
   mlp_fused_pair_kernel<C><<<2 * pairs, kThreads2, F::kSmem, stream>>>(map_y, map_w1, map_w2, map_x, m, b1, b2, scale);
   CNB_LAUNCH_OK();
   return 0;

@@ -48,6 +48,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(x), "r"(y), "r"(bar)
       : "memory");
 }
+// cache-hint form: `policy` is one of kernels.h kL2Evict*
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst),
+      "l"(map), "r"(x), "r"(y), "r"(bar), "l"(policy)
+      : "memory");
+}
 // one lane of a converged warp (the single thread that issues tcgen05.mma / commit).  Run the surrounding control flow on the
 // whole warp with warp-uniform values: under `if (lane == 0)` the compiler cannot keep descriptors in uniform registers and
 // wraps every MMA in a vector -> uniform waterfall loop (~90 cycles per instruction).

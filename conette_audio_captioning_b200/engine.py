@@ -11,7 +11,7 @@ libconette_b200.so.  The methods mirror the reference's operator seams (SURVEY.m
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, Optional, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import torch
 from torch import Tensor
@@ -101,6 +101,19 @@ class Engine:
         cnt = (C.c_int64 * n)()
         _lib.check(self.lib.cnb_profile_end(self.handle, ms, cnt, n))
         return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(_lib.KERNEL_CLASSES)}
+
+    def profile_timeline_begin(self) -> None:
+        _lib.check(self.lib.cnb_profile_timeline_begin(self.handle))
+
+    def profile_timeline_end(self, cap: int = 1 << 16) -> List[Tuple[str, float, float]]:
+        """[(kernel class, begin ms, end ms)] for every bracket since profile_timeline_begin, in issue order (streaming overlap
+        stays on, so brackets of the decode stream interleave with the encoder's)."""
+        cls = (C.c_int32 * cap)()
+        t0 = (C.c_float * cap)()
+        t1 = (C.c_float * cap)()
+        n = C.c_int32(0)
+        _lib.check(self.lib.cnb_profile_timeline_end(self.handle, cls, t0, t1, cap, C.byref(n)))
+        return [(_lib.KERNEL_CLASSES[cls[i]], float(t0[i]), float(t1[i])) for i in range(min(n.value, cap))]
 
     # ---- stages -------------------------------------------------------------------------------------------------------
     def resample(self, wav: Tensor, orig_sr: int, lens: Optional[Tensor] = None, new_sr: int = 32_000,

@@ -181,6 +181,11 @@ enum {
 };
 int cnb_profile_begin(cnb_handle* h);
 int cnb_profile_end(cnb_handle* h, float* ms_per_class, int64_t* brackets_per_class, int32_t n_classes);
+/* Timeline form of the same brackets: unlike cnb_profile_begin it leaves the streaming overlap of cnb_caption_host_begin on
+ * (decode of batch i on its own stream next to the encoder of batch i+1), and _end returns every bracket in issue order:
+ * class, begin and end in ms after the first bracket's begin.  At most `cap` entries are written, *n_out = brackets recorded. */
+int cnb_profile_timeline_begin(cnb_handle* h);
+int cnb_profile_timeline_end(cnb_handle* h, int32_t* cls, float* t_begin_ms, float* t_end_ms, int32_t cap, int32_t* n_out);
 
 /* Number of kernels launched by this handle since creation (bench.py reports the per-step delta as gpu_launches). */
 int64_t cnb_launch_count(const cnb_handle* h);

@@ -100,3 +100,39 @@ def test_stream_with_mixed_sample_rates(sd):
                 assert torch.equal(a["lprobs"], c["lprobs"]) and torch.equal(a["tags_probs"], c["tags_probs"]), rep
     finally:
         model.engine.close()
+
+
+def test_timeline_brackets_keep_the_overlap(sd):
+    """cnb_profile_timeline_begin/_end: every launch group is bracketed in issue order while the decode of batch i still runs
+    on its own stream next to the encoder of batch i+1, and the results are unchanged."""
+    from conette_audio_captioning_b200.engine import Engine
+
+    eng = Engine(sd, sd["model.decoder.classifier.weight"].shape[0], precision="fast")
+    try:
+        forbid = sd["model.forbid_rep_mask"]
+        b, n = 16, 64000
+        wavs = [synth.make_audio(b, n, seed=70 + i)[:, 0].contiguous().pin_memory() for i in range(3)]
+        bos = sd["model.task_id_to_token_id"][torch.zeros(b, dtype=torch.long)]
+        want = [eng.caption_host(w, None, bos, forbid, 3, 3, 20) for w in wavs]
+        eng.profile_timeline_begin()
+        got, ticket = [], None
+        for w in wavs:
+            nxt = eng.caption_host_begin(w, None, bos, forbid, 3, 3, 20)
+            if ticket is not None:
+                got.append(eng.caption_host_end(ticket))
+            ticket = nxt
+        got.append(eng.caption_host_end(ticket))
+        tl = eng.profile_timeline_end()
+        for a, c in zip(want, got):
+            for x, y in zip(a, c):
+                assert torch.equal(x, y)
+        names = [name for name, _, _ in tl]
+        assert names.count("dec_gemm") == 3 and names.count("dwconv_ln.s1") == 9 and "frontend" in names
+        assert all(t1 >= t0 >= 0.0 for _, t0, t1 in tl)
+        dec = [(t0, t1) for name, t0, t1 in tl if name == "dec_gemm"]
+        enc = [(t0, t1) for name, t0, t1 in tl if name == "dwconv_ln.s1"]
+        # the second batch's first ConvNeXt block starts before the first batch's decode has finished
+        assert enc[3][0] < dec[0][1]
+        assert eng.profile_timeline_end() == []  # nothing recorded outside a begin/end pair
+    finally:
+        eng.close()
