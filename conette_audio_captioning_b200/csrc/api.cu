@@ -86,6 +86,7 @@ struct cnb_handle {
   float *head_ln_g, *head_ln_b, *head_w, *head_b;
   // projection + decoder
   float *proj_w, *proj_b, *emb, *pe, *ca_kv_w, *ca_kv_b, *cls_w, *cls_b;
+  act16 *proj_w3 = nullptr, *ca_kv_w3 = nullptr;  // [W1 | W1 | W2] rows for the split-precision tensor-core projection (dec_project)
   void* dec_tmaps = nullptr;  // kDecMaps TMA descriptors of the fp16-split decoder weights (cluster decoder)
   LayerW layers[6];
   // workspace (grown on demand)
@@ -232,6 +233,13 @@ static int put_f16(cnb_handle* h, const std::vector<float>& v, act16** out) {
   if (int _rc = put_f32(h, vec, &(dst))) return _rc
 #define PUT_BF(dst, vec) \
   if (int _rc = put_f16(h, vec, &(dst))) return _rc
+// an already converted fp16 vector
+#define PUT_BF16V(dst, vec)                                                                          \
+  do {                                                                                               \
+    const std::vector<act16> _v = (vec);                                                             \
+    (dst) = h->arena.take<act16>(_v.size());                                                         \
+    CNB_CUDA_OK(cudaMemcpy((dst), _v.data(), _v.size() * sizeof(act16), cudaMemcpyHostToDevice));    \
+  } while (0)
 
 // fp16 hi/lo split of a decoder weight matrix for the cluster decoder (decoder_cluster.cu): W = W1 + 2^-11 W2 with
 // W1 = fp16(W), W2 = fp16((W - W1) * 2048); `out` = [W1 (n*k) | W2 (n*k)].  `head_pack`: columns regrouped per attention head,
@@ -247,6 +255,25 @@ static std::vector<act16> split_f16(const std::vector<float>& w, int n, int k, b
       const size_t o = head_pack ? ((size_t)(c / 32) * n + r) * 32 + (c % 32) : (size_t)r * k + c;
       out[o] = h1;
       out[sz + o] = h2;
+    }
+  return out;
+}
+
+// Weights of a GEMM that runs on the tensor cores at fp32-level accuracy through ONE fp16 GEMM of triple depth (dec_project):
+// row r = [W1 | W1 | W2] with W1 = fp16(W), W2 = fp16(W - W1), against activation rows [A1 | A2 | A1]:
+// A1 W1 + A2 W1 + A1 W2 = A W - A2 W2.  The low parts are stored unscaled: they fall into fp16's subnormal range, whose fixed
+// 2^-24 step still resolves them to 2^-13 of the high part's unit in the last place (|W| < 0.25, |A| < 64 here), i.e. ~1e-6
+// relative on the product sums -- the level of fp32 accumulation order effects.
+static std::vector<act16> concat3_f16(const std::vector<float>& w, int n, int k) {
+  std::vector<act16> out((size_t)n * 3 * k);
+  for (int r = 0; r < n; ++r)
+    for (int c = 0; c < k; ++c) {
+      const float v = w[(size_t)r * k + c];
+      const act16 h1 = float2act(v);
+      act16* o = &out[(size_t)r * 3 * k];
+      o[c] = h1;
+      o[k + c] = h1;
+      o[2 * k + c] = float2act(v - act2float(h1));
     }
   return out;
 }
@@ -440,6 +467,7 @@ static int finalize(cnb_handle* h) {
     GET(cw, D + "classifier.weight", V, kD);
     GET(cb, D + "classifier.bias", V);
     PUT(h->proj_w, pw->data); PUT(h->proj_b, pb->data); PUT(h->emb, emb->data); PUT(h->cls_w, cw->data);
+    PUT_BF16V(h->proj_w3, concat3_f16(pw->data, kD, 768));
     PUT(h->cls_b, cb->data);
     // fp16-split decoder weights + their TMA descriptors (cluster decoder): map index 12 l + 2 j + half, classifier 72 + half
     std::vector<uint8_t> maps((size_t)kDecMaps * 128);
@@ -501,6 +529,7 @@ static int finalize(cnb_handle* h) {
       }
     }
     PUT(h->ca_kv_w, kvw); PUT(h->ca_kv_b, kvb);
+    PUT_BF16V(h->ca_kv_w3, concat3_f16(kvw, kLayers * 2 * kD, kD));
     CNB_CUDA_OK(cudaMalloc(&h->dec_tmaps, maps.size()));
     CNB_CUDA_OK(cudaMemcpy(h->dec_tmaps, maps.data(), maps.size(), cudaMemcpyHostToDevice));
   }
@@ -709,16 +738,42 @@ static int dec_prepare(cnb_handle* h, int batch, int tp, int rows, int max_len, 
 }
 
 // projection: Linear(768,256) + ReLU (reference common.py:71-78); cross-attention K|V of all 6 layers in one GEMM
+// rows [A1 | A2 | A1] of the triple-depth GEMM (see concat3_f16): A1 = fp16(a), A2 = fp16(a - A1)
+__global__ void split3_act16_kernel(const float* __restrict__ in, act16* __restrict__ out, int64_t rows, int k) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per pair of columns
+  const int kp = k >> 1;
+  if (i >= rows * kp) return;
+  const int64_t r = i / kp;
+  const int c = 2 * (int)(i - r * kp);
+  const float2 v = *reinterpret_cast<const float2*>(in + r * k + c);
+  const act16x2 h1 = floats2act2(v.x, v.y);
+  const float2 f1 = __half22float2(h1);
+  const act16x2 h2 = floats2act2(v.x - f1.x, v.y - f1.y);
+  act16* o = out + r * 3 * k + c;
+  *reinterpret_cast<act16x2*>(o) = h1;
+  *reinterpret_cast<act16x2*>(o + k) = h2;
+  *reinterpret_cast<act16x2*>(o + 2 * k) = h1;
+}
+
 static int dec_project(cnb_handle* h, const float* frame_embs, int batch, int tp, const DecWs& w, cudaStream_t st) {
   Prof _p(h, CNB_K_PROJ_KV, st);
-  EpiParams ep;
+  EpiParams ep, ek;
   ep.bias = h->proj_b;
-  if (int rc = launch_gemm_f32<float>(frame_embs, 768, h->proj_w, batch * tp, kD, 768, EPI_BIAS_RELU, ep, w.mem, kD, st))
-    return rc;
-  EpiParams ek;
   ek.bias = h->ca_kv_b;
-  return launch_gemm_f32<float>(w.mem, kD, h->ca_kv_w, batch * tp, kLayers * 2 * kD, kD, EPI_BIAS, ek, w.ckv,
-                                kLayers * 2 * kD, st);
+  const int m = batch * tp;
+  static const bool simt = getenv("CNB_PROJ_SIMT") != nullptr;
+  if (h->cfg.precision == CNB_PRECISION_FAST && !simt && m > 0) {
+    // fast mode: both GEMMs on the tensor cores at fp32-level accuracy (split operands, one fp16 GEMM of triple depth each)
+    WS(h, "mem3", act16, (size_t)m * 3 * 768, a3);
+    split3_act16_kernel<<<(unsigned)ceil_div((int64_t)m * 384, 256), 256, 0, st>>>(frame_embs, a3, m, 768);
+    CNB_LAUNCH_OK();
+    if (int rc = launch_gemm_tc<float>(a3, h->proj_w3, m, kD, 3 * 768, EPI_BIAS_RELU, ep, w.mem, kD, st)) return rc;
+    split3_act16_kernel<<<(unsigned)ceil_div((int64_t)m * (kD / 2), 256), 256, 0, st>>>(w.mem, a3, m, kD);
+    CNB_LAUNCH_OK();
+    return launch_gemm_tc<float>(a3, h->ca_kv_w3, m, kLayers * 2 * kD, 3 * kD, EPI_BIAS, ek, w.ckv, kLayers * 2 * kD, st);
+  }
+  if (int rc = launch_gemm_f32<float>(frame_embs, 768, h->proj_w, m, kD, 768, EPI_BIAS_RELU, ep, w.mem, kD, st)) return rc;
+  return launch_gemm_f32<float>(w.mem, kD, h->ca_kv_w, m, kLayers * 2 * kD, kD, EPI_BIAS, ek, w.ckv, kLayers * 2 * kD, st);
 }
 
 // one decoder step for position `pos`: tokens[r][pos] -> logits (R, V)
