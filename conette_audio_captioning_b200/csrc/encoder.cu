@@ -439,6 +439,180 @@ static int launch_dwconv_ring_t(const float* x, int batch, int h, const float* w
   return 0;
 }
 
+// =====================================================================================================================
+// K-DWLN stage 4 (C = 768, W = 7): the whole image row (7 pixels x 768 channels = 21 KB of fp32) is one contiguous run of the
+// NHWC tensor, every output pixel's 7x7 window spans the full width, and a clip has only T'/... = 31 rows.
+//   CTA = 384 threads = one channel pair each, all 768 channels (LayerNorm stays inside the CTA); it walks a contiguous range
+//   of the flattened (clip, row) space with its 49 x float2 weights in registers;
+//   input rows live in a 10-slot shared-memory ring (7 live + 3 in flight), each filled by ONE cp.async.bulk of 21 504 bytes;
+//   the horizontal zero padding is resolved at compile time (tap (p, j) exists iff 0 <= p + j - 3 < 7: 37 of 49 per kernel
+//   row, 259 packed FMAs per output row instead of 343), the vertical one by skipping rows (CTA-uniform branch);
+//   LayerNorm: one pass (sum | sum of squares) through the 16-value butterfly, per-warp partials combined in fixed order.
+// The generic one-CTA-per-row kernel above re-read 7 input rows and 49 weights per output row from L1/L2 (57 us per launch at
+// 64 clips, 4x its FP32 floor).
+// =====================================================================================================================
+constexpr int kW7Slots = 10;
+constexpr int kW7RowFloats = 7 * 768;
+constexpr int kW7RowBytes = kW7RowFloats * 4;
+constexpr int kW7Smem = kW7Slots * kW7RowBytes + 2 * 16 * 12 * 4 + kW7Slots * 8 + 128;
+
+__device__ __forceinline__ void w7_mbar_init(uint32_t bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar)); }
+__device__ __forceinline__ void w7_mbar_expect(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void w7_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (!ok) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    if (!ok && ++spins > (1u << 22)) {  // a lost row would otherwise hang the GPU: fail loudly instead
+      printf("conette_b200: dwconv_ln_w7 row wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void w7_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(384, 1)
+dwconv_ln_w7_kernel(const float* __restrict__ x, int H, int rows_total, int quota, const float* __restrict__ w_t,
+                    const float* __restrict__ bias, const float* __restrict__ ln_g, const float* __restrict__ ln_b,
+                    OutT* __restrict__ out) {
+  constexpr int C = 768, W = 7;
+  extern __shared__ uint8_t w7_raw[];
+  const uint32_t base = ((uint32_t)__cvta_generic_to_shared(w7_raw) + 127u) & ~127u;
+  uint8_t* sm = w7_raw + (base - (uint32_t)__cvta_generic_to_shared(w7_raw));
+  const float* ring = reinterpret_cast<const float*>(sm);
+  float* s_part = reinterpret_cast<float*>(sm + kW7Slots * kW7RowBytes);  // [2][16 values][12 warps]
+  const uint32_t bar0 = base + kW7Slots * kW7RowBytes + 2 * 16 * 12 * 4;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < kW7Slots; ++s) w7_mbar_init(bar0 + 8 * s);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  float2 wr[49];
+#pragma unroll
+  for (int t = 0; t < 49; ++t) wr[t] = __ldg(reinterpret_cast<const float2*>(w_t + t * C + 2 * tid));
+  const float2 bi = *reinterpret_cast<const float2*>(bias + 2 * tid);
+  const float2 gm = *reinterpret_cast<const float2*>(ln_g + 2 * tid);
+  const float2 be = *reinterpret_cast<const float2*>(ln_b + 2 * tid);
+  __syncthreads();
+
+  const int u_begin = (int)blockIdx.x * quota, u_end = min(rows_total, u_begin + quota);
+  uint32_t k_issue = 0;  // input rows requested so far by this CTA: request k lives in slot k % 10, barrier phase (k / 10) & 1
+  uint32_t it = 0;       // output rows produced so far (partial buffer it & 1)
+  for (int u = u_begin; u < u_end;) {
+    const int b = u / H, h_first = u - b * H;
+    const int h_last = min(H, h_first + (u_end - u)) - 1;  // last output row of this segment (same clip)
+    u += h_last - h_first + 1;
+    const int r_lo = max(0, h_first - 3), r_hi = min(H - 1, h_last + 3);
+    const uint32_t k_seg = k_issue;  // request index of input row r_lo
+    const float* xb = x + (int64_t)b * H * kW7RowFloats;
+    int r_req = r_lo;                // next input row to request
+    int r_seen = r_lo - 1;           // rows up to here have landed (as seen by this thread)
+    for (int h = h_first; h <= h_last; ++h, ++it) {
+      // slots of rows < h - 3 were released by the barrier that ended the previous output row
+      const int want = min(r_hi, h + kW7Slots - 4);  // 7 live rows + (slots - 7) in flight
+      if (tid == 0) {
+        for (int r = r_req; r <= want; ++r) {
+          const uint32_t s = (k_issue + (uint32_t)(r - r_req)) % kW7Slots, bar = bar0 + 8 * s;
+          w7_mbar_expect(bar, kW7RowBytes);
+          w7_bulk_load(base + s * kW7RowBytes, xb + (int64_t)r * kW7RowFloats, kW7RowBytes, bar);
+        }
+      }
+      if (want >= r_req) {  // every thread tracks the request counters
+        k_issue += (uint32_t)(want - r_req + 1);
+        r_req = want + 1;
+      }
+      const int need = min(r_hi, h + 3);
+      for (; r_seen < need; ++r_seen) {
+        const uint32_t k = k_seg + (uint32_t)(r_seen + 1 - r_lo);
+        w7_mbar_wait(bar0 + 8 * (k % kW7Slots), (k / kW7Slots) & 1u);
+      }
+      float2 acc[W];
+#pragma unroll
+      for (int p = 0; p < W; ++p) acc[p] = bi;
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        const int r = h + i - 3;
+        if (r < 0 || r >= H) continue;  // zero padding above / below the clip (Appendix F.3: also at the padded-batch border)
+        const uint32_t k = k_seg + (uint32_t)(r - r_lo);
+        const float2* row = reinterpret_cast<const float2*>(ring + (size_t)(k % kW7Slots) * kW7RowFloats) + tid;
+        float2 in[W];
+#pragma unroll
+        for (int q = 0; q < W; ++q) in[q] = row[q * (C / 2)];
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+#pragma unroll
+          for (int p = 0; p < W; ++p)
+            if (p + j - 3 >= 0 && p + j - 3 < W) acc[p] = __ffma2_rn(in[p + j - 3], wr[i * 7 + j], acc[p]);
+      }
+      // LayerNorm over the 768 channels of each of the 7 pixels
+      float st[16];
+#pragma unroll
+      for (int p = 0; p < W; ++p) {
+        st[p] = acc[p].x + acc[p].y;
+        st[p + 8] = fmaf(acc[p].x, acc[p].x, acc[p].y * acc[p].y);
+      }
+      st[7] = st[15] = 0.f;
+      const float tot = warp_sum16(st, lane);  // lane l holds value (l >> 1) & 15
+      float* part = s_part + (it & 1u) * (16 * 12);
+      if ((lane & 1) == 0) part[(lane >> 1) * 12 + warp] = tot;
+      __syncthreads();  // partials visible; every thread has also finished reading the ring for this output row
+      // second stage in every warp: lane v < 16 adds the 12 per-warp partials of value v in fixed order (12 LDS per lane
+      // instead of 168 broadcast loads per thread), the pixel statistics travel by shuffle
+      float tv = 0.f;
+      if (lane < 16) {
+#pragma unroll
+        for (int w = 0; w < 12; ++w) tv += part[lane * 12 + w];
+      }
+      OutT* o = out + ((int64_t)(b * H + h) * W) * C + 2 * tid;
+#pragma unroll
+      for (int p = 0; p < W; ++p) {
+        const float s1 = __shfl_sync(0xffffffffu, tv, p), s2 = __shfl_sync(0xffffffffu, tv, p + 8);
+        const float mean = s1 * (1.f / C);
+        const float var = fmaxf(fmaf(s2, 1.f / C, -mean * mean), 0.f);
+        const float rstd = 1.f / sqrtf(var + kLnEps);
+        const float y0 = (acc[p].x - mean) * rstd * gm.x + be.x;
+        const float y1 = (acc[p].y - mean) * rstd * gm.y + be.y;
+        if constexpr (sizeof(OutT) == 2) {
+          *reinterpret_cast<act16x2*>(o + (int64_t)p * C) = floats2act2(y0, y1);
+        } else {
+          *reinterpret_cast<float2*>(o + (int64_t)p * C) = make_float2(y0, y1);
+        }
+      }
+    }
+    __syncthreads();  // the next segment's first requests overwrite slots this segment may still be reading
+  }
+}
+
+template <typename OutT>
+static int launch_dwconv_ln_w7(const float* x, int batch, int h, const float* w_t, const float* bias, const float* ln_g,
+                               const float* ln_b, OutT* out, cudaStream_t stream) {
+  auto kern = dwconv_ln_w7_kernel<OutT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CNB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kW7Smem));
+    attr_set = true;
+  }
+  const int total = batch * h;
+  if (total == 0) return 0;
+  // contiguous row ranges, one per SM; at least 4 rows each so that the 6 halo rows of a range stay a minority
+  int ctas = std::min(sm_budget(), (int)ceil_div(total, 4));
+  const int quota = (int)ceil_div(total, ctas);
+  ctas = (int)ceil_div(total, quota);
+  kern<<<ctas, 384, kW7Smem, stream>>>(x, h, total, quota, w_t, bias, ln_g, ln_b, out);
+  CNB_LAUNCH_OK();
+  return 0;
+}
+
 template <int C, int W, typename OutT>
 static int launch_dwconv_ln_t(const float* x, int batch, int h, const float* w_t, const float* bias, const float* ln_g,
                               const float* ln_b, OutT* out, cudaStream_t stream) {
@@ -460,6 +634,8 @@ int launch_dwconv_ln(const float* x, int batch, int h, int w, int c, const float
   if (c == 96 && w == 56) return launch_dwconv_ring_t<96, 56, 28, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
   if (c == 192 && w == 28) return launch_dwconv_ring_t<192, 28, 14, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
   if (c == 384 && w == 14) return launch_dwconv_ring_t<384, 14, 7, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
+  static const bool w7_ring = getenv("CNB_DW_S4_GENERIC") == nullptr;  // A/B switch: the one-CTA-per-row kernel
+  if (c == 768 && w == 7 && w7_ring) return launch_dwconv_ln_w7<OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
   if (c == 768 && w == 7) return launch_dwconv_ln_t<768, 7, OutT>(x, batch, h, w_t, bias, ln_g, ln_b, out, stream);
   set_error("dwconv_ln: unsupported (C, W) = (" + std::to_string(c) + ", " + std::to_string(w) + ")");
   return -1;
