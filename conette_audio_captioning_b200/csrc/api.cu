@@ -964,9 +964,9 @@ static int decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, c
     // L2 eviction priority of the weight-ring loads.  Every cluster re-reads the weights from L2 every step while the next
     // batch's encoder streams activations through the same L2; CNB_DEC_L2=last keeps them at the lowest eviction priority.
     // Measured on the streaming step (tools/stream_timeline.py): decoder 4.33 ms either way -- the weights stay resident
-    // anyway -- so the default is the plain policy.
+    // anyway -- so the default is the plain instruction without a hint (0).
     const char* e = getenv("CNB_DEC_L2");
-    ca.w_policy = e && !strcmp(e, "last") ? kL2EvictLast : e && !strcmp(e, "first") ? kL2EvictFirst : kL2EvictNormal;
+    ca.w_policy = !e ? 0ull : !strcmp(e, "last") ? kL2EvictLast : !strcmp(e, "first") ? kL2EvictFirst : !strcmp(e, "normal") ? kL2EvictNormal : 0ull;
   }
 
   const bool want_cluster = h->use_cluster == 2 || (h->use_cluster == 1 && h->cfg.precision == CNB_PRECISION_FAST);
@@ -1001,7 +1001,8 @@ static int decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, c
       if (tot == 0) return 0;
       for (int i = 0; i < 18; ++i)
         fprintf(stderr, "[dec cluster trace] %-24s %9.1f us  (%4.1f %%)\n", names[i], (double)t[i] / 1e3, 100.0 * t[i] / tot);
-      fprintf(stderr, "[dec cluster trace] total %.1f us\n", tot / 1e3);
+      fprintf(stderr, "[dec cluster trace] total %.1f us; SM clock of the traced CTA %.0f MHz\n", tot / 1e3,
+              t[19] ? 1e3 * (double)t[18] / (double)t[19] : 0.0);
       return 0;
     };
     if (trace_mode) {

@@ -344,8 +344,14 @@ __device__ __forceinline__ void attend(const float* const (&q)[NRW], const int (
 //              FF2      8 chunks: tile t (128 outputs) x k-chunk c of this CTA's K slice [256 rank, +256)
 //   classifier 8 chunks per round of 256 words: tile t x k-chunk c; rows beyond the vocabulary are zero-filled by TMA
 // Chunk g (running index) lives in ring stage g % kStages.
+// weight-ring load: plain, or with an L2 eviction-priority hint when the launch asks for one (ClusterArgs::w_policy != 0)
+__device__ __forceinline__ void tma_w(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar, unsigned long long policy) {
+  if (policy == 0) tma_load_2d(dst, map, x, y, bar);
+  else tma_load_2d_hint(dst, map, x, y, bar, policy);
+}
+
 template <int kStages>
-__device__ __forceinline__ void issue_chunk(uint8_t* ring, unsigned long long* full, const ClusterArgs& a, uint32_t g, int rank,
+__device__ __noinline__ void issue_chunk(uint8_t* ring, unsigned long long* full, const ClusterArgs& a, uint32_t g, int rank,
                                             int v0, int chunks_per_step) {
   const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(a.tmaps);
   const int s = (int)(g % kStages);
@@ -361,30 +367,30 @@ __device__ __forceinline__ void issue_chunk(uint8_t* ring, unsigned long long* f
       for (int half = 0; half < 2; ++half)
 #pragma unroll
         for (int part = 0; part < 3; ++part)
-          tma_load_2d_hint(dst + half * kHalfStage + part * 4096, lm + 0 + half, j * 64, part * kCD + rank * kCHead, bar, a.w_policy);
+          tma_w(dst + half * kHalfStage + part * 4096, lm + 0 + half, j * 64, part * kCD + rank * kCHead, bar, a.w_policy);
     } else if (j == 4 || j == 6) {  // sa_out / ca_out (head-packed, K = 32)
       mbar_expect_tx(bar, 4 * 8192);
       const CUtensorMap* m = lm + (j == 4 ? 2 : 6);
 #pragma unroll
       for (int half = 0; half < 2; ++half)
 #pragma unroll
-        for (int t = 0; t < 2; ++t) tma_load_2d_hint(dst + half * kHalfStage + t * 8192, m + half, 0, rank * kCD + t * 128, bar, a.w_policy);
+        for (int t = 0; t < 2; ++t) tma_w(dst + half * kHalfStage + t * 8192, m + half, 0, rank * kCD + t * 128, bar, a.w_policy);
     } else if (j == 5) {  // ca_q
       mbar_expect_tx(bar, 8 * 4096);
 #pragma unroll
       for (int half = 0; half < 2; ++half)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tma_load_2d_hint(dst + half * kHalfStage + c * 4096, lm + 4 + half, c * 64, rank * kCHead, bar, a.w_policy);
+        for (int c = 0; c < 4; ++c) tma_w(dst + half * kHalfStage + c * 4096, lm + 4 + half, c * 64, rank * kCHead, bar, a.w_policy);
     } else if (j < 15) {  // FF1: hidden units [256 rank + 128 t, +128)
       const int t = (j - 7) >> 2, c = (j - 7) & 3;
       mbar_expect_tx(bar, 2 * kHalfStage);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) tma_load_2d_hint(dst + half * kHalfStage, lm + 8 + half, c * 64, rank * kCD + t * 128, bar, a.w_policy);
+      for (int half = 0; half < 2; ++half) tma_w(dst + half * kHalfStage, lm + 8 + half, c * 64, rank * kCD + t * 128, bar, a.w_policy);
     } else {  // FF2: outputs [128 t, +128), this CTA's K slice
       const int t = (j - 15) >> 2, c = (j - 15) & 3;
       mbar_expect_tx(bar, 2 * kHalfStage);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) tma_load_2d_hint(dst + half * kHalfStage, lm + 10 + half, rank * kCD + c * 64, t * 128, bar, a.w_policy);
+      for (int half = 0; half < 2; ++half) tma_w(dst + half * kHalfStage, lm + 10 + half, rank * kCD + c * 64, t * 128, bar, a.w_policy);
     }
   } else {  // classifier
     const int jj = idx - kCLayers * kChunksPerLayer;
@@ -392,7 +398,7 @@ __device__ __forceinline__ void issue_chunk(uint8_t* ring, unsigned long long* f
     mbar_expect_tx(bar, 2 * kHalfStage);
 #pragma unroll
     for (int half = 0; half < 2; ++half)
-      tma_load_2d_hint(dst + half * kHalfStage, maps + kCLayers * kDecMapsPerLayer + half, c * 64, v0 + rd * kClsRound + t * 128, bar, a.w_policy);
+      tma_w(dst + half * kHalfStage, maps + kCLayers * kDecMapsPerLayer + half, c * 64, v0 + rd * kClsRound + t * 128, bar, a.w_policy);
   }
 }
 
@@ -1067,7 +1073,9 @@ decoder_cluster_kernel(const __grid_constant__ ClusterArgs a, int clips_per_grou
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&S.tmem_slot);
   // debug trace (CNB_DEC_TRACE): thread 0 of the first CTA accumulates the time between phase marks
   const bool tr_on = a.trace != nullptr && blockIdx.x == 0 && tid == 0;
+  const long long tr_clk0 = clock64();
   if (tr_on) S.tr_last = cl_global_ns();
+  const unsigned long long tr_ns0 = tr_on ? S.tr_last : 0ull;
   cl.sync();  // every CTA's mbarriers are initialised before any peer pushes data at them
   Pipe pp;
   ExCount ex;
@@ -1128,8 +1136,11 @@ decoder_cluster_kernel(const __grid_constant__ ClusterArgs a, int clips_per_grou
   // drain the weight chunks that were requested ahead but never consumed
   if (warp == kProducerWarp)
     for (uint32_t u = pp.use; u < pp.load; ++u) mbar_wait(smem_addr(&S.full[u % kStages]), (u / kStages) & 1u);
-  if (tr_on)
-    for (int i = 0; i < kTrSlots; ++i) a.trace[i] = S.tr_acc[i];
+  if (tr_on) {
+    for (int i = 0; i < 18; ++i) a.trace[i] = S.tr_acc[i];
+    a.trace[18] = (unsigned long long)(clock64() - tr_clk0);  // SM cycles / elapsed ns = the clock this SM really ran at
+    a.trace[19] = cl_global_ns() - tr_ns0;
+  }
   if (rank == 0 && tid == 0 && steps_max > 0) atomicMax(&a.bs.done[1], steps_max);
   tcgen05_fence_before();
   cl.sync();  // no CTA may exit while a peer can still push into its shared memory

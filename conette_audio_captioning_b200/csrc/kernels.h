@@ -165,7 +165,7 @@ struct ClusterArgs {
   BeamState bs;              // out_preds / out_lp / done are used
   float* tap;                // optional (tests): raw logits of every step, (max_len, rows, vocab)
   unsigned long long* trace; // optional (debug): phase times of the first CTA
-  unsigned long long w_policy; // L2 eviction policy of the weight-ring loads (kL2Evict*)
+  unsigned long long w_policy; // L2 eviction policy of the weight-ring loads (kL2Evict*; 0 = no hint)
   int rows, beam, tp, max_len, vocab, min_len, batch;
   int compact;               // 1 = prefer few, fat clusters (32 rows each): the decode shares the GPU with the next encoder
 };

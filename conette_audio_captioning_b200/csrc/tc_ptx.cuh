@@ -31,16 +31,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug becomes a trapped launch (reported through the C ABI) instead of a hung GPU.
+// Bounded wait: a protocol bug becomes a trapped launch (reported through the C ABI) instead of a hung GPU.  The report lives
+// in ONE out-of-line function: inlined at every wait site the printf argument set-up made up a sixth of the cluster decoder's
+// 320 KB of code, which is instruction-fetch sensitive (its speed moved by 7 % with the placement of the code in memory).
+static __device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+  printf("conette_b200: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) {
-      printf("conette_b200: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar,
-             parity);
-      __trap();
-    }
-  }
+  while (!mbar_try_wait(bar, parity))
+    if (++spins > (1u << 22)) mbar_timeout(bar, parity);
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
   asm volatile(

@@ -26,3 +26,9 @@ for _ in range(2):
     out = eng.decode(fe, torch.full((b,), 31), bos, forbid)
 torch.cuda.synchronize()
 print("pred_size", out[0].shape, out[2].shape)
+eng.profile_begin()
+for _ in range(3):
+    eng.decode(fe, torch.full((b,), 31), bos, forbid)
+prof = eng.profile_end()
+print("event-timed: decoder kernel %.3f ms/launch, projection + cross K/V %.3f ms/decode" % (
+    prof["dec_gemm"][0] / 3, prof["proj_crosskv"][0] / 3))
