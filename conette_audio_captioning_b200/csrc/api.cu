@@ -961,12 +961,17 @@ static int decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, c
   ca.rows = rows; ca.beam = beam; ca.tp = tp; ca.max_len = max_len; ca.vocab = h->cfg.vocab_size; ca.min_len = min_len;
   ca.batch = batch; ca.compact = h->dec_compact ? 1 : 0;
   {
-    // L2 eviction priority of the weight-ring loads.  Every cluster re-reads the weights from L2 every step while the next
-    // batch's encoder streams activations through the same L2; CNB_DEC_L2=last keeps them at the lowest eviction priority.
-    // Measured on the streaming step (tools/stream_timeline.py): decoder 4.33 ms either way -- the weights stay resident
-    // anyway -- so the default is the plain instruction without a hint (0).
+    // L2 eviction priority of the weight-ring loads.  A decode step touches the 43 MB of weights once per cluster and then not for
+    // another ~190 us, during which the cross-attention K/V (25 MB at 64 clips) and the self-attention caches (up to 47 MB) are
+    // re-read by latency-critical loads.  With the default policy the weight stream pushes those out of L2 -- how badly depends
+    // on where the workspaces happen to be mapped (decoder 3.94 .. 4.13 ms between processes) -- and still comes from DRAM every
+    // step itself (ncu: 37 MB of DRAM reads per step).  evict_first on the stream keeps the attention data resident:
+    // 3.85 ms at every placement (profiles/r2_decoder_l2_policy.txt).  CNB_DEC_L2=none|normal|last|first overrides.
     const char* e = getenv("CNB_DEC_L2");
-    ca.w_policy = !e ? 0ull : !strcmp(e, "last") ? kL2EvictLast : !strcmp(e, "first") ? kL2EvictFirst : !strcmp(e, "normal") ? kL2EvictNormal : 0ull;
+    ca.w_policy = !e ? kL2EvictFirst
+                     : !strcmp(e, "last") ? kL2EvictLast : !strcmp(e, "first") ? kL2EvictFirst : !strcmp(e, "normal") ? kL2EvictNormal : 0ull;
+    const char* k = getenv("CNB_DEC_KV_L2");
+    ca.kv_policy = k && !strcmp(k, "last") ? kL2EvictLast : kL2EvictNormal;
   }
 
   const bool want_cluster = h->use_cluster == 2 || (h->use_cluster == 1 && h->cfg.precision == CNB_PRECISION_FAST);
@@ -989,7 +994,7 @@ static int decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, c
     const char* trace_env = getenv("CNB_DEC_TRACE");
     const int trace_mode = trace_env ? (trace_env[0] == '2' ? 2 : 1) : 0;
     auto print_trace = [&](unsigned long long* dev) -> int {
-      unsigned long long t[20];
+      unsigned long long t[24];
       CNB_CUDA_OK(cudaStreamSynchronize(st));
       CNB_CUDA_OK(cudaMemcpy(t, dev, sizeof(t), cudaMemcpyDeviceToHost));
       static const char* names[] = {"qkv gemm", "self attn", "sa_out gemm (K-split)", "ln1", "ca_q gemm",
@@ -1001,8 +1006,9 @@ static int decode(cnb_handle* h, const float* frame_embs, const int32_t* lens, c
       if (tot == 0) return 0;
       for (int i = 0; i < 18; ++i)
         fprintf(stderr, "[dec cluster trace] %-24s %9.1f us  (%4.1f %%)\n", names[i], (double)t[i] / 1e3, 100.0 * t[i] / tot);
-      fprintf(stderr, "[dec cluster trace] total %.1f us; SM clock of the traced CTA %.0f MHz\n", tot / 1e3,
-              t[19] ? 1e3 * (double)t[18] / (double)t[19] : 0.0);
+      const double mhz = t[19] ? 1e3 * (double)t[18] / (double)t[19] : 0.0;
+      fprintf(stderr, "[dec cluster trace] total %.1f us; SM clock of the traced CTA %.0f MHz; its MMA issuer waited %.1f us for weight chunks\n",
+              tot / 1e3, mhz, mhz > 0 ? (double)t[20] / mhz : 0.0);
       return 0;
     };
     if (trace_mode) {

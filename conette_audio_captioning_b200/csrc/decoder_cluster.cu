@@ -175,6 +175,7 @@ template <int NR> struct CSmem {
   unsigned long long full[kStages], empty[kStages], tile_full[kTileSlots];
   unsigned long long tr_acc[kTrSlots];
   unsigned long long tr_last;
+  unsigned long long tr_wait_full;  // debug trace: SM cycles the MMA issuer of the first CTA spent waiting for weight chunks
 
   __device__ __forceinline__ float (*q())[kCHead] { return reinterpret_cast<float(*)[kCHead]>(oph); }
   __device__ __forceinline__ float (*kv())[2 * kCHead] { return reinterpret_cast<float(*)[2 * kCHead]>(oph + NR * kCHead * 4); }
@@ -192,6 +193,24 @@ struct Pipe {
   uint32_t use = 0;   // chunks consumed so far
 };
 
+// Global loads / stores of the attention data (self-attention caches, cross-attention K / V) with an explicit L2 eviction priority
+// (ClusterArgs::kv_policy, always a valid policy: kL2EvictNormal = the default behaviour)
+__device__ __forceinline__ float4 ldg_f4_pol(const float* p, unsigned long long pol) {
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float ldg_f32_pol(const float* p, unsigned long long pol) {
+  float v;
+  asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void stg_f32_pol(float* p, float v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+
 // Attention of NRW rows at once by one warp over up to NCH*32 cached keys each (+ optionally one extra key/value held in
 // shared memory: the position being decoded).  kptr(rr, j) / vptr(rr, j) give the 32-float head slice of key / value j of
 // row rr.  Scores: lane = key (8 x LDG.128 each, all rows / chunks requested before the first use).  Values: lane =
@@ -203,7 +222,7 @@ struct Pipe {
 template <int NR, int NRW, int NCH, bool KT, typename KPtr, typename VPtr>
 __device__ __forceinline__ void attend(const float* const (&q)[NRW], const int (&n)[NRW], const bool (&valid)[NRW], KPtr kptr,
                                        VPtr vptr, const float* const (&kv_new)[NRW], bool has_new, uint8_t* opa,
-                                       const int (&out_row)[NRW], int lane, int tpad = 0) {
+                                       const int (&out_row)[NRW], int lane, unsigned long long pol, int tpad = 0) {
   float sc[NRW][NCH];
   // one row x one chunk per warp (10 s clips in 16-row clusters): the value rows are requested together with the keys, so the
   // phase costs one L2 round trip instead of two (the addresses do not depend on the scores)
@@ -214,7 +233,7 @@ __device__ __forceinline__ void attend(const float* const (&q)[NRW], const int (
     for (int u = 0; u < 8; ++u) {
       const int j = (lane >> 3) + 4 * u;
       vh[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (valid[0] && j < n[0]) vh[u] = *reinterpret_cast<const float4*>(vptr(0, j) + 4 * (lane & 7));
+      if (valid[0] && j < n[0]) vh[u] = ldg_f4_pol(vptr(0, j) + 4 * (lane & 7), pol);
     }
   }
 #pragma unroll
@@ -234,17 +253,17 @@ __device__ __forceinline__ void attend(const float* const (&q)[NRW], const int (
           const float* kb = kptr(rr, 0) + j;
           float kk[kCHead];
 #pragma unroll
-          for (int d = 0; d < kCHead; ++d) kk[d] = kb[d * tpad];
+          for (int d = 0; d < kCHead; ++d) kk[d] = ldg_f32_pol(kb + d * tpad, pol);
           float a = 0.f;
 #pragma unroll
           for (int d = 0; d < kCHead; ++d) a = fmaf(qv[d], kk[d], a);
           sc[rr][ch] = a * kCAttScale;
         }
       } else if (valid[rr] && j < n[rr]) {
-        const float4* kr = reinterpret_cast<const float4*>(kptr(rr, j));
+        const float* kr = kptr(rr, j);
         float4 kk[8];
 #pragma unroll
-        for (int d = 0; d < 8; ++d) kk[d] = kr[d];
+        for (int d = 0; d < 8; ++d) kk[d] = ldg_f4_pol(kr + 4 * d, pol);
         float a = 0.f;
 #pragma unroll
         for (int d = 0; d < 8; ++d) {
@@ -292,7 +311,7 @@ __device__ __forceinline__ void attend(const float* const (&q)[NRW], const int (
           vv[u] = vh[u];
         } else {
           vv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (valid[rr] && j < n[rr]) vv[u] = *reinterpret_cast<const float4*>(vptr(rr, j) + 4 * dq);
+          if (valid[rr] && j < n[rr]) vv[u] = ldg_f4_pol(vptr(rr, j) + 4 * dq, pol);
         }
       }
 #pragma unroll
@@ -350,14 +369,18 @@ __device__ __forceinline__ void tma_w(uint32_t dst, const CUtensorMap* map, int 
   else tma_load_2d_hint(dst, map, x, y, bar, policy);
 }
 
+// Chunk g into its ring stage.  (Pulling the boxes into L2 a few chunks ahead of the ring with cp.async.bulk.prefetch.tensor was
+// tried and removed: the prefetches queue in front of the ring's own loads in the TMA unit -- issuer wait 160 us -> 1000 us per
+// decode, kernel 3.85 -> 5.2 ms at every distance from 4 to 23 chunks.)
 template <int kStages>
 __device__ __noinline__ void issue_chunk(uint8_t* ring, unsigned long long* full, const ClusterArgs& a, uint32_t g, int rank,
-                                            int v0, int chunks_per_step) {
+                                         int v0, int chunks_per_step) {
   const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(a.tmaps);
   const int s = (int)(g % kStages);
   const int idx = (int)(g % (uint32_t)chunks_per_step);
   const uint32_t dst = smem_addr(ring + (size_t)s * kStageBytes);
   const uint32_t bar = smem_addr(&full[s]);
+  auto box = [&](uint32_t to, const CUtensorMap* m, int x, int y) { tma_w(to, m, x, y, bar, a.w_policy); };
   if (idx < kCLayers * kChunksPerLayer) {
     const int l = idx / kChunksPerLayer, j = idx - l * kChunksPerLayer;
     const CUtensorMap* lm = maps + kDecMapsPerLayer * l;
@@ -367,30 +390,30 @@ __device__ __noinline__ void issue_chunk(uint8_t* ring, unsigned long long* full
       for (int half = 0; half < 2; ++half)
 #pragma unroll
         for (int part = 0; part < 3; ++part)
-          tma_w(dst + half * kHalfStage + part * 4096, lm + 0 + half, j * 64, part * kCD + rank * kCHead, bar, a.w_policy);
+          box(dst + half * kHalfStage + part * 4096, lm + 0 + half, j * 64, part * kCD + rank * kCHead);
     } else if (j == 4 || j == 6) {  // sa_out / ca_out (head-packed, K = 32)
       mbar_expect_tx(bar, 4 * 8192);
       const CUtensorMap* m = lm + (j == 4 ? 2 : 6);
 #pragma unroll
       for (int half = 0; half < 2; ++half)
 #pragma unroll
-        for (int t = 0; t < 2; ++t) tma_w(dst + half * kHalfStage + t * 8192, m + half, 0, rank * kCD + t * 128, bar, a.w_policy);
+        for (int t = 0; t < 2; ++t) box(dst + half * kHalfStage + t * 8192, m + half, 0, rank * kCD + t * 128);
     } else if (j == 5) {  // ca_q
       mbar_expect_tx(bar, 8 * 4096);
 #pragma unroll
       for (int half = 0; half < 2; ++half)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tma_w(dst + half * kHalfStage + c * 4096, lm + 4 + half, c * 64, rank * kCHead, bar, a.w_policy);
+        for (int c = 0; c < 4; ++c) box(dst + half * kHalfStage + c * 4096, lm + 4 + half, c * 64, rank * kCHead);
     } else if (j < 15) {  // FF1: hidden units [256 rank + 128 t, +128)
       const int t = (j - 7) >> 2, c = (j - 7) & 3;
       mbar_expect_tx(bar, 2 * kHalfStage);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) tma_w(dst + half * kHalfStage, lm + 8 + half, c * 64, rank * kCD + t * 128, bar, a.w_policy);
+      for (int half = 0; half < 2; ++half) box(dst + half * kHalfStage, lm + 8 + half, c * 64, rank * kCD + t * 128);
     } else {  // FF2: outputs [128 t, +128), this CTA's K slice
       const int t = (j - 15) >> 2, c = (j - 15) & 3;
       mbar_expect_tx(bar, 2 * kHalfStage);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) tma_w(dst + half * kHalfStage, lm + 10 + half, rank * kCD + c * 64, t * 128, bar, a.w_policy);
+      for (int half = 0; half < 2; ++half) box(dst + half * kHalfStage, lm + 10 + half, rank * kCD + c * 64, t * 128);
     }
   } else {  // classifier
     const int jj = idx - kCLayers * kChunksPerLayer;
@@ -398,7 +421,7 @@ __device__ __noinline__ void issue_chunk(uint8_t* ring, unsigned long long* full
     mbar_expect_tx(bar, 2 * kHalfStage);
 #pragma unroll
     for (int half = 0; half < 2; ++half)
-      tma_w(dst + half * kHalfStage, maps + kCLayers * kDecMapsPerLayer + half, c * 64, v0 + rd * kClsRound + t * 128, bar, a.w_policy);
+      box(dst + half * kHalfStage, maps + kCLayers * kDecMapsPerLayer + half, c * 64, v0 + rd * kClsRound + t * 128);
   }
 }
 
@@ -437,7 +460,13 @@ __device__ __forceinline__ void tc_gemm(CSmem<NR>& S, const ClusterArgs& a, Pipe
     for (int i = 0; i < n_chunks; ++i) {
       const uint32_t u = pp.use + (uint32_t)i;
       const int s = (int)(u % kStages);
-      mbar_wait(smem_addr(&S.full[s]), (u / kStages) & 1u);
+      if (a.trace != nullptr && blockIdx.x == 0) {
+        const long long c0 = clock64();
+        mbar_wait(smem_addr(&S.full[s]), (u / kStages) & 1u);
+        if (lane == 0) S.tr_wait_full += (unsigned long long)(clock64() - c0);
+      } else {
+        mbar_wait(smem_addr(&S.full[s]), (u / kStages) & 1u);
+      }
       tcgen05_fence_after();
       if (elect_one()) {
         const uint32_t st = smem_addr(&S.ring[s][0]);
@@ -685,15 +714,15 @@ __device__ __noinline__ void decode_layer(CSmem<NR>& S, const ClusterArgs& a, Pi
       s0[rr] = &S.src[cur][r][0];
       if (valid[rr]) {  // the new position goes to this head's slice of the global cache (read back in later steps only)
         const int64_t o = ((int64_t)(grow0 + r) * max_len + pos) * kCD + rank * kCHead + lane;
-        kc[o] = kvn[rr][lane];
-        vc[o] = kvn[rr][kCHead + lane];
+        stg_f32_pol(kc + o, kvn[rr][lane], a.kv_policy);
+        stg_f32_pol(vc + o, kvn[rr][kCHead + lane], a.kv_policy);
       }
     }
     auto kp = [&](int rr, int j) { return kc + ((int64_t)(grow0 + s0[rr][j]) * max_len + j) * kCD + rank * kCHead; };
     auto vp = [&](int rr, int j) { return vc + ((int64_t)(grow0 + s0[rr][j]) * max_len + j) * kCD + rank * kCHead; };
     if (valid[0]) {  // warp-uniform (rows of a warp: r, r + 16)
-      if (pos <= 32) attend<NR, NRW, 1, false>(qq, nn, valid, kp, vp, kvn, true, S.opa, orow, lane);
-      else attend<NR, NRW, 2, false>(qq, nn, valid, kp, vp, kvn, true, S.opa, orow, lane);
+      if (pos <= 32) attend<NR, NRW, 1, false>(qq, nn, valid, kp, vp, kvn, true, S.opa, orow, lane, a.kv_policy);
+      else attend<NR, NRW, 2, false>(qq, nn, valid, kp, vp, kvn, true, S.opa, orow, lane, a.kv_policy);
     }
   }
   CL_TR(1);
@@ -734,9 +763,9 @@ __device__ __noinline__ void decode_layer(CSmem<NR>& S, const ClusterArgs& a, Pi
     auto kp = [&](int rr, int) { return kt + (int64_t)c0[rr] * kCLayers * kCD * tpad; };
     auto vp = [&](int rr, int j) { return ck + ((int64_t)c0[rr] * tp + j) * kv_stride + kCD; };
     if (valid[0]) {
-      if (tp <= 32) attend<NR, NRW, 1, true>(qq, nn, valid, kp, vp, kvn, false, S.opa, orow, lane, tpad);
-      else if (tp <= 64) attend<NR, NRW, 2, true>(qq, nn, valid, kp, vp, kvn, false, S.opa, orow, lane, tpad);
-      else attend<NR, NRW, 4, true>(qq, nn, valid, kp, vp, kvn, false, S.opa, orow, lane, tpad);
+      if (tp <= 32) attend<NR, NRW, 1, true>(qq, nn, valid, kp, vp, kvn, false, S.opa, orow, lane, a.kv_policy, tpad);
+      else if (tp <= 64) attend<NR, NRW, 2, true>(qq, nn, valid, kp, vp, kvn, false, S.opa, orow, lane, a.kv_policy, tpad);
+      else attend<NR, NRW, 4, true>(qq, nn, valid, kp, vp, kvn, false, S.opa, orow, lane, a.kv_policy, tpad);
     }
   }
   CL_TR(5);
@@ -1074,6 +1103,7 @@ decoder_cluster_kernel(const __grid_constant__ ClusterArgs a, int clips_per_grou
   // debug trace (CNB_DEC_TRACE): thread 0 of the first CTA accumulates the time between phase marks
   const bool tr_on = a.trace != nullptr && blockIdx.x == 0 && tid == 0;
   const long long tr_clk0 = clock64();
+  if (tid == 0) S.tr_wait_full = 0ull;
   if (tr_on) S.tr_last = cl_global_ns();
   const unsigned long long tr_ns0 = tr_on ? S.tr_last : 0ull;
   cl.sync();  // every CTA's mbarriers are initialised before any peer pushes data at them
@@ -1140,6 +1170,7 @@ decoder_cluster_kernel(const __grid_constant__ ClusterArgs a, int clips_per_grou
     for (int i = 0; i < 18; ++i) a.trace[i] = S.tr_acc[i];
     a.trace[18] = (unsigned long long)(clock64() - tr_clk0);  // SM cycles / elapsed ns = the clock this SM really ran at
     a.trace[19] = cl_global_ns() - tr_ns0;
+    a.trace[20] = S.tr_wait_full;
   }
   if (rank == 0 && tid == 0 && steps_max > 0) atomicMax(&a.bs.done[1], steps_max);
   tcgen05_fence_before();

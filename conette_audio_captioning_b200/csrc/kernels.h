@@ -166,6 +166,7 @@ struct ClusterArgs {
   float* tap;                // optional (tests): raw logits of every step, (max_len, rows, vocab)
   unsigned long long* trace; // optional (debug): phase times of the first CTA
   unsigned long long w_policy; // L2 eviction policy of the weight-ring loads (kL2Evict*; 0 = no hint)
+  unsigned long long kv_policy; // ... of the attention data (K/V caches, cross-attention K/V): always a valid policy
   int rows, beam, tp, max_len, vocab, min_len, batch;
   int compact;               // 1 = prefer few, fat clusters (32 rows each): the decode shares the GPU with the next encoder
 };

@@ -19,6 +19,11 @@ sd = synth.make_state_dict(seed=1234, n_words=4000)
 V = sd["model.decoder.classifier.weight"].shape[0]
 forbid = sd["model.forbid_rep_mask"].cuda().to(torch.uint8)
 eng = Engine(sd, V, precision="fast", decoder=a.decoder)
+if os.environ.get("DUMMY_MB"):  # experiment: shift the addresses of the workspaces the first decode allocates
+    import ctypes
+    _rt = ctypes.CDLL("libcudart.so.12")
+    _p = ctypes.c_void_p()
+    _rt.cudaMalloc(ctypes.byref(_p), ctypes.c_size_t(int(os.environ["DUMMY_MB"]) << 20))
 b = a.batch
 fe = torch.randn(b, 31, 768, device="cuda")
 bos = sd["model.task_id_to_token_id"][torch.zeros(b, dtype=torch.long)].cuda()
