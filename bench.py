@@ -613,7 +613,11 @@ def run_ours(args, rank, world, local_rank):
             "l2_to_smem_gbs": n_groups * dbytes / (dec_ms * 1e-3) / 1e9,
             "note": "one launch; latency-bound chain of ~45 dependent phases per step (6 layers x {4 tensor-core GEMM phases, 2 attention "
                     "phases, 3 reduce-scatter + all-gather + LayerNorm exchanges} + classifier rounds + beam merge) on 16-row operands, "
-                    "fp16 hi/lo split MMAs (fp32-level accuracy); reported against the weight bytes one step has to stream"}
+                    "fp16 hi/lo split MMAs (fp32-level accuracy); reported against the weight bytes one step has to stream.  "
+                    "`traffic` exceeds that figure because the weight ring loads with L2 evict-first priority: the stream is "
+                    "fetched from DRAM about twice per step (0.4 TB/s) so that the latency-critical attention data stays in L2 "
+                    "(with the default policy 0.85 GB per launch, once per step, but the kernel is 6 % slower: "
+                    "profiles/r2_decoder_l2_policy.txt)"}
         work["decoder"] = ("hbm", dbytes)
     roofline = roofline_of(kernels, work, pk, b, n, vocab)
 
